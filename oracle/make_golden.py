@@ -37,7 +37,7 @@ MODEL_CASES = dict(
 
 
 def _np(t):
-    return t.detach().cpu().numpy()
+    return t.detach().cpu().numpy().copy()   # copy: parameters are mutated in place later
 
 
 def build_learner(ref, case, seed, **extra):
