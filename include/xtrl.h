@@ -1,0 +1,240 @@
+/* xtrl.h -- C ABI of libxtrl.so: the B200 (sm_100a) rollout-and-learn hot path that stands in for
+ * the arithmetic of tinycrops/x-transformers-rl (citations: paths relative to the reference tree).
+ *
+ * Contract
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name says `host`; the
+ *     library never allocates, frees or retains a pointer past the call.
+ *   - every entry point is asynchronous on the caller's stream (`stream` is a cudaStream_t passed
+ *     as void*), never synchronises, and keeps no mutable global state beyond one-time
+ *     cudaFuncSetAttribute calls.
+ *   - return value: 0 = ok, negative = error (XTRL_E_*); text via xtrl_last_error() (thread-local).
+ *   - an unsupported configuration is an ERROR, never a fallback: there is no CPU path in here.
+ */
+#ifndef XTRL_H
+#define XTRL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XTRL_ABI_VERSION 1
+
+#define XTRL_OK            0
+#define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
+#define XTRL_E_UNSUPPORTED -2  /* configuration outside what the kernels are built for        */
+#define XTRL_E_CUDA       -3   /* a CUDA runtime call failed (message holds cudaGetErrorString) */
+
+int         xtrl_abi_version(void);
+const char *xtrl_last_error(void);
+/* compute capability of the current device as major*10+minor, or a negative error.           */
+int         xtrl_device_sm(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) world-model / actor-critic rollout step
+ *     replaces Learner.forward's state_to_pred_action_and_value closure + dist.sample/log_prob
+ *     (x_transformers_rl/x_transformers_rl.py:1250-1289): RSNorm.eval (:588-594) ->
+ *     WorldModelActorCritic.forward (:479-559) with the x-transformers Decoder and its KV cache
+ *     (call site :721-734, :505-512) -> Discrete (:197-222) -> HL-Gauss decode (:843).
+ *     One call advances EVERY env of the batch by one timestep.
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct xtrl_model_desc {
+    int32_t state_dim;        /* S                                                            */
+    int32_t num_actions;      /* A (discrete)                                                 */
+    int32_t dim;              /* D, Agent hidden_dim (:666); kernels are built for 48         */
+    int32_t heads;            /* H                                                            */
+    int32_t dim_head;         /* kernels are built for 16                                     */
+    int32_t depth;            /* L                                                            */
+    int32_t num_bins;         /* K, critic_pred_num_bins (:665)                               */
+    int32_t dim_gene;         /* G, 0 = not evolutionary                                      */
+    int32_t gate_values;      /* world_model['attn_gate_values']                              */
+    int32_t value_residual;   /* world_model['add_value_residual']                            */
+    int32_t learned_mix;      /* world_model['learned_value_residual_mix']                    */
+    int32_t max_timesteps;    /* Tmax: KV-cache capacity per env                              */
+    int32_t rotary_true_pos;  /* 0 = reference behaviour (all rollout positions 0) */
+    int32_t kv_bf16;          /* 0 = fp32 KV cache, 1 = bf16 KV cache                         */
+    float   reward_min, reward_max;   /* HL-Gauss support (reward_range)                      */
+} xtrl_model_desc;
+
+/* offsets (in floats) of every tensor inside the packed fp32 weight blob the step kernel reads.
+ * The host packs a reference-style state_dict into this layout (weights are stored K-major,
+ * i.e. transposed nn.Linear.weight, so a warp reads consecutive output features).             */
+#define XTRL_MAX_DEPTH 16
+typedef struct xtrl_weight_layout {
+    int64_t total;                 /* blob length in floats                                   */
+    int32_t s_pad;                 /* S rounded up to a multiple of 4                         */
+    int32_t n_qkv;                 /* fused q|k|v|gate|mix output width (padded to even)      */
+    int32_t head_in;               /* 2D or 3D (evolutionary)                                 */
+    int64_t in_proj;               /* [s_pad][2D]: project_in (no bias) | to_state_embed      */
+    int64_t state_embed_bias;      /* [D]                                                     */
+    int64_t action_embed;          /* [A][D]                                                  */
+    int64_t reward_embed;          /* [D]                                                     */
+    int64_t latent_w;              /* [G][D] (evolutionary)                                   */
+    int64_t latent_b;              /* [D]                                                     */
+    int64_t final_gamma;           /* [D]                                                     */
+    int64_t head1_w;               /* [head_in][4D]: action_head.0 | critic_head.0            */
+    int64_t head1_b;               /* [4D]                                                    */
+    int64_t actor2_w;              /* [2D][A]                                                 */
+    int64_t actor2_b;              /* [A]                                                     */
+    int64_t critic2_w;             /* [2D][K]                                                 */
+    int64_t critic2_b;             /* [K]                                                     */
+    struct {
+        int64_t ln1_gamma;         /* [D]                                                     */
+        int64_t qkv_w;             /* [D][n_qkv]: to_q | to_k | to_v | to_v_gate | mix        */
+        int64_t qkv_b;             /* [n_qkv] (zeros for q,k,v)                               */
+        int64_t out_w;             /* [I][D]                                                  */
+        int64_t ln2_gamma;         /* [D]                                                     */
+        int64_t ff1_w;             /* [D][4D]                                                 */
+        int64_t ff1_b;             /* [4D]                                                    */
+        int64_t ff2_w;             /* [4D][D]                                                 */
+        int64_t ff2_b;             /* [D]                                                     */
+    } layer[XTRL_MAX_DEPTH];
+} xtrl_weight_layout;
+
+/* fills *out; HOST pointers.  Pure host arithmetic (usable without a GPU).                    */
+int xtrl_wm_weight_layout(const xtrl_model_desc *desc, xtrl_weight_layout *out);
+
+/* bytes of KV cache the caller must allocate for `num_envs` envs:
+ *   [2 (k,v)][L][num_envs][H][Tmax][dim_head] in fp32 or bf16.                                */
+int64_t xtrl_wm_kv_cache_bytes(const xtrl_model_desc *desc, int64_t num_envs);
+
+typedef struct xtrl_step_io {
+    /* inputs */
+    const float   *state;         /* [B][S] raw (un-normalised) observation                   */
+    const int32_t *prev_action;   /* [B], -1 = none (:1244)                                   */
+    const float   *prev_reward;   /* [B] raw previous reward (0 at t=0, :1246)                */
+    const int32_t *pos;           /* [B] number of tokens already cached for this env (its t) */
+    const float   *rs_mean;       /* [S+1] RSNorm running_mean                                */
+    const float   *rs_var;        /* [S+1] RSNorm running_variance                            */
+    const float   *genes;         /* [num_genes][G] un-normalised gene matrix, or NULL        */
+    const int32_t *gene_ids;      /* [B] or NULL                                              */
+    const float   *uniform;       /* [B] u in [0,1): inverse-CDF sampling; NULL =
+                                     do not sample (action_out untouched unless forced)      */
+    const int32_t *forced_action; /* [B] or NULL: evaluate log-prob of this action instead    */
+    float          reward_flag;   /* the per-forward reward-conditioning flag (:501-503)      */
+    /* outputs (any may be NULL) */
+    int32_t *action;              /* [B]                                                      */
+    float   *log_prob;            /* [B] log(clamp(p[a], eps, 1-eps))                         */
+    float   *value;               /* [B] HL-Gauss expectation of the critic logits            */
+    float   *raw_actions;         /* [B][A] actor logits                                      */
+    float   *value_logits;        /* [B][K] critic logits                                     */
+} xtrl_step_io;
+
+int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, void *kv_cache,
+                 const xtrl_step_io *io, int32_t num_envs, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) GAE / returns -- replaces calc_gae (x_transformers_rl.py:616-640), i.e. the seam the
+ *     reference itself exposes as AssocScan(reverse=True, use_accelerated=...) (:634-636).
+ *     returns[e,t] = gae[e,t] + values[e,t],  gae_t = delta_t + gamma*lam*m_t*gae_{t+1},
+ *     delta_t = r_t + gamma*v_{t+1}*m_t - v_t,  v_T = 0,  m = !is_boundary.
+ *     Element (e,t) of every array lives at  e*stride_e + t*stride_t  (in elements); either
+ *     episode-major (stride_t == 1, the reference's (E,T)) or time-major (stride_e == 1, the
+ *     rollout buffer's (T,B)).
+ * ---------------------------------------------------------------------------------------- */
+int xtrl_gae(const float *rewards, const float *values, const uint8_t *is_boundary,
+             float *returns, int32_t num_episodes, int32_t num_timesteps,
+             int64_t stride_e, int64_t stride_t, float gamma, float lam, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) fused PPO loss, forward + backward w.r.t. the head outputs -- replaces
+ *     compute_actor_loss (:413-444), compute_critic_loss (:446-477),
+ *     compute_autoregressive_loss (:398-404, with Continuous.mean_variance :232-241),
+ *     compute_done_loss (:406-411) and the assembly of Agent.learn (:939-978).
+ *     Rows are the b*T timesteps of one minibatch, row r = (episode r / T, step r % T).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct xtrl_loss_cfg {
+    int32_t num_actions, num_bins, state_dim;
+    float   reward_min, reward_max;
+    float   eps_clip, value_clip, entropy_weight;
+    float   actor_weight, critic_weight, autoreg_weight;
+    int32_t normalize_advantages;   /* 1 (reference default, :298)                            */
+    int32_t bf16_io;                /* 0: head outputs / grads fp32; 1: bf16 (math stays fp32) */
+} xtrl_loss_cfg;
+
+typedef struct xtrl_loss_io {
+    /* head outputs of the model, row-major (fp32, or bf16 when cfg.bf16_io) */
+    const void *raw_actions;        /* [N][A] actor logits                                    */
+    const void *value_logits;       /* [N][K] critic logits                                   */
+    const void *state_pred_raw;     /* [N][2(S+1)] to_pred output, (mean,logvar) interleaved; NULL = skip */
+    const void *done_logit;         /* [N] pre-sigmoid to_pred_done; NULL = skip              */
+    /* episode buffer (always fp32 / int) */
+    const int32_t *actions;         /* [N]                                                    */
+    const float   *old_log_probs;   /* [N]                                                    */
+    const float   *returns;         /* [N]                                                    */
+    const float   *old_values;      /* [N] scalar (HL-Gauss decode of the stored logits, :427) */
+    const float   *target;          /* [N][S+1] normalised (state||prev reward), :920-926     */
+    const uint8_t *dones;           /* [N] is_boundary                                        */
+    const int32_t *episode_lens;    /* [b]                                                    */
+    /* outputs */
+    void  *g_raw_actions;           /* [N][A]   d loss / d raw_actions                        */
+    void  *g_value_logits;          /* [N][K]                                                 */
+    void  *g_state_pred_raw;        /* [N][2(S+1)]                                            */
+    void  *g_done_logit;            /* [N]                                                    */
+    float *per_step;                /* [N][2] (actor, critic) per-timestep losses or NULL     */
+    float *scalars;                 /* [8]: total, actor_mean, critic_mean, autoreg_mean, done_mean,
+                                        n_masked, adv_mean, adv_var                           */
+    double *workspace;              /* xtrl_ppo_loss_workspace_bytes() bytes, any contents     */
+} xtrl_loss_io;
+
+int64_t xtrl_ppo_loss_workspace_bytes(void);
+int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_io *io,
+                          int32_t batch, int32_t num_timesteps, void *stream);
+
+/* HL-Gauss decode (hl_gauss(logits), :843/:427): out[n] = sum_k softmax(logits[n])_k * centre_k */
+int xtrl_hl_decode(const float *logits, float *out, int64_t n, int32_t num_bins,
+                   float reward_min, float reward_max, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) latent gene pool -- replaces LatentGenePool.evolve_ (evolution.py:76-184).  The three
+ *     random tensors the reference draws (evolution.py:113,133,173) are INPUTS.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct xtrl_pool_desc {
+    int32_t dim;                    /* G                                                      */
+    int32_t num_islands;            /* I                                                      */
+    int32_t num_genes_per_island;   /* g                                                      */
+    int32_t num_selected;           /* s                                                      */
+    int32_t tournament_size;        /* k                                                      */
+    int32_t num_elites;
+    int32_t migrate;                /* 1 = this call is a migration step (evolution.py:137-141) */
+    int32_t num_migrate;            /* rows moved when migrate (host validates the reference's
+                                       int/float quirk)                           */
+    float   mutation_std_dev;
+    float   temperature;            /* 1.5 (evolution.py:79)                                  */
+} xtrl_pool_desc;
+
+/* genes [I*g][G] updated IN PLACE; fitness [I*g]; noise_tourn [I][c][s]; noise_cross [I][c][G];
+ * noise_mut [I][g - (elites?1:0)][G]; selected_ids [I][s] (int64, as the reference returns);
+ * scratch: I*g*G floats.                                                                      */
+int xtrl_evolve(float *genes, const float *fitness, const float *noise_tourn,
+                const float *noise_cross, const float *noise_mut, int64_t *selected_ids,
+                float *scratch, const xtrl_pool_desc *desc, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) optimiser step over the flat fp32 parameter buffer -- replaces the python loops of
+ *     clip_grad_norm_ (:987) + AdoptAtan2.step (:749,:991) + the EMA post-step hook (:753).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct xtrl_opt_cfg {
+    float lr, init_lr, beta1, beta2, regen_rate, cautious_factor, a, b, max_grad_norm;
+    int32_t first_step;             /* 1: initialise v=g*g, param_init=p, no update (ADOPT)   */
+    float ema_mode;                 /* 0 none, 1 copy online->ema, 2 lerp with ema_decay      */
+    float ema_decay;
+    int32_t copy_ema_to_online;     /* update_model_with_ema_every hit                        */
+} xtrl_opt_cfg;
+
+/* params, grads, m, v, param_init, ema: [n] fp32; seg_offsets [num_tensors+1] (int64, device):
+ * the cautious mask is normalised per parameter tensor; workspace: 2 + num_tensors doubles.   */
+int64_t xtrl_opt_workspace_bytes(int32_t num_tensors);
+int xtrl_adopt_atan2_step(float *params, const float *grads, float *m, float *v, float *param_init,
+                          float *ema, const int64_t *seg_offsets, int32_t num_tensors, int64_t n,
+                          const xtrl_opt_cfg *cfg, double *workspace, float *grad_norm_out,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XTRL_H */

@@ -32,38 +32,55 @@ def _install_shims():
         sys.modules[name] = importlib.import_module(f'oracle.shims.{name}')
 
 
+_CACHE = {}
+
+
 def load():
-    """Returns the reference's `x_transformers_rl.x_transformers_rl` module (with `.evolution`
-    and `.distributed` reachable as `sys.modules['x_transformers_rl.evolution']` etc.)."""
+    """Returns the reference's `x_transformers_rl.x_transformers_rl` module.  The reference files import
+    each other as `x_transformers_rl.*`, so that name is bound to a synthetic parent package while
+    they execute and then RESTORED: the repo's own drop-in package of the same import name
+    (x_transformers_rl/ at the repo root) stays importable in the same process."""
     if not available():
         raise FileNotFoundError(f'reference tree not found under {REFERENCE_ROOT}')
-    full = f'{_PKG}.x_transformers_rl'
-    if full in sys.modules and getattr(sys.modules[full], '__xtrl_ref__', False):
-        return sys.modules[full]
+    if 'x_transformers_rl' in _CACHE:
+        return _CACHE['x_transformers_rl']
     _install_shims()
+    saved = {k: v for k, v in sys.modules.items() if k == _PKG or k.startswith(_PKG + '.')}
+    for k in saved:
+        del sys.modules[k]
     pkg_dir = os.path.join(REFERENCE_ROOT, _PKG)
     pkg = types.ModuleType(_PKG)
     pkg.__path__ = [pkg_dir]          # submodules resolve to the reference's own files
     pkg.__xtrl_ref__ = True
     sys.modules[_PKG] = pkg
-    mods = {}
-    for sub in ('distributed', 'evolution', 'x_transformers_rl'):
-        name = f'{_PKG}.{sub}'
-        spec = importlib.util.spec_from_file_location(name, os.path.join(pkg_dir, f'{sub}.py'))
-        mod = importlib.util.module_from_spec(spec)
-        mod.__xtrl_ref__ = True
-        sys.modules[name] = mod
-        sys.dont_write_bytecode, prev = True, sys.dont_write_bytecode   # /root/reference is read-only
-        try:
-            spec.loader.exec_module(mod)
-        finally:
-            sys.dont_write_bytecode = prev
-        setattr(pkg, sub, mod)
-        mods[sub] = mod
-    pkg.Learner, pkg.Agent = mods['x_transformers_rl'].Learner, mods['x_transformers_rl'].Agent
-    return mods['x_transformers_rl']
+    try:
+        for sub in ('distributed', 'evolution', 'x_transformers_rl'):
+            name = f'{_PKG}.{sub}'
+            spec = importlib.util.spec_from_file_location(name, os.path.join(pkg_dir, f'{sub}.py'))
+            mod = importlib.util.module_from_spec(spec)
+            mod.__xtrl_ref__ = True
+            sys.modules[name] = mod
+            sys.dont_write_bytecode, prev = True, sys.dont_write_bytecode   # /root/reference is read-only
+            try:
+                spec.loader.exec_module(mod)
+            finally:
+                sys.dont_write_bytecode = prev
+            setattr(pkg, sub, mod)
+            _CACHE[sub] = mod
+    finally:
+        for k in [k for k in sys.modules if k == _PKG or k.startswith(_PKG + '.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    pkg.Learner, pkg.Agent = _CACHE['x_transformers_rl'].Learner, _CACHE['x_transformers_rl'].Agent
+    _CACHE['package'] = pkg
+    return _CACHE['x_transformers_rl']
 
 
 def evolution():
     load()
-    return sys.modules[f'{_PKG}.evolution']
+    return _CACHE['evolution']
+
+
+def distributed():
+    load()
+    return _CACHE['distributed']

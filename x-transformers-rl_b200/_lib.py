@@ -1,0 +1,133 @@
+"""ctypes binding of libxtrl.so (include/xtrl.h).  The library is the ONLY compute backend: if it is
+missing or does not load, importing the ops fails loudly -- there is no CPU / eager fallback.
+
+Structures below mirror include/xtrl.h field for field; `tests/test_abi.py` checks every
+declared symbol is exported and that sizes agree with what the C side reports.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+XTRL_ABI_VERSION = 1
+XTRL_MAX_DEPTH = 16
+
+c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [(n, c_i32) for n in (
+        'state_dim', 'num_actions', 'dim', 'heads', 'dim_head', 'depth', 'num_bins', 'dim_gene',
+        'gate_values', 'value_residual', 'learned_mix', 'max_timesteps', 'rotary_true_pos', 'kv_bf16')] + [
+        ('reward_min', c_f32), ('reward_max', c_f32)]
+
+
+class _LayerLayout(C.Structure):
+    _fields_ = [(n, c_i64) for n in ('ln1_gamma', 'qkv_w', 'qkv_b', 'out_w', 'ln2_gamma',
+                                     'ff1_w', 'ff1_b', 'ff2_w', 'ff2_b')]
+
+
+class WeightLayout(C.Structure):
+    _fields_ = [('total', c_i64), ('s_pad', c_i32), ('n_qkv', c_i32), ('head_in', c_i32)] + [
+        (n, c_i64) for n in ('in_proj', 'state_embed_bias', 'action_embed', 'reward_embed', 'latent_w',
+                             'latent_b', 'final_gamma', 'head1_w', 'head1_b', 'actor2_w', 'actor2_b',
+                             'critic2_w', 'critic2_b')] + [('layer', _LayerLayout * XTRL_MAX_DEPTH)]
+
+
+class StepIO(C.Structure):
+    _fields_ = [(n, c_vp) for n in ('state', 'prev_action', 'prev_reward', 'pos', 'rs_mean', 'rs_var',
+                                    'genes', 'gene_ids', 'uniform', 'forced_action')] + [
+        ('reward_flag', c_f32)] + [(n, c_vp) for n in ('action', 'log_prob', 'value', 'raw_actions', 'value_logits')]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [('num_actions', c_i32), ('num_bins', c_i32), ('state_dim', c_i32),
+                ('reward_min', c_f32), ('reward_max', c_f32),
+                ('eps_clip', c_f32), ('value_clip', c_f32), ('entropy_weight', c_f32),
+                ('actor_weight', c_f32), ('critic_weight', c_f32), ('autoreg_weight', c_f32),
+                ('normalize_advantages', c_i32), ('bf16_io', c_i32)]
+
+
+class LossIO(C.Structure):
+    _fields_ = [(n, c_vp) for n in (
+        'raw_actions', 'value_logits', 'state_pred_raw', 'done_logit',
+        'actions', 'old_log_probs', 'returns', 'old_values', 'target', 'dones', 'episode_lens',
+        'g_raw_actions', 'g_value_logits', 'g_state_pred_raw', 'g_done_logit', 'per_step', 'scalars', 'workspace')]
+
+
+class PoolDesc(C.Structure):
+    _fields_ = [(n, c_i32) for n in ('dim', 'num_islands', 'num_genes_per_island', 'num_selected',
+                                     'tournament_size', 'num_elites', 'migrate', 'num_migrate')] + [
+        ('mutation_std_dev', c_f32), ('temperature', c_f32)]
+
+
+class OptCfg(C.Structure):
+    _fields_ = [(n, c_f32) for n in ('lr', 'init_lr', 'beta1', 'beta2', 'regen_rate', 'cautious_factor',
+                                     'a', 'b', 'max_grad_norm')] + [
+        ('first_step', c_i32), ('ema_mode', c_f32), ('ema_decay', c_f32), ('copy_ema_to_online', c_i32)]
+
+
+# every symbol include/xtrl.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    'xtrl_abi_version': (c_i32, []),
+    'xtrl_last_error': (C.c_char_p, []),
+    'xtrl_device_sm': (c_i32, []),
+    'xtrl_wm_weight_layout': (c_i32, [C.POINTER(ModelDesc), C.POINTER(WeightLayout)]),
+    'xtrl_wm_kv_cache_bytes': (c_i64, [C.POINTER(ModelDesc), c_i64]),
+    'xtrl_wm_step': (c_i32, [C.POINTER(ModelDesc), c_vp, c_vp, C.POINTER(StepIO), c_i32, c_vp]),
+    'xtrl_gae': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_i64, c_f32, c_f32, c_vp]),
+    'xtrl_ppo_loss_workspace_bytes': (c_i64, []),
+    'xtrl_ppo_loss_fwd_bwd': (c_i32, [C.POINTER(LossCfg), C.POINTER(LossIO), c_i32, c_i32, c_vp]),
+    'xtrl_hl_decode': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_f32, c_vp]),
+    'xtrl_evolve': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(PoolDesc), c_vp]),
+    'xtrl_opt_workspace_bytes': (c_i64, [c_i32]),
+    'xtrl_adopt_atan2_step': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64,
+                                      C.POINTER(OptCfg), c_vp, c_vp, c_vp]),
+}
+
+
+class XtrlError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen libxtrl.so (building it first if the in-tree copy is absent or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    import torch  # noqa: F401  (loads libcudart.so.12 into the process before our dlopen)
+    path = _build.LIB_PATH
+    if not _build.is_fresh():
+        try:
+            path = _build.build()
+        except Exception as exc:
+            if not os.path.exists(path):
+                raise XtrlError(f'libxtrl.so is missing and could not be built ({exc}); '
+                                'this package has no CPU fallback') from exc
+    try:
+        lib = C.CDLL(path)
+    except OSError as exc:
+        raise XtrlError(f'cannot load {path}: {exc}; this package has no CPU fallback') from exc
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError = ABI mismatch, let it surface
+        fn.restype, fn.argtypes = res, args
+    got = lib.xtrl_abi_version()
+    if got != XTRL_ABI_VERSION:
+        raise XtrlError(f'libxtrl.so ABI {got} != binding {XTRL_ABI_VERSION}')
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().xtrl_last_error()
+        raise XtrlError(f'{what} failed ({rc}): {msg.decode() if msg else "?"}')

@@ -1,0 +1,407 @@
+// ppo_loss.cu -- fused PPO clipped-surrogate + entropy + HL-Gauss clipped value loss + world-model
+// Gaussian NLL + done BCE: forward values AND gradients w.r.t. every head output, one pass.
+//
+// Replaces, on the rows of one minibatch (x_transformers_rl/x_transformers_rl.py):
+//   compute_actor_loss :413-444 (Discrete :197-222, normalize :103-112),
+//   compute_critic_loss :446-477 (HLGaussLoss; per-element, U3),
+//   compute_autoregressive_loss :398-404 (+ Continuous.mean_variance :232-241, softclamp :124),
+//   compute_done_loss :406-411, and the assembly + backward of Agent.learn :939-983.
+//
+// HBM-bound: per timestep 8A+8K+21 B (+20(S+1)+9 B for the world-model terms), each byte touched
+// once.  One warp per timestep row: the K critic logits and their gradients move as coalesced
+// 128 B rows (lane <-> bin, stride 32), bin-edge erf values are shared between neighbouring lanes
+// by shuffle, and erf is only evaluated where fp32 erf is not saturated.
+// Launch sequence (all on the caller's stream): memset workspace -> stats (masked advantage
+// mean / unbiased variance, counts; fp64 accumulators) -> main -> finalize (8 scalars).
+#include "common.cuh"
+#include <math.h>
+
+namespace xtrl {
+
+enum { WS_ADV_SUM = 0, WS_ADV_SQ, WS_N_MASK, WS_N_WM, WS_AC_MASKED, WS_ACTOR_ALL, WS_CRITIC_ALL,
+       WS_NLL, WS_DONE, WS_COUNT };
+
+template <typename T> __device__ __forceinline__ float ld_as_float(const T *p);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float *p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    return __bfloat162float(*p);
+}
+template <typename T> __device__ __forceinline__ void st_from_float(T *p, float v);
+template <> __device__ __forceinline__ void st_from_float<float>(float *p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16 *p, float v) {
+    *p = __float2bfloat16_rn(v);
+}
+
+struct HlSupport {           // torch.linspace(lo, hi, K+1) in fp32 (two-sided formula)
+    float lo, hi, step, denom;   // denom = sqrt(2) * sigma, sigma = 2 * (edge1 - edge0)
+    int K;
+    __device__ __forceinline__ float edge(int i) const {
+        return (i < (K + 1) / 2) ? lo + step * (float)i : hi - step * (float)(K - i);
+    }
+    __device__ __forceinline__ float centre(int k) const { return (edge(k) + edge(k + 1)) * 0.5f; }
+};
+
+static HlSupport make_support(float lo, float hi, int K) {
+    HlSupport s;
+    s.lo = lo; s.hi = hi; s.K = K;
+    s.step = (hi - lo) / (float)K;
+    const float e1 = (1 < (K + 1) / 2) ? lo + s.step * 1.f : hi - s.step * (float)(K - 1);
+    const double sigma = 2.0 * (double)(e1 - lo);
+    s.denom = (float)(sqrt(2.0) * sigma);
+    return s;
+}
+
+// ---- stats: masked sum / sum of squares of the advantages, counts --------------------------
+__global__ void __launch_bounds__(256)
+ppo_stats_kernel(const float *__restrict__ returns, const float *__restrict__ old_values,
+                 const int32_t *__restrict__ lens, int b, int T, double *__restrict__ ws) {
+    double s = 0., q = 0., n = 0., nw = 0.;
+    const int64_t N = (int64_t)b * T;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < N; r += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(r / T), t = (int)(r - (int64_t)e * T);
+        if (t < __ldg(lens + e)) {
+            const double a = (double)(__ldg(returns + r) - __ldg(old_values + r));
+            s += a; q += a * a; n += 1.;
+            if (t < T - 1) nw += 1.;
+        }
+    }
+    __shared__ double sh[4][8];
+    s = warp_sum(s); q = warp_sum(q); n = warp_sum(n); nw = warp_sum(nw);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][w] = s; sh[1][w] = q; sh[2][w] = n; sh[3][w] = nw; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double a = 0.;
+        for (int i = 0; i < 8; ++i) a += sh[threadIdx.x][i];
+        const int slot = threadIdx.x == 0 ? WS_ADV_SUM : threadIdx.x == 1 ? WS_ADV_SQ
+                       : threadIdx.x == 2 ? WS_N_MASK : WS_N_WM;
+        atomicAdd(ws + slot, a);
+    }
+}
+
+// ---- main ----------------------------------------------------------------------------------
+struct LossArgs {
+    xtrl_loss_cfg cfg;
+    xtrl_loss_io io;
+    HlSupport sup;
+    int b, T;
+};
+
+constexpr int kLossWarps = 8;
+
+template <typename TIO, int KJ>
+__global__ void __launch_bounds__(kLossWarps * 32)
+ppo_loss_kernel(const LossArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int A = a.cfg.num_actions, K = a.cfg.num_bins, S1 = a.cfg.state_dim + 1, T = a.T;
+    const int64_t N = (int64_t)a.b * T;
+    const double *ws = a.io.workspace;
+
+    // masked advantage statistics (normalize(), :103-112)
+    const double n_mask = ws[WS_N_MASK], n_wm = ws[WS_N_WM];
+    float adv_mean = 0.f, adv_inv_std = 1.f;
+    if (a.cfg.normalize_advantages && n_mask > 0.) {
+        const double mean = ws[WS_ADV_SUM] / n_mask;
+        const double var = (ws[WS_ADV_SQ] - n_mask * mean * mean) / (n_mask - 1.);   // unbiased
+        adv_mean = (float)mean;
+        adv_inv_std = 1.f / sqrtf(fmaxf((float)var, 1e-5f));
+    }
+    const float g_ac = n_mask > 0. ? (float)(1. / n_mask) : 0.f;                      // d mean / d elem
+    const float g_done = g_ac * a.cfg.autoreg_weight;
+    const float g_wm = n_wm > 0. ? a.cfg.autoreg_weight * (float)(1. / (n_wm * S1)) : 0.f;
+    const float feps = 1.1920928955078125e-07f;                                      // finfo(fp32).eps
+
+    const TIO *raw_actions = (const TIO *)a.io.raw_actions;
+    const TIO *value_logits = (const TIO *)a.io.value_logits;
+    const TIO *sp_raw = (const TIO *)a.io.state_pred_raw;
+    const TIO *done_logit = (const TIO *)a.io.done_logit;
+    TIO *g_ra = (TIO *)a.io.g_raw_actions;
+    TIO *g_vl = (TIO *)a.io.g_value_logits;
+    TIO *g_sp = (TIO *)a.io.g_state_pred_raw;
+    TIO *g_dl = (TIO *)a.io.g_done_logit;
+
+    float acc_ac = 0.f, acc_actor = 0.f, acc_critic = 0.f, acc_nll = 0.f, acc_done = 0.f;
+
+    for (int64_t r = (int64_t)blockIdx.x * kLossWarps + warp; r < N; r += (int64_t)gridDim.x * kLossWarps) {
+        const int e = (int)(r / T), t = (int)(r - (int64_t)e * T);
+        const bool masked = t < __ldg(a.io.episode_lens + e);
+        const float ret = __ldg(a.io.returns + r);
+        const float v_old = __ldg(a.io.old_values + r);
+
+        // ---------------- critic: HL-Gauss CE against returns and clamped returns ------------
+        float lg[KJ], ex[KJ];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) {
+            const int k = j * 32 + lane;
+            lg[j] = k < K ? ld_as_float(value_logits + r * K + k) : -INFINITY;
+            mx = fmaxf(mx, lg[j]);
+        }
+        mx = warp_max(mx);
+        float se = 0.f, sc = 0.f;
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) {
+            const int k = j * 32 + lane;
+            ex[j] = k < K ? expf(lg[j] - mx) : 0.f;
+            se += ex[j];
+            sc += k < K ? ex[j] * a.sup.centre(k) : 0.f;
+        }
+        se = warp_sum(se); sc = warp_sum(sc);
+        const float v_new = sc / se;                       // hl_gauss(values), :455
+        const float lse = logf(se) + mx;
+
+        const float y0 = fminf(fmaxf(ret, a.sup.lo), a.sup.hi);                                     // clamp_to_range
+        const float y1 = fminf(fmaxf(fminf(fmaxf(ret, -a.cfg.value_clip), a.cfg.value_clip), a.sup.lo), a.sup.hi);  // :459
+        // cdf at the lower edge of each of my bins; the upper edge comes from the next lane
+        float c0[KJ], c1[KJ];
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) {
+            const int k = j * 32 + lane;
+            const float ed = a.sup.edge(min(k, K));
+            c0[j] = erff((ed - y0) / a.sup.denom);
+            c1[j] = erff((ed - y1) / a.sup.denom);
+        }
+        const float z0 = fmaxf(erff((a.sup.hi - y0) / a.sup.denom) - erff((a.sup.lo - y0) / a.sup.denom), 1e-10f);
+        const float z1 = fmaxf(erff((a.sup.hi - y1) / a.sup.denom) - erff((a.sup.lo - y1) / a.sup.denom), 1e-10f);
+        float p0[KJ], p1[KJ];
+        float ce0 = 0.f, ce1 = 0.f, sp0 = 0.f, sp1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) {
+            const int k = j * 32 + lane;
+            // upper edge k+1: lane+1 of this j, or lane 0 of j+1
+            float u0 = __shfl_down_sync(0xffffffffu, c0[j], 1);
+            float u1 = __shfl_down_sync(0xffffffffu, c1[j], 1);
+            const float n0 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c0[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
+            const float n1 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c1[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
+            if (lane == 31) { u0 = n0; u1 = n1; }
+            if (k + 1 == K) {                                  // last edge is `hi` exactly
+                u0 = erff((a.sup.edge(K) - y0) / a.sup.denom);
+                u1 = erff((a.sup.edge(K) - y1) / a.sup.denom);
+            }
+            p0[j] = k < K ? (u0 - c0[j]) / z0 : 0.f;
+            p1[j] = k < K ? (u1 - c1[j]) / z1 : 0.f;
+            const float lsm = k < K ? lg[j] - lse : 0.f;
+            ce0 -= p0[j] * lsm; ce1 -= p1[j] * lsm;
+            sp0 += p0[j]; sp1 += p1[j];
+        }
+        ce0 = warp_sum(ce0); ce1 = warp_sum(ce1); sp0 = warp_sum(sp0); sp1 = warp_sum(sp1);
+        const float lo_old = v_old - a.cfg.value_clip, hi_old = v_old + a.cfg.value_clip;
+        const bool zero = (ret < v_new && v_new < lo_old) || (hi_old < v_new && v_new < ret);   // :470-472
+        const float critic = zero ? 0.f : fminf(ce0, ce1);
+        if (g_vl) {
+            // d min(ce0, ce1): the smaller one; an exact tie splits evenly (torch minimum)
+            const float w0 = zero ? 0.f : (ce0 < ce1 ? 1.f : (ce0 > ce1 ? 0.f : 0.5f));
+            const float w1 = zero ? 0.f : 1.f - w0;
+            const float gc = masked ? g_ac * a.cfg.critic_weight : 0.f;
+            const float inv_se = 1.f / se;
+#pragma unroll
+            for (int j = 0; j < KJ; ++j) {
+                const int k = j * 32 + lane;
+                if (k < K) {
+                    const float sm = ex[j] * inv_se;
+                    const float g = gc * (w0 * (sm * sp0 - p0[j]) + w1 * (sm * sp1 - p1[j]));
+                    st_from_float(g_vl + r * K + k, g);
+                }
+            }
+        }
+
+        // ---------------- actor: clipped surrogate + entropy (lane i <-> action i) ------------
+        const int act = __ldg(a.io.actions + r);
+        const float la = lane < A ? ld_as_float(raw_actions + r * A + lane) : -INFINITY;
+        const float amx = warp_max(la);
+        const float q = lane < A ? expf(la - amx) : 0.f;
+        const float qs = warp_sum(q);
+        const float sm = q / qs;                              // softmax
+        const float ssum = warp_sum(sm);                      // Categorical renormalises probs
+        const float p = sm / ssum;
+        const bool inside = p >= feps && p <= 1.f - feps;
+        const float L = lane < A ? logf(fminf(fmaxf(p, feps), 1.f - feps)) : 0.f;
+        const float ent = -warp_sum(p * L);
+        const float logp = __shfl_sync(0xffffffffu, L, act & 31);
+        const float ratio = expf(logp - __ldg(a.io.old_log_probs + r));
+        const float clipped = fminf(fmaxf(ratio, 1.f - a.cfg.eps_clip), 1.f + a.cfg.eps_clip);
+        const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
+        const float surr1 = ratio * adv, surr2 = clipped * adv;
+        const float actor = -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
+        if (g_ra) {
+            const bool in_range = ratio >= 1.f - a.cfg.eps_clip && ratio <= 1.f + a.cfg.eps_clip;
+            const float dmin = in_range ? adv : (surr1 < surr2 ? adv : 0.f);
+            const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
+            const float g_logp = -ga * dmin * ratio;
+            // d/dp_i of  -beta*ent + logp-term
+            float gp = 0.f;
+            if (lane < A) {
+                gp = ga * a.cfg.entropy_weight * (L + (inside ? 1.f : 0.f));
+                if (lane == act && inside) gp += g_logp / p;
+            }
+            // p = sm / sum(sm);  sm = softmax(logits)
+            const float dot_p = warp_sum(gp * p);
+            const float gq = (gp - dot_p) / ssum;
+            const float dot_q = warp_sum(lane < A ? gq * sm : 0.f);
+            if (lane < A) st_from_float(g_ra + r * A + lane, sm * (gq - dot_q));
+        }
+
+        // ---------------- world model: Gaussian NLL of next (state || reward), done BCE -------
+        float nll = 0.f, bce = 0.f;
+        if (sp_raw) {
+            const bool valid = masked && t < T - 1;
+            if (lane < S1) {
+                const float mean = ld_as_float(sp_raw + (r * S1 + lane) * 2);
+                const float lv = ld_as_float(sp_raw + (r * S1 + lane) * 2 + 1);
+                const float th = tanhf(lv / 3.f);
+                const float var = fmaxf(expf(th * 3.f), 1e-6f);
+                float gm = 0.f, gl = 0.f;
+                if (valid) {
+                    const float d = mean - __ldg(a.io.target + (r + 1) * S1 + lane);
+                    nll = 0.5f * (logf(var) + d * d / var);
+                    gm = g_wm * d / var;
+                    gl = g_wm * 0.5f * (1.f / var - d * d / (var * var)) * var * (1.f - th * th);
+                }
+                if (g_sp) {
+                    st_from_float(g_sp + (r * S1 + lane) * 2, gm);
+                    st_from_float(g_sp + (r * S1 + lane) * 2 + 1, gl);
+                }
+            }
+            nll = warp_sum(nll);
+        }
+        if (done_logit && lane == 0) {
+            const float z = ld_as_float(done_logit + r);
+            const float pd = 1.f / (1.f + expf(-z));
+            const float y = __ldg(a.io.dones + r) ? 1.f : 0.f;
+            const float l1 = logf(pd), l0 = logf(1.f - pd);
+            bce = -(y * fmaxf(l1, -100.f) + (1.f - y) * fmaxf(l0, -100.f));
+            float g = 0.f;
+            if (masked) {
+                const float dp = -((l1 > -100.f ? y / pd : 0.f) - (l0 > -100.f ? (1.f - y) / (1.f - pd) : 0.f));
+                g = g_done * dp * pd * (1.f - pd);
+                if (!isfinite(g)) g = 0.f;
+            }
+            if (g_dl) st_from_float(g_dl + r, g);
+        }
+
+        if (lane == 0) {
+            if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
+            acc_actor += actor; acc_critic += critic;
+            if (masked) {
+                acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
+                acc_done += bce;
+            }
+            acc_nll += nll;                                    // already zero where invalid
+        }
+    }
+
+    __shared__ float sh[5][kLossWarps];
+    if (lane == 0) { sh[0][warp] = acc_ac; sh[1][warp] = acc_actor; sh[2][warp] = acc_critic; sh[3][warp] = acc_nll; sh[4][warp] = acc_done; }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0.;
+        for (int i = 0; i < kLossWarps; ++i) s += (double)sh[threadIdx.x][i];
+        atomicAdd(a.io.workspace + WS_AC_MASKED + threadIdx.x, s);
+    }
+}
+
+__global__ void ppo_finalize_kernel(const double *__restrict__ ws, float *__restrict__ scalars,
+                                    int64_t N, int S1, float w_ar, int normalize) {
+    const double n = ws[WS_N_MASK], nw = ws[WS_N_WM] * S1;
+    const double ac = n > 0 ? ws[WS_AC_MASKED] / n : NAN;
+    const double nll = nw > 0 ? ws[WS_NLL] / nw : NAN;
+    const double dn = n > 0 ? ws[WS_DONE] / n : NAN;
+    scalars[0] = (float)(ac + (nll + dn) * (double)w_ar);
+    scalars[1] = (float)(ws[WS_ACTOR_ALL] / (double)N);
+    scalars[2] = (float)(ws[WS_CRITIC_ALL] / (double)N);
+    scalars[3] = (float)nll;
+    scalars[4] = (float)dn;
+    scalars[5] = (float)n;
+    const double mean = n > 0 ? ws[WS_ADV_SUM] / n : 0.;
+    scalars[6] = (float)mean;
+    scalars[7] = (float)(n > 1 ? (ws[WS_ADV_SQ] - n * mean * mean) / (n - 1.) : NAN);
+}
+
+// ---- HL-Gauss decode -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hl_decode_kernel(const float *__restrict__ logits, float *__restrict__ out, int64_t n, HlSupport sup) {
+    const int lane = threadIdx.x & 31;
+    const int K = sup.K;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (int64_t)gridDim.x * 8) {
+        float mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, __ldg(logits + r * K + k));
+        mx = warp_max(mx);
+        float se = 0.f, sc = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float ex = expf(__ldg(logits + r * K + k) - mx);
+            se += ex; sc += ex * sup.centre(k);
+        }
+        se = warp_sum(se); sc = warp_sum(sc);
+        if (lane == 0) out[r] = sc / se;
+    }
+}
+
+template <typename TIO>
+static int launch_loss(const LossArgs &la, int KJ, int blocks, cudaStream_t s) {
+    switch (KJ) {
+        case 1: ppo_loss_kernel<TIO, 1><<<blocks, kLossWarps * 32, 0, s>>>(la); break;
+        case 2: ppo_loss_kernel<TIO, 2><<<blocks, kLossWarps * 32, 0, s>>>(la); break;
+        case 4: ppo_loss_kernel<TIO, 4><<<blocks, kLossWarps * 32, 0, s>>>(la); break;
+        default: ppo_loss_kernel<TIO, 8><<<blocks, kLossWarps * 32, 0, s>>>(la); break;
+    }
+    XTRL_LAUNCH_CHECK("ppo_loss_kernel");
+    return XTRL_OK;
+}
+
+}  // namespace xtrl
+
+extern "C" int64_t xtrl_ppo_loss_workspace_bytes(void) { return (int64_t)sizeof(double) * 16; }
+
+extern "C" int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_io *io,
+                                     int32_t batch, int32_t num_timesteps, void *stream) {
+    using namespace xtrl;
+    XTRL_REQUIRE(cfg && io, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: null cfg/io");
+    XTRL_REQUIRE(batch >= 0 && num_timesteps >= 0, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: negative shape");
+    XTRL_REQUIRE(cfg->num_actions >= 1 && cfg->num_actions <= 32, XTRL_E_UNSUPPORTED,
+                 "xtrl_ppo_loss_fwd_bwd: num_actions=%d outside [1,32]", cfg->num_actions);
+    XTRL_REQUIRE(cfg->num_bins >= 2 && cfg->num_bins <= 256, XTRL_E_UNSUPPORTED,
+                 "xtrl_ppo_loss_fwd_bwd: num_bins=%d outside [2,256]", cfg->num_bins);
+    XTRL_REQUIRE(cfg->state_dim >= 1 && cfg->state_dim + 1 <= 32, XTRL_E_UNSUPPORTED,
+                 "xtrl_ppo_loss_fwd_bwd: state_dim=%d outside [1,31]", cfg->state_dim);
+    XTRL_REQUIRE(io->raw_actions && io->value_logits && io->actions && io->old_log_probs && io->returns &&
+                 io->old_values && io->episode_lens && io->scalars && io->workspace, XTRL_E_BADARG,
+                 "xtrl_ppo_loss_fwd_bwd: null required pointer");
+    XTRL_REQUIRE(!io->state_pred_raw || io->target, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: state_pred_raw without target");
+    XTRL_REQUIRE(!io->done_logit || io->dones, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: done_logit without dones");
+    cudaStream_t s = (cudaStream_t)stream;
+    XTRL_CUDA(cudaMemsetAsync(io->workspace, 0, sizeof(double) * 16, s));
+    const int64_t N = (int64_t)batch * num_timesteps;
+    if (N == 0) {
+        XTRL_CUDA(cudaMemsetAsync(io->scalars, 0, sizeof(float) * 8, s));
+        return XTRL_OK;
+    }
+    const int sblocks = (int)((N + 255) / 256 < 4 * kNumSMs ? (N + 255) / 256 : 4 * kNumSMs);
+    ppo_stats_kernel<<<sblocks, 256, 0, s>>>(io->returns, io->old_values, io->episode_lens, batch, num_timesteps, io->workspace);
+    XTRL_LAUNCH_CHECK("ppo_stats_kernel");
+    LossArgs la;
+    la.cfg = *cfg; la.io = *io; la.b = batch; la.T = num_timesteps;
+    la.sup = make_support(cfg->reward_min, cfg->reward_max, cfg->num_bins);
+    const int kj = (cfg->num_bins + 31) / 32;
+    const int KJ = kj <= 1 ? 1 : kj <= 2 ? 2 : kj <= 4 ? 4 : 8;
+    const int64_t want = (N + kLossWarps - 1) / kLossWarps;
+    const int blocks = (int)(want < 8 * kNumSMs ? want : 8 * kNumSMs);   // 8 resident CTAs / SM, persistent rows
+    int rc = cfg->bf16_io ? launch_loss<__nv_bfloat16>(la, KJ, blocks, s) : launch_loss<float>(la, KJ, blocks, s);
+    if (rc) return rc;
+    ppo_finalize_kernel<<<1, 1, 0, s>>>(io->workspace, io->scalars, N, cfg->state_dim + 1, cfg->autoreg_weight,
+                                        cfg->normalize_advantages);
+    XTRL_LAUNCH_CHECK("ppo_finalize_kernel");
+    return XTRL_OK;
+}
+
+extern "C" int xtrl_hl_decode(const float *logits, float *out, int64_t n, int32_t num_bins,
+                              float reward_min, float reward_max, void *stream) {
+    using namespace xtrl;
+    XTRL_REQUIRE(n >= 0 && num_bins >= 2, XTRL_E_BADARG, "xtrl_hl_decode: bad shape");
+    if (n == 0) return XTRL_OK;
+    XTRL_REQUIRE(logits && out, XTRL_E_BADARG, "xtrl_hl_decode: null pointer");
+    const int64_t want = (n + 7) / 8;
+    const int blocks = (int)(want < 8 * kNumSMs ? want : 8 * kNumSMs);
+    hl_decode_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, out, n, make_support(reward_min, reward_max, num_bins));
+    XTRL_LAUNCH_CHECK("hl_decode_kernel");
+    return XTRL_OK;
+}

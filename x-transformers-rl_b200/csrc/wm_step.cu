@@ -1,0 +1,517 @@
+// wm_step.cu -- one rollout timestep of the world-model / actor-critic for a batch of envs.
+//
+// Replaces, for every env at once (reference is batch 1, ~45 ATen launches per layer, >=9 host
+// syncs per step -- x_transformers_rl/x_transformers_rl.py:1250-1289):
+//   RSNorm.eval (:588-594) -> project_in + SafeEmbedding(prev action) + reward conditioning
+//   (:492-503) -> x-transformers Decoder with a KV cache (call site :721-734 / :505-512; SURVEY
+//   App. A.1: pre-LN, q/k/v/out without bias, dim_head 16, optional sigmoid value gate and
+//   value-residual mix, GELU feed-forward, final LN) -> cat(embed, state_embed[, latent])
+//   (:537-549) -> action_head / critic_head (:348-369) -> Discrete (:197-222): inverse-CDF sample
+//   + clamped log-prob -> HL-Gauss expectation of the critic logits (:843).
+//
+// One launch per timestep.  A CTA owns kTE envs; their activations never leave shared memory.
+// Bound: HBM, by the KV-cache stream -- L*2*I*(t+1) elements per env-step against ~0.9 MFLOP of
+// dense math.  Layout [k|v][layer][env][head][Tmax][16]: the stream of one
+// (env, head) is contiguous, a warp owns one (env, head), lane j reads key j's 64 B row
+// (4 x LDG.128, no L1 allocation), keeps a private online softmax, and the 32 partial
+// (max, sum, acc[16]) states are merged once by shuffles.  Dense parts: fp32 FFMA with weights
+// stored K-major so a warp reads consecutive output features (coalesced, L1/L2 resident).
+#include "common.cuh"
+#include <math.h>
+
+namespace xtrl {
+
+constexpr int kTE = 16;            // envs per CTA
+constexpr int kThreads = 256;
+constexpr int kDH = 16;            // dim_head the kernels are built for
+
+static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
+struct StepDims {
+    int S, Spad, A, Apad, D, H, I, L, K, Kpad, G, NQ, HIN, Tmax;
+    int gate, vres, mix, rot, kvbf16;
+};
+
+static int make_dims(const xtrl_model_desc *d, StepDims *o) {
+    o->S = d->state_dim; o->Spad = (int)align4(d->state_dim + 0); o->A = d->num_actions;
+    o->Apad = (d->num_actions + 1) & ~1; o->D = d->dim; o->H = d->heads; o->I = d->heads * d->dim_head;
+    o->L = d->depth; o->K = d->num_bins; o->Kpad = (d->num_bins + 1) & ~1; o->G = d->dim_gene;
+    o->gate = d->gate_values != 0; o->vres = d->value_residual != 0;
+    o->mix = o->vres && d->learned_mix != 0;
+    o->NQ = 3 * o->I + (o->gate ? o->I : 0) + (o->mix ? ((o->H + 1) & ~1) : 0);
+    o->HIN = (d->dim_gene > 0 ? 3 : 2) * d->dim; o->Tmax = d->max_timesteps;
+    o->rot = d->rotary_true_pos != 0; o->kvbf16 = d->kv_bf16 != 0;
+    return 0;
+}
+
+static int check_desc(const xtrl_model_desc *d) {
+    XTRL_REQUIRE(d, XTRL_E_BADARG, "null model desc");
+    XTRL_REQUIRE(d->dim_head == kDH, XTRL_E_UNSUPPORTED, "dim_head=%d: kernels are built for dim_head=16", d->dim_head);
+    XTRL_REQUIRE(d->dim >= 16 && d->dim <= 64 && d->dim % 4 == 0, XTRL_E_UNSUPPORTED,
+                 "dim=%d: supported hidden_dim is a multiple of 4 in [16,64] (reference default 48)", d->dim);
+    XTRL_REQUIRE(d->heads >= 1 && d->heads <= 16, XTRL_E_UNSUPPORTED, "heads=%d outside [1,16]", d->heads);
+    XTRL_REQUIRE(d->depth >= 1 && d->depth <= XTRL_MAX_DEPTH, XTRL_E_UNSUPPORTED, "depth=%d outside [1,%d]", d->depth, XTRL_MAX_DEPTH);
+    XTRL_REQUIRE(d->state_dim >= 1 && d->state_dim <= 63, XTRL_E_UNSUPPORTED, "state_dim=%d outside [1,63]", d->state_dim);
+    XTRL_REQUIRE(d->num_actions >= 1 && d->num_actions <= 32, XTRL_E_UNSUPPORTED, "num_actions=%d outside [1,32]", d->num_actions);
+    XTRL_REQUIRE(d->num_bins >= 2 && d->num_bins <= 256, XTRL_E_UNSUPPORTED, "num_bins=%d outside [2,256]", d->num_bins);
+    XTRL_REQUIRE(d->dim_gene >= 0 && d->dim_gene <= 256 && d->dim_gene % 4 == 0, XTRL_E_UNSUPPORTED,
+                 "dim_gene=%d: must be a multiple of 4 in [0,256]", d->dim_gene);
+    XTRL_REQUIRE(d->max_timesteps >= 1, XTRL_E_BADARG, "max_timesteps=%d", d->max_timesteps);
+    XTRL_REQUIRE(!d->learned_mix || d->value_residual, XTRL_E_BADARG, "learned_mix without value_residual");
+    return XTRL_OK;
+}
+
+}  // namespace xtrl
+
+extern "C" int xtrl_wm_weight_layout(const xtrl_model_desc *desc, xtrl_weight_layout *out) {
+    using namespace xtrl;
+    int rc = check_desc(desc);
+    if (rc) return rc;
+    XTRL_REQUIRE(out, XTRL_E_BADARG, "xtrl_wm_weight_layout: null out");
+    StepDims d;
+    make_dims(desc, &d);
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t at = o; o += align4(n); return at; };
+    out->s_pad = d.Spad; out->n_qkv = d.NQ; out->head_in = d.HIN;
+    out->in_proj = take((int64_t)d.Spad * 2 * d.D);
+    out->state_embed_bias = take(d.D);
+    out->action_embed = take((int64_t)d.A * d.D);
+    out->reward_embed = take(d.D);
+    out->latent_w = take((int64_t)d.G * d.D);
+    out->latent_b = take(d.D);
+    out->final_gamma = take(d.D);
+    out->head1_w = take((int64_t)d.HIN * 4 * d.D);
+    out->head1_b = take(4 * d.D);
+    out->actor2_w = take((int64_t)2 * d.D * d.Apad);
+    out->actor2_b = take(d.Apad);
+    out->critic2_w = take((int64_t)2 * d.D * d.Kpad);
+    out->critic2_b = take(d.Kpad);
+    for (int l = 0; l < XTRL_MAX_DEPTH; ++l) {
+        if (l >= d.L) { out->layer[l] = {-1, -1, -1, -1, -1, -1, -1, -1, -1}; continue; }
+        out->layer[l].ln1_gamma = take(d.D);
+        out->layer[l].qkv_w = take((int64_t)d.D * d.NQ);
+        out->layer[l].qkv_b = take(d.NQ);
+        out->layer[l].out_w = take((int64_t)d.I * d.D);
+        out->layer[l].ln2_gamma = take(d.D);
+        out->layer[l].ff1_w = take((int64_t)d.D * 4 * d.D);
+        out->layer[l].ff1_b = take(4 * d.D);
+        out->layer[l].ff2_w = take((int64_t)4 * d.D * d.D);
+        out->layer[l].ff2_b = take(d.D);
+    }
+    out->total = o;
+    return XTRL_OK;
+}
+
+extern "C" int64_t xtrl_wm_kv_cache_bytes(const xtrl_model_desc *desc, int64_t num_envs) {
+    using namespace xtrl;
+    if (check_desc(desc) || num_envs < 0) return -1;
+    const int64_t elems = 2LL * desc->depth * num_envs * desc->heads * desc->max_timesteps * desc->dim_head;
+    return elems * (desc->kv_bf16 ? 2 : 4);
+}
+
+namespace xtrl {
+
+struct StepArgs {
+    StepDims d;
+    xtrl_weight_layout w;
+    xtrl_step_io io;
+    const float *weights;
+    void *kv;
+    int B;
+    float reward_lo, reward_hi;
+    float hl_step;
+};
+
+struct Smem {                       // offsets in floats into the dynamic shared-memory block
+    int x, xn, qkv, v1, ao, ff, st, hin, gene, logit, total;
+};
+
+__host__ __device__ static inline Smem smem_layout(const StepDims &d) {
+    Smem s; int o = 0;
+    auto take = [&](int n) { int at = o; o += (n + 3) & ~3; return at; };
+    s.x = take(kTE * d.D);
+    s.xn = take(kTE * d.D);
+    s.qkv = take(kTE * d.NQ);
+    s.v1 = take(d.vres ? kTE * d.I : 0);
+    s.ao = take(kTE * d.I);
+    s.ff = take(kTE * 4 * d.D);
+    s.st = take(kTE * (d.Spad + 4));          // normalised state (padded) + normalised reward
+    s.hin = take(kTE * d.HIN);
+    s.gene = take(kTE * d.G);
+    s.logit = take(kTE * (d.Apad + d.Kpad));
+    s.total = o;
+    return s;
+}
+
+// Y[e][n] = sum_k X[e][k] * Wt[k][n] for the CTA's kTE envs.  A work item is (column pair, group
+// of ES envs); items are spread over the CTA so narrow layers still use every warp.  X rows are read
+// as broadcast LDS.128, W as coalesced LDG.64.  epi(e, n, acc) consumes each output.
+template <int ES, class Epi>
+__device__ __forceinline__ void dense_tile(const float *__restrict__ Wt, int K, int N,
+                                           const float *__restrict__ sX, int ldx, Epi epi) {
+    const int cps = N >> 1, groups = kTE / ES;
+    for (int item = threadIdx.x; item < cps * groups; item += kThreads) {
+        const int cp = item % cps, e0 = (item / cps) * ES;
+        const float *w = Wt + 2 * cp;
+        float acc0[ES], acc1[ES];
+#pragma unroll
+        for (int e = 0; e < ES; ++e) { acc0[e] = 0.f; acc1[e] = 0.f; }
+        for (int k = 0; k < K; k += 4) {
+            const float2 w0 = __ldg((const float2 *)(w + (int64_t)(k + 0) * N));
+            const float2 w1 = __ldg((const float2 *)(w + (int64_t)(k + 1) * N));
+            const float2 w2 = __ldg((const float2 *)(w + (int64_t)(k + 2) * N));
+            const float2 w3 = __ldg((const float2 *)(w + (int64_t)(k + 3) * N));
+#pragma unroll
+            for (int e = 0; e < ES; ++e) {
+                const float4 x = *(const float4 *)(sX + (e0 + e) * ldx + k);
+                acc0[e] = fmaf(x.x, w0.x, acc0[e]); acc1[e] = fmaf(x.x, w0.y, acc1[e]);
+                acc0[e] = fmaf(x.y, w1.x, acc0[e]); acc1[e] = fmaf(x.y, w1.y, acc1[e]);
+                acc0[e] = fmaf(x.z, w2.x, acc0[e]); acc1[e] = fmaf(x.z, w2.y, acc1[e]);
+                acc0[e] = fmaf(x.w, w3.x, acc0[e]); acc1[e] = fmaf(x.w, w3.y, acc1[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < ES; ++e) { epi(e0 + e, 2 * cp, acc0[e]); epi(e0 + e, 2 * cp + 1, acc1[e]); }
+    }
+}
+
+// x-transformers bias-less LayerNorm (eps 1e-5) * gamma; a warp normalises kTE/8 envs.
+__device__ __forceinline__ void layer_norm_tile(const float *__restrict__ sIn, float *__restrict__ sOut, int ldo,
+                                                const float *__restrict__ gamma, int D) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = warp; e < kTE; e += kThreads / 32) {
+        const float a = lane < D ? sIn[e * D + lane] : 0.f;
+        const float b = lane + 32 < D ? sIn[e * D + lane + 32] : 0.f;
+        const float mean = warp_sum(a + b) / (float)D;
+        const float da = lane < D ? a - mean : 0.f, db = lane + 32 < D ? b - mean : 0.f;
+        const float rstd = rsqrtf(warp_sum(da * da + db * db) / (float)D + 1e-5f);
+        if (lane < D) sOut[e * ldo + lane] = da * rstd * __ldg(gamma + lane);
+        if (lane + 32 < D) sOut[e * ldo + lane + 32] = db * rstd * __ldg(gamma + lane + 32);
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <typename KV> struct KvRow;
+template <> struct KvRow<float> {
+    static __device__ __forceinline__ void load(const float *p, float (&r)[kDH]) {
+        const float4 *q = (const float4 *)p;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float4 v = ld_stream_f4(q + i); r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w; }
+    }
+    static __device__ __forceinline__ void store1(float *p, float v) { *p = v; }
+};
+template <> struct KvRow<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&r)[kDH]) {
+        const uint4 *q = (const uint4 *)p;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint4 v = ld_stream_u4(q + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+                r[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+            }
+        }
+    }
+    static __device__ __forceinline__ void store1(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+template <typename KV>
+__global__ void __launch_bounds__(kThreads, 2)
+wm_step_kernel(const StepArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const StepDims &d = a.d;
+    const Smem so = smem_layout(d);
+    float *sx = sm + so.x, *sxn = sm + so.xn, *sqkv = sm + so.qkv, *sv1 = sm + so.v1, *sao = sm + so.ao;
+    float *sff = sm + so.ff, *sst = sm + so.st, *shin = sm + so.hin, *sgene = sm + so.gene, *slog = sm + so.logit;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int env0 = blockIdx.x * kTE;
+    const int D = d.D, I = d.I, H = d.H, NQ = d.NQ, S = d.S, Spad = d.Spad;
+    const float *W = a.weights;
+    const int lst = Spad + 4;
+
+    // ---- RSNorm.eval on (state || prev reward) (:588-594); gene rows l2-normalised (evolution.py:73-74)
+    for (int i = tid; i < kTE * lst; i += kThreads) {
+        const int e = i / lst, j = i - e * lst, env = env0 + e;
+        float v = 0.f;
+        if (env < a.B && j <= Spad && (j < S || j == Spad)) {
+            const int f = j < S ? j : S;                       // slot Spad holds the reward
+            const float raw = j < S ? __ldg(a.io.state + (int64_t)env * S + j) : __ldg(a.io.prev_reward + env);
+            v = (raw - __ldg(a.io.rs_mean + f)) / fmaxf(sqrtf(__ldg(a.io.rs_var + f)), 1e-5f);
+        }
+        sst[i] = v;
+    }
+    if (d.G > 0) {
+        for (int e = warp; e < kTE; e += kThreads / 32) {
+            const int env = env0 + e;
+            const float *row = env < a.B ? a.io.genes + (int64_t)__ldg(a.io.gene_ids + env) * d.G : nullptr;
+            float ss = 0.f;
+            for (int g = lane; g < d.G; g += 32) { const float v = row ? __ldg(row + g) : 0.f; sgene[e * d.G + g] = v; ss = fmaf(v, v, ss); }
+            ss = warp_sum(ss);
+            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            for (int g = lane; g < d.G; g += 32) sgene[e * d.G + g] *= inv;
+        }
+    }
+    __syncthreads();
+
+    // ---- token embedding (:492-503) and the two state-only head inputs (:492, :544)
+    dense_tile<4>(W + a.w.in_proj, Spad, 2 * D, sst, lst, [&](int e, int n, float acc) {
+        const int env = env0 + e;
+        if (n < D) {
+            float v = acc;
+            if (env < a.B) {
+                const int pa = __ldg(a.io.prev_action + env);
+                if (pa >= 0) v += __ldg(W + a.w.action_embed + (int64_t)pa * D + n);     // SafeEmbedding :181-195
+                v += sst[e * lst + Spad] * __ldg(W + a.w.reward_embed + n) * a.io.reward_flag;
+            }
+            sx[e * D + n] = v;
+        } else {
+            shin[e * d.HIN + n] = acc + __ldg(W + a.w.state_embed_bias + n - D);          // to_state_embed
+        }
+    });
+    if (d.G > 0) {
+        dense_tile<2>(W + a.w.latent_w, d.G, D, sgene, d.G, [&](int e, int n, float acc) {
+            shin[e * d.HIN + 2 * D + n] = acc + __ldg(W + a.w.latent_b + n);              // latent_to_embed
+        });
+    }
+    __syncthreads();
+
+    const int64_t kv_head_stride = (int64_t)d.Tmax * kDH;
+    const int64_t kv_half = (int64_t)d.L * a.B * H * kv_head_stride;
+    KV *kvbase = (KV *)a.kv;
+
+    for (int l = 0; l < d.L; ++l) {
+        const auto &wl = a.w.layer[l];
+        layer_norm_tile(sx, sxn, D, W + wl.ln1_gamma, D);
+        __syncthreads();
+        // fused q | k | v | gate | mix projection
+        dense_tile<16>(W + wl.qkv_w, D, NQ, sxn, D, [&](int e, int n, float acc) {
+            float v = acc + __ldg(W + wl.qkv_b + n);
+            if (n >= 3 * I) v = sigmoidf_(v);                  // to_v_gate / to_value_residual_mix
+            sqkv[e * NQ + n] = v;
+        });
+        __syncthreads();
+        // value residual (App. A.1) and, in true-position mode, rotary on q and the new k
+        if (d.vres) {
+            const int mix_off = 3 * I + (d.gate ? I : 0);
+            for (int i = tid; i < kTE * I; i += kThreads) {
+                const int e = i / I, n = i - e * I;
+                float *vp = sqkv + e * NQ + 2 * I + n;
+                if (l == 0) sv1[i] = *vp;
+                else {
+                    const float v1 = sv1[i], v = *vp;
+                    if (d.mix) { const float w = sqkv[e * NQ + mix_off + n / kDH]; const float df = v - v1; *vp = w < 0.5f ? fmaf(w, df, v1) : fmaf(-df, 1.f - w, v); }
+                    else *vp = v1 * 0.5f + v * 0.5f;
+                }
+            }
+        }
+        if (d.rot) {
+            for (int i = tid; i < kTE * H * 4 * 2; i += kThreads) {
+                const int which = i & 1, pr = (i >> 1) & 3, eh = i >> 3, e = eh / H, h = eh - e * H;
+                const int env = env0 + e;
+                const float p = env < a.B ? (float)__ldg(a.io.pos + env) : 0.f;
+                const float ang = p * powf(10000.f, -(float)(2 * pr) / 8.f);
+                float sn, cs;
+                sincosf(ang, &sn, &cs);
+                float *t = sqkv + e * NQ + which * I + h * kDH + 2 * pr;
+                const float x0 = t[0], x1 = t[1];
+                t[0] = x0 * cs - x1 * sn;
+                t[1] = x1 * cs + x0 * sn;
+            }
+        }
+        if (d.vres || d.rot) __syncthreads();
+
+        // ---- attention over the cache: one warp per (env, head)
+        for (int eh = warp; eh < kTE * H; eh += kThreads / 32) {
+            const int e = eh / H, h = eh - e * H, env = env0 + e;
+            if (env >= a.B) continue;
+            const int len = min(__ldg(a.io.pos + env), d.Tmax - 1);   // keys already cached
+            KV *kc = kvbase + (((int64_t)l * a.B + env) * H + h) * kv_head_stride;
+            KV *vc = kc + kv_half;
+            const float *qs = sqkv + e * NQ + h * kDH;
+            // append the new key / value (lanes 0-15: k, 16-31: v)
+            {
+                const float nv = qs[(lane < kDH ? I : 2 * I) + (lane & (kDH - 1))];
+                KvRow<KV>::store1((lane < kDH ? kc : vc) + (int64_t)len * kDH + (lane & (kDH - 1)), nv);
+            }
+            float q[kDH];
+#pragma unroll
+            for (int i = 0; i < kDH; ++i) q[i] = qs[i];
+            float m = -INFINITY, lsum = 0.f, acc[kDH];
+#pragma unroll
+            for (int i = 0; i < kDH; ++i) acc[i] = 0.f;
+            for (int j0 = 0; j0 < len; j0 += 64) {
+                const int ja = j0 + lane, jb = j0 + 32 + lane;
+                float ka[kDH], va[kDH], kb[kDH], vb[kDH];
+                if (ja < len) { KvRow<KV>::load(kc + (int64_t)ja * kDH, ka); KvRow<KV>::load(vc + (int64_t)ja * kDH, va); }
+                if (jb < len) { KvRow<KV>::load(kc + (int64_t)jb * kDH, kb); KvRow<KV>::load(vc + (int64_t)jb * kDH, vb); }
+                if (ja < len) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kDH; ++i) s = fmaf(q[i], ka[i], s);
+                    s *= 0.25f;                                  // dim_head^-0.5
+                    const float mn = fmaxf(m, s), c = expf(m - mn), p = expf(s - mn);
+                    lsum = fmaf(lsum, c, p);
+#pragma unroll
+                    for (int i = 0; i < kDH; ++i) acc[i] = fmaf(acc[i], c, p * va[i]);
+                    m = mn;
+                }
+                if (jb < len) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kDH; ++i) s = fmaf(q[i], kb[i], s);
+                    s *= 0.25f;
+                    const float mn = fmaxf(m, s), c = expf(m - mn), p = expf(s - mn);
+                    lsum = fmaf(lsum, c, p);
+#pragma unroll
+                    for (int i = 0; i < kDH; ++i) acc[i] = fmaf(acc[i], c, p * vb[i]);
+                    m = mn;
+                }
+            }
+            if (lane == 0) {                                    // the token attends to itself
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < kDH; ++i) s = fmaf(q[i], qs[I + i], s);
+                s *= 0.25f;
+                const float mn = fmaxf(m, s), c = expf(m - mn), p = expf(s - mn);
+                lsum = fmaf(lsum, c, p);
+#pragma unroll
+                for (int i = 0; i < kDH; ++i) acc[i] = fmaf(acc[i], c, p * qs[2 * I + i]);
+                m = mn;
+            }
+            const float M = warp_max(m);
+            const float f = m == -INFINITY ? 0.f : expf(m - M);
+            const float denom = warp_sum(lsum * f);
+            float mine = 0.f;
+#pragma unroll
+            for (int i = 0; i < kDH; ++i) {
+                const float t = warp_sum(acc[i] * f);
+                if (lane == i) mine = t;
+            }
+            if (lane < kDH) {
+                float o = mine / denom;
+                if (d.gate) o *= sqkv[e * NQ + 3 * I + h * kDH + lane];
+                sao[e * I + h * kDH + lane] = o;
+            }
+        }
+        __syncthreads();
+        // to_out + residual
+        dense_tile<2>(W + wl.out_w, I, D, sao, I, [&](int e, int n, float acc) { sx[e * D + n] += acc; });
+        __syncthreads();
+        layer_norm_tile(sx, sxn, D, W + wl.ln2_gamma, D);
+        __syncthreads();
+        dense_tile<8>(W + wl.ff1_w, D, 4 * D, sxn, D, [&](int e, int n, float acc) {
+            sff[e * 4 * D + n] = gelu_erf(acc + __ldg(W + wl.ff1_b + n));
+        });
+        __syncthreads();
+        dense_tile<2>(W + wl.ff2_w, 4 * D, D, sff, 4 * D, [&](int e, int n, float acc) {
+            sx[e * D + n] += acc + __ldg(W + wl.ff2_b + n);
+        });
+        __syncthreads();
+    }
+
+    // ---- final norm -> heads (:533-557)
+    layer_norm_tile(sx, shin, d.HIN, W + a.w.final_gamma, D);
+    __syncthreads();
+    dense_tile<8>(W + a.w.head1_w, d.HIN, 4 * D, shin, d.HIN, [&](int e, int n, float acc) {
+        sff[e * 4 * D + n] = silu(acc + __ldg(W + a.w.head1_b + n));
+    });
+    __syncthreads();
+    const int ll = d.Apad + d.Kpad;
+    dense_tile<1>(W + a.w.actor2_w, 2 * D, d.Apad, sff, 4 * D, [&](int e, int n, float acc) {
+        slog[e * ll + n] = acc + __ldg(W + a.w.actor2_b + n);
+    });
+    dense_tile<4>(W + a.w.critic2_w, 2 * D, d.Kpad, sff + 2 * D, 4 * D, [&](int e, int n, float acc) {
+        slog[e * ll + d.Apad + n] = acc + __ldg(W + a.w.critic2_b + n);
+    });
+    __syncthreads();
+
+    // ---- Discrete (:197-222) + HL-Gauss expectation (:843): a warp finishes kTE/8 envs
+    for (int e = warp; e < kTE; e += kThreads / 32) {
+        const int env = env0 + e;
+        if (env >= a.B) continue;
+        const float *la = slog + e * ll, *lv = la + d.Apad;
+        // critic: softmax over K bins . bin centres
+        float mx = -INFINITY;
+        for (int k = lane; k < d.K; k += 32) mx = fmaxf(mx, lv[k]);
+        mx = warp_max(mx);
+        float se = 0.f, sc = 0.f;
+        const int half = (d.K + 1) / 2;
+        for (int k = lane; k < d.K; k += 32) {
+            const float ex = expf(lv[k] - mx);
+            const float e0 = k < half ? a.reward_lo + a.hl_step * (float)k : a.reward_hi - a.hl_step * (float)(d.K - k);
+            const float e1 = k + 1 < half ? a.reward_lo + a.hl_step * (float)(k + 1) : a.reward_hi - a.hl_step * (float)(d.K - k - 1);
+            se += ex; sc = fmaf(ex, (e0 + e1) * 0.5f, sc);
+            if (a.io.value_logits) a.io.value_logits[(int64_t)env * d.K + k] = lv[k];
+        }
+        se = warp_sum(se); sc = warp_sum(sc);
+        if (lane == 0 && a.io.value) a.io.value[env] = sc / se;
+        // actor
+        const float lg = lane < d.A ? la[lane] : -INFINITY;
+        if (lane < d.A && a.io.raw_actions) a.io.raw_actions[(int64_t)env * d.A + lane] = lg;
+        const float amx = warp_max(lg);
+        const float qx = lane < d.A ? expf(lg - amx) : 0.f;
+        const float smx = qx / warp_sum(qx);
+        const float p = smx / warp_sum(smx);                   // Categorical(probs) renormalises
+        int act = -1;
+        if (a.io.forced_action) act = __ldg(a.io.forced_action + env);
+        else if (a.io.uniform) {
+            const float u = __ldg(a.io.uniform + env);
+            float run = 0.f;
+            act = d.A - 1;
+            for (int i = 0; i < d.A; ++i) {                    // sequential fp32 running sum
+                run += __shfl_sync(0xffffffffu, p, i);
+                if (run > u) { act = i; break; }
+            }
+        }
+        if (act >= 0) {
+            const float feps = 1.1920928955078125e-07f;
+            const float pa = __shfl_sync(0xffffffffu, p, act & 31);
+            if (lane == 0) {
+                if (a.io.action) a.io.action[env] = act;
+                if (a.io.log_prob) a.io.log_prob[env] = logf(fminf(fmaxf(pa, feps), 1.f - feps));
+            }
+        }
+    }
+}
+
+}  // namespace xtrl
+
+extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, void *kv_cache,
+                            const xtrl_step_io *io, int32_t num_envs, void *stream) {
+    using namespace xtrl;
+    int rc = check_desc(desc);
+    if (rc) return rc;
+    XTRL_REQUIRE(io && weights && kv_cache, XTRL_E_BADARG, "xtrl_wm_step: null pointer");
+    XTRL_REQUIRE(num_envs >= 0, XTRL_E_BADARG, "xtrl_wm_step: num_envs=%d", num_envs);
+    if (num_envs == 0) return XTRL_OK;
+    XTRL_REQUIRE(io->state && io->prev_action && io->prev_reward && io->pos && io->rs_mean && io->rs_var,
+                 XTRL_E_BADARG, "xtrl_wm_step: null required input");
+    XTRL_REQUIRE(desc->dim_gene == 0 || (io->genes && io->gene_ids), XTRL_E_BADARG,
+                 "xtrl_wm_step: evolutionary model needs genes and gene_ids");
+    StepArgs a;
+    make_dims(desc, &a.d);
+    rc = xtrl_wm_weight_layout(desc, &a.w);
+    if (rc) return rc;
+    a.io = *io; a.weights = weights; a.kv = kv_cache; a.B = num_envs;
+    a.reward_lo = desc->reward_min; a.reward_hi = desc->reward_max;
+    a.hl_step = (desc->reward_max - desc->reward_min) / (float)desc->num_bins;
+    const Smem so = smem_layout(a.d);
+    const size_t smem = (size_t)so.total * sizeof(float);
+    XTRL_REQUIRE(smem <= 110 * 1024, XTRL_E_UNSUPPORTED, "xtrl_wm_step: configuration needs %zu B shared memory per CTA (max 110 KiB)", smem);
+    const int blocks = (num_envs + kTE - 1) / kTE;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (desc->kv_bf16) {
+        XTRL_CUDA(cudaFuncSetAttribute(wm_step_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wm_step_kernel<__nv_bfloat16><<<blocks, kThreads, smem, s>>>(a);
+    } else {
+        XTRL_CUDA(cudaFuncSetAttribute(wm_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wm_step_kernel<float><<<blocks, kThreads, smem, s>>>(a);
+    }
+    XTRL_LAUNCH_CHECK("wm_step_kernel");
+    return XTRL_OK;
+}

@@ -1,0 +1,347 @@
+"""torch-tensor front of the C ABI (include/xtrl.h).  Every function launches hand-written sm_100a
+kernels from libxtrl.so on torch's current CUDA stream; tensors only provide device memory.
+
+Each function mirrors one operator seam of the reference:
+    gae                    <- calc_gae                     x_transformers_rl.py:616-640
+    hl_decode              <- HLGaussLoss(logits)          :843, :427
+    ppo_loss_fwd_bwd       <- compute_*_loss + assembly    :398-477, :939-983
+    evolve                 <- LatentGenePool.evolve_       evolution.py:76-184
+    adopt_atan2_step       <- clip_grad_norm_/AdoptAtan2/EMA  :987-992, :753
+    WorldModelStepper.step <- state_to_pred_action_and_value + sample  :1250-1289
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, name='tensor'):
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise L.XtrlError(f'{name} must be a CUDA tensor (there is no CPU path)')
+    if dtype is not None and t.dtype != dtype:
+        raise L.XtrlError(f'{name} must be {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise L.XtrlError(f'{name} must be contiguous')
+    return C.c_void_p(t.data_ptr())
+
+
+# --------------------------------------------------------------------------------------------
+# (2) GAE
+# --------------------------------------------------------------------------------------------
+
+def gae(rewards, values, is_boundary, gamma=0.99, lam=0.95, time_major=False, out=None):
+    """returns = gae + values.  rewards/values fp32, is_boundary bool/uint8; (E,T) episode-major
+    (the reference's layout) or, with time_major=True, (T,B) as the rollout buffer stores them."""
+    lib = L.load()
+    if rewards.shape != values.shape or rewards.shape != is_boundary.shape or rewards.ndim != 2:
+        raise L.XtrlError(f'gae: shapes {tuple(rewards.shape)}, {tuple(values.shape)}, {tuple(is_boundary.shape)}')
+    bd = is_boundary.view(torch.uint8) if is_boundary.dtype == torch.bool else is_boundary
+    out = torch.empty_like(rewards) if out is None else out
+    if time_major:
+        T, E = rewards.shape
+        se, st = 1, E
+    else:
+        E, T = rewards.shape
+        se, st = T, 1
+    L.check(lib.xtrl_gae(_ptr(rewards, torch.float32, 'rewards'), _ptr(values, torch.float32, 'values'),
+                         _ptr(bd, torch.uint8, 'is_boundary'), _ptr(out, torch.float32, 'out'),
+                         E, T, se, st, gamma, lam, _stream()), 'xtrl_gae')
+    return out
+
+
+def hl_decode(logits, reward_range):
+    lib = L.load()
+    K = logits.shape[-1]
+    out = torch.empty(logits.shape[:-1], device=logits.device, dtype=torch.float32)
+    L.check(lib.xtrl_hl_decode(_ptr(logits, torch.float32, 'logits'), _ptr(out), out.numel(), K,
+                               float(reward_range[0]), float(reward_range[1]), _stream()), 'xtrl_hl_decode')
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# (3) fused PPO loss forward + backward w.r.t. the head outputs
+# --------------------------------------------------------------------------------------------
+
+@dataclass
+class LossConfig:
+    num_actions: int
+    num_bins: int
+    state_dim: int
+    reward_range: tuple
+    eps_clip: float = 0.2
+    value_clip: float = 0.4
+    entropy_weight: float = 0.01
+    actor_weight: float = 1.
+    critic_weight: float = 1.
+    autoreg_weight: float = 1.
+    normalize_advantages: bool = True
+
+    def c_struct(self, bf16):
+        return L.LossCfg(self.num_actions, self.num_bins, self.state_dim, float(self.reward_range[0]),
+                         float(self.reward_range[1]), self.eps_clip, self.value_clip, self.entropy_weight,
+                         self.actor_weight, self.critic_weight, self.autoreg_weight,
+                         int(self.normalize_advantages), int(bf16))
+
+
+SCALAR_NAMES = ('total', 'actor_loss', 'critic_loss', 'autoreg_loss', 'pred_done_loss', 'n_masked', 'adv_mean', 'adv_var')
+
+
+def ppo_loss_fwd_bwd(cfg: LossConfig, raw_actions, value_logits, state_pred_raw, done_logit, actions,
+                     old_log_probs, returns, old_values, target, dones, episode_lens, per_step=False):
+    """All rows of a (b, T) minibatch.  Head outputs (b,T,A), (b,T,K), (b,T,2(S+1)) raw (mean, logvar
+    interleaved), (b,T) pre-sigmoid; fp32 or bf16.  Returns (scalars[8], grads dict[, per_step (b,T,2)])."""
+    lib = L.load()
+    b, T = actions.shape
+    io_dtype = raw_actions.dtype
+    if io_dtype not in (torch.float32, torch.bfloat16):
+        raise L.XtrlError(f'ppo_loss: head outputs must be fp32 or bf16, got {io_dtype}')
+    for n, t_ in (('value_logits', value_logits), ('state_pred_raw', state_pred_raw), ('done_logit', done_logit)):
+        if t_ is not None and t_.dtype != io_dtype:
+            raise L.XtrlError(f'ppo_loss: {n} dtype {t_.dtype} != {io_dtype}')
+    dev = raw_actions.device
+    bd = None if dones is None else (dones.view(torch.uint8) if dones.dtype == torch.bool else dones)
+    g_ra, g_vl = torch.empty_like(raw_actions), torch.empty_like(value_logits)
+    g_sp = None if state_pred_raw is None else torch.empty_like(state_pred_raw)
+    g_dl = None if done_logit is None else torch.empty_like(done_logit)
+    ps = torch.empty(b, T, 2, device=dev, dtype=torch.float32) if per_step else None
+    scalars = torch.empty(8, device=dev, dtype=torch.float32)
+    ws = torch.empty(lib.xtrl_ppo_loss_workspace_bytes() // 8, device=dev, dtype=torch.float64)
+    io = L.LossIO(_ptr(raw_actions, None, 'raw_actions'), _ptr(value_logits, None, 'value_logits'),
+                  _ptr(state_pred_raw, None, 'state_pred_raw'), _ptr(done_logit, None, 'done_logit'),
+                  _ptr(actions, torch.int32, 'actions'), _ptr(old_log_probs, torch.float32, 'old_log_probs'),
+                  _ptr(returns, torch.float32, 'returns'), _ptr(old_values, torch.float32, 'old_values'),
+                  _ptr(target, torch.float32, 'target'), _ptr(bd, torch.uint8, 'dones'),
+                  _ptr(episode_lens, torch.int32, 'episode_lens'),
+                  _ptr(g_ra), _ptr(g_vl), _ptr(g_sp), _ptr(g_dl), _ptr(ps), _ptr(scalars), _ptr(ws))
+    cs = cfg.c_struct(io_dtype == torch.bfloat16)
+    L.check(lib.xtrl_ppo_loss_fwd_bwd(C.byref(cs), C.byref(io), b, T, _stream()), 'xtrl_ppo_loss_fwd_bwd')
+    grads = dict(raw_actions=g_ra, value_logits=g_vl, state_pred_raw=g_sp, done_logit=g_dl)
+    return (scalars, grads, ps) if per_step else (scalars, grads)
+
+
+# --------------------------------------------------------------------------------------------
+# (4) gene pool
+# --------------------------------------------------------------------------------------------
+
+def evolve_(genes, fitness, noise_tourn, noise_cross, noise_mut, *, num_islands, num_genes_per_island,
+            num_selected, tournament_size, num_elites=1, mutation_std_dev=0.1, migrate=False,
+            num_migrate=0, temperature=1.5):
+    """in-place evolution step; returns selected gene ids (I, s) int64 like the reference."""
+    lib = L.load()
+    G = genes.shape[-1]
+    sel = torch.empty(num_islands, num_selected, device=genes.device, dtype=torch.int64)
+    scratch = torch.empty_like(genes)
+    pd = L.PoolDesc(G, num_islands, num_genes_per_island, num_selected, tournament_size, num_elites,
+                    int(migrate), int(num_migrate), mutation_std_dev, temperature)
+    L.check(lib.xtrl_evolve(_ptr(genes, torch.float32, 'genes'), _ptr(fitness, torch.float32, 'fitness'),
+                            _ptr(noise_tourn, torch.float32, 'noise_tourn'), _ptr(noise_cross, torch.float32, 'noise_cross'),
+                            _ptr(noise_mut, torch.float32, 'noise_mut'), _ptr(sel), _ptr(scratch), C.byref(pd),
+                            _stream()), 'xtrl_evolve')
+    return sel
+
+
+# --------------------------------------------------------------------------------------------
+# (5) optimiser over flat buffers
+# --------------------------------------------------------------------------------------------
+
+def adopt_atan2_step(params, grads, m, v, param_init, ema, seg_offsets, *, lr, init_lr, betas, regen_rate,
+                     cautious_factor, max_grad_norm, first_step, ema_mode=0, ema_decay=0., copy_ema_to_online=False,
+                     a=1.27, b=1., workspace=None, grad_norm_out=None):
+    lib = L.load()
+    nt = seg_offsets.numel() - 1
+    n = params.numel()
+    if workspace is None:
+        workspace = torch.empty(lib.xtrl_opt_workspace_bytes(nt) // 8, device=params.device, dtype=torch.float64)
+    cfg = L.OptCfg(lr, init_lr, betas[0], betas[1], regen_rate, cautious_factor, a, b, max_grad_norm,
+                   int(first_step), float(ema_mode), ema_decay, int(copy_ema_to_online))
+    L.check(lib.xtrl_adopt_atan2_step(_ptr(params, torch.float32, 'params'), _ptr(grads, torch.float32, 'grads'),
+                                      _ptr(m, torch.float32), _ptr(v, torch.float32), _ptr(param_init, torch.float32),
+                                      _ptr(ema, torch.float32), _ptr(seg_offsets, torch.int64, 'seg_offsets'), nt, n,
+                                      C.byref(cfg), _ptr(workspace), _ptr(grad_norm_out), _stream()),
+            'xtrl_adopt_atan2_step')
+
+
+# --------------------------------------------------------------------------------------------
+# (1) rollout step
+# --------------------------------------------------------------------------------------------
+
+@dataclass
+class ModelConfig:
+    """shape of the WorldModelActorCritic the kernels are asked to run (x_transformers_rl.py:281-369,
+    :709-735).  world_model keys accepted: attn_dim_head, heads, depth, attn_gate_values,
+    add_value_residual, learned_value_residual_mix -- anything else is an error."""
+    state_dim: int
+    num_actions: int
+    reward_range: tuple
+    max_timesteps: int
+    dim: int = 48
+    heads: int = 4
+    dim_head: int = 16
+    depth: int = 1
+    num_bins: int = 100
+    dim_gene: int = 0
+    gate_values: bool = False
+    value_residual: bool = False
+    learned_mix: bool = False
+    rotary_true_pos: bool = False
+    kv_bf16: bool = False
+
+    WORLD_MODEL_KEYS = ('attn_dim_head', 'heads', 'depth', 'attn_gate_values', 'add_value_residual',
+                        'learned_value_residual_mix')
+
+    @classmethod
+    def from_learner_kwargs(cls, state_dim, num_actions, reward_range, max_timesteps, world_model, hidden_dim=48,
+                            num_bins=100, dim_gene=0, **extra):
+        unknown = set(world_model) - set(cls.WORLD_MODEL_KEYS)
+        if unknown:
+            raise L.XtrlError(f'world_model keys {sorted(unknown)} are not supported by the B200 kernels '
+                              f'(supported: {cls.WORLD_MODEL_KEYS})')
+        vres = bool(world_model.get('add_value_residual', False))
+        return cls(state_dim=state_dim, num_actions=num_actions, reward_range=tuple(reward_range),
+                   max_timesteps=max_timesteps, dim=hidden_dim, heads=world_model.get('heads', 8),
+                   dim_head=world_model.get('attn_dim_head', 64), depth=world_model['depth'], num_bins=num_bins,
+                   dim_gene=dim_gene, gate_values=bool(world_model.get('attn_gate_values', False)),
+                   value_residual=vres, learned_mix=vres and bool(world_model.get('learned_value_residual_mix', False)),
+                   **extra)
+
+    @property
+    def inner(self):
+        return self.heads * self.dim_head
+
+    def c_struct(self):
+        return L.ModelDesc(self.state_dim, self.num_actions, self.dim, self.heads, self.dim_head, self.depth,
+                           self.num_bins, self.dim_gene, int(self.gate_values), int(self.value_residual),
+                           int(self.learned_mix), self.max_timesteps, int(self.rotary_true_pos), int(self.kv_bf16),
+                           float(self.reward_range[0]), float(self.reward_range[1]))
+
+
+def weight_layout(cfg: ModelConfig) -> L.WeightLayout:
+    lib = L.load()
+    out = L.WeightLayout()
+    d = cfg.c_struct()
+    L.check(lib.xtrl_wm_weight_layout(C.byref(d), C.byref(out)), 'xtrl_wm_weight_layout')
+    return out
+
+
+def pack_weights(sd: dict, cfg: ModelConfig, out=None, device=None):
+    """reference-style state_dict -> the packed fp32 blob xtrl_wm_step reads (K-major weights)."""
+    lay = weight_layout(cfg)
+    device = device if device is not None else next(iter(sd.values())).device
+    blob = torch.zeros(lay.total, device=device, dtype=torch.float32) if out is None else out.zero_()
+    D, I, H, S, A, K, G = cfg.dim, cfg.inner, cfg.heads, cfg.state_dim, cfg.num_actions, cfg.num_bins, cfg.dim_gene
+
+    def put(off, t, rows=None, ld=None):
+        t = t.detach().to(device=device, dtype=torch.float32)
+        if t.ndim == 1:
+            blob[off:off + t.numel()] = t
+        else:  # (rows, cols) written with leading dimension ld
+            r, c = t.shape
+            ld = c if ld is None else ld
+            blob[off:off + r * ld].view(r, ld)[:, :c] = t
+
+    tf = 'transformer.attn_layers'
+    in_proj = torch.cat((sd['transformer.project_in.weight'].T, sd['to_state_embed.weight'].T), dim=1)   # (S, 2D)
+    put(lay.in_proj, in_proj)
+    put(lay.state_embed_bias, sd['to_state_embed.bias'])
+    put(lay.action_embed, sd['action_embeds.embed.weight'])
+    put(lay.reward_embed, sd['reward_embed'])
+    if G > 0:
+        put(lay.latent_w, sd['latent_to_embed.weight'].T)
+        put(lay.latent_b, sd['latent_to_embed.bias'])
+    put(lay.final_gamma, sd[f'{tf}.final_norm.gamma'])
+    put(lay.head1_w, torch.cat((sd['action_head.0.weight'].T, sd['critic_head.0.weight'].T), dim=1))
+    put(lay.head1_b, torch.cat((sd['action_head.0.bias'], sd['critic_head.0.bias'])))
+    a_pad, k_pad = (A + 1) & ~1, (K + 1) & ~1
+    put(lay.actor2_w, sd['action_head.2.weight'].T, ld=a_pad)
+    put(lay.actor2_b, sd['action_head.2.bias'])
+    put(lay.critic2_w, sd['critic_head.2.weight'].T, ld=k_pad)
+    put(lay.critic2_b, sd['critic_head.2.bias'])
+    for l in range(cfg.depth):
+        pa, pf = f'{tf}.layers.{2 * l}', f'{tf}.layers.{2 * l + 1}'
+        ll = lay.layer[l]
+        put(ll.ln1_gamma, sd[f'{pa}.0.gamma'])
+        cols = [sd[f'{pa}.1.to_q.weight'].T, sd[f'{pa}.1.to_k.weight'].T, sd[f'{pa}.1.to_v.weight'].T]
+        bias = [torch.zeros(3 * I, device=device)]
+        if cfg.gate_values:
+            cols.append(sd[f'{pa}.1.to_v_gate.weight'].T)
+            bias.append(sd[f'{pa}.1.to_v_gate.bias'].to(device))
+        if cfg.learned_mix:
+            hp = (H + 1) & ~1
+            w, bb = torch.zeros(D, hp, device=device), torch.zeros(hp, device=device)
+            if l > 0:
+                w[:, :H] = sd[f'{pa}.1.to_value_residual_mix.0.weight'].T
+                bb[:H] = sd[f'{pa}.1.to_value_residual_mix.0.bias']
+            cols.append(w)
+            bias.append(bb)
+        qkv = torch.cat([c.to(device=device, dtype=torch.float32) for c in cols], dim=1)
+        assert qkv.shape == (D, lay.n_qkv), (qkv.shape, lay.n_qkv)
+        put(ll.qkv_w, qkv)
+        put(ll.qkv_b, torch.cat([b_.float() for b_ in bias]))
+        put(ll.out_w, sd[f'{pa}.1.to_out.weight'].T)
+        put(ll.ln2_gamma, sd[f'{pf}.0.gamma'])
+        put(ll.ff1_w, sd[f'{pf}.1.ff.0.0.weight'].T)
+        put(ll.ff1_b, sd[f'{pf}.1.ff.0.0.bias'])
+        put(ll.ff2_w, sd[f'{pf}.1.ff.2.weight'].T)
+        put(ll.ff2_b, sd[f'{pf}.1.ff.2.bias'])
+    return blob
+
+
+class WorldModelStepper:
+    """Owns the packed weights and the KV cache of `num_envs` envs and advances all of them one
+    timestep per call (x_transformers_rl.py:1250-1289, vectorised)."""
+
+    def __init__(self, cfg: ModelConfig, num_envs: int, device='cuda'):
+        self.lib = L.load()
+        self.cfg, self.num_envs, self.device = cfg, num_envs, torch.device(device)
+        self.desc = cfg.c_struct()
+        nbytes = self.lib.xtrl_wm_kv_cache_bytes(C.byref(self.desc), num_envs)
+        if nbytes < 0:
+            L.check(self.lib.xtrl_wm_weight_layout(C.byref(self.desc), C.byref(L.WeightLayout())), 'model config')
+        self.kv_cache = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        self.weights = None
+        self.pos = torch.zeros(num_envs, device=self.device, dtype=torch.int32)
+
+    def load_state_dict(self, sd):
+        self.weights = pack_weights(sd, self.cfg, out=self.weights, device=self.device)
+
+    def reset(self):
+        self.pos.zero_()
+
+    def step(self, state, prev_action, prev_reward, rs_mean, rs_var, *, uniform=None, forced_action=None,
+             genes=None, gene_ids=None, reward_flag=1., out=None, want_logits=False, advance=True):
+        """state (B,S) f32; prev_action (B,) i32 (-1 none); prev_reward (B,) f32; uniform (B,) f32.
+        Returns dict(action i32, log_prob, value[, raw_actions, value_logits])."""
+        if self.weights is None:
+            raise L.XtrlError('WorldModelStepper: load_state_dict() first')
+        B, cfg, dev = self.num_envs, self.cfg, self.device
+        if state.shape != (B, cfg.state_dim):
+            raise L.XtrlError(f'step: state shape {tuple(state.shape)} != {(B, cfg.state_dim)}')
+        out = {} if out is None else out
+        for name, dt, shape in (('action', torch.int32, (B,)), ('log_prob', torch.float32, (B,)), ('value', torch.float32, (B,))):
+            if name not in out:
+                out[name] = torch.empty(shape, device=dev, dtype=dt)
+        if want_logits:
+            out.setdefault('raw_actions', torch.empty(B, cfg.num_actions, device=dev))
+            out.setdefault('value_logits', torch.empty(B, cfg.num_bins, device=dev))
+        io = L.StepIO(_ptr(state, torch.float32, 'state'), _ptr(prev_action, torch.int32, 'prev_action'),
+                      _ptr(prev_reward, torch.float32, 'prev_reward'), _ptr(self.pos, torch.int32),
+                      _ptr(rs_mean, torch.float32, 'rs_mean'), _ptr(rs_var, torch.float32, 'rs_var'),
+                      _ptr(genes, torch.float32, 'genes'), _ptr(gene_ids, torch.int32, 'gene_ids'),
+                      _ptr(uniform, torch.float32, 'uniform'), _ptr(forced_action, torch.int32, 'forced_action'),
+                      float(reward_flag), _ptr(out['action']), _ptr(out['log_prob']), _ptr(out['value']),
+                      _ptr(out.get('raw_actions')), _ptr(out.get('value_logits')))
+        L.check(self.lib.xtrl_wm_step(C.byref(self.desc), _ptr(self.weights), _ptr(self.kv_cache), C.byref(io), B,
+                                      _stream()), 'xtrl_wm_step')
+        if advance:
+            self.pos.add_(1)
+        return out
