@@ -1,0 +1,229 @@
+"""Learn-side (teacher-forced, full-sequence) world-model / actor-critic.
+
+Host-side plumbing for `Agent.learn`: the sequence model is expressed with torch ops + autograd
+(SURVEY 8f row 1 lists its fused fwd/bwd kernels as the next step); the hot arithmetic the
+north star names -- the PPO / value / world-model losses with their backward, GAE, the optimiser and
+the rollout step -- runs in libxtrl.so.  Parameter names and shapes equal the reference's
+`WorldModelActorCritic.state_dict()` (x_transformers_rl.py:281-369 with x-transformers'
+ContinuousTransformerWrapper/Decoder underneath, :721-734) so `Agent.save/load`
+checkpoints interchange and `ops.pack_weights` can feed the rollout kernel from the same dict.
+
+All parameters are views into ONE flat fp32 buffer (and one flat gradient buffer): the optimiser
+kernel, the EMA copy and the NCCL gradient all-reduce each touch a single contiguous tensor.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+
+class _Norm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        return F.layer_norm(x, x.shape[-1:]) * self.gamma
+
+
+class _Rotary(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.register_buffer('inv_freq', 1. / (10000 ** (torch.arange(0, dim, 2).float() / dim)))
+
+
+class _SafeEmbedding(nn.Module):
+    """embedding that yields zeros for id -1 (x_transformers_rl.py:181-195)."""
+
+    def __init__(self, n, dim):
+        super().__init__()
+        self.embed = nn.Embedding(n, dim)
+
+    def forward(self, ids):
+        has = ids >= 0
+        return self.embed(ids.clamp(min=0)) * has[..., None].to(self.embed.weight.dtype)
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, heads, dim_head, gate, mix):
+        super().__init__()
+        inner = heads * dim_head
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_k = nn.Linear(dim, inner, bias=False)
+        self.to_v = nn.Linear(dim, inner, bias=False)
+        self.to_out = nn.Linear(inner, dim, bias=False)
+        if gate:
+            self.to_v_gate = nn.Linear(dim, inner)
+            nn.init.constant_(self.to_v_gate.weight, 0.)
+            nn.init.constant_(self.to_v_gate.bias, 10.)
+        if mix:
+            self.to_value_residual_mix = nn.Sequential(nn.Linear(dim, heads), nn.Sigmoid())
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.ff = nn.Sequential(nn.Sequential(nn.Linear(dim, dim * mult), nn.GELU()), nn.Identity(),
+                                nn.Linear(dim * mult, dim))
+
+
+class _Decoder(nn.Module):
+    def __init__(self, cfg: ops.ModelConfig):
+        super().__init__()
+        self.dim = cfg.dim
+        self.rotary_pos_emb = _Rotary(cfg.dim_head // 2)
+        self.layers = nn.ModuleList()
+        for l in range(cfg.depth):
+            self.layers.append(nn.ModuleList([_Norm(cfg.dim), _Attention(cfg.dim, cfg.heads, cfg.dim_head, cfg.gate_values,
+                                                                          cfg.learned_mix and l > 0)]))
+            self.layers.append(nn.ModuleList([_Norm(cfg.dim), _FeedForward(cfg.dim)]))
+        self.final_norm = _Norm(cfg.dim)
+
+
+class _Wrapper(nn.Module):
+    def __init__(self, cfg: ops.ModelConfig):
+        super().__init__()
+        self.project_in = nn.Linear(cfg.state_dim, cfg.dim, bias=False)
+        self.attn_layers = _Decoder(cfg)
+
+
+def _rotate(t, cos, sin, rot):
+    x, rest = t[..., :rot], t[..., rot:]
+    pairs = x.unflatten(-1, (-1, 2))
+    half = torch.stack((-pairs[..., 1], pairs[..., 0]), dim=-1).flatten(-2)
+    return torch.cat((x * cos + half * sin, rest), dim=-1)
+
+
+class WorldModelActorCritic(nn.Module):
+    def __init__(self, cfg: ops.ModelConfig, dropout=0.25, frac_actor_critic_head_gradient=0.5, reward_dropout=0.5):
+        super().__init__()
+        self.cfg, self.dropout, self.frac, self.reward_dropout_p = cfg, dropout, frac_actor_critic_head_gradient, reward_dropout
+        D, S, A, K = cfg.dim, cfg.state_dim, cfg.num_actions, cfg.num_bins
+        self.transformer = _Wrapper(cfg)
+        self.reward_embed = nn.Parameter(torch.ones(D) * 1e-2)
+        self.action_embeds = _SafeEmbedding(A, D)
+        self.to_state_embed = nn.Linear(S, D)
+        self.to_pred_done = nn.Sequential(nn.Linear(2 * D, 1))
+        self.to_pred = nn.Sequential(nn.Linear(2 * D, D), nn.SiLU(), nn.Linear(D, 2 * (S + 1)))
+        self.evolutionary = cfg.dim_gene > 0
+        if self.evolutionary:
+            self.latent_to_embed = nn.Linear(cfg.dim_gene, D)
+        hin = (3 if self.evolutionary else 2) * D
+        self.critic_head = nn.Sequential(nn.Linear(hin, 2 * D), nn.SiLU(), nn.Linear(2 * D, K))
+        self.action_head = nn.Sequential(nn.Linear(hin, 2 * D), nn.SiLU(), nn.Linear(2 * D, A))
+        self._flatten()
+
+    # -- one flat fp32 buffer behind every parameter ------------------------------------------
+    def _flatten(self):
+        params = list(self.parameters())
+        sizes = [p.numel() for p in params]
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        flat = torch.empty(offs[-1], dtype=torch.float32, device=params[0].device)
+        for p, o in zip(params, offs):
+            flat[o:o + p.numel()].copy_(p.data.reshape(-1))
+        self._offsets = offs
+        self._bind(flat, torch.zeros_like(flat))
+
+    def _bind(self, flat, flat_grad):
+        self.flat_params, self.flat_grads = flat, flat_grad
+        for p, o in zip(self.parameters(), self._offsets):
+            p.data = flat[o:o + p.numel()].view(p.shape)
+            p.grad = flat_grad[o:o + p.numel()].view(p.shape)
+        self.seg_offsets = torch.tensor(self._offsets, dtype=torch.int64, device=flat.device)
+
+    def _apply(self, fn, *a, **k):            # .to(device) must keep the flat-buffer aliasing
+        flat, grad = fn(self.flat_params), fn(self.flat_grads)
+        super()._apply(fn, *a, **k)
+        self._bind(flat, grad)
+        return self
+
+    def state_dict_from_flat(self, flat):
+        """a reference-style state_dict whose tensors view `flat` (e.g. the EMA buffer)."""
+        out = {}
+        for (name, p), o in zip(self.named_parameters(), self._offsets):
+            out[name] = flat[o:o + p.numel()].view(p.shape)
+        return out
+
+    # -- full-sequence forward (x_transformers_rl.py:479-559 with mask=, :928-935) ---------------
+    def forward(self, state, rewards, actions, next_actions, mask, latent_gene=None, reward_flag=1.):
+        """state (b,n,S) normalised; rewards (b,n) normalised prev rewards; actions (b,n) prev actions
+        (-1 none); next_actions (b,n); mask (b,n) bool.  Returns raw head outputs:
+        raw_actions (b,n,A), value_logits (b,n,K), state_pred_raw (b,n,2(S+1)), done_logit (b,n)."""
+        cfg, tfm = self.cfg, self.transformer
+        dec = tfm.attn_layers
+        b, n, _ = state.shape
+        h, dh, rot = cfg.heads, cfg.dim_head, cfg.dim_head // 2
+        p_drop = self.dropout if self.training else 0.
+        state_embed = self.to_state_embed(state)
+        x = tfm.project_in(state) + self.action_embeds(actions) + rewards[..., None] * self.reward_embed * reward_flag
+        ang = torch.arange(n, device=state.device, dtype=torch.float32)[:, None] * dec.rotary_pos_emb.inv_freq[None]
+        ang = ang.repeat_interleave(2, dim=-1)                       # (n, rot) interleaved (t0,t0,t1,t1,..)
+        cos, sin = ang.cos().to(x.dtype), ang.sin().to(x.dtype)
+        # key padding + causal, as an additive-free boolean mask (True = attend)
+        allow = mask[:, None, None, :] & torch.ones(n, n, dtype=torch.bool, device=state.device).tril()[None, None]
+        first_v = None
+        for l in range(cfg.depth):
+            norm, attn = dec.layers[2 * l]
+            xn = norm(x)
+            split = lambda t: t.view(b, n, h, dh).transpose(1, 2)
+            q, k, v = split(attn.to_q(xn)), split(attn.to_k(xn)), split(attn.to_v(xn))
+            if cfg.value_residual:
+                if l == 0:
+                    first_v = v
+                elif cfg.learned_mix:
+                    mix = attn.to_value_residual_mix(xn).transpose(1, 2)[..., None]
+                    v = first_v.lerp(v, mix)
+                else:
+                    v = first_v * 0.5 + v * 0.5
+            q, k = _rotate(q, cos, sin, rot), _rotate(k, cos, sin, rot)
+            out = F.scaled_dot_product_attention(q, k, v, attn_mask=allow, dropout_p=p_drop)
+            out = out.transpose(1, 2).reshape(b, n, h * dh)
+            if cfg.gate_values:
+                out = out * attn.to_v_gate(xn).sigmoid()
+            out = attn.to_out(out).masked_fill(~mask[..., None], 0.)
+            x = x + out
+            norm, ff = dec.layers[2 * l + 1]
+            hid = ff.ff[0](norm(x))
+            hid = F.dropout(hid, p_drop, self.training)
+            x = x + ff.ff[2](hid)
+        embed = dec.final_norm(x)
+
+        ewa = torch.cat((embed, self.action_embeds(next_actions)), dim=-1)          # :516-529
+        state_pred_raw = self.to_pred(ewa)
+        done_logit = self.to_pred_done(ewa)[..., 0]
+
+        embed = embed.detach() * (1. - self.frac) + embed * self.frac             # frac_gradient :114-116,:533
+        ac_in = torch.cat((embed, state_embed), dim=-1)
+        if self.evolutionary:
+            lat = self.latent_to_embed(latent_gene)
+            ac_in = torch.cat((ac_in, lat[:, None].expand(-1, n, -1).to(ac_in.dtype)), dim=-1)
+        return self.action_head(ac_in), self.critic_head(ac_in), state_pred_raw, done_logit
+
+
+class FusedPPOLoss(torch.autograd.Function):
+    """autograd seam around xtrl_ppo_loss_fwd_bwd: forward launches the fused kernel, which already
+    produced d loss / d head-outputs; backward hands those (scaled by the incoming scalar) to autograd
+    so the sequence model's own backward continues from them."""
+
+    @staticmethod
+    def forward(ctx, cfg, raw_actions, value_logits, state_pred_raw, done_logit, actions, old_log_probs, returns,
+                old_values, target, dones, episode_lens):
+        scalars, grads = ops.ppo_loss_fwd_bwd(cfg, raw_actions.contiguous(), value_logits.contiguous(),
+                                              state_pred_raw.contiguous(), done_logit.contiguous(), actions,
+                                              old_log_probs, returns, old_values, target, dones, episode_lens)
+        ctx.save_for_backward(grads['raw_actions'], grads['value_logits'], grads['state_pred_raw'], grads['done_logit'])
+        ctx.mark_non_differentiable(scalars)
+        return scalars[0].clone(), scalars
+
+    @staticmethod
+    def backward(ctx, g_total, _g_scalars):
+        g_ra, g_vl, g_sp, g_dl = ctx.saved_tensors
+        s = g_total.to(g_ra.dtype)
+        return (None, g_ra * s, g_vl * s, g_sp * s, g_dl * s, None, None, None, None, None, None, None)
