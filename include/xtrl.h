@@ -107,7 +107,8 @@ typedef struct xtrl_step_io {
     const float   *state;         /* [B][S] raw (un-normalised) observation                   */
     const int32_t *prev_action;   /* [B], -1 = none (:1244)                                   */
     const float   *prev_reward;   /* [B] raw previous reward (0 at t=0, :1246)                */
-    const int32_t *pos;           /* [B] number of tokens already cached for this env (its t) */
+    const int32_t *pos;           /* [B] number of tokens already cached for this env (its t);
+                                     NULL = every env is at `pos_uniform` (lock-step rollout)  */
     const float   *rs_mean;       /* [S+1] RSNorm running_mean                                */
     const float   *rs_var;        /* [S+1] RSNorm running_variance                            */
     const float   *genes;         /* [num_genes][G] un-normalised gene matrix, or NULL        */
@@ -116,6 +117,7 @@ typedef struct xtrl_step_io {
                                      do not sample (action_out untouched unless forced)      */
     const int32_t *forced_action; /* [B] or NULL: evaluate log-prob of this action instead    */
     float          reward_flag;   /* the per-forward reward-conditioning flag (:501-503)      */
+    int32_t        pos_uniform;   /* used when pos == NULL                                    */
     /* outputs (any may be NULL) */
     int32_t *action;              /* [B]                                                      */
     float   *log_prob;            /* [B] log(clamp(p[a], eps, 1-eps))                         */

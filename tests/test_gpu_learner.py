@@ -1,0 +1,210 @@
+"""GPU: the drop-in Learner / Agent API (reference tests/test_x_transformers_rl.py:4-53), the learn-side
+model + fused loss against the oracle's autograd, and the vectorised rollout against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restated as R
+from helpers import rel_err, xtrl, oracle_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _learner_cls():
+    import x_transformers_rl            # the drop-in import name
+    return x_transformers_rl.Learner
+
+
+class Sim:                                # README.md:16-21 / reference tests :10-15
+    def reset(self, seed=None):
+        return np.random.randn(5)
+
+    def step(self, actions):
+        return np.random.randn(5), np.random.randn(1), False
+
+
+@pytest.mark.parametrize('evolutionary', (False, True))
+def test_e2e_reference_smoke(evolutionary, tmp_path):
+    """the reference's own (only) test, discrete half: construct, learn one update, act twice."""
+    Learner = _learner_cls()
+    learner = Learner(
+        state_dim=5, num_actions=2, reward_range=(-1., 1.), max_timesteps=10, batch_size=2, num_episodes_per_update=2,
+        evolutionary=evolutionary,
+        latent_gene_pool=dict(dim=32, num_genes_per_island=3, num_selected=2, tournament_size=2),
+        world_model=dict(attn_dim_head=16, heads=4, depth=1),
+        agent_kwargs=dict(save_path=str(tmp_path / 'ppo.pt')))
+    learner(Sim(), 1)
+    hiddens = None
+    actions, hiddens = learner.agent(np.random.randn(5), hiddens=hiddens)
+    actions, hiddens = learner.agent(np.random.randn(5), hiddens=hiddens)
+    assert actions.shape == (2,) and torch.isfinite(actions).all()
+    assert os.path.exists(tmp_path / 'ppo.pt')
+    assert learner.timings['env_steps'] == 2 * 10 * (3 if evolutionary else 1)
+    assert learner.accelerator.is_main_process and len(learner.episode_genes_for_process) == (6 if evolutionary else 2)
+    sd = torch.load(tmp_path / 'ppo.pt', weights_only=True)['model']
+    assert 'transformer.attn_layers.layers.0.1.to_q.weight' in sd and 'critic_head.2.bias' in sd
+
+
+def test_continuous_actions_raise_not_fallback(tmp_path):
+    with pytest.raises(NotImplementedError):
+        _learner_cls()(state_dim=5, num_actions=2, reward_range=(-1., 1.), continuous_actions=True,
+                       world_model=dict(attn_dim_head=16, heads=4, depth=1), agent_kwargs=dict(save_path=str(tmp_path / 'p.pt')))
+
+
+LANDER_WM = dict(attn_dim_head=16, heads=4, depth=2, attn_gate_values=True, add_value_residual=True,
+                 learned_value_residual_mix=True)
+
+
+def _make(tmp_path, B, T, **kw):
+    Learner = _learner_cls()
+    args = dict(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=T, batch_size=B,
+                num_episodes_per_update=B, world_model=LANDER_WM, epochs=1,
+                agent_kwargs=dict(save_path=str(tmp_path / 'ppo.pt'), dropout=0.))
+    args.update(kw)
+    return Learner(**args)
+
+
+def test_vectorized_rollout_matches_oracle(tmp_path):
+    """B envs in lock step through the kernel == the oracle stepping the same envs with the same uniforms."""
+    pkg = xtrl()
+    from importlib import import_module
+    envs = import_module('x-transformers-rl_b200.envs')
+    B, T = 24, 12
+    torch.manual_seed(0)
+    learner = _make(tmp_path, B, T)
+    agent = learner.agent
+    with torch.no_grad():                  # move the weights off their init so gates / mixes matter
+        agent.ema_params.add_(torch.randn_like(agent.ema_params) * 0.1)
+        agent.rsnorm.running_mean.normal_(); agent.rsnorm.running_variance.uniform_(0.5, 2.)
+    env = envs.SyntheticVecEnv(B, 8, T, device=learner.device, seed=3)
+    u = torch.rand(T, B, device=learner.device)
+    gids = torch.zeros(B, dtype=torch.int32, device=learner.device)
+    buf, cum = learner.rollout_vectorized(env, gids, T, uniforms=u)
+    sd = {k: v.cpu() for k, v in agent.ema_state_dict().items()}
+    cfg = oracle_config(dict(state_dim=8, num_actions=4, reward_range=(-5., 5.), world_model=LANDER_WM))
+    mean, var = agent.rsnorm.running_mean.cpu(), agent.rsnorm.running_variance.cpu()
+    states, rewards, uc = env.states[:T].cpu(), env.rewards.cpu(), u.cpu()
+    cache, prev_a, prev_r = None, torch.full((B, 1), -1), torch.zeros(B, 1)
+    n_safe = 0
+    for t in range(T):
+        packed = R.rsnorm_eval(torch.cat((states[t], prev_r), -1), mean, var)
+        ra, va, _, _, cache = R.wm_forward(sd, cfg, packed[:, None, :-1], prev_a, packed[:, -1:], 1., cache=cache)
+        probs, logp, _ = R.discrete_stats(ra[:, 0])
+        got_a = buf.actions[t].cpu().long()
+        margin = (probs.cumsum(-1) - uc[t][:, None]).abs().min(-1).values
+        safe = margin > 1e-4
+        assert torch.equal(got_a[safe], R.sample_inverse_cdf(probs, uc[t])[safe])
+        n_safe += int(safe.sum())
+        assert rel_err(buf.values[t].cpu(), R.hl_decode(va[:, 0], cfg)) < 5e-5
+        assert rel_err(buf.log_probs[t].cpu(), logp.gather(-1, got_a[:, None])[:, 0]) < 5e-5
+        prev_a, prev_r = got_a[:, None], rewards[t][:, None]       # follow the kernel's actions
+    assert n_safe > 0.98 * B * T
+    assert torch.equal(buf.episode_lens.cpu(), torch.full((B,), T, dtype=torch.int32))
+    assert rel_err(cum.cpu(), rewards.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize('evolutionary', (False, True))
+def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary):
+    """one minibatch of Agent.learn (dropout 0): GAE kernel + torch sequence model + fused loss kernel +
+    autograd  ==  the oracle's learn_minibatch differentiated by autograd, gradient for gradient."""
+    from importlib import import_module
+    agent_mod = import_module('x-transformers-rl_b200.agent')
+    B, T = 6, 14
+    torch.manual_seed(1)
+    kw = dict(evolutionary=True, latent_gene_pool=dict(dim=32, num_genes_per_island=3, num_selected=2, tournament_size=2),
+              num_episodes_per_update=2, batch_size=2) if evolutionary else {}
+    learner = _make(tmp_path, B, T, **kw)
+    agent, dev = learner.agent, learner.device
+    agent.batch_size = B
+    with torch.no_grad():
+        agent.model.flat_params.add_(torch.randn_like(agent.model.flat_params) * 0.1)
+        agent.rsnorm.running_mean.normal_(); agent.rsnorm.running_variance.uniform_(0.5, 2.)
+    g = torch.Generator().manual_seed(5)
+    buf = agent_mod.RolloutBuffer.allocate(T, B, 8, dev)
+    lens = torch.tensor([T, T - 3, 5, T, 2, T - 1], dtype=torch.int32)
+    tm_mask = (torch.arange(T)[:, None] < lens[None, :])
+    data = dict(states=torch.randn(T, B, 8, generator=g), actions=torch.randint(0, 4, (T, B), generator=g).int(),
+                log_probs=-torch.rand(T, B, generator=g) * 1.5, rewards=torch.randn(T, B, generator=g),
+                values=torch.randn(T, B, generator=g), is_boundary=torch.rand(T, B, generator=g) < 0.05)
+    for k, v in data.items():              # padding rows hold pad_sequence zeros, like the reference
+        v = torch.where(tm_mask if v.ndim == 2 else tm_mask[..., None], v, torch.zeros_like(v))
+        data[k] = v
+        getattr(buf, k).copy_(v)
+    buf.episode_lens.copy_(lens)
+    gene_ids = torch.tensor([0, 1, 2, 0, 1, 2], dtype=torch.int32)
+    buf.gene_ids.copy_(gene_ids)
+    agent.keep_last_grads = True
+    sd = {k: v.detach().cpu().clone().requires_grad_() for k, v in agent.model.state_dict().items() if v.is_floating_point()}
+    mean, var = agent.rsnorm.running_mean.cpu().clone(), agent.rsnorm.running_variance.cpu().clone()
+    genes = agent.gene_pool.genes.detach().cpu().clone() if evolutionary else None
+    processed = agent.learn(buf, fitnesses=None, permutations=[torch.arange(B)])
+    assert processed == int(lens.sum())
+    # oracle
+    wm = dict(LANDER_WM)
+    cfg = oracle_config(dict(state_dim=8, num_actions=4, reward_range=(-5., 5.), world_model=wm, evolutionary=evolutionary,
+                             latent_gene_pool=dict(dim=32)))
+    em = lambda t: t.transpose(0, 1).contiguous()
+    returns = R.calc_gae(em(data['rewards']), em(data['values']), ~em(data['is_boundary']))
+    batch = dict(states=em(data['states']), actions=em(data['actions']).long(), rewards=em(data['rewards']),
+                 old_log_probs=em(data['log_probs']), returns=returns, old_values=em(data['values']),
+                 dones=em(data['is_boundary']), gene_ids=gene_ids.long(), episode_lens=lens.long())
+    loss, logs, packed_masked = R.learn_minibatch(sd, cfg, batch, mean, var, reward_flag=1., genes=genes)
+    loss.backward()
+    # reward dropout: the product drew its own Bernoulli flag; replay the oracle with the flag it used
+    got_total = agent.last_logs[0].item()
+    if abs(got_total - loss.item()) > 1e-4 * abs(loss.item()):
+        for p in sd.values():
+            p.grad = None
+        loss, logs, packed_masked = R.learn_minibatch(sd, cfg, batch, mean, var, reward_flag=0., genes=genes)
+        loss.backward()
+    assert rel_err(torch.tensor(got_total), loss.detach()) < 1e-4
+    names = [n for n, _ in agent.model.named_parameters()]
+    offs = agent.model._offsets
+    worst = 0.
+    for n, o0, o1 in zip(names, offs[:-1], offs[1:]):
+        want = sd[n].grad if sd[n].grad is not None else torch.zeros_like(sd[n])
+        got = agent.last_grads[o0:o1].view(want.shape).cpu()
+        if want.abs().max() < 1e-7:
+            assert got.abs().max() < 1e-6, n
+            continue
+        worst = max(worst, rel_err(got, want))
+        assert rel_err(got, want) < 2e-3, n          # whole-model fp32 fwd+bwd on two different back ends
+    # RSNorm copy was updated from the batch mean of the already-normalised rows
+    m2, v2, _ = R.rsnorm_update(packed_masked.detach(), mean, var, 1)
+    assert rel_err(agent.rsnorm.running_mean.cpu(), m2) < 1e-4
+    assert agent.rsnorm.time == 2 and agent._step_host == 1 and agent.opt_steps == 1
+
+
+def test_vectorized_learner_runs_updates(tmp_path):
+    from importlib import import_module
+    envs = import_module('x-transformers-rl_b200.envs')
+    B, T = 32, 16
+    learner = _make(tmp_path, 8, T, num_episodes_per_update=B, epochs=2, evolutionary=True, evolve_every=1,
+                    evolve_after_step=0,
+                    latent_gene_pool=dict(dim=32, num_genes_per_island=4, num_selected=2, tournament_size=2))
+    B_total = B * 4
+    env = envs.SyntheticVecEnv(B_total, 8, T, device=learner.device, seed=1)
+    before = learner.agent.model.flat_params.clone()
+    genes_before = learner.agent.gene_pool.genes.clone()
+    learner(env, 3, seed=0)
+    assert learner.timings['env_steps'] == 3 * B_total * T
+    assert learner.timings['learn_timesteps'] == 3 * 2 * B_total * T
+    assert torch.isfinite(learner.agent.model.flat_params).all()
+    assert not torch.equal(before, learner.agent.model.flat_params)
+    assert not torch.equal(genes_before, learner.agent.gene_pool.genes)          # evolve_ ran (step > evolve_after_step)
+    assert rel_err(learner.agent.gene_pool.genes.norm(dim=-1).cpu(), torch.ones(4)) < 1e-5
+    # host-memory env: same API, states cross PCIe every step
+    henv = envs.HostVecEnv(B_total, 8, T, seed=1)
+    learner(henv, 1)
+    assert learner.timings['env_steps'] == 4 * B_total * T
+
+
+def test_bf16_learn_step(tmp_path):
+    from importlib import import_module
+    envs = import_module('x-transformers-rl_b200.envs')
+    learner = _make(tmp_path, 8, 16, num_episodes_per_update=16, accelerate_kwargs=dict(mixed_precision='bf16'))
+    env = envs.SyntheticVecEnv(16, 8, 16, device=learner.device, seed=1)
+    learner(env, 2, seed=0)
+    assert torch.isfinite(learner.agent.model.flat_params).all()

@@ -39,7 +39,7 @@ class WeightLayout(C.Structure):
 class StepIO(C.Structure):
     _fields_ = [(n, c_vp) for n in ('state', 'prev_action', 'prev_reward', 'pos', 'rs_mean', 'rs_var',
                                     'genes', 'gene_ids', 'uniform', 'forced_action')] + [
-        ('reward_flag', c_f32)] + [(n, c_vp) for n in ('action', 'log_prob', 'value', 'raw_actions', 'value_logits')]
+        ('reward_flag', c_f32), ('pos_uniform', c_i32)] + [(n, c_vp) for n in ('action', 'log_prob', 'value', 'raw_actions', 'value_logits')]
 
 
 class LossCfg(C.Structure):

@@ -1,0 +1,287 @@
+"""Agent with the reference's interface (x_transformers_rl/x_transformers_rl.py:644-1065).
+
+Owns the online model (flat fp32 parameters), the EMA copy (a second flat buffer the rollout kernel
+reads), AdoptAtan2 state (three more flat buffers), RSNorm statistics and the gene pool.
+`learn` = GAE kernel -> epochs x minibatches of [torch sequence model fwd -> fused loss kernel
+(fwd+bwd) -> autograd through the model -> one flat-gradient all-reduce -> optimiser/EMA kernel].
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from dataclasses import dataclass
+from pathlib import Path
+
+import torch
+import torch.nn.functional as F
+from torch import nn, tensor
+
+from . import ops
+from .distributed import Accelerator, all_reduce_mean_, is_distributed
+from .evolution import LatentGenePool
+from .model import FusedPPOLoss, WorldModelActorCritic
+from .schedule import EmaSchedule
+
+Memory = namedtuple('Memory', ['state', 'action', 'action_log_prob', 'reward', 'is_boundary', 'value'])
+
+
+@dataclass
+class RolloutBuffer:
+    """device-resident trajectories of one learning update, TIME-major as the step kernel writes them:
+    states (T,B,S) f32, actions (T,B) i32, log_probs (T,B), rewards (T,B), is_boundary (T,B) bool,
+    values (T,B) scalar HL-Gauss expectations; episode_lens (B,) i32, gene_ids (B,) i32."""
+    states: torch.Tensor
+    actions: torch.Tensor
+    log_probs: torch.Tensor
+    rewards: torch.Tensor
+    is_boundary: torch.Tensor
+    values: torch.Tensor
+    episode_lens: torch.Tensor
+    gene_ids: torch.Tensor
+
+    @classmethod
+    def allocate(cls, T, B, S, device):
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, device=device, dtype=dt)
+        return cls(z(T, B, S), z(T, B, dt=torch.int32), z(T, B), z(T, B), z(T, B, dt=torch.bool), z(T, B),
+                   z(B, dt=torch.int32), z(B, dt=torch.int32))
+
+    @classmethod
+    def cat(cls, bufs):
+        if len(bufs) == 1:
+            return bufs[0]
+        c = lambda name, dim: torch.cat([getattr(b, name) for b in bufs], dim=dim)
+        return cls(c('states', 1), c('actions', 1), c('log_probs', 1), c('rewards', 1), c('is_boundary', 1),
+                   c('values', 1), c('episode_lens', 0), c('gene_ids', 0))
+
+
+class RSNorm(nn.Module):
+    """running mean / variance of (state || prev reward), x_transformers_rl.py:565-612.  The eval
+    normalisation itself is fused into the kernels; this module only holds and updates the statistics."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.dim, self.eps = dim, eps
+        self.register_buffer('step', tensor(1))
+        self.register_buffer('running_mean', torch.zeros(dim))
+        self.register_buffer('running_variance', torch.ones(dim))
+        self.time = 1                    # host mirror of `step`: no .item() sync on the hot path
+
+    def normalize(self, x):
+        return (x - self.running_mean) / self.running_variance.sqrt().clamp(min=self.eps)
+
+    @torch.no_grad()
+    def update_(self, batch_mean):
+        """the train-branch update (:598-610) given the (already all-reduced) batch mean."""
+        t = float(self.time)
+        delta = batch_mean - self.running_mean
+        self.running_variance.copy_((t - 1) / t * (self.running_variance + delta ** 2 / t))
+        self.running_mean.add_(delta / t)
+        self.step.add_(1)
+        self.time += 1
+
+    def copy_from(self, other):
+        self.running_mean.copy_(other.running_mean); self.running_variance.copy_(other.running_variance)
+        self.step.copy_(other.step); self.time = other.time
+
+
+class Hiddens:
+    """opaque recurrent state returned by Agent.forward (the KV cache of one env)."""
+
+    def __init__(self, stepper):
+        self.stepper = stepper
+
+
+class Agent(nn.Module):
+    def __init__(self, state_dim, num_actions, reward_range, epochs, max_timesteps, batch_size, lr, betas, lam, gamma,
+                 beta_s, regen_reg_rate, cautious_factor, eps_clip, value_clip, ema_decay, continuous_actions=False,
+                 squash_continuous=True, critic_pred_num_bins=100, hidden_dim=48, evolutionary=False, evolve_every=1,
+                 evolve_after_step=20, latent_gene_pool=None, world_model=None, dropout=0.25, max_grad_norm=0.5,
+                 frac_actor_critic_head_gradient=0.5, ema_kwargs=None, save_path='./ppo.pt', accelerator=None,
+                 actor_loss_weight=1., critic_loss_weight=1., autoregressive_loss_weight=1.,
+                 rollout_positions='reference', kv_cache_dtype='fp32'):
+        super().__init__()
+        if continuous_actions:
+            raise NotImplementedError('continuous actions are outside the B200 hot path built so far (SURVEY 8f row 4); '
+                                      'there is no fallback')
+        latent_gene_pool = latent_gene_pool if latent_gene_pool is not None else dict(
+            dim=128, num_genes_per_island=3, num_selected=2, tournament_size=2)
+        world_model = world_model if world_model is not None else dict(
+            attn_dim_head=16, heads=4, depth=4, attn_gate_values=True, add_value_residual=True,
+            learned_value_residual_mix=True)
+        ema_kwargs = ema_kwargs if ema_kwargs is not None else dict(update_model_with_ema_every=1250)
+        self.accelerator = accelerator if accelerator is not None else Accelerator()
+        device = self.accelerator.device
+        if device.type != 'cuda':
+            raise ops.L.XtrlError('Agent needs a CUDA device: the hot path has no CPU fallback')
+
+        self.model_dim = hidden_dim
+        self.evolutionary, self.evolve_every, self.evolve_after_step = evolutionary, evolve_every, evolve_after_step
+        self.gene_pool = LatentGenePool(**latent_gene_pool) if evolutionary else None
+        self.cfg = ops.ModelConfig.from_learner_kwargs(
+            state_dim, num_actions, reward_range, max_timesteps, world_model, hidden_dim=hidden_dim,
+            num_bins=critic_pred_num_bins, dim_gene=self.gene_pool.dim_gene if evolutionary else 0,
+            rotary_true_pos=(rollout_positions == 'true'), kv_bf16=(kv_cache_dtype == 'bf16'))
+        self.model = WorldModelActorCritic(self.cfg, dropout=dropout,
+                                           frac_actor_critic_head_gradient=frac_actor_critic_head_gradient)
+        self.loss_cfg = ops.LossConfig(num_actions=num_actions, num_bins=critic_pred_num_bins, state_dim=state_dim,
+                                       reward_range=tuple(reward_range), eps_clip=eps_clip, value_clip=value_clip,
+                                       entropy_weight=beta_s, actor_weight=actor_loss_weight,
+                                       critic_weight=critic_loss_weight, autoreg_weight=autoregressive_loss_weight)
+        self.rsnorm = RSNorm(state_dim + 1)
+        self.continuous_actions = continuous_actions
+        self.max_grad_norm = max_grad_norm
+        self.batch_size, self.epochs, self.lam, self.gamma, self.beta_s = batch_size, epochs, lam, gamma, beta_s
+        self.eps_clip, self.value_clip = eps_clip, value_clip
+        self.lr, self.betas, self.regen_reg_rate, self.cautious_factor = lr, tuple(betas), regen_reg_rate, cautious_factor
+        self.save_path = Path(save_path)
+        self.actor_loss_weight, self.critic_loss_weight = actor_loss_weight, critic_loss_weight
+        self.autoregressive_loss_weight = autoregressive_loss_weight
+        self.register_buffer('step', tensor(0))
+        self._step_host = 0
+        self.to(device)
+
+        # optimiser / EMA state: flat fp32 buffers parallel to model.flat_params
+        n = self.model.flat_params.numel()
+        z = lambda: torch.zeros(n, device=device, dtype=torch.float32)
+        self.opt_m, self.opt_v, self.opt_param_init = z(), z(), z()
+        self.ema_params = self.model.flat_params.clone()      # EMA(model) starts as a deep copy (:747)
+        self.ema_schedule = EmaSchedule(beta=ema_decay, **ema_kwargs)
+        self.opt_steps = 0
+        self._opt_ws = torch.empty(ops.L.load().xtrl_opt_workspace_bytes(len(self.model._offsets) - 1) // 8,
+                                   device=device, dtype=torch.float64)
+        # gradient all-reduce buffer: [flat grads | RSNorm batch mean] so one collective carries both
+        self._comm = torch.zeros(n + state_dim + 1, device=device, dtype=torch.float32)
+        self.model._bind(self.model.flat_params, self._comm[:n])
+        self.last_logs = None
+        self.keep_last_grads = False
+        self.last_grads = None
+
+    @property
+    def device(self):
+        return self.step.device
+
+    # ---- weights for the rollout kernel ------------------------------------------------------
+    def ema_state_dict(self):
+        return self.model.state_dict_from_flat(self.ema_params)
+
+    def save(self):
+        if not self.accelerator.is_main_process:
+            return
+        torch.save({'model': self.model.state_dict()}, str(self.save_path))
+
+    def load(self):
+        if not self.save_path.exists():
+            return
+        data = torch.load(str(self.save_path), weights_only=True)
+        self.model.load_state_dict(data['model'])
+
+    # ---- learn ---------------------------------------------------------------------------------
+    def _buffer_from_memories(self, memories, episode_lens, gene_ids):
+        """reference format (list of episodes, each a list of Memory with value LOGITS) -> episode-major
+        tensors, padded like pad_sequence (:822-837)."""
+        dev = self.device
+        eps = []
+        for episode in memories:
+            cols = list(zip(*episode))
+            eps.append([torch.stack([torch.as_tensor(v) for v in col]).to(dev) for col in cols])
+        pad = lambda i: nn.utils.rnn.pad_sequence([e[i] for e in eps], batch_first=True)
+        states, actions, logp, rewards, bd, values = (pad(i) for i in range(6))
+        if values.ndim == 3:
+            values = ops.hl_decode(values.float().contiguous(), self.cfg.reward_range)       # :843
+        return dict(states=states.float(), actions=actions.int(), old_log_probs=logp.float(), rewards=rewards.float(),
+                    dones=bd.bool(), old_values=values.float(), lens=episode_lens.to(dev).int(),
+                    gene_ids=gene_ids.to(dev).int(), time_major=False)
+
+    def learn(self, memories, episode_lens=None, gene_ids=None, fitnesses=None, permutations=None):
+        """reference signature (:808-814).  `memories` is either the reference's list[list[Memory]] or a
+        RolloutBuffer (vectorised rollouts).  permutations: optional list (one per epoch) of episode
+        orders, for tests that must replay the reference's DataLoader shuffle."""
+        cfg, dev, model = self.cfg, self.device, self.model
+        if isinstance(memories, RolloutBuffer):
+            buf = memories
+            returns_tm = ops.gae(buf.rewards, buf.values, buf.is_boundary, self.gamma, self.lam, time_major=True)
+            em = lambda t: t.transpose(0, 1).contiguous()
+            data = dict(states=em(buf.states), actions=em(buf.actions), old_log_probs=em(buf.log_probs),
+                        rewards=em(buf.rewards), dones=em(buf.is_boundary), old_values=em(buf.values),
+                        returns=em(returns_tm), lens=buf.episode_lens, gene_ids=buf.gene_ids)
+        else:
+            data = self._buffer_from_memories(memories, episode_lens, gene_ids)
+            data.pop('time_major')
+            data['returns'] = ops.gae(data['rewards'].contiguous(), data['old_values'].contiguous(),
+                                      data['dones'].contiguous(), self.gamma, self.lam)
+        E, T = data['actions'].shape
+        S = cfg.state_dim
+        n = model.flat_params.numel()
+        rs_copy = RSNorm(S + 1).to(dev)
+        rs_copy.copy_from(self.rsnorm)
+        model.train()
+        autocast = torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.accelerator.mixed_precision == 'bf16')
+        arange_t = torch.arange(T, device=dev)
+        self.last_grads = None
+        for epoch in range(self.epochs):
+            perm = permutations[epoch].to(dev) if permutations is not None else torch.randperm(E, device=dev)
+            for lo in range(0, E, self.batch_size):
+                idx = perm[lo:lo + self.batch_size]
+                b = idx.numel()
+                states, actions, rewards = data['states'][idx], data['actions'][idx], data['rewards'][idx]
+                lens = data['lens'][idx].contiguous()
+                mask = arange_t[None, :] < lens[:, None]                                              # :908-909
+                prev_actions = F.pad(actions, (1, -1), value=-1)                                     # :911-916
+                prev_rewards = F.pad(rewards, (1, -1), value=0.)                                     # :918
+                packed = self.rsnorm.normalize(torch.cat((states, prev_rewards[..., None]), dim=-1))  # :920-926
+                gene = self.gene_pool[data['gene_ids'][idx].long()] if self.evolutionary else None   # :906
+                flag = float(torch.rand(()) >= 0.5) if model.training else 1.                        # reward dropout :501
+                with autocast:
+                    ra, vl, spr, dl = model(packed[..., :S], packed[..., S], prev_actions.long(), actions.long(), mask,
+                                            latent_gene=gene, reward_flag=flag)
+                loss, scalars = FusedPPOLoss.apply(self.loss_cfg, ra, vl, spr, dl, actions.contiguous(),
+                                                   data['old_log_probs'][idx].contiguous(), data['returns'][idx].contiguous(),
+                                                   data['old_values'][idx].contiguous(), packed.contiguous(),
+                                                   data['dones'][idx].contiguous(), lens)
+                loss.backward()
+                # RSNorm batch mean over the masked rows rides in the tail of the gradient buffer (:1005, :601)
+                mf = mask[..., None].float()
+                self._comm[n:] = (packed * mf).sum(dim=(0, 1)) / mf.sum().clamp(min=1.)
+                all_reduce_mean_(self._comm)
+                if self.keep_last_grads:
+                    self.last_grads = model.flat_grads.clone()
+                self._optimizer_step()
+                rs_copy.update_(self._comm[n:])
+                self.last_logs = scalars
+                if (self.evolutionary and fitnesses is not None and self._step_host > self.evolve_after_step
+                        and self._step_host % self.evolve_every == 0):                                # :1009-1015
+                    self.gene_pool.evolve_(fitnesses)
+                self.accelerator.log(dict(losses=scalars))
+        self.rsnorm.copy_from(rs_copy)
+        self.step.add_(1)
+        self._step_host += 1
+        return self.epochs * int(data['lens'].sum().item())        # learn-timesteps processed
+
+    def _optimizer_step(self):
+        model = self.model
+        mode, decay, back = self.ema_schedule.next()
+        ops.adopt_atan2_step(model.flat_params, model.flat_grads, self.opt_m, self.opt_v, self.opt_param_init,
+                             self.ema_params, model.seg_offsets, lr=self.lr, init_lr=self.lr, betas=self.betas,
+                             regen_rate=self.regen_reg_rate, cautious_factor=self.cautious_factor,
+                             max_grad_norm=self.max_grad_norm, first_step=(self.opt_steps == 0), ema_mode=mode,
+                             ema_decay=decay, copy_ema_to_online=back, workspace=self._opt_ws)
+        self.opt_steps += 1
+        model.flat_grads.zero_()
+
+    # ---- deploy --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, state, reward=None, hiddens=None, latent_gene_id=0):
+        """(:1025-1065) one env, one step, ONLINE weights; returns (raw_actions (A,), hiddens)."""
+        dev, cfg = self.device, self.cfg
+        if hiddens is None:
+            st = ops.WorldModelStepper(cfg, 1, dev)
+            st.load_state_dict(self.model.state_dict())
+            hiddens = Hiddens(st)
+        st = hiddens.stepper
+        state = torch.as_tensor(state, dtype=torch.float32).to(dev).reshape(1, cfg.state_dim).contiguous()
+        has_reward = reward is not None
+        prev_r = torch.as_tensor(float(reward) if has_reward else 0., dtype=torch.float32, device=dev).reshape(1)
+        out = st.step(state, torch.full((1,), -1, dtype=torch.int32, device=dev), prev_r, self.rsnorm.running_mean,
+                      self.rsnorm.running_variance, genes=self.gene_pool.genes.data if self.evolutionary else None,
+                      gene_ids=torch.full((1,), int(latent_gene_id), dtype=torch.int32, device=dev) if self.evolutionary else None,
+                      reward_flag=1. if has_reward else 0., want_logits=True)
+        return out['raw_actions'][0].clone(), hiddens

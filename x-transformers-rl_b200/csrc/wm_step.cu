@@ -313,7 +313,7 @@ wm_step_kernel(const StepArgs a) {
             for (int i = tid; i < kTE * H * 4 * 2; i += kThreads) {
                 const int which = i & 1, pr = (i >> 1) & 3, eh = i >> 3, e = eh / H, h = eh - e * H;
                 const int env = env0 + e;
-                const float p = env < a.B ? (float)__ldg(a.io.pos + env) : 0.f;
+                const float p = env < a.B ? (float)(a.io.pos ? __ldg(a.io.pos + env) : a.io.pos_uniform) : 0.f;
                 const float ang = p * powf(10000.f, -(float)(2 * pr) / 8.f);
                 float sn, cs;
                 sincosf(ang, &sn, &cs);
@@ -329,7 +329,7 @@ wm_step_kernel(const StepArgs a) {
         for (int eh = warp; eh < kTE * H; eh += kThreads / 32) {
             const int e = eh / H, h = eh - e * H, env = env0 + e;
             if (env >= a.B) continue;
-            const int len = min(__ldg(a.io.pos + env), d.Tmax - 1);   // keys already cached
+            const int len = min(a.io.pos ? __ldg(a.io.pos + env) : a.io.pos_uniform, d.Tmax - 1);   // keys already cached
             KV *kc = kvbase + (((int64_t)l * a.B + env) * H + h) * kv_head_stride;
             KV *vc = kc + kv_half;
             const float *qs = sqkv + e * NQ + h * kDH;
@@ -489,8 +489,10 @@ extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, v
     XTRL_REQUIRE(io && weights && kv_cache, XTRL_E_BADARG, "xtrl_wm_step: null pointer");
     XTRL_REQUIRE(num_envs >= 0, XTRL_E_BADARG, "xtrl_wm_step: num_envs=%d", num_envs);
     if (num_envs == 0) return XTRL_OK;
-    XTRL_REQUIRE(io->state && io->prev_action && io->prev_reward && io->pos && io->rs_mean && io->rs_var,
+    XTRL_REQUIRE(io->state && io->prev_action && io->prev_reward && io->rs_mean && io->rs_var,
                  XTRL_E_BADARG, "xtrl_wm_step: null required input");
+    XTRL_REQUIRE(io->pos || (io->pos_uniform >= 0 && io->pos_uniform < desc->max_timesteps), XTRL_E_BADARG,
+                 "xtrl_wm_step: pos_uniform=%d outside [0, max_timesteps=%d)", io->pos_uniform, desc->max_timesteps);
     XTRL_REQUIRE(desc->dim_gene == 0 || (io->genes && io->gene_ids), XTRL_E_BADARG,
                  "xtrl_wm_step: evolutionary model needs genes and gene_ids");
     StepArgs a;

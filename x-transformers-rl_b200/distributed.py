@@ -1,0 +1,102 @@
+"""One process per GPU; torch.distributed (NCCL over NVLink 5 / NVSwitch on the box, gloo in the CPU
+tests) is the plumbing.  The data path shards by episode and needs exactly four small collectives
+ -- replacing accelerate + x_transformers_rl/distributed.py:1-99 of the reference:
+
+  sync_seed            all-reduce(sum) of one random int64          distributed.py:42-48, :1211
+  reduce_fitness       all-gather of per-rank (num_genes,) partials, summed in rank order (bit-identical
+                       on every rank, unlike a ring all-reduce)     x_transformers_rl.py:1362
+  all_reduce_grads     ONE all-reduce of the flat fp32 gradient buffer (+ the RSNorm batch mean packed in
+                       its tail), averaged                          DDP in accelerator.prepare :885, :601
+  barrier                                                          :1359
+
+Nothing here touches CUDA directly: it works on whatever device the tensors live on, so the same code
+runs under gloo on CPU tensors in tests/test_distributed_cpu.py.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def is_distributed() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class Accelerator:
+    """the slice of accelerate.Accelerator the reference touches (x_transformers_rl.py:1106,
+    train_lander.py:56): .device, .is_main_process, .num_processes, .process_index,
+    .wait_for_everyone(), .reduce(), .log().  Launch with torchrun; rank / world come from the env."""
+
+    def __init__(self, device=None, mixed_precision=None, backend=None, cpu=False, **unknown):
+        if unknown:
+            raise TypeError(f'accelerate_kwargs {sorted(unknown)} are not supported')
+        world = int(os.environ.get('WORLD_SIZE', '1'))
+        if world > 1 and not (dist.is_available() and dist.is_initialized()):
+            use_cuda = torch.cuda.is_available() and not cpu
+            if use_cuda:
+                torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+            dist.init_process_group(backend or ('nccl' if use_cuda else 'gloo'))
+        self.num_processes = dist.get_world_size() if is_distributed() else 1
+        self.process_index = dist.get_rank() if is_distributed() else 0
+        self.is_main_process = self.process_index == 0
+        if device is not None:
+            self.device = torch.device(device)
+        elif torch.cuda.is_available() and not cpu:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        else:
+            self.device = torch.device('cpu')
+        if mixed_precision not in (None, 'no', 'bf16'):
+            raise ValueError(f"mixed_precision={mixed_precision!r}: only None/'no'/'bf16'")
+        self.mixed_precision = None if mixed_precision in (None, 'no') else 'bf16'
+        self.last_logs = None
+
+    def wait_for_everyone(self):
+        if is_distributed():
+            dist.barrier()
+
+    def reduce(self, t, reduction='sum'):
+        out = reduce_fitness(t)
+        return out / self.num_processes if reduction == 'mean' else out
+
+    def log(self, logs):              # no tracker configured in the reference either
+        self.last_logs = logs
+
+
+def sync_seed(device, max_size=int(1e6)) -> int:
+    """every rank draws an int, the sum is the shared seed (reference distributed.py:42-48)."""
+    rand = torch.randint(0, max_size, (), device=device if torch.device(device).type == 'cuda' else 'cpu')
+    if is_distributed():
+        dist.all_reduce(rand)
+    return int(rand.item())
+
+
+def reduce_fitness(partial: torch.Tensor) -> torch.Tensor:
+    """sum of per-rank partial fitness, deterministic: all-gather then add in rank order."""
+    if not is_distributed():
+        return partial
+    parts = [torch.empty_like(partial) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, partial.contiguous())
+    out = torch.zeros_like(partial)
+    for p in parts:
+        out += p
+    return out
+
+
+def all_reduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    """in-place mean all-reduce of one flat buffer (gradients [+ RSNorm batch mean in the tail])."""
+    if is_distributed():
+        dist.all_reduce(flat)
+        flat.div_(dist.get_world_size())
+    return flat
+
+
+def shard_episode_genes(num_episodes_per_update: int, num_genes: int, num_processes: int, process_index: int):
+    """the (episode, gene) pairs this rank rolls out: cartesian_prod(...).chunk(world)[rank]
+    (x_transformers_rl.py:1146-1154)."""
+    pairs = torch.cartesian_prod(torch.arange(num_episodes_per_update), torch.arange(num_genes))
+    if pairs.ndim == 1:
+        pairs = pairs[:, None]
+    assert pairs.size(0) >= num_processes
+    return pairs.chunk(num_processes, dim=0)[process_index].tolist()

@@ -1,0 +1,231 @@
+"""Learner with the reference's constructor and call signature
+(x_transformers_rl/x_transformers_rl.py:1069-1380):
+
+    learner = Learner(state_dim, num_actions, reward_range, max_timesteps=..., world_model=dict(...))
+    learner(env, num_learning_updates)
+
+The rollout loop is re-architected: instead of batch-1 episodes with ~10 host syncs per step, all
+episodes of an update advance in lock step, one xtrl_wm_step launch per timestep, trajectories stay
+on the device.  A vectorised env (`num_envs` attribute, see envs.py) is stepped B-wide; a plain env
+keeps the reference's one-episode-at-a-time semantics through the same kernel with B = 1.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .agent import Agent, Memory, RolloutBuffer  # noqa: F401
+from .distributed import Accelerator, reduce_fitness, shard_episode_genes, sync_seed
+
+
+def _to_device_state(x, device, pinned=None):
+    if torch.is_tensor(x):
+        return x.to(device=device, dtype=torch.float32, non_blocking=True)
+    x = np.asarray(x, dtype=np.float32)
+    if pinned is not None:
+        pinned.copy_(torch.from_numpy(x).reshape(pinned.shape))
+        return pinned.to(device, non_blocking=True)
+    return torch.from_numpy(x).to(device)
+
+
+class Learner(nn.Module):
+    def __init__(self, state_dim, num_actions, reward_range, world_model: dict, continuous_actions=False,
+                 squash_continuous=True, continuous_actions_clamp=None, evolutionary=False, evolve_every=10,
+                 evolve_after_step=20, latent_gene_pool=None, max_timesteps=500, batch_size=8,
+                 num_episodes_per_update=64, lr=0.0008, betas=(0.9, 0.99), lam=0.95, gamma=0.99, eps_clip=0.2,
+                 value_clip=0.4, beta_s=.01, regen_reg_rate=1e-4, cautious_factor=0.1, epochs=4, ema_decay=0.9,
+                 save_every=100, frac_actor_critic_head_gradient=0.5, accelerate_kwargs: dict = dict(),
+                 agent_kwargs: dict = dict()):
+        super().__init__()
+        assert num_episodes_per_update % batch_size == 0
+        self.accelerator = Accelerator(**accelerate_kwargs)
+        self.agent = Agent(state_dim=state_dim, num_actions=num_actions, continuous_actions=continuous_actions,
+                           squash_continuous=squash_continuous, reward_range=reward_range, world_model=world_model,
+                           evolutionary=evolutionary, evolve_every=evolve_every, evolve_after_step=evolve_after_step,
+                           latent_gene_pool=latent_gene_pool, epochs=epochs, max_timesteps=max_timesteps,
+                           batch_size=batch_size, lr=lr, betas=betas, lam=lam, gamma=gamma, beta_s=beta_s,
+                           regen_reg_rate=regen_reg_rate, cautious_factor=cautious_factor, eps_clip=eps_clip,
+                           value_clip=value_clip, ema_decay=ema_decay,
+                           frac_actor_critic_head_gradient=frac_actor_critic_head_gradient,
+                           accelerator=self.accelerator, **agent_kwargs)
+        self.num_episodes_per_update, self.max_timesteps = num_episodes_per_update, max_timesteps
+        num_genes = self.agent.gene_pool.num_genes if self.agent.gene_pool is not None else 1
+        self.episode_genes_for_process = shard_episode_genes(num_episodes_per_update, num_genes,
+                                                             self.accelerator.num_processes,
+                                                             self.accelerator.process_index)
+        self.num_actions, self.continuous_actions = num_actions, continuous_actions
+        self.continuous_actions_clamp = continuous_actions_clamp
+        self.save_every = save_every
+        self._steppers = {}
+        self.timings = dict(rollout_s=0., learn_s=0., env_steps=0, learn_timesteps=0)
+
+    @property
+    def device(self):
+        return self.accelerator.device
+
+    def _stepper(self, num_envs, max_timesteps):
+        key = (num_envs, max_timesteps)
+        if key not in self._steppers:
+            cfg = self.agent.cfg
+            if max_timesteps > cfg.max_timesteps:
+                raise ops.L.XtrlError(f'max_timesteps={max_timesteps} exceeds the KV-cache capacity {cfg.max_timesteps}')
+            self._steppers = {key: ops.WorldModelStepper(cfg, num_envs, self.device)}     # one live KV cache at a time
+        return self._steppers[key]
+
+    # ---- vectorised rollout: B envs in lock step, one kernel launch per timestep -------------------
+    @torch.no_grad()
+    def rollout_vectorized(self, env, gene_ids, max_timesteps, seed=None, uniforms=None):
+        """returns (RolloutBuffer (T,B,..), cumulative_rewards (B,)).  Sampling consumes `uniforms`
+        (T,B) in [0,1) -- drawn here from torch's CUDA generator unless given (parity tests)."""
+        agent, dev, cfg = self.agent, self.device, self.agent.cfg
+        B, T, S = env.num_envs, max_timesteps, cfg.state_dim
+        st = self._stepper(B, max_timesteps)
+        st.load_state_dict(agent.ema_state_dict())               # rollouts read the EMA weights (:1194)
+        buf = RolloutBuffer.allocate(T, B, S, dev)
+        buf.gene_ids.copy_(gene_ids)
+        u = torch.rand(T, B, device=dev) if uniforms is None else uniforms
+        first_a = torch.full((B,), -1, dtype=torch.int32, device=dev)     # :1244
+        first_r = torch.zeros(B, device=dev)                              # :1246
+        pin_s = pin_r = None
+        state = env.reset(**({} if seed is None else dict(seed=seed)))
+        if isinstance(state, tuple):
+            state = state[0]
+        if not torch.is_tensor(state):
+            pin_s = torch.empty(B, S, dtype=torch.float32).pin_memory()
+            pin_r = torch.empty(B, dtype=torch.float32).pin_memory()
+        never_done = getattr(env, 'never_terminates', False)
+        alive = torch.ones(B, dtype=torch.bool, device=dev)
+        lens = torch.zeros(B, dtype=torch.int32, device=dev)
+        genes = agent.gene_pool.genes.data if agent.evolutionary else None
+        rs_mean, rs_var = agent.rsnorm.running_mean, agent.rsnorm.running_variance
+        pad_value = float(sum(cfg.reward_range)) / 2.     # decode of all-zero logits = mean of the bin centres
+        for t in range(T):
+            buf.states[t].copy_(_to_device_state(state, dev, pin_s), non_blocking=True)
+            out = dict(action=buf.actions[t], log_prob=buf.log_probs[t], value=buf.values[t])
+            st.step(buf.states[t], first_a if t == 0 else buf.actions[t - 1], first_r if t == 0 else buf.rewards[t - 1],
+                    rs_mean, rs_var, uniform=u[t], genes=genes, gene_ids=buf.gene_ids if genes is not None else None,
+                    out=out, pos_uniform=t)
+            action = buf.actions[t]
+            step_out = env.step(action if pin_s is None else action.cpu().numpy())     # host env: D2H sync
+            if len(step_out) >= 4:
+                state, reward, terminated, truncated = step_out[:4]
+            elif len(step_out) == 3:
+                state, reward, terminated = step_out
+                truncated = None
+            else:
+                raise RuntimeError('invalid number of returns from environment .step')
+            if torch.is_tensor(reward):
+                buf.rewards[t].copy_(reward, non_blocking=True)
+            else:
+                pin_r.copy_(torch.from_numpy(np.asarray(reward, dtype=np.float32).reshape(B)))
+                buf.rewards[t].copy_(pin_r, non_blocking=True)
+            if not never_done:
+                term = torch.as_tensor(terminated, device=dev).bool()
+                done = term if truncated is None else term | torch.as_tensor(truncated, device=dev).bool()
+                buf.is_boundary[t] = term & alive
+                # finished envs keep stepping (lock step) but their rows become pad_sequence padding (:837)
+                dead = ~alive
+                buf.states[t].masked_fill_(dead[:, None], 0.); buf.actions[t].masked_fill_(dead, 0)
+                buf.log_probs[t].masked_fill_(dead, 0.); buf.rewards[t].masked_fill_(dead, 0.)
+                buf.values[t].masked_fill_(dead, pad_value)
+                lens += alive.int()
+                alive = alive & ~done
+        if never_done:
+            lens.fill_(T)
+        buf.episode_lens.copy_(lens)
+        return buf, buf.rewards.sum(dim=0)
+
+    # ---- plain env: reference semantics, one episode at a time (:1220-1355) -------------------------
+    @torch.no_grad()
+    def rollout_episode(self, env, gene_id, max_timesteps, reset_kwargs):
+        agent, dev, cfg = self.agent, self.device, self.agent.cfg
+        st = self._stepper(1, max_timesteps)
+        st.reset()
+        reset_out = env.reset(**reset_kwargs)
+        state = reset_out[0] if isinstance(reset_out, tuple) else reset_out
+        genes = agent.gene_pool.genes.data if agent.evolutionary else None
+        gid = torch.full((1,), int(gene_id), dtype=torch.int32, device=dev)
+        prev_a = torch.full((1,), -1, dtype=torch.int32, device=dev)
+        prev_r = torch.zeros(1, device=dev)
+        memories, cumulative = [], 0.
+        for timestep in range(max_timesteps):
+            s = torch.as_tensor(np.asarray(state, dtype=np.float32) if not torch.is_tensor(state) else state,
+                                dtype=torch.float32).to(dev).reshape(1, cfg.state_dim).contiguous()
+            out = st.step(s, prev_a, prev_r, agent.rsnorm.running_mean, agent.rsnorm.running_variance,
+                          uniform=torch.rand(1, device=dev), genes=genes, gene_ids=gid if genes is not None else None)
+            action = out['action'].clone()
+            step_out = env.step(action.tolist()[0])
+            if len(step_out) >= 4:
+                state, reward, terminated, truncated = step_out[:4]
+            elif len(step_out) == 3:
+                state, reward, terminated = step_out
+                truncated = False
+            else:
+                raise RuntimeError('invalid number of returns from environment .step')
+            reward = float(reward)
+            cumulative += reward
+            memories.append(Memory(s[0], action[0], out['log_prob'][0].clone(), torch.tensor(reward, device=dev),
+                                   torch.tensor(bool(terminated), device=dev), out['value'][0].clone()))
+            prev_a, prev_r = action, torch.full((1,), reward, device=dev)
+            if terminated or truncated:
+                break
+        return memories, timestep + 1, cumulative
+
+    def forward(self, env, num_learning_updates: int, seed=None, max_timesteps=None):
+        import time
+        max_timesteps = max_timesteps if max_timesteps is not None else self.max_timesteps
+        agent, dev = self.agent, self.device
+        if seed is not None:
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+        agent.eval()
+        vectorized = hasattr(env, 'num_envs')
+        pairs = self.episode_genes_for_process
+        for learning_update in range(num_learning_updates):
+            fitnesses, episode_seeds = None, None
+            if agent.evolutionary:
+                fitnesses = torch.zeros(agent.gene_pool.num_genes, device=dev)
+                torch.manual_seed(sync_seed(dev))                                              # :1211-1212
+                episode_seeds = torch.randint(0, int(1e7), (self.num_episodes_per_update,))
+            torch.cuda.synchronize(dev); t0 = time.perf_counter()
+            if vectorized:
+                B = env.num_envs
+                if len(pairs) % B != 0:
+                    raise ValueError(f'{len(pairs)} (episode, gene) pairs on this rank are not a multiple of env.num_envs={B}')
+                bufs = []
+                for w in range(0, len(pairs), B):
+                    wave = pairs[w:w + B]
+                    gids = torch.tensor([p[1] for p in wave], dtype=torch.int32, device=dev)
+                    wave_seed = int(episode_seeds[wave[0][0]]) if episode_seeds is not None else None
+                    buf, cum = self.rollout_vectorized(env, gids, max_timesteps, seed=wave_seed)
+                    if fitnesses is not None:
+                        fitnesses.index_add_(0, gids.long(), cum)                              # :1345-1346
+                    bufs.append(buf)
+                memories = RolloutBuffer.cat(bufs)
+                lens_t = gids_t = None
+                steps = len(pairs) * max_timesteps
+            else:
+                memories, lens, gids = [], [], []
+                for episode, gene_id in pairs:
+                    kw = dict(seed=int(episode_seeds[episode])) if episode_seeds is not None else {}
+                    mem, n, cum = self.rollout_episode(env, gene_id, max_timesteps, kw)
+                    if fitnesses is not None:
+                        fitnesses[gene_id] += cum
+                    memories.append(mem); lens.append(n); gids.append(gene_id)
+                lens_t, gids_t = torch.tensor(lens, device=dev), torch.tensor(gids, device=dev)
+                steps = sum(lens)
+            self.accelerator.wait_for_everyone()                                               # :1359
+            if fitnesses is not None:
+                fitnesses = reduce_fitness(fitnesses)                                          # :1362
+            torch.cuda.synchronize(dev); t1 = time.perf_counter()
+            learned = agent.learn(memories, lens_t, gids_t, fitnesses)                         # :1364
+            torch.cuda.synchronize(dev); t2 = time.perf_counter()
+            self.timings['rollout_s'] += t1 - t0; self.timings['learn_s'] += t2 - t1
+            self.timings['env_steps'] += steps; self.timings['learn_timesteps'] += learned
+            if learning_update % self.save_every == 0:
+                agent.save()
+        agent.save()
+        if self.accelerator.is_main_process:
+            print('training complete')

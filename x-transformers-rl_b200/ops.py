@@ -318,8 +318,9 @@ class WorldModelStepper:
         self.pos.zero_()
 
     def step(self, state, prev_action, prev_reward, rs_mean, rs_var, *, uniform=None, forced_action=None,
-             genes=None, gene_ids=None, reward_flag=1., out=None, want_logits=False, advance=True):
+             genes=None, gene_ids=None, reward_flag=1., out=None, want_logits=False, advance=True, pos_uniform=None):
         """state (B,S) f32; prev_action (B,) i32 (-1 none); prev_reward (B,) f32; uniform (B,) f32.
+        pos_uniform: int -> every env is at that timestep (lock-step rollout; self.pos is not read or advanced).
         Returns dict(action i32, log_prob, value[, raw_actions, value_logits])."""
         if self.weights is None:
             raise L.XtrlError('WorldModelStepper: load_state_dict() first')
@@ -334,14 +335,14 @@ class WorldModelStepper:
             out.setdefault('raw_actions', torch.empty(B, cfg.num_actions, device=dev))
             out.setdefault('value_logits', torch.empty(B, cfg.num_bins, device=dev))
         io = L.StepIO(_ptr(state, torch.float32, 'state'), _ptr(prev_action, torch.int32, 'prev_action'),
-                      _ptr(prev_reward, torch.float32, 'prev_reward'), _ptr(self.pos, torch.int32),
+                      _ptr(prev_reward, torch.float32, 'prev_reward'), _ptr(self.pos if pos_uniform is None else None, torch.int32),
                       _ptr(rs_mean, torch.float32, 'rs_mean'), _ptr(rs_var, torch.float32, 'rs_var'),
                       _ptr(genes, torch.float32, 'genes'), _ptr(gene_ids, torch.int32, 'gene_ids'),
                       _ptr(uniform, torch.float32, 'uniform'), _ptr(forced_action, torch.int32, 'forced_action'),
-                      float(reward_flag), _ptr(out['action']), _ptr(out['log_prob']), _ptr(out['value']),
+                      float(reward_flag), int(pos_uniform or 0), _ptr(out['action']), _ptr(out['log_prob']), _ptr(out['value']),
                       _ptr(out.get('raw_actions')), _ptr(out.get('value_logits')))
         L.check(self.lib.xtrl_wm_step(C.byref(self.desc), _ptr(self.weights), _ptr(self.kv_cache), C.byref(io), B,
                                       _stream()), 'xtrl_wm_step')
-        if advance:
+        if advance and pos_uniform is None:
             self.pos.add_(1)
         return out
