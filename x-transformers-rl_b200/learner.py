@@ -208,6 +208,7 @@ class Learner(nn.Module):
                 steps = len(pairs) * max_timesteps
             else:
                 memories, lens, gids = [], [], []
+                self._stepper(1, max_timesteps).load_state_dict(agent.ema_state_dict())   # EMA weights (:1194)
                 for episode, gene_id in pairs:
                     kw = dict(seed=int(episode_seeds[episode])) if episode_seeds is not None else {}
                     mem, n, cum = self.rollout_episode(env, gene_id, max_timesteps, kw)
