@@ -164,7 +164,7 @@ class Learner(nn.Module):
                 truncated = False
             else:
                 raise RuntimeError('invalid number of returns from environment .step')
-            reward = float(reward)
+            reward = float(np.asarray(reward, dtype=np.float64).reshape(-1)[0])      # accepts shape-(1,) arrays (README.md:21)
             cumulative += reward
             memories.append(Memory(s[0], action[0], out['log_prob'][0].clone(), torch.tensor(reward, device=dev),
                                    torch.tensor(bool(terminated), device=dev), out['value'][0].clone()))
