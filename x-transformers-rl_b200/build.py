@@ -36,7 +36,7 @@ def source_hash() -> str:
     files.append(os.path.join(os.path.dirname(HERE), 'include', 'xtrl.h'))
     for f in files:
         h.update(f.encode()); h.update(open(f, 'rb').read())
-    h.update(' '.join(NVCC_FLAGS).encode())
+    h.update((' '.join(NVCC_FLAGS) + os.environ.get('XTRL_NVCC_EXTRA', '')).encode())
     return h.hexdigest()
 
 
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_fresh():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, '-Xptxas', '-v', '-o', LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get('XTRL_NVCC_EXTRA', '').split(), '-Xptxas', '-v', '-o', LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     with open(os.path.join(LIB_DIR, 'build.log'), 'w') as f:
         f.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)

@@ -21,9 +21,21 @@
 
 namespace xtrl {
 
-constexpr int kTE = 16;            // envs per CTA
+#ifndef XTRL_TE
+#define XTRL_TE 16
+#endif
+#ifndef XTRL_MINBLOCKS
+#define XTRL_MINBLOCKS 2
+#endif
+#ifndef XTRL_KVBUF
+#define XTRL_KVBUF 2
+#endif
+constexpr int kTE = XTRL_TE;       // envs per CTA
+constexpr int kMinBlocks = XTRL_MINBLOCKS;   // resident CTAs per SM the register budget is sized for
+constexpr int kKvBuf = XTRL_KVBUF; // 32-key chunks in flight per warp in the attention stream
 constexpr int kThreads = 256;
 constexpr int kDH = 16;            // dim_head the kernels are built for
+constexpr int kSplitK = 64 / XTRL_TE;   // K slices of the narrow (N = D) residual layers (4 at kTE=16, 8 at kTE=8)
 
 static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
@@ -34,11 +46,11 @@ struct StepDims {
 
 static int make_dims(const xtrl_model_desc *d, StepDims *o) {
     o->S = d->state_dim; o->Spad = (int)align4(d->state_dim + 0); o->A = d->num_actions;
-    o->Apad = (d->num_actions + 1) & ~1; o->D = d->dim; o->H = d->heads; o->I = d->heads * d->dim_head;
-    o->L = d->depth; o->K = d->num_bins; o->Kpad = (d->num_bins + 1) & ~1; o->G = d->dim_gene;
+    o->Apad = (d->num_actions + 3) & ~3; o->D = d->dim; o->H = d->heads; o->I = d->heads * d->dim_head;
+    o->L = d->depth; o->K = d->num_bins; o->Kpad = (d->num_bins + 3) & ~3; o->G = d->dim_gene;
     o->gate = d->gate_values != 0; o->vres = d->value_residual != 0;
     o->mix = o->vres && d->learned_mix != 0;
-    o->NQ = 3 * o->I + (o->gate ? o->I : 0) + (o->mix ? ((o->H + 1) & ~1) : 0);
+    o->NQ = 3 * o->I + (o->gate ? o->I : 0) + (o->mix ? ((o->H + 3) & ~3) : 0);
     o->HIN = (d->dim_gene > 0 ? 3 : 2) * d->dim; o->Tmax = d->max_timesteps;
     o->rot = d->rotary_true_pos != 0; o->kvbf16 = d->kv_bf16 != 0;
     return 0;
@@ -131,7 +143,7 @@ __host__ __device__ static inline Smem smem_layout(const StepDims &d) {
     auto take = [&](int n) { int at = o; o += (n + 3) & ~3; return at; };
     s.x = take(kTE * d.D);
     s.xn = take(kTE * d.D);
-    s.qkv = take(kTE * d.NQ);
+    s.qkv = take(kTE * d.NQ > kSplitK * kTE * d.D ? kTE * d.NQ : kSplitK * kTE * d.D);   // also split-K scratch
     s.v1 = take(d.vres ? kTE * d.I : 0);
     s.ao = take(kTE * d.I);
     s.ff = take(kTE * 4 * d.D);
@@ -143,35 +155,62 @@ __host__ __device__ static inline Smem smem_layout(const StepDims &d) {
     return s;
 }
 
-// Y[e][n] = sum_k X[e][k] * Wt[k][n] for the CTA's kTE envs.  A work item is (column pair, group
-// of ES envs); items are spread over the CTA so narrow layers still use every warp.  X rows are read
-// as broadcast LDS.128, W as coalesced LDG.64.  epi(e, n, acc) consumes each output.
-template <int ES, class Epi>
+// Y[e][n] = sum_k X[e][k] * Wt[k][n] for the CTA's kTE envs.  A work item is (4 adjacent columns, a
+// group of ES envs, one of KS slices of K); items are spread over the CTA so narrow layers still use
+// every warp.  W moves as coalesced LDG.128 rows (two 4-row blocks in flight), X as LDS.128.
+// epi(e, n, ks, acc) consumes each (partial, when KS > 1) output.
+template <int ES, int KS, class Epi>
 __device__ __forceinline__ void dense_tile(const float *__restrict__ Wt, int K, int N,
                                            const float *__restrict__ sX, int ldx, Epi epi) {
-    const int cps = N >> 1, groups = kTE / ES;
-    for (int item = threadIdx.x; item < cps * groups; item += kThreads) {
-        const int cp = item % cps, e0 = (item / cps) * ES;
-        const float *w = Wt + 2 * cp;
-        float acc0[ES], acc1[ES];
+    const int quads = N >> 2, groups = kTE / ES, kper = K / KS;
+    for (int item = threadIdx.x; item < quads * groups * KS; item += kThreads) {
+        const int q = item % quads, rest = item / quads, e0 = (rest % groups) * ES, ks = rest / groups;
+        const float *w = Wt + 4 * q;
+        float acc[ES][4];
 #pragma unroll
-        for (int e = 0; e < ES; ++e) { acc0[e] = 0.f; acc1[e] = 0.f; }
-        for (int k = 0; k < K; k += 4) {
-            const float2 w0 = __ldg((const float2 *)(w + (int64_t)(k + 0) * N));
-            const float2 w1 = __ldg((const float2 *)(w + (int64_t)(k + 1) * N));
-            const float2 w2 = __ldg((const float2 *)(w + (int64_t)(k + 2) * N));
-            const float2 w3 = __ldg((const float2 *)(w + (int64_t)(k + 3) * N));
+        for (int e = 0; e < ES; ++e) { acc[e][0] = 0.f; acc[e][1] = 0.f; acc[e][2] = 0.f; acc[e][3] = 0.f; }
+#pragma unroll 2
+        for (int k = ks * kper; k < (ks + 1) * kper; k += 4) {
+            const float4 w0 = __ldg((const float4 *)(w + (int64_t)(k + 0) * N));
+            const float4 w1 = __ldg((const float4 *)(w + (int64_t)(k + 1) * N));
+            const float4 w2 = __ldg((const float4 *)(w + (int64_t)(k + 2) * N));
+            const float4 w3 = __ldg((const float4 *)(w + (int64_t)(k + 3) * N));
 #pragma unroll
             for (int e = 0; e < ES; ++e) {
                 const float4 x = *(const float4 *)(sX + (e0 + e) * ldx + k);
-                acc0[e] = fmaf(x.x, w0.x, acc0[e]); acc1[e] = fmaf(x.x, w0.y, acc1[e]);
-                acc0[e] = fmaf(x.y, w1.x, acc0[e]); acc1[e] = fmaf(x.y, w1.y, acc1[e]);
-                acc0[e] = fmaf(x.z, w2.x, acc0[e]); acc1[e] = fmaf(x.z, w2.y, acc1[e]);
-                acc0[e] = fmaf(x.w, w3.x, acc0[e]); acc1[e] = fmaf(x.w, w3.y, acc1[e]);
+                acc[e][0] = fmaf(x.x, w0.x, acc[e][0]); acc[e][1] = fmaf(x.x, w0.y, acc[e][1]);
+                acc[e][2] = fmaf(x.x, w0.z, acc[e][2]); acc[e][3] = fmaf(x.x, w0.w, acc[e][3]);
+                acc[e][0] = fmaf(x.y, w1.x, acc[e][0]); acc[e][1] = fmaf(x.y, w1.y, acc[e][1]);
+                acc[e][2] = fmaf(x.y, w1.z, acc[e][2]); acc[e][3] = fmaf(x.y, w1.w, acc[e][3]);
+                acc[e][0] = fmaf(x.z, w2.x, acc[e][0]); acc[e][1] = fmaf(x.z, w2.y, acc[e][1]);
+                acc[e][2] = fmaf(x.z, w2.z, acc[e][2]); acc[e][3] = fmaf(x.z, w2.w, acc[e][3]);
+                acc[e][0] = fmaf(x.w, w3.x, acc[e][0]); acc[e][1] = fmaf(x.w, w3.y, acc[e][1]);
+                acc[e][2] = fmaf(x.w, w3.z, acc[e][2]); acc[e][3] = fmaf(x.w, w3.w, acc[e][3]);
             }
         }
 #pragma unroll
-        for (int e = 0; e < ES; ++e) { epi(e0 + e, 2 * cp, acc0[e]); epi(e0 + e, 2 * cp + 1, acc1[e]); }
+        for (int e = 0; e < ES; ++e) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) epi(e0 + e, 4 * q + c, ks, acc[e][c]);
+        }
+    }
+}
+
+// narrow residual layers (N = D): split K four ways so the whole CTA works, partial sums meet in a
+// scratch tile [KS][kTE][D] and are folded into the residual stream in a fixed order (deterministic).
+template <class Fin>
+__device__ __forceinline__ void dense_residual(const float *__restrict__ Wt, int K, int D,
+                                               const float *__restrict__ sX, int ldx,
+                                               float *__restrict__ scratch, float *__restrict__ sx, Fin bias) {
+    dense_tile<4, kSplitK>(Wt, K, D, sX, ldx, [&](int e, int n, int ks, float acc) {
+        scratch[(ks * kTE + e) * D + n] = acc;
+    });
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTE * D; i += kThreads) {
+        float v = sx[i] + bias(i % D);
+#pragma unroll
+        for (int ks = 0; ks < kSplitK; ++ks) v += scratch[ks * kTE * D + i];
+        sx[i] = v;
     }
 }
 
@@ -194,34 +233,30 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-template <typename KV> struct KvRow;
-template <> struct KvRow<float> {
-    static __device__ __forceinline__ void load(const float *p, float (&r)[kDH]) {
-        const float4 *q = (const float4 *)p;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const float4 v = ld_stream_f4(q + i); r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w; }
+// KV-cache element traits.  A row (one key or value of one head) is dim_head elements = PPR 16-byte
+// pieces of EP elements.  The stream of one (env, head) is read as consecutive 16-byte pieces by
+// consecutive lanes -- every LDG.128 of a warp covers 512 contiguous bytes, each 32-byte sector is
+// fetched from L2 exactly once -- so lane = (row group, piece-of-row): grp = lane / PPR, sub = lane % PPR.
+template <typename KV> struct KvTraits;
+template <> struct KvTraits<float> {
+    static constexpr int EP = 4, PPR = 4, LOG_PPR = 2;
+    static __device__ __forceinline__ void unpack(const uint4 &r, float (&o)[4]) {
+        o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
     }
     static __device__ __forceinline__ void store1(float *p, float v) { *p = v; }
 };
-template <> struct KvRow<__nv_bfloat16> {
-    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&r)[kDH]) {
-        const uint4 *q = (const uint4 *)p;
+template <> struct KvTraits<__nv_bfloat16> {
+    static constexpr int EP = 8, PPR = 2, LOG_PPR = 1;
+    static __device__ __forceinline__ void unpack(const uint4 &r, float (&o)[8]) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const uint4 v = ld_stream_u4(q + i);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                r[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
-                r[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
-            }
-        }
+        for (int j = 0; j < 4; ++j) { o[2 * j] = __uint_as_float(w[j] << 16); o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
     }
     static __device__ __forceinline__ void store1(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
 template <typename KV>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 wm_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) float sm[];
     const StepDims &d = a.d;
@@ -233,6 +268,8 @@ wm_step_kernel(const StepArgs a) {
     const int D = d.D, I = d.I, H = d.H, NQ = d.NQ, S = d.S, Spad = d.Spad;
     const float *W = a.weights;
     const int lst = Spad + 4;
+    using TR = KvTraits<KV>;
+    constexpr int EP = TR::EP, PPR = TR::PPR, RPI = 32 / TR::PPR;     // elems per piece, pieces per row, rows per LDG
 
     // ---- RSNorm.eval on (state || prev reward) (:588-594); gene rows l2-normalised (evolution.py:73-74)
     for (int i = tid; i < kTE * lst; i += kThreads) {
@@ -259,7 +296,7 @@ wm_step_kernel(const StepArgs a) {
     __syncthreads();
 
     // ---- token embedding (:492-503) and the two state-only head inputs (:492, :544)
-    dense_tile<4>(W + a.w.in_proj, Spad, 2 * D, sst, lst, [&](int e, int n, float acc) {
+    dense_tile<kTE / 8, 1>(W + a.w.in_proj, Spad, 2 * D, sst, lst, [&](int e, int n, int, float acc) {
         const int env = env0 + e;
         if (n < D) {
             float v = acc;
@@ -274,7 +311,7 @@ wm_step_kernel(const StepArgs a) {
         }
     });
     if (d.G > 0) {
-        dense_tile<2>(W + a.w.latent_w, d.G, D, sgene, d.G, [&](int e, int n, float acc) {
+        dense_tile<kTE / 8, 1>(W + a.w.latent_w, d.G, D, sgene, d.G, [&](int e, int n, int, float acc) {
             shin[e * d.HIN + 2 * D + n] = acc + __ldg(W + a.w.latent_b + n);              // latent_to_embed
         });
     }
@@ -289,7 +326,7 @@ wm_step_kernel(const StepArgs a) {
         layer_norm_tile(sx, sxn, D, W + wl.ln1_gamma, D);
         __syncthreads();
         // fused q | k | v | gate | mix projection
-        dense_tile<16>(W + wl.qkv_w, D, NQ, sxn, D, [&](int e, int n, float acc) {
+        dense_tile<kTE / 2, 1>(W + wl.qkv_w, D, NQ, sxn, D, [&](int e, int n, int, float acc) {
             float v = acc + __ldg(W + wl.qkv_b + n);
             if (n >= 3 * I) v = sigmoidf_(v);                  // to_v_gate / to_value_residual_mix
             sqkv[e * NQ + n] = v;
@@ -336,96 +373,127 @@ wm_step_kernel(const StepArgs a) {
             // append the new key / value (lanes 0-15: k, 16-31: v)
             {
                 const float nv = qs[(lane < kDH ? I : 2 * I) + (lane & (kDH - 1))];
-                KvRow<KV>::store1((lane < kDH ? kc : vc) + (int64_t)len * kDH + (lane & (kDH - 1)), nv);
+                TR::store1((lane < kDH ? kc : vc) + (int64_t)len * kDH + (lane & (kDH - 1)), nv);
             }
-            float q[kDH];
+            const int sub = lane & (PPR - 1), grp = lane >> TR::LOG_PPR;
+            const uint4 *kp = (const uint4 *)kc, *vp = (const uint4 *)vc;      // 16-byte pieces, PPR per row
+            float q[EP], acc[EP];
 #pragma unroll
-            for (int i = 0; i < kDH; ++i) q[i] = qs[i];
-            float m = -INFINITY, lsum = 0.f, acc[kDH];
+            for (int i = 0; i < EP; ++i) { q[i] = qs[sub * EP + i]; acc[i] = 0.f; }
+            float m = -INFINITY, lsum = 0.f;
+            // keys 0..len-1 stream from the cache; key `len` is the token itself, still in shared memory
+            auto fetch = [&](int c, uint4 (&kr)[PPR], uint4 (&vr)[PPR]) {
 #pragma unroll
-            for (int i = 0; i < kDH; ++i) acc[i] = 0.f;
-            for (int j0 = 0; j0 < len; j0 += 64) {
-                const int ja = j0 + lane, jb = j0 + 32 + lane;
-                float ka[kDH], va[kDH], kb[kDH], vb[kDH];
-                if (ja < len) { KvRow<KV>::load(kc + (int64_t)ja * kDH, ka); KvRow<KV>::load(vc + (int64_t)ja * kDH, va); }
-                if (jb < len) { KvRow<KV>::load(kc + (int64_t)jb * kDH, kb); KvRow<KV>::load(vc + (int64_t)jb * kDH, vb); }
-                if (ja < len) {
-                    float s = 0.f;
+                for (int i = 0; i < PPR; ++i) {
+                    const int j = c * 32 + i * RPI + grp;
+                    if (j < len) { kr[i] = ld_stream_u4(kp + (int64_t)j * PPR + sub); vr[i] = ld_stream_u4(vp + (int64_t)j * PPR + sub); }
+                }
+            };
+            auto process = [&](int c, const uint4 (&kr)[PPR], const uint4 (&vr)[PPR]) {
+                float sc[PPR], vf[PPR][EP];
+                float mn = m;
 #pragma unroll
-                    for (int i = 0; i < kDH; ++i) s = fmaf(q[i], ka[i], s);
-                    s *= 0.25f;                                  // dim_head^-0.5
-                    const float mn = fmaxf(m, s), c = expf(m - mn), p = expf(s - mn);
-                    lsum = fmaf(lsum, c, p);
+                for (int i = 0; i < PPR; ++i) {
+                    const int j = c * 32 + i * RPI + grp;
+                    float kf[EP];
+                    if (j < len) { TR::unpack(kr[i], kf); TR::unpack(vr[i], vf[i]); }
+                    else {
 #pragma unroll
-                    for (int i = 0; i < kDH; ++i) acc[i] = fmaf(acc[i], c, p * va[i]);
+                        for (int t = 0; t < EP; ++t) {
+                            kf[t] = j == len ? qs[I + sub * EP + t] : 0.f;
+                            vf[i][t] = j == len ? qs[2 * I + sub * EP + t] : 0.f;
+                        }
+                    }
+                    float part = 0.f;
+#pragma unroll
+                    for (int t = 0; t < EP; ++t) part = fmaf(q[t], kf[t], part);
+#pragma unroll
+                    for (int o = 1; o < PPR; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    sc[i] = j <= len ? part * 0.25f : -INFINITY;           // dim_head^-0.5
+                    mn = fmaxf(mn, sc[i]);
+                }
+                if (mn > -INFINITY) {                                      // a row group with no valid key yet skips
+                    const float c0 = expf(m - mn);
+                    lsum *= c0;
+#pragma unroll
+                    for (int t = 0; t < EP; ++t) acc[t] *= c0;
+#pragma unroll
+                    for (int i = 0; i < PPR; ++i) {
+                        const float pi = expf(sc[i] - mn);
+                        lsum += pi;
+#pragma unroll
+                        for (int t = 0; t < EP; ++t) acc[t] = fmaf(pi, vf[i][t], acc[t]);
+                    }
                     m = mn;
                 }
-                if (jb < len) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int i = 0; i < kDH; ++i) s = fmaf(q[i], kb[i], s);
-                    s *= 0.25f;
-                    const float mn = fmaxf(m, s), c = expf(m - mn), p = expf(s - mn);
-                    lsum = fmaf(lsum, c, p);
-#pragma unroll
-                    for (int i = 0; i < kDH; ++i) acc[i] = fmaf(acc[i], c, p * vb[i]);
-                    m = mn;
+            };
+            // software pipeline over 32-key chunks (two register buffers, ping-pong): the loads of chunk
+            // c+1 are in flight while chunk c is folded into the online softmax
+            const int nchunks = len / 32 + 1;
+            if constexpr (kKvBuf >= 2) {
+                uint4 ka[PPR], va[PPR], kb[PPR], vb[PPR];
+                fetch(0, ka, va);
+                for (int c = 0; c < nchunks; c += 2) {
+                    fetch(c + 1, kb, vb);
+                    process(c, ka, va);
+                    fetch(c + 2, ka, va);
+                    if (c + 1 < nchunks) process(c + 1, kb, vb);
                 }
+            } else {                                                   // one chunk in flight per warp; more warps per SM
+                uint4 ka[PPR], va[PPR];
+                for (int c = 0; c < nchunks; ++c) { fetch(c, ka, va); process(c, ka, va); }
             }
-            if (lane == 0) {                                    // the token attends to itself
-                float s = 0.f;
+            // merge the row groups: rescale to the common max, then butterfly sums across groups
+            float M = m;
 #pragma unroll
-                for (int i = 0; i < kDH; ++i) s = fmaf(q[i], qs[I + i], s);
-                s *= 0.25f;
-                const float mn = fmaxf(m, s), c = expf(m - mn), p = expf(s - mn);
-                lsum = fmaf(lsum, c, p);
-#pragma unroll
-                for (int i = 0; i < kDH; ++i) acc[i] = fmaf(acc[i], c, p * qs[2 * I + i]);
-                m = mn;
-            }
-            const float M = warp_max(m);
+            for (int o = PPR; o < 32; o <<= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
             const float f = m == -INFINITY ? 0.f : expf(m - M);
-            const float denom = warp_sum(lsum * f);
-            float mine = 0.f;
+            lsum *= f;
 #pragma unroll
-            for (int i = 0; i < kDH; ++i) {
-                const float t = warp_sum(acc[i] * f);
-                if (lane == i) mine = t;
+            for (int t = 0; t < EP; ++t) acc[t] *= f;
+#pragma unroll
+            for (int o = PPR; o < 32; o <<= 1) {
+                lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+#pragma unroll
+                for (int t = 0; t < EP; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
             }
-            if (lane < kDH) {
-                float o = mine / denom;
-                if (d.gate) o *= sqkv[e * NQ + 3 * I + h * kDH + lane];
-                sao[e * I + h * kDH + lane] = o;
+            if (grp == 0) {
+                const float inv = 1.f / lsum;
+#pragma unroll
+                for (int t = 0; t < EP; ++t) {
+                    const int dd = sub * EP + t;
+                    float o = acc[t] * inv;
+                    if (d.gate) o *= sqkv[e * NQ + 3 * I + h * kDH + dd];
+                    sao[e * I + h * kDH + dd] = o;
+                }
             }
         }
         __syncthreads();
         // to_out + residual
-        dense_tile<2>(W + wl.out_w, I, D, sao, I, [&](int e, int n, float acc) { sx[e * D + n] += acc; });
+        dense_residual(W + wl.out_w, I, D, sao, I, sqkv, sx, [](int) { return 0.f; });   // sqkv is dead here: scratch
         __syncthreads();
         layer_norm_tile(sx, sxn, D, W + wl.ln2_gamma, D);
         __syncthreads();
-        dense_tile<8>(W + wl.ff1_w, D, 4 * D, sxn, D, [&](int e, int n, float acc) {
+        dense_tile<kTE / 4, 1>(W + wl.ff1_w, D, 4 * D, sxn, D, [&](int e, int n, int, float acc) {
             sff[e * 4 * D + n] = gelu_erf(acc + __ldg(W + wl.ff1_b + n));
         });
         __syncthreads();
-        dense_tile<2>(W + wl.ff2_w, 4 * D, D, sff, 4 * D, [&](int e, int n, float acc) {
-            sx[e * D + n] += acc + __ldg(W + wl.ff2_b + n);
-        });
+        dense_residual(W + wl.ff2_w, 4 * D, D, sff, 4 * D, sqkv, sx, [&](int n) { return __ldg(W + wl.ff2_b + n); });
         __syncthreads();
     }
 
     // ---- final norm -> heads (:533-557)
     layer_norm_tile(sx, shin, d.HIN, W + a.w.final_gamma, D);
     __syncthreads();
-    dense_tile<8>(W + a.w.head1_w, d.HIN, 4 * D, shin, d.HIN, [&](int e, int n, float acc) {
+    dense_tile<kTE / 4, 1>(W + a.w.head1_w, d.HIN, 4 * D, shin, d.HIN, [&](int e, int n, int, float acc) {
         sff[e * 4 * D + n] = silu(acc + __ldg(W + a.w.head1_b + n));
     });
     __syncthreads();
     const int ll = d.Apad + d.Kpad;
-    dense_tile<1>(W + a.w.actor2_w, 2 * D, d.Apad, sff, 4 * D, [&](int e, int n, float acc) {
+    dense_tile<1, 1>(W + a.w.actor2_w, 2 * D, d.Apad, sff, 4 * D, [&](int e, int n, int, float acc) {
         slog[e * ll + n] = acc + __ldg(W + a.w.actor2_b + n);
     });
-    dense_tile<4>(W + a.w.critic2_w, 2 * D, d.Kpad, sff + 2 * D, 4 * D, [&](int e, int n, float acc) {
+    dense_tile<kTE / 8, 1>(W + a.w.critic2_w, 2 * D, d.Kpad, sff + 2 * D, 4 * D, [&](int e, int n, int, float acc) {
         slog[e * ll + d.Apad + n] = acc + __ldg(W + a.w.critic2_b + n);
     });
     __syncthreads();

@@ -261,7 +261,7 @@ def pack_weights(sd: dict, cfg: ModelConfig, out=None, device=None):
     put(lay.final_gamma, sd[f'{tf}.final_norm.gamma'])
     put(lay.head1_w, torch.cat((sd['action_head.0.weight'].T, sd['critic_head.0.weight'].T), dim=1))
     put(lay.head1_b, torch.cat((sd['action_head.0.bias'], sd['critic_head.0.bias'])))
-    a_pad, k_pad = (A + 1) & ~1, (K + 1) & ~1
+    a_pad, k_pad = (A + 3) & ~3, (K + 3) & ~3
     put(lay.actor2_w, sd['action_head.2.weight'].T, ld=a_pad)
     put(lay.actor2_b, sd['action_head.2.bias'])
     put(lay.critic2_w, sd['critic_head.2.weight'].T, ld=k_pad)
@@ -276,7 +276,7 @@ def pack_weights(sd: dict, cfg: ModelConfig, out=None, device=None):
             cols.append(sd[f'{pa}.1.to_v_gate.weight'].T)
             bias.append(sd[f'{pa}.1.to_v_gate.bias'].to(device))
         if cfg.learned_mix:
-            hp = (H + 1) & ~1
+            hp = (H + 3) & ~3
             w, bb = torch.zeros(D, hp, device=device), torch.zeros(hp, device=device)
             if l > 0:
                 w[:, :H] = sd[f'{pa}.1.to_value_residual_mix.0.weight'].T
