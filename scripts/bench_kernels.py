@@ -1,0 +1,78 @@
+"""Roofline microbench of the non-step kernels (GAE, fused PPO loss, evolve, optimiser) through the C ABI.
+Each kernel: L2 flushed between iterations (256 MB write), CUDA-event timing per launch, algorithmic
+bytes from SURVEY 8d / DESIGN.md.  One JSON line per kernel.   python scripts/bench_kernels.py [--iters 10]"""
+import argparse, importlib, json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+ops = importlib.import_module('x-transformers-rl_b200').ops
+ap = argparse.ArgumentParser(); ap.add_argument('--iters', type=int, default=10); ap.add_argument('--only', default='')
+a = ap.parse_args()
+dev = 'cuda'
+peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.
+flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=a.iters):
+    for _ in range(3):
+        fn()
+    ms = []
+    for _ in range(iters):
+        flush_buf.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+def report(name, alg_bytes, ms, **extra):
+    gbs = alg_bytes / (ms / 1e3) / 1e9
+    print(json.dumps(dict(kernel=name, ms=ms, algorithmic_bytes=alg_bytes, achieved_gbs=gbs, peak_gbs=peak, frac=gbs / peak, **extra)))
+
+
+E, T, A, K, S = 4096, 500, 4, 100, 8
+g = torch.Generator(device=dev).manual_seed(0)
+if not a.only or 'gae' in a.only:
+    r, v = torch.randn(E, T, device=dev, generator=g), torch.randn(E, T, device=dev, generator=g)
+    bd = torch.rand(E, T, device=dev, generator=g) < 0.02
+    out = torch.empty_like(r)
+    report('gae_episode_major (E=4096,T=500)', 13 * E * T, timeit(lambda: ops.gae(r, v, bd, out=out)), unit_bytes=13)
+    rt, vt, bt = r.T.contiguous(), v.T.contiguous(), bd.T.contiguous()
+    outt = torch.empty_like(rt)
+    report('gae_time_major (T=500,B=4096)', 13 * E * T, timeit(lambda: ops.gae(rt, vt, bt, time_major=True, out=outt)), unit_bytes=13)
+if not a.only or 'loss' in a.only:
+    for dt, nm in ((torch.float32, 'fp32'), (torch.bfloat16, 'bf16')):
+        b = 1024                                            # 512k timesteps: 0.5 GB of logits+grads in fp32
+        ra, vl = torch.randn(b, T, A, device=dev, generator=g).to(dt), torch.randn(b, T, K, device=dev, generator=g).to(dt)
+        sp, dl = torch.randn(b, T, 2 * (S + 1), device=dev, generator=g).to(dt), torch.randn(b, T, device=dev, generator=g).to(dt)
+        actions = torch.randint(0, A, (b, T), device=dev, generator=g).int()
+        olp, ret, ov = -torch.rand(b, T, device=dev, generator=g), torch.randn(b, T, device=dev, generator=g), torch.randn(b, T, device=dev, generator=g)
+        tgt, dn = torch.randn(b, T, S + 1, device=dev, generator=g), torch.rand(b, T, device=dev, generator=g) < 0.05
+        lens = torch.full((b,), T, dtype=torch.int32, device=dev)
+        cfg = ops.LossConfig(num_actions=A, num_bins=K, state_dim=S, reward_range=(-5., 5.))
+        sz = 4 if dt == torch.float32 else 2
+        per = (2 * A + 2 * K) * sz + 21 + (4 * (S + 1) + 2) * sz + 4 * (S + 1) + 1
+        report(f'ppo_loss_fwd_bwd {nm} (b=1024,T=500,A=4,K=100,S=8)', per * b * T,
+               timeit(lambda: ops.ppo_loss_fwd_bwd(cfg, ra, vl, sp, dl, actions, olp, ret, ov, tgt, dn, lens)), unit_bytes=per,
+               note='includes memset + stats + finalize launches and the output allocations of the wrapper')
+if not a.only or 'evolve' in a.only:
+    for (I, gg, s, k, G, nm) in ((4096, 16, 4, 2, 128, 'scaled 4096x16x128'), (1, 64, 16, 4, 128, 'c4 1x64x128'), (8, 8, 4, 2, 128, 'c4 8x8x128')):
+        c = gg - s
+        genes = torch.nn.functional.normalize(torch.randn(I * gg, G, device=dev, generator=g), dim=-1)
+        fit = torch.randn(I * gg, device=dev, generator=g)
+        nt, nc, nm_ = torch.randn(I, c, s, device=dev, generator=g), torch.randn(I, c, G, device=dev, generator=g), torch.randn(I, gg - 1, G, device=dev, generator=g)
+        alg = 2 * I * gg * G * 4 + 4 * I * gg + 4 * I * (c * s + c * G + (gg - 1) * G)
+        report(f'evolve ({nm})', alg, timeit(lambda: ops.evolve_(genes, fit, nt, nc, nm_, num_islands=I, num_genes_per_island=gg,
+                                                                  num_selected=s, tournament_size=k)))
+if not a.only or 'opt' in a.only:
+    for n, nm in ((208827, 'c3 model, 208,827 params'), (64 << 20, 'synthetic 64Mi params')):
+        nt = 50
+        offs = torch.linspace(0, n, nt + 1, device=dev).long(); offs[-1] = n
+        P, G_, M, V, PI, EM = (torch.randn(n, device=dev, generator=g) * 0.1 for _ in range(6))
+        V.abs_()
+        ws = None
+        report(f'adopt_atan2_step+clip+ema ({nm})', 40 * n,
+               timeit(lambda: ops.adopt_atan2_step(P, G_, M, V, PI, EM, offs, lr=8e-4, init_lr=8e-4, betas=(0.9, 0.99), regen_rate=1e-4,
+                                                   cautious_factor=0.1, max_grad_norm=0.5, first_step=False, ema_mode=2, ema_decay=0.9)),
+               unit_bytes=40, note='3 launches; the gradient is re-read by each (48 B/elem actual minimum with 3 passes)')

@@ -18,7 +18,7 @@
 namespace xtrl {
 
 constexpr int kGaeWarpsPerBlock = 8;    // episode-major: 8 episodes per CTA
-constexpr int kGaePrefetch = 4;         // blocks of 32 timesteps held in registers at once
+constexpr int kGaePrefetch = 8;         // blocks of 32 timesteps held in registers at once
 
 __global__ void __launch_bounds__(kGaeWarpsPerBlock * 32)
 gae_episode_major_kernel(const float *__restrict__ rewards, const float *__restrict__ values,

@@ -88,14 +88,70 @@ struct LossArgs {
 };
 
 constexpr int kLossWarps = 8;
+constexpr int kTileRows = 64;            // rows (timesteps) staged per tile; 8 per warp
+
+// ---- asynchronous tile staging (cp.async 16 B, zero-fill past the end of the source) -----------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// copies bytes [start, start+want) of a buffer of `total` bytes into smem (16-byte chunks; everything
+// past `total` reads as zero).  start is a multiple of 16 by construction (tile starts are 64 rows).
+__device__ __forceinline__ void stage_region(unsigned char *dst, const void *base, int64_t start, int want, int64_t total) {
+    if (base == nullptr) return;
+    const unsigned char *src = (const unsigned char *)base;
+    for (int c = threadIdx.x; c * 16 < want; c += kLossWarps * 32) {
+        const int64_t off = start + (int64_t)c * 16;
+        const int64_t left = total - off;
+        const int valid = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+        cp_async16(dst + c * 16, valid > 0 ? src + off : src, valid);
+    }
+}
+
+struct TileLayout {                      // byte offsets inside one stage of shared memory
+    int vl, ra, sp, dl, act, olp, ret, ov, tgt, dn, total;
+};
+__host__ __device__ static inline TileLayout tile_layout(int A, int K, int S1, int sz) {
+    TileLayout t; int o = 0;
+    auto take = [&](int n) { int at = o; o += (n + 15) & ~15; return at; };
+    t.vl = take(kTileRows * K * sz);
+    t.ra = take(kTileRows * A * sz);
+    t.sp = take(kTileRows * 2 * S1 * sz);
+    t.dl = take(kTileRows * sz);
+    t.act = take(kTileRows * 4);
+    t.olp = take(kTileRows * 4);
+    t.ret = take(kTileRows * 4);
+    t.ov = take(kTileRows * 4);
+    t.tgt = take((kTileRows + 1) * S1 * 4);
+    t.dn = take(kTileRows);
+    t.total = o;
+    return t;
+}
+
+template <typename T> __device__ __forceinline__ float sm_as_float(const T *p);
+template <> __device__ __forceinline__ float sm_as_float<float>(const float *p) { return *p; }
+template <> __device__ __forceinline__ float sm_as_float<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+// erf with the fp32-saturated region (|z| >= 4 rounds to +-1 exactly) skipped warp-uniformly
+__device__ __forceinline__ float erf_window(float z) {
+    const bool need = fabsf(z) < 4.f;
+    float c = copysignf(1.f, z);
+    if (__any_sync(0xffffffffu, need)) { const float e = erff(z); c = need ? e : c; }
+    return c;
+}
 
 template <typename TIO, int KJ>
-__global__ void __launch_bounds__(kLossWarps * 32)
+__global__ void __launch_bounds__(kLossWarps * 32, 2)
 ppo_loss_kernel(const LossArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int A = a.cfg.num_actions, K = a.cfg.num_bins, S1 = a.cfg.state_dim + 1, T = a.T;
     const int64_t N = (int64_t)a.b * T;
     const double *ws = a.io.workspace;
+    const TileLayout tl = tile_layout(A, K, S1, (int)sizeof(TIO));
 
     // masked advantage statistics (normalize(), :103-112)
     const double n_mask = ws[WS_N_MASK], n_wm = ws[WS_N_WM];
@@ -111,183 +167,221 @@ ppo_loss_kernel(const LossArgs a) {
     const float g_wm = n_wm > 0. ? a.cfg.autoreg_weight * (float)(1. / (n_wm * S1)) : 0.f;
     const float feps = 1.1920928955078125e-07f;                                      // finfo(fp32).eps
 
-    const TIO *raw_actions = (const TIO *)a.io.raw_actions;
-    const TIO *value_logits = (const TIO *)a.io.value_logits;
-    const TIO *sp_raw = (const TIO *)a.io.state_pred_raw;
-    const TIO *done_logit = (const TIO *)a.io.done_logit;
     TIO *g_ra = (TIO *)a.io.g_raw_actions;
     TIO *g_vl = (TIO *)a.io.g_value_logits;
     TIO *g_sp = (TIO *)a.io.g_state_pred_raw;
     TIO *g_dl = (TIO *)a.io.g_done_logit;
+    const bool has_sp = a.io.state_pred_raw != nullptr, has_dl = a.io.done_logit != nullptr;
+
+    const int64_t ntiles = (N + kTileRows - 1) / kTileRows;
+    auto stage = [&](int64_t tile, int buf) {
+        unsigned char *st = smem + (size_t)buf * tl.total;
+        const int64_t r0 = tile * kTileRows;
+        const int sz = (int)sizeof(TIO);
+        stage_region(st + tl.vl, a.io.value_logits, r0 * K * sz, kTileRows * K * sz, N * K * sz);
+        stage_region(st + tl.ra, a.io.raw_actions, r0 * A * sz, kTileRows * A * sz, N * A * sz);
+        stage_region(st + tl.sp, a.io.state_pred_raw, r0 * 2 * S1 * sz, kTileRows * 2 * S1 * sz, N * 2 * S1 * sz);
+        stage_region(st + tl.dl, a.io.done_logit, r0 * sz, kTileRows * sz, N * sz);
+        stage_region(st + tl.act, a.io.actions, r0 * 4, kTileRows * 4, N * 4);
+        stage_region(st + tl.olp, a.io.old_log_probs, r0 * 4, kTileRows * 4, N * 4);
+        stage_region(st + tl.ret, a.io.returns, r0 * 4, kTileRows * 4, N * 4);
+        stage_region(st + tl.ov, a.io.old_values, r0 * 4, kTileRows * 4, N * 4);
+        stage_region(st + tl.tgt, a.io.target, r0 * S1 * 4, (kTileRows + 1) * S1 * 4, N * S1 * 4);
+        stage_region(st + tl.dn, a.io.dones, r0, kTileRows, N);
+        cp_async_commit();
+    };
 
     float acc_ac = 0.f, acc_actor = 0.f, acc_critic = 0.f, acc_nll = 0.f, acc_done = 0.f;
 
-    for (int64_t r = (int64_t)blockIdx.x * kLossWarps + warp; r < N; r += (int64_t)gridDim.x * kLossWarps) {
-        const int e = (int)(r / T), t = (int)(r - (int64_t)e * T);
-        const bool masked = t < __ldg(a.io.episode_lens + e);
-        const float ret = __ldg(a.io.returns + r);
-        const float v_old = __ldg(a.io.old_values + r);
+    int buf = 0;
+    if ((int64_t)blockIdx.x < ntiles) stage(blockIdx.x, 0);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int64_t next = tile + gridDim.x;
+        if (next < ntiles) { stage(next, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const unsigned char *st = smem + (size_t)buf * tl.total;
+        const TIO *s_vl = (const TIO *)(st + tl.vl), *s_ra = (const TIO *)(st + tl.ra);
+        const TIO *s_sp = (const TIO *)(st + tl.sp), *s_dl = (const TIO *)(st + tl.dl);
+        const int32_t *s_act = (const int32_t *)(st + tl.act);
+        const float *s_olp = (const float *)(st + tl.olp), *s_ret = (const float *)(st + tl.ret);
+        const float *s_ov = (const float *)(st + tl.ov), *s_tgt = (const float *)(st + tl.tgt);
+        const uint8_t *s_dn = (const uint8_t *)(st + tl.dn);
 
-        // ---------------- critic: HL-Gauss CE against returns and clamped returns ------------
-        float lg[KJ], ex[KJ];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < KJ; ++j) {
-            const int k = j * 32 + lane;
-            lg[j] = k < K ? ld_as_float(value_logits + r * K + k) : -INFINITY;
-            mx = fmaxf(mx, lg[j]);
-        }
-        mx = warp_max(mx);
-        float se = 0.f, sc = 0.f;
-#pragma unroll
-        for (int j = 0; j < KJ; ++j) {
-            const int k = j * 32 + lane;
-            ex[j] = k < K ? expf(lg[j] - mx) : 0.f;
-            se += ex[j];
-            sc += k < K ? ex[j] * a.sup.centre(k) : 0.f;
-        }
-        se = warp_sum(se); sc = warp_sum(sc);
-        const float v_new = sc / se;                       // hl_gauss(values), :455
-        const float lse = logf(se) + mx;
+        for (int lr = warp; lr < kTileRows; lr += kLossWarps) {
+            const int64_t r = tile * kTileRows + lr;
+            if (r >= N) break;
+            const int e = (int)(r / T), t = (int)(r - (int64_t)e * T);
+            const bool masked = t < __ldg(a.io.episode_lens + e);
+            const float ret = s_ret[lr];
+            const float v_old = s_ov[lr];
 
-        const float y0 = fminf(fmaxf(ret, a.sup.lo), a.sup.hi);                                     // clamp_to_range
-        const float y1 = fminf(fmaxf(fminf(fmaxf(ret, -a.cfg.value_clip), a.cfg.value_clip), a.sup.lo), a.sup.hi);  // :459
-        // cdf at the lower edge of each of my bins; the upper edge comes from the next lane
-        float c0[KJ], c1[KJ];
-#pragma unroll
-        for (int j = 0; j < KJ; ++j) {
-            const int k = j * 32 + lane;
-            const float ed = a.sup.edge(min(k, K));
-            c0[j] = erff((ed - y0) / a.sup.denom);
-            c1[j] = erff((ed - y1) / a.sup.denom);
-        }
-        const float z0 = fmaxf(erff((a.sup.hi - y0) / a.sup.denom) - erff((a.sup.lo - y0) / a.sup.denom), 1e-10f);
-        const float z1 = fmaxf(erff((a.sup.hi - y1) / a.sup.denom) - erff((a.sup.lo - y1) / a.sup.denom), 1e-10f);
-        float p0[KJ], p1[KJ];
-        float ce0 = 0.f, ce1 = 0.f, sp0 = 0.f, sp1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < KJ; ++j) {
-            const int k = j * 32 + lane;
-            // upper edge k+1: lane+1 of this j, or lane 0 of j+1
-            float u0 = __shfl_down_sync(0xffffffffu, c0[j], 1);
-            float u1 = __shfl_down_sync(0xffffffffu, c1[j], 1);
-            const float n0 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c0[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
-            const float n1 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c1[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
-            if (lane == 31) { u0 = n0; u1 = n1; }
-            if (k + 1 == K) {                                  // last edge is `hi` exactly
-                u0 = erff((a.sup.edge(K) - y0) / a.sup.denom);
-                u1 = erff((a.sup.edge(K) - y1) / a.sup.denom);
-            }
-            p0[j] = k < K ? (u0 - c0[j]) / z0 : 0.f;
-            p1[j] = k < K ? (u1 - c1[j]) / z1 : 0.f;
-            const float lsm = k < K ? lg[j] - lse : 0.f;
-            ce0 -= p0[j] * lsm; ce1 -= p1[j] * lsm;
-            sp0 += p0[j]; sp1 += p1[j];
-        }
-        ce0 = warp_sum(ce0); ce1 = warp_sum(ce1); sp0 = warp_sum(sp0); sp1 = warp_sum(sp1);
-        const float lo_old = v_old - a.cfg.value_clip, hi_old = v_old + a.cfg.value_clip;
-        const bool zero = (ret < v_new && v_new < lo_old) || (hi_old < v_new && v_new < ret);   // :470-472
-        const float critic = zero ? 0.f : fminf(ce0, ce1);
-        if (g_vl) {
-            // d min(ce0, ce1): the smaller one; an exact tie splits evenly (torch minimum)
-            const float w0 = zero ? 0.f : (ce0 < ce1 ? 1.f : (ce0 > ce1 ? 0.f : 0.5f));
-            const float w1 = zero ? 0.f : 1.f - w0;
-            const float gc = masked ? g_ac * a.cfg.critic_weight : 0.f;
-            const float inv_se = 1.f / se;
+            // ---------------- critic: HL-Gauss CE against returns and clamped returns ------------
+            float lg[KJ], ex[KJ];
+            float mx = -INFINITY;
 #pragma unroll
             for (int j = 0; j < KJ; ++j) {
                 const int k = j * 32 + lane;
-                if (k < K) {
-                    const float sm = ex[j] * inv_se;
-                    const float g = gc * (w0 * (sm * sp0 - p0[j]) + w1 * (sm * sp1 - p1[j]));
-                    st_from_float(g_vl + r * K + k, g);
+                lg[j] = k < K ? sm_as_float(s_vl + lr * K + k) : -INFINITY;
+                mx = fmaxf(mx, lg[j]);
+            }
+            mx = warp_max(mx);
+            float se = 0.f, sc = 0.f;
+#pragma unroll
+            for (int j = 0; j < KJ; ++j) {
+                const int k = j * 32 + lane;
+                ex[j] = k < K ? expf(lg[j] - mx) : 0.f;
+                se += ex[j];
+                sc += k < K ? ex[j] * a.sup.centre(k) : 0.f;
+            }
+            se = warp_sum(se); sc = warp_sum(sc);
+            const float v_new = sc / se;                       // hl_gauss(values), :455
+            const float lse = logf(se) + mx;
+
+            const float y0 = fminf(fmaxf(ret, a.sup.lo), a.sup.hi);                                     // clamp_to_range
+            const float y1 = fminf(fmaxf(fminf(fmaxf(ret, -a.cfg.value_clip), a.cfg.value_clip), a.sup.lo), a.sup.hi);  // :459
+            const bool same = y0 == y1;                        // returns inside +-value_clip: one histogram serves both
+            // normalisers: lanes 0..3 evaluate erf at (hi,y0) (lo,y0) (hi,y1) (lo,y1), then broadcast
+            const float zarg = ((lane & 1) ? a.sup.lo : a.sup.hi) - ((lane & 2) ? y1 : y0);
+            const float zerf = erff(zarg / a.sup.denom);
+            const float z0 = fmaxf(__shfl_sync(0xffffffffu, zerf, 0) - __shfl_sync(0xffffffffu, zerf, 1), 1e-10f);
+            const float z1 = fmaxf(__shfl_sync(0xffffffffu, zerf, 2) - __shfl_sync(0xffffffffu, zerf, 3), 1e-10f);
+            // cdf at the lower edge of each of my bins; the upper edge comes from the next lane
+            float c0[KJ], c1[KJ];
+#pragma unroll
+            for (int j = 0; j < KJ; ++j) {
+                const int k = j * 32 + lane;
+                const float ed = a.sup.edge(min(k, K));
+                c0[j] = erf_window((ed - y0) / a.sup.denom);
+                c1[j] = same ? c0[j] : erf_window((ed - y1) / a.sup.denom);
+            }
+            float p0[KJ], p1[KJ];
+            float ce0 = 0.f, ce1 = 0.f, sp0 = 0.f, sp1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < KJ; ++j) {
+                const int k = j * 32 + lane;
+                // upper edge k+1: lane+1 of this j, or lane 0 of j+1
+                float u0 = __shfl_down_sync(0xffffffffu, c0[j], 1);
+                float u1 = __shfl_down_sync(0xffffffffu, c1[j], 1);
+                const float n0 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c0[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
+                const float n1 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c1[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
+                if (lane == 31) { u0 = n0; u1 = n1; }
+                if (k + 1 == K && (K & 31) == 0) {               // the last edge has no lane of its own
+                    u0 = erff((a.sup.hi - y0) / a.sup.denom);
+                    u1 = erff((a.sup.hi - y1) / a.sup.denom);
+                }
+                p0[j] = k < K ? (u0 - c0[j]) / z0 : 0.f;
+                p1[j] = k < K ? (u1 - c1[j]) / z1 : 0.f;
+                const float lsm = k < K ? lg[j] - lse : 0.f;
+                ce0 -= p0[j] * lsm; ce1 -= p1[j] * lsm;
+                sp0 += p0[j]; sp1 += p1[j];
+            }
+            ce0 = warp_sum(ce0); sp0 = warp_sum(sp0);
+            if (same) { ce1 = ce0; sp1 = sp0; } else { ce1 = warp_sum(ce1); sp1 = warp_sum(sp1); }
+            const float lo_old = v_old - a.cfg.value_clip, hi_old = v_old + a.cfg.value_clip;
+            const bool zero = (ret < v_new && v_new < lo_old) || (hi_old < v_new && v_new < ret);   // :470-472
+            const float critic = zero ? 0.f : fminf(ce0, ce1);
+            if (g_vl) {
+                // d min(ce0, ce1): the smaller one; an exact tie splits evenly (torch minimum)
+                const float w0 = zero ? 0.f : (ce0 < ce1 ? 1.f : (ce0 > ce1 ? 0.f : 0.5f));
+                const float w1 = zero ? 0.f : 1.f - w0;
+                const float gc = masked ? g_ac * a.cfg.critic_weight : 0.f;
+                const float inv_se = 1.f / se;
+#pragma unroll
+                for (int j = 0; j < KJ; ++j) {
+                    const int k = j * 32 + lane;
+                    if (k < K) {
+                        const float sm = ex[j] * inv_se;
+                        const float g = gc * (w0 * (sm * sp0 - p0[j]) + w1 * (sm * sp1 - p1[j]));
+                        st_from_float(g_vl + r * K + k, g);
+                    }
                 }
             }
-        }
 
-        // ---------------- actor: clipped surrogate + entropy (lane i <-> action i) ------------
-        const int act = __ldg(a.io.actions + r);
-        const float la = lane < A ? ld_as_float(raw_actions + r * A + lane) : -INFINITY;
-        const float amx = warp_max(la);
-        const float q = lane < A ? expf(la - amx) : 0.f;
-        const float qs = warp_sum(q);
-        const float sm = q / qs;                              // softmax
-        const float ssum = warp_sum(sm);                      // Categorical renormalises probs
-        const float p = sm / ssum;
-        const bool inside = p >= feps && p <= 1.f - feps;
-        const float L = lane < A ? logf(fminf(fmaxf(p, feps), 1.f - feps)) : 0.f;
-        const float ent = -warp_sum(p * L);
-        const float logp = __shfl_sync(0xffffffffu, L, act & 31);
-        const float ratio = expf(logp - __ldg(a.io.old_log_probs + r));
-        const float clipped = fminf(fmaxf(ratio, 1.f - a.cfg.eps_clip), 1.f + a.cfg.eps_clip);
-        const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
-        const float surr1 = ratio * adv, surr2 = clipped * adv;
-        const float actor = -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
-        if (g_ra) {
-            const bool in_range = ratio >= 1.f - a.cfg.eps_clip && ratio <= 1.f + a.cfg.eps_clip;
-            const float dmin = in_range ? adv : (surr1 < surr2 ? adv : 0.f);
-            const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
-            const float g_logp = -ga * dmin * ratio;
-            // d/dp_i of  -beta*ent + logp-term
-            float gp = 0.f;
-            if (lane < A) {
-                gp = ga * a.cfg.entropy_weight * (L + (inside ? 1.f : 0.f));
-                if (lane == act && inside) gp += g_logp / p;
-            }
-            // p = sm / sum(sm);  sm = softmax(logits)
-            const float dot_p = warp_sum(gp * p);
-            const float gq = (gp - dot_p) / ssum;
-            const float dot_q = warp_sum(lane < A ? gq * sm : 0.f);
-            if (lane < A) st_from_float(g_ra + r * A + lane, sm * (gq - dot_q));
-        }
-
-        // ---------------- world model: Gaussian NLL of next (state || reward), done BCE -------
-        float nll = 0.f, bce = 0.f;
-        if (sp_raw) {
-            const bool valid = masked && t < T - 1;
-            if (lane < S1) {
-                const float mean = ld_as_float(sp_raw + (r * S1 + lane) * 2);
-                const float lv = ld_as_float(sp_raw + (r * S1 + lane) * 2 + 1);
-                const float th = tanhf(lv / 3.f);
-                const float var = fmaxf(expf(th * 3.f), 1e-6f);
-                float gm = 0.f, gl = 0.f;
-                if (valid) {
-                    const float d = mean - __ldg(a.io.target + (r + 1) * S1 + lane);
-                    nll = 0.5f * (logf(var) + d * d / var);
-                    gm = g_wm * d / var;
-                    gl = g_wm * 0.5f * (1.f / var - d * d / (var * var)) * var * (1.f - th * th);
+            // ---------------- actor: clipped surrogate + entropy (lane i <-> action i) ------------
+            const int act = s_act[lr];
+            const float la = lane < A ? sm_as_float(s_ra + lr * A + lane) : -INFINITY;
+            const float amx = warp_max(la);
+            const float q = lane < A ? expf(la - amx) : 0.f;
+            const float qs = warp_sum(q);
+            const float sm = q / qs;                              // softmax
+            const float ssum = warp_sum(sm);                      // Categorical renormalises probs
+            const float p = sm / ssum;
+            const bool inside = p >= feps && p <= 1.f - feps;
+            const float L = lane < A ? logf(fminf(fmaxf(p, feps), 1.f - feps)) : 0.f;
+            const float ent = -warp_sum(p * L);
+            const float logp = __shfl_sync(0xffffffffu, L, act & 31);
+            const float ratio = expf(logp - s_olp[lr]);
+            const float clipped = fminf(fmaxf(ratio, 1.f - a.cfg.eps_clip), 1.f + a.cfg.eps_clip);
+            const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
+            const float surr1 = ratio * adv, surr2 = clipped * adv;
+            const float actor = -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
+            if (g_ra) {
+                const bool in_range = ratio >= 1.f - a.cfg.eps_clip && ratio <= 1.f + a.cfg.eps_clip;
+                const float dmin = in_range ? adv : (surr1 < surr2 ? adv : 0.f);
+                const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
+                const float g_logp = -ga * dmin * ratio;
+                // d/dp_i of  -beta*ent + logp-term
+                float gp = 0.f;
+                if (lane < A) {
+                    gp = ga * a.cfg.entropy_weight * (L + (inside ? 1.f : 0.f));
+                    if (lane == act && inside) gp += g_logp / p;
                 }
-                if (g_sp) {
-                    st_from_float(g_sp + (r * S1 + lane) * 2, gm);
-                    st_from_float(g_sp + (r * S1 + lane) * 2 + 1, gl);
-                }
+                // p = sm / sum(sm);  sm = softmax(logits)
+                const float dot_p = warp_sum(gp * p);
+                const float gq = (gp - dot_p) / ssum;
+                const float dot_q = warp_sum(lane < A ? gq * sm : 0.f);
+                if (lane < A) st_from_float(g_ra + r * A + lane, sm * (gq - dot_q));
             }
-            nll = warp_sum(nll);
-        }
-        if (done_logit && lane == 0) {
-            const float z = ld_as_float(done_logit + r);
-            const float pd = 1.f / (1.f + expf(-z));
-            const float y = __ldg(a.io.dones + r) ? 1.f : 0.f;
-            const float l1 = logf(pd), l0 = logf(1.f - pd);
-            bce = -(y * fmaxf(l1, -100.f) + (1.f - y) * fmaxf(l0, -100.f));
-            float g = 0.f;
-            if (masked) {
-                const float dp = -((l1 > -100.f ? y / pd : 0.f) - (l0 > -100.f ? (1.f - y) / (1.f - pd) : 0.f));
-                g = g_done * dp * pd * (1.f - pd);
-                if (!isfinite(g)) g = 0.f;
-            }
-            if (g_dl) st_from_float(g_dl + r, g);
-        }
 
-        if (lane == 0) {
-            if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
-            acc_actor += actor; acc_critic += critic;
-            if (masked) {
-                acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
-                acc_done += bce;
+            // ---------------- world model: Gaussian NLL of next (state || reward), done BCE -------
+            float nll = 0.f, bce = 0.f;
+            if (has_sp) {
+                const bool valid = masked && t < T - 1;
+                if (lane < S1) {
+                    const float mean = sm_as_float(s_sp + (lr * S1 + lane) * 2);
+                    const float lv = sm_as_float(s_sp + (lr * S1 + lane) * 2 + 1);
+                    const float th = tanhf(lv / 3.f);
+                    const float var = fmaxf(expf(th * 3.f), 1e-6f);
+                    float gm = 0.f, gl = 0.f;
+                    if (valid) {
+                        const float d = mean - s_tgt[(lr + 1) * S1 + lane];
+                        nll = 0.5f * (logf(var) + d * d / var);
+                        gm = g_wm * d / var;
+                        gl = g_wm * 0.5f * (1.f / var - d * d / (var * var)) * var * (1.f - th * th);
+                    }
+                    if (g_sp) {
+                        st_from_float(g_sp + (r * S1 + lane) * 2, gm);
+                        st_from_float(g_sp + (r * S1 + lane) * 2 + 1, gl);
+                    }
+                }
+                nll = warp_sum(nll);
             }
-            acc_nll += nll;                                    // already zero where invalid
+            if (has_dl && lane == 0) {
+                const float z = sm_as_float(s_dl + lr);
+                const float pd = 1.f / (1.f + expf(-z));
+                const float y = s_dn[lr] ? 1.f : 0.f;
+                const float l1 = logf(pd), l0 = logf(1.f - pd);
+                bce = -(y * fmaxf(l1, -100.f) + (1.f - y) * fmaxf(l0, -100.f));
+                float g = 0.f;
+                if (masked) {
+                    const float dp = -((l1 > -100.f ? y / pd : 0.f) - (l0 > -100.f ? (1.f - y) / (1.f - pd) : 0.f));
+                    g = g_done * dp * pd * (1.f - pd);
+                    if (!isfinite(g)) g = 0.f;
+                }
+                if (g_dl) st_from_float(g_dl + r, g);
+            }
+
+            if (lane == 0) {
+                if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
+                acc_actor += actor; acc_critic += critic;
+                if (masked) {
+                    acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
+                    acc_done += bce;
+                }
+                acc_nll += nll;                                    // already zero where invalid
+            }
         }
+        __syncthreads();                                           // this stage is refilled two tiles from now
     }
 
     __shared__ float sh[5][kLossWarps];
@@ -336,16 +430,22 @@ hl_decode_kernel(const float *__restrict__ logits, float *__restrict__ out, int6
     }
 }
 
-template <typename TIO>
-static int launch_loss(const LossArgs &la, int KJ, int blocks, cudaStream_t s) {
-    switch (KJ) {
-        case 1: ppo_loss_kernel<TIO, 1><<<blocks, kLossWarps * 32, 0, s>>>(la); break;
-        case 2: ppo_loss_kernel<TIO, 2><<<blocks, kLossWarps * 32, 0, s>>>(la); break;
-        case 4: ppo_loss_kernel<TIO, 4><<<blocks, kLossWarps * 32, 0, s>>>(la); break;
-        default: ppo_loss_kernel<TIO, 8><<<blocks, kLossWarps * 32, 0, s>>>(la); break;
-    }
+template <typename TIO, int KJ>
+static int launch_loss_kj(const LossArgs &la, int blocks, size_t smem, cudaStream_t s) {
+    XTRL_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<TIO, KJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ppo_loss_kernel<TIO, KJ><<<blocks, kLossWarps * 32, smem, s>>>(la);
     XTRL_LAUNCH_CHECK("ppo_loss_kernel");
     return XTRL_OK;
+}
+
+template <typename TIO>
+static int launch_loss(const LossArgs &la, int KJ, int blocks, size_t smem, cudaStream_t s) {
+    switch (KJ) {
+        case 1: return launch_loss_kj<TIO, 1>(la, blocks, smem, s);
+        case 2: return launch_loss_kj<TIO, 2>(la, blocks, smem, s);
+        case 4: return launch_loss_kj<TIO, 4>(la, blocks, smem, s);
+        default: return launch_loss_kj<TIO, 8>(la, blocks, smem, s);
+    }
 }
 
 }  // namespace xtrl
@@ -383,9 +483,18 @@ extern "C" int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_i
     la.sup = make_support(cfg->reward_min, cfg->reward_max, cfg->num_bins);
     const int kj = (cfg->num_bins + 31) / 32;
     const int KJ = kj <= 1 ? 1 : kj <= 2 ? 2 : kj <= 4 ? 4 : 8;
-    const int64_t want = (N + kLossWarps - 1) / kLossWarps;
-    const int blocks = (int)(want < 8 * kNumSMs ? want : 8 * kNumSMs);   // 8 resident CTAs / SM, persistent rows
-    int rc = cfg->bf16_io ? launch_loss<__nv_bfloat16>(la, KJ, blocks, s) : launch_loss<float>(la, KJ, blocks, s);
+    const int sz = cfg->bf16_io ? 2 : 4;
+    const TileLayout tl = tile_layout(cfg->num_actions, cfg->num_bins, cfg->state_dim + 1, sz);
+    const size_t smem = 2 * (size_t)tl.total;                              // double-buffered tile stages
+    XTRL_REQUIRE(smem <= 200 * 1024, XTRL_E_UNSUPPORTED, "xtrl_ppo_loss_fwd_bwd: tile needs %zu B shared memory", smem);
+    const void *ptrs[] = {io->raw_actions, io->value_logits, io->state_pred_raw, io->done_logit, io->actions, io->old_log_probs,
+                          io->returns, io->old_values, io->target, io->dones};
+    for (const void *p : ptrs)
+        XTRL_REQUIRE(((uintptr_t)p & 15) == 0, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: input pointers must be 16-byte aligned");
+    const int64_t ntiles = (N + kTileRows - 1) / kTileRows;
+    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    const int blocks = (int)(ntiles < (int64_t)per_sm * kNumSMs ? ntiles : (int64_t)per_sm * kNumSMs);   // persistent CTAs
+    int rc = cfg->bf16_io ? launch_loss<__nv_bfloat16>(la, KJ, blocks, smem, s) : launch_loss<float>(la, KJ, blocks, smem, s);
     if (rc) return rc;
     ppo_finalize_kernel<<<1, 1, 0, s>>>(io->workspace, io->scalars, N, cfg->state_dim + 1, cfg->autoreg_weight,
                                         cfg->normalize_advantages);
