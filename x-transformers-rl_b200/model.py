@@ -166,8 +166,9 @@ class WorldModelActorCritic(nn.Module):
         ang = torch.arange(n, device=state.device, dtype=torch.float32)[:, None] * dec.rotary_pos_emb.inv_freq[None]
         ang = ang.repeat_interleave(2, dim=-1)                       # (n, rot) interleaved (t0,t0,t1,t1,..)
         cos, sin = ang.cos().to(x.dtype), ang.sin().to(x.dtype)
-        # key padding + causal, as an additive-free boolean mask (True = attend)
-        allow = mask[:, None, None, :] & torch.ones(n, n, dtype=torch.bool, device=state.device).tril()[None, None]
+        # Episodes are right-padded, so every padded key lies in the causal future of every valid query:
+        # the causal flag alone reproduces the reference's key-padding + causal mask on valid rows, and
+        # padded rows are zeroed after to_out exactly as the reference does (App. A.1) -- no mask tensor.
         first_v = None
         for l in range(cfg.depth):
             norm, attn = dec.layers[2 * l]
@@ -183,7 +184,7 @@ class WorldModelActorCritic(nn.Module):
                 else:
                     v = first_v * 0.5 + v * 0.5
             q, k = _rotate(q, cos, sin, rot), _rotate(k, cos, sin, rot)
-            out = F.scaled_dot_product_attention(q, k, v, attn_mask=allow, dropout_p=p_drop)
+            out = F.scaled_dot_product_attention(q, k, v, is_causal=True, dropout_p=p_drop)
             out = out.transpose(1, 2).reshape(b, n, h * dh)
             if cfg.gate_values:
                 out = out * attn.to_v_gate(xn).sigmoid()
