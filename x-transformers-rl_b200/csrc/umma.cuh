@@ -1,0 +1,101 @@
+// umma.cuh -- the few sm_100a primitives the dense part of the step kernel needs, as inline PTX:
+// mbarrier, 1-D TMA bulk copy (cp.async.bulk), TMEM allocation, tcgen05.mma (cta_group::1, kind::f16,
+// both operands from shared memory), tcgen05.commit, tcgen05.ld.  Descriptor encodings follow the PTX
+// ISA "tcgen05 matrix / instruction descriptor" tables (bit positions noted inline).
+//
+// Canonical K-major, no-swizzle operand image used here (one "core matrix" = 8 rows x 16 bytes, stored
+// as 128 contiguous bytes):   byte(r, kb) = (kb / 16) * LBO + (r / 8) * 128 + (r % 8) * 16 + kb % 16
+// i.e. 16-byte K-chunks are the outer dimension (stride LBO = rows * 16), 8-row groups are adjacent
+// (SBO = 128).  Weights are packed into this image on the host, so one bulk copy lands them ready.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace xtrl {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---- TMA: 1-D bulk copy global -> shared, completion on an mbarrier ------------------------------
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA / tensor core)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM --------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols) {        // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {           // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- descriptors -------------------------------------------------------------------------------
+// shared-memory matrix descriptor: [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
+// [49,52) base offset=0, [52] lbo mode=0, [61,64) layout type (0 = no swizzle)
+__device__ __forceinline__ uint64_t smem_desc(const void *p, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint64_t a = (smem_u32(p) & 0x3FFFFu) >> 4;
+    return a | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: [4,6) D fmt (1=f32), [7,10) A fmt, [10,13) B fmt (0=f16, 1=bf16),
+// [15] A major (0=K), [16] B major (0=K), [17,23) N>>3, [24,29) M>>4
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T   (one elected thread)
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all previously issued MMAs of this thread -> arrive on the mbarrier when they complete
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread i of the warp <-> TMEM lane
+// 32*(warp%4)+i).  taddr = base + (lane << 16) + column.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of element (row r, k) inside a canonical K-major image of `rows` rows, bf16
+__host__ __device__ constexpr int img_off_bf16(int rows, int r, int k) {
+    return (k >> 3) * rows * 16 + (r >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
+}
+
+}  // namespace umma
+}  // namespace xtrl
