@@ -148,6 +148,14 @@ def run_reference(args, w):
     }))
 
 
+def dense_name(dense):
+    return 'tcgen05 bf16 GEMMs, fp32 accumulate (TMEM)' if dense == 'bf16' else 'fp32 FFMA'
+
+
+def dtype_name(kv, dense):
+    return ('bf16' if dense == 'bf16' else 'f32') + f' dense / {"f32" if kv == "fp32" else "bf16"} KV cache, f32 accumulate'
+
+
 def workload_config(name, w, n_gpus, **extra):
     wm = w['world_model']
     return dict(workload=f'{name}: {w["envs"]} vectorised synthetic envs per GPU, state_dim={w["S"]} num_actions={w["A"]} '
@@ -173,16 +181,19 @@ def run_b200(args, w):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     B, T, S = w['envs'], w['T'], w['S']
     evolutionary = w['genes'] > 0
-    kw = dict(state_dim=S, num_actions=w['A'], reward_range=w['reward_range'], max_timesteps=T, world_model=w['world_model'],
-              batch_size=w['learn_batch'], num_episodes_per_update=(B // max(w['genes'], 1)) * world, epochs=args.learn_epochs,
-              evolutionary=evolutionary,
-              agent_kwargs=dict(save_path=os.path.join(tempfile.gettempdir(), f'xtrl_bench_{os.getpid()}.pt'),
-                                kv_cache_dtype=args.kv))
-    if evolutionary:
-        kw['latent_gene_pool'] = dict(dim=w['gene_dim'], num_genes_per_island=w['genes'], num_selected=2, tournament_size=2)
-    if args.learn_dtype == 'bf16':
-        kw['accelerate_kwargs'] = dict(mixed_precision='bf16')
-    learner = learner_mod.Learner(**kw)
+    def make_learner(kv, dense):
+        kw = dict(state_dim=S, num_actions=w['A'], reward_range=w['reward_range'], max_timesteps=T, world_model=w['world_model'],
+                  batch_size=w['learn_batch'], num_episodes_per_update=(B // max(w['genes'], 1)) * world, epochs=args.learn_epochs,
+                  evolutionary=evolutionary,
+                  agent_kwargs=dict(save_path=os.path.join(tempfile.gettempdir(), f'xtrl_bench_{os.getpid()}.pt'),
+                                    kv_cache_dtype=kv, rollout_dense_dtype=dense))
+        if evolutionary:
+            kw['latent_gene_pool'] = dict(dim=w['gene_dim'], num_genes_per_island=w['genes'], num_selected=2, tournament_size=2)
+        if args.learn_dtype == 'bf16':
+            kw['accelerate_kwargs'] = dict(mixed_precision='bf16')
+        return learner_mod.Learner(**kw)
+
+    learner = make_learner(args.kv, args.dense)
     acc, dev = learner.accelerator, learner.device
     rank = acc.process_index
     assert acc.num_processes == world == args.gpus or world == 1, (acc.num_processes, world, args.gpus)
@@ -192,8 +203,9 @@ def run_b200(args, w):
     gids = torch.tensor([p[1] for p in pairs[:B]], dtype=torch.int32, device=dev)
     agent = learner.agent
 
-    def one_pass(e):
-        buf, cum = learner.rollout_vectorized(e, gids, T)
+    def one_pass(e, lrn=None):
+        lrn = lrn or learner
+        buf, cum = lrn.rollout_vectorized(e, gids, T)
         returns = pkg.ops.gae(buf.rewards, buf.values, buf.is_boundary, agent.gamma, agent.lam, time_major=True)
         return buf, returns
 
@@ -225,14 +237,14 @@ def run_b200(args, w):
     result = {
         'metric': 'env-steps/sec (rollout)', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32' if args.kv == 'fp32' else 'f32 (bf16 KV cache)', 'data': 'synthetic',
-        'config': workload_config(args.workload, w, world, kv_cache=args.kv),
+        'vs_baseline': None, 'dtype': dtype_name(args.kv, args.dense), 'data': 'synthetic',
+        'config': workload_config(args.workload, w, world, kv_cache=args.kv, dense=dense_name(args.dense)),
         'gpu_launches': gpu_launches, 'clocks': clocks.summary(),
     }
 
     # ---- roofline of the dominant kernel: CUDA events around every wm_step launch of one more pass ----
-    if rank == 0 or world > 1:
-        st = learner._stepper(B, T)
+    def roofline_pass(lrn, kv):
+        st = lrn._stepper(B, T)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(T)]
         orig = st.step
 
@@ -241,11 +253,12 @@ def run_b200(args, w):
             evs[t][0].record(); r = orig(*a, **k); evs[t][1].record()
             return r
         st.step = wrapped
-        one_pass(env)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); one_pass(env, lrn); e1.record()
         torch.cuda.synchronize(dev)
         st.step = orig
         kern_ms = [a.elapsed_time(b) for a, b in evs]
-        kvb = 4 if args.kv == 'fp32' else 2
+        kvb = 4 if kv == 'fp32' else 2
         alg = sum(algorithmic_bytes_per_env_step(w, t, kvb) for t in range(T)) * B / T        # bytes per launch (avg)
         avg_s = sum(kern_ms) / T / 1e3
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
@@ -254,12 +267,32 @@ def run_b200(args, w):
         traffic = None
         prof = os.path.join(ROOT, 'profiles', 'r01_wm_step_traffic.json')
         if os.path.exists(prof):
-            traffic = json.load(open(prof)).get(f'{args.workload}_{args.kv}')
-        result['roofline'] = dict(kernel='wm_step_kernel', bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
-                                  frac=achieved / peak, traffic=traffic,
-                                  peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s',
-                                  bytes_per_launch=alg, launch_ms_avg=avg_s * 1e3, launch_ms_first=kern_ms[0],
-                                  launch_ms_last=kern_ms[-1], kernel_share_of_step=sum(kern_ms) / (ms / args.steps))
+            traffic = json.load(open(prof)).get(f'{args.workload}_{kv}')
+        return dict(kernel='wm_step_kernel', bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                    traffic=traffic, peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s',
+                    bytes_per_launch=alg, launch_ms_avg=avg_s * 1e3, launch_ms_first=kern_ms[0], launch_ms_last=kern_ms[-1],
+                    kernel_share_of_step=sum(kern_ms) / e0.elapsed_time(e1))
+
+    result['roofline'] = roofline_pass(learner, args.kv)
+
+    # ---- the other precision classes of the same rollout (same workload, same measurement) ----------
+    if not args.no_variants and world == 1:
+        result['variants'] = {}
+        for kv, dense in (('fp32', 'fp32'), ('bf16', 'bf16')):
+            if (kv, dense) == (args.kv, args.dense):
+                continue
+            learner._steppers.clear()                       # one KV cache alive at a time
+            torch.cuda.empty_cache()
+            lv = make_learner(kv, dense)
+            for _ in range(2):
+                one_pass(env, lv)
+            vms, _ = timed(lambda: one_pass(env, lv), 2)
+            rf = roofline_pass(lv, kv)
+            result['variants'][f'kv_{kv}+dense_{dense}'] = dict(
+                value=B * T * 2 / (vms / 1e3), unit='env-steps/s', dtype=dtype_name(kv, dense), roofline_frac=rf['frac'],
+                roofline_achieved_gbs=rf['achieved'], parity_class='1e-5 (fp32, equals the reference)' if dense == 'fp32' and kv == 'fp32' else '1e-2 (bf16)')
+            lv._steppers.clear(); del lv
+            torch.cuda.empty_cache()
 
     # ---- learn leg: PPO learn-timesteps/sec of Agent.learn on the trajectories just collected --------
     if not args.no_learn:
@@ -300,6 +333,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=('b200', 'reference'))
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--kv', default='fp32', choices=('fp32', 'bf16'))
+    ap.add_argument('--dense', default='bf16', choices=('fp32', 'bf16'),
+                    help='rollout QKV/out/FFN/head GEMMs: bf16 = tcgen05 tensor cores (1e-2 class), fp32 = FFMA (1e-5 class)')
+    ap.add_argument('--no-variants', action='store_true')
     ap.add_argument('--learn-dtype', default='bf16', choices=('fp32', 'bf16'))
     ap.add_argument('--learn-epochs', type=int, default=4)
     ap.add_argument('--cpu-seconds', type=float, default=15.)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define XTRL_ABI_VERSION 1
+#define XTRL_ABI_VERSION 2
 
 #define XTRL_OK            0
 #define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
@@ -58,6 +58,9 @@ typedef struct xtrl_model_desc {
     int32_t rotary_true_pos;  /* 0 = reference behaviour (all rollout positions 0) */
     int32_t kv_bf16;          /* 0 = fp32 KV cache, 1 = bf16 KV cache                         */
     float   reward_min, reward_max;   /* HL-Gauss support (reward_range)                      */
+    int32_t dense_bf16;       /* 0 = dense layers in fp32 FFMA (1e-5 parity with the fp32 reference);
+                                 1 = QKV/out/FFN/head GEMMs on tcgen05 tensor cores, bf16 operands, fp32
+                                 accumulation in TMEM (the 1e-2 "bf16" tolerance class)              */
 } xtrl_model_desc;
 
 /* offsets (in floats) of every tensor inside the packed fp32 weight blob the step kernel reads.
@@ -98,6 +101,12 @@ typedef struct xtrl_weight_layout {
 /* fills *out; HOST pointers.  Pure host arithmetic (usable without a GPU).                    */
 int xtrl_wm_weight_layout(const xtrl_model_desc *desc, xtrl_weight_layout *out);
 
+/* tensor-core path (desc->dense_bf16): size of, and packing into, the bf16 operand images the UMMA
+ * descriptors read (128-row tiles, canonical K-major no-swizzle core-matrix layout).  xtrl_wm_pack_tc
+ * converts the fp32 blob above on the device; pass the result as xtrl_step_io.tc_weights.            */
+int64_t xtrl_wm_tc_weights_bytes(const xtrl_model_desc *desc);
+int     xtrl_wm_pack_tc(const xtrl_model_desc *desc, const float *weights, void *tc_weights, void *stream);
+
 /* bytes of KV cache the caller must allocate for `num_envs` envs:
  *   [2 (k,v)][L][num_envs][H][Tmax][dim_head] in fp32 or bf16.                                */
 int64_t xtrl_wm_kv_cache_bytes(const xtrl_model_desc *desc, int64_t num_envs);
@@ -118,6 +127,7 @@ typedef struct xtrl_step_io {
     const int32_t *forced_action; /* [B] or NULL: evaluate log-prob of this action instead    */
     float          reward_flag;   /* the per-forward reward-conditioning flag (:501-503)      */
     int32_t        pos_uniform;   /* used when pos == NULL                                    */
+    const void    *tc_weights;    /* xtrl_wm_pack_tc output; required iff desc->dense_bf16     */
     /* outputs (any may be NULL) */
     int32_t *action;              /* [B]                                                      */
     float   *log_prob;            /* [B] log(clamp(p[a], eps, 1-eps))                         */

@@ -10,13 +10,13 @@ ops = importlib.import_module('x-transformers-rl_b200').ops
 ap = argparse.ArgumentParser()
 ap.add_argument('--envs', type=int, default=4096); ap.add_argument('--T', type=int, default=500)
 ap.add_argument('--depth', type=int, default=4); ap.add_argument('--heads', type=int, default=8)
-ap.add_argument('--bf16', action='store_true'); ap.add_argument('--reps', type=int, default=2)
+ap.add_argument('--bf16', action='store_true'); ap.add_argument('--reps', type=int, default=2); ap.add_argument('--tc', action='store_true')
 a = ap.parse_args()
 dev = 'cuda'
 cfg = R.Config(state_dim=8, num_actions=4, heads=a.heads, depth=a.depth, reward_range=(-5., 5.))
 sd = random_state_dict(cfg, seed=0)
 B, T = a.envs, a.T
-st = ops.WorldModelStepper(model_config(cfg, T, kv_bf16=a.bf16), B, dev)
+st = ops.WorldModelStepper(model_config(cfg, T, kv_bf16=a.bf16, dense_bf16=a.tc), B, dev)
 st.load_state_dict({k: v.to(dev) for k, v in sd.items()})
 states = torch.randn(T, B, 8, device=dev); rewards = torch.randn(T, B, device=dev); u = torch.rand(T, B, device=dev)
 mean, var = torch.zeros(9, device=dev), torch.ones(9, device=dev)

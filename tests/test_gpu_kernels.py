@@ -304,6 +304,35 @@ def test_wm_step_sampling_and_rsnorm():
     assert rel_err(out['value'].cpu(), R.hl_decode(va, cfg)) < 3e-5
 
 
+@pytest.mark.parametrize('kw', [
+    dict(heads=8, depth=4, state_dim=8, num_actions=4),                                      # c3
+    dict(heads=4, depth=4, state_dim=8, num_actions=4, gate_values=True, value_residual=True,
+         learned_mix=True, evolutionary=True, dim_gene=32),                                  # c2: NQ=260 -> 3 tiles, HIN=144
+    dict(heads=8, depth=2, state_dim=8, num_actions=4, gate_values=True, value_residual=True, learned_mix=True),  # NQ=520: 5 tiles, 2 weight groups
+])
+@pytest.mark.parametrize('kv_bf16', (False, True))
+def test_wm_step_tensor_core_dense(kw, kv_bf16):
+    """tcgen05 path (bf16 operands, fp32 accumulation in TMEM) against the fp32 oracle: the 1e-2 class."""
+    cfg = R.Config(reward_range=(-5., 5.), **kw)
+    sd = random_state_dict(cfg, seed=1)
+    B, T = 37, 40
+    g = torch.Generator().manual_seed(2)
+    states, prev_r = torch.randn(B, T, cfg.state_dim, generator=g), torch.randn(B, T, generator=g)
+    prev_a = torch.randint(-1, cfg.num_actions, (B, T), generator=g)
+    genes = gene_ids = gene_n = None
+    if cfg.evolutionary:
+        genes = torch.randn(5, cfg.dim_gene, generator=g)
+        gene_ids = torch.randint(0, 5, (B,), generator=g)
+        gene_n = torch.nn.functional.normalize(genes[gene_ids], dim=-1)
+    ra, va, val = _rollout_kernel(sd, cfg, states, prev_a, prev_r, genes=genes, gene_ids=gene_ids, dense_bf16=True, kv_bf16=kv_bf16)
+    want_ra, want_va = _rollout_oracle(sd, cfg, states, prev_a, prev_r, gene_n)
+    assert rel_err(ra, want_ra) < 2e-2
+    assert rel_err(va, want_va) < 2e-2
+    assert rel_err(val, R.hl_decode(want_va, cfg)) < 2e-2
+    # and it is NOT the fp32 path in disguise: bf16 rounding must be visible
+    assert rel_err(ra, want_ra) > 1e-5
+
+
 def test_wm_step_bf16_kv_cache():
     cfg = R.Config(state_dim=8, num_actions=4, heads=8, depth=4, reward_range=(-5., 5.))
     sd = random_state_dict(cfg, seed=1)

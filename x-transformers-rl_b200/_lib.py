@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-XTRL_ABI_VERSION = 1
+XTRL_ABI_VERSION = 2
 XTRL_MAX_DEPTH = 16
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -21,7 +21,7 @@ class ModelDesc(C.Structure):
     _fields_ = [(n, c_i32) for n in (
         'state_dim', 'num_actions', 'dim', 'heads', 'dim_head', 'depth', 'num_bins', 'dim_gene',
         'gate_values', 'value_residual', 'learned_mix', 'max_timesteps', 'rotary_true_pos', 'kv_bf16')] + [
-        ('reward_min', c_f32), ('reward_max', c_f32)]
+        ('reward_min', c_f32), ('reward_max', c_f32), ('dense_bf16', c_i32)]
 
 
 class _LayerLayout(C.Structure):
@@ -39,7 +39,7 @@ class WeightLayout(C.Structure):
 class StepIO(C.Structure):
     _fields_ = [(n, c_vp) for n in ('state', 'prev_action', 'prev_reward', 'pos', 'rs_mean', 'rs_var',
                                     'genes', 'gene_ids', 'uniform', 'forced_action')] + [
-        ('reward_flag', c_f32), ('pos_uniform', c_i32)] + [(n, c_vp) for n in ('action', 'log_prob', 'value', 'raw_actions', 'value_logits')]
+        ('reward_flag', c_f32), ('pos_uniform', c_i32), ('tc_weights', c_vp)] + [(n, c_vp) for n in ('action', 'log_prob', 'value', 'raw_actions', 'value_logits')]
 
 
 class LossCfg(C.Structure):
@@ -76,6 +76,8 @@ SYMBOLS = {
     'xtrl_device_sm': (c_i32, []),
     'xtrl_wm_weight_layout': (c_i32, [C.POINTER(ModelDesc), C.POINTER(WeightLayout)]),
     'xtrl_wm_kv_cache_bytes': (c_i64, [C.POINTER(ModelDesc), c_i64]),
+    'xtrl_wm_tc_weights_bytes': (c_i64, [C.POINTER(ModelDesc)]),
+    'xtrl_wm_pack_tc': (c_i32, [C.POINTER(ModelDesc), c_vp, c_vp, c_vp]),
     'xtrl_wm_step': (c_i32, [C.POINTER(ModelDesc), c_vp, c_vp, C.POINTER(StepIO), c_i32, c_vp]),
     'xtrl_gae': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_i64, c_f32, c_f32, c_vp]),
     'xtrl_ppo_loss_workspace_bytes': (c_i64, []),

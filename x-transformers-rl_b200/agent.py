@@ -97,7 +97,7 @@ class Agent(nn.Module):
                  evolve_after_step=20, latent_gene_pool=None, world_model=None, dropout=0.25, max_grad_norm=0.5,
                  frac_actor_critic_head_gradient=0.5, ema_kwargs=None, save_path='./ppo.pt', accelerator=None,
                  actor_loss_weight=1., critic_loss_weight=1., autoregressive_loss_weight=1.,
-                 rollout_positions='reference', kv_cache_dtype='fp32'):
+                 rollout_positions='reference', kv_cache_dtype='fp32', rollout_dense_dtype='fp32'):
         super().__init__()
         if continuous_actions:
             raise NotImplementedError('continuous actions are outside the B200 hot path built so far (SURVEY 8f row 4); '
@@ -119,7 +119,8 @@ class Agent(nn.Module):
         self.cfg = ops.ModelConfig.from_learner_kwargs(
             state_dim, num_actions, reward_range, max_timesteps, world_model, hidden_dim=hidden_dim,
             num_bins=critic_pred_num_bins, dim_gene=self.gene_pool.dim_gene if evolutionary else 0,
-            rotary_true_pos=(rollout_positions == 'true'), kv_bf16=(kv_cache_dtype == 'bf16'))
+            rotary_true_pos=(rollout_positions == 'true'), kv_bf16=(kv_cache_dtype == 'bf16'),
+            dense_bf16=(rollout_dense_dtype == 'bf16'))
         self.model = WorldModelActorCritic(self.cfg, dropout=dropout,
                                            frac_actor_critic_head_gradient=frac_actor_critic_head_gradient)
         self.loss_cfg = ops.LossConfig(num_actions=num_actions, num_bins=critic_pred_num_bins, state_dim=state_dim,

@@ -17,6 +17,7 @@
 // (max, sum, acc[16]) states are merged once by shuffles.  Dense parts: fp32 FFMA with weights
 // stored K-major so a warp reads consecutive output features (coalesced, L1/L2 resident).
 #include "common.cuh"
+#include "umma.cuh"
 #include <math.h>
 
 namespace xtrl {
@@ -41,7 +42,7 @@ static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
 struct StepDims {
     int S, Spad, A, Apad, D, H, I, L, K, Kpad, G, NQ, HIN, Tmax;
-    int gate, vres, mix, rot, kvbf16;
+    int gate, vres, mix, rot, kvbf16, tc;
 };
 
 static int make_dims(const xtrl_model_desc *d, StepDims *o) {
@@ -52,7 +53,7 @@ static int make_dims(const xtrl_model_desc *d, StepDims *o) {
     o->mix = o->vres && d->learned_mix != 0;
     o->NQ = 3 * o->I + (o->gate ? o->I : 0) + (o->mix ? ((o->H + 3) & ~3) : 0);
     o->HIN = (d->dim_gene > 0 ? 3 : 2) * d->dim; o->Tmax = d->max_timesteps;
-    o->rot = d->rotary_true_pos != 0; o->kvbf16 = d->kv_bf16 != 0;
+    o->rot = d->rotary_true_pos != 0; o->kvbf16 = d->kv_bf16 != 0; o->tc = d->dense_bf16 != 0;
     return 0;
 }
 
@@ -70,6 +71,8 @@ static int check_desc(const xtrl_model_desc *d) {
                  "dim_gene=%d: must be a multiple of 4 in [0,256]", d->dim_gene);
     XTRL_REQUIRE(d->max_timesteps >= 1, XTRL_E_BADARG, "max_timesteps=%d", d->max_timesteps);
     XTRL_REQUIRE(!d->learned_mix || d->value_residual, XTRL_E_BADARG, "learned_mix without value_residual");
+    XTRL_REQUIRE(!d->dense_bf16 || d->dim % 16 == 0, XTRL_E_UNSUPPORTED,
+                 "dense_bf16: hidden dim %d must be a multiple of 16 (UMMA K step)", d->dim);
     return XTRL_OK;
 }
 
@@ -123,6 +126,40 @@ extern "C" int64_t xtrl_wm_kv_cache_bytes(const xtrl_model_desc *desc, int64_t n
 
 namespace xtrl {
 
+// ---- tensor-core path: where each GEMM's bf16 operand image lives in the tc blob (byte offsets) ----------
+constexpr int kWbufBytes = 49152;          // shared-memory weight stage: one 128 x 192 bf16 tile (FF2), 4 tiles at K=48
+struct TcLayout {
+    int64_t total;
+    int tiles_q, tiles_f;
+    int64_t qkv[XTRL_MAX_DEPTH], out[XTRL_MAX_DEPTH], ff1[XTRL_MAX_DEPTH], ff2[XTRL_MAX_DEPTH];
+    int64_t head_a, head_c;
+};
+static TcLayout tc_layout(const StepDims &d) {
+    TcLayout t{};
+    int64_t o = 0;
+    auto take = [&](int tiles, int K) { int64_t at = o; o += (int64_t)tiles * 128 * K * 2; return at; };
+    t.tiles_q = (d.NQ + 127) / 128; t.tiles_f = (4 * d.D + 127) / 128;
+    for (int l = 0; l < d.L; ++l) {
+        t.qkv[l] = take(t.tiles_q, d.D); t.out[l] = take(1, d.I);
+        t.ff1[l] = take(t.tiles_f, d.D); t.ff2[l] = take(1, 4 * d.D);
+    }
+    t.head_a = take(1, d.HIN); t.head_c = take(1, d.HIN);
+    t.total = o;
+    return t;
+}
+
+// fp32 K-major W[K][ld] (columns coff .. coff+nvalid) -> bf16 canonical 128-row tile images
+__global__ void pack_tc_kernel(const float *__restrict__ src, int ld, int coff, int nvalid, int K, int tiles,
+                               __nv_bfloat16 *__restrict__ dst) {
+    const int64_t total = (int64_t)tiles * 128 * K;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tile = (int)(i / (128 * K)), rem = (int)(i - (int64_t)tile * 128 * K), r = rem / K, k = rem - r * K;
+        const int n = tile * 128 + r;
+        const float v = n < nvalid ? src[(int64_t)k * ld + coff + n] : 0.f;
+        dst[(int64_t)tile * 128 * K + umma::img_off_bf16(128, r, k) / 2] = __float2bfloat16_rn(v);
+    }
+}
+
 struct StepArgs {
     StepDims d;
     xtrl_weight_layout w;
@@ -132,15 +169,35 @@ struct StepArgs {
     int B;
     float reward_lo, reward_hi;
     float hl_step;
+    TcLayout tc;
+    const unsigned char *tcw;
 };
 
 struct Smem {                       // offsets in floats into the dynamic shared-memory block
     int x, xn, qkv, v1, ao, ff, st, hin, gene, logit, total;
+    int wbuf, xn_img, ao_img, ff_img, hin_img, bars;       // tensor-core path only
 };
 
 __host__ __device__ static inline Smem smem_layout(const StepDims &d) {
-    Smem s; int o = 0;
+    Smem s{}; int o = 0;
     auto take = [&](int n) { int at = o; o += (n + 3) & ~3; return at; };
+    if (d.tc) {
+        // operands of the GEMMs live only as bf16 UMMA images; fp32 copies exist only where SIMT code reads them
+        s.wbuf = take(kWbufBytes / 4);                                   // first: 128-byte aligned with the block
+        s.xn_img = take(kTE * d.D / 2); s.ao_img = take(kTE * d.I / 2);
+        s.ff_img = take(kTE * 4 * d.D / 2); s.hin_img = take(kTE * d.HIN / 2);
+        s.bars = take(8);
+        s.x = take(kTE * d.D);
+        s.qkv = take(kTE * d.NQ > kTE * 4 * d.D ? kTE * d.NQ : kTE * 4 * d.D);   // later reused as the fp32 head hidden
+        s.ff = s.qkv;
+        s.v1 = take(d.vres ? kTE * d.I : 0);
+        s.st = take(kTE * (d.Spad + 4));
+        s.gene = take(kTE * d.G);
+        s.logit = take(kTE * (d.Apad + d.Kpad));
+        s.xn = s.ao = s.hin = 0;
+        s.total = o;
+        return s;
+    }
     s.x = take(kTE * d.D);
     s.xn = take(kTE * d.D);
     s.qkv = take(kTE * d.NQ > kSplitK * kTE * d.D ? kTE * d.NQ : kSplitK * kTE * d.D);   // also split-K scratch
@@ -229,6 +286,21 @@ __device__ __forceinline__ void layer_norm_tile(const float *__restrict__ sIn, f
     }
 }
 
+// same normalisation, written as the bf16 B-operand image of the next GEMM (kTE rows, K = D)
+__device__ __forceinline__ void layer_norm_img(const float *__restrict__ sIn, unsigned char *__restrict__ img,
+                                               const float *__restrict__ gamma, int D) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = warp; e < kTE; e += kThreads / 32) {
+        const float a = lane < D ? sIn[e * D + lane] : 0.f;
+        const float b = lane + 32 < D ? sIn[e * D + lane + 32] : 0.f;
+        const float mean = warp_sum(a + b) / (float)D;
+        const float da = lane < D ? a - mean : 0.f, db = lane + 32 < D ? b - mean : 0.f;
+        const float rstd = rsqrtf(warp_sum(da * da + db * db) / (float)D + 1e-5f);
+        if (lane < D) *(__nv_bfloat16 *)(img + umma::img_off_bf16(kTE, e, lane)) = __float2bfloat16_rn(da * rstd * __ldg(gamma + lane));
+        if (lane + 32 < D) *(__nv_bfloat16 *)(img + umma::img_off_bf16(kTE, e, lane + 32)) = __float2bfloat16_rn(db * rstd * __ldg(gamma + lane + 32));
+    }
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -255,10 +327,10 @@ template <> struct KvTraits<__nv_bfloat16> {
     static __device__ __forceinline__ void store1(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
-template <typename KV>
+template <typename KV, bool TC>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 wm_step_kernel(const StepArgs a) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     const StepDims &d = a.d;
     const Smem so = smem_layout(d);
     float *sx = sm + so.x, *sxn = sm + so.xn, *sqkv = sm + so.qkv, *sv1 = sm + so.v1, *sao = sm + so.ao;
@@ -270,6 +342,61 @@ wm_step_kernel(const StepArgs a) {
     const int lst = Spad + 4;
     using TR = KvTraits<KV>;
     constexpr int EP = TR::EP, PPR = TR::PPR, RPI = 32 / TR::PPR;     // elems per piece, pieces per row, rows per LDG
+
+    // ---- tensor-core plumbing (TC): one weight stage fed by TMA bulk copies, accumulators in TMEM ----
+    unsigned char *wbuf = (unsigned char *)(sm + so.wbuf), *xn_img = (unsigned char *)(sm + so.xn_img);
+    unsigned char *ao_img = (unsigned char *)(sm + so.ao_img), *ff_img = (unsigned char *)(sm + so.ff_img);
+    unsigned char *hin_img = (unsigned char *)(sm + so.hin_img);
+    uint64_t *bars = (uint64_t *)(sm + so.bars);                        // [0] weights landed, [1] MMAs complete
+    uint32_t *tslot = (uint32_t *)(bars + 2);
+    uint32_t tbase = 0, pw = 0, pm = 0;                                 // TMEM base, barrier phase parities
+    constexpr uint32_t kTmemCols = 64;                                  // up to 4 tiles x 16 fp32 columns
+    auto tc_load = [&](int64_t off, uint32_t bytes) {                   // thread 0: next weights -> wbuf
+        if (tid == 0) { umma::mbar_expect_tx(&bars[0], bytes); umma::bulk_g2s(wbuf, a.tcw + off, bytes, &bars[0]); }
+    };
+    // D[tile t] = W_tile[128 x K] * X[kTE x K]^T for nt tiles; returns when the accumulators are complete
+    auto tc_mma = [&](int nt, int K, const unsigned char *bimg) {
+        if (tid == 0) {
+            umma::mbar_wait(&bars[0], pw);
+            umma::tc_fence_after();
+            const uint32_t idesc = umma::idesc_bf16(128, kTE);
+            for (int t = 0; t < nt; ++t)
+                for (int s = 0; s < K / 16; ++s)
+                    umma::mma_bf16_ss(tbase + t * kTE, umma::smem_desc(wbuf + (size_t)t * 128 * K * 2 + s * 2 * (128 * 16), 128 * 16, 128),
+                                      umma::smem_desc(bimg + s * 2 * (kTE * 16), kTE * 16, 128), idesc, s > 0);
+            umma::mma_commit(&bars[1]);
+        }
+        pw ^= 1;
+        umma::mbar_wait(&bars[1], pm);
+        pm ^= 1;
+        umma::tc_fence_after();
+    };
+    // accumulators -> registers: warp (q = warp%4, half = warp/4) reads TMEM lanes 32q.. and 8 of the 16 env
+    // columns of every tile; thread <-> output feature.  epi(e, f, acc).  Ends with a CTA barrier.
+    auto tc_epilogue = [&](int nt, int tile0, auto epi) {
+        const int q = warp & 3, half = warp >> 2;
+        for (int t = 0; t < nt; ++t) {
+            float v[8];
+            umma::tmem_ld8(tbase + t * kTE + half * 8 + ((uint32_t)(q * 32) << 16), v);
+            const int f = (tile0 + t) * 128 + q * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) epi(half * 8 + j, f, v[j]);
+        }
+        umma::tc_fence_before();
+        umma::fence_proxy_async();
+        __syncthreads();
+    };
+    if constexpr (TC) {
+        static_assert(kTE == 16 && kThreads == 256, "the UMMA path is built for 16 envs (N=16) and 8 warps per CTA");
+        if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::fence_mbar_init(); }
+        if (warp == 0) umma::tmem_alloc(tslot, kTmemCols);
+        umma::tc_fence_before();
+        __syncthreads();
+        umma::tc_fence_after();
+        tbase = *tslot;
+        const int g0 = min(a.tc.tiles_q, kWbufBytes / (128 * D * 2));
+        tc_load(a.tc.qkv[0], (uint32_t)g0 * 128 * D * 2);               // layer 0 QKV weights fly during the prologue
+    }
 
     // ---- RSNorm.eval on (state || prev reward) (:588-594); gene rows l2-normalised (evolution.py:73-74)
     for (int i = tid; i < kTE * lst; i += kThreads) {
@@ -307,12 +434,16 @@ wm_step_kernel(const StepArgs a) {
             }
             sx[e * D + n] = v;
         } else {
-            shin[e * d.HIN + n] = acc + __ldg(W + a.w.state_embed_bias + n - D);          // to_state_embed
+            const float v = acc + __ldg(W + a.w.state_embed_bias + n - D);                  // to_state_embed
+            if constexpr (TC) *(__nv_bfloat16 *)(hin_img + umma::img_off_bf16(kTE, e, n)) = __float2bfloat16_rn(v);
+            else shin[e * d.HIN + n] = v;
         }
     });
     if (d.G > 0) {
         dense_tile<kTE / 8, 1>(W + a.w.latent_w, d.G, D, sgene, d.G, [&](int e, int n, int, float acc) {
-            shin[e * d.HIN + 2 * D + n] = acc + __ldg(W + a.w.latent_b + n);              // latent_to_embed
+            const float v = acc + __ldg(W + a.w.latent_b + n);                              // latent_to_embed
+            if constexpr (TC) *(__nv_bfloat16 *)(hin_img + umma::img_off_bf16(kTE, e, 2 * D + n)) = __float2bfloat16_rn(v);
+            else shin[e * d.HIN + 2 * D + n] = v;
         });
     }
     __syncthreads();
@@ -323,15 +454,32 @@ wm_step_kernel(const StepArgs a) {
 
     for (int l = 0; l < d.L; ++l) {
         const auto &wl = a.w.layer[l];
-        layer_norm_tile(sx, sxn, D, W + wl.ln1_gamma, D);
-        __syncthreads();
-        // fused q | k | v | gate | mix projection
-        dense_tile<kTE / 2, 1>(W + wl.qkv_w, D, NQ, sxn, D, [&](int e, int n, int, float acc) {
-            float v = acc + __ldg(W + wl.qkv_b + n);
-            if (n >= 3 * I) v = sigmoidf_(v);                  // to_v_gate / to_value_residual_mix
-            sqkv[e * NQ + n] = v;
-        });
-        __syncthreads();
+        const int wgroup = kWbufBytes / (128 * D * 2);                   // 128-row tiles of a K = D GEMM per weight stage
+        auto qkv_epi = [&](int e, int n, float acc) {
+            if (n < NQ) {
+                float v = acc + __ldg(W + wl.qkv_b + n);
+                if (n >= 3 * I) v = sigmoidf_(v);              // to_v_gate / to_value_residual_mix
+                sqkv[e * NQ + n] = v;
+            }
+        };
+        if constexpr (TC) {
+            layer_norm_img(sx, xn_img, W + wl.ln1_gamma, D);
+            umma::fence_proxy_async();
+            __syncthreads();
+            for (int t0 = 0; t0 < a.tc.tiles_q; t0 += wgroup) {
+                const int nt = min(wgroup, a.tc.tiles_q - t0), t1 = t0 + nt;
+                tc_mma(nt, D, xn_img);
+                if (t1 < a.tc.tiles_q) tc_load(a.tc.qkv[l] + (int64_t)t1 * 128 * D * 2, (uint32_t)min(wgroup, a.tc.tiles_q - t1) * 128 * D * 2);
+                else tc_load(a.tc.out[l], 128u * I * 2);
+                tc_epilogue(nt, t0, qkv_epi);
+            }
+        } else {
+            layer_norm_tile(sx, sxn, D, W + wl.ln1_gamma, D);
+            __syncthreads();
+            // fused q | k | v | gate | mix projection
+            dense_tile<kTE / 2, 1>(W + wl.qkv_w, D, NQ, sxn, D, [&](int e, int n, int, float acc) { qkv_epi(e, n, acc); });
+            __syncthreads();
+        }
         // value residual (App. A.1) and, in true-position mode, rotary on q and the new k
         if (d.vres) {
             const int mix_off = 3 * I + (d.gate ? I : 0);
@@ -464,10 +612,35 @@ wm_step_kernel(const StepArgs a) {
                     const int dd = sub * EP + t;
                     float o = acc[t] * inv;
                     if (d.gate) o *= sqkv[e * NQ + 3 * I + h * kDH + dd];
-                    sao[e * I + h * kDH + dd] = o;
+                    if constexpr (TC) *(__nv_bfloat16 *)(ao_img + umma::img_off_bf16(kTE, e, h * kDH + dd)) = __float2bfloat16_rn(o);
+                    else sao[e * I + h * kDH + dd] = o;
                 }
             }
         }
+        if constexpr (TC) {
+            umma::fence_proxy_async();
+            __syncthreads();
+            // to_out + residual
+            tc_mma(1, I, ao_img);
+            tc_load(a.tc.ff1[l], (uint32_t)min(wgroup, a.tc.tiles_f) * 128 * D * 2);
+            tc_epilogue(1, 0, [&](int e, int n, float acc) { if (n < D) sx[e * D + n] += acc; });
+            layer_norm_img(sx, xn_img, W + wl.ln2_gamma, D);
+            umma::fence_proxy_async();
+            __syncthreads();
+            for (int t0 = 0; t0 < a.tc.tiles_f; t0 += wgroup) {
+                const int nt = min(wgroup, a.tc.tiles_f - t0), t1 = t0 + nt;
+                tc_mma(nt, D, xn_img);
+                if (t1 < a.tc.tiles_f) tc_load(a.tc.ff1[l] + (int64_t)t1 * 128 * D * 2, (uint32_t)min(wgroup, a.tc.tiles_f - t1) * 128 * D * 2);
+                else tc_load(a.tc.ff2[l], 128u * 4 * D * 2);
+                tc_epilogue(nt, t0, [&](int e, int n, float acc) {
+                    if (n < 4 * D) *(__nv_bfloat16 *)(ff_img + umma::img_off_bf16(kTE, e, n)) = __float2bfloat16_rn(gelu_erf(acc + __ldg(W + wl.ff1_b + n)));
+                });
+            }
+            tc_mma(1, 4 * D, ff_img);
+            if (l + 1 < d.L) tc_load(a.tc.qkv[l + 1], (uint32_t)min(wgroup, a.tc.tiles_q) * 128 * D * 2);
+            else tc_load(a.tc.head_a, 128u * d.HIN * 2);
+            tc_epilogue(1, 0, [&](int e, int n, float acc) { if (n < D) sx[e * D + n] += acc + __ldg(W + wl.ff2_b + n); });
+        } else {
         __syncthreads();
         // to_out + residual
         dense_residual(W + wl.out_w, I, D, sao, I, sqkv, sx, [](int) { return 0.f; });   // sqkv is dead here: scratch
@@ -480,15 +653,28 @@ wm_step_kernel(const StepArgs a) {
         __syncthreads();
         dense_residual(W + wl.ff2_w, 4 * D, D, sff, 4 * D, sqkv, sx, [&](int n) { return __ldg(W + wl.ff2_b + n); });
         __syncthreads();
+        }
     }
 
     // ---- final norm -> heads (:533-557)
+    if constexpr (TC) {
+        layer_norm_img(sx, hin_img, W + a.w.final_gamma, D);               // embed -> columns [0, D) of the head input
+        umma::fence_proxy_async();
+        __syncthreads();
+        tc_mma(1, d.HIN, hin_img);                                         // action_head.0
+        tc_load(a.tc.head_c, 128u * d.HIN * 2);
+        tc_epilogue(1, 0, [&](int e, int n, float acc) { if (n < 2 * D) sff[e * 4 * D + n] = silu(acc + __ldg(W + a.w.head1_b + n)); });
+        tc_mma(1, d.HIN, hin_img);                                         // critic_head.0
+        tc_epilogue(1, 0, [&](int e, int n, float acc) { if (n < 2 * D) sff[e * 4 * D + 2 * D + n] = silu(acc + __ldg(W + a.w.head1_b + 2 * D + n)); });
+        if (warp == 0) umma::tmem_dealloc(tbase, kTmemCols);               // no tcgen05 op follows
+    } else {
     layer_norm_tile(sx, shin, d.HIN, W + a.w.final_gamma, D);
     __syncthreads();
     dense_tile<kTE / 4, 1>(W + a.w.head1_w, d.HIN, 4 * D, shin, d.HIN, [&](int e, int n, int, float acc) {
         sff[e * 4 * D + n] = silu(acc + __ldg(W + a.w.head1_b + n));
     });
     __syncthreads();
+    }
     const int ll = d.Apad + d.Kpad;
     dense_tile<1, 1>(W + a.w.actor2_w, 2 * D, d.Apad, sff, 4 * D, [&](int e, int n, int, float acc) {
         slog[e * ll + n] = acc + __ldg(W + a.w.actor2_b + n);
@@ -572,16 +758,68 @@ extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, v
     a.hl_step = (desc->reward_max - desc->reward_min) / (float)desc->num_bins;
     const Smem so = smem_layout(a.d);
     const size_t smem = (size_t)so.total * sizeof(float);
-    XTRL_REQUIRE(smem <= 110 * 1024, XTRL_E_UNSUPPORTED, "xtrl_wm_step: configuration needs %zu B shared memory per CTA (max 110 KiB)", smem);
+    XTRL_REQUIRE(smem <= 200 * 1024, XTRL_E_UNSUPPORTED, "xtrl_wm_step: configuration needs %zu B shared memory per CTA (max 200 KiB)", smem);
+    a.tcw = (const unsigned char *)io->tc_weights;
+    if (a.d.tc) {
+        XTRL_REQUIRE(io->tc_weights, XTRL_E_BADARG, "xtrl_wm_step: dense_bf16 needs io->tc_weights (xtrl_wm_pack_tc)");
+        XTRL_REQUIRE(((uintptr_t)io->tc_weights & 15) == 0, XTRL_E_BADARG, "xtrl_wm_step: tc_weights must be 16-byte aligned");
+        XTRL_REQUIRE(128 * 4 * a.d.D * 2 <= kWbufBytes && 128 * a.d.I * 2 <= kWbufBytes && 128 * a.d.HIN * 2 <= kWbufBytes,
+                     XTRL_E_UNSUPPORTED, "xtrl_wm_step: dense_bf16 weight tile exceeds the %d-byte stage (dim=%d heads=%d)", kWbufBytes, a.d.D, a.d.H);
+        a.tc = tc_layout(a.d);
+    }
     const int blocks = (num_envs + kTE - 1) / kTE;
     cudaStream_t s = (cudaStream_t)stream;
-    if (desc->kv_bf16) {
-        XTRL_CUDA(cudaFuncSetAttribute(wm_step_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        wm_step_kernel<__nv_bfloat16><<<blocks, kThreads, smem, s>>>(a);
-    } else {
-        XTRL_CUDA(cudaFuncSetAttribute(wm_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        wm_step_kernel<float><<<blocks, kThreads, smem, s>>>(a);
+    auto launch = [&](auto kern) -> int {
+        XTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, kThreads, smem, s>>>(a);
+        XTRL_LAUNCH_CHECK("wm_step_kernel");
+        return XTRL_OK;
+    };
+    if (a.d.tc) {
+#if XTRL_TE == 16
+        return desc->kv_bf16 ? launch(wm_step_kernel<__nv_bfloat16, true>) : launch(wm_step_kernel<float, true>);
+#else
+        return fail(XTRL_E_UNSUPPORTED, "xtrl_wm_step: dense_bf16 needs the 16-env CTA tile this library was not built with");
+#endif
     }
-    XTRL_LAUNCH_CHECK("wm_step_kernel");
+    return desc->kv_bf16 ? launch(wm_step_kernel<__nv_bfloat16, false>) : launch(wm_step_kernel<float, false>);
+}
+
+extern "C" int64_t xtrl_wm_tc_weights_bytes(const xtrl_model_desc *desc) {
+    using namespace xtrl;
+    if (check_desc(desc)) return -1;
+    StepDims d;
+    make_dims(desc, &d);
+    return tc_layout(d).total;
+}
+
+extern "C" int xtrl_wm_pack_tc(const xtrl_model_desc *desc, const float *weights, void *tc_weights, void *stream) {
+    using namespace xtrl;
+    int rc = check_desc(desc);
+    if (rc) return rc;
+    XTRL_REQUIRE(weights && tc_weights, XTRL_E_BADARG, "xtrl_wm_pack_tc: null pointer");
+    StepDims d;
+    make_dims(desc, &d);
+    xtrl_weight_layout w;
+    rc = xtrl_wm_weight_layout(desc, &w);
+    if (rc) return rc;
+    const TcLayout t = tc_layout(d);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *dst = (unsigned char *)tc_weights;
+    auto pack = [&](int64_t src_off, int ld, int coff, int nvalid, int K, int tiles, int64_t dst_off) -> int {
+        const int64_t total = (int64_t)tiles * 128 * K;
+        pack_tc_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(weights + src_off, ld, coff, nvalid, K, tiles,
+                                                                 (__nv_bfloat16 *)(dst + dst_off));
+        XTRL_LAUNCH_CHECK("pack_tc_kernel");
+        return XTRL_OK;
+    };
+    for (int l = 0; l < d.L; ++l) {
+        if ((rc = pack(w.layer[l].qkv_w, d.NQ, 0, d.NQ, d.D, t.tiles_q, t.qkv[l]))) return rc;
+        if ((rc = pack(w.layer[l].out_w, d.D, 0, d.D, d.I, 1, t.out[l]))) return rc;
+        if ((rc = pack(w.layer[l].ff1_w, 4 * d.D, 0, 4 * d.D, d.D, t.tiles_f, t.ff1[l]))) return rc;
+        if ((rc = pack(w.layer[l].ff2_w, d.D, 0, d.D, 4 * d.D, 1, t.ff2[l]))) return rc;
+    }
+    if ((rc = pack(w.head1_w, 4 * d.D, 0, 2 * d.D, d.HIN, 1, t.head_a))) return rc;
+    if ((rc = pack(w.head1_w, 4 * d.D, 2 * d.D, 2 * d.D, d.HIN, 1, t.head_c))) return rc;
     return XTRL_OK;
 }

@@ -195,6 +195,7 @@ class ModelConfig:
     learned_mix: bool = False
     rotary_true_pos: bool = False
     kv_bf16: bool = False
+    dense_bf16: bool = False      # tcgen05 bf16 GEMMs for QKV/out/FFN/heads (1e-2 tolerance class)
 
     WORLD_MODEL_KEYS = ('attn_dim_head', 'heads', 'depth', 'attn_gate_values', 'add_value_residual',
                         'learned_value_residual_mix')
@@ -222,7 +223,7 @@ class ModelConfig:
         return L.ModelDesc(self.state_dim, self.num_actions, self.dim, self.heads, self.dim_head, self.depth,
                            self.num_bins, self.dim_gene, int(self.gate_values), int(self.value_residual),
                            int(self.learned_mix), self.max_timesteps, int(self.rotary_true_pos), int(self.kv_bf16),
-                           float(self.reward_range[0]), float(self.reward_range[1]))
+                           float(self.reward_range[0]), float(self.reward_range[1]), int(self.dense_bf16))
 
 
 def weight_layout(cfg: ModelConfig) -> L.WeightLayout:
@@ -309,10 +310,17 @@ class WorldModelStepper:
             L.check(self.lib.xtrl_wm_weight_layout(C.byref(self.desc), C.byref(L.WeightLayout())), 'model config')
         self.kv_cache = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
         self.weights = None
+        self.tc_weights = None
         self.pos = torch.zeros(num_envs, device=self.device, dtype=torch.int32)
 
     def load_state_dict(self, sd):
         self.weights = pack_weights(sd, self.cfg, out=self.weights, device=self.device)
+        if self.cfg.dense_bf16:                    # bf16 UMMA operand images, converted on the device
+            if self.tc_weights is None:
+                n = self.lib.xtrl_wm_tc_weights_bytes(C.byref(self.desc))
+                self.tc_weights = torch.empty(n, device=self.device, dtype=torch.uint8)
+            L.check(self.lib.xtrl_wm_pack_tc(C.byref(self.desc), _ptr(self.weights), _ptr(self.tc_weights), _stream()),
+                    'xtrl_wm_pack_tc')
 
     def reset(self):
         self.pos.zero_()
@@ -339,7 +347,7 @@ class WorldModelStepper:
                       _ptr(rs_mean, torch.float32, 'rs_mean'), _ptr(rs_var, torch.float32, 'rs_var'),
                       _ptr(genes, torch.float32, 'genes'), _ptr(gene_ids, torch.int32, 'gene_ids'),
                       _ptr(uniform, torch.float32, 'uniform'), _ptr(forced_action, torch.int32, 'forced_action'),
-                      float(reward_flag), int(pos_uniform or 0), _ptr(out['action']), _ptr(out['log_prob']), _ptr(out['value']),
+                      float(reward_flag), int(pos_uniform or 0), _ptr(self.tc_weights), _ptr(out['action']), _ptr(out['log_prob']), _ptr(out['value']),
                       _ptr(out.get('raw_actions')), _ptr(out.get('value_logits')))
         L.check(self.lib.xtrl_wm_step(C.byref(self.desc), _ptr(self.weights), _ptr(self.kv_cache), C.byref(io), B,
                                       _stream()), 'xtrl_wm_step')
