@@ -171,6 +171,7 @@ struct StepArgs {
     float hl_step;
     TcLayout tc;
     const unsigned char *tcw;
+    int epc;                       // envs owned per CTA (<= kTE)
 };
 
 struct Smem {                       // offsets in floats into the dynamic shared-memory block
@@ -336,7 +337,10 @@ wm_step_kernel(const StepArgs a) {
     float *sx = sm + so.x, *sxn = sm + so.xn, *sqkv = sm + so.qkv, *sv1 = sm + so.v1, *sao = sm + so.ao;
     float *sff = sm + so.ff, *sst = sm + so.st, *shin = sm + so.hin, *sgene = sm + so.gene, *slog = sm + so.logit;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int env0 = blockIdx.x * kTE;
+    // a CTA has kTE env slots but owns only `epc` envs (the host sizes epc so the grid fills the SMs evenly);
+    // slots e >= epc are padding: env index B, i.e. invalid everywhere below
+    const int epc = a.epc, env0 = blockIdx.x * epc;
+    auto env_of = [&](int e) { return e < epc ? env0 + e : a.B; };
     const int D = d.D, I = d.I, H = d.H, NQ = d.NQ, S = d.S, Spad = d.Spad;
     const float *W = a.weights;
     const int lst = Spad + 4;
@@ -400,7 +404,7 @@ wm_step_kernel(const StepArgs a) {
 
     // ---- RSNorm.eval on (state || prev reward) (:588-594); gene rows l2-normalised (evolution.py:73-74)
     for (int i = tid; i < kTE * lst; i += kThreads) {
-        const int e = i / lst, j = i - e * lst, env = env0 + e;
+        const int e = i / lst, j = i - e * lst, env = env_of(e);
         float v = 0.f;
         if (env < a.B && j <= Spad && (j < S || j == Spad)) {
             const int f = j < S ? j : S;                       // slot Spad holds the reward
@@ -411,7 +415,7 @@ wm_step_kernel(const StepArgs a) {
     }
     if (d.G > 0) {
         for (int e = warp; e < kTE; e += kThreads / 32) {
-            const int env = env0 + e;
+            const int env = env_of(e);
             const float *row = env < a.B ? a.io.genes + (int64_t)__ldg(a.io.gene_ids + env) * d.G : nullptr;
             float ss = 0.f;
             for (int g = lane; g < d.G; g += 32) { const float v = row ? __ldg(row + g) : 0.f; sgene[e * d.G + g] = v; ss = fmaf(v, v, ss); }
@@ -424,7 +428,7 @@ wm_step_kernel(const StepArgs a) {
 
     // ---- token embedding (:492-503) and the two state-only head inputs (:492, :544)
     dense_tile<kTE / 8, 1>(W + a.w.in_proj, Spad, 2 * D, sst, lst, [&](int e, int n, int, float acc) {
-        const int env = env0 + e;
+        const int env = env_of(e);
         if (n < D) {
             float v = acc;
             if (env < a.B) {
@@ -497,7 +501,7 @@ wm_step_kernel(const StepArgs a) {
         if (d.rot) {
             for (int i = tid; i < kTE * H * 4 * 2; i += kThreads) {
                 const int which = i & 1, pr = (i >> 1) & 3, eh = i >> 3, e = eh / H, h = eh - e * H;
-                const int env = env0 + e;
+                const int env = env_of(e);
                 const float p = env < a.B ? (float)(a.io.pos ? __ldg(a.io.pos + env) : a.io.pos_uniform) : 0.f;
                 const float ang = p * powf(10000.f, -(float)(2 * pr) / 8.f);
                 float sn, cs;
@@ -511,7 +515,7 @@ wm_step_kernel(const StepArgs a) {
         if (d.vres || d.rot) __syncthreads();
 
         // ---- attention over the cache: one warp per (env, head)
-        for (int eh = warp; eh < kTE * H; eh += kThreads / 32) {
+        for (int eh = warp; eh < epc * H; eh += kThreads / 32) {
             const int e = eh / H, h = eh - e * H, env = env0 + e;
             if (env >= a.B) continue;
             const int len = min(a.io.pos ? __ldg(a.io.pos + env) : a.io.pos_uniform, d.Tmax - 1);   // keys already cached
@@ -686,7 +690,7 @@ wm_step_kernel(const StepArgs a) {
 
     // ---- Discrete (:197-222) + HL-Gauss expectation (:843): a warp finishes kTE/8 envs
     for (int e = warp; e < kTE; e += kThreads / 32) {
-        const int env = env0 + e;
+        const int env = env_of(e);
         if (env >= a.B) continue;
         const float *la = slog + e * ll, *lv = la + d.Apad;
         // critic: softmax over K bins . bin centres
@@ -767,7 +771,13 @@ extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, v
                      XTRL_E_UNSUPPORTED, "xtrl_wm_step: dense_bf16 weight tile exceeds the %d-byte stage (dim=%d heads=%d)", kWbufBytes, a.d.D, a.d.H);
         a.tc = tc_layout(a.d);
     }
-    const int blocks = (num_envs + kTE - 1) / kTE;
+    // spread the envs so that every CTA slot of the chip (2 per SM while shared memory allows) gets the same
+    // share: 4096 envs -> 14 per CTA, 293 CTAs on 296 slots instead of 256 CTAs (108 SMs with two, 40 with one)
+    const int slots = (smem <= 113 * 1024 ? 2 : 1) * kNumSMs;
+    int epc = (num_envs + slots - 1) / slots;
+    epc = epc < 1 ? 1 : (epc > kTE ? kTE : epc);
+    a.epc = epc;
+    const int blocks = (num_envs + epc - 1) / epc;
     cudaStream_t s = (cudaStream_t)stream;
     auto launch = [&](auto kern) -> int {
         XTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
