@@ -193,6 +193,16 @@ ppo_loss_kernel(const LossArgs a) {
 
     float acc_ac = 0.f, acc_actor = 0.f, acc_critic = 0.f, acc_nll = 0.f, acc_done = 0.f;
 
+    // per-lane constants of my KJ bins: lower edge and centre (lane <-> bin k = j*32 + lane)
+    float edge_lo[KJ], centre[KJ];
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+        const int k = j * 32 + lane;
+        edge_lo[j] = a.sup.edge(min(k, K));
+        centre[j] = k < K ? a.sup.centre(k) : 0.f;
+    }
+    const float inv_denom = 1.f / a.sup.denom;
+
     int buf = 0;
     if ((int64_t)blockIdx.x < ntiles) stage(blockIdx.x, 0);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
@@ -231,7 +241,7 @@ ppo_loss_kernel(const LossArgs a) {
                 const int k = j * 32 + lane;
                 ex[j] = k < K ? expf(lg[j] - mx) : 0.f;
                 se += ex[j];
-                sc += k < K ? ex[j] * a.sup.centre(k) : 0.f;
+                sc = fmaf(ex[j], centre[j], sc);
             }
             se = warp_sum(se); sc = warp_sum(sc);
             const float v_new = sc / se;                       // hl_gauss(values), :455
@@ -242,17 +252,15 @@ ppo_loss_kernel(const LossArgs a) {
             const bool same = y0 == y1;                        // returns inside +-value_clip: one histogram serves both
             // normalisers: lanes 0..3 evaluate erf at (hi,y0) (lo,y0) (hi,y1) (lo,y1), then broadcast
             const float zarg = ((lane & 1) ? a.sup.lo : a.sup.hi) - ((lane & 2) ? y1 : y0);
-            const float zerf = erff(zarg / a.sup.denom);
-            const float z0 = fmaxf(__shfl_sync(0xffffffffu, zerf, 0) - __shfl_sync(0xffffffffu, zerf, 1), 1e-10f);
-            const float z1 = fmaxf(__shfl_sync(0xffffffffu, zerf, 2) - __shfl_sync(0xffffffffu, zerf, 3), 1e-10f);
+            const float zerf = erff(zarg * inv_denom);
+            const float iz0 = 1.f / fmaxf(__shfl_sync(0xffffffffu, zerf, 0) - __shfl_sync(0xffffffffu, zerf, 1), 1e-10f);
+            const float iz1 = 1.f / fmaxf(__shfl_sync(0xffffffffu, zerf, 2) - __shfl_sync(0xffffffffu, zerf, 3), 1e-10f);
             // cdf at the lower edge of each of my bins; the upper edge comes from the next lane
             float c0[KJ], c1[KJ];
 #pragma unroll
             for (int j = 0; j < KJ; ++j) {
-                const int k = j * 32 + lane;
-                const float ed = a.sup.edge(min(k, K));
-                c0[j] = erf_window((ed - y0) / a.sup.denom);
-                c1[j] = same ? c0[j] : erf_window((ed - y1) / a.sup.denom);
+                c0[j] = erf_window((edge_lo[j] - y0) * inv_denom);
+                c1[j] = same ? c0[j] : erf_window((edge_lo[j] - y1) * inv_denom);
             }
             float p0[KJ], p1[KJ];
             float ce0 = 0.f, ce1 = 0.f, sp0 = 0.f, sp1 = 0.f;
@@ -266,11 +274,11 @@ ppo_loss_kernel(const LossArgs a) {
                 const float n1 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c1[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
                 if (lane == 31) { u0 = n0; u1 = n1; }
                 if (k + 1 == K && (K & 31) == 0) {               // the last edge has no lane of its own
-                    u0 = erff((a.sup.hi - y0) / a.sup.denom);
-                    u1 = erff((a.sup.hi - y1) / a.sup.denom);
+                    u0 = erff((a.sup.hi - y0) * inv_denom);
+                    u1 = erff((a.sup.hi - y1) * inv_denom);
                 }
-                p0[j] = k < K ? (u0 - c0[j]) / z0 : 0.f;
-                p1[j] = k < K ? (u1 - c1[j]) / z1 : 0.f;
+                p0[j] = k < K ? (u0 - c0[j]) * iz0 : 0.f;
+                p1[j] = k < K ? (u1 - c1[j]) * iz1 : 0.f;
                 const float lsm = k < K ? lg[j] - lse : 0.f;
                 ce0 -= p0[j] * lsm; ce1 -= p1[j] * lsm;
                 sp0 += p0[j]; sp1 += p1[j];
