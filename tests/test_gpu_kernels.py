@@ -333,6 +333,57 @@ def test_wm_step_tensor_core_dense(kw, kv_bf16):
     assert rel_err(ra, want_ra) > 1e-5
 
 
+def test_wm_step_full_size_c3():
+    """BASELINE c3 at full size (4096 envs, T=500, depth 4, heads 8).  Envs are independent, so (a) a few
+    envs of the 4096-wide kernel rollout equal the oracle stepping just those envs, (b) at the LAST timestep
+    (500 cached keys) the fp32 kernel, the tensor-core kernel and the bf16-KV kernel agree within their classes,
+    (c) every env's cache row count advanced identically (idempotent re-run gives bit-identical outputs)."""
+    ops = xtrl().ops
+    cfg = R.Config(state_dim=8, num_actions=4, heads=8, depth=4, reward_range=(-5., 5.))
+    sd = random_state_dict(cfg, seed=3)
+    B, T = 4096, 500
+    g = torch.Generator(device=DEV).manual_seed(11)
+    states = torch.randn(T, B, 8, device=DEV, generator=g)
+    rewards = torch.randn(T, B, device=DEV, generator=g)
+    acts = torch.randint(-1, 4, (T, B), device=DEV, generator=g, dtype=torch.int32)
+    mean, var = torch.zeros(9, device=DEV), torch.ones(9, device=DEV)
+    pick = torch.tensor([0, 7, 2049, 4095])
+
+    def run(**extra):
+        st = ops.WorldModelStepper(model_config(cfg, T, **extra), B, DEV)
+        st.load_state_dict({k: v.to(DEV) for k, v in sd.items()})
+        early, last = [], None
+        for t in range(T):
+            out = st.step(states[t], acts[t], rewards[t], mean, var, forced_action=acts[t].clamp(min=0), want_logits=True,
+                          pos_uniform=t)
+            if t < 48:
+                early.append(out['raw_actions'][pick.to(DEV)].clone())
+            last = out
+        res = dict(early=torch.stack(early).cpu(), ra=last['raw_actions'].cpu(), vl=last['value_logits'].cpu(),
+                   val=last['value'].cpu(), lp=last['log_prob'].cpu())
+        del st
+        torch.cuda.empty_cache()
+        return res
+
+    fp32 = run()
+    # (a) against the oracle on the picked envs, first 48 steps
+    cache, want = None, []
+    s_cpu, r_cpu, a_cpu = states[:48, pick.to(DEV)].cpu(), rewards[:48, pick.to(DEV)].cpu(), acts[:48, pick.to(DEV)].cpu().long()
+    for t in range(48):
+        ra, va, _, _, cache = R.wm_forward(sd, cfg, s_cpu[t][:, None], a_cpu[t][:, None], r_cpu[t][:, None], 1., cache=cache)
+        want.append(ra[:, 0])
+    assert rel_err(fp32['early'], torch.stack(want)) < 3e-5
+    # (c) determinism of the whole 500-step rollout
+    again = run()
+    assert torch.equal(again['ra'], fp32['ra']) and torch.equal(again['val'], fp32['val'])
+    # (b) precision classes at t = 499
+    tc = run(dense_bf16=True)
+    assert rel_err(tc['ra'], fp32['ra']) < 2e-2 and rel_err(tc['val'], fp32['val']) < 2e-2
+    lo = run(dense_bf16=True, kv_bf16=True)
+    assert rel_err(lo['ra'], fp32['ra']) < 3e-2 and rel_err(lo['val'], fp32['val']) < 3e-2
+    assert torch.isfinite(fp32['vl']).all() and torch.isfinite(lo['lp']).all()
+
+
 def test_wm_step_bf16_kv_cache():
     cfg = R.Config(state_dim=8, num_actions=4, heads=8, depth=4, reward_range=(-5., 5.))
     sd = random_state_dict(cfg, seed=1)
