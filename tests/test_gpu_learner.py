@@ -208,3 +208,23 @@ def test_bf16_learn_step(tmp_path):
     env = envs.SyntheticVecEnv(16, 8, 16, device=learner.device, seed=1)
     learner(env, 2, seed=0)
     assert torch.isfinite(learner.agent.model.flat_params).all()
+
+
+def test_pipelined_host_env_rollout_equals_single_stream(tmp_path):
+    """groups of envs pipelined on separate streams (host-memory env) == the one-stream rollout, bit for bit."""
+    from importlib import import_module
+    envs = import_module('x-transformers-rl_b200.envs')
+    B, T = 512, 12
+    learner = _make(tmp_path, 8, T, num_episodes_per_update=B)
+    with torch.no_grad():
+        learner.agent.ema_params.add_(torch.randn_like(learner.agent.ema_params) * 0.1)
+    u = torch.rand(T, B, device=learner.device)
+    gids = torch.zeros(B, dtype=torch.int32, device=learner.device)
+    henv = envs.HostVecEnv(B, 8, T, seed=5)
+    learner.rollout_groups = 1
+    a, cum_a = learner.rollout_vectorized(henv, gids, T, seed=9, uniforms=u)
+    learner.rollout_groups = 2
+    b, cum_b = learner.rollout_vectorized(henv, gids, T, seed=9, uniforms=u)
+    for name in ('states', 'actions', 'log_probs', 'rewards', 'values', 'episode_lens'):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(cum_a, cum_b)

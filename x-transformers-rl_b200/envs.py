@@ -84,3 +84,32 @@ class HostVecEnv:
         t = self._t
         self._t += 1
         return self.states[t + 1], self.rewards[t], self.done
+
+
+class _HostSubEnv:
+    """envs [lo, hi) of a HostVecEnv, steppable on their own (lets the learner pipeline groups of envs)."""
+
+    def __init__(self, parent, lo, hi):
+        self.parent, self.lo, self.hi = parent, lo, hi
+        self.num_envs, self.state_dim, self.never_terminates = hi - lo, parent.state_dim, True
+        self._t = 0
+
+    def reset(self, seed=None):
+        self._t = 0
+        return self.parent.states[0, self.lo:self.hi]
+
+    def step(self, action):
+        assert action.shape == (self.num_envs,)
+        t = self._t
+        self._t += 1
+        return self.parent.states[t + 1, self.lo:self.hi], self.parent.rewards[t, self.lo:self.hi], self.parent.done[self.lo:self.hi]
+
+
+def _host_split(self, n):
+    """n equally sized sub-envs (views).  Call reset() on the parent first to draw a new block."""
+    assert self.num_envs % n == 0
+    b = self.num_envs // n
+    return [_HostSubEnv(self, i * b, (i + 1) * b) for i in range(n)]
+
+
+HostVecEnv.split = _host_split

@@ -59,14 +59,21 @@ class Learner(nn.Module):
         self.continuous_actions_clamp = continuous_actions_clamp
         self.save_every = save_every
         self._steppers = {}
+        self.rollout_groups = 2          # host-memory envs that can split(): groups of envs pipelined on separate streams
         self.timings = dict(rollout_s=0., learn_s=0., env_steps=0, learn_timesteps=0)
 
     @property
     def device(self):
         return self.accelerator.device
 
-    def _stepper(self, num_envs, max_timesteps):
-        key = (num_envs, max_timesteps)
+    def _stepper(self, num_envs, max_timesteps, group=None):
+        key = (num_envs, max_timesteps, group)
+        if group is not None:                       # pipelined groups: one stepper (KV cache) per group, kept together
+            if key not in self._steppers:
+                if any(k[2] is None for k in self._steppers):
+                    self._steppers = {}
+                self._steppers[key] = ops.WorldModelStepper(self.agent.cfg, num_envs, self.device)
+            return self._steppers[key]
         if key not in self._steppers:
             cfg = self.agent.cfg
             if max_timesteps > cfg.max_timesteps:
@@ -81,6 +88,9 @@ class Learner(nn.Module):
         (T,B) in [0,1) -- drawn here from torch's CUDA generator unless given (parity tests)."""
         agent, dev, cfg = self.agent, self.device, self.agent.cfg
         B, T, S = env.num_envs, max_timesteps, cfg.state_dim
+        if (self.rollout_groups > 1 and hasattr(env, 'split') and getattr(env, 'never_terminates', False)
+                and B % self.rollout_groups == 0 and B // self.rollout_groups >= 256):
+            return self._rollout_pipelined(env, gene_ids, max_timesteps, seed, uniforms)
         st = self._stepper(B, max_timesteps)
         st.load_state_dict(agent.ema_state_dict())               # rollouts read the EMA weights (:1194)
         buf = RolloutBuffer.allocate(T, B, S, dev)
@@ -135,6 +145,59 @@ class Learner(nn.Module):
         if never_done:
             lens.fill_(T)
         buf.episode_lens.copy_(lens)
+        return buf, buf.rewards.sum(dim=0)
+
+    @torch.no_grad()
+    def _rollout_pipelined(self, env, gene_ids, max_timesteps, seed=None, uniforms=None):
+        """host-memory vector env split into groups: while the host steps group A's simulators and moves its
+        states over PCIe, the GPU runs group B's timestep (one stream, one KV cache, one pinned staging set per
+        group).  Same buffers and results as rollout_vectorized; never-terminating envs only."""
+        agent, dev, cfg = self.agent, self.device, self.agent.cfg
+        B, T, S, G = env.num_envs, max_timesteps, cfg.state_dim, self.rollout_groups
+        Bg = B // G
+        env.reset(**({} if seed is None else dict(seed=seed)))
+        subs = env.split(G)
+        buf = RolloutBuffer.allocate(T, B, S, dev)
+        buf.gene_ids.copy_(gene_ids)
+        u = torch.rand(T, B, device=dev) if uniforms is None else uniforms
+        first_a = torch.full((Bg,), -1, dtype=torch.int32, device=dev)
+        first_r = torch.zeros(Bg, device=dev)
+        genes = agent.gene_pool.genes.data if agent.evolutionary else None
+        rs_mean, rs_var = agent.rsnorm.running_mean, agent.rsnorm.running_variance
+        sd = agent.ema_state_dict()
+        main = torch.cuda.current_stream(dev)
+        grp = []
+        for g, sub in enumerate(subs):
+            st = self._stepper(Bg, T, group=g)
+            st.load_state_dict(sd)
+            grp.append(dict(env=sub, st=st, lo=g * Bg, hi=(g + 1) * Bg, stream=torch.cuda.Stream(dev), ev=torch.cuda.Event(),
+                            pin_s=torch.empty(Bg, S).pin_memory(), pin_r=torch.empty(Bg).pin_memory(),
+                            pin_a=torch.empty(Bg, dtype=torch.int32).pin_memory(), state=sub.reset()))
+        for q in grp:
+            q['stream'].wait_stream(main)
+        for t in range(T + 1):
+            for q in grp:
+                lo, hi = q['lo'], q['hi']
+                with torch.cuda.stream(q['stream']):
+                    if t > 0:
+                        q['ev'].synchronize()                                  # actions of step t-1 are on the host
+                        step_out = q['env'].step(q['pin_a'].numpy())
+                        q['state'], reward = step_out[0], step_out[1]
+                        q['pin_r'].copy_(torch.from_numpy(np.ascontiguousarray(reward, dtype=np.float32)))
+                        buf.rewards[t - 1, lo:hi].copy_(q['pin_r'], non_blocking=True)
+                    if t == T:
+                        continue
+                    q['pin_s'].copy_(torch.from_numpy(np.ascontiguousarray(q['state'], dtype=np.float32)))
+                    buf.states[t, lo:hi].copy_(q['pin_s'], non_blocking=True)
+                    out = dict(action=buf.actions[t, lo:hi], log_prob=buf.log_probs[t, lo:hi], value=buf.values[t, lo:hi])
+                    q['st'].step(buf.states[t, lo:hi], first_a if t == 0 else buf.actions[t - 1, lo:hi],
+                                 first_r if t == 0 else buf.rewards[t - 1, lo:hi], rs_mean, rs_var, uniform=u[t, lo:hi],
+                                 genes=genes, gene_ids=buf.gene_ids[lo:hi] if genes is not None else None, out=out, pos_uniform=t)
+                    q['pin_a'].copy_(buf.actions[t, lo:hi], non_blocking=True)
+                    q['ev'].record(q['stream'])
+        for q in grp:
+            main.wait_stream(q['stream'])
+        buf.episode_lens.fill_(T)
         return buf, buf.rewards.sum(dim=0)
 
     # ---- plain env: reference semantics, one episode at a time (:1220-1355) -------------------------
