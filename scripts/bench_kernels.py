@@ -41,6 +41,14 @@ if not a.only or 'gae' in a.only:
     rt, vt, bt = r.T.contiguous(), v.T.contiguous(), bd.T.contiguous()
     outt = torch.empty_like(rt)
     report('gae_time_major (T=500,B=4096)', 13 * E * T, timeit(lambda: ops.gae(rt, vt, bt, time_major=True, out=outt)), unit_bytes=13)
+    E8 = 8 * E                                              # c5 total: 32768 episodes (213 MB)
+    r8, v8 = torch.randn(T, E8, device=dev, generator=g), torch.randn(T, E8, device=dev, generator=g)
+    b8 = torch.rand(T, E8, device=dev, generator=g) < 0.02
+    o8 = torch.empty_like(r8)
+    report('gae_time_major (T=500,B=32768)', 13 * E8 * T, timeit(lambda: ops.gae(r8, v8, b8, time_major=True, out=o8)), unit_bytes=13)
+    r8e, v8e, b8e = r8.T.contiguous(), v8.T.contiguous(), b8.T.contiguous()
+    report('gae_episode_major (E=32768,T=500)', 13 * E8 * T, timeit(lambda: ops.gae(r8e, v8e, b8e, out=o8.view(E8, T))), unit_bytes=13)
+    del r8, v8, b8, o8, r8e, v8e, b8e
 if not a.only or 'loss' in a.only:
     for dt, nm in ((torch.float32, 'fp32'), (torch.bfloat16, 'bf16')):
         b = 1024                                            # 512k timesteps: 0.5 GB of logits+grads in fp32

@@ -72,7 +72,12 @@ gae_episode_major_kernel(const float *__restrict__ rewards, const float *__restr
 }
 
 constexpr int kGaeChunks = 16;          // time-major: warps (time chunks) per CTA
+constexpr int kGaeRegChunk = 32;        // chunk length held in registers (T <= 512)
 
+// REG: the thread's whole chunk (<= 32 timesteps) is loaded into registers up front -- all 3*C loads of
+// a thread are in flight together, inputs cross the memory system exactly once -- then folded, carried
+// through shared memory, and replayed from registers.  !REG (T > 512): two sweeps, the second from L2.
+template <bool REG>
 __global__ void __launch_bounds__(kGaeChunks * 32)
 gae_time_major_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
                       const uint8_t *__restrict__ boundary, float *__restrict__ returns,
@@ -84,6 +89,39 @@ gae_time_major_kernel(const float *__restrict__ rewards, const float *__restrict
     const bool live = e < E;
     const int C = (T + kGaeChunks - 1) / kGaeChunks;
     const int t_lo = w * C, t_hi = min(T, t_lo + C);      // [t_lo, t_hi)
+
+    if constexpr (REG) {
+        float dl[kGaeRegChunk], gt[kGaeRegChunk], vv[kGaeRegChunk + 1];
+#pragma unroll
+        for (int i = 0; i <= kGaeRegChunk; ++i) {          // values, one extra for v_{t+1} of the last step
+            const int t = t_lo + i;
+            vv[i] = (live && i <= C && t < T) ? __ldg(values + (int64_t)t * stride_t + e) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < kGaeRegChunk; ++i) {
+            const int t = t_lo + i;
+            const bool ok = live && i < C && t < t_hi;
+            const float rv = ok ? __ldg(rewards + (int64_t)t * stride_t + e) : 0.f;
+            const float m = (ok && __ldg(boundary + (int64_t)t * stride_t + e)) ? 0.f : 1.f;
+            gt[i] = ok ? gl * m : 1.f;                      // identity map outside the chunk
+            dl[i] = ok ? rv + gamma * vv[i + 1] * m - vv[i] : 0.f;
+        }
+        float A = 1.f, Bc = 0.f;
+#pragma unroll
+        for (int i = kGaeRegChunk - 1; i >= 0; --i) { Bc = fmaf(gt[i], Bc, dl[i]); A *= gt[i]; }
+        sA[w][lane] = A;
+        sB[w][lane] = Bc;
+        __syncthreads();
+        float h = 0.f;                                     // gae at t_hi
+        for (int c = kGaeChunks - 1; c > w; --c) h = fmaf(sA[c][lane], h, sB[c][lane]);
+#pragma unroll
+        for (int i = kGaeRegChunk - 1; i >= 0; --i) {
+            h = fmaf(gt[i], h, dl[i]);
+            const int t = t_lo + i;
+            if (live && i < C && t < t_hi) returns[(int64_t)t * stride_t + e] = h + vv[i];
+        }
+        return;
+    }
 
     // sweep 1: fold the chunk into h -> B + A*h
     float A = 1.f, Bc = 0.f;
@@ -136,8 +174,10 @@ extern "C" int xtrl_gae(const float *rewards, const float *values, const uint8_t
         XTRL_LAUNCH_CHECK("gae_episode_major_kernel");
     } else if (stride_e == 1 && stride_t >= E) {
         const int blocks = (E + 31) / 32;
-        gae_time_major_kernel<<<blocks, kGaeChunks * 32, 0, s>>>(
-            rewards, values, is_boundary, returns, E, T, stride_t, gamma, gl);
+        if (T <= kGaeChunks * kGaeRegChunk)
+            gae_time_major_kernel<true><<<blocks, kGaeChunks * 32, 0, s>>>(rewards, values, is_boundary, returns, E, T, stride_t, gamma, gl);
+        else
+            gae_time_major_kernel<false><<<blocks, kGaeChunks * 32, 0, s>>>(rewards, values, is_boundary, returns, E, T, stride_t, gamma, gl);
         XTRL_LAUNCH_CHECK("gae_time_major_kernel");
     } else {
         return fail(XTRL_E_UNSUPPORTED,
