@@ -384,6 +384,59 @@ def test_wm_step_full_size_c3():
     assert torch.isfinite(fp32['vl']).all() and torch.isfinite(lo['lp']).all()
 
 
+def test_wm_step_ragged_positions_and_empty_batch():
+    """per-env cache lengths: envs that restart (pos -> 0) mid-rollout while their neighbours continue, as a
+    vector env with auto-reset needs; and a zero-env call is a no-op."""
+    ops = xtrl().ops
+    cfg = R.Config(state_dim=8, num_actions=4, heads=4, depth=2, reward_range=(-5., 5.), value_residual=True)
+    sd = random_state_dict(cfg, seed=7)
+    B, T = 21, 40
+    g = torch.Generator().manual_seed(3)
+    states, prev_r = torch.randn(B, T, 8, generator=g), torch.randn(B, T, generator=g)
+    prev_a = torch.randint(-1, 4, (B, T), generator=g)
+    restart_at = torch.randint(1, T, (B,), generator=g)
+    restart_at[::3] = T + 1                                        # a third of the envs never restart
+    st = ops.WorldModelStepper(model_config(cfg, T), B, DEV)
+    st.load_state_dict({k: v.to(DEV) for k, v in sd.items()})
+    mean, var = torch.zeros(9, device=DEV), torch.ones(9, device=DEV)
+    got = []
+    for t in range(T):
+        st.pos[(restart_at == t).to(DEV)] = 0                      # episode ended: empty cache for those envs
+        out = st.step(cu(states[:, t]), cu(prev_a[:, t].int()), cu(prev_r[:, t]), mean, var,
+                      forced_action=cu(torch.zeros(B, dtype=torch.int32)), want_logits=True)
+        got.append(out['raw_actions'].cpu().clone())
+    got = torch.stack(got, 1)                                      # (B, T, A)
+    for b in range(B):
+        cache = None
+        for t in range(T):
+            if t == int(restart_at[b]):
+                cache = None
+            ra, _, _, _, cache = R.wm_forward(sd, cfg, states[b:b + 1, t:t + 1], prev_a[b:b + 1, t:t + 1], prev_r[b:b + 1, t:t + 1], 1., cache=cache)
+            assert rel_err(got[b, t], ra[0, 0]) < 5e-5, (b, t)
+    empty = ops.WorldModelStepper(model_config(cfg, T), 0, DEV)
+    empty.load_state_dict({k: v.to(DEV) for k, v in sd.items()})
+    out = empty.step(torch.empty(0, 8, device=DEV), torch.empty(0, dtype=torch.int32, device=DEV), torch.empty(0, device=DEV), mean, var)
+    assert out['action'].shape == (0,)
+
+
+def test_ppo_loss_empty_and_single_row():
+    ops = xtrl().ops
+    lc = ops.LossConfig(num_actions=3, num_bins=51, state_dim=4, reward_range=(-1., 1.))
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, device=DEV, dtype=dt)
+    scal, grads = ops.ppo_loss_fwd_bwd(lc, z(0, 5, 3), z(0, 5, 51), z(0, 5, 10), z(0, 5), z(0, 5, dt=torch.int32), z(0, 5), z(0, 5),
+                                       z(0, 5), z(0, 5, 5), z(0, 5, dt=torch.bool), z(0, dt=torch.int32))
+    assert grads['raw_actions'].shape == (0, 5, 3) and torch.all(scal.cpu() == 0)
+    # one episode of one step: the unbiased variance of a single advantage is NaN in the reference too
+    g = torch.Generator().manual_seed(0)
+    ra, va = torch.randn(1, 1, 3, generator=g), torch.randn(1, 1, 51, generator=g)
+    scal, grads = ops.ppo_loss_fwd_bwd(lc, cu(ra), cu(va), z(1, 1, 10), z(1, 1), z(1, 1, dt=torch.int32), z(1, 1), z(1, 1) + 0.3,
+                                       z(1, 1), z(1, 1, 5), z(1, 1, dt=torch.bool), torch.ones(1, device=DEV, dtype=torch.int32))
+    assert scal[5].item() == 1 and torch.isnan(scal[7]).item()
+    cfg = R.Config(state_dim=4, num_actions=3, reward_range=(-1., 1.), num_bins=51)
+    want = R.critic_loss(va, torch.full((1, 1), 0.3), torch.zeros(1, 1), cfg)
+    assert rel_err(scal[2].cpu(), want.mean()) < 1e-5
+
+
 def test_wm_step_bf16_kv_cache():
     cfg = R.Config(state_dim=8, num_actions=4, heads=8, depth=4, reward_range=(-5., 5.))
     sd = random_state_dict(cfg, seed=1)

@@ -471,18 +471,19 @@ extern "C" int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_i
                  "xtrl_ppo_loss_fwd_bwd: num_bins=%d outside [2,256]", cfg->num_bins);
     XTRL_REQUIRE(cfg->state_dim >= 1 && cfg->state_dim + 1 <= 32, XTRL_E_UNSUPPORTED,
                  "xtrl_ppo_loss_fwd_bwd: state_dim=%d outside [1,31]", cfg->state_dim);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t N = (int64_t)batch * num_timesteps;
+    if (N == 0) {                                           // empty minibatch: zero scalars, nothing else (buffers may be empty)
+        XTRL_REQUIRE(io->scalars, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: null scalars");
+        XTRL_CUDA(cudaMemsetAsync(io->scalars, 0, sizeof(float) * 8, s));
+        return XTRL_OK;
+    }
     XTRL_REQUIRE(io->raw_actions && io->value_logits && io->actions && io->old_log_probs && io->returns &&
                  io->old_values && io->episode_lens && io->scalars && io->workspace, XTRL_E_BADARG,
                  "xtrl_ppo_loss_fwd_bwd: null required pointer");
     XTRL_REQUIRE(!io->state_pred_raw || io->target, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: state_pred_raw without target");
     XTRL_REQUIRE(!io->done_logit || io->dones, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: done_logit without dones");
-    cudaStream_t s = (cudaStream_t)stream;
     XTRL_CUDA(cudaMemsetAsync(io->workspace, 0, sizeof(double) * 16, s));
-    const int64_t N = (int64_t)batch * num_timesteps;
-    if (N == 0) {
-        XTRL_CUDA(cudaMemsetAsync(io->scalars, 0, sizeof(float) * 8, s));
-        return XTRL_OK;
-    }
     const int sblocks = (int)((N + 255) / 256 < 4 * kNumSMs ? (N + 255) / 256 : 4 * kNumSMs);
     ppo_stats_kernel<<<sblocks, 256, 0, s>>>(io->returns, io->old_values, io->episode_lens, batch, num_timesteps, io->workspace);
     XTRL_LAUNCH_CHECK("ppo_stats_kernel");

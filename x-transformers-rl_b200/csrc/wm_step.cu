@@ -744,9 +744,9 @@ extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, v
     using namespace xtrl;
     int rc = check_desc(desc);
     if (rc) return rc;
-    XTRL_REQUIRE(io && weights && kv_cache, XTRL_E_BADARG, "xtrl_wm_step: null pointer");
     XTRL_REQUIRE(num_envs >= 0, XTRL_E_BADARG, "xtrl_wm_step: num_envs=%d", num_envs);
-    if (num_envs == 0) return XTRL_OK;
+    if (num_envs == 0) return XTRL_OK;                      // nothing to do (and the caller's buffers may be empty)
+    XTRL_REQUIRE(io && weights && kv_cache, XTRL_E_BADARG, "xtrl_wm_step: null pointer");
     XTRL_REQUIRE(io->state && io->prev_action && io->prev_reward && io->rs_mean && io->rs_var,
                  XTRL_E_BADARG, "xtrl_wm_step: null required input");
     XTRL_REQUIRE(io->pos || (io->pos_uniform >= 0 && io->pos_uniform < desc->max_timesteps), XTRL_E_BADARG,
