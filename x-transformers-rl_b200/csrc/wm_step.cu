@@ -528,17 +528,21 @@ wm_step_kernel(const StepArgs a) {
                 TR::store1((lane < kDH ? kc : vc) + (int64_t)len * kDH + (lane & (kDH - 1)), nv);
             }
             const int sub = lane & (PPR - 1), grp = lane >> TR::LOG_PPR;
-            const uint4 *kp = (const uint4 *)kc, *vp = (const uint4 *)vc;      // 16-byte pieces, PPR per row
+            // this lane's piece of every cached row: 16-byte pieces, PPR per row, 32-bit row offsets
+            const uint4 *kpl = (const uint4 *)kc + sub, *vpl = (const uint4 *)vc + sub;
             float q[EP], acc[EP];
 #pragma unroll
             for (int i = 0; i < EP; ++i) { q[i] = qs[sub * EP + i]; acc[i] = 0.f; }
             float m = -INFINITY, lsum = 0.f;
-            // keys 0..len-1 stream from the cache; key `len` is the token itself, still in shared memory
+            // Cached keys 0..len-1.  Loads are unconditional: row indices past the end are clamped to the last
+            // cached row (finite data) and masked out of the softmax, so the stream carries no per-load branches.
+            const int last = len - 1;
             auto fetch = [&](int c, uint4 (&kr)[PPR], uint4 (&vr)[PPR]) {
 #pragma unroll
                 for (int i = 0; i < PPR; ++i) {
-                    const int j = c * 32 + i * RPI + grp;
-                    if (j < len) { kr[i] = ld_stream_u4(kp + (int64_t)j * PPR + sub); vr[i] = ld_stream_u4(vp + (int64_t)j * PPR + sub); }
+                    const int j = min(c * 32 + i * RPI + grp, last);
+                    kr[i] = ld_stream_u4(kpl + j * PPR);
+                    vr[i] = ld_stream_u4(vpl + j * PPR);
                 }
             };
             auto process = [&](int c, const uint4 (&kr)[PPR], const uint4 (&vr)[PPR]) {
@@ -546,22 +550,15 @@ wm_step_kernel(const StepArgs a) {
                 float mn = m;
 #pragma unroll
                 for (int i = 0; i < PPR; ++i) {
-                    const int j = c * 32 + i * RPI + grp;
                     float kf[EP];
-                    if (j < len) { TR::unpack(kr[i], kf); TR::unpack(vr[i], vf[i]); }
-                    else {
-#pragma unroll
-                        for (int t = 0; t < EP; ++t) {
-                            kf[t] = j == len ? qs[I + sub * EP + t] : 0.f;
-                            vf[i][t] = j == len ? qs[2 * I + sub * EP + t] : 0.f;
-                        }
-                    }
+                    TR::unpack(kr[i], kf);
+                    TR::unpack(vr[i], vf[i]);
                     float part = 0.f;
 #pragma unroll
                     for (int t = 0; t < EP; ++t) part = fmaf(q[t], kf[t], part);
 #pragma unroll
                     for (int o = 1; o < PPR; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                    sc[i] = j <= len ? part * 0.25f : -INFINITY;           // dim_head^-0.5
+                    sc[i] = (c * 32 + i * RPI + grp) < len ? part * 0.25f : -INFINITY;     // dim_head^-0.5
                     mn = fmaxf(mn, sc[i]);
                 }
                 if (mn > -INFINITY) {                                      // a row group with no valid key yet skips
@@ -581,19 +578,36 @@ wm_step_kernel(const StepArgs a) {
             };
             // software pipeline over 32-key chunks (two register buffers, ping-pong): the loads of chunk
             // c+1 are in flight while chunk c is folded into the online softmax
-            const int nchunks = len / 32 + 1;
-            if constexpr (kKvBuf >= 2) {
-                uint4 ka[PPR], va[PPR], kb[PPR], vb[PPR];
-                fetch(0, ka, va);
-                for (int c = 0; c < nchunks; c += 2) {
-                    fetch(c + 1, kb, vb);
-                    process(c, ka, va);
-                    fetch(c + 2, ka, va);
-                    if (c + 1 < nchunks) process(c + 1, kb, vb);
+            const int nchunks = (len + 31) >> 5;
+            if (nchunks > 0) {
+                if constexpr (kKvBuf >= 2) {
+                    uint4 ka[PPR], va[PPR], kb[PPR], vb[PPR];
+                    fetch(0, ka, va);
+                    for (int c = 0; c < nchunks; c += 2) {
+                        if (c + 1 < nchunks) fetch(c + 1, kb, vb);
+                        process(c, ka, va);
+                        if (c + 2 < nchunks) fetch(c + 2, ka, va);
+                        if (c + 1 < nchunks) process(c + 1, kb, vb);
+                    }
+                } else {                                               // one chunk in flight per warp; more warps per SM
+                    uint4 ka[PPR], va[PPR];
+                    for (int c = 0; c < nchunks; ++c) { fetch(c, ka, va); process(c, ka, va); }
                 }
-            } else {                                                   // one chunk in flight per warp; more warps per SM
-                uint4 ka[PPR], va[PPR];
-                for (int c = 0; c < nchunks; ++c) { fetch(c, ka, va); process(c, ka, va); }
+            }
+            // the token itself (key `len`, still in shared memory): every lane scores its piece, row group 0 folds it
+            {
+                float part = 0.f, vself[EP];
+#pragma unroll
+                for (int t = 0; t < EP; ++t) { part = fmaf(q[t], qs[I + sub * EP + t], part); vself[t] = qs[2 * I + sub * EP + t]; }
+#pragma unroll
+                for (int o = 1; o < PPR; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if (grp == 0) {
+                    const float sc = part * 0.25f, mn = fmaxf(m, sc), c0 = expf(m - mn), pi = expf(sc - mn);
+                    lsum = fmaf(lsum, c0, pi);
+#pragma unroll
+                    for (int t = 0; t < EP; ++t) acc[t] = fmaf(acc[t], c0, pi * vself[t]);
+                    m = mn;
+                }
             }
             // merge the row groups: rescale to the common max, then butterfly sums across groups
             float M = m;
