@@ -162,6 +162,7 @@ def workload_config(name, w, n_gpus, **extra):
                          f'T={w["T"]} depth={wm["depth"]} heads={wm["heads"]} dim_head={wm["attn_dim_head"]} hidden=48',
                 envs_per_gpu=w['envs'], total_envs=w['envs'] * n_gpus, timesteps=w['T'],
                 parallelism=f'episode-sharded dp{n_gpus}, no data-path collective in rollout',
+                launch='the T step launches of a pass are replayed as one CUDA graph (device-resident synthetic env)',
                 l2='inputs larger than L2 (KV cache GBs per pass); tiny workloads (c1/c2) are L2-resident by nature',
                 **extra)
 
@@ -253,10 +254,11 @@ def run_b200(args, w):
             evs[t][0].record(); r = orig(*a, **k); evs[t][1].record()
             return r
         st.step = wrapped
+        graphed, lrn.use_cuda_graph = lrn.use_cuda_graph, False        # per-launch events need the eager launch loop
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); one_pass(env, lrn); e1.record()
         torch.cuda.synchronize(dev)
-        st.step = orig
+        st.step, lrn.use_cuda_graph = orig, graphed
         kern_ms = [a.elapsed_time(b) for a, b in evs]
         kvb = 4 if kv == 'fp32' else 2
         alg = sum(algorithmic_bytes_per_env_step(w, t, kvb) for t in range(T)) * B / T        # bytes per launch (avg)

@@ -33,14 +33,19 @@ class SyntheticVecEnv:
         self.num_envs, self.state_dim, self.horizon, self.device = num_envs, state_dim, horizon, torch.device(device)
         self.gen = torch.Generator(device=self.device).manual_seed(seed)
         self.never_terminates = True
+        # step() only hands out views of tensors that keep their storage across reset(): a whole rollout over
+        # this env can be captured in one CUDA graph and replayed (learner.Learner.use_cuda_graph)
+        self.cuda_graph_safe = True
         self._t = 0
+        B, S, H = num_envs, state_dim, horizon
+        self.states = torch.empty(H + 1, B, S, device=self.device)
+        self.rewards = torch.empty(H, B, device=self.device)
+        self.done = torch.zeros(B, dtype=torch.bool, device=self.device)
         self._draw()
 
     def _draw(self):
-        B, S, H = self.num_envs, self.state_dim, self.horizon
-        self.states = torch.randn(H + 1, B, S, device=self.device, generator=self.gen)
-        self.rewards = torch.randn(H, B, device=self.device, generator=self.gen)
-        self.done = torch.zeros(B, dtype=torch.bool, device=self.device)
+        self.states.normal_(generator=self.gen)       # in place: storage (and any captured graph) stays valid
+        self.rewards.normal_(generator=self.gen)
 
     def reset(self, seed=None):
         if seed is not None:

@@ -59,6 +59,8 @@ class Learner(nn.Module):
         self.continuous_actions_clamp = continuous_actions_clamp
         self.save_every = save_every
         self._steppers = {}
+        self.use_cuda_graph = True       # device envs that declare cuda_graph_safe: the T-step rollout is one graph replay
+        self._graphs = {}
         self.rollout_groups = 2          # host-memory envs that can split(): groups of envs pipelined on separate streams
         self.timings = dict(rollout_s=0., learn_s=0., env_steps=0, learn_timesteps=0)
 
@@ -83,7 +85,7 @@ class Learner(nn.Module):
 
     # ---- vectorised rollout: B envs in lock step, one kernel launch per timestep -------------------
     @torch.no_grad()
-    def rollout_vectorized(self, env, gene_ids, max_timesteps, seed=None, uniforms=None):
+    def rollout_vectorized(self, env, gene_ids, max_timesteps, seed=None, uniforms=None, allow_graph=True):
         """returns (RolloutBuffer (T,B,..), cumulative_rewards (B,)).  Sampling consumes `uniforms`
         (T,B) in [0,1) -- drawn here from torch's CUDA generator unless given (parity tests)."""
         agent, dev, cfg = self.agent, self.device, self.agent.cfg
@@ -91,6 +93,9 @@ class Learner(nn.Module):
         if (self.rollout_groups > 1 and hasattr(env, 'split') and getattr(env, 'never_terminates', False)
                 and B % self.rollout_groups == 0 and B // self.rollout_groups >= 256):
             return self._rollout_pipelined(env, gene_ids, max_timesteps, seed, uniforms)
+        if (self.use_cuda_graph and allow_graph and uniforms is None and getattr(env, 'cuda_graph_safe', False)
+                and getattr(env, 'never_terminates', False)):
+            return self._rollout_graphed(env, gene_ids, max_timesteps, seed)
         st = self._stepper(B, max_timesteps)
         st.load_state_dict(agent.ema_state_dict())               # rollouts read the EMA weights (:1194)
         buf = RolloutBuffer.allocate(T, B, S, dev)
@@ -145,6 +150,59 @@ class Learner(nn.Module):
         if never_done:
             lens.fill_(T)
         buf.episode_lens.copy_(lens)
+        return buf, buf.rewards.sum(dim=0)
+
+    @torch.no_grad()
+    def _rollout_graphed(self, env, gene_ids, max_timesteps, seed=None):
+        """device-resident, never-terminating env whose step() is pure views: the whole rollout -- T x (state copy,
+        xtrl_wm_step, reward copy) -- is captured ONCE into a CUDA graph over static buffers (trajectory buffer,
+        KV cache, packed weights, RSNorm stats, uniforms) and replayed per update: one launch from the host
+        instead of 3T.  Everything that changes between updates is refreshed in place before the replay."""
+        agent, dev, cfg = self.agent, self.device, self.agent.cfg
+        B, T, S = env.num_envs, max_timesteps, cfg.state_dim
+        key = (id(env), B, T)
+        st = self._stepper(B, T)
+        st.load_state_dict(agent.ema_state_dict())               # in place: the captured pointers stay valid
+        state0 = env.reset(**({} if seed is None else dict(seed=seed)))
+        ent = self._graphs.get(key)
+        if ent is None or ent['st'] is not st:
+            buf = RolloutBuffer.allocate(T, B, S, dev)
+            buf.episode_lens.fill_(T)
+            u = torch.empty(T, B, device=dev)
+            first_a = torch.full((B,), -1, dtype=torch.int32, device=dev)
+            first_r = torch.zeros(B, device=dev)
+            genes = agent.gene_pool.genes.data if agent.evolutionary else None
+            rs_mean, rs_var = agent.rsnorm.running_mean, agent.rsnorm.running_variance
+
+            def body():
+                state = state0
+                for t in range(T):
+                    buf.states[t].copy_(state)
+                    st.step(buf.states[t], first_a if t == 0 else buf.actions[t - 1], first_r if t == 0 else buf.rewards[t - 1],
+                            rs_mean, rs_var, uniform=u[t], genes=genes, gene_ids=buf.gene_ids if genes is not None else None,
+                            out=dict(action=buf.actions[t], log_prob=buf.log_probs[t], value=buf.values[t]), pos_uniform=t)
+                    state, reward = env.step(buf.actions[t])[:2]
+                    buf.rewards[t].copy_(reward)
+                env._t = 0
+
+            buf.gene_ids.copy_(gene_ids)
+            u.uniform_()
+            side = torch.cuda.Stream(dev)                        # one eager pass first: lazy module loads cannot be captured
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            # every tensor whose address the graph baked in must outlive the graph
+            ent = self._graphs[key] = dict(graph=graph, buf=buf, u=u, st=st, keep=(first_a, first_r, genes, rs_mean, rs_var, state0))
+            if len(self._graphs) > 2:
+                self._graphs.pop(next(iter(self._graphs)))
+        buf = ent['buf']
+        buf.gene_ids.copy_(gene_ids)
+        ent['u'].uniform_()
+        ent['graph'].replay()
         return buf, buf.rewards.sum(dim=0)
 
     @torch.no_grad()
@@ -262,7 +320,7 @@ class Learner(nn.Module):
                     wave = pairs[w:w + B]
                     gids = torch.tensor([p[1] for p in wave], dtype=torch.int32, device=dev)
                     wave_seed = int(episode_seeds[wave[0][0]]) if episode_seeds is not None else None
-                    buf, cum = self.rollout_vectorized(env, gids, max_timesteps, seed=wave_seed)
+                    buf, cum = self.rollout_vectorized(env, gids, max_timesteps, seed=wave_seed, allow_graph=(len(pairs) == B))
                     if fitnesses is not None:
                         fitnesses.index_add_(0, gids.long(), cum)                              # :1345-1346
                     bufs.append(buf)
