@@ -191,7 +191,8 @@ ppo_loss_kernel(const LossArgs a) {
         cp_async_commit();
     };
 
-    float acc_ac = 0.f, acc_actor = 0.f, acc_critic = 0.f, acc_nll = 0.f, acc_done = 0.f;
+    float acc_ac = 0.f, acc_actor = 0.f, acc_critic = 0.f, acc_nll = 0.f, acc_done = 0.f;   // per THREAD partial sums
+    __shared__ float s_crit[kTileRows];
 
     // per-lane constants of my KJ bins: lower edge and centre (lane <-> bin k = j*32 + lane)
     float edge_lo[KJ], centre[KJ];
@@ -305,93 +306,120 @@ ppo_loss_kernel(const LossArgs a) {
                 }
             }
 
-            // ---------------- actor: clipped surrogate + entropy (lane i <-> action i) ------------
-            const int act = s_act[lr];
-            const float la = lane < A ? sm_as_float(s_ra + lr * A + lane) : -INFINITY;
-            const float amx = warp_max(la);
-            const float q = lane < A ? expf(la - amx) : 0.f;
-            const float qs = warp_sum(q);
-            const float sm = q / qs;                              // softmax
-            const float ssum = warp_sum(sm);                      // Categorical renormalises probs
-            const float p = sm / ssum;
-            const bool inside = p >= feps && p <= 1.f - feps;
-            const float L = lane < A ? logf(fminf(fmaxf(p, feps), 1.f - feps)) : 0.f;
-            const float ent = -warp_sum(p * L);
-            const float logp = __shfl_sync(0xffffffffu, L, act & 31);
-            const float ratio = expf(logp - s_olp[lr]);
-            const float clipped = fminf(fmaxf(ratio, 1.f - a.cfg.eps_clip), 1.f + a.cfg.eps_clip);
-            const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
-            const float surr1 = ratio * adv, surr2 = clipped * adv;
-            const float actor = -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
-            if (g_ra) {
-                const bool in_range = ratio >= 1.f - a.cfg.eps_clip && ratio <= 1.f + a.cfg.eps_clip;
-                const float dmin = in_range ? adv : (surr1 < surr2 ? adv : 0.f);
-                const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
-                const float g_logp = -ga * dmin * ratio;
-                // d/dp_i of  -beta*ent + logp-term
-                float gp = 0.f;
-                if (lane < A) {
-                    gp = ga * a.cfg.entropy_weight * (L + (inside ? 1.f : 0.f));
-                    if (lane == act && inside) gp += g_logp / p;
-                }
-                // p = sm / sum(sm);  sm = softmax(logits)
-                const float dot_p = warp_sum(gp * p);
-                const float gq = (gp - dot_p) / ssum;
-                const float dot_q = warp_sum(lane < A ? gq * sm : 0.f);
-                if (lane < A) st_from_float(g_ra + r * A + lane, sm * (gq - dot_q));
-            }
+            if (lane == 0) s_crit[lr] = critic;
+        }
+        __syncthreads();
 
-            // ---------------- world model: Gaussian NLL of next (state || reward), done BCE -------
-            float nll = 0.f, bce = 0.f;
-            if (has_sp) {
-                const bool valid = masked && t < T - 1;
-                if (lane < S1) {
-                    const float mean = sm_as_float(s_sp + (lr * S1 + lane) * 2);
-                    const float lv = sm_as_float(s_sp + (lr * S1 + lane) * 2 + 1);
-                    const float th = tanhf(lv / 3.f);
-                    const float var = fmaxf(expf(th * 3.f), 1e-6f);
-                    float gm = 0.f, gl = 0.f;
-                    if (valid) {
-                        const float d = mean - s_tgt[(lr + 1) * S1 + lane];
-                        nll = 0.5f * (logf(var) + d * d / var);
-                        gm = g_wm * d / var;
-                        gl = g_wm * 0.5f * (1.f / var - d * d / (var * var)) * var * (1.f - th * th);
+        // ---- phase B: the narrow terms, one THREAD per (row, part) instead of one warp per row -------------
+        // part 0: actor (A logits), part 1: world-model NLL over the S+1 dims, part 2: done BCE.  A warp now
+        // finishes 32 rows of a part per pass; these terms cost ~16 warp-instructions per row instead of ~430.
+        for (int item = threadIdx.x; item < kTileRows * 3; item += kLossWarps * 32) {
+            const int part = item / kTileRows, lr = item - part * kTileRows;
+            const int64_t r = tile * kTileRows + lr;
+            if (r >= N) continue;
+            const int e = (int)(r / T), t = (int)(r - (int64_t)e * T);
+            const bool masked = t < __ldg(a.io.episode_lens + e);
+            if (part == 0) {
+                // actor: clipped surrogate + entropy (:413-444, Discrete :197-222)
+                const int act = s_act[lr];
+                const float ret = s_ret[lr], v_old = s_ov[lr];
+                float amx = -INFINITY;
+                for (int i = 0; i < A; ++i) amx = fmaxf(amx, sm_as_float(s_ra + lr * A + i));
+                float qs = 0.f;
+                for (int i = 0; i < A; ++i) qs += expf(sm_as_float(s_ra + lr * A + i) - amx);
+                float ssum = 0.f;
+                for (int i = 0; i < A; ++i) ssum += expf(sm_as_float(s_ra + lr * A + i) - amx) / qs;   // Categorical renormalises
+                float ent = 0.f, logp = 0.f, p_act = 1.f, dot_p = 0.f;
+                bool in_act = false;
+                for (int i = 0; i < A; ++i) {
+                    const float sm = expf(sm_as_float(s_ra + lr * A + i) - amx) / qs, p = sm / ssum;
+                    const float L = logf(fminf(fmaxf(p, feps), 1.f - feps));
+                    ent -= p * L;
+                    if (i == act) { logp = L; p_act = p; in_act = p >= feps && p <= 1.f - feps; }
+                }
+                const float ratio = expf(logp - s_olp[lr]);
+                const float clipped = fminf(fmaxf(ratio, 1.f - a.cfg.eps_clip), 1.f + a.cfg.eps_clip);
+                const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
+                const float surr1 = ratio * adv, surr2 = clipped * adv;
+                const float actor = -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
+                const float critic = s_crit[lr];
+                if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
+                acc_actor += actor; acc_critic += critic;
+                if (masked) acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
+                if (g_ra) {
+                    const bool in_range = ratio >= 1.f - a.cfg.eps_clip && ratio <= 1.f + a.cfg.eps_clip;
+                    const float dmin = in_range ? adv : (surr1 < surr2 ? adv : 0.f);
+                    const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
+                    const float g_logp = -ga * dmin * ratio;
+                    // gp_i = d/dp_i of (-beta*ent + logp term);  p = sm / sum(sm);  sm = softmax(logits)
+                    auto gp_of = [&](int i, float p, float L) {
+                        const bool inside = p >= feps && p <= 1.f - feps;
+                        float gp = ga * a.cfg.entropy_weight * (L + (inside ? 1.f : 0.f));
+                        if (i == act && in_act) gp += g_logp / p_act;
+                        return gp;
+                    };
+                    float dot_q = 0.f;
+                    for (int i = 0; i < A; ++i) {
+                        const float sm = expf(sm_as_float(s_ra + lr * A + i) - amx) / qs, p = sm / ssum;
+                        dot_p += gp_of(i, p, logf(fminf(fmaxf(p, feps), 1.f - feps))) * p;
                     }
-                    if (g_sp) {
-                        st_from_float(g_sp + (r * S1 + lane) * 2, gm);
-                        st_from_float(g_sp + (r * S1 + lane) * 2 + 1, gl);
+                    for (int i = 0; i < A; ++i) {
+                        const float sm = expf(sm_as_float(s_ra + lr * A + i) - amx) / qs, p = sm / ssum;
+                        const float gq = (gp_of(i, p, logf(fminf(fmaxf(p, feps), 1.f - feps))) - dot_p) / ssum;
+                        dot_q += gq * sm;
+                    }
+                    for (int i = 0; i < A; ++i) {
+                        const float sm = expf(sm_as_float(s_ra + lr * A + i) - amx) / qs, p = sm / ssum;
+                        const float gq = (gp_of(i, p, logf(fminf(fmaxf(p, feps), 1.f - feps))) - dot_p) / ssum;
+                        st_from_float(g_ra + r * A + i, sm * (gq - dot_q));
                     }
                 }
-                nll = warp_sum(nll);
-            }
-            if (has_dl && lane == 0) {
+            } else if (part == 1) {
+                // world model: Gaussian NLL of next (state || reward) (:398-404, :232-241)
+                if (has_sp) {
+                    const bool valid = masked && t < T - 1;
+                    float nll = 0.f;
+                    for (int dd = 0; dd < S1; ++dd) {
+                        const float mean = sm_as_float(s_sp + (lr * S1 + dd) * 2);
+                        const float lv = sm_as_float(s_sp + (lr * S1 + dd) * 2 + 1);
+                        float gm = 0.f, gl = 0.f;
+                        if (valid) {
+                            const float th = tanhf(lv / 3.f);
+                            const float var = fmaxf(expf(th * 3.f), 1e-6f);
+                            const float d = mean - s_tgt[(lr + 1) * S1 + dd];
+                            nll += 0.5f * (logf(var) + d * d / var);
+                            gm = g_wm * d / var;
+                            gl = g_wm * 0.5f * (1.f / var - d * d / (var * var)) * var * (1.f - th * th);
+                        }
+                        if (g_sp) {
+                            st_from_float(g_sp + (r * S1 + dd) * 2, gm);
+                            st_from_float(g_sp + (r * S1 + dd) * 2 + 1, gl);
+                        }
+                    }
+                    acc_nll += nll;
+                }
+            } else if (has_dl) {
+                // done head: BCE on sigmoid(logit) (:406-411)
                 const float z = sm_as_float(s_dl + lr);
                 const float pd = 1.f / (1.f + expf(-z));
                 const float y = s_dn[lr] ? 1.f : 0.f;
                 const float l1 = logf(pd), l0 = logf(1.f - pd);
-                bce = -(y * fmaxf(l1, -100.f) + (1.f - y) * fmaxf(l0, -100.f));
+                const float bce = -(y * fmaxf(l1, -100.f) + (1.f - y) * fmaxf(l0, -100.f));
                 float g = 0.f;
                 if (masked) {
+                    acc_done += bce;
                     const float dp = -((l1 > -100.f ? y / pd : 0.f) - (l0 > -100.f ? (1.f - y) / (1.f - pd) : 0.f));
                     g = g_done * dp * pd * (1.f - pd);
                     if (!isfinite(g)) g = 0.f;
                 }
                 if (g_dl) st_from_float(g_dl + r, g);
             }
-
-            if (lane == 0) {
-                if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
-                acc_actor += actor; acc_critic += critic;
-                if (masked) {
-                    acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
-                    acc_done += bce;
-                }
-                acc_nll += nll;                                    // already zero where invalid
-            }
         }
         __syncthreads();                                           // this stage is refilled two tiles from now
     }
 
+    acc_ac = warp_sum(acc_ac); acc_actor = warp_sum(acc_actor); acc_critic = warp_sum(acc_critic);
+    acc_nll = warp_sum(acc_nll); acc_done = warp_sum(acc_done);
     __shared__ float sh[5][kLossWarps];
     if (lane == 0) { sh[0][warp] = acc_ac; sh[1][warp] = acc_actor; sh[2][warp] = acc_critic; sh[3][warp] = acc_nll; sh[4][warp] = acc_done; }
     __syncthreads();
