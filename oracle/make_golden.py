@@ -30,6 +30,11 @@ MODEL_CASES = dict(
              evolutionary=True,
              latent_gene_pool=dict(dim=32, num_genes_per_island=3, num_selected=2, tournament_size=2)),
     # value residual with the constant 0.5 mix, 8 heads
+    # continuous actions (tests/test_x_transformers_rl.py:5 parametrises them): squashed (Learner default) and not
+    c4c=dict(state_dim=6, num_actions=3, reward_range=(-2., 2.), max_timesteps=8, continuous_actions=True,
+             world_model=dict(attn_dim_head=16, heads=4, depth=2, attn_gate_values=True), evolutionary=False),
+    c5c=dict(state_dim=6, num_actions=3, reward_range=(-2., 2.), max_timesteps=8, continuous_actions=True, squash_continuous=False,
+             world_model=dict(attn_dim_head=16, heads=4, depth=1), evolutionary=False),
     c3s=dict(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=9,
              world_model=dict(attn_dim_head=16, heads=8, depth=2, add_value_residual=True),
              evolutionary=False),
@@ -71,8 +76,13 @@ def model_case(ref, case, seed):
         out[f'sd/{k}'] = _np(v)
     states = torch.randn(b, T, S, generator=g)
     prev_rewards = torch.randn(b, T, generator=g)
-    actions = torch.randint(0, A, (b, T), generator=g)
-    prev_actions = torch.cat((torch.full((b, 1), -1), actions[:, :-1]), dim=1)
+    cont = kw.get('continuous_actions', False)
+    if cont:
+        actions = torch.tanh(torch.randn(b, T, A, generator=g))
+        prev_actions = torch.cat((torch.zeros(b, 1, A), actions[:, :-1]), dim=1)
+    else:
+        actions = torch.randint(0, A, (b, T), generator=g)
+        prev_actions = torch.cat((torch.full((b, 1), -1), actions[:, :-1]), dim=1)
     lens = torch.tensor([T, max(T - 3, 2), max(T // 2, 2)])
     mask = torch.arange(T)[None] < lens[:, None]
     gene = None
@@ -103,16 +113,21 @@ def model_case(ref, case, seed):
     out['step/raw_actions'] = _np(torch.stack(step_ra))
     out['step/values'] = _np(torch.stack(step_va))
 
-    # (3) Discrete on the step logits (:197-222) -- probs, log-prob of a fixed action, entropy
-    d = ref.Discrete(torch.stack(step_ra))
+    # (3) the action distribution on the step outputs (:197-277)
     acts0 = actions[0]
-    out['step/probs'] = _np(d.probs)
-    out['step/log_prob'] = _np(d.log_prob(acts0))
-    out['step/entropy'] = _np(d.entropy())
+    if cont:
+        d = model.action_type_klass(torch.stack(step_ra))
+        out['step/mean_variance'] = _np(d.mean_variance)
+        out['step/log_prob'] = _np(d.log_prob(acts0))
+    else:
+        d = ref.Discrete(torch.stack(step_ra))
+        out['step/probs'] = _np(d.probs)
+        out['step/log_prob'] = _np(d.log_prob(acts0))
+        out['step/entropy'] = _np(d.entropy())
 
     # (4) losses on the full-sequence outputs, with gradients w.r.t. every head output (:939-978)
     old_values = torch.randn(b, T, va.shape[-1], generator=g) * 0.5
-    old_log_probs = -torch.rand(b, T, generator=g) * 1.5
+    old_log_probs = -torch.rand(*((b, T, A) if cont else (b, T)), generator=g) * 1.5
     lo, hi = kw['reward_range']
     returns = torch.randn(b, T, generator=g) * (hi - lo) * 0.2
     dones = torch.rand(b, T, generator=g) < 0.1

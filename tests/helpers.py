@@ -34,6 +34,7 @@ def oracle_config(kw, **over) -> R.Config:
         gate_values=wm.get('attn_gate_values', False), value_residual=wm.get('add_value_residual', False),
         learned_mix=wm.get('learned_value_residual_mix', False),
         evolutionary=kw.get('evolutionary', False), dim_gene=pool.get('dim', 0) if kw.get('evolutionary') else 0,
+        continuous=kw.get('continuous_actions', False), squash=kw.get('squash_continuous', True),
     )
     for k, v in over.items():
         setattr(cfg, k, v)

@@ -9,7 +9,7 @@ import torch
 from oracle import restated as R
 from helpers import golden_model, load_golden, split, t, rel_err
 
-CASES = ('c1', 'c2s', 'c3s')
+CASES = ('c1', 'c2s', 'c3s', 'c4c', 'c5c')
 TOL = 2e-5
 
 
@@ -44,6 +44,11 @@ def test_cached_rollout_steps(case, batched):
         ras.append(ra[0, 0]); vas.append(va[0, 0])
     assert rel_err(torch.stack(ras), step['raw_actions']) < TOL
     assert rel_err(torch.stack(vas), step['values']) < TOL
+    if cfg.continuous:
+        mean, var, _ = R.continuous_stats(step['raw_actions'])
+        assert rel_err(torch.stack((mean, var)), step['mean_variance']) < 1e-6
+        assert rel_err(R.continuous_log_prob(step['raw_actions'], i['actions'][0], cfg.squash), step['log_prob']) < 1e-5
+        return
     probs, logp, ent = R.discrete_stats(step['raw_actions'])
     assert rel_err(probs, step['probs']) < 1e-6
     assert rel_err(logp.gather(-1, i['actions'][0][:, None])[:, 0], step['log_prob']) < 1e-6
