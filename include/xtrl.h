@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define XTRL_ABI_VERSION 2
+#define XTRL_ABI_VERSION 3
 
 #define XTRL_OK            0
 #define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
@@ -61,6 +61,9 @@ typedef struct xtrl_model_desc {
     int32_t dense_bf16;       /* 0 = dense layers in fp32 FFMA (1e-5 parity with the fp32 reference);
                                  1 = QKV/out/FFN/head GEMMs on tcgen05 tensor cores, bf16 operands, fp32
                                  accumulation in TMEM (the 1e-2 "bf16" tolerance class)              */
+    int32_t continuous_actions; /* 0 = Discrete (:197-222); 1 = Continuous (:224-277): the actor head emits
+                                 (mean, log-variance) pairs, actions are float vectors of num_actions    */
+    int32_t squash_continuous;  /* tanh-squash sampled actions (Learner default :1077)                     */
 } xtrl_model_desc;
 
 /* offsets (in floats) of every tensor inside the packed fp32 weight blob the step kernel reads.
@@ -96,6 +99,7 @@ typedef struct xtrl_weight_layout {
         int64_t ff2_w;             /* [4D][D]                                                 */
         int64_t ff2_b;             /* [D]                                                     */
     } layer[XTRL_MAX_DEPTH];
+    int64_t action_embed_bias;     /* [D] continuous only: action_embeds is nn.Linear(A, D) (:309)           */
 } xtrl_weight_layout;
 
 /* fills *out; HOST pointers.  Pure host arithmetic (usable without a GPU).                    */
@@ -134,6 +138,12 @@ typedef struct xtrl_step_io {
     float   *value;               /* [B] HL-Gauss expectation of the critic logits            */
     float   *raw_actions;         /* [B][A] actor logits                                      */
     float   *value_logits;        /* [B][K] critic logits                                     */
+    /* continuous actions (desc->continuous_actions): float action vectors replace the int ids above;
+       log_prob is then [B][A] (per action dim) and raw_actions [B][2A] (mean, log-variance interleaved) */
+    const float   *prev_action_f;   /* [B][A] previous action, zeros at t=0 (:1242)             */
+    const float   *normal;          /* [B][A] standard-normal draws for Normal.sample */
+    const float   *forced_action_f; /* [B][A] or NULL: evaluate log-prob of these actions instead */
+    float         *action_f;        /* [B][A]                                                    */
 } xtrl_step_io;
 
 int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, void *kv_cache,
@@ -166,6 +176,9 @@ typedef struct xtrl_loss_cfg {
     float   actor_weight, critic_weight, autoreg_weight;
     int32_t normalize_advantages;   /* 1 (reference default, :298)                            */
     int32_t bf16_io;                /* 0: head outputs / grads fp32; 1: bf16 (math stays fp32) */
+    int32_t continuous;             /* Continuous actor (:224-277): raw_actions [N][2A], actions_f [N][A],
+                                       old_log_probs [N][A]                                                   */
+    int32_t squash;                 /* squash_continuous: entropy term = -log_prob (:425)                     */
 } xtrl_loss_cfg;
 
 typedef struct xtrl_loss_io {
@@ -191,6 +204,7 @@ typedef struct xtrl_loss_io {
     float *scalars;                 /* [8]: total, actor_mean, critic_mean, autoreg_mean, done_mean,
                                         n_masked, adv_mean, adv_var                           */
     double *workspace;              /* xtrl_ppo_loss_workspace_bytes() bytes, any contents     */
+    const float *actions_f;         /* [N][A] continuous actions (cfg.continuous), else NULL   */
 } xtrl_loss_io;
 
 int64_t xtrl_ppo_loss_workspace_bytes(void);

@@ -67,7 +67,7 @@ def model_config(cfg: R.Config, max_timesteps, **extra):
                            max_timesteps=max_timesteps, dim=cfg.dim, heads=cfg.heads, dim_head=cfg.dim_head,
                            depth=cfg.depth, num_bins=cfg.num_bins, dim_gene=cfg.dim_gene,
                            gate_values=cfg.gate_values, value_residual=cfg.value_residual,
-                           learned_mix=cfg.learned_mix, **extra)
+                           learned_mix=cfg.learned_mix, continuous=cfg.continuous, squash=cfg.squash, **extra)
 
 
 def random_state_dict(cfg: R.Config, seed=0, scale=0.2):
@@ -77,7 +77,7 @@ def random_state_dict(cfg: R.Config, seed=0, scale=0.2):
     rn = lambda *shape: torch.randn(*shape, generator=g) * scale
     hin = (3 if cfg.evolutionary else 2) * D
     sd = {
-        'reward_embed': rn(D), 'action_embeds.embed.weight': rn(A, D),
+        'reward_embed': rn(D),
         'to_state_embed.weight': rn(D, S), 'to_state_embed.bias': rn(D),
         'to_pred_done.0.weight': rn(1, 2 * D), 'to_pred_done.0.bias': rn(1),
         'to_pred.0.weight': rn(D, 2 * D), 'to_pred.0.bias': rn(D),
@@ -85,10 +85,14 @@ def random_state_dict(cfg: R.Config, seed=0, scale=0.2):
         'critic_head.0.weight': rn(2 * D, hin), 'critic_head.0.bias': rn(2 * D),
         'critic_head.2.weight': rn(K, 2 * D), 'critic_head.2.bias': rn(K),
         'action_head.0.weight': rn(2 * D, hin), 'action_head.0.bias': rn(2 * D),
-        'action_head.2.weight': rn(A, 2 * D), 'action_head.2.bias': rn(A),
+        'action_head.2.weight': rn(2 * A if cfg.continuous else A, 2 * D), 'action_head.2.bias': rn(2 * A if cfg.continuous else A),
         'transformer.project_in.weight': rn(D, S),
         'transformer.attn_layers.final_norm.gamma': 1 + rn(D),
     }
+    if cfg.continuous:
+        sd['action_embeds.weight'], sd['action_embeds.bias'] = rn(D, A), rn(D)
+    else:
+        sd['action_embeds.embed.weight'] = rn(A, D)
     if cfg.evolutionary:
         sd['latent_to_embed.weight'] = rn(D, G)
         sd['latent_to_embed.bias'] = rn(D)

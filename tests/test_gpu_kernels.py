@@ -82,7 +82,7 @@ def _loss_case(case):
     return cfg, i, seq, Lg, mask, ra, va, raw
 
 
-@pytest.mark.parametrize('case', ('c1', 'c2s', 'c3s'))
+@pytest.mark.parametrize('case', ('c1', 'c2s', 'c3s', 'c4c', 'c5c'))
 def test_ppo_loss_golden(case):
     ops = xtrl().ops
     cfg, i, seq, Lg, mask, ra, va, raw = _loss_case(case)
@@ -90,12 +90,13 @@ def test_ppo_loss_golden(case):
     lc = ops.LossConfig(num_actions=cfg.num_actions, num_bins=cfg.num_bins, state_dim=cfg.state_dim,
                         reward_range=cfg.reward_range, eps_clip=cfg.eps_clip, value_clip=cfg.value_clip,
                         entropy_weight=cfg.entropy_weight, actor_weight=cfg.actor_loss_weight,
-                        critic_weight=cfg.critic_loss_weight, autoreg_weight=cfg.autoregressive_loss_weight)
+                        critic_weight=cfg.critic_loss_weight, autoreg_weight=cfg.autoregressive_loss_weight,
+                        continuous=cfg.continuous, squash=cfg.squash)
     # the head outputs of the reference run (golden) feed the kernel; raw world-model heads from the oracle
     scal, grads, per = ops.ppo_loss_fwd_bwd(
         lc, cu(seq['raw_actions']), cu(seq['values']), cu(raw['state_pred_raw'].detach()), cu(raw['done_logit'].detach()),
-        cu(i['actions'].int()), cu(Lg['old_log_probs']), cu(Lg['returns']), cu(Lg['old_values_scalar']), cu(real),
-        cu(Lg['dones']), cu(i['lens'].int()), per_step=True)
+        cu(i['actions'].float() if cfg.continuous else i['actions'].int()), cu(Lg['old_log_probs']), cu(Lg['returns']),
+        cu(Lg['old_values_scalar']), cu(real), cu(Lg['dones']), cu(i['lens'].int()), per_step=True)
     scal, per = scal.cpu(), per.cpu()
     assert rel_err(per[..., 0], Lg['actor']) < TOL
     assert rel_err(per[..., 1], Lg['critic']) < TOL
@@ -223,14 +224,15 @@ def _rollout_kernel(sd, cfg, states, prev_actions, prev_rewards, genes=None, gen
     mean, var = torch.zeros(S + 1, device=DEV), torch.ones(S + 1, device=DEV)
     ras, vas, vals = [], [], []
     for t in range(T):
-        out = st.step(cu(states[:, t]), cu(prev_actions[:, t].int()), cu(prev_rewards[:, t]), mean, var,
-                      forced_action=cu(torch.zeros(B, dtype=torch.int32)), want_logits=True,
+        pa = cu(prev_actions[:, t].float()) if cfg.continuous else cu(prev_actions[:, t].int())
+        fa = cu(torch.zeros(B, cfg.num_actions)) if cfg.continuous else cu(torch.zeros(B, dtype=torch.int32))
+        out = st.step(cu(states[:, t]), pa, cu(prev_rewards[:, t]), mean, var, forced_action=fa, want_logits=True,
                       genes=None if genes is None else cu(genes), gene_ids=None if gene_ids is None else cu(gene_ids.int()))
         ras.append(out['raw_actions'].clone()); vas.append(out['value_logits'].clone()); vals.append(out['value'].clone())
     return torch.stack(ras).cpu(), torch.stack(vas).cpu(), torch.stack(vals).cpu()
 
 
-@pytest.mark.parametrize('case', ('c1', 'c2s', 'c3s'))
+@pytest.mark.parametrize('case', ('c1', 'c2s', 'c3s', 'c4c', 'c5c'))
 def test_wm_step_golden_rollout(case):
     """the reference's own forward_eval loop (golden `step/*`, env 0) and the oracle for all 3 envs."""
     z, kw, cfg, sd = golden_model(case)
@@ -435,6 +437,30 @@ def test_ppo_loss_empty_and_single_row():
     cfg = R.Config(state_dim=4, num_actions=3, reward_range=(-1., 1.), num_bins=51)
     want = R.critic_loss(va, torch.full((1, 1), 0.3), torch.zeros(1, 1), cfg)
     assert rel_err(scal[2].cpu(), want.mean()) < 1e-5
+
+
+@pytest.mark.parametrize('squash', (True, False))
+def test_wm_step_continuous_sampling(squash):
+    """Continuous head (:224-277): sample = mean + std * normal (tanh-squashed), per-dim log-prob, on given normals."""
+    ops = xtrl().ops
+    cfg = R.Config(state_dim=6, num_actions=3, heads=4, depth=2, reward_range=(-2., 2.), continuous=True, squash=squash)
+    sd = random_state_dict(cfg, seed=9, scale=0.4)
+    B = 300
+    g = torch.Generator().manual_seed(1)
+    state, prev_r = torch.randn(B, 6, generator=g), torch.randn(B, generator=g)
+    prev_a, normal = torch.tanh(torch.randn(B, 3, generator=g)), torch.randn(B, 3, generator=g)
+    st = ops.WorldModelStepper(model_config(cfg, 4), B, DEV)
+    st.load_state_dict({k: v.to(DEV) for k, v in sd.items()})
+    mean, var = torch.zeros(7, device=DEV), torch.ones(7, device=DEV)
+    out = st.step(cu(state), cu(prev_a), cu(prev_r), mean, var, normal=cu(normal), want_logits=True)
+    ra, va, *_ = R.wm_forward(sd, cfg, state[:, None], prev_a[:, None], prev_r[:, None], 1.)
+    ra = ra[:, 0]
+    assert out['raw_actions'].shape == (B, 6) and rel_err(out['raw_actions'].cpu(), ra) < 3e-5
+    want_a = R.continuous_sample(ra, normal, squash)
+    assert rel_err(out['action'].cpu(), want_a) < 3e-5
+    got_lp = out['log_prob'].cpu()
+    want_lp = R.continuous_log_prob(ra, out['action'].cpu(), squash)          # at the kernel's own action
+    assert got_lp.shape == (B, 3) and rel_err(got_lp, want_lp) < 1e-4
 
 
 def test_wm_step_bf16_kv_cache():

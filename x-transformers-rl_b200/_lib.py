@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-XTRL_ABI_VERSION = 2
+XTRL_ABI_VERSION = 3
 XTRL_MAX_DEPTH = 16
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -21,7 +21,8 @@ class ModelDesc(C.Structure):
     _fields_ = [(n, c_i32) for n in (
         'state_dim', 'num_actions', 'dim', 'heads', 'dim_head', 'depth', 'num_bins', 'dim_gene',
         'gate_values', 'value_residual', 'learned_mix', 'max_timesteps', 'rotary_true_pos', 'kv_bf16')] + [
-        ('reward_min', c_f32), ('reward_max', c_f32), ('dense_bf16', c_i32)]
+        ('reward_min', c_f32), ('reward_max', c_f32), ('dense_bf16', c_i32), ('continuous_actions', c_i32),
+        ('squash_continuous', c_i32)]
 
 
 class _LayerLayout(C.Structure):
@@ -33,13 +34,14 @@ class WeightLayout(C.Structure):
     _fields_ = [('total', c_i64), ('s_pad', c_i32), ('n_qkv', c_i32), ('head_in', c_i32)] + [
         (n, c_i64) for n in ('in_proj', 'state_embed_bias', 'action_embed', 'reward_embed', 'latent_w',
                              'latent_b', 'final_gamma', 'head1_w', 'head1_b', 'actor2_w', 'actor2_b',
-                             'critic2_w', 'critic2_b')] + [('layer', _LayerLayout * XTRL_MAX_DEPTH)]
+                             'critic2_w', 'critic2_b')] + [('layer', _LayerLayout * XTRL_MAX_DEPTH), ('action_embed_bias', c_i64)]
 
 
 class StepIO(C.Structure):
     _fields_ = [(n, c_vp) for n in ('state', 'prev_action', 'prev_reward', 'pos', 'rs_mean', 'rs_var',
                                     'genes', 'gene_ids', 'uniform', 'forced_action')] + [
-        ('reward_flag', c_f32), ('pos_uniform', c_i32), ('tc_weights', c_vp)] + [(n, c_vp) for n in ('action', 'log_prob', 'value', 'raw_actions', 'value_logits')]
+        ('reward_flag', c_f32), ('pos_uniform', c_i32), ('tc_weights', c_vp)] + [(n, c_vp) for n in ('action', 'log_prob', 'value', 'raw_actions', 'value_logits',
+                                           'prev_action_f', 'normal', 'forced_action_f', 'action_f')]
 
 
 class LossCfg(C.Structure):
@@ -47,14 +49,15 @@ class LossCfg(C.Structure):
                 ('reward_min', c_f32), ('reward_max', c_f32),
                 ('eps_clip', c_f32), ('value_clip', c_f32), ('entropy_weight', c_f32),
                 ('actor_weight', c_f32), ('critic_weight', c_f32), ('autoreg_weight', c_f32),
-                ('normalize_advantages', c_i32), ('bf16_io', c_i32)]
+                ('normalize_advantages', c_i32), ('bf16_io', c_i32), ('continuous', c_i32), ('squash', c_i32)]
 
 
 class LossIO(C.Structure):
     _fields_ = [(n, c_vp) for n in (
         'raw_actions', 'value_logits', 'state_pred_raw', 'done_logit',
         'actions', 'old_log_probs', 'returns', 'old_values', 'target', 'dones', 'episode_lens',
-        'g_raw_actions', 'g_value_logits', 'g_state_pred_raw', 'g_done_logit', 'per_step', 'scalars', 'workspace')]
+        'g_raw_actions', 'g_value_logits', 'g_state_pred_raw', 'g_done_logit', 'per_step', 'scalars', 'workspace',
+        'actions_f')]
 
 
 class PoolDesc(C.Structure):

@@ -114,15 +114,15 @@ __device__ __forceinline__ void stage_region(unsigned char *dst, const void *bas
 struct TileLayout {                      // byte offsets inside one stage of shared memory
     int vl, ra, sp, dl, act, olp, ret, ov, tgt, dn, total;
 };
-__host__ __device__ static inline TileLayout tile_layout(int A, int K, int S1, int sz) {
+__host__ __device__ static inline TileLayout tile_layout(int AW, int AL, int K, int S1, int sz) {   // AW: actor head width, AL: actions per row
     TileLayout t; int o = 0;
     auto take = [&](int n) { int at = o; o += (n + 15) & ~15; return at; };
     t.vl = take(kTileRows * K * sz);
-    t.ra = take(kTileRows * A * sz);
+    t.ra = take(kTileRows * AW * sz);
     t.sp = take(kTileRows * 2 * S1 * sz);
     t.dl = take(kTileRows * sz);
-    t.act = take(kTileRows * 4);
-    t.olp = take(kTileRows * 4);
+    t.act = take(kTileRows * 4 * AL);
+    t.olp = take(kTileRows * 4 * AL);
     t.ret = take(kTileRows * 4);
     t.ov = take(kTileRows * 4);
     t.tgt = take((kTileRows + 1) * S1 * 4);
@@ -151,7 +151,9 @@ ppo_loss_kernel(const LossArgs a) {
     const int A = a.cfg.num_actions, K = a.cfg.num_bins, S1 = a.cfg.state_dim + 1, T = a.T;
     const int64_t N = (int64_t)a.b * T;
     const double *ws = a.io.workspace;
-    const TileLayout tl = tile_layout(A, K, S1, (int)sizeof(TIO));
+    const bool cont = a.cfg.continuous != 0;
+    const int AW = cont ? 2 * A : A, AL = cont ? A : 1;
+    const TileLayout tl = tile_layout(AW, AL, K, S1, (int)sizeof(TIO));
 
     // masked advantage statistics (normalize(), :103-112)
     const double n_mask = ws[WS_N_MASK], n_wm = ws[WS_N_WM];
@@ -179,11 +181,11 @@ ppo_loss_kernel(const LossArgs a) {
         const int64_t r0 = tile * kTileRows;
         const int sz = (int)sizeof(TIO);
         stage_region(st + tl.vl, a.io.value_logits, r0 * K * sz, kTileRows * K * sz, N * K * sz);
-        stage_region(st + tl.ra, a.io.raw_actions, r0 * A * sz, kTileRows * A * sz, N * A * sz);
+        stage_region(st + tl.ra, a.io.raw_actions, r0 * AW * sz, kTileRows * AW * sz, N * AW * sz);
         stage_region(st + tl.sp, a.io.state_pred_raw, r0 * 2 * S1 * sz, kTileRows * 2 * S1 * sz, N * 2 * S1 * sz);
         stage_region(st + tl.dl, a.io.done_logit, r0 * sz, kTileRows * sz, N * sz);
-        stage_region(st + tl.act, a.io.actions, r0 * 4, kTileRows * 4, N * 4);
-        stage_region(st + tl.olp, a.io.old_log_probs, r0 * 4, kTileRows * 4, N * 4);
+        stage_region(st + tl.act, cont ? (const void *)a.io.actions_f : (const void *)a.io.actions, r0 * 4 * AL, kTileRows * 4 * AL, N * 4 * AL);
+        stage_region(st + tl.olp, a.io.old_log_probs, r0 * 4 * AL, kTileRows * 4 * AL, N * 4 * AL);
         stage_region(st + tl.ret, a.io.returns, r0 * 4, kTileRows * 4, N * 4);
         stage_region(st + tl.ov, a.io.old_values, r0 * 4, kTileRows * 4, N * 4);
         stage_region(st + tl.tgt, a.io.target, r0 * S1 * 4, (kTileRows + 1) * S1 * 4, N * S1 * 4);
@@ -319,7 +321,43 @@ ppo_loss_kernel(const LossArgs a) {
             if (r >= N) continue;
             const int e = (int)(r / T), t = (int)(r - (int64_t)e * T);
             const bool masked = t < __ldg(a.io.episode_lens + e);
-            if (part == 0) {
+            if (part == 0 && cont) {
+                // actor, Continuous (:224-277, :413-444): per action dim, summed over dims (:442)
+                const float ret = s_ret[lr], v_old = s_ov[lr];
+                const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
+                const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
+                const float *s_af = (const float *)s_act;
+                float actor = 0.f;
+                for (int i = 0; i < A; ++i) {
+                    const float mean = sm_as_float(s_ra + (lr * A + i) * 2), lv = sm_as_float(s_ra + (lr * A + i) * 2 + 1);
+                    const float th = tanhf(lv / 3.f), var = expf(th * 3.f);
+                    const bool inside = var > 1e-5f;
+                    const float sd = sqrtf(fmaxf(var, 1e-5f));
+                    const float v = s_af[lr * A + i], df = v - mean;
+                    float logp = -(df * df) / (2.f * sd * sd) - logf(sd) - 0.91893853320467274178f;
+                    if (a.cfg.squash) logp -= logf(fmaxf(1.f - v * v, 1e-20f));
+                    const float ent = a.cfg.squash ? -logp : 1.41893853320467274178f + logf(sd);   // 0.5 + 0.5 log(2 pi) + log sd
+                    const float ratio = expf(logp - s_olp[lr * A + i]);
+                    const float clipped = fminf(fmaxf(ratio, 1.f - a.cfg.eps_clip), 1.f + a.cfg.eps_clip);
+                    const float surr1 = ratio * adv, surr2 = clipped * adv;
+                    actor += -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
+                    if (g_ra) {
+                        const bool in_range = ratio >= 1.f - a.cfg.eps_clip && ratio <= 1.f + a.cfg.eps_clip;
+                        const float dmin = in_range ? adv : (surr1 < surr2 ? adv : 0.f);
+                        const float g_lp = ga * (-dmin * ratio + (a.cfg.squash ? a.cfg.entropy_weight : 0.f));
+                        const float g_mean = g_lp * df / (sd * sd);
+                        float g_sd = g_lp * (df * df / (sd * sd * sd) - 1.f / sd);
+                        if (!a.cfg.squash) g_sd -= ga * a.cfg.entropy_weight / sd;
+                        const float g_lv = inside ? g_sd * (0.5f / sd) * var * (1.f - th * th) : 0.f;
+                        st_from_float(g_ra + (r * A + i) * 2, g_mean);
+                        st_from_float(g_ra + (r * A + i) * 2 + 1, g_lv);
+                    }
+                }
+                const float critic = s_crit[lr];
+                if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
+                acc_actor += actor; acc_critic += critic;
+                if (masked) acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
+            } else if (part == 0) {
                 // actor: clipped surrogate + entropy (:413-444, Discrete :197-222)
                 const int act = s_act[lr];
                 const float ret = s_ret[lr], v_old = s_ov[lr];
@@ -506,7 +544,7 @@ extern "C" int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_i
         XTRL_CUDA(cudaMemsetAsync(io->scalars, 0, sizeof(float) * 8, s));
         return XTRL_OK;
     }
-    XTRL_REQUIRE(io->raw_actions && io->value_logits && io->actions && io->old_log_probs && io->returns &&
+    XTRL_REQUIRE(io->raw_actions && io->value_logits && (cfg->continuous ? (const void *)io->actions_f : (const void *)io->actions) && io->old_log_probs && io->returns &&
                  io->old_values && io->episode_lens && io->scalars && io->workspace, XTRL_E_BADARG,
                  "xtrl_ppo_loss_fwd_bwd: null required pointer");
     XTRL_REQUIRE(!io->state_pred_raw || io->target, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: state_pred_raw without target");
@@ -521,11 +559,12 @@ extern "C" int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_i
     const int kj = (cfg->num_bins + 31) / 32;
     const int KJ = kj <= 1 ? 1 : kj <= 2 ? 2 : kj <= 4 ? 4 : 8;
     const int sz = cfg->bf16_io ? 2 : 4;
-    const TileLayout tl = tile_layout(cfg->num_actions, cfg->num_bins, cfg->state_dim + 1, sz);
+    const int AWh = cfg->continuous ? 2 * cfg->num_actions : cfg->num_actions, ALh = cfg->continuous ? cfg->num_actions : 1;
+    const TileLayout tl = tile_layout(AWh, ALh, cfg->num_bins, cfg->state_dim + 1, sz);
     const size_t smem = 2 * (size_t)tl.total;                              // double-buffered tile stages
     XTRL_REQUIRE(smem <= 200 * 1024, XTRL_E_UNSUPPORTED, "xtrl_ppo_loss_fwd_bwd: tile needs %zu B shared memory", smem);
     const void *ptrs[] = {io->raw_actions, io->value_logits, io->state_pred_raw, io->done_logit, io->actions, io->old_log_probs,
-                          io->returns, io->old_values, io->target, io->dones};
+                          io->returns, io->old_values, io->target, io->dones, io->actions_f};
     for (const void *p : ptrs)
         XTRL_REQUIRE(((uintptr_t)p & 15) == 0, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: input pointers must be 16-byte aligned");
     const int64_t ntiles = (N + kTileRows - 1) / kTileRows;

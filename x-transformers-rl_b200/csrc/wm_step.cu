@@ -42,12 +42,13 @@ static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
 struct StepDims {
     int S, Spad, A, Apad, D, H, I, L, K, Kpad, G, NQ, HIN, Tmax;
-    int gate, vres, mix, rot, kvbf16, tc;
+    int gate, vres, mix, rot, kvbf16, tc, cont, squash;
 };
 
 static int make_dims(const xtrl_model_desc *d, StepDims *o) {
     o->S = d->state_dim; o->Spad = (int)align4(d->state_dim + 0); o->A = d->num_actions;
-    o->Apad = (d->num_actions + 3) & ~3; o->D = d->dim; o->H = d->heads; o->I = d->heads * d->dim_head;
+    o->cont = d->continuous_actions != 0; o->squash = d->squash_continuous != 0;
+    o->Apad = ((o->cont ? 2 : 1) * d->num_actions + 3) & ~3;      /* actor head width: A logits, or A (mean, log-variance) pairs */ o->D = d->dim; o->H = d->heads; o->I = d->heads * d->dim_head;
     o->L = d->depth; o->K = d->num_bins; o->Kpad = (d->num_bins + 3) & ~3; o->G = d->dim_gene;
     o->gate = d->gate_values != 0; o->vres = d->value_residual != 0;
     o->mix = o->vres && d->learned_mix != 0;
@@ -113,6 +114,7 @@ extern "C" int xtrl_wm_weight_layout(const xtrl_model_desc *desc, xtrl_weight_la
         out->layer[l].ff2_w = take((int64_t)4 * d.D * d.D);
         out->layer[l].ff2_b = take(d.D);
     }
+    out->action_embed_bias = d.cont ? take(d.D) : -1;
     out->total = o;
     return XTRL_OK;
 }
@@ -432,8 +434,14 @@ wm_step_kernel(const StepArgs a) {
         if (n < D) {
             float v = acc;
             if (env < a.B) {
-                const int pa = __ldg(a.io.prev_action + env);
-                if (pa >= 0) v += __ldg(W + a.w.action_embed + (int64_t)pa * D + n);     // SafeEmbedding :181-195
+                if (d.cont) {                                                            // nn.Linear(A, D) on the previous action (:309)
+                    v += __ldg(W + a.w.action_embed_bias + n);
+                    for (int i = 0; i < d.A; ++i)
+                        v = fmaf(__ldg(a.io.prev_action_f + (int64_t)env * d.A + i), __ldg(W + a.w.action_embed + (int64_t)i * D + n), v);
+                } else {
+                    const int pa = __ldg(a.io.prev_action + env);
+                    if (pa >= 0) v += __ldg(W + a.w.action_embed + (int64_t)pa * D + n); // SafeEmbedding :181-195
+                }
                 v += sst[e * lst + Spad] * __ldg(W + a.w.reward_embed + n) * a.io.reward_flag;
             }
             sx[e * D + n] = v;
@@ -723,6 +731,30 @@ wm_step_kernel(const StepArgs a) {
         se = warp_sum(se); sc = warp_sum(sc);
         if (lane == 0 && a.io.value) a.io.value[env] = sc / se;
         // actor
+        if (d.cont) {                                          // Continuous (:224-277): lane i <-> action dim i
+            if (a.io.raw_actions)
+                for (int i = lane; i < 2 * d.A; i += 32) a.io.raw_actions[(int64_t)env * 2 * d.A + i] = la[i];
+            if (lane < d.A) {
+                const float mean = la[2 * lane], lv = la[2 * lane + 1];
+                const float var = expf(tanhf(lv / 3.f) * 3.f);                 // softclamp :124,:237
+                const float sd = sqrtf(fmaxf(var, 1e-5f));
+                float x;
+                bool have = true;
+                if (a.io.forced_action_f) x = __ldg(a.io.forced_action_f + (int64_t)env * d.A + lane);
+                else if (a.io.normal) {
+                    x = fmaf(sd, __ldg(a.io.normal + (int64_t)env * d.A + lane), mean);
+                    if (d.squash) x = tanhf(x);
+                } else { x = 0.f; have = false; }
+                if (have) {
+                    const float df = x - mean;
+                    float lp = -(df * df) / (2.f * sd * sd) - logf(sd) - 0.91893853320467274178f;   // log sqrt(2 pi)
+                    if (d.squash) lp -= logf(fmaxf(1.f - x * x, 1e-20f));    // :271 (evaluated at the squashed value)
+                    if (a.io.action_f) a.io.action_f[(int64_t)env * d.A + lane] = x;
+                    if (a.io.log_prob) a.io.log_prob[(int64_t)env * d.A + lane] = lp;
+                }
+            }
+            continue;
+        }
         const float lg = lane < d.A ? la[lane] : -INFINITY;
         if (lane < d.A && a.io.raw_actions) a.io.raw_actions[(int64_t)env * d.A + lane] = lg;
         const float amx = warp_max(lg);
@@ -761,8 +793,9 @@ extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, v
     XTRL_REQUIRE(num_envs >= 0, XTRL_E_BADARG, "xtrl_wm_step: num_envs=%d", num_envs);
     if (num_envs == 0) return XTRL_OK;                      // nothing to do (and the caller's buffers may be empty)
     XTRL_REQUIRE(io && weights && kv_cache, XTRL_E_BADARG, "xtrl_wm_step: null pointer");
-    XTRL_REQUIRE(io->state && io->prev_action && io->prev_reward && io->rs_mean && io->rs_var,
-                 XTRL_E_BADARG, "xtrl_wm_step: null required input");
+    XTRL_REQUIRE(io->state && io->prev_reward && io->rs_mean && io->rs_var, XTRL_E_BADARG, "xtrl_wm_step: null required input");
+    XTRL_REQUIRE(desc->continuous_actions ? io->prev_action_f != nullptr : io->prev_action != nullptr, XTRL_E_BADARG,
+                 "xtrl_wm_step: previous actions missing (%s)", desc->continuous_actions ? "prev_action_f" : "prev_action");
     XTRL_REQUIRE(io->pos || (io->pos_uniform >= 0 && io->pos_uniform < desc->max_timesteps), XTRL_E_BADARG,
                  "xtrl_wm_step: pos_uniform=%d outside [0, max_timesteps=%d)", io->pos_uniform, desc->max_timesteps);
     XTRL_REQUIRE(desc->dim_gene == 0 || (io->genes && io->gene_ids), XTRL_E_BADARG,

@@ -85,12 +85,14 @@ class LossConfig:
     critic_weight: float = 1.
     autoreg_weight: float = 1.
     normalize_advantages: bool = True
+    continuous: bool = False
+    squash: bool = True
 
     def c_struct(self, bf16):
         return L.LossCfg(self.num_actions, self.num_bins, self.state_dim, float(self.reward_range[0]),
                          float(self.reward_range[1]), self.eps_clip, self.value_clip, self.entropy_weight,
                          self.actor_weight, self.critic_weight, self.autoreg_weight,
-                         int(self.normalize_advantages), int(bf16))
+                         int(self.normalize_advantages), int(bf16), int(self.continuous), int(self.squash))
 
 
 SCALAR_NAMES = ('total', 'actor_loss', 'critic_loss', 'autoreg_loss', 'pred_done_loss', 'n_masked', 'adv_mean', 'adv_var')
@@ -101,7 +103,7 @@ def ppo_loss_fwd_bwd(cfg: LossConfig, raw_actions, value_logits, state_pred_raw,
     """All rows of a (b, T) minibatch.  Head outputs (b,T,A), (b,T,K), (b,T,2(S+1)) raw (mean, logvar
     interleaved), (b,T) pre-sigmoid; fp32 or bf16.  Returns (scalars[8], grads dict[, per_step (b,T,2)])."""
     lib = L.load()
-    b, T = actions.shape
+    b, T = actions.shape[:2]
     io_dtype = raw_actions.dtype
     if io_dtype not in (torch.float32, torch.bfloat16):
         raise L.XtrlError(f'ppo_loss: head outputs must be fp32 or bf16, got {io_dtype}')
@@ -118,11 +120,12 @@ def ppo_loss_fwd_bwd(cfg: LossConfig, raw_actions, value_logits, state_pred_raw,
     ws = torch.empty(lib.xtrl_ppo_loss_workspace_bytes() // 8, device=dev, dtype=torch.float64)
     io = L.LossIO(_ptr(raw_actions, None, 'raw_actions'), _ptr(value_logits, None, 'value_logits'),
                   _ptr(state_pred_raw, None, 'state_pred_raw'), _ptr(done_logit, None, 'done_logit'),
-                  _ptr(actions, torch.int32, 'actions'), _ptr(old_log_probs, torch.float32, 'old_log_probs'),
+                  _ptr(None if cfg.continuous else actions, torch.int32, 'actions'), _ptr(old_log_probs, torch.float32, 'old_log_probs'),
                   _ptr(returns, torch.float32, 'returns'), _ptr(old_values, torch.float32, 'old_values'),
                   _ptr(target, torch.float32, 'target'), _ptr(bd, torch.uint8, 'dones'),
                   _ptr(episode_lens, torch.int32, 'episode_lens'),
-                  _ptr(g_ra), _ptr(g_vl), _ptr(g_sp), _ptr(g_dl), _ptr(ps), _ptr(scalars), _ptr(ws))
+                  _ptr(g_ra), _ptr(g_vl), _ptr(g_sp), _ptr(g_dl), _ptr(ps), _ptr(scalars), _ptr(ws),
+                  _ptr(actions if cfg.continuous else None, torch.float32, 'actions (continuous)'))
     cs = cfg.c_struct(io_dtype == torch.bfloat16)
     L.check(lib.xtrl_ppo_loss_fwd_bwd(C.byref(cs), C.byref(io), b, T, _stream()), 'xtrl_ppo_loss_fwd_bwd')
     grads = dict(raw_actions=g_ra, value_logits=g_vl, state_pred_raw=g_sp, done_logit=g_dl)
@@ -196,6 +199,8 @@ class ModelConfig:
     rotary_true_pos: bool = False
     kv_bf16: bool = False
     dense_bf16: bool = False      # tcgen05 bf16 GEMMs for QKV/out/FFN/heads (1e-2 tolerance class)
+    continuous: bool = False      # continuous_actions: Gaussian (mean, log-variance) actor head, float action vectors
+    squash: bool = True           # squash_continuous
 
     WORLD_MODEL_KEYS = ('attn_dim_head', 'heads', 'depth', 'attn_gate_values', 'add_value_residual',
                         'learned_value_residual_mix')
@@ -223,7 +228,8 @@ class ModelConfig:
         return L.ModelDesc(self.state_dim, self.num_actions, self.dim, self.heads, self.dim_head, self.depth,
                            self.num_bins, self.dim_gene, int(self.gate_values), int(self.value_residual),
                            int(self.learned_mix), self.max_timesteps, int(self.rotary_true_pos), int(self.kv_bf16),
-                           float(self.reward_range[0]), float(self.reward_range[1]), int(self.dense_bf16))
+                           float(self.reward_range[0]), float(self.reward_range[1]), int(self.dense_bf16),
+                           int(self.continuous), int(self.squash))
 
 
 def weight_layout(cfg: ModelConfig) -> L.WeightLayout:
@@ -254,7 +260,11 @@ def pack_weights(sd: dict, cfg: ModelConfig, out=None, device=None):
     in_proj = torch.cat((sd['transformer.project_in.weight'].T, sd['to_state_embed.weight'].T), dim=1)   # (S, 2D)
     put(lay.in_proj, in_proj)
     put(lay.state_embed_bias, sd['to_state_embed.bias'])
-    put(lay.action_embed, sd['action_embeds.embed.weight'])
+    if cfg.continuous:
+        put(lay.action_embed, sd['action_embeds.weight'].T)           # nn.Linear(A, D) -> [A][D]
+        put(lay.action_embed_bias, sd['action_embeds.bias'])
+    else:
+        put(lay.action_embed, sd['action_embeds.embed.weight'])
     put(lay.reward_embed, sd['reward_embed'])
     if G > 0:
         put(lay.latent_w, sd['latent_to_embed.weight'].T)
@@ -262,7 +272,7 @@ def pack_weights(sd: dict, cfg: ModelConfig, out=None, device=None):
     put(lay.final_gamma, sd[f'{tf}.final_norm.gamma'])
     put(lay.head1_w, torch.cat((sd['action_head.0.weight'].T, sd['critic_head.0.weight'].T), dim=1))
     put(lay.head1_b, torch.cat((sd['action_head.0.bias'], sd['critic_head.0.bias'])))
-    a_pad, k_pad = (A + 3) & ~3, (K + 3) & ~3
+    a_pad, k_pad = ((2 * A if cfg.continuous else A) + 3) & ~3, (K + 3) & ~3
     put(lay.actor2_w, sd['action_head.2.weight'].T, ld=a_pad)
     put(lay.actor2_b, sd['action_head.2.bias'])
     put(lay.critic2_w, sd['critic_head.2.weight'].T, ld=k_pad)
@@ -326,7 +336,8 @@ class WorldModelStepper:
         self.pos.zero_()
 
     def step(self, state, prev_action, prev_reward, rs_mean, rs_var, *, uniform=None, forced_action=None,
-             genes=None, gene_ids=None, reward_flag=1., out=None, want_logits=False, advance=True, pos_uniform=None):
+             genes=None, gene_ids=None, reward_flag=1., out=None, want_logits=False, advance=True, pos_uniform=None,
+             normal=None):
         """state (B,S) f32; prev_action (B,) i32 (-1 none); prev_reward (B,) f32; uniform (B,) f32.
         pos_uniform: int -> every env is at that timestep (lock-step rollout; self.pos is not read or advanced).
         Returns dict(action i32, log_prob, value[, raw_actions, value_logits])."""
@@ -336,19 +347,26 @@ class WorldModelStepper:
         if state.shape != (B, cfg.state_dim):
             raise L.XtrlError(f'step: state shape {tuple(state.shape)} != {(B, cfg.state_dim)}')
         out = {} if out is None else out
-        for name, dt, shape in (('action', torch.int32, (B,)), ('log_prob', torch.float32, (B,)), ('value', torch.float32, (B,))):
+        cont, A = cfg.continuous, cfg.num_actions
+        # continuous: prev_action / forced_action / action are float (B, A), log_prob is (B, A), `normal` replaces `uniform`
+        for name, dt, shape in (('action', torch.float32 if cont else torch.int32, (B, A) if cont else (B,)),
+                                ('log_prob', torch.float32, (B, A) if cont else (B,)), ('value', torch.float32, (B,))):
             if name not in out:
                 out[name] = torch.empty(shape, device=dev, dtype=dt)
         if want_logits:
-            out.setdefault('raw_actions', torch.empty(B, cfg.num_actions, device=dev))
+            out.setdefault('raw_actions', torch.empty(B, 2 * A if cont else A, device=dev))
             out.setdefault('value_logits', torch.empty(B, cfg.num_bins, device=dev))
-        io = L.StepIO(_ptr(state, torch.float32, 'state'), _ptr(prev_action, torch.int32, 'prev_action'),
+        io = L.StepIO(_ptr(state, torch.float32, 'state'), _ptr(None if cont else prev_action, torch.int32, 'prev_action'),
                       _ptr(prev_reward, torch.float32, 'prev_reward'), _ptr(self.pos if pos_uniform is None else None, torch.int32),
                       _ptr(rs_mean, torch.float32, 'rs_mean'), _ptr(rs_var, torch.float32, 'rs_var'),
                       _ptr(genes, torch.float32, 'genes'), _ptr(gene_ids, torch.int32, 'gene_ids'),
-                      _ptr(uniform, torch.float32, 'uniform'), _ptr(forced_action, torch.int32, 'forced_action'),
-                      float(reward_flag), int(pos_uniform or 0), _ptr(self.tc_weights), _ptr(out['action']), _ptr(out['log_prob']), _ptr(out['value']),
-                      _ptr(out.get('raw_actions')), _ptr(out.get('value_logits')))
+                      _ptr(uniform, torch.float32, 'uniform'), _ptr(None if cont else forced_action, torch.int32, 'forced_action'),
+                      float(reward_flag), int(pos_uniform or 0), _ptr(self.tc_weights), _ptr(None if cont else out['action']),
+                      _ptr(out['log_prob']), _ptr(out['value']), _ptr(out.get('raw_actions')), _ptr(out.get('value_logits')),
+                      _ptr(prev_action if cont else None, torch.float32, 'prev_action (continuous)'),
+                      _ptr(normal if cont else None, torch.float32, 'normal'),
+                      _ptr(forced_action if cont else None, torch.float32, 'forced_action (continuous)'),
+                      _ptr(out['action'] if cont else None))
         L.check(self.lib.xtrl_wm_step(C.byref(self.desc), _ptr(self.weights), _ptr(self.kv_cache), C.byref(io), B,
                                       _stream()), 'xtrl_wm_step')
         if advance and pos_uniform is None:
