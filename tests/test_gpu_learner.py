@@ -26,12 +26,14 @@ class Sim:                                # README.md:16-21 / reference tests :1
 
 
 @pytest.mark.parametrize('evolutionary', (False, True))
-def test_e2e_reference_smoke(evolutionary, tmp_path):
-    """the reference's own (only) test, discrete half: construct, learn one update, act twice."""
+@pytest.mark.parametrize('continuous_actions', (False, True))
+def test_e2e_reference_smoke(evolutionary, continuous_actions, tmp_path):
+    """the reference's own (only) test, all four parameter combinations (tests/test_x_transformers_rl.py:4-53):
+    construct, learn one update, act twice."""
     Learner = _learner_cls()
     learner = Learner(
         state_dim=5, num_actions=2, reward_range=(-1., 1.), max_timesteps=10, batch_size=2, num_episodes_per_update=2,
-        evolutionary=evolutionary,
+        evolutionary=evolutionary, continuous_actions=continuous_actions,
         latent_gene_pool=dict(dim=32, num_genes_per_island=3, num_selected=2, tournament_size=2),
         world_model=dict(attn_dim_head=16, heads=4, depth=1),
         agent_kwargs=dict(save_path=str(tmp_path / 'ppo.pt')))
@@ -39,7 +41,7 @@ def test_e2e_reference_smoke(evolutionary, tmp_path):
     hiddens = None
     actions, hiddens = learner.agent(np.random.randn(5), hiddens=hiddens)
     actions, hiddens = learner.agent(np.random.randn(5), hiddens=hiddens)
-    assert actions.shape == (2,) and torch.isfinite(actions).all()
+    assert actions.shape == ((4,) if continuous_actions else (2,)) and torch.isfinite(actions).all()
     assert os.path.exists(tmp_path / 'ppo.pt')
     assert learner.timings['env_steps'] == 2 * 10 * (3 if evolutionary else 1)
     assert learner.accelerator.is_main_process and len(learner.episode_genes_for_process) == (6 if evolutionary else 2)
@@ -47,10 +49,18 @@ def test_e2e_reference_smoke(evolutionary, tmp_path):
     assert 'transformer.attn_layers.layers.0.1.to_q.weight' in sd and 'critic_head.2.bias' in sd
 
 
-def test_continuous_actions_raise_not_fallback(tmp_path):
-    with pytest.raises(NotImplementedError):
-        _learner_cls()(state_dim=5, num_actions=2, reward_range=(-1., 1.), continuous_actions=True,
-                       world_model=dict(attn_dim_head=16, heads=4, depth=1), agent_kwargs=dict(save_path=str(tmp_path / 'p.pt')))
+def test_continuous_vectorized_rollout_and_clamp(tmp_path):
+    """continuous actions through the vectorised rollout: tanh-squashed samples, environment clamp (:1291-1295)."""
+    from importlib import import_module
+    envs = import_module('x-transformers-rl_b200.envs')
+    learner = _make(tmp_path, 8, 12, num_episodes_per_update=32, continuous_actions=True, continuous_actions_clamp=(-0.5, 0.5))
+    env = envs.SyntheticVecEnv(32, 8, 12, device=learner.device, seed=2)
+    learner(env, 2, seed=0)
+    gids = torch.zeros(32, dtype=torch.int32, device=learner.device)
+    buf, _ = learner.rollout_vectorized(env, gids, 12)
+    assert buf.actions.shape == (12, 32, 4) and buf.log_probs.shape == (12, 32, 4)
+    assert buf.actions.abs().max() <= 0.5 and torch.isfinite(buf.log_probs).all()
+    assert torch.isfinite(learner.agent.model.flat_params).all()
 
 
 LANDER_WM = dict(attn_dim_head=16, heads=4, depth=2, attn_gate_values=True, add_value_residual=True,
@@ -105,8 +115,8 @@ def test_vectorized_rollout_matches_oracle(tmp_path):
     assert rel_err(cum.cpu(), rewards.sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize('evolutionary', (False, True))
-def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary):
+@pytest.mark.parametrize('evolutionary,continuous', ((False, False), (True, False), (False, True)))
+def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary, continuous):
     """one minibatch of Agent.learn (dropout 0): GAE kernel + torch sequence model + fused loss kernel +
     autograd  ==  the oracle's learn_minibatch differentiated by autograd, gradient for gradient."""
     from importlib import import_module
@@ -115,6 +125,8 @@ def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary):
     torch.manual_seed(1)
     kw = dict(evolutionary=True, latent_gene_pool=dict(dim=32, num_genes_per_island=3, num_selected=2, tournament_size=2),
               num_episodes_per_update=2, batch_size=2) if evolutionary else {}
+    if continuous:
+        kw['continuous_actions'] = True
     learner = _make(tmp_path, B, T, **kw)
     agent, dev = learner.agent, learner.device
     agent.batch_size = B
@@ -122,11 +134,12 @@ def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary):
         agent.model.flat_params.add_(torch.randn_like(agent.model.flat_params) * 0.1)
         agent.rsnorm.running_mean.normal_(); agent.rsnorm.running_variance.uniform_(0.5, 2.)
     g = torch.Generator().manual_seed(5)
-    buf = agent_mod.RolloutBuffer.allocate(T, B, 8, dev)
+    buf = agent_mod.RolloutBuffer.allocate(T, B, 8, dev, continuous_dim=4 if continuous else 0)
     lens = torch.tensor([T, T - 3, 5, T, 2, T - 1], dtype=torch.int32)
     tm_mask = (torch.arange(T)[:, None] < lens[None, :])
-    data = dict(states=torch.randn(T, B, 8, generator=g), actions=torch.randint(0, 4, (T, B), generator=g).int(),
-                log_probs=-torch.rand(T, B, generator=g) * 1.5, rewards=torch.randn(T, B, generator=g),
+    acts = torch.tanh(torch.randn(T, B, 4, generator=g)) * 0.9 if continuous else torch.randint(0, 4, (T, B), generator=g).int()
+    data = dict(states=torch.randn(T, B, 8, generator=g), actions=acts,
+                log_probs=-torch.rand(*((T, B, 4) if continuous else (T, B)), generator=g) * 1.5, rewards=torch.randn(T, B, generator=g),
                 values=torch.randn(T, B, generator=g), is_boundary=torch.rand(T, B, generator=g) < 0.05)
     for k, v in data.items():              # padding rows hold pad_sequence zeros, like the reference
         v = torch.where(tm_mask if v.ndim == 2 else tm_mask[..., None], v, torch.zeros_like(v))
@@ -144,10 +157,10 @@ def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary):
     # oracle
     wm = dict(LANDER_WM)
     cfg = oracle_config(dict(state_dim=8, num_actions=4, reward_range=(-5., 5.), world_model=wm, evolutionary=evolutionary,
-                             latent_gene_pool=dict(dim=32)))
+                             latent_gene_pool=dict(dim=32), continuous_actions=continuous))
     em = lambda t: t.transpose(0, 1).contiguous()
     returns = R.calc_gae(em(data['rewards']), em(data['values']), ~em(data['is_boundary']))
-    batch = dict(states=em(data['states']), actions=em(data['actions']).long(), rewards=em(data['rewards']),
+    batch = dict(states=em(data['states']), actions=em(data['actions']) if continuous else em(data['actions']).long(), rewards=em(data['rewards']),
                  old_log_probs=em(data['log_probs']), returns=returns, old_values=em(data['values']),
                  dones=em(data['is_boundary']), gene_ids=gene_ids.long(), episode_lens=lens.long())
     loss, logs, packed_masked = R.learn_minibatch(sd, cfg, batch, mean, var, reward_flag=1., genes=genes)

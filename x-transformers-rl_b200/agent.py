@@ -39,10 +39,12 @@ class RolloutBuffer:
     gene_ids: torch.Tensor
 
     @classmethod
-    def allocate(cls, T, B, S, device):
+    def allocate(cls, T, B, S, device, continuous_dim=0):
+        """continuous_dim = A for continuous actions: actions (T,B,A) f32 and per-dim log_probs (T,B,A)."""
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=device, dtype=dt)
-        return cls(z(T, B, S), z(T, B, dt=torch.int32), z(T, B), z(T, B), z(T, B, dt=torch.bool), z(T, B),
-                   z(B, dt=torch.int32), z(B, dt=torch.int32))
+        acts = z(T, B, continuous_dim) if continuous_dim else z(T, B, dt=torch.int32)
+        logp = z(T, B, continuous_dim) if continuous_dim else z(T, B)
+        return cls(z(T, B, S), acts, logp, z(T, B), z(T, B, dt=torch.bool), z(T, B), z(B, dt=torch.int32), z(B, dt=torch.int32))
 
     @classmethod
     def cat(cls, bufs):
@@ -99,9 +101,6 @@ class Agent(nn.Module):
                  actor_loss_weight=1., critic_loss_weight=1., autoregressive_loss_weight=1.,
                  rollout_positions='reference', kv_cache_dtype='fp32', rollout_dense_dtype='fp32'):
         super().__init__()
-        if continuous_actions:
-            raise NotImplementedError('continuous actions are outside the B200 hot path built so far (SURVEY 8f row 4); '
-                                      'there is no fallback')
         latent_gene_pool = latent_gene_pool if latent_gene_pool is not None else dict(
             dim=128, num_genes_per_island=3, num_selected=2, tournament_size=2)
         world_model = world_model if world_model is not None else dict(
@@ -120,13 +119,15 @@ class Agent(nn.Module):
             state_dim, num_actions, reward_range, max_timesteps, world_model, hidden_dim=hidden_dim,
             num_bins=critic_pred_num_bins, dim_gene=self.gene_pool.dim_gene if evolutionary else 0,
             rotary_true_pos=(rollout_positions == 'true'), kv_bf16=(kv_cache_dtype == 'bf16'),
-            dense_bf16=(rollout_dense_dtype == 'bf16'))
+            dense_bf16=(rollout_dense_dtype == 'bf16'), continuous=bool(continuous_actions),
+            squash=bool(squash_continuous))
         self.model = WorldModelActorCritic(self.cfg, dropout=dropout,
                                            frac_actor_critic_head_gradient=frac_actor_critic_head_gradient)
         self.loss_cfg = ops.LossConfig(num_actions=num_actions, num_bins=critic_pred_num_bins, state_dim=state_dim,
                                        reward_range=tuple(reward_range), eps_clip=eps_clip, value_clip=value_clip,
                                        entropy_weight=beta_s, actor_weight=actor_loss_weight,
-                                       critic_weight=critic_loss_weight, autoreg_weight=autoregressive_loss_weight)
+                                       critic_weight=critic_loss_weight, autoreg_weight=autoregressive_loss_weight,
+                                       continuous=bool(continuous_actions), squash=bool(squash_continuous))
         self.rsnorm = RSNorm(state_dim + 1)
         self.continuous_actions = continuous_actions
         self.max_grad_norm = max_grad_norm
@@ -188,7 +189,8 @@ class Agent(nn.Module):
         states, actions, logp, rewards, bd, values = (pad(i) for i in range(6))
         if values.ndim == 3:
             values = ops.hl_decode(values.float().contiguous(), self.cfg.reward_range)       # :843
-        return dict(states=states.float(), actions=actions.int(), old_log_probs=logp.float(), rewards=rewards.float(),
+        return dict(states=states.float(), actions=actions.float() if self.continuous_actions else actions.int(),
+                    old_log_probs=logp.float(), rewards=rewards.float(),
                     dones=bd.bool(), old_values=values.float(), lens=episode_lens.to(dev).int(),
                     gene_ids=gene_ids.to(dev).int(), time_major=False)
 
@@ -209,7 +211,7 @@ class Agent(nn.Module):
             data.pop('time_major')
             data['returns'] = ops.gae(data['rewards'].contiguous(), data['old_values'].contiguous(),
                                       data['dones'].contiguous(), self.gamma, self.lam)
-        E, T = data['actions'].shape
+        E, T = data['actions'].shape[:2]
         S = cfg.state_dim
         n = model.flat_params.numel()
         rs_copy = RSNorm(S + 1).to(dev)
@@ -226,13 +228,17 @@ class Agent(nn.Module):
                 states, actions, rewards = data['states'][idx], data['actions'][idx], data['rewards'][idx]
                 lens = data['lens'][idx].contiguous()
                 mask = arange_t[None, :] < lens[:, None]                                              # :908-909
-                prev_actions = F.pad(actions, (1, -1), value=-1)                                     # :911-916
+                if self.continuous_actions:                                                          # :911-916
+                    prev_actions = F.pad(actions, (0, 0, 1, -1), value=0.)
+                else:
+                    prev_actions = F.pad(actions, (1, -1), value=-1)
                 prev_rewards = F.pad(rewards, (1, -1), value=0.)                                     # :918
                 packed = self.rsnorm.normalize(torch.cat((states, prev_rewards[..., None]), dim=-1))  # :920-926
                 gene = self.gene_pool[data['gene_ids'][idx].long()] if self.evolutionary else None   # :906
                 flag = float(torch.rand(()) >= 0.5) if model.training else 1.                        # reward dropout :501
                 with autocast:
-                    ra, vl, spr, dl = model(packed[..., :S], packed[..., S], prev_actions.long(), actions.long(), mask,
+                    cast = (lambda t: t) if self.continuous_actions else (lambda t: t.long())
+                    ra, vl, spr, dl = model(packed[..., :S], packed[..., S], cast(prev_actions), cast(actions), mask,
                                             latent_gene=gene, reward_flag=flag)
                 loss, scalars = FusedPPOLoss.apply(self.loss_cfg, ra, vl, spr, dl, actions.contiguous(),
                                                    data['old_log_probs'][idx].contiguous(), data['returns'][idx].contiguous(),
@@ -281,7 +287,8 @@ class Agent(nn.Module):
         state = torch.as_tensor(state, dtype=torch.float32).to(dev).reshape(1, cfg.state_dim).contiguous()
         has_reward = reward is not None
         prev_r = torch.as_tensor(float(reward) if has_reward else 0., dtype=torch.float32, device=dev).reshape(1)
-        out = st.step(state, torch.full((1,), -1, dtype=torch.int32, device=dev), prev_r, self.rsnorm.running_mean,
+        no_action = None if self.continuous_actions else torch.full((1,), -1, dtype=torch.int32, device=dev)
+        out = st.step(state, no_action, prev_r, self.rsnorm.running_mean,
                       self.rsnorm.running_variance, genes=self.gene_pool.genes.data if self.evolutionary else None,
                       gene_ids=torch.full((1,), int(latent_gene_id), dtype=torch.int32, device=dev) if self.evolutionary else None,
                       reward_flag=1. if has_reward else 0., want_logits=True)

@@ -434,7 +434,9 @@ wm_step_kernel(const StepArgs a) {
         if (n < D) {
             float v = acc;
             if (env < a.B) {
-                if (d.cont) {                                                            // nn.Linear(A, D) on the previous action (:309)
+                if (d.cont && a.io.prev_action_f == nullptr) {
+                    // deploy call without a previous action (:1056-1061): no action embedding at all
+                } else if (d.cont) {                                                     // nn.Linear(A, D) on the previous action (:309)
                     v += __ldg(W + a.w.action_embed_bias + n);
                     for (int i = 0; i < d.A; ++i)
                         v = fmaf(__ldg(a.io.prev_action_f + (int64_t)env * d.A + i), __ldg(W + a.w.action_embed + (int64_t)i * D + n), v);
@@ -794,8 +796,7 @@ extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, v
     if (num_envs == 0) return XTRL_OK;                      // nothing to do (and the caller's buffers may be empty)
     XTRL_REQUIRE(io && weights && kv_cache, XTRL_E_BADARG, "xtrl_wm_step: null pointer");
     XTRL_REQUIRE(io->state && io->prev_reward && io->rs_mean && io->rs_var, XTRL_E_BADARG, "xtrl_wm_step: null required input");
-    XTRL_REQUIRE(desc->continuous_actions ? io->prev_action_f != nullptr : io->prev_action != nullptr, XTRL_E_BADARG,
-                 "xtrl_wm_step: previous actions missing (%s)", desc->continuous_actions ? "prev_action_f" : "prev_action");
+    XTRL_REQUIRE(desc->continuous_actions || io->prev_action != nullptr, XTRL_E_BADARG, "xtrl_wm_step: prev_action missing");
     XTRL_REQUIRE(io->pos || (io->pos_uniform >= 0 && io->pos_uniform < desc->max_timesteps), XTRL_E_BADARG,
                  "xtrl_wm_step: pos_uniform=%d outside [0, max_timesteps=%d)", io->pos_uniform, desc->max_timesteps);
     XTRL_REQUIRE(desc->dim_gene == 0 || (io->genes && io->gene_ids), XTRL_E_BADARG,

@@ -90,18 +90,24 @@ class Learner(nn.Module):
         (T,B) in [0,1) -- drawn here from torch's CUDA generator unless given (parity tests)."""
         agent, dev, cfg = self.agent, self.device, self.agent.cfg
         B, T, S = env.num_envs, max_timesteps, cfg.state_dim
-        if (self.rollout_groups > 1 and hasattr(env, 'split') and getattr(env, 'never_terminates', False)
+        cont = cfg.continuous
+        if (not cont and self.rollout_groups > 1 and hasattr(env, 'split') and getattr(env, 'never_terminates', False)
                 and B % self.rollout_groups == 0 and B // self.rollout_groups >= 256):
             return self._rollout_pipelined(env, gene_ids, max_timesteps, seed, uniforms)
-        if (self.use_cuda_graph and allow_graph and uniforms is None and getattr(env, 'cuda_graph_safe', False)
+        if (not cont and self.use_cuda_graph and allow_graph and uniforms is None and getattr(env, 'cuda_graph_safe', False)
                 and getattr(env, 'never_terminates', False)):
             return self._rollout_graphed(env, gene_ids, max_timesteps, seed)
         st = self._stepper(B, max_timesteps)
         st.load_state_dict(agent.ema_state_dict())               # rollouts read the EMA weights (:1194)
-        buf = RolloutBuffer.allocate(T, B, S, dev)
+        A = cfg.num_actions
+        buf = RolloutBuffer.allocate(T, B, S, dev, continuous_dim=A if cont else 0)
         buf.gene_ids.copy_(gene_ids)
-        u = torch.rand(T, B, device=dev) if uniforms is None else uniforms
-        first_a = torch.full((B,), -1, dtype=torch.int32, device=dev)     # :1244
+        # the random inputs of the sampler: uniforms (inverse CDF) or, for continuous actions, standard normals
+        if uniforms is not None:
+            u = uniforms
+        else:
+            u = torch.randn(T, B, A, device=dev) if cont else torch.rand(T, B, device=dev)
+        first_a = torch.zeros(B, A, device=dev) if cont else torch.full((B,), -1, dtype=torch.int32, device=dev)   # :1241-1244
         first_r = torch.zeros(B, device=dev)                              # :1246
         pin_s = pin_r = None
         state = env.reset(**({} if seed is None else dict(seed=seed)))
@@ -120,9 +126,11 @@ class Learner(nn.Module):
             buf.states[t].copy_(_to_device_state(state, dev, pin_s), non_blocking=True)
             out = dict(action=buf.actions[t], log_prob=buf.log_probs[t], value=buf.values[t])
             st.step(buf.states[t], first_a if t == 0 else buf.actions[t - 1], first_r if t == 0 else buf.rewards[t - 1],
-                    rs_mean, rs_var, uniform=u[t], genes=genes, gene_ids=buf.gene_ids if genes is not None else None,
-                    out=out, pos_uniform=t)
+                    rs_mean, rs_var, uniform=None if cont else u[t], normal=u[t] if cont else None, genes=genes,
+                    gene_ids=buf.gene_ids if genes is not None else None, out=out, pos_uniform=t)
             action = buf.actions[t]
+            if cont and self.continuous_actions_clamp is not None:      # environment clamping (:1291-1295)
+                action.clamp_(*self.continuous_actions_clamp)
             step_out = env.step(action if pin_s is None else action.cpu().numpy())     # host env: D2H sync
             if len(step_out) >= 4:
                 state, reward, terminated, truncated = step_out[:4]
@@ -142,8 +150,9 @@ class Learner(nn.Module):
                 buf.is_boundary[t] = term & alive
                 # finished envs keep stepping (lock step) but their rows become pad_sequence padding (:837)
                 dead = ~alive
-                buf.states[t].masked_fill_(dead[:, None], 0.); buf.actions[t].masked_fill_(dead, 0)
-                buf.log_probs[t].masked_fill_(dead, 0.); buf.rewards[t].masked_fill_(dead, 0.)
+                dead_a = dead[:, None] if cont else dead
+                buf.states[t].masked_fill_(dead[:, None], 0.); buf.actions[t].masked_fill_(dead_a, 0)
+                buf.log_probs[t].masked_fill_(dead_a, 0.); buf.rewards[t].masked_fill_(dead, 0.)
                 buf.values[t].masked_fill_(dead, pad_value)
                 lens += alive.int()
                 alive = alive & ~done
@@ -268,15 +277,19 @@ class Learner(nn.Module):
         state = reset_out[0] if isinstance(reset_out, tuple) else reset_out
         genes = agent.gene_pool.genes.data if agent.evolutionary else None
         gid = torch.full((1,), int(gene_id), dtype=torch.int32, device=dev)
-        prev_a = torch.full((1,), -1, dtype=torch.int32, device=dev)
+        cont, A = cfg.continuous, cfg.num_actions
+        prev_a = torch.zeros(1, A, device=dev) if cont else torch.full((1,), -1, dtype=torch.int32, device=dev)
         prev_r = torch.zeros(1, device=dev)
         memories, cumulative = [], 0.
         for timestep in range(max_timesteps):
             s = torch.as_tensor(np.asarray(state, dtype=np.float32) if not torch.is_tensor(state) else state,
                                 dtype=torch.float32).to(dev).reshape(1, cfg.state_dim).contiguous()
             out = st.step(s, prev_a, prev_r, agent.rsnorm.running_mean, agent.rsnorm.running_variance,
-                          uniform=torch.rand(1, device=dev), genes=genes, gene_ids=gid if genes is not None else None)
+                          uniform=None if cont else torch.rand(1, device=dev), normal=torch.randn(1, A, device=dev) if cont else None,
+                          genes=genes, gene_ids=gid if genes is not None else None)
             action = out['action'].clone()
+            if cont and self.continuous_actions_clamp is not None:
+                action.clamp_(*self.continuous_actions_clamp)
             step_out = env.step(action.tolist()[0])
             if len(step_out) >= 4:
                 state, reward, terminated, truncated = step_out[:4]

@@ -106,7 +106,7 @@ class WorldModelActorCritic(nn.Module):
         D, S, A, K = cfg.dim, cfg.state_dim, cfg.num_actions, cfg.num_bins
         self.transformer = _Wrapper(cfg)
         self.reward_embed = nn.Parameter(torch.ones(D) * 1e-2)
-        self.action_embeds = _SafeEmbedding(A, D)
+        self.action_embeds = nn.Linear(A, D) if cfg.continuous else _SafeEmbedding(A, D)      # :306-309
         self.to_state_embed = nn.Linear(S, D)
         self.to_pred_done = nn.Sequential(nn.Linear(2 * D, 1))
         self.to_pred = nn.Sequential(nn.Linear(2 * D, D), nn.SiLU(), nn.Linear(D, 2 * (S + 1)))
@@ -115,7 +115,7 @@ class WorldModelActorCritic(nn.Module):
             self.latent_to_embed = nn.Linear(cfg.dim_gene, D)
         hin = (3 if self.evolutionary else 2) * D
         self.critic_head = nn.Sequential(nn.Linear(hin, 2 * D), nn.SiLU(), nn.Linear(2 * D, K))
-        self.action_head = nn.Sequential(nn.Linear(hin, 2 * D), nn.SiLU(), nn.Linear(2 * D, A))
+        self.action_head = nn.Sequential(nn.Linear(hin, 2 * D), nn.SiLU(), nn.Linear(2 * D, 2 * A if cfg.continuous else A))
         self._flatten()
 
     # -- one flat fp32 buffer behind every parameter ------------------------------------------
@@ -154,8 +154,9 @@ class WorldModelActorCritic(nn.Module):
     # -- full-sequence forward (x_transformers_rl.py:479-559 with mask=, :928-935) ---------------
     def forward(self, state, rewards, actions, next_actions, mask, latent_gene=None, reward_flag=1.):
         """state (b,n,S) normalised; rewards (b,n) normalised prev rewards; actions (b,n) prev actions
-        (-1 none); next_actions (b,n); mask (b,n) bool.  Returns raw head outputs:
-        raw_actions (b,n,A), value_logits (b,n,K), state_pred_raw (b,n,2(S+1)), done_logit (b,n)."""
+        (-1 none; continuous: float (b,n,A), zeros for none); next_actions likewise; mask (b,n) bool.
+        Returns raw head outputs: raw_actions (b,n,A | 2A), value_logits (b,n,K), state_pred_raw (b,n,2(S+1)),
+        done_logit (b,n)."""
         cfg, tfm = self.cfg, self.transformer
         dec = tfm.attn_layers
         b, n, _ = state.shape
