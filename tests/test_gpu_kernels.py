@@ -328,9 +328,12 @@ def test_wm_step_tensor_core_dense(kw, kv_bf16):
         gene_n = torch.nn.functional.normalize(genes[gene_ids], dim=-1)
     ra, va, val = _rollout_kernel(sd, cfg, states, prev_a, prev_r, genes=genes, gene_ids=gene_ids, dense_bf16=True, kv_bf16=kv_bf16)
     want_ra, want_va = _rollout_oracle(sd, cfg, states, prev_a, prev_r, gene_n)
+    # measured on B200 (scripts/tc_error_probe.py): logits 0.7-1.4 % of their max, decoded value <= 0.9 % of the
+    # reward range -- the bf16-operand class; the fp32 path is the 1e-5 class
     assert rel_err(ra, want_ra) < 2e-2
     assert rel_err(va, want_va) < 2e-2
-    assert rel_err(val, R.hl_decode(want_va, cfg)) < 2e-2
+    lo, hi = cfg.reward_range
+    assert ((val - R.hl_decode(want_va, cfg)).abs().max() / (hi - lo)).item() < 1.5e-2
     # and it is NOT the fp32 path in disguise: bf16 rounding must be visible
     assert rel_err(ra, want_ra) > 1e-5
 
@@ -380,9 +383,9 @@ def test_wm_step_full_size_c3():
     assert torch.equal(again['ra'], fp32['ra']) and torch.equal(again['val'], fp32['val'])
     # (b) precision classes at t = 499
     tc = run(dense_bf16=True)
-    assert rel_err(tc['ra'], fp32['ra']) < 2e-2 and rel_err(tc['val'], fp32['val']) < 2e-2
+    assert rel_err(tc['ra'], fp32['ra']) < 2e-2 and ((tc['val'] - fp32['val']).abs().max() / 10.).item() < 1.5e-2
     lo = run(dense_bf16=True, kv_bf16=True)
-    assert rel_err(lo['ra'], fp32['ra']) < 3e-2 and rel_err(lo['val'], fp32['val']) < 3e-2
+    assert rel_err(lo['ra'], fp32['ra']) < 3e-2 and ((lo['val'] - fp32['val']).abs().max() / 10.).item() < 1.5e-2
     assert torch.isfinite(fp32['vl']).all() and torch.isfinite(lo['lp']).all()
 
 
