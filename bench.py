@@ -33,6 +33,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION) out of it
+if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+    os.environ['NCCL_DEBUG'] = 'WARN'
 
 WORKLOADS = {
     'c1': dict(S=5, A=2, T=10, envs=64, reward_range=(-1., 1.), world_model=dict(attn_dim_head=16, heads=4, depth=1),
