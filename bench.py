@@ -45,6 +45,12 @@ WORKLOADS = {
                                 learned_value_residual_mix=True), genes=3, gene_dim=32, learn_batch=8),
     'c3': dict(S=8, A=4, T=500, envs=4096, reward_range=(-5., 5.), world_model=dict(attn_dim_head=16, heads=8, depth=4),
                genes=0, learn_batch=256),
+    # c4: evolutionary policy optimisation, 64 genes (1 island x 64, 16 selected, tournaments of 4), gene dim 128;
+    # 64 episodes x 64 genes = 4096 (episode, gene) pairs per GPU; fitness partials are all-gathered across ranks
+    'c4': dict(S=8, A=4, T=500, envs=4096, reward_range=(-5., 5.),
+               world_model=dict(attn_dim_head=16, heads=4, depth=4, attn_gate_values=True, add_value_residual=True,
+                                learned_value_residual_mix=True), genes=64, gene_dim=128, learn_batch=64,
+               pool=dict(num_selected=16, tournament_size=4)),
     'c5': dict(S=8, A=4, T=500, envs=4096, reward_range=(-5., 5.), world_model=dict(attn_dim_head=16, heads=8, depth=6),
                genes=0, learn_batch=256),
 }
@@ -132,6 +138,37 @@ def cpu_rollout_port(w, episodes, max_seconds=None, threads=None):
     return steps, time.perf_counter() - t0, threads
 
 
+def cpu_learn_port(w, episodes=8, threads=None, max_seconds=20.):
+    """the reference's learn minibatch (x_transformers_rl.py:903-992) restated on CPU torch: teacher-forced forward,
+    the four losses, autograd backward -- on `episodes` synthetic episodes of T steps.  Returns timesteps/s."""
+    import torch
+    from oracle import restated as R
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from helpers import random_state_dict, oracle_config
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = oracle_config(dict(state_dim=w['S'], num_actions=w['A'], reward_range=w['reward_range'], world_model=w['world_model'],
+                             evolutionary=w['genes'] > 0, latent_gene_pool=dict(dim=w.get('gene_dim', 0))))
+    sd = {k: v.requires_grad_() for k, v in random_state_dict(cfg, seed=0).items()}
+    g = torch.Generator().manual_seed(0)
+    b, T, S, A = episodes, w['T'], w['S'], w['A']
+    batch = dict(states=torch.randn(b, T, S, generator=g), actions=torch.randint(0, A, (b, T), generator=g),
+                 rewards=torch.randn(b, T, generator=g), old_log_probs=-torch.rand(b, T, generator=g), returns=torch.randn(b, T, generator=g),
+                 old_values=torch.randn(b, T, generator=g), dones=torch.zeros(b, T, dtype=torch.bool), gene_ids=torch.zeros(b, dtype=torch.long),
+                 episode_lens=torch.full((b,), T))
+    genes = torch.randn(max(w['genes'], 1), cfg.dim_gene) if cfg.evolutionary else None
+    mean, var = torch.zeros(S + 1), torch.ones(S + 1)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        loss, _, _ = R.learn_minibatch(sd, cfg, batch, mean, var, genes=genes)
+        loss.backward()
+        n += 1
+        if time.perf_counter() - t0 > max_seconds or n >= 8:
+            break
+    secs = time.perf_counter() - t0
+    return n * b * T / secs, n, secs, threads
+
+
 def run_reference(args, w):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -192,7 +229,8 @@ def run_b200(args, w):
                   agent_kwargs=dict(save_path=os.path.join(tempfile.gettempdir(), f'xtrl_bench_{os.getpid()}.pt'),
                                     kv_cache_dtype=kv, rollout_dense_dtype=dense))
         if evolutionary:
-            kw['latent_gene_pool'] = dict(dim=w['gene_dim'], num_genes_per_island=w['genes'], num_selected=2, tournament_size=2)
+            kw['latent_gene_pool'] = dict(dim=w['gene_dim'], num_genes_per_island=w['genes'],
+                                          **w.get('pool', dict(num_selected=2, tournament_size=2)))
         if args.learn_dtype == 'bf16':
             kw['accelerate_kwargs'] = dict(mixed_precision='bf16')
         return learner_mod.Learner(**kw)
@@ -309,6 +347,20 @@ def run_b200(args, w):
                                note='sequence model fwd/bwd = torch ops (SURVEY 8f-1 next); GAE, fused loss fwd+bwd, '
                                     'optimiser+EMA = libxtrl kernels; one flat-gradient all-reduce per optimiser step')
 
+    # ---- gene pool (evolutionary workloads): evolve_ launch + the cross-rank fitness gather ----------------------
+    if evolutionary:
+        dist_mod = importlib.import_module('x-transformers-rl_b200.distributed')
+        pool = agent.gene_pool
+        fit = torch.randn(pool.num_genes, device=dev)
+        for _ in range(3):
+            pool.evolve_(fit)
+        ems_, _ = timed(lambda: [pool.evolve_(fit) for _ in range(20)], 1)
+        gms_, _ = timed(lambda: [dist_mod.reduce_fitness(fit) for _ in range(20)], 1)
+        result['evolve'] = dict(genes=pool.num_genes, dim=pool.dim_gene, ms_per_evolve=ems_ / 20,
+                                ms_per_fitness_gather=gms_ / 20, ranks=world,
+                                note='evolve_ = 3 torch.randn draws (reference order) + ONE xtrl_evolve launch; fitness = all-gather of '
+                                     'per-rank partial sums, added in rank order (bit-identical on every rank)')
+
     # ---- e2e: the same rollout through the public API with a HOST-memory env -------------------------
     if not args.no_e2e:
         henv = envs_mod.HostVecEnv(B, S, T, seed=rank)
@@ -320,6 +372,10 @@ def run_b200(args, w):
 
     # ---- cpu baseline beside it (rank 0, N=1 only) ---------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
+        if 'learn' in result:
+            lv, n, lsecs, lthreads = cpu_learn_port(w)
+            result['learn']['cpu_baseline'] = dict(value=lv, unit='timesteps/s', cores=lthreads, kind='port',
+                                                   sample=f'{n} minibatch(es) of 8 episodes x {T} steps, fwd + losses + backward in {lsecs:.1f}s, oracle/restated.py')
         steps, secs, threads = cpu_rollout_port(w, episodes=10 ** 6, max_seconds=args.cpu_seconds)
         result['cpu_baseline'] = dict(value=steps / secs, unit='env-steps/s', cores=threads, kind='port',
                                       sample=f'{steps} env-steps of batch-1 episodes (T={T}) in {secs:.1f}s, oracle/restated.py')
