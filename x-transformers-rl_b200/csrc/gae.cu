@@ -71,8 +71,8 @@ gae_episode_major_kernel(const float *__restrict__ rewards, const float *__restr
     }
 }
 
-constexpr int kGaeChunks = 16;          // time-major: warps (time chunks) per CTA
-constexpr int kGaeRegChunk = 32;        // chunk length held in registers (T <= 512)
+constexpr int kGaeChunks = 32;          // time-major: warps (time chunks) per CTA
+constexpr int kGaeRegChunk = 16;        // chunk length held in registers (T <= 512)
 
 // REG: the thread's whole chunk (<= 32 timesteps) is loaded into registers up front -- all 3*C loads of
 // a thread are in flight together, inputs cross the memory system exactly once -- then folded, carried
