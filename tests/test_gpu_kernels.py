@@ -311,6 +311,7 @@ def test_wm_step_sampling_and_rsnorm():
     dict(heads=4, depth=4, state_dim=8, num_actions=4, gate_values=True, value_residual=True,
          learned_mix=True, evolutionary=True, dim_gene=32),                                  # c2: NQ=260 -> 3 tiles, HIN=144
     dict(heads=8, depth=2, state_dim=8, num_actions=4, gate_values=True, value_residual=True, learned_mix=True),  # NQ=520: 5 tiles, 2 weight groups
+    dict(heads=6, depth=2, state_dim=5, num_actions=3, dim=32, gate_values=True),              # hidden_dim 32: K=32, tile groups capped by TMEM
 ])
 @pytest.mark.parametrize('kv_bf16', (False, True))
 def test_wm_step_tensor_core_dense(kw, kv_bf16):

@@ -400,7 +400,7 @@ wm_step_kernel(const StepArgs a) {
         __syncthreads();
         umma::tc_fence_after();
         tbase = *tslot;
-        const int g0 = min(a.tc.tiles_q, kWbufBytes / (128 * D * 2));
+        const int g0 = min(a.tc.tiles_q, min(kWbufBytes / (128 * D * 2), (int)kTmemCols / kTE));
         tc_load(a.tc.qkv[0], (uint32_t)g0 * 128 * D * 2);               // layer 0 QKV weights fly during the prologue
     }
 
@@ -468,7 +468,8 @@ wm_step_kernel(const StepArgs a) {
 
     for (int l = 0; l < d.L; ++l) {
         const auto &wl = a.w.layer[l];
-        const int wgroup = kWbufBytes / (128 * D * 2);                   // 128-row tiles of a K = D GEMM per weight stage
+        // 128-row tiles of a K = D GEMM per pass: what fits the weight stage AND the TMEM columns (16 per tile)
+        const int wgroup = min(kWbufBytes / (128 * D * 2), (int)kTmemCols / kTE);
         auto qkv_epi = [&](int e, int n, float acc) {
             if (n < NQ) {
                 float v = acc + __ldg(W + wl.qkv_b + n);
