@@ -88,8 +88,8 @@ class RSNorm(nn.Module):
 class Hiddens:
     """opaque recurrent state returned by Agent.forward (the KV cache of one env)."""
 
-    def __init__(self, stepper):
-        self.stepper = stepper
+    def __init__(self, stepper, weights_version):
+        self.stepper, self.weights_version = stepper, weights_version
 
 
 class Agent(nn.Module):
@@ -282,8 +282,11 @@ class Agent(nn.Module):
         if hiddens is None:
             st = ops.WorldModelStepper(cfg, 1, dev)
             st.load_state_dict(self.model.state_dict())
-            hiddens = Hiddens(st)
+            hiddens = Hiddens(st, self.opt_steps)
         st = hiddens.stepper
+        if hiddens.weights_version != self.opt_steps:          # the online weights moved on since this cache was created
+            st.load_state_dict(self.model.state_dict())
+            hiddens.weights_version = self.opt_steps
         state = torch.as_tensor(state, dtype=torch.float32).to(dev).reshape(1, cfg.state_dim).contiguous()
         has_reward = reward is not None
         prev_r = torch.as_tensor(float(reward) if has_reward else 0., dtype=torch.float32, device=dev).reshape(1)

@@ -11,6 +11,8 @@ keeps the reference's one-episode-at-a-time semantics through the same kernel wi
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 from torch import nn
@@ -174,7 +176,7 @@ class Learner(nn.Module):
         st.load_state_dict(agent.ema_state_dict())               # in place: the captured pointers stay valid
         state0 = env.reset(**({} if seed is None else dict(seed=seed)))
         ent = self._graphs.get(key)
-        if ent is None or ent['st'] is not st:
+        if ent is None or ent['st'] is not st or ent['env']() is not env:       # id() can be recycled: check identity
             buf = RolloutBuffer.allocate(T, B, S, dev)
             buf.episode_lens.fill_(T)
             u = torch.empty(T, B, device=dev)
@@ -205,7 +207,7 @@ class Learner(nn.Module):
             with torch.cuda.graph(graph):
                 body()
             # every tensor whose address the graph baked in must outlive the graph
-            ent = self._graphs[key] = dict(graph=graph, buf=buf, u=u, st=st, keep=(first_a, first_r, genes, rs_mean, rs_var, state0))
+            ent = self._graphs[key] = dict(graph=graph, buf=buf, u=u, st=st, env=weakref.ref(env), keep=(first_a, first_r, genes, rs_mean, rs_var, state0))
             if len(self._graphs) > 2:
                 self._graphs.pop(next(iter(self._graphs)))
         buf = ent['buf']
