@@ -92,6 +92,41 @@ class Hiddens:
         self.stepper, self.weights_version = stepper, weights_version
 
 
+class _LearnGraph:
+    """static minibatch buffers + the CUDA graph of Agent._fwd_bwd over them.  Captured lazily on the first real
+    minibatch (after two eager warm-up passes on a side stream, as graph capture requires)."""
+
+    def __init__(self, agent, b, T):
+        self.agent, dev, cfg = agent, agent.device, agent.cfg
+        A = cfg.num_actions
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, device=dev, dtype=dt)
+        cont = agent.continuous_actions
+        self.mb = dict(states=z(b, T, cfg.state_dim), actions=z(b, T, A) if cont else z(b, T, dt=torch.int32), rewards=z(b, T),
+                       old_log_probs=z(b, T, A) if cont else z(b, T), returns=z(b, T), old_values=z(b, T),
+                       dones=z(b, T, dt=torch.bool), lens=z(b, dt=torch.int32), gene_ids=z(b, dt=torch.int32))
+        self.flag = torch.ones((), device=dev)
+        self.graph, self.scalars = None, None
+
+    def run(self):
+        agent = self.agent
+        if self.graph is None:
+            cur = torch.cuda.current_stream(agent.device)
+            side = torch.cuda.Stream(agent.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    agent._fwd_bwd(self.mb, self.flag)
+                agent.model.flat_grads.zero_()
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.scalars = agent._fwd_bwd(self.mb, self.flag)
+            self.graph = graph
+            agent.model.flat_grads.zero_()          # capture does not execute; start the replay from clean gradients
+        self.graph.replay()
+        return self.scalars
+
+
 class Agent(nn.Module):
     def __init__(self, state_dim, num_actions, reward_range, epochs, max_timesteps, batch_size, lr, betas, lam, gamma,
                  beta_s, regen_reg_rate, cautious_factor, eps_clip, value_clip, ema_decay, continuous_actions=False,
@@ -156,6 +191,8 @@ class Agent(nn.Module):
         self.last_logs = None
         self.keep_last_grads = False
         self.last_grads = None
+        self.use_cuda_graph_learn = True     # fwd + losses + bwd of a minibatch as one graph replay (launch-bound at small batches)
+        self._learn_graphs = {}
 
     @property
     def device(self):
@@ -217,38 +254,22 @@ class Agent(nn.Module):
         rs_copy = RSNorm(S + 1).to(dev)
         rs_copy.copy_from(self.rsnorm)
         model.train()
-        autocast = torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.accelerator.mixed_precision == 'bf16')
-        arange_t = torch.arange(T, device=dev)
         self.last_grads = None
+        fields = ('states', 'actions', 'rewards', 'old_log_probs', 'returns', 'old_values', 'dones', 'lens', 'gene_ids')
         for epoch in range(self.epochs):
             perm = permutations[epoch].to(dev) if permutations is not None else torch.randperm(E, device=dev)
             for lo in range(0, E, self.batch_size):
                 idx = perm[lo:lo + self.batch_size]
-                b = idx.numel()
-                states, actions, rewards = data['states'][idx], data['actions'][idx], data['rewards'][idx]
-                lens = data['lens'][idx].contiguous()
-                mask = arange_t[None, :] < lens[:, None]                                              # :908-909
-                if self.continuous_actions:                                                          # :911-916
-                    prev_actions = F.pad(actions, (0, 0, 1, -1), value=0.)
-                else:
-                    prev_actions = F.pad(actions, (1, -1), value=-1)
-                prev_rewards = F.pad(rewards, (1, -1), value=0.)                                     # :918
-                packed = self.rsnorm.normalize(torch.cat((states, prev_rewards[..., None]), dim=-1))  # :920-926
-                gene = self.gene_pool[data['gene_ids'][idx].long()] if self.evolutionary else None   # :906
                 flag = float(torch.rand(()) >= 0.5) if model.training else 1.                        # reward dropout :501
-                with autocast:
-                    cast = (lambda t: t) if self.continuous_actions else (lambda t: t.long())
-                    ra, vl, spr, dl = model(packed[..., :S], packed[..., S], cast(prev_actions), cast(actions), mask,
-                                            latent_gene=gene, reward_flag=flag)
-                loss, scalars = FusedPPOLoss.apply(self.loss_cfg, ra, vl, spr, dl, actions.contiguous(),
-                                                   data['old_log_probs'][idx].contiguous(), data['returns'][idx].contiguous(),
-                                                   data['old_values'][idx].contiguous(), packed.contiguous(),
-                                                   data['dones'][idx].contiguous(), lens)
-                loss.backward()
-                # RSNorm batch mean over the masked rows rides in the tail of the gradient buffer (:1005, :601)
-                mf = mask[..., None].float()
-                self._comm[n:] = (packed * mf).sum(dim=(0, 1)) / mf.sum().clamp(min=1.)
-                all_reduce_mean_(self._comm)
+                lg = self._learn_graph(idx.numel(), T) if self.use_cuda_graph_learn else None
+                if lg is not None:                       # static minibatch buffers -> one graph replay (fwd + losses + bwd)
+                    for k in fields:
+                        torch.index_select(data[k], 0, idx, out=lg.mb[k])
+                    lg.flag.fill_(flag)
+                    scalars = lg.run()
+                else:
+                    scalars = self._fwd_bwd({k: data[k][idx] for k in fields}, flag)
+                all_reduce_mean_(self._comm)             # gradients (+ RSNorm batch mean in the tail), one collective
                 if self.keep_last_grads:
                     self.last_grads = model.flat_grads.clone()
                 self._optimizer_step()
@@ -262,6 +283,48 @@ class Agent(nn.Module):
         self.step.add_(1)
         self._step_host += 1
         return self.epochs * int(data['lens'].sum().item())        # learn-timesteps processed
+
+    def _fwd_bwd(self, mb, flag):
+        """one minibatch: prep (:903-926) -> sequence model -> fused loss kernel (fwd + grads w.r.t. head outputs) ->
+        autograd backward into the flat gradient buffer; the RSNorm batch mean lands in the buffer's tail.  No host
+        synchronisation and only static shapes, so the whole thing can be captured in a CUDA graph (_LearnGraph)."""
+        model, cfg = self.model, self.cfg
+        S, n = cfg.state_dim, model.flat_params.numel()
+        states, actions, rewards, lens = mb['states'], mb['actions'], mb['rewards'], mb['lens']
+        T = actions.shape[1]
+        mask = torch.arange(T, device=states.device)[None, :] < lens[:, None]                 # :908-909
+        if self.continuous_actions:                                                          # :911-916
+            prev_actions = F.pad(actions, (0, 0, 1, -1), value=0.)
+        else:
+            prev_actions = F.pad(actions, (1, -1), value=-1)
+        prev_rewards = F.pad(rewards, (1, -1), value=0.)                                     # :918
+        packed = self.rsnorm.normalize(torch.cat((states, prev_rewards[..., None]), dim=-1))  # :920-926
+        gene = self.gene_pool[mb['gene_ids'].long()] if self.evolutionary else None          # :906
+        cast = (lambda t: t) if self.continuous_actions else (lambda t: t.long())
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.accelerator.mixed_precision == 'bf16'):
+            ra, vl, spr, dl = model(packed[..., :S], packed[..., S], cast(prev_actions), cast(actions), mask,
+                                    latent_gene=gene, reward_flag=flag)
+        loss, scalars = FusedPPOLoss.apply(self.loss_cfg, ra, vl, spr, dl, actions.contiguous(), mb['old_log_probs'].contiguous(),
+                                           mb['returns'].contiguous(), mb['old_values'].contiguous(), packed.contiguous(),
+                                           mb['dones'].contiguous(), lens.contiguous())
+        loss.backward()
+        # RSNorm batch mean over the masked rows rides in the tail of the gradient buffer (:1005, :601)
+        mf = mask[..., None].float()
+        self._comm[n:] = (packed * mf).sum(dim=(0, 1)) / mf.sum().clamp(min=1.)
+        return scalars
+
+    def _learn_graph(self, b, T):
+        """the captured fwd+bwd of a (b, T) minibatch, or None (capture disabled / failed -> eager launches)."""
+        key = (b, T)
+        if key not in self._learn_graphs:
+            try:
+                self._learn_graphs[key] = _LearnGraph(self, b, T)
+            except Exception as exc:                # host orchestration only: the same kernels run, launched one by one
+                import warnings
+                warnings.warn(f'CUDA-graph capture of the learn step failed ({exc!r}); using eager launches')
+                self._learn_graphs[key] = None
+                self.model.flat_grads.zero_()
+        return self._learn_graphs[key]
 
     def _optimizer_step(self):
         model = self.model
