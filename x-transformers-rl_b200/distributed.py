@@ -35,9 +35,12 @@ class Accelerator:
         world = int(os.environ.get('WORLD_SIZE', '1'))
         if world > 1 and not (dist.is_available() and dist.is_initialized()):
             use_cuda = torch.cuda.is_available() and not cpu
+            kw = {}
             if use_cuda:
-                torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
-            dist.init_process_group(backend or ('nccl' if use_cuda else 'gloo'))
+                local = int(os.environ.get('LOCAL_RANK', '0'))
+                torch.cuda.set_device(local)
+                kw['device_id'] = torch.device('cuda', local)       # rank <-> GPU binding is explicit, not guessed
+            dist.init_process_group(backend or ('nccl' if use_cuda else 'gloo'), **kw)
         self.num_processes = dist.get_world_size() if is_distributed() else 1
         self.process_index = dist.get_rank() if is_distributed() else 0
         self.is_main_process = self.process_index == 0
