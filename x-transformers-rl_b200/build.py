@@ -34,8 +34,8 @@ def source_hash() -> str:
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cu', '.cuh'))]
     files.append(os.path.join(os.path.dirname(HERE), 'include', 'xtrl.h'))
-    for f in files:
-        h.update(f.encode()); h.update(open(f, 'rb').read())
+    for f in files:                                   # names, not absolute paths: the snapshot on a GPU box lives elsewhere
+        h.update(os.path.basename(f).encode()); h.update(open(f, 'rb').read())
     h.update((' '.join(NVCC_FLAGS) + os.environ.get('XTRL_NVCC_EXTRA', '')).encode())
     return h.hexdigest()
 
@@ -48,14 +48,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_fresh():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get('XTRL_NVCC_EXTRA', '').split(), '-Xptxas', '-v', '-o', LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    with open(os.path.join(LIB_DIR, 'build.log'), 'w') as f:
-        f.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stderr[-4000:])
-    with open(STAMP, 'w') as f:
-        f.write(source_hash())
+    import fcntl
+    with open(os.path.join(LIB_DIR, '.build.lock'), 'w') as lock:      # one builder at a time (torchrun starts N ranks at once)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and is_fresh():                                   # another rank built it while we waited
+            return LIB_PATH
+        tmp = LIB_PATH + f'.tmp{os.getpid()}'
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get('XTRL_NVCC_EXTRA', '').split(), '-Xptxas', '-v', '-o', tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        with open(os.path.join(LIB_DIR, 'build.log'), 'w') as f:
+            f.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError('nvcc failed:\n' + res.stderr[-4000:])
+        os.replace(tmp, LIB_PATH)                                      # atomic: readers never see a half-written library
+        with open(STAMP, 'w') as f:
+            f.write(source_hash())
     if verbose:
         print(res.stderr, file=sys.stderr)
     return LIB_PATH
