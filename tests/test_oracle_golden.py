@@ -2,12 +2,11 @@
 (oracle/make_golden.py -> tests/golden).  Tolerances are fp32 re-association level."""
 import json
 
-import numpy as np
 import pytest
 import torch
 
 from oracle import restated as R
-from helpers import golden_model, load_golden, split, t, rel_err
+from helpers import golden_model, load_golden, split, rel_err
 
 CASES = ('c1', 'c2s', 'c3s', 'c4c', 'c5c')
 TOL = 2e-5

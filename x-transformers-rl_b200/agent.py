@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from torch import nn, tensor
 
 from . import ops
-from .distributed import Accelerator, all_reduce_mean_, is_distributed
+from .distributed import Accelerator, all_reduce_mean_
 from .evolution import LatentGenePool
 from .model import FusedPPOLoss, WorldModelActorCritic
 from .schedule import EmaSchedule

@@ -13,7 +13,6 @@ kernel, the EMA copy and the NCCL gradient all-reduce each touch a single contig
 """
 from __future__ import annotations
 
-import math
 
 import torch
 import torch.nn.functional as F
