@@ -591,7 +591,23 @@ wm_step_kernel(const StepArgs a) {
             // c+1 are in flight while chunk c is folded into the online softmax
             const int nchunks = (len + 31) >> 5;
             if (nchunks > 0) {
-                if constexpr (kKvBuf >= 2) {
+                if constexpr (kKvBuf >= 2 && PPR == 2) {
+                    // bf16 cache: a chunk is only 2 KB, so four register buffers keep the same 8 KB per warp in flight
+                    uint4 ka[PPR], va[PPR], kb[PPR], vb[PPR], kc4[PPR], vc4[PPR], kd[PPR], vd[PPR];
+                    fetch(0, ka, va);
+                    if (1 < nchunks) fetch(1, kb, vb);
+                    if (2 < nchunks) fetch(2, kc4, vc4);
+                    for (int c = 0; c < nchunks; c += 4) {
+                        if (c + 3 < nchunks) fetch(c + 3, kd, vd);
+                        process(c, ka, va);
+                        if (c + 4 < nchunks) fetch(c + 4, ka, va);
+                        if (c + 1 < nchunks) process(c + 1, kb, vb);
+                        if (c + 5 < nchunks) fetch(c + 5, kb, vb);
+                        if (c + 2 < nchunks) process(c + 2, kc4, vc4);
+                        if (c + 6 < nchunks) fetch(c + 6, kc4, vc4);
+                        if (c + 3 < nchunks) process(c + 3, kd, vd);
+                    }
+                } else if constexpr (kKvBuf >= 2) {
                     uint4 ka[PPR], va[PPR], kb[PPR], vb[PPR];
                     fetch(0, ka, va);
                     for (int c = 0; c < nchunks; c += 2) {
