@@ -144,6 +144,8 @@ typedef struct xtrl_step_io {
     const float   *normal;          /* [B][A] standard-normal draws for Normal.sample */
     const float   *forced_action_f; /* [B][A] or NULL: evaluate log-prob of these actions instead */
     float         *action_f;        /* [B][A]                                                    */
+    int32_t        envs_per_cta;    /* 0 = size the grid to fill the chip with THIS call's envs; >0 = envs per CTA
+                                       (<= 16), for callers that run several calls concurrently on different streams */
 } xtrl_step_io;
 
 int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, void *kv_cache,

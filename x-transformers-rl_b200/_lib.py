@@ -41,7 +41,7 @@ class StepIO(C.Structure):
     _fields_ = [(n, c_vp) for n in ('state', 'prev_action', 'prev_reward', 'pos', 'rs_mean', 'rs_var',
                                     'genes', 'gene_ids', 'uniform', 'forced_action')] + [
         ('reward_flag', c_f32), ('pos_uniform', c_i32), ('tc_weights', c_vp)] + [(n, c_vp) for n in ('action', 'log_prob', 'value', 'raw_actions', 'value_logits',
-                                           'prev_action_f', 'normal', 'forced_action_f', 'action_f')]
+                                           'prev_action_f', 'normal', 'forced_action_f', 'action_f')] + [('envs_per_cta', c_i32)]
 
 
 class LossCfg(C.Structure):
@@ -130,6 +130,21 @@ def load():
         raise XtrlError(f'libxtrl.so ABI {got} != binding {XTRL_ABI_VERSION}')
     _lib = lib
     return lib
+
+
+_cudart = None
+
+
+def cudart():
+    """the CUDA runtime already mapped into this process (torch's), for raw cudaMemcpyAsync on hot host loops."""
+    global _cudart
+    if _cudart is None:
+        import torch  # noqa: F401
+        rt = C.CDLL('libcudart.so.12')
+        rt.cudaMemcpyAsync.restype = c_i32
+        rt.cudaMemcpyAsync.argtypes = [c_vp, c_vp, C.c_size_t, c_i32, c_vp]
+        _cudart = rt
+    return _cudart
 
 
 def check(rc: int, what: str):

@@ -840,6 +840,7 @@ extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, v
     // share: 4096 envs -> 14 per CTA, 293 CTAs on 296 slots instead of 256 CTAs (108 SMs with two, 40 with one)
     const int slots = (smem <= 113 * 1024 ? 2 : 1) * kNumSMs;
     int epc = (num_envs + slots - 1) / slots;
+    if (io->envs_per_cta > 0) epc = io->envs_per_cta;                 // caller overlaps several calls on different streams
     epc = epc < 1 ? 1 : (epc > kTE ? kTE : epc);
     a.epc = epc;
     const int blocks = (num_envs + epc - 1) / epc;

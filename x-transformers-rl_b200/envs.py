@@ -78,9 +78,11 @@ class HostVecEnv:
         self.done = np.zeros(B, dtype=bool)
 
     def reset(self, seed=None):
+        """rewinds to the start of the pre-drawn block; a seed draws a new block (numpy draws 16 M normals in
+        ~0.2 s at the c3 shape -- simulator cost, kept out of the per-update path unless asked for)."""
         if seed is not None:
             self.rng = np.random.default_rng(int(seed))
-        self._draw()
+            self._draw()
         self._t = 0
         return self.states[0]
 

@@ -11,6 +11,7 @@ keeps the reference's one-episode-at-a-time semantics through the same kernel wi
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 import numpy as np
@@ -63,7 +64,9 @@ class Learner(nn.Module):
         self._steppers = {}
         self.use_cuda_graph = True       # device envs that declare cuda_graph_safe: the T-step rollout is one graph replay
         self._graphs = {}
-        self.rollout_groups = 2          # host-memory envs that can split(): groups of envs pipelined on separate streams
+        # host-memory envs that can split(): groups of envs stepped on separate streams through the raw-pointer loop
+        self.rollout_groups = int(os.environ.get('XTRL_ROLLOUT_GROUPS', '2'))
+        self.rollout_group_epc = os.environ.get('XTRL_GROUP_EPC', 'share')     # 'share' the CTA slots or 'fill' per call
         self.timings = dict(rollout_s=0., learn_s=0., env_steps=0, learn_timesteps=0)
 
     @property
@@ -93,7 +96,7 @@ class Learner(nn.Module):
         agent, dev, cfg = self.agent, self.device, self.agent.cfg
         B, T, S = env.num_envs, max_timesteps, cfg.state_dim
         cont = cfg.continuous
-        if (not cont and self.rollout_groups > 1 and hasattr(env, 'split') and getattr(env, 'never_terminates', False)
+        if (not cont and self.rollout_groups >= 1 and hasattr(env, 'split') and getattr(env, 'never_terminates', False)
                 and B % self.rollout_groups == 0 and B // self.rollout_groups >= 256):
             return self._rollout_pipelined(env, gene_ids, max_timesteps, seed, uniforms)
         if (not cont and self.use_cuda_graph and allow_graph and uniforms is None and getattr(env, 'cuda_graph_safe', False)
@@ -244,26 +247,55 @@ class Learner(nn.Module):
                             pin_a=torch.empty(Bg, dtype=torch.int32).pin_memory(), state=sub.reset()))
         for q in grp:
             q['stream'].wait_stream(main)
+        # Hot loop on raw pointers: the per-timestep host work (2 x G times per timestep) is a numpy copy into pinned
+        # memory, three cudaMemcpyAsync, one xtrl_wm_step and one event record -- no tensor views, no marshalling.
+        import ctypes as C
+        rt = ops.L.cudart()
+        lib = ops.L.load()
+        H2D, D2H = 1, 2
+        f4 = 4
+        for q in grp:
+            lo, st = q['lo'], q['st']
+            q['sid'] = C.c_void_p(q['stream'].cuda_stream)
+            q['io'] = ops.L.StepIO()
+            io = q['io']
+            io.rs_mean, io.rs_var = rs_mean.data_ptr(), rs_var.data_ptr()
+            io.genes = genes.data_ptr() if genes is not None else None
+            io.gene_ids = buf.gene_ids.data_ptr() + lo * 4 if genes is not None else None
+            io.reward_flag, io.tc_weights = 1., (st.tc_weights.data_ptr() if st.tc_weights is not None else None)
+            # the groups' kernels run concurrently: size each grid as if the whole batch were one call, so that a group
+            # takes its share of the CTA slots instead of paying the per-CTA fixed cost twice
+            io.envs_per_cta = min(16, max(1, -(-B // (2 * 148)))) if self.rollout_group_epc == 'share' else 0
+            q['p'] = dict(states=buf.states.data_ptr() + lo * S * f4, actions=buf.actions.data_ptr() + lo * 4,
+                          logp=buf.log_probs.data_ptr() + lo * f4, values=buf.values.data_ptr() + lo * f4,
+                          rewards=buf.rewards.data_ptr() + lo * f4, u=u.data_ptr() + lo * f4,
+                          pin_s=q['pin_s'].data_ptr(), pin_r=q['pin_r'].data_ptr(), pin_a=q['pin_a'].data_ptr(),
+                          first_a=first_a.data_ptr(), first_r=first_r.data_ptr())
+            q['np_s'], q['np_r'], q['np_a'] = q['pin_s'].numpy(), q['pin_r'].numpy(), q['pin_a'].numpy()
+            q['desc'], q['w'], q['kv'] = C.byref(st.desc), C.c_void_p(st.weights.data_ptr()), C.c_void_p(st.kv_cache.data_ptr())
+        row_s, row = B * S * f4, B * f4                               # byte strides of one timestep in the (T, B, .) buffers
         for t in range(T + 1):
             for q in grp:
-                lo, hi = q['lo'], q['hi']
-                with torch.cuda.stream(q['stream']):
-                    if t > 0:
-                        q['ev'].synchronize()                                  # actions of step t-1 are on the host
-                        step_out = q['env'].step(q['pin_a'].numpy())
-                        q['state'], reward = step_out[0], step_out[1]
-                        q['pin_r'].copy_(torch.from_numpy(np.ascontiguousarray(reward, dtype=np.float32)))
-                        buf.rewards[t - 1, lo:hi].copy_(q['pin_r'], non_blocking=True)
-                    if t == T:
-                        continue
-                    q['pin_s'].copy_(torch.from_numpy(np.ascontiguousarray(q['state'], dtype=np.float32)))
-                    buf.states[t, lo:hi].copy_(q['pin_s'], non_blocking=True)
-                    out = dict(action=buf.actions[t, lo:hi], log_prob=buf.log_probs[t, lo:hi], value=buf.values[t, lo:hi])
-                    q['st'].step(buf.states[t, lo:hi], first_a if t == 0 else buf.actions[t - 1, lo:hi],
-                                 first_r if t == 0 else buf.rewards[t - 1, lo:hi], rs_mean, rs_var, uniform=u[t, lo:hi],
-                                 genes=genes, gene_ids=buf.gene_ids[lo:hi] if genes is not None else None, out=out, pos_uniform=t)
-                    q['pin_a'].copy_(buf.actions[t, lo:hi], non_blocking=True)
-                    q['ev'].record(q['stream'])
+                p, sid = q['p'], q['sid']
+                if t > 0:
+                    q['ev'].synchronize()                              # actions of step t-1 are on the host
+                    step_out = q['env'].step(q['np_a'])
+                    q['state'] = step_out[0]
+                    np.copyto(q['np_r'], step_out[1], casting='same_kind')
+                    rt.cudaMemcpyAsync(C.c_void_p(p['rewards'] + (t - 1) * row), C.c_void_p(p['pin_r']), Bg * f4, H2D, sid)
+                if t == T:
+                    continue
+                np.copyto(q['np_s'], q['state'], casting='same_kind')
+                rt.cudaMemcpyAsync(C.c_void_p(p['states'] + t * row_s), C.c_void_p(p['pin_s']), Bg * S * f4, H2D, sid)
+                io = q['io']
+                io.state = p['states'] + t * row_s
+                io.prev_action = p['first_a'] if t == 0 else p['actions'] + (t - 1) * row
+                io.prev_reward = p['first_r'] if t == 0 else p['rewards'] + (t - 1) * row
+                io.uniform, io.pos_uniform = p['u'] + t * row, t
+                io.action, io.log_prob, io.value = p['actions'] + t * row, p['logp'] + t * row, p['values'] + t * row
+                ops.L.check(lib.xtrl_wm_step(q['desc'], q['w'], q['kv'], C.byref(io), Bg, sid), 'xtrl_wm_step')
+                rt.cudaMemcpyAsync(C.c_void_p(p['pin_a']), C.c_void_p(p['actions'] + t * row), Bg * 4, D2H, sid)
+                q['ev'].record(q['stream'])
         for q in grp:
             main.wait_stream(q['stream'])
         buf.episode_lens.fill_(T)
