@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define XTRL_ABI_VERSION 3
+#define XTRL_ABI_VERSION 4
 
 #define XTRL_OK            0
 #define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
@@ -261,6 +261,38 @@ int xtrl_adopt_atan2_step(float *params, const float *grads, float *m, float *v,
                           float *ema, const int64_t *seg_offsets, int32_t num_tensors, int64_t n,
                           const xtrl_opt_cfg *cfg, double *workspace, float *grad_norm_out,
                           void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (6) learn-side sequence model, fused sub-layers on tcgen05 -- replace the
+ *     teacher-forced Decoder pass inside Agent.learn (x_transformers_rl.py:928-935; x-transformers
+ *     Decoder, App. A.1) piece by piece.  bf16 operands, fp32 accumulate, fp32 residual stream.
+ *
+ *     feed-forward sub-layer:  y = x + W2 . drop(gelu(W1 . (LayerNorm(x) * gamma) + b1)) + b2
+ *     x, y, dy, dx: [N][dim] fp32 (N tokens, any order).  The forward saves nothing: the backward
+ *     recomputes from x and regenerates the dropout mask from (*rng_step, rng_key).  Gradients of the
+ *     parameters are ACCUMULATED (+=) into d_* (fp32, the layouts of the torch parameters).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct xtrl_ff_io {
+    const float *x;                 /* [N][dim]                                               */
+    const float *dy;                /* [N][dim]            (backward)                         */
+    const float *ln_gamma;          /* [dim]                                                  */
+    const float *b1;                /* [hidden]                                               */
+    const float *b2;                /* [dim]                                                  */
+    const void  *w_img;             /* xtrl_ff_pack output (bf16 operand images of W1, W2)    */
+    float *y;                       /* [N][dim]            (forward)                          */
+    float *dx;                      /* [N][dim]            (backward)                         */
+    float *d_ln_gamma, *d_w1, *d_b1, *d_w2, *d_b2;        /* += (backward)                    */
+    const int64_t *rng_step;        /* device counter the caller bumps once per fwd/bwd pair; may
+                                       be NULL when dropout == 0                              */
+    uint32_t rng_key;               /* distinguishes call sites (layer index)                 */
+    float dropout;                  /* p in [0,1); 0 = none                                   */
+} xtrl_ff_io;
+
+int64_t xtrl_ff_img_bytes(int32_t dim, int32_t hidden);          /* -1 if the shape is not built */
+int xtrl_ff_pack(const float *w1 /*[hidden][dim]*/, const float *w2 /*[dim][hidden]*/, void *img,
+                 int32_t dim, int32_t hidden, void *stream);
+int xtrl_ff_fwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t hidden, void *stream);
+int xtrl_ff_bwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t hidden, void *stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-XTRL_ABI_VERSION = 3
+XTRL_ABI_VERSION = 4
 XTRL_MAX_DEPTH = 16
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -72,6 +72,12 @@ class OptCfg(C.Structure):
         ('first_step', c_i32), ('ema_mode', c_f32), ('ema_decay', c_f32), ('copy_ema_to_online', c_i32)]
 
 
+class FfIO(C.Structure):
+    _fields_ = [(n, c_vp) for n in ('x', 'dy', 'ln_gamma', 'b1', 'b2', 'w_img', 'y', 'dx',
+                                    'd_ln_gamma', 'd_w1', 'd_b1', 'd_w2', 'd_b2', 'rng_step')] + [
+        ('rng_key', C.c_uint32), ('dropout', c_f32)]
+
+
 # every symbol include/xtrl.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'xtrl_abi_version': (c_i32, []),
@@ -90,6 +96,10 @@ SYMBOLS = {
     'xtrl_opt_workspace_bytes': (c_i64, [c_i32]),
     'xtrl_adopt_atan2_step': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64,
                                       C.POINTER(OptCfg), c_vp, c_vp, c_vp]),
+    'xtrl_ff_img_bytes': (c_i64, [c_i32, c_i32]),
+    'xtrl_ff_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    'xtrl_ff_fwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
+    'xtrl_ff_bwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
 }
 
 

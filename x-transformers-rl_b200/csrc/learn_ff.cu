@@ -1,0 +1,510 @@
+// learn_ff.cu -- learn-side feed-forward block of the sequence model, forward and backward, on tcgen05.
+//
+//     y = x + W2 * drop(gelu(W1 * (LN(x) * gamma) + b1)) + b2           (tokens x 48 -> 192 -> 48)
+//
+// Replaces, inside Agent.learn's teacher-forced pass (x_transformers_rl.py:928-935; x-transformers
+// Decoder feed-forward sub-layer): LayerNorm -> Linear(D,4D) -> GELU -> Dropout ->
+// Linear(4D,D) -> +residual, and their backward.  SURVEY 8f row 1.
+//
+// A CTA walks 128-token tiles; TMEM lane = token row.  256 threads: thread (row, half) owns half of the
+// row's columns in every epilogue.  Operands are bf16 canonical no-swizzle images in shared memory, fp32
+// accumulators in TMEM:
+//   fwd:  PRE[128x192] = Xn * W1^T          H = drop(gelu(PRE + b1))       OUT[128x48] = H * W2^T
+//   bwd:  recompute PRE / H (nothing but x is saved by the forward), then
+//         dH[128x192]  = dY * W2            dPRE = dH . gelu'(PRE) . mask
+//         dXn[128x48]  = dPRE * W1          dx = dy + LN'(dXn * gamma)
+//         dW1 | db1   += dPRE^T * [Xn | 1]  dW2^T | db2 += [H | 1]^T * dY  -- accumulated in TMEM across all
+//         tiles of the CTA; the token-major images the token GEMMs already use are re-read as MN-major
+//         ("transposed") operands, so no transposed copy is ever written; bias gradients fall out of a
+//         constant-one column.  One atomicAdd pass per CTA at the end.
+// HBM traffic per token: fwd 192 B read + 192 B written; bwd 384 B read + 192 B written (fp32 residual
+// stream); weights stay in shared memory for the life of the CTA.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace xtrl {
+namespace ff {
+using namespace umma;
+
+constexpr int D = 48, F = 192, TOK = 128, NT = 256;
+constexpr int XW = 64;                 // Xn / dY image width: 48 features + a ones column (48) + zero pad
+constexpr int HW = 200;                // H image width: 192 features + a ones column (192) + zero pad
+constexpr int kW1 = F * D * 2;         // W1 image: rows = 192 outputs, K = 48
+constexpr int kW2 = D * F * 2;         // W2 image: rows = 48 outputs, K = 192
+constexpr int kCore = TOK * 16;        // bytes between 8-feature chunks of a 128-token image
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4 u, float (&o)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void gelu_both(float x, float &g, float &dg) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+    g = x * cdf;
+    dg = cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+// two 16-bit uniforms per (token, column pair): murmur3 finaliser over a counter
+__device__ __forceinline__ uint32_t hash2(uint32_t idx, uint32_t key) {
+    uint32_t h = idx * 0x9E3779B1u ^ key;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t fold_key(const int64_t *rng_step, uint32_t key) {
+    const uint64_t s = (uint64_t)(rng_step ? *rng_step : 0) * 0x9E3779B97F4A7C15ull;
+    return (uint32_t)(s >> 32) ^ (uint32_t)s ^ (key * 0x632BE5ABu);
+}
+// keep-factors (0 or 1/(1-p)) for columns c, c+1 of token t
+__device__ __forceinline__ void drop2(uint32_t t, int c, uint32_t key, uint32_t thr, float scale, float &k0, float &k1) {
+    const uint32_t h = hash2(t * (uint32_t)(F / 2) + (uint32_t)(c >> 1), key);
+    k0 = (h & 0xffffu) >= thr ? scale : 0.f;
+    k1 = (h >> 16) >= thr ? scale : 0.f;
+}
+
+struct Args {
+    const float *x, *dy, *gamma, *b1, *b2;
+    const unsigned char *wimg;
+    float *y, *dx, *dgamma, *dW1, *db1, *dW2, *db2;
+    const int64_t *rng_step;
+    uint32_t rng_key, drop_thr;
+    float drop_scale;
+    int N;
+};
+
+// row statistics of LayerNorm over 48 fp32 values held in registers
+__device__ __forceinline__ void ln_stats(const float (&xr)[D], float &mean, float &rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s += xr[i];
+    mean = s * (1.f / D);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { const float d = xr[i] - mean; v = fmaf(d, d, v); }
+    rstd = rsqrtf(v * (1.f / D) + 1e-5f);
+}
+__device__ __forceinline__ void load_row(const float *p, bool ok, float (&xr)[D]) {
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+        const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(p) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
+    }
+}
+// 8 consecutive features of this thread's row -> one 16-byte piece of a 128-token image
+__device__ __forceinline__ void put8(unsigned char *img, int row, int chunk, const float (&v)[8]) {
+    *reinterpret_cast<uint4 *>(img + chunk * kCore + (row >> 3) * 128 + (row & 7) * 16) =
+        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+
+// ------------------------------------------------------------------------------------------ forward
+constexpr int kFwdSmem = kW1 + kW2 + TOK * D * 2 + TOK * F * 2 + (F + 2 * D) * 4 + 64;
+
+__global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *sW1 = smem, *sW2 = sW1 + kW1, *sXn = sW2 + kW2, *sH = sXn + TOK * D * 2;
+    float *sB1 = reinterpret_cast<float *>(sH + TOK * F * 2), *sB2 = sB1 + F, *sG = sB2 + D;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(tslot, 256);
+    for (int i = tid; i < F; i += NT) sB1[i] = a.b1[i];
+    if (tid < D) { sB2[tid] = a.b2[tid]; sG[tid] = a.gamma[tid]; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
+    if (tid == 0) { mbar_expect_tx(&bars[0], kW1 + kW2); bulk_g2s(sW1, a.wimg, kW1 + kW2, &bars[0]); }
+    const uint32_t key = fold_key(a.rng_step, a.rng_key);
+    uint32_t ph = 0;
+    bool first = true;
+    const int ntiles = (a.N + TOK - 1) / TOK;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t = tile * TOK + row;
+        const bool ok = t < a.N;
+        float xr[D];
+        load_row(a.x + (size_t)t * D, ok, xr);
+        float mean, rstd, own[24];
+        ln_stats(xr, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < 24; ++i) own[i] = half ? xr[24 + i] : xr[i];           // this thread's half of the row
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (own[c * 8 + j] - mean) * rstd * sG[half * 24 + c * 8 + j];
+            put8(sXn, row, half * 3 + c, v);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            if (first) mbar_wait(&bars[0], 0);
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < D / 16; ++s)
+                mma_bf16_ss(tbase, smem_desc(sXn + s * 2 * kCore, kCore, 128), smem_desc(sW1 + s * 2 * F * 16, F * 16, 128),
+                            idesc_bf16(128, F), s > 0);
+            mma_commit(&bars[1]);
+        }
+        first = false;
+        mbar_wait(&bars[1], ph); ph ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+            const int col0 = half * 96 + c * 16;
+            float v[16];
+            tmem_ld16(tlane + col0, v);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const float p0 = v[j] + sB1[col0 + j], p1 = v[j + 1] + sB1[col0 + j + 1];
+                float g0 = p0 * 0.5f * (1.f + erff(p0 * 0.70710678118654752f));
+                float g1 = p1 * 0.5f * (1.f + erff(p1 * 0.70710678118654752f));
+                if (a.drop_thr) {
+                    float k0, k1;
+                    drop2((uint32_t)t, col0 + j, key, a.drop_thr, a.drop_scale, k0, k1);
+                    g0 *= k0; g1 *= k1;
+                }
+                v[j] = g0; v[j + 1] = g1;
+            }
+            float lo[8], hi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+            put8(sH, row, col0 / 8, lo);
+            put8(sH, row, col0 / 8 + 1, hi);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < F / 16; ++s)
+                mma_bf16_ss(tbase + F, smem_desc(sH + s * 2 * kCore, kCore, 128), smem_desc(sW2 + s * 2 * D * 16, D * 16, 128),
+                            idesc_bf16(128, D), s > 0);
+            mma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], ph); ph ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v[8];
+            tmem_ld8(tlane + F + half * 24 + c * 8, v);
+            if (ok) {
+                float4 *dst = reinterpret_cast<float4 *>(a.y + (size_t)t * D + half * 24 + c * 8);
+                const int f = half * 24 + c * 8;
+                const float *o = own + c * 8;
+                dst[0] = make_float4(v[0] + sB2[f] + o[0], v[1] + sB2[f + 1] + o[1], v[2] + sB2[f + 2] + o[2], v[3] + sB2[f + 3] + o[3]);
+                dst[1] = make_float4(v[4] + sB2[f + 4] + o[4], v[5] + sB2[f + 5] + o[5], v[6] + sB2[f + 6] + o[6], v[7] + sB2[f + 7] + o[7]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+// ----------------------------------------------------------------------------------------- backward
+// shared-memory order matters: the dW MMAs read 128 "feature rows" starting at feature 128 of the H and
+// dPRE images (64 real + 64 beyond the image); what follows each image is more shared memory of this
+// CTA, and the accumulator rows those bytes feed (>= 64, resp. > 64) are never read.
+constexpr int kBwdH = TOK * HW * 2, kBwdDP = TOK * F * 2, kBwdX = TOK * XW * 2;
+constexpr int kBwdSmem = kBwdH + kBwdDP + 2 * kBwdX + kW1 + kW2 + (F + D) * 4 + 64;
+constexpr uint32_t kIdA = 1u << 15, kIdB = 1u << 16;                 // MN-major operand flags of the idesc
+
+__global__ void __launch_bounds__(NT, 1) ff_bwd_kernel(const Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *sH = smem, *sDP = sH + kBwdH, *sXn = sDP + kBwdDP, *sDY = sXn + kBwdX;
+    unsigned char *sW1 = sDY + kBwdX, *sW2 = sW1 + kW1;
+    float *sB1 = reinterpret_cast<float *>(sW2 + kW2), *sG = sB1 + F;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+    constexpr uint32_t cPre = 0, cDxn = 192, cA = 256, cB = 320, cC = 384, cD = 448;
+
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(tslot, 512);
+    for (int i = tid; i < F; i += NT) sB1[i] = a.b1[i];
+    if (tid < D) sG[tid] = a.gamma[tid];
+    if (half == 0) {                       // constant columns: [1, 0 x 7] then zeros
+        const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        put8(sXn, row, 6, one); put8(sXn, row, 7, zero);
+        put8(sDY, row, 6, one); put8(sDY, row, 7, zero);
+        put8(sH, row, 24, one);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
+    if (tid == 0) { mbar_expect_tx(&bars[0], kW1 + kW2); bulk_g2s(sW1, a.wimg, kW1 + kW2, &bars[0]); }
+    const uint32_t key = fold_key(a.rng_step, a.rng_key);
+    uint32_t ph = 0;
+    bool first = true;
+    float dg_acc[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) dg_acc[i] = 0.f;
+    const int ntiles = (a.N + TOK - 1) / TOK;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t = tile * TOK + row;
+        const bool ok = t < a.N;
+        float xr[D], dyr[24];
+        load_row(a.x + (size_t)t * D, ok, xr);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(a.dy + (size_t)t * D + half * 24) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dyr[4 * i] = v.x; dyr[4 * i + 1] = v.y; dyr[4 * i + 2] = v.z; dyr[4 * i + 3] = v.w;
+        }
+        float mean, rstd;
+        ln_stats(xr, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < D; ++i) xr[i] = (xr[i] - mean) * rstd;               // xr is xhat from here on
+        float own[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) own[i] = half ? xr[24 + i] : xr[i];         // this thread's half of xhat
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v[8], w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = own[c * 8 + j] * sG[half * 24 + c * 8 + j]; w[j] = dyr[c * 8 + j]; }
+            put8(sXn, row, half * 3 + c, v);
+            put8(sDY, row, half * 3 + c, w);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {                                                          // PRE = Xn * W1^T
+            if (first) mbar_wait(&bars[0], 0);
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < D / 16; ++s)
+                mma_bf16_ss(tbase + cPre, smem_desc(sXn + s * 2 * kCore, kCore, 128), smem_desc(sW1 + s * 2 * F * 16, F * 16, 128),
+                            idesc_bf16(128, F), s > 0);
+            mma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], ph); ph ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {                                            // H and gelu'.mask
+            const int col0 = half * 96 + c * 16;
+            float v[16], d[16];
+            tmem_ld16(tlane + cPre + col0, v);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                float g0, g1, d0, d1;
+                gelu_both(v[j] + sB1[col0 + j], g0, d0);
+                gelu_both(v[j + 1] + sB1[col0 + j + 1], g1, d1);
+                if (a.drop_thr) {
+                    float k0, k1;
+                    drop2((uint32_t)t, col0 + j, key, a.drop_thr, a.drop_scale, k0, k1);
+                    g0 *= k0; g1 *= k1; d0 *= k0; d1 *= k1;
+                }
+                v[j] = g0; v[j + 1] = g1; d[j] = d0; d[j + 1] = d1;
+            }
+            float lo[8], hi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+            put8(sH, row, col0 / 8, lo);
+            put8(sH, row, col0 / 8 + 1, hi);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { lo[j] = d[j]; hi[j] = d[8 + j]; }
+            put8(sDP, row, col0 / 8, lo);                                        // parked in dPRE's slot
+            put8(sDP, row, col0 / 8 + 1, hi);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < D / 16; ++s)                                     // dH = dY * W2 (W2 image read MN-major)
+                mma_bf16_ss(tbase + cPre, smem_desc(sDY + s * 2 * kCore, kCore, 128), smem_desc(sW2 + s * 256, 128, D * 16),
+                            idesc_bf16(128, F) | kIdB, s > 0);
+#pragma unroll
+            for (int s = 0; s < TOK / 16; ++s) {                                 // dW2^T | db2 += [H|1]^T * dY
+                const uint64_t bd = smem_desc(sDY + s * 256, 128, kCore);
+                mma_bf16_ss(tbase + cC, smem_desc(sH + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
+                mma_bf16_ss(tbase + cD, smem_desc(sH + 16 * kCore + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
+            }
+            mma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], ph); ph ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {                                            // dPRE = dH . gelu'.mask
+            const int col0 = half * 96 + c * 16;
+            float v[16], lo[8], hi[8];
+            tmem_ld16(tlane + cPre + col0, v);
+            unsigned char *p = sDP + (col0 / 8) * kCore + (row >> 3) * 128 + (row & 7) * 16;
+            unpack8(*reinterpret_cast<const uint4 *>(p), lo);
+            unpack8(*reinterpret_cast<const uint4 *>(p + kCore), hi);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { lo[j] *= v[j]; hi[j] *= v[8 + j]; }
+            put8(sDP, row, col0 / 8, lo);
+            put8(sDP, row, col0 / 8 + 1, hi);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < F / 16; ++s)                                     // dXn = dPRE * W1 (W1 image read MN-major)
+                mma_bf16_ss(tbase + cDxn, smem_desc(sDP + s * 2 * kCore, kCore, 128), smem_desc(sW1 + s * 256, 128, F * 16),
+                            idesc_bf16(128, D) | kIdB, s > 0);
+#pragma unroll
+            for (int s = 0; s < TOK / 16; ++s) {                                 // dW1 | db1 += dPRE^T * [Xn|1]
+                const uint64_t bd = smem_desc(sXn + s * 256, 128, kCore);
+                mma_bf16_ss(tbase + cA, smem_desc(sDP + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
+                mma_bf16_ss(tbase + cB, smem_desc(sDP + 16 * kCore + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
+            }
+            mma_commit(&bars[1]);
+        }
+        first = false;
+        mbar_wait(&bars[1], ph); ph ^= 1;
+        tc_fence_after();
+        {                                                                        // LayerNorm backward + residual
+            float dxn[D];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                float v[8];
+                tmem_ld8(tlane + cDxn + c * 8, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dxn[c * 8 + j] = v[j];
+            }
+            float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { const float dh = dxn[i] * sG[i]; c1 += dh; c2 = fmaf(dh, xr[i], c2); }
+            c1 *= (1.f / D); c2 *= (1.f / D);
+            float o[24];
+#pragma unroll
+            for (int i = 0; i < 24; ++i) {
+                const float dxi = half ? dxn[24 + i] : dxn[i];
+                dg_acc[i] = fmaf(dxi, own[i], dg_acc[i]);
+                o[i] = dyr[i] + rstd * (dxi * sG[half * 24 + i] - c1 - own[i] * c2);
+            }
+            if (ok) {
+                float4 *dst = reinterpret_cast<float4 *>(a.dx + (size_t)t * D + half * 24);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+        }
+        tc_fence_before();
+    }
+    // ---- flush the per-CTA weight-gradient accumulators ----
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+        const float s = warp_sum(dg_acc[i]);
+        if (lane == 0 && s != 0.f) atomicAdd(a.dgamma + half * 24 + i, s);
+    }
+    if (!first) {                                                                // this CTA saw at least one tile
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {                                            // half 0: columns 0..31, half 1: 32..63
+            const int col0 = half * 32 + c * 8;
+            if (col0 > D) break;
+            float va[8], vb[8], vc[8], vd[8];
+            tmem_ld8(tlane + cA + col0, va);
+            tmem_ld8(tlane + cB + col0, vb);
+            tmem_ld8(tlane + cC + col0, vc);
+            tmem_ld8(tlane + cD + col0, vd);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = col0 + j;
+                if (i < D) {
+                    atomicAdd(a.dW1 + row * D + i, va[j]);
+                    atomicAdd(a.dW2 + i * F + row, vc[j]);
+                    if (row < 64) { atomicAdd(a.dW1 + (128 + row) * D + i, vb[j]); atomicAdd(a.dW2 + i * F + 128 + row, vd[j]); }
+                    if (row == 64) atomicAdd(a.db2 + i, vd[j]);
+                } else if (i == D) {
+                    atomicAdd(a.db1 + row, va[j]);
+                    if (row < 64) atomicAdd(a.db1 + 128 + row, vb[j]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+__global__ void ff_pack_kernel(const float *__restrict__ w1, const float *__restrict__ w2, unsigned char *__restrict__ img) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F * D) {
+        const int j = i / D, k = i % D;                                          // w1 [192][48]
+        *reinterpret_cast<__nv_bfloat16 *>(img + img_off_bf16(F, j, k)) = __float2bfloat16(w1[i]);
+        const int o = i / F, h = i % F;                                          // w2 [48][192]
+        *reinterpret_cast<__nv_bfloat16 *>(img + kW1 + img_off_bf16(D, o, h)) = __float2bfloat16(w2[i]);
+    }
+}
+
+static int check_dims(int dim, int hidden) {
+    XTRL_REQUIRE(dim == D && hidden == F, XTRL_E_UNSUPPORTED, "xtrl_ff_*: built for dim=%d hidden=%d (got %d, %d)", D, F, dim, hidden);
+    return XTRL_OK;
+}
+static int fill(const xtrl_ff_io *io, int64_t N, Args &a) {
+    XTRL_REQUIRE(N <= (int64_t)1 << 24, XTRL_E_BADARG, "xtrl_ff_*: at most 2^24 tokens per call (N=%lld)", (long long)N);
+    XTRL_REQUIRE(io->dropout >= 0.f && io->dropout < 1.f, XTRL_E_BADARG, "xtrl_ff_*: dropout %f not in [0,1)", io->dropout);
+    a.x = io->x; a.dy = io->dy; a.gamma = io->ln_gamma; a.b1 = io->b1; a.b2 = io->b2;
+    a.wimg = static_cast<const unsigned char *>(io->w_img);
+    a.y = io->y; a.dx = io->dx; a.dgamma = io->d_ln_gamma; a.dW1 = io->d_w1; a.db1 = io->d_b1; a.dW2 = io->d_w2; a.db2 = io->d_b2;
+    a.rng_step = io->rng_step; a.rng_key = io->rng_key;
+    a.drop_thr = (uint32_t)(io->dropout * 65536.f + 0.5f);
+    a.drop_scale = 1.f / (1.f - (float)a.drop_thr / 65536.f);
+    a.N = (int)N;
+    return XTRL_OK;
+}
+
+}  // namespace ff
+}  // namespace xtrl
+
+extern "C" int64_t xtrl_ff_img_bytes(int32_t dim, int32_t hidden) {
+    using namespace xtrl::ff;
+    return (dim == D && hidden == F) ? (int64_t)(kW1 + kW2) : -1;
+}
+
+extern "C" int xtrl_ff_pack(const float *w1, const float *w2, void *img, int32_t dim, int32_t hidden, void *stream) {
+    using namespace xtrl; using namespace xtrl::ff;
+    if (int rc = check_dims(dim, hidden)) return rc;
+    XTRL_REQUIRE(w1 && w2 && img, XTRL_E_BADARG, "xtrl_ff_pack: null pointer");
+    ff_pack_kernel<<<(F * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w1, w2, static_cast<unsigned char *>(img));
+    XTRL_LAUNCH_CHECK("ff_pack_kernel");
+    return XTRL_OK;
+}
+
+extern "C" int xtrl_ff_fwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t hidden, void *stream) {
+    using namespace xtrl; using namespace xtrl::ff;
+    if (int rc = check_dims(dim, hidden)) return rc;
+    XTRL_REQUIRE(io && N >= 0, XTRL_E_BADARG, "xtrl_ff_fwd: bad arguments");
+    if (N == 0) return XTRL_OK;
+    XTRL_REQUIRE(io->x && io->ln_gamma && io->b1 && io->b2 && io->w_img && io->y, XTRL_E_BADARG, "xtrl_ff_fwd: null pointer");
+    Args a;
+    if (int rc = fill(io, N, a)) return rc;
+    static bool attr = false;
+    if (!attr) { XTRL_CUDA(cudaFuncSetAttribute(ff_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
+    const int ntiles = (int)((N + TOK - 1) / TOK);
+    const int grid = ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
+    ff_fwd_kernel<<<grid, NT, kFwdSmem, (cudaStream_t)stream>>>(a);
+    XTRL_LAUNCH_CHECK("ff_fwd_kernel");
+    return XTRL_OK;
+}
+
+extern "C" int xtrl_ff_bwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t hidden, void *stream) {
+    using namespace xtrl; using namespace xtrl::ff;
+    if (int rc = check_dims(dim, hidden)) return rc;
+    XTRL_REQUIRE(io && N >= 0, XTRL_E_BADARG, "xtrl_ff_bwd: bad arguments");
+    if (N == 0) return XTRL_OK;
+    XTRL_REQUIRE(io->x && io->dy && io->ln_gamma && io->b1 && io->w_img && io->dx && io->d_ln_gamma && io->d_w1 && io->d_b1 &&
+                 io->d_w2 && io->d_b2, XTRL_E_BADARG, "xtrl_ff_bwd: null pointer");
+    Args a;
+    if (int rc = fill(io, N, a)) return rc;
+    static bool attr = false;
+    if (!attr) { XTRL_CUDA(cudaFuncSetAttribute(ff_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
+    const int ntiles = (int)((N + TOK - 1) / TOK);
+    const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+    ff_bwd_kernel<<<grid, NT, kBwdSmem, (cudaStream_t)stream>>>(a);
+    XTRL_LAUNCH_CHECK("ff_bwd_kernel");
+    return XTRL_OK;
+}

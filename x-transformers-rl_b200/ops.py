@@ -175,6 +175,55 @@ def adopt_atan2_step(params, grads, m, v, param_init, ema, seg_offsets, *, lr, i
 
 
 # --------------------------------------------------------------------------------------------
+# (6) learn-side fused sub-layers (tcgen05)
+# --------------------------------------------------------------------------------------------
+
+def ff_supported(dim, hidden) -> bool:
+    return L.load().xtrl_ff_img_bytes(dim, hidden) > 0
+
+
+def ff_pack(w1, w2, out=None):
+    """bf16 operand images of the feed-forward weights (w1 (hidden, dim), w2 (dim, hidden)); once per weight update."""
+    lib = L.load()
+    hidden, dim = w1.shape
+    nbytes = lib.xtrl_ff_img_bytes(dim, hidden)
+    if nbytes < 0:
+        raise L.XtrlError(f'ff_pack: dim={dim}, hidden={hidden} is not built')
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w1.device) if out is None else out
+    L.check(lib.xtrl_ff_pack(_ptr(w1, torch.float32, 'w1'), _ptr(w2, torch.float32, 'w2'), _ptr(out, torch.uint8, 'img'),
+                             dim, hidden, _stream()), 'xtrl_ff_pack')
+    return out
+
+
+def ff_fwd(x, ln_gamma, b1, b2, img, *, dropout=0., rng_step=None, rng_key=0, out=None):
+    """y = x + FF(LayerNorm(x) * gamma), x (..., dim) fp32."""
+    lib = L.load()
+    dim, hidden = x.shape[-1], b1.numel()
+    y = torch.empty_like(x) if out is None else out
+    io = L.FfIO(x=_ptr(x, torch.float32, 'x'), ln_gamma=_ptr(ln_gamma, torch.float32, 'ln_gamma'), b1=_ptr(b1, torch.float32, 'b1'),
+                b2=_ptr(b2, torch.float32, 'b2'), w_img=_ptr(img, torch.uint8, 'img'), y=_ptr(y, torch.float32, 'y'),
+                rng_step=_ptr(rng_step, torch.int64, 'rng_step'), rng_key=rng_key, dropout=dropout)
+    if dropout > 0. and rng_step is None:
+        raise L.XtrlError('ff_fwd: dropout needs the rng_step counter tensor')
+    L.check(lib.xtrl_ff_fwd(C.byref(io), x.numel() // dim, dim, hidden, _stream()), 'xtrl_ff_fwd')
+    return y
+
+
+def ff_bwd(x, dy, ln_gamma, b1, img, d_ln_gamma, d_w1, d_b1, d_w2, d_b2, *, dropout=0., rng_step=None, rng_key=0):
+    """dx of the feed-forward sub-layer; parameter gradients are accumulated (+=) into the d_* tensors."""
+    lib = L.load()
+    dim, hidden = x.shape[-1], b1.numel()
+    dx = torch.empty_like(x)
+    f32 = torch.float32
+    io = L.FfIO(x=_ptr(x, f32, 'x'), dy=_ptr(dy, f32, 'dy'), ln_gamma=_ptr(ln_gamma, f32, 'ln_gamma'), b1=_ptr(b1, f32, 'b1'),
+                w_img=_ptr(img, torch.uint8, 'img'), dx=_ptr(dx, f32, 'dx'), d_ln_gamma=_ptr(d_ln_gamma, f32, 'd_ln_gamma'),
+                d_w1=_ptr(d_w1, f32, 'd_w1'), d_b1=_ptr(d_b1, f32, 'd_b1'), d_w2=_ptr(d_w2, f32, 'd_w2'), d_b2=_ptr(d_b2, f32, 'd_b2'),
+                rng_step=_ptr(rng_step, torch.int64, 'rng_step'), rng_key=rng_key, dropout=dropout)
+    L.check(lib.xtrl_ff_bwd(C.byref(io), x.numel() // dim, dim, hidden, _stream()), 'xtrl_ff_bwd')
+    return dx
+
+
+# --------------------------------------------------------------------------------------------
 # (1) rollout step
 # --------------------------------------------------------------------------------------------
 
