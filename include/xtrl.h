@@ -294,6 +294,37 @@ int xtrl_ff_pack(const float *w1 /*[hidden][dim]*/, const float *w2 /*[dim][hidd
 int xtrl_ff_fwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t hidden, void *stream);
 int xtrl_ff_bwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t hidden, void *stream);
 
+/*     attention sub-layer around the attention core (plain block: no value gate / value residual):
+ *       pre :  [q|k|v] = (LayerNorm(x) * gamma) . Wqkv^T, partial rotary on q, k; bf16 [b][H][n][16]
+ *       post:  y = x + mask . (o . Wo^T), o bf16 [b][H][n][16], mask = position < lens[episode]
+ *     x, y, dy, dx: [b*n][dim] fp32, token t = episode * n + position.  cos_tab / sin_tab: [n][dim_head/4]
+ *     fp32 (angle = position * inv_freq, as the caller's rotary embedding defines it).  Parameter gradients
+ *     are ACCUMULATED (+=).  pre_bwd returns only the LayerNorm path's dx (the residual path is the caller's).  */
+typedef struct xtrl_attn_io {
+    const float *x;                 /* [b*n][dim]              pre fwd/bwd, post fwd           */
+    const float *ln_gamma;          /* [dim]                   pre                             */
+    const float *cos_tab, *sin_tab; /* [n][4]                  pre                             */
+    const void  *w_img;             /* xtrl_attn_pack output                                   */
+    void *q, *k, *v;                /* bf16 [b][H][n][16]      pre fwd out                     */
+    const void *dq, *dk, *dv;       /* bf16 [b][H][n][16]      pre bwd in                      */
+    float *dx;                      /* [b*n][dim]              pre bwd out                     */
+    float *d_ln_gamma, *d_wq, *d_wk, *d_wv;               /* += pre bwd                        */
+    const void *o;                  /* bf16 [b][H][n][16]      post fwd/bwd in                 */
+    const int32_t *lens;            /* [b]                     post                            */
+    float *y;                       /* [b*n][dim]              post fwd out                    */
+    const float *dy;                /* [b*n][dim]              post bwd in (dx of the residual path = dy) */
+    void *d_o;                      /* bf16 [b][H][n][16]      post bwd out                    */
+    float *d_wo;                    /* += post bwd                                             */
+} xtrl_attn_io;
+
+int64_t xtrl_attn_img_bytes(int32_t dim, int32_t heads, int32_t dim_head);   /* -1 if not built */
+int xtrl_attn_pack(const float *wq, const float *wk, const float *wv /*[H*16][dim]*/, const float *wo /*[dim][H*16]*/,
+                   void *img, int32_t dim, int32_t heads, int32_t dim_head, void *stream);
+int xtrl_attn_pre_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
+int xtrl_attn_pre_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
+int xtrl_attn_post_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
+int xtrl_attn_post_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

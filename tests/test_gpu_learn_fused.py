@@ -83,3 +83,116 @@ def test_ff_dropout_mask_is_shared_by_forward_and_backward():
         assert (mask_row - mask_row.round()).abs().max() < 0.02
         assert abs(float(mask_row.sum()) - float(kept[t0])) < 0.6
         assert float(gr[4][0]) == 1.                                 # db2 = sum of dy
+
+
+# ---------------------------------------------------------------------------------------------
+# whole learn step: the bf16 class with fused sub-layers against the fp32 class (torch expression, itself checked
+# gradient for gradient against the oracle in test_gpu_learner.py) on the same weights and the same minibatch
+# ---------------------------------------------------------------------------------------------
+
+def _learn_once(tmp_path, tag, mixed, fused, T=40, B=12):
+    from importlib import import_module
+    L = import_module('x-transformers-rl_b200.learner')
+    agent_mod = import_module('x-transformers-rl_b200.agent')
+    torch.manual_seed(3)
+    learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=T, batch_size=B, num_episodes_per_update=B,
+                        world_model=dict(attn_dim_head=16, heads=4, depth=2, attn_gate_values=True, add_value_residual=True,
+                                         learned_value_residual_mix=True), epochs=1,
+                        agent_kwargs=dict(save_path=str(tmp_path / f'{tag}.pt'), dropout=0.),
+                        accelerate_kwargs=dict(mixed_precision='bf16') if mixed else {})
+    agent, dev = learner.agent, learner.device
+    agent.fused_learn = fused
+    with torch.no_grad():
+        g0 = torch.Generator(device=dev).manual_seed(11)
+        agent.model.flat_params.add_(torch.randn(agent.model.flat_params.shape, generator=g0, device=dev) * 0.1)
+    g = torch.Generator().manual_seed(5)
+    buf = agent_mod.RolloutBuffer.allocate(T, B, 8, dev)
+    lens = torch.randint(T // 2, T + 1, (B,), generator=g).int()
+    tm_mask = torch.arange(T)[:, None] < lens[None, :]
+    data = dict(states=torch.randn(T, B, 8, generator=g), actions=torch.randint(0, 4, (T, B), generator=g).int(),
+                log_probs=-torch.rand(T, B, generator=g) * 1.5, rewards=torch.randn(T, B, generator=g),
+                values=torch.randn(T, B, generator=g), is_boundary=torch.rand(T, B, generator=g) < 0.05)
+    for k, v in data.items():
+        getattr(buf, k).copy_(torch.where(tm_mask if v.ndim == 2 else tm_mask[..., None], v, torch.zeros_like(v)))
+    buf.episode_lens.copy_(lens)
+    agent.keep_last_grads = True
+    torch.manual_seed(0)                                   # same reward-dropout flag in every variant
+    agent.learn(buf, fitnesses=None, permutations=[torch.arange(B)])
+    return agent.last_grads.clone(), agent.last_logs.clone(), agent.model._offsets, [n for n, _ in agent.model.named_parameters()]
+
+
+def test_fused_bf16_learn_step_tracks_fp32(tmp_path):
+    g32, s32, offs, names = _learn_once(tmp_path, 'f32', mixed=False, fused=False)
+    gfu, sfu, _, _ = _learn_once(tmp_path, 'fused', mixed=True, fused=True)
+    gun, sun, _, _ = _learn_once(tmp_path, 'unfused', mixed=True, fused=False)
+    assert abs(float(sfu[0] - s32[0])) < TOL_BF16 * abs(float(s32[0]))          # total loss, 1e-2 relative (bf16 class)
+    cos = lambda a, b: float(torch.dot(a, b) / (a.norm() * b.norm()))
+    assert cos(gfu, g32) > 0.999 and cos(gun, g32) > 0.999
+    err_fused, err_unfused = float((gfu - g32).norm() / g32.norm()), float((gun - g32).norm() / g32.norm())
+    assert err_fused < 3e-2, (err_fused, err_unfused)
+    assert err_fused < 1.5 * err_unfused + 5e-3, (err_fused, err_unfused)       # no worse than torch's own bf16 autocast path
+    for n, o0, o1 in zip(names, offs[:-1], offs[1:]):                            # and tensor by tensor on the fused sub-layers
+        if '.ff.' in n or ('layers.1.' in n or 'layers.3.' in n) and n.endswith('gamma'):
+            ref = g32[o0:o1]
+            assert float((gfu[o0:o1] - ref).abs().max() / ref.abs().max().clamp(min=1e-12)) < 5e-2, n
+
+
+# ---------------------------------------------------------------------------------------------
+# attention sub-layer around the core: pre (LN, q/k/v, rotary, head layout) and post (to_out, mask, residual)
+# ---------------------------------------------------------------------------------------------
+
+def _rotate_ref(t, cos, sin):
+    x, rest = t[..., :8], t[..., 8:]
+    pairs = x.unflatten(-1, (-1, 2))
+    half = torch.stack((-pairs[..., 1], pairs[..., 0]), dim=-1).flatten(-2)
+    return torch.cat((x * cos + half * sin, rest), dim=-1)
+
+
+def _tables(n):
+    inv_freq = 1. / (10000 ** (torch.arange(0, 8, 2).float() / 8))
+    ang = torch.arange(n, dtype=torch.float32)[:, None] * inv_freq[None]
+    return ang.cos().to(DEV).contiguous(), ang.sin().to(DEV).contiguous()
+
+
+@pytest.mark.parametrize('H,b,n', [(8, 3, 50), (4, 2, 77), (8, 5, 128), (8, 40, 500), (4, 1, 1)])
+def test_attn_pre_post_vs_torch(H, b, n):
+    ops = xtrl().ops
+    g = torch.Generator().manual_seed(H * 1000 + b * 10 + n)
+    I, D = 16 * H, 48
+    r = lambda *s, sc=1.: (torch.randn(*s, generator=g) * sc).to(DEV).requires_grad_()
+    gamma, wq, wk, wv, wo = r(D, sc=0.2), r(I, D, sc=D ** -0.5), r(I, D, sc=D ** -0.5), r(I, D, sc=D ** -0.5), r(D, I, sc=I ** -0.5)
+    with torch.no_grad():
+        gamma += 1.
+    x = (torch.randn(b, n, D, generator=g) * 1.3 + 0.2).to(DEV).requires_grad_()
+    cos, sin = _tables(n)
+    cos8, sin8 = cos.repeat_interleave(2, -1), sin.repeat_interleave(2, -1)
+    img = ops.attn_pack(wq.detach(), wk.detach(), wv.detach(), wo.detach())
+    # ---- pre ----
+    xn = F.layer_norm(x, (D,)) * gamma
+    split = lambda t: t.view(b, n, H, 16).transpose(1, 2)
+    q_ref, k_ref, v_ref = _rotate_ref(split(xn @ wq.T), cos8, sin8), _rotate_ref(split(xn @ wk.T), cos8, sin8), split(xn @ wv.T)
+    q, k, v = ops.attn_pre_fwd(x.detach(), gamma.detach(), img, cos, sin, H)
+    for got, ref in ((q, q_ref), (k, k_ref), (v, v_ref)):
+        assert maxrel(got.float(), ref.detach()) < TOL_BF16
+    dq, dk, dv = (torch.randn(b, H, n, 16, generator=g).to(DEV).bfloat16() for _ in range(3))
+    (q_ref * dq.float()).sum().add((k_ref * dk.float()).sum()).add((v_ref * dv.float()).sum()).backward()
+    gr = {k_: torch.zeros_like(t) for k_, t in dict(gamma=gamma, wq=wq, wk=wk, wv=wv).items()}
+    dx = ops.attn_pre_bwd(x.detach(), dq, dk, dv, gamma.detach(), img, cos, sin, gr['gamma'], gr['wq'], gr['wk'], gr['wv'])
+    assert maxrel(dx, x.grad) < TOL_BF16
+    for k_, t in dict(gamma=gamma, wq=wq, wk=wk, wv=wv).items():
+        assert maxrel(gr[k_], t.grad) < 2 * TOL_BF16, k_
+    # ---- post ----
+    x.grad = None
+    lens = torch.randint(1, n + 1, (b,), generator=g).int().to(DEV)
+    mask = torch.arange(n, device=DEV)[None, :] < lens[:, None]
+    o = torch.randn(b, H, n, 16, generator=g).to(DEV).bfloat16()
+    o32 = o.float().requires_grad_()
+    y_ref = x + (o32.transpose(1, 2).reshape(b, n, I) @ wo.T).masked_fill(~mask[..., None], 0.)
+    y = ops.attn_post_fwd(x.detach(), o, lens, img)
+    assert maxrel(y - x.detach(), (y_ref - x).detach()) < TOL_BF16
+    dy = torch.randn(b, n, D, generator=g).to(DEV)
+    y_ref.backward(dy)
+    d_wo = torch.zeros_like(wo)
+    d_o = ops.attn_post_bwd(dy, o, lens, img, d_wo)
+    assert maxrel(d_o.float(), o32.grad) < TOL_BF16
+    assert maxrel(d_wo, wo.grad) < 2 * TOL_BF16

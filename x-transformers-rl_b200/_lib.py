@@ -78,6 +78,11 @@ class FfIO(C.Structure):
         ('rng_key', C.c_uint32), ('dropout', c_f32)]
 
 
+class AttnIO(C.Structure):
+    _fields_ = [(n, c_vp) for n in ('x', 'ln_gamma', 'cos_tab', 'sin_tab', 'w_img', 'q', 'k', 'v', 'dq', 'dk', 'dv', 'dx',
+                                    'd_ln_gamma', 'd_wq', 'd_wk', 'd_wv', 'o', 'lens', 'y', 'dy', 'd_o', 'd_wo')]
+
+
 # every symbol include/xtrl.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'xtrl_abi_version': (c_i32, []),
@@ -100,6 +105,12 @@ SYMBOLS = {
     'xtrl_ff_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'xtrl_ff_fwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
     'xtrl_ff_bwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
+    'xtrl_attn_img_bytes': (c_i64, [c_i32, c_i32, c_i32]),
+    'xtrl_attn_pack': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_attn_pre_fwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_attn_pre_bwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_attn_post_fwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_attn_post_bwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
 }
 
 

@@ -7,6 +7,8 @@ reads), AdoptAtan2 state (three more flat buffers), RSNorm statistics and the ge
 """
 from __future__ import annotations
 
+import os
+
 from collections import namedtuple
 from dataclasses import dataclass
 from pathlib import Path
@@ -191,6 +193,9 @@ class Agent(nn.Module):
         self.last_logs = None
         self.keep_last_grads = False
         self.last_grads = None
+        # bf16 learn passes run the sequence model's sub-layers as fused tcgen05 kernels (csrc/learn_*.cu); the fp32 class
+        # keeps the exact torch expression.  XTRL_LEARN_FUSED=0 is the A/B switch for measurements.
+        self.fused_learn = self.accelerator.mixed_precision == 'bf16' and os.environ.get('XTRL_LEARN_FUSED', '1') != '0'
         self.use_cuda_graph_learn = True     # fwd + losses + bwd of a minibatch as one graph replay (launch-bound at small batches)
         self._learn_graphs = {}
 
@@ -303,7 +308,7 @@ class Agent(nn.Module):
         cast = (lambda t: t) if self.continuous_actions else (lambda t: t.long())
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.accelerator.mixed_precision == 'bf16'):
             ra, vl, spr, dl = model(packed[..., :S], packed[..., S], cast(prev_actions), cast(actions), mask,
-                                    latent_gene=gene, reward_flag=flag)
+                                    latent_gene=gene, reward_flag=flag, fused=self.fused_learn)
         loss, scalars = FusedPPOLoss.apply(self.loss_cfg, ra, vl, spr, dl, actions.contiguous(), mb['old_log_probs'].contiguous(),
                                            mb['returns'].contiguous(), mb['old_values'].contiguous(), packed.contiguous(),
                                            mb['dones'].contiguous(), lens.contiguous())

@@ -1,0 +1,49 @@
+// learn_common.cuh -- pieces shared by the learn-side fused sub-layer kernels (learn_ff.cu, learn_attn.cu):
+// 128-token tiles, thread (row, half) ownership, bf16 operand images, LayerNorm over D = 48 in registers.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace xtrl {
+namespace learn {
+
+constexpr int D = 48, TOK = 128, NT = 256;
+constexpr int kCore = TOK * 16;        // bytes between 8-feature chunks of a 128-token image
+constexpr uint32_t kIdA = 1u << 15, kIdB = 1u << 16;                 // MN-major operand flags of the idesc
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4 u, float (&o)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+// row statistics of LayerNorm over 48 fp32 values held in registers
+__device__ __forceinline__ void ln_stats(const float (&xr)[D], float &mean, float &rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s += xr[i];
+    mean = s * (1.f / D);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { const float d = xr[i] - mean; v = fmaf(d, d, v); }
+    rstd = rsqrtf(v * (1.f / D) + 1e-5f);
+}
+__device__ __forceinline__ void load_row(const float *p, bool ok, float (&xr)[D]) {
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+        const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(p) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
+    }
+}
+// 8 consecutive features of this thread's row -> one 16-byte piece of a 128-token image
+__device__ __forceinline__ void put8(unsigned char *img, int row, int chunk, const float (&v)[8]) {
+    *reinterpret_cast<uint4 *>(img + chunk * kCore + (row >> 3) * 128 + (row & 7) * 16) =
+        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+
+
+}  // namespace learn
+}  // namespace xtrl

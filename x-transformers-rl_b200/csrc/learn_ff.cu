@@ -20,28 +20,19 @@
 // HBM traffic per token: fwd 192 B read + 192 B written; bwd 384 B read + 192 B written (fp32 residual
 // stream); weights stay in shared memory for the life of the CTA.
 #include "common.cuh"
-#include "umma.cuh"
+#include "learn_common.cuh"
 
 namespace xtrl {
 namespace ff {
 using namespace umma;
+using namespace learn;
 
-constexpr int D = 48, F = 192, TOK = 128, NT = 256;
+constexpr int F = 192;
 constexpr int XW = 64;                 // Xn / dY image width: 48 features + a ones column (48) + zero pad
 constexpr int HW = 200;                // H image width: 192 features + a ones column (192) + zero pad
 constexpr int kW1 = F * D * 2;         // W1 image: rows = 192 outputs, K = 48
 constexpr int kW2 = D * F * 2;         // W2 image: rows = 48 outputs, K = 192
-constexpr int kCore = TOK * 16;        // bytes between 8-feature chunks of a 128-token image
 
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
-__device__ __forceinline__ void unpack8(const uint4 u, float (&o)[8]) {
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-}
 __device__ __forceinline__ void gelu_both(float x, float &g, float &dg) {
     const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
     g = x * cdf;
@@ -73,30 +64,6 @@ struct Args {
     float drop_scale;
     int N;
 };
-
-// row statistics of LayerNorm over 48 fp32 values held in registers
-__device__ __forceinline__ void ln_stats(const float (&xr)[D], float &mean, float &rstd) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < D; ++i) s += xr[i];
-    mean = s * (1.f / D);
-    float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < D; ++i) { const float d = xr[i] - mean; v = fmaf(d, d, v); }
-    rstd = rsqrtf(v * (1.f / D) + 1e-5f);
-}
-__device__ __forceinline__ void load_row(const float *p, bool ok, float (&xr)[D]) {
-#pragma unroll
-    for (int i = 0; i < D / 4; ++i) {
-        const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(p) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
-    }
-}
-// 8 consecutive features of this thread's row -> one 16-byte piece of a 128-token image
-__device__ __forceinline__ void put8(unsigned char *img, int row, int chunk, const float (&v)[8]) {
-    *reinterpret_cast<uint4 *>(img + chunk * kCore + (row >> 3) * 128 + (row & 7) * 16) =
-        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-}
 
 // ------------------------------------------------------------------------------------------ forward
 constexpr int kFwdSmem = kW1 + kW2 + TOK * D * 2 + TOK * F * 2 + (F + 2 * D) * 4 + 64;
@@ -213,7 +180,6 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
 // CTA, and the accumulator rows those bytes feed (>= 64, resp. > 64) are never read.
 constexpr int kBwdH = TOK * HW * 2, kBwdDP = TOK * F * 2, kBwdX = TOK * XW * 2;
 constexpr int kBwdSmem = kBwdH + kBwdDP + 2 * kBwdX + kW1 + kW2 + (F + D) * 4 + 64;
-constexpr uint32_t kIdA = 1u << 15, kIdB = 1u << 16;                 // MN-major operand flags of the idesc
 
 __global__ void __launch_bounds__(NT, 1) ff_bwd_kernel(const Args a) {
     extern __shared__ __align__(128) unsigned char smem[];

@@ -98,6 +98,27 @@ def _rotate(t, cos, sin, rot):
     return torch.cat((x * cos + half * sin, rest), dim=-1)
 
 
+class _FusedFeedForward(torch.autograd.Function):
+    """autograd seam around xtrl_ff_fwd / xtrl_ff_bwd (csrc/learn_ff.cu): x -> x + FF(LN(x)).  Only x is saved; the
+    backward recomputes on the tensor cores and ADDS the parameter gradients straight into the parameters' .grad
+    views of the flat gradient buffer (so the parameters are not autograd inputs here)."""
+
+    @staticmethod
+    def forward(ctx, x, norm, ff, img, rng_step, key, p_drop):
+        lin1, lin2 = ff.ff[0][0], ff.ff[2]
+        x = x.float().contiguous()
+        ctx.save_for_backward(x)
+        ctx.mods, ctx.img, ctx.rng = (norm, lin1, lin2), img, (rng_step, key, p_drop)
+        return ops.ff_fwd(x, norm.gamma.data, lin1.bias.data, lin2.bias.data, img, dropout=p_drop, rng_step=rng_step, rng_key=key)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,), (norm, lin1, lin2), (rng_step, key, p_drop) = ctx.saved_tensors, ctx.mods, ctx.rng
+        dx = ops.ff_bwd(x, dy.float().contiguous(), norm.gamma.data, lin1.bias.data, ctx.img, norm.gamma.grad, lin1.weight.grad,
+                        lin1.bias.grad, lin2.weight.grad, lin2.bias.grad, dropout=p_drop, rng_step=rng_step, rng_key=key)
+        return dx, None, None, None, None, None, None
+
+
 class WorldModelActorCritic(nn.Module):
     def __init__(self, cfg: ops.ModelConfig, dropout=0.25, frac_actor_critic_head_gradient=0.5, reward_dropout=0.5):
         super().__init__()
@@ -129,6 +150,18 @@ class WorldModelActorCritic(nn.Module):
             flat[o:o + p.numel()].copy_(p.data.reshape(-1))
         self._offsets = offs
         self._bind(flat, torch.zeros_like(flat))
+        self._fused = None                       # lazily built device state of the fused learn-side kernels
+
+    def fused_state(self):
+        """per-layer operand images + the dropout counter of the tcgen05 sub-layer kernels, or None when this
+        shape is not built (then the torch-op expression below runs)."""
+        if self._fused is None:
+            cfg, dev = self.cfg, self.flat_params.device
+            ok = dev.type == 'cuda' and ops.ff_supported(cfg.dim, 4 * cfg.dim)
+            self._fused = dict(ff_img=[torch.empty(ops.L.load().xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim), dtype=torch.uint8, device=dev)
+                                       for _ in range(cfg.depth)],
+                               rng_step=torch.zeros((), dtype=torch.int64, device=dev)) if ok else False
+        return self._fused or None
 
     def _bind(self, flat, flat_grad):
         self.flat_params, self.flat_grads = flat, flat_grad
@@ -151,7 +184,7 @@ class WorldModelActorCritic(nn.Module):
         return out
 
     # -- full-sequence forward (x_transformers_rl.py:479-559 with mask=, :928-935) ---------------
-    def forward(self, state, rewards, actions, next_actions, mask, latent_gene=None, reward_flag=1.):
+    def forward(self, state, rewards, actions, next_actions, mask, latent_gene=None, reward_flag=1., fused=False):
         """state (b,n,S) normalised; rewards (b,n) normalised prev rewards; actions (b,n) prev actions
         (-1 none; continuous: float (b,n,A), zeros for none); next_actions likewise; mask (b,n) bool.
         Returns raw head outputs: raw_actions (b,n,A | 2A), value_logits (b,n,K), state_pred_raw (b,n,2(S+1)),
@@ -170,6 +203,12 @@ class WorldModelActorCritic(nn.Module):
         # the causal flag alone reproduces the reference's key-padding + causal mask on valid rows, and
         # padded rows are zeroed after to_out exactly as the reference does (App. A.1) -- no mask tensor.
         first_v = None
+        fs = self.fused_state() if fused else None
+        if fs is not None:                        # bf16 operand images follow the current weights; one counter bump per pass
+            fs['rng_step'].add_(1)
+            for l in range(cfg.depth):
+                ff = dec.layers[2 * l + 1][1]
+                ops.ff_pack(ff.ff[0][0].weight.data, ff.ff[2].weight.data, out=fs['ff_img'][l])
         for l in range(cfg.depth):
             norm, attn = dec.layers[2 * l]
             xn = norm(x)
@@ -191,6 +230,9 @@ class WorldModelActorCritic(nn.Module):
             out = attn.to_out(out).masked_fill(~mask[..., None], 0.)
             x = x + out
             norm, ff = dec.layers[2 * l + 1]
+            if fs is not None:
+                x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)
+                continue
             hid = ff.ff[0](norm(x))
             hid = F.dropout(hid, p_drop, self.training)
             x = x + ff.ff[2](hid)

@@ -223,6 +223,74 @@ def ff_bwd(x, dy, ln_gamma, b1, img, d_ln_gamma, d_w1, d_b1, d_w2, d_b2, *, drop
     return dx
 
 
+def attn_supported(dim, heads, dim_head) -> bool:
+    return L.load().xtrl_attn_img_bytes(dim, heads, dim_head) > 0
+
+
+def attn_pack(wq, wk, wv, wo, out=None):
+    """bf16 operand images of to_q/to_k/to_v (H*16, dim) and to_out (dim, H*16); once per weight update."""
+    lib = L.load()
+    inner, dim = wq.shape
+    heads = inner // 16
+    nbytes = lib.xtrl_attn_img_bytes(dim, heads, 16)
+    if nbytes < 0:
+        raise L.XtrlError(f'attn_pack: dim={dim}, heads={heads} is not built')
+    out = torch.empty(nbytes, dtype=torch.uint8, device=wq.device) if out is None else out
+    f32 = torch.float32
+    L.check(lib.xtrl_attn_pack(_ptr(wq, f32, 'wq'), _ptr(wk, f32, 'wk'), _ptr(wv, f32, 'wv'), _ptr(wo, f32, 'wo'),
+                               _ptr(out, torch.uint8, 'img'), dim, heads, 16, _stream()), 'xtrl_attn_pack')
+    return out
+
+
+def attn_pre_fwd(x, ln_gamma, img, cos_tab, sin_tab, heads):
+    """x (b, n, dim) fp32 -> q, k, v bf16 (b, H, n, 16): LayerNorm, projections, partial rotary on q and k."""
+    lib = L.load()
+    b, n, _ = x.shape
+    qkv = torch.empty(3, b, heads, n, 16, dtype=torch.bfloat16, device=x.device)
+    f32 = torch.float32
+    io = L.AttnIO(x=_ptr(x, f32, 'x'), ln_gamma=_ptr(ln_gamma, f32, 'ln_gamma'), cos_tab=_ptr(cos_tab, f32, 'cos_tab'),
+                  sin_tab=_ptr(sin_tab, f32, 'sin_tab'), w_img=_ptr(img, torch.uint8, 'img'),
+                  q=_ptr(qkv[0]), k=_ptr(qkv[1]), v=_ptr(qkv[2]))
+    L.check(lib.xtrl_attn_pre_fwd(C.byref(io), b, n, heads, _stream()), 'xtrl_attn_pre_fwd')
+    return qkv[0], qkv[1], qkv[2]
+
+
+def attn_pre_bwd(x, dq, dk, dv, ln_gamma, img, cos_tab, sin_tab, d_ln_gamma, d_wq, d_wk, d_wv):
+    """dx of the LayerNorm -> projection path; parameter gradients accumulated (+=)."""
+    lib = L.load()
+    b, heads, n, _ = dq.shape
+    dx = torch.empty_like(x)
+    f32, bf = torch.float32, torch.bfloat16
+    io = L.AttnIO(x=_ptr(x, f32, 'x'), ln_gamma=_ptr(ln_gamma, f32, 'ln_gamma'), cos_tab=_ptr(cos_tab, f32, 'cos_tab'),
+                  sin_tab=_ptr(sin_tab, f32, 'sin_tab'), w_img=_ptr(img, torch.uint8, 'img'),
+                  dq=_ptr(dq, bf, 'dq'), dk=_ptr(dk, bf, 'dk'), dv=_ptr(dv, bf, 'dv'), dx=_ptr(dx, f32, 'dx'),
+                  d_ln_gamma=_ptr(d_ln_gamma, f32), d_wq=_ptr(d_wq, f32), d_wk=_ptr(d_wk, f32), d_wv=_ptr(d_wv, f32))
+    L.check(lib.xtrl_attn_pre_bwd(C.byref(io), b, n, heads, _stream()), 'xtrl_attn_pre_bwd')
+    return dx
+
+
+def attn_post_fwd(x, o, lens, img):
+    """y = x + mask * (o . Wo^T); x (b, n, dim) fp32, o (b, H, n, 16) bf16, lens (b,) int32."""
+    lib = L.load()
+    b, heads, n, _ = o.shape
+    y = torch.empty_like(x)
+    io = L.AttnIO(x=_ptr(x, torch.float32, 'x'), o=_ptr(o, torch.bfloat16, 'o'), lens=_ptr(lens, torch.int32, 'lens'),
+                  w_img=_ptr(img, torch.uint8, 'img'), y=_ptr(y, torch.float32, 'y'))
+    L.check(lib.xtrl_attn_post_fwd(C.byref(io), b, n, heads, _stream()), 'xtrl_attn_post_fwd')
+    return y
+
+
+def attn_post_bwd(dy, o, lens, img, d_wo):
+    """d_o (b, H, n, 16) bf16 of the output projection; d_wo accumulated (+=).  (dx of the residual path is dy.)"""
+    lib = L.load()
+    b, heads, n, _ = o.shape
+    d_o = torch.empty_like(o)
+    io = L.AttnIO(dy=_ptr(dy, torch.float32, 'dy'), o=_ptr(o, torch.bfloat16, 'o'), lens=_ptr(lens, torch.int32, 'lens'),
+                  w_img=_ptr(img, torch.uint8, 'img'), d_o=_ptr(d_o, torch.bfloat16, 'd_o'), d_wo=_ptr(d_wo, torch.float32, 'd_wo'))
+    L.check(lib.xtrl_attn_post_bwd(C.byref(io), b, n, heads, _stream()), 'xtrl_attn_post_bwd')
+    return d_o
+
+
 # --------------------------------------------------------------------------------------------
 # (1) rollout step
 # --------------------------------------------------------------------------------------------
