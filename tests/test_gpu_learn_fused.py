@@ -90,14 +90,13 @@ def test_ff_dropout_mask_is_shared_by_forward_and_backward():
 # gradient for gradient against the oracle in test_gpu_learner.py) on the same weights and the same minibatch
 # ---------------------------------------------------------------------------------------------
 
-def _learn_once(tmp_path, tag, mixed, fused, T=40, B=12):
+def _learn_once(tmp_path, tag, mixed, fused, wm, T=40, B=12):
     from importlib import import_module
     L = import_module('x-transformers-rl_b200.learner')
     agent_mod = import_module('x-transformers-rl_b200.agent')
     torch.manual_seed(3)
     learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=T, batch_size=B, num_episodes_per_update=B,
-                        world_model=dict(attn_dim_head=16, heads=4, depth=2, attn_gate_values=True, add_value_residual=True,
-                                         learned_value_residual_mix=True), epochs=1,
+                        world_model=wm, epochs=1,
                         agent_kwargs=dict(save_path=str(tmp_path / f'{tag}.pt'), dropout=0.),
                         accelerate_kwargs=dict(mixed_precision='bf16') if mixed else {})
     agent, dev = learner.agent, learner.device
@@ -121,10 +120,16 @@ def _learn_once(tmp_path, tag, mixed, fused, T=40, B=12):
     return agent.last_grads.clone(), agent.last_logs.clone(), agent.model._offsets, [n for n, _ in agent.model.named_parameters()]
 
 
-def test_fused_bf16_learn_step_tracks_fp32(tmp_path):
-    g32, s32, offs, names = _learn_once(tmp_path, 'f32', mixed=False, fused=False)
-    gfu, sfu, _, _ = _learn_once(tmp_path, 'fused', mixed=True, fused=True)
-    gun, sun, _, _ = _learn_once(tmp_path, 'unfused', mixed=True, fused=False)
+WM_LANDER = dict(attn_dim_head=16, heads=4, depth=2, attn_gate_values=True, add_value_residual=True, learned_value_residual_mix=True)
+WM_PLAIN8 = dict(attn_dim_head=16, heads=8, depth=2)        # the c3 block: fused attention projections + fused feed-forward
+WM_PLAIN4 = dict(attn_dim_head=16, heads=4, depth=1)        # the README block
+
+
+@pytest.mark.parametrize('wm', (WM_LANDER, WM_PLAIN8, WM_PLAIN4), ids=('lander', 'plain8', 'plain4'))
+def test_fused_bf16_learn_step_tracks_fp32(tmp_path, wm):
+    g32, s32, offs, names = _learn_once(tmp_path, 'f32', mixed=False, fused=False, wm=wm)
+    gfu, sfu, _, _ = _learn_once(tmp_path, 'fused', mixed=True, fused=True, wm=wm)
+    gun, sun, _, _ = _learn_once(tmp_path, 'unfused', mixed=True, fused=False, wm=wm)
     assert abs(float(sfu[0] - s32[0])) < TOL_BF16 * abs(float(s32[0]))          # total loss, 1e-2 relative (bf16 class)
     cos = lambda a, b: float(torch.dot(a, b) / (a.norm() * b.norm()))
     assert cos(gfu, g32) > 0.999 and cos(gun, g32) > 0.999
@@ -132,7 +137,9 @@ def test_fused_bf16_learn_step_tracks_fp32(tmp_path):
     assert err_fused < 3e-2, (err_fused, err_unfused)
     assert err_fused < 1.5 * err_unfused + 5e-3, (err_fused, err_unfused)       # no worse than torch's own bf16 autocast path
     for n, o0, o1 in zip(names, offs[:-1], offs[1:]):                            # and tensor by tensor on the fused sub-layers
-        if '.ff.' in n or ('layers.1.' in n or 'layers.3.' in n) and n.endswith('gamma'):
+        fused_attn = not wm.get('attn_gate_values') and ('.to_q.' in n or '.to_k.' in n or '.to_v.' in n or '.to_out.' in n or
+                                                         ('layers.0.' in n or 'layers.2.' in n) and n.endswith('gamma'))
+        if '.ff.' in n or ('layers.1.' in n or 'layers.3.' in n) and n.endswith('gamma') or fused_attn:
             ref = g32[o0:o1]
             assert float((gfu[o0:o1] - ref).abs().max() / ref.abs().max().clamp(min=1e-12)) < 5e-2, n
 

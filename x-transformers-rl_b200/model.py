@@ -119,6 +119,43 @@ class _FusedFeedForward(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+class _FusedAttnPre(torch.autograd.Function):
+    """x -> q, k, v (b, H, n, 16) bf16 through xtrl_attn_pre_fwd / _bwd (csrc/learn_attn.cu): LayerNorm, the three
+    projections, partial rotary, head-major layout.  Returns only the LayerNorm path's dx; the residual path of x is
+    autograd's.  Parameter gradients go straight into the flat gradient buffer, as in _FusedFeedForward."""
+
+    @staticmethod
+    def forward(ctx, x, norm, attn, img, cos, sin, heads):
+        x = x.float().contiguous()
+        ctx.save_for_backward(x)
+        ctx.mods, ctx.aux = (norm, attn), (img, cos, sin)
+        return ops.attn_pre_fwd(x, norm.gamma.data, img, cos, sin, heads)
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        (x,), (norm, attn), (img, cos, sin) = ctx.saved_tensors, ctx.mods, ctx.aux
+        dx = ops.attn_pre_bwd(x, dq.contiguous(), dk.contiguous(), dv.contiguous(), norm.gamma.data, img, cos, sin,
+                              norm.gamma.grad, attn.to_q.weight.grad, attn.to_k.weight.grad, attn.to_v.weight.grad)
+        return dx, None, None, None, None, None, None
+
+
+class _FusedAttnPost(torch.autograd.Function):
+    """(x, o) -> x + mask * to_out(o) through xtrl_attn_post_fwd / _bwd; o (b, H, n, 16) bf16 from the attention core."""
+
+    @staticmethod
+    def forward(ctx, x, o, attn, img, lens):
+        x, o = x.float().contiguous(), o.contiguous()
+        ctx.save_for_backward(o, lens)
+        ctx.attn, ctx.img = attn, img
+        return ops.attn_post_fwd(x, o, lens, img)
+
+    @staticmethod
+    def backward(ctx, dy):
+        o, lens = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        return dy, ops.attn_post_bwd(dy, o, lens, ctx.img, ctx.attn.to_out.weight.grad), None, None, None
+
+
 class WorldModelActorCritic(nn.Module):
     def __init__(self, cfg: ops.ModelConfig, dropout=0.25, frac_actor_critic_head_gradient=0.5, reward_dropout=0.5):
         super().__init__()
@@ -158,8 +195,12 @@ class WorldModelActorCritic(nn.Module):
         if self._fused is None:
             cfg, dev = self.cfg, self.flat_params.device
             ok = dev.type == 'cuda' and ops.ff_supported(cfg.dim, 4 * cfg.dim)
-            self._fused = dict(ff_img=[torch.empty(ops.L.load().xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim), dtype=torch.uint8, device=dev)
-                                       for _ in range(cfg.depth)],
+            u8 = lambda nbytes: [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(cfg.depth)]
+            lib = ops.L.load()
+            # the fused attention projections cover the plain block; value gates / value residual keep the torch ops
+            attn_ok = ok and not cfg.gate_values and not cfg.value_residual and ops.attn_supported(cfg.dim, cfg.heads, cfg.dim_head)
+            self._fused = dict(ff_img=u8(lib.xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim)),
+                               attn_img=u8(lib.xtrl_attn_img_bytes(cfg.dim, cfg.heads, cfg.dim_head)) if attn_ok else None,
                                rng_step=torch.zeros((), dtype=torch.int64, device=dev)) if ok else False
         return self._fused or None
 
@@ -209,8 +250,22 @@ class WorldModelActorCritic(nn.Module):
             for l in range(cfg.depth):
                 ff = dec.layers[2 * l + 1][1]
                 ops.ff_pack(ff.ff[0][0].weight.data, ff.ff[2].weight.data, out=fs['ff_img'][l])
+                if fs['attn_img'] is not None:
+                    at = dec.layers[2 * l][1]
+                    ops.attn_pack(at.to_q.weight.data, at.to_k.weight.data, at.to_v.weight.data, at.to_out.weight.data, out=fs['attn_img'][l])
+            if fs['attn_img'] is not None:
+                lens32 = mask.sum(dim=1, dtype=torch.int32)          # episodes are right-padded: mask == position < length
+                ang4 = ang[:, ::2].contiguous()
+                cos4, sin4 = ang4.cos(), ang4.sin()
         for l in range(cfg.depth):
             norm, attn = dec.layers[2 * l]
+            if fs is not None and fs['attn_img'] is not None:
+                q, k, v = _FusedAttnPre.apply(x, norm, attn, fs['attn_img'][l], cos4, sin4, h)
+                out = F.scaled_dot_product_attention(q, k, v, is_causal=True, dropout_p=p_drop)
+                x = _FusedAttnPost.apply(x, out, attn, fs['attn_img'][l], lens32)
+                norm, ff = dec.layers[2 * l + 1]
+                x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)
+                continue
             xn = norm(x)
             split = lambda t: t.view(b, n, h, dh).transpose(1, 2)
             q, k, v = split(attn.to_q(xn)), split(attn.to_k(xn)), split(attn.to_v(xn))
