@@ -325,6 +325,25 @@ int xtrl_attn_pre_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t head
 int xtrl_attn_post_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
 int xtrl_attn_post_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
 
+/*     attention core for dim_head = 16, n <= 512:  o = dropout(softmax(scale . q k^T + causal)) v  per (episode, head).
+ *     q, k, v, o, d_o, dq, dk, dv: bf16 [bh][n][16] (bh = episodes * heads); lse: fp32 [bh][n], natural-log
+ *     sum-exp of the scaled scores (written by fwd, read by bwd).  Deterministic (no atomics).               */
+typedef struct xtrl_attn_core_io {
+    const void *q, *k, *v;
+    const void *o, *d_o;            /* bwd in                                                 */
+    void *o_out;                    /* fwd out                                                */
+    void *dq, *dk, *dv;             /* bwd out                                                */
+    float *lse;
+    const int64_t *rng_step;        /* as in xtrl_ff_io                                       */
+    uint32_t rng_key;
+    float dropout;
+    float scale;                    /* dim_head^-1/2                                          */
+} xtrl_attn_core_io;
+
+int xtrl_attn_core_supported(int32_t n, int32_t dim_head);
+int xtrl_attn_core_fwd(const xtrl_attn_core_io *io, int32_t bh, int32_t n, int32_t dim_head, void *stream);
+int xtrl_attn_core_bwd(const xtrl_attn_core_io *io, int32_t bh, int32_t n, int32_t dim_head, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

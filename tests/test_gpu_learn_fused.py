@@ -203,3 +203,68 @@ def test_attn_pre_post_vs_torch(H, b, n):
     d_o = ops.attn_post_bwd(dy, o, lens, img, d_wo)
     assert maxrel(d_o.float(), o32.grad) < TOL_BF16
     assert maxrel(d_wo, wo.grad) < 2 * TOL_BF16
+
+
+# ---------------------------------------------------------------------------------------------
+# attention core (dim_head 16, causal, n <= 512)
+# ---------------------------------------------------------------------------------------------
+
+def _core_reference(q, k, v, keep=None, p=0.):
+    n = q.shape[-2]
+    s = (q @ k.transpose(-1, -2)) * 0.25
+    s = s.masked_fill(torch.ones(n, n, dtype=torch.bool, device=q.device).triu(1), float('-inf'))
+    a = s.softmax(-1)
+    if keep is not None:
+        a = a * keep / (1. - p)
+    return a @ v
+
+
+@pytest.mark.parametrize('b,H,n', [(1, 1, 1), (2, 4, 10), (1, 2, 127), (2, 1, 128), (1, 3, 129), (2, 8, 300), (3, 8, 500), (1, 2, 512)])
+def test_attn_core_vs_torch(b, H, n):
+    ops = xtrl().ops
+    g = torch.Generator().manual_seed(b * 100000 + H * 1000 + n)
+    q, k, v, d_o = ((torch.randn(b, H, n, 16, generator=g) * sc).to(DEV).bfloat16() for sc in (1.5, 1.5, 1., 1.))
+    q32, k32, v32 = (t.float().requires_grad_() for t in (q, k, v))
+    o_ref = _core_reference(q32, k32, v32)
+    o_ref.backward(d_o.float())
+    o, lse = ops.attn_core_fwd(q, k, v)
+    assert maxrel(o.float(), o_ref.detach()) < TOL_BF16
+    s = (q32 @ k32.transpose(-1, -2) * 0.25).masked_fill(torch.ones(n, n, dtype=torch.bool, device=DEV).triu(1), float('-inf'))
+    assert (lse - s.logsumexp(-1)).abs().max() < 2e-3
+    dq, dk, dv = ops.attn_core_bwd(q, k, v, o, lse, d_o)
+    for got, ref, name in ((dq, q32.grad, 'dq'), (dk, k32.grad, 'dk'), (dv, v32.grad, 'dv')):
+        assert maxrel(got.float(), ref) < 2 * TOL_BF16, (name, maxrel(got.float(), ref))
+
+
+def test_attn_core_dropout_mask_is_shared_and_unbiased():
+    """a one-hot dO on query q0 makes dV[:, 0] the dropped attention row of q0: that recovers the mask the backward
+    used; the forward and both gradients must then agree with a torch reference that applies the same mask."""
+    ops = xtrl().ops
+    b, H, n, p = 1, 2, 70, 0.25
+    g = torch.Generator().manual_seed(9)
+    q, k, v, d_o = ((torch.randn(b, H, n, 16, generator=g) * sc).to(DEV).bfloat16() for sc in (1., 1., 1., 1.))
+    step = torch.tensor(3, dtype=torch.int64, device=DEV)
+    kw = dict(dropout=p, rng_step=step, rng_key=2)
+    o, lse = ops.attn_core_fwd(q, k, v, **kw)
+    assert torch.equal(o, ops.attn_core_fwd(q, k, v, **kw)[0])
+    assert not torch.equal(o, ops.attn_core_fwd(q, k, v, dropout=p, rng_step=step + 1, rng_key=2)[0])
+    o_plain, lse_plain = ops.attn_core_fwd(q, k, v)
+    assert torch.equal(lse, lse_plain)                               # the normaliser ignores the mask
+    keep = torch.zeros(b, H, n, n, device=DEV)
+    a_plain = (q.float() @ k.float().transpose(-1, -2) * 0.25).masked_fill(torch.ones(n, n, dtype=torch.bool, device=DEV).triu(1), float('-inf')).softmax(-1)
+    for q0 in range(n):
+        one = torch.zeros(b, H, n, 16, device=DEV)
+        one[:, :, q0, 0] = 1.
+        _, _, dv = ops.attn_core_bwd(q, k, v, o, lse, one.bfloat16(), **kw)
+        keep[:, :, q0] = (dv[..., 0].float() > 0.5 * a_plain[:, :, q0] / (1 - p)).float() * (a_plain[:, :, q0] > 0)
+    causal = torch.ones(n, n, device=DEV).tril()
+    rate = float((keep * causal).sum() / (causal.sum() * b * H))
+    assert abs(rate - (1 - p)) < 0.03, rate
+    assert not torch.equal(keep[0, 0], keep[0, 1])                   # heads draw different masks
+    q32, k32, v32 = (t.float().requires_grad_() for t in (q, k, v))
+    o_ref = _core_reference(q32, k32, v32, keep=keep, p=p)
+    o_ref.backward(d_o.float())
+    assert maxrel(o.float(), o_ref.detach()) < TOL_BF16
+    dq, dk, dv = ops.attn_core_bwd(q, k, v, o, lse, d_o, **kw)
+    for got, ref, name in ((dq, q32.grad, 'dq'), (dk, k32.grad, 'dk'), (dv, v32.grad, 'dv')):
+        assert maxrel(got.float(), ref) < 2 * TOL_BF16, (name, maxrel(got.float(), ref))

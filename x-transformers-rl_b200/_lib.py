@@ -83,6 +83,11 @@ class AttnIO(C.Structure):
                                     'd_ln_gamma', 'd_wq', 'd_wk', 'd_wv', 'o', 'lens', 'y', 'dy', 'd_o', 'd_wo')]
 
 
+class AttnCoreIO(C.Structure):
+    _fields_ = [(n, c_vp) for n in ('q', 'k', 'v', 'o', 'd_o', 'o_out', 'dq', 'dk', 'dv', 'lse', 'rng_step')] + [
+        ('rng_key', C.c_uint32), ('dropout', c_f32), ('scale', c_f32)]
+
+
 # every symbol include/xtrl.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'xtrl_abi_version': (c_i32, []),
@@ -111,6 +116,9 @@ SYMBOLS = {
     'xtrl_attn_pre_bwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_post_fwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_post_bwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_attn_core_supported': (c_i32, [c_i32, c_i32]),
+    'xtrl_attn_core_fwd': (c_i32, [C.POINTER(AttnCoreIO), c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_attn_core_bwd': (c_i32, [C.POINTER(AttnCoreIO), c_i32, c_i32, c_i32, c_vp]),
 }
 
 

@@ -291,6 +291,39 @@ def attn_post_bwd(dy, o, lens, img, d_wo):
     return d_o
 
 
+def attn_core_supported(n, dim_head) -> bool:
+    return bool(L.load().xtrl_attn_core_supported(n, dim_head))
+
+
+def attn_core_fwd(q, k, v, *, dropout=0., rng_step=None, rng_key=0, scale=None):
+    """causal attention core, q/k/v (b, H, n, 16) bf16 -> o (b, H, n, 16) bf16, lse (b, H, n) fp32."""
+    lib = L.load()
+    b, heads, n, dh = q.shape
+    bf = torch.bfloat16
+    o = torch.empty_like(q)
+    lse = torch.empty(b, heads, n, dtype=torch.float32, device=q.device)
+    if dropout > 0. and rng_step is None:
+        raise L.XtrlError('attn_core_fwd: dropout needs the rng_step counter tensor')
+    io = L.AttnCoreIO(q=_ptr(q, bf, 'q'), k=_ptr(k, bf, 'k'), v=_ptr(v, bf, 'v'), o_out=_ptr(o), lse=_ptr(lse),
+                      rng_step=_ptr(rng_step, torch.int64, 'rng_step'), rng_key=rng_key, dropout=dropout,
+                      scale=dh ** -0.5 if scale is None else scale)
+    L.check(lib.xtrl_attn_core_fwd(C.byref(io), b * heads, n, dh, _stream()), 'xtrl_attn_core_fwd')
+    return o, lse
+
+
+def attn_core_bwd(q, k, v, o, lse, d_o, *, dropout=0., rng_step=None, rng_key=0, scale=None):
+    lib = L.load()
+    b, heads, n, dh = q.shape
+    bf = torch.bfloat16
+    dqkv = torch.empty(3, *q.shape, dtype=bf, device=q.device)
+    io = L.AttnCoreIO(q=_ptr(q, bf, 'q'), k=_ptr(k, bf, 'k'), v=_ptr(v, bf, 'v'), o=_ptr(o, bf, 'o'), d_o=_ptr(d_o, bf, 'd_o'),
+                      dq=_ptr(dqkv[0]), dk=_ptr(dqkv[1]), dv=_ptr(dqkv[2]), lse=_ptr(lse, torch.float32, 'lse'),
+                      rng_step=_ptr(rng_step, torch.int64, 'rng_step'), rng_key=rng_key, dropout=dropout,
+                      scale=dh ** -0.5 if scale is None else scale)
+    L.check(lib.xtrl_attn_core_bwd(C.byref(io), b * heads, n, dh, _stream()), 'xtrl_attn_core_bwd')
+    return dqkv[0], dqkv[1], dqkv[2]
+
+
 # --------------------------------------------------------------------------------------------
 # (1) rollout step
 # --------------------------------------------------------------------------------------------
