@@ -24,7 +24,7 @@ namespace core {
 using namespace umma;
 using learn::pack2;
 
-constexpr int R = 512, NTH = 512, DH = 16;
+constexpr int R = 512, NCOMP = 512, NTH = NCOMP + 32, DH = 16;      // 16 compute warps + one warp that only issues MMAs
 constexpr int kImg = R * DH * 2;              // one q / k / v / dO image: 2 chunks of 8 dims x 512 rows x 16 B
 constexpr int kChunk = R * 16;                // bytes between the two 8-dim chunks
 constexpr int kTileImg = 128 * 128 * 2;       // P / dS operand image of one tile
@@ -37,8 +37,8 @@ struct Args {
     __nv_bfloat16 *out, *dq, *dk, *dv;
     float *lse;
     const int64_t *rng_step;
-    uint32_t rng_key, drop_thr;
-    float drop_scale, scale;
+    uint32_t rng_key, drop_thr4;              // keep a score when its hash byte >= threshold (replicated x4); 0 = no dropout
+    float drop_scale, drop_log2scale, scale;
     int n;
 };
 
@@ -55,11 +55,9 @@ __device__ __forceinline__ uint32_t cta_key(const int64_t *rng_step, uint32_t ke
     const uint64_t s = (uint64_t)(rng_step ? *rng_step : 0) * 0x9E3779B97F4A7C15ull;
     return mix32((uint32_t)(s >> 32) ^ (uint32_t)s ^ (key * 0x632BE5ABu) ^ (bh * 0x9E3779B1u + 0x7F4A7C15u));
 }
-// keep factors of keys (key, key+1), key even, for query qrow
-__device__ __forceinline__ void drop2(uint32_t qrow, uint32_t key, uint32_t ckey, uint32_t thr, float scale, float &k0, float &k1) {
-    const uint32_t h = mix32((qrow * (uint32_t)(R / 2) + (key >> 1)) * 0x9E3779B1u ^ ckey);
-    k0 = (h & 0xffffu) >= thr ? scale : 0.f;
-    k1 = (h >> 16) >= thr ? scale : 0.f;
+// byte mask (0xFF = keep) of the four keys 4*g4 .. 4*g4+3 of query qrow: one hash, four 8-bit uniforms
+__device__ __forceinline__ uint32_t keep4(uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t thr4) {
+    return __vcmpgeu4(mix32((qrow * (uint32_t)(R / 4) + g4) * 0x9E3779B1u ^ ckey), thr4);
 }
 // [n][16] bf16 rows of one (episode, head) -> 512-row token-major image (rows >= n zero, up to `rows`)
 __device__ __forceinline__ void load_img(unsigned char *img, const __nv_bfloat16 *src, int n, int rows, int tid) {
@@ -69,35 +67,146 @@ __device__ __forceinline__ void load_img(unsigned char *img, const __nv_bfloat16
         *reinterpret_cast<uint4 *>(img + c * kChunk + (r >> 3) * 128 + (r & 7) * 16) = v;
     }
 }
-// 16 consecutive keys of this thread's query row -> two 16-byte pieces of a tile image
-__device__ __forceinline__ void put16(unsigned char *img, int row, int col0, const float (&v)[16]) {
-    unsigned char *p = img + (col0 >> 3) * kTCore + (row >> 3) * 128 + (row & 7) * 16;
-    *reinterpret_cast<uint4 *>(p) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-    *reinterpret_cast<uint4 *>(p + kTCore) = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+// NA arrays at once: every thread first issues all its 16-byte loads (2 per array), then stores them
+template <int NA>
+__device__ __forceinline__ void load_imgs(unsigned char *const (&img)[NA], const __nv_bfloat16 *const (&src)[NA], int n, int rows, int tid) {
+    uint4 v[NA][2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * NTH, r = i >> 1, c = i & 1;
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+            v[a][k] = (i < rows * 2 && r < n) ? __ldg(reinterpret_cast<const uint4 *>(src[a] + (size_t)r * DH) + c) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * NTH, r = i >> 1, c = i & 1;
+        if (i < rows * 2) {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) *reinterpret_cast<uint4 *>(img[a] + c * kChunk + (r >> 3) * 128 + (r & 7) * 16) = v[a][k];
+        }
+    }
 }
-// token-major 512-row image, 128-row tile t: as a K-major operand [128 x K=16] and as an MN-major operand [N=16 x K=128 tokens]
-__device__ __forceinline__ uint64_t desc_rows(const unsigned char *img, int t) { return smem_desc(img + t * 2048, kChunk, 128); }
-__device__ __forceinline__ uint64_t desc_cols(const unsigned char *img, int t, int s) { return smem_desc(img + t * 2048 + s * 256, 128, kChunk); }
+static_assert(2 * NTH >= 2 * R, "load_imgs covers an image in two passes");
+__device__ __forceinline__ float row_norm2(const unsigned char *img, int r) {
+    float x[8], y[8], s = 0.f;
+    learn::unpack8(*reinterpret_cast<const uint4 *>(img + (r >> 3) * 128 + (r & 7) * 16), x);
+    learn::unpack8(*reinterpret_cast<const uint4 *>(img + kChunk + (r >> 3) * 128 + (r & 7) * 16), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s = fmaf(x[j], x[j], fmaf(y[j], y[j], s));
+    return s;
+}
+// 16 consecutive keys of this thread's query row (already packed bf16 pairs) -> two 16-byte pieces of a tile image
+__device__ __forceinline__ void put16w(unsigned char *img, int row, int col0, const uint32_t (&w)[8]) {
+    unsigned char *p = img + (col0 >> 3) * kTCore + (row >> 3) * 128 + (row & 7) * 16;
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4 *>(p + kTCore) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+// Descriptors are built once per operand; every MMA then only adds a start-address offset (in 16-byte units) -- a
+// tcgen05.mma of these shapes costs ~48 cycles of issue, building a descriptor from a pointer costs about as much again.
+// token-major 512-row image: rows(t) = K-major operand [128 rows of tile t x K=16] (64-row key tiles: + kt * 64);
+// cols(t, s) = MN-major operand [N=16 x K = 16 tokens of step s of tile t]
+struct ImgDesc {
+    uint64_t rows, cols;
+    __device__ __forceinline__ explicit ImgDesc(const unsigned char *img) : rows(smem_desc(img, kChunk, 128)), cols(smem_desc(img, 128, kChunk)) {}
+};
+// step image [128 queries x 64 keys]: kmaj(s) = A operand [128 q x K = 16 keys of step s]; mnmaj(s) = A operand [M = keys x K = 16 queries of step s]
+struct StepDesc {
+    uint64_t kmaj, mnmaj;
+    __device__ __forceinline__ explicit StepDesc(const unsigned char *img) : kmaj(smem_desc(img, kTCore, 128)), mnmaj(smem_desc(img, 128, kTCore)) {}
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the 16 compute warps
+// this warp's part of a step image is written and its TMEM tile is read: tell the MMA warp (one arrival per warp)
+__device__ __forceinline__ void images_ready(uint64_t *bar, int lane) {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+// ---- step schedule ---------------------------------------------------------------------------------------
+// Scores are produced in steps of one [128 queries x 64 keys] tile.  A step is software-pipelined against the
+// tensor core: while the threads turn tile i into operand images, the MMAs that produce tile i+1.. and the
+// products of tile i-1 are in flight (rings of TMEM tiles, operand images and mbarriers).
+constexpr int KT = 64;                        // keys per step
+constexpr int kStepImg = 128 * KT * 2;        // P / dS operand image of one step (8 key chunks x 2048 B)
+
+// block-local first key of this thread's 16-key chunk relative to the query tile's first row (>= 0 only on the diagonal block)
+struct StepGeom { int qt, kt, keyb; bool diag; };
+__device__ __forceinline__ StepGeom geom(int qt, int kt, int c4) {
+    StepGeom g;
+    g.qt = qt; g.kt = kt; g.diag = (kt >> 1) == qt;
+    g.keyb = (kt - 2 * qt) * KT + c4 * 16;
+    return g;
+}
+
+// one 16-key chunk of the forward: P = 2^(s*sl2 + off) (dropout folded in), returns the chunk's row sum
+template <bool DIAG>
+__device__ __forceinline__ float fwd_chunk(uint32_t taddr, unsigned char *sP, int row, int col0, int keyb, float sl2, float off,
+                                           uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t thr4) {
+    uint32_t r[16], w[8];
+    tmem_ld16_issue(taddr, r);
+    tmem_ld_wait();
+    tmem_pin16(r);
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        float p0 = ex2(fmaf(__uint_as_float(r[j]), sl2, off)), p1 = ex2(fmaf(__uint_as_float(r[j + 1]), sl2, off));
+        if (DIAG) { p0 = keyb + j <= row ? p0 : 0.f; p1 = keyb + j + 1 <= row ? p1 : 0.f; }
+        l += p0 + p1;
+        w[j >> 1] = pack2(p0, p1);
+    }
+    if (thr4) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t m = keep4(qrow, g4 + g, ckey, thr4);
+            w[2 * g] &= __byte_perm(m, 0, 0x1100);
+            w[2 * g + 1] &= __byte_perm(m, 0, 0x3322);
+        }
+    }
+    put16w(sP, row, col0, w);
+    return l;
+}
 
 // -------------------------------------------------------------------------------------------- forward
-constexpr int kFwdSmem = 3 * kImg + kTileImg + 4 * 128 * 4 + 64;
+constexpr int kFwdSmem = 3 * kImg + 2 * kStepImg + 2 * 4 * 128 * 4 + R * 4 + 128;
+constexpr float kBoundMax = 40.f;             // use the norm bound instead of the exact row max while it is below this
 
 __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sQ = smem, *sK = sQ + kImg, *sV = sK + kImg, *sP = sV + kImg;
-    float *sRed = reinterpret_cast<float *>(sP + kTileImg);                 // [4][128]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sRed + 4 * 128);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bar + 1);
+    unsigned char *sQ = smem, *sK = sQ + kImg, *sV = sK + kImg, *sP = sV + kImg;              // sP: ring of 2 step images
+    float *sRed = reinterpret_cast<float *>(sP + 2 * kStepImg);             // [2][4][128]
+    float *sQn = sRed + 2 * 4 * 128;                                         // |q_row|^2
+    uint64_t *bS = reinterpret_cast<uint64_t *>(sQn + R), *bP = bS + 3, *bI = bP + 2;      // S tile ready (3), P.V done (2), image ready (2)
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bI + 2);
+    int *sMax = reinterpret_cast<int *>(tslot + 1);                          // [0] max |k|^2, [1] max |q|^2 (float bits)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q4 = warp & 3, c4 = warp >> 2, row = q4 * 32 + lane;
+    const int q4 = warp & 3, c4 = warp >> 2, row = q4 * 32 + lane;           // c4 == 4: the MMA warp
     const int bh = blockIdx.x, n = a.n, nt = (n + 127) >> 7;
-    constexpr uint32_t cS = 0, cO = 128;
-    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    constexpr uint32_t cS = 0, cO = 192;
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(&bS[i], 1);
+        mbar_init(&bI[0], NCOMP / 32); mbar_init(&bI[1], NCOMP / 32);
+        fence_mbar_init(); sMax[0] = 0; sMax[1] = 0;
+    }
     if (warp == 0) tmem_alloc(tslot, 256);
     const size_t base = (size_t)bh * n * DH;
-    load_img(sQ, a.q + base, n, nt * 128, tid);
-    load_img(sK, a.k + base, n, nt * 128, tid);
-    load_img(sV, a.v + base, n, nt * 128, tid);
+    {
+        unsigned char *const imgs[3] = {sQ, sK, sV};
+        const __nv_bfloat16 *const srcs[3] = {a.q + base, a.k + base, a.v + base};
+        load_imgs<3>(imgs, srcs, n, nt * 128, tid);
+    }
+    __syncthreads();
+    for (int r = tid; r < nt * 128 + 32; r += NTH) {                         // norms for the softmax shift bound (whole warps: shuffles)
+        const bool in = r < nt * 128;
+        const float qn = in ? row_norm2(sQ, r) : 0.f, kn = learn::warp_max_f(in ? row_norm2(sK, r) : 0.f), qm = learn::warp_max_f(qn);
+        if (in) sQn[r] = qn;
+        if (lane == 0) { atomicMax(&sMax[0], __float_as_int(kn)); atomicMax(&sMax[1], __float_as_int(qm)); }
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -105,122 +214,220 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q4 * 32) << 16);
     const uint32_t ckey = cta_key(a.rng_step, a.rng_key, (uint32_t)bh);
     const float sl2 = a.scale * kLog2e;
-    uint32_t ph = 0;
-    for (int qt = 0; qt < nt; ++qt) {
-        const int qrow = qt * 128 + row;
-        float m = -INFINITY;
-        for (int kt = 0; kt <= qt; ++kt) {                                   // pass A: exact row max
-            if (tid == 0) {
-                tc_fence_after();
-                mma_bf16_ss(tbase + cS, desc_rows(sQ, qt), desc_rows(sK, kt), idesc_bf16(128, 128), 0);
-                mma_commit(bar);
-            }
-            mbar_wait(bar, ph); ph ^= 1;
+    const float kmax2 = __int_as_float(sMax[0]);
+    const bool bounded = a.scale * sqrtf(kmax2 * __int_as_float(sMax[1])) <= kBoundMax;          // CTA-uniform
+    const int total = nt * (nt + 1);                                         // steps: sum over qt of 2 qt + 2
+    auto advance = [&](int &qt, int &kt) { if (++kt > 2 * qt + 1) { kt = 0; ++qt; } };
+    const ImgDesc dQ_(sQ), dK_(sK), dV_(sV);
+    const StepDesc dP0(sP), dP1(sP + kStepImg);
+    auto issue_s = [&](int qt, int kt, int buf, uint64_t *bar) {             // S tile = Q_qt K_kt^T (one thread)
+        mma_bf16_ss(tbase + cS + buf * KT, dQ_.rows + qt * 128, dK_.rows + kt * 64, idesc_bf16(128, KT), 0);
+        mma_commit(bar);
+    };
+    auto issue_pv = [&](int qt, int kt, int slot, uint64_t *bar) {           // O[qt & 1] (+)= P V_kt
+        const uint64_t pa = slot ? dP1.kmaj : dP0.kmaj, vb = dV_.cols + kt * 64;
+#pragma unroll
+        for (int s = 0; s < KT / 16; ++s)
+            mma_bf16_ss(tbase + cO + (qt & 1) * DH, pa + s * 256, vb + s * 16, idesc_bf16(128, DH) | kIdB, kt > 0 || s > 0);
+        mma_commit(bar);
+    };
+
+    if (warp == NCOMP / 32) {
+        // ---- MMA warp: keeps three S tiles in flight, turns every finished P image into O += P V ----
+        if (lane == 0) {
+            uint32_t phx = 0;
+            int iq = 0, ik = 0, qt = 0, kt = 0;
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float s[16];
-                tmem_ld16(tlane + cS + c4 * 32 + c * 16, s);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const bool valid = kt < qt || c4 * 32 + c * 16 + j <= row;
-                    m = fmaxf(m, valid ? s[j] : -INFINITY);
+            if (bounded) {
+                for (int i = 0; i < 3 && i < total; ++i) { issue_s(iq, ik, i, &bS[i]); advance(iq, ik); }
+                for (int i = 0; i < total; ++i) {
+                    mbar_wait(&bI[i & 1], (i >> 1) & 1);
+                    tc_fence_after();
+                    issue_pv(qt, kt, i & 1, &bP[i & 1]);
+                    if (i + 3 < total) { issue_s(iq, ik, i % 3, &bS[i % 3]); advance(iq, ik); }
+                    advance(qt, kt);
                 }
+            } else {
+                // exact-max fallback: per query tile one pass of S tiles for the max, then S / P.V one step at a time
+                for (int q = 0; q < nt; ++q) {
+                    for (int pass = 0; pass < 2; ++pass)
+                        for (int k = 0; k <= 2 * q + 1; ++k) {
+                            issue_s(q, k, 0, &bS[0]);
+                            mbar_wait(&bI[0], phx); phx ^= 1;                 // the compute warps are done with the S tile (and wrote P in pass 1)
+                            tc_fence_after();
+                            if (pass == 1) issue_pv(q, k, 0, &bP[0]);
+                        }
+                }
+            }
+        }
+    } else if (!bounded) {
+        // ---- compute warps, exact-max fallback (norm bound too loose to be a safe softmax shift; unpipelined) ----
+        uint32_t phs = 0, php = 0;
+        for (int qt = 0; qt < nt; ++qt) {
+            float m = -INFINITY;
+            for (int kt = 0; kt <= 2 * qt + 1; ++kt) {
+                mbar_wait(&bS[0], phs); phs ^= 1;
+                tc_fence_after();
+                float s[16];
+                tmem_ld16(tlane + cS + c4 * 16, s);
+                const int keyb = (kt - 2 * qt) * KT + c4 * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) m = fmaxf(m, keyb + j <= row ? s[j] : -INFINITY);
+                images_ready(&bI[0], lane);
+            }
+            sRed[c4 * 128 + row] = m;
+            csync();
+            m = fmaxf(fmaxf(sRed[row], sRed[128 + row]), fmaxf(sRed[256 + row], sRed[384 + row])) * a.scale;
+            csync();
+            const float off = a.drop_log2scale - m * kLog2e;
+            float l = 0.f;
+            for (int kt = 0; kt <= 2 * qt + 1; ++kt) {
+                mbar_wait(&bS[0], phs); phs ^= 1;
+                if (kt > 0 || qt > 0) { mbar_wait(&bP[0], php); php ^= 1; }   // the previous P.V has read the image
+                tc_fence_after();
+                const int keyb = (kt - 2 * qt) * KT + c4 * 16;
+                const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
+                if (keyb <= q4 * 32 + 31) l += fwd_chunk<true>(tlane + cS + c4 * 16, sP, row, c4 * 16, keyb, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_thr4);
+                else { const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; put16w(sP, row, c4 * 16, z); }
+                images_ready(&bI[0], lane);
+            }
+            sRed[c4 * 128 + row] = l;
+            csync();
+            mbar_wait(&bP[0], php);                                           // last P.V of the tile (parity consumed by the next tile's first wait)
+            tc_fence_after();
+            const int qrow = qt * 128 + row;
+            const float lt = ((sRed[row] + sRed[128 + row]) + (sRed[256 + row] + sRed[384 + row])) / a.drop_scale;
+            if (c4 < 2) {
+                float o[8];
+                tmem_ld8(tlane + cO + (qt & 1) * DH + c4 * 8, o);
+                const float inv = 1.f / lt;
+                if (qrow < n)
+                    *reinterpret_cast<uint4 *>(a.out + base + (size_t)qrow * DH + c4 * 8) =
+                        make_uint4(pack2(o[0] * inv, o[1] * inv), pack2(o[2] * inv, o[3] * inv), pack2(o[4] * inv, o[5] * inv), pack2(o[6] * inv, o[7] * inv));
+            } else if (c4 == 2 && qrow < n) {
+                a.lse[(size_t)bh * n + qrow] = m + __logf(lt);
             }
             tc_fence_before();
-            __syncthreads();
+            csync();
         }
-        sRed[c4 * 128 + row] = m;
-        __syncthreads();
-        m = fmaxf(fmaxf(sRed[row], sRed[128 + row]), fmaxf(sRed[256 + row], sRed[384 + row]));
-        const float ml2 = m * sl2;
-        float l = 0.f;
-        for (int kt = 0; kt <= qt; ++kt) {                                   // pass B: P, row sum, O += P V
-            if (tid == 0) {
-                tc_fence_after();
-                if (kt > 0) {
-#pragma unroll
-                    for (int s = 0; s < 8; ++s)
-                        mma_bf16_ss(tbase + cO, smem_desc(sP + s * 2 * kTCore, kTCore, 128), desc_cols(sV, kt - 1, s),
-                                    idesc_bf16(128, DH) | kIdB, kt > 1 || s > 0);
-                }
-                mma_bf16_ss(tbase + cS, desc_rows(sQ, qt), desc_rows(sK, kt), idesc_bf16(128, 128), 0);
-                mma_commit(bar);
-            }
-            mbar_wait(bar, ph); ph ^= 1;
+    } else {
+        // ---- compute warps, pipelined ----
+        auto row_shift = [&](int qt) -> float {                              // >= every scaled score of the row (Cauchy-Schwarz)
+            return a.scale * sqrtf(kmax2 * sQn[qt * 128 + row]) * 1.0002f + 1e-4f;
+        };
+        auto finalize = [&](int qt, float m, int wait_step) {                // O / l and logsumexp of query tile qt
+            if (wait_step >= 0) mbar_wait(&bP[wait_step & 1], (wait_step >> 1) & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int col0 = c4 * 32 + c * 16;
-                float s[16];
-                tmem_ld16(tlane + cS + col0, s);
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const bool v0 = kt < qt || col0 + j <= row, v1 = kt < qt || col0 + j + 1 <= row;
-                    float p0 = v0 ? ex2(fmaf(s[j], sl2, -ml2)) : 0.f, p1 = v1 ? ex2(fmaf(s[j + 1], sl2, -ml2)) : 0.f;
-                    l += p0 + p1;
-                    if (a.drop_thr) {
-                        float k0, k1;
-                        drop2((uint32_t)qrow, (uint32_t)(kt * 128 + col0 + j), ckey, a.drop_thr, a.drop_scale, k0, k1);
-                        p0 *= k0; p1 *= k1;
-                    }
-                    s[j] = p0; s[j + 1] = p1;
-                }
-                put16(sP, row, col0, s);
+            const int qrow = qt * 128 + row;
+            const float *red = sRed + (qt & 1) * 512;
+            const float l = ((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])) / a.drop_scale;
+            if (c4 < 2) {
+                float o[8];
+                tmem_ld8(tlane + cO + (qt & 1) * DH + c4 * 8, o);
+                const float inv = 1.f / l;
+                if (qrow < n)
+                    *reinterpret_cast<uint4 *>(a.out + base + (size_t)qrow * DH + c4 * 8) =
+                        make_uint4(pack2(o[0] * inv, o[1] * inv), pack2(o[2] * inv, o[3] * inv), pack2(o[4] * inv, o[5] * inv), pack2(o[6] * inv, o[7] * inv));
+            } else if (c4 == 2 && qrow < n) {
+                a.lse[(size_t)bh * n + qrow] = m + __logf(l);
             }
-            fence_proxy_async();
             tc_fence_before();
-            __syncthreads();
-        }
-        if (tid == 0) {
+        };
+        int qt = 0, kt = 0;
+        float m = row_shift(0), m_prev = 0.f, l = 0.f;
+        float off = a.drop_log2scale - m * kLog2e;
+        for (int i = 0; i < total; ++i) {
+            const int sb = i % 3, pb = i & 1;
+            mbar_wait(&bS[sb], (i / 3) & 1);
+            if (i >= 2) mbar_wait(&bP[pb], ((i - 2) >> 1) & 1);               // the P.V that read this image is done
             tc_fence_after();
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                mma_bf16_ss(tbase + cO, smem_desc(sP + s * 2 * kTCore, kTCore, 128), desc_cols(sV, qt, s),
-                            idesc_bf16(128, DH) | kIdB, qt > 0 || s > 0);
-            mma_commit(bar);
+            const StepGeom g = geom(qt, kt, c4);
+            const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
+            unsigned char *img = sP + pb * kStepImg;
+            if (!g.diag) l += fwd_chunk<false>(tlane + cS + sb * KT + c4 * 16, img, row, c4 * 16, 0, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_thr4);
+            else if (g.keyb <= q4 * 32 + 31) l += fwd_chunk<true>(tlane + cS + sb * KT + c4 * 16, img, row, c4 * 16, g.keyb, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_thr4);
+            else { const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; put16w(img, row, c4 * 16, z); }
+            images_ready(&bI[pb], lane);
+            const bool last_of_q = kt == 2 * qt + 1;
+            if (kt == 1 && qt > 0) finalize(qt - 1, m_prev, -1);              // one step late: its last P.V (step i-2) completed with the wait above
+            if (last_of_q) {
+                sRed[(qt & 1) * 512 + c4 * 128 + row] = l;
+                csync();                                                     // row sums of the four column quarters meet here
+                m_prev = m; l = 0.f;
+                if (qt + 1 < nt) { m = row_shift(qt + 1); off = a.drop_log2scale - m * kLog2e; }
+            }
+            advance(qt, kt);
         }
-        sRed[c4 * 128 + row] = l;
-        __syncthreads();
-        l = (sRed[row] + sRed[128 + row]) + (sRed[256 + row] + sRed[384 + row]);
-        mbar_wait(bar, ph); ph ^= 1;
-        tc_fence_after();
-        if (c4 < 2) {
-            float o[8];
-            tmem_ld8(tlane + cO + c4 * 8, o);
-            const float inv = 1.f / l;
-            if (qrow < n)
-                *reinterpret_cast<uint4 *>(a.out + base + (size_t)qrow * DH + c4 * 8) =
-                    make_uint4(pack2(o[0] * inv, o[1] * inv), pack2(o[2] * inv, o[3] * inv), pack2(o[4] * inv, o[5] * inv), pack2(o[6] * inv, o[7] * inv));
-        } else if (c4 == 2 && qrow < n) {
-            a.lse[(size_t)bh * n + qrow] = m * a.scale + __logf(l);
-        }
-        tc_fence_before();
-        __syncthreads();
+        finalize(nt - 1, m_prev, total - 1);
     }
+    __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
 // ------------------------------------------------------------------------------------------- backward
-constexpr int kBwdSmem = 4 * kImg + 2 * kTileImg + 2 * R * 4 + 64;
+// shared-memory order: the step images first -- dV / dK read them MN-major with M = 128 keys although a step holds
+// 64, so each read runs 16 KB past its image into the next one (the last into sQ); the accumulator rows those
+// bytes feed (TMEM lanes 64..127) are never read.
+constexpr int kBwdSmem = 4 * kStepImg + 4 * kImg + 2 * R * 4 + 128;
+
+// one 16-key chunk of the backward: P~ and dS' = P~ dP~ - P delta (the softmax scale is applied to dQ / dK at the end)
+template <bool DIAG>
+__device__ __forceinline__ void bwd_chunk(uint32_t ts, uint32_t tdp, unsigned char *sP, unsigned char *sdS, int row, int col0, int keyb,
+                                          float sl2, float off, float ndelta, uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t thr4) {
+    uint32_t rs[16], rd[16], wp[8], wd[8];
+    tmem_ld16_issue(ts, rs);
+    tmem_ld16_issue(tdp, rd);
+    tmem_ld_wait();
+    tmem_pin16(rs);
+    tmem_pin16(rd);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t m = thr4 ? keep4(qrow, g4 + g, ckey, thr4) : 0xffffffffu;
+        float pd[4], ds[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = 4 * g + i;
+            float ps = ex2(fmaf(__uint_as_float(rs[j]), sl2, off));          // P * drop_scale
+            if (DIAG) ps = keyb + j <= row ? ps : 0.f;
+            pd[i] = __uint_as_float(__float_as_uint(ps) & __byte_perm(m, 0, 0x1111 * i));
+            ds[i] = fmaf(pd[i], __uint_as_float(rd[j]), ps * ndelta);
+        }
+        wp[2 * g] = pack2(pd[0], pd[1]); wp[2 * g + 1] = pack2(pd[2], pd[3]);
+        wd[2 * g] = pack2(ds[0], ds[1]); wd[2 * g + 1] = pack2(ds[2], ds[3]);
+    }
+    put16w(sP, row, col0, wp);
+    put16w(sdS, row, col0, wd);
+}
+
+__device__ __forceinline__ void store_row16(__nv_bfloat16 *p, const float (&v)[16], float f) {
+    uint4 *dst = reinterpret_cast<uint4 *>(p);
+    dst[0] = make_uint4(pack2(v[0] * f, v[1] * f), pack2(v[2] * f, v[3] * f), pack2(v[4] * f, v[5] * f), pack2(v[6] * f, v[7] * f));
+    dst[1] = make_uint4(pack2(v[8] * f, v[9] * f), pack2(v[10] * f, v[11] * f), pack2(v[12] * f, v[13] * f), pack2(v[14] * f, v[15] * f));
+}
 
 __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sQ = smem, *sK = sQ + kImg, *sV = sK + kImg, *sdO = sV + kImg, *sP = sdO + kImg, *sdS = sP + kTileImg;
-    float *sL = reinterpret_cast<float *>(sdS + kTileImg), *sDelta = sL + R;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sDelta + R);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bar + 1);
+    unsigned char *sStep = smem;                                             // [2] x (P~ image, dS image)
+    unsigned char *sQ = sStep + 4 * kStepImg, *sK = sQ + kImg, *sV = sK + kImg, *sdO = sV + kImg;
+    float *sL = reinterpret_cast<float *>(sdO + kImg), *sDelta = sL + R;
+    uint64_t *bS = reinterpret_cast<uint64_t *>(sDelta + R), *bP = bS + 3, *bI = bP + 2;   // S / dP~ ready (ring of 3), products done, images ready (rings of 2)
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bI + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q4 = warp & 3, c4 = warp >> 2, row = q4 * 32 + lane;
+    const int q4 = warp & 3, c4 = warp >> 2, row = q4 * 32 + lane;           // c4 == 4: the MMA warp
     const int bh = blockIdx.x, n = a.n, nt = (n + 127) >> 7;
-    constexpr uint32_t cS = 0, cDP = 128, cDQ = 256, cDK = 320, cDV = 336;
-    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    constexpr uint32_t cS = 0, cDP = 192, cDQ = 384, cDK = 448, cDV = 480;    // S, dP~: rings of 3 x 64; dK, dV: two buffers of 16 columns
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(&bS[i], 1);
+        mbar_init(&bI[0], NCOMP / 32); mbar_init(&bI[1], NCOMP / 32);
+        fence_mbar_init();
+    }
     if (warp == 0) tmem_alloc(tslot, 512);
     const size_t base = (size_t)bh * n * DH;
-    load_img(sQ, a.q + base, n, nt * 128, tid);
-    load_img(sK, a.k + base, n, nt * 128, tid);
-    load_img(sV, a.v + base, n, nt * 128, tid);
-    load_img(sdO, a.d_o + base, n, nt * 128, tid);
+    {
+        unsigned char *const imgs[4] = {sQ, sK, sV, sdO};
+        const __nv_bfloat16 *const srcs[4] = {a.q + base, a.k + base, a.v + base, a.d_o + base};
+        load_imgs<4>(imgs, srcs, n, nt * 128, tid);
+    }
     for (int r = tid; r < nt * 128; r += NTH) {                              // delta = rowsum(dO . O); logsumexp in log2 units
         float d = 0.f, L = 1e30f;
         if (r < n) {
@@ -235,8 +442,8 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
             }
             L = a.lse[(size_t)bh * n + r] * kLog2e;
         }
-        sDelta[r] = d;
-        sL[r] = L;
+        sDelta[r] = -d / a.drop_scale;
+        sL[r] = a.drop_log2scale - L;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -245,103 +452,89 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q4 * 32) << 16);
     const uint32_t ckey = cta_key(a.rng_step, a.rng_key, (uint32_t)bh);
     const float sl2 = a.scale * kLog2e;
-    uint32_t ph = 0;
-    bool pending = false;                                                    // operand images of the previous pair are waiting for their MMAs
-    int pq = 0, pk = 0;
-    for (int kt = 0; kt < nt; ++kt) {
-        for (int qt = kt; qt < nt; ++qt) {
-            if (tid == 0) {
-                tc_fence_after();
-                if (pending) {
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const uint64_t pT = smem_desc(sP + s * 256, 128, kTCore), dsT = smem_desc(sdS + s * 256, 128, kTCore);
-                        mma_bf16_ss(tbase + cDV, pT, desc_cols(sdO, pq, s), idesc_bf16(128, DH) | kIdA | kIdB, pq > pk || s > 0);      // dV += P~^T dO
-                        mma_bf16_ss(tbase + cDK, dsT, desc_cols(sQ, pq, s), idesc_bf16(128, DH) | kIdA | kIdB, pq > pk || s > 0);      // dK += dS^T Q
-                        mma_bf16_ss(tbase + cDQ + pq * DH, smem_desc(sdS + s * 2 * kTCore, kTCore, 128), desc_cols(sK, pk, s),
-                                    idesc_bf16(128, DH) | kIdB, pk > 0 || s > 0);                                                        // dQ += dS K
-                    }
-                }
-                mma_bf16_ss(tbase + cS, desc_rows(sQ, qt), desc_rows(sK, kt), idesc_bf16(128, 128), 0);                                 // S = Q K^T
-                mma_bf16_ss(tbase + cDP, desc_rows(sdO, qt), desc_rows(sV, kt), idesc_bf16(128, 128), 0);                               // dP~ = dO V^T
+    const int total = nt * (nt + 1);                                         // steps: key tile kt (64 keys) x query tiles qt >= kt/2
+    auto advance = [&](int &kt, int &qt) { if (++qt >= nt) { ++kt; qt = kt >> 1; } };
+
+    if (warp == NCOMP / 32) {
+        // ---- MMA warp ----
+        if (lane == 0) {
+            const ImgDesc dQ_(sQ), dK_(sK), dV_(sV), dO_(sdO);
+            const StepDesc dP0(sStep), dS0(sStep + kStepImg), dP1(sStep + 2 * kStepImg), dS1(sStep + 3 * kStepImg);
+            auto issue_s = [&](int kt, int qt, int buf, uint64_t *bar) {     // S = Q K^T and dP~ = dO V^T of one step
+                mma_bf16_ss(tbase + cS + buf * KT, dQ_.rows + qt * 128, dK_.rows + kt * 64, idesc_bf16(128, KT), 0);
+                mma_bf16_ss(tbase + cDP + buf * KT, dO_.rows + qt * 128, dV_.rows + kt * 64, idesc_bf16(128, KT), 0);
                 mma_commit(bar);
-            }
-            mbar_wait(bar, ph); ph ^= 1;
+            };
+            int ik = 0, iq = 0, kt = 0, qt = 0;
             tc_fence_after();
-            if (pending && pq == nt - 1) {                                   // the previous key tile is complete: write its dK, dV
-                if (c4 < 2) {
-                    float v[16];
-                    tmem_ld16(tlane + (c4 == 0 ? cDK : cDV), v);
-                    const int krow = pk * 128 + row;
-                    if (krow < n) {
-                        uint4 *dst = reinterpret_cast<uint4 *>((c4 == 0 ? a.dk : a.dv) + base + (size_t)krow * DH);
-                        dst[0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-                        dst[1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-                    }
+            for (int i = 0; i < 3 && i < total; ++i) { issue_s(ik, iq, i, &bS[i]); advance(ik, iq); }
+            for (int i = 0; i < total; ++i) {
+                const int b = i & 1;
+                mbar_wait(&bI[b], (i >> 1) & 1);
+                tc_fence_after();
+                const StepDesc &dP = b ? dP1 : dP0, &dS = b ? dS1 : dS0;
+                const bool first_q = qt == (kt >> 1);
+                const uint64_t doc = dO_.cols + qt * 128, qc = dQ_.cols + qt * 128, kc = dK_.cols + kt * 64;
+                const uint32_t tdv = tbase + cDV + (kt & 1) * DH, tdk = tbase + cDK + (kt & 1) * DH, tdq = tbase + cDQ + qt * DH;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {                                 // K = 128 queries
+                    mma_bf16_ss(tdv, dP.mnmaj + s * 16, doc + s * 16, idesc_bf16(128, DH) | kIdA | kIdB, !first_q || s > 0);        // dV += P~^T dO
+                    mma_bf16_ss(tdk, dS.mnmaj + s * 16, qc + s * 16, idesc_bf16(128, DH) | kIdA | kIdB, !first_q || s > 0);         // dK += dS^T Q
                 }
+#pragma unroll
+                for (int s = 0; s < KT / 16; ++s)                             // K = 64 keys
+                    mma_bf16_ss(tdq, dS.kmaj + s * 256, kc + s * 16, idesc_bf16(128, DH) | kIdB, kt > 0 || s > 0);                  // dQ += dS K
+                mma_commit(&bP[b]);
+                if (i + 3 < total) { issue_s(ik, iq, i % 3, &bS[i % 3]); advance(ik, iq); }
+                advance(kt, qt);
             }
+        }
+    } else {
+        // ---- compute warps ----
+        auto write_dkv = [&](int kt) {                                       // dK, dV rows of key tile kt (lanes 0..63)
+            if (c4 < 2 && q4 < 2) {
+                float v[16];
+                tmem_ld16(tlane + (c4 == 0 ? cDK : cDV) + (kt & 1) * DH, v);
+                const int krow = kt * KT + row;
+                if (krow < n) store_row16((c4 == 0 ? a.dk : a.dv) + base + (size_t)krow * DH, v, c4 == 0 ? a.scale : 1.f);
+            }
+        };
+        int kt = 0, qt = 0, pend_kt = -1, pend_ready = 0;                     // a finished key tile whose dK, dV are still in TMEM
+        for (int i = 0; i < total; ++i) {
+            const int b = i & 1, sb = i % 3;
+            mbar_wait(&bS[sb], (i / 3) & 1);
+            if (i >= 2) mbar_wait(&bP[b], ((i - 2) >> 1) & 1);                // the products that read these images are done
+            tc_fence_after();
+            if (pend_kt >= 0 && i >= pend_ready + 2) { write_dkv(pend_kt); pend_kt = -1; }    // products(pend_ready) completed with the wait above
+            if (qt == (kt >> 1) && kt > 0) { pend_kt = kt - 1; pend_ready = i - 1; }             // written two steps after its last product: no drain
+            unsigned char *imgP = sStep + b * 2 * kStepImg, *imgS = imgP + kStepImg;
+            const StepGeom g = geom(qt, kt, c4);
             const int qrow = qt * 128 + row;
-            const float Lq = sL[qrow], delta = sDelta[qrow];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int col0 = c4 * 32 + c * 16;
-                float s[16], dp[16];
-                tmem_ld16(tlane + cS + col0, s);
-                tmem_ld16(tlane + cDP + col0, dp);
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const bool v0 = kt < qt || col0 + j <= row, v1 = kt < qt || col0 + j + 1 <= row;
-                    const float p0 = v0 ? ex2(fmaf(s[j], sl2, -Lq)) : 0.f, p1 = v1 ? ex2(fmaf(s[j + 1], sl2, -Lq)) : 0.f;
-                    float k0 = 1.f, k1 = 1.f;
-                    if (a.drop_thr) drop2((uint32_t)qrow, (uint32_t)(kt * 128 + col0 + j), ckey, a.drop_thr, a.drop_scale, k0, k1);
-                    s[j] = p0 * k0; s[j + 1] = p1 * k1;
-                    dp[j] = p0 * (dp[j] * k0 - delta) * a.scale;
-                    dp[j + 1] = p1 * (dp[j + 1] * k1 - delta) * a.scale;
-                }
-                put16(sP, row, col0, s);
-                put16(sdS, row, col0, dp);
+            const float off = sL[qrow], ndelta = sDelta[qrow];
+            const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
+            const uint32_t ts = tlane + cS + sb * KT + c4 * 16, tdp = tlane + cDP + sb * KT + c4 * 16;
+            if (!g.diag) bwd_chunk<false>(ts, tdp, imgP, imgS, row, c4 * 16, 0, sl2, off, ndelta, (uint32_t)qrow, g4, ckey, a.drop_thr4);
+            else if (g.keyb <= q4 * 32 + 31) bwd_chunk<true>(ts, tdp, imgP, imgS, row, c4 * 16, g.keyb, sl2, off, ndelta, (uint32_t)qrow, g4, ckey, a.drop_thr4);
+            else {
+                const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                put16w(imgP, row, c4 * 16, z);
+                put16w(imgS, row, c4 * 16, z);
             }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();
-            pending = true; pq = qt; pk = kt;
+            images_ready(&bI[b], lane);
+            advance(kt, qt);
         }
-    }
-    if (tid == 0) {                                                          // the last pair's products
+        mbar_wait(&bP[(total - 1) & 1], ((total - 1) >> 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const uint64_t pT = smem_desc(sP + s * 256, 128, kTCore), dsT = smem_desc(sdS + s * 256, 128, kTCore);
-            mma_bf16_ss(tbase + cDV, pT, desc_cols(sdO, pq, s), idesc_bf16(128, DH) | kIdA | kIdB, pq > pk || s > 0);
-            mma_bf16_ss(tbase + cDK, dsT, desc_cols(sQ, pq, s), idesc_bf16(128, DH) | kIdA | kIdB, pq > pk || s > 0);
-            mma_bf16_ss(tbase + cDQ + pq * DH, smem_desc(sdS + s * 2 * kTCore, kTCore, 128), desc_cols(sK, pk, s),
-                        idesc_bf16(128, DH) | kIdB, pk > 0 || s > 0);
+        if (pend_kt >= 0) write_dkv(pend_kt);
+        write_dkv(2 * nt - 1);
+        if (c4 < nt) {                                                       // dQ of query tile c4
+            float v[16];
+            tmem_ld16(tlane + cDQ + c4 * DH, v);
+            const int qrow = c4 * 128 + row;
+            if (qrow < n) store_row16(a.dq + base + (size_t)qrow * DH, v, a.scale);
         }
-        mma_commit(bar);
+        tc_fence_before();
     }
-    mbar_wait(bar, ph); ph ^= 1;
-    tc_fence_after();
-    if (c4 < 2) {
-        float v[16];
-        tmem_ld16(tlane + (c4 == 0 ? cDK : cDV), v);
-        const int krow = pk * 128 + row;
-        if (krow < n) {
-            uint4 *dst = reinterpret_cast<uint4 *>((c4 == 0 ? a.dk : a.dv) + base + (size_t)krow * DH);
-            dst[0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-            dst[1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-        }
-    }
-    if (c4 < nt) {                                                           // dQ of query tile c4
-        float v[16];
-        tmem_ld16(tlane + cDQ + c4 * DH, v);
-        const int qrow = c4 * 128 + row;
-        if (qrow < n) {
-            uint4 *dst = reinterpret_cast<uint4 *>(a.dq + base + (size_t)qrow * DH);
-            dst[0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-            dst[1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-        }
-    }
-    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
@@ -354,8 +547,10 @@ static int fill(const xtrl_attn_core_io *io, int32_t n, int32_t dim_head, Args &
     a.out = static_cast<__nv_bfloat16 *>(io->o_out); a.dq = static_cast<__nv_bfloat16 *>(io->dq); a.dk = static_cast<__nv_bfloat16 *>(io->dk);
     a.dv = static_cast<__nv_bfloat16 *>(io->dv); a.lse = io->lse;
     a.rng_step = io->rng_step; a.rng_key = io->rng_key;
-    a.drop_thr = (uint32_t)(io->dropout * 65536.f + 0.5f);
-    a.drop_scale = 1.f / (1.f - (float)a.drop_thr / 65536.f);
+    const uint32_t thr = (uint32_t)(io->dropout * 256.f + 0.5f);              // the drop probability is quantised to 1/256
+    a.drop_thr4 = thr * 0x01010101u;
+    a.drop_scale = 1.f / (1.f - (float)thr / 256.f);
+    a.drop_log2scale = log2f(a.drop_scale);
     a.scale = io->scale; a.n = n;
     return XTRL_OK;
 }

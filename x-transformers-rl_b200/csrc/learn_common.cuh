@@ -45,5 +45,11 @@ __device__ __forceinline__ void put8(unsigned char *img, int row, int chunk, con
 }
 
 
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 }  // namespace learn
 }  // namespace xtrl

@@ -14,6 +14,8 @@ kernel, the EMA copy and the NCCL gradient all-reduce each touch a single contig
 from __future__ import annotations
 
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -139,6 +141,24 @@ class _FusedAttnPre(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+class _FusedAttnCore(torch.autograd.Function):
+    """causal softmax(q k^T / 4) v with attention dropout for dim_head 16, n <= 512 (csrc/learn_attn_core.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, rng_step, key, p_drop):
+        o, lse = ops.attn_core_fwd(q, k, v, dropout=p_drop, rng_step=rng_step, rng_key=key)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.rng = (rng_step, key, p_drop)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse = ctx.saved_tensors
+        rng_step, key, p_drop = ctx.rng
+        dq, dk, dv = ops.attn_core_bwd(q, k, v, o, lse, d_o.contiguous(), dropout=p_drop, rng_step=rng_step, rng_key=key)
+        return dq, dk, dv, None, None, None
+
+
 class _FusedAttnPost(torch.autograd.Function):
     """(x, o) -> x + mask * to_out(o) through xtrl_attn_post_fwd / _bwd; o (b, H, n, 16) bf16 from the attention core."""
 
@@ -254,6 +274,7 @@ class WorldModelActorCritic(nn.Module):
                     at = dec.layers[2 * l][1]
                     ops.attn_pack(at.to_q.weight.data, at.to_k.weight.data, at.to_v.weight.data, at.to_out.weight.data, out=fs['attn_img'][l])
             if fs['attn_img'] is not None:
+                fs['core'] = ops.attn_core_supported(n, dh) and os.environ.get('XTRL_LEARN_CORE', '1') != '0'
                 lens32 = mask.sum(dim=1, dtype=torch.int32)          # episodes are right-padded: mask == position < length
                 ang4 = ang[:, ::2].contiguous()
                 cos4, sin4 = ang4.cos(), ang4.sin()
@@ -261,7 +282,10 @@ class WorldModelActorCritic(nn.Module):
             norm, attn = dec.layers[2 * l]
             if fs is not None and fs['attn_img'] is not None:
                 q, k, v = _FusedAttnPre.apply(x, norm, attn, fs['attn_img'][l], cos4, sin4, h)
-                out = F.scaled_dot_product_attention(q, k, v, is_causal=True, dropout_p=p_drop)
+                if fs['core']:
+                    out = _FusedAttnCore.apply(q, k, v, fs['rng_step'], 1000 + l, p_drop)
+                else:
+                    out = F.scaled_dot_product_attention(q, k, v, is_causal=True, dropout_p=p_drop)
                 x = _FusedAttnPost.apply(x, out, attn, fs['attn_img'][l], lens32)
                 norm, ff = dec.layers[2 * l + 1]
                 x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)
