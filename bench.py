@@ -344,8 +344,11 @@ def run_b200(args, w):
         lms, processed = timed(lambda: agent.learn(buf), 1)
         result['learn'] = dict(metric='PPO learn-timesteps/sec', value=world * processed / (lms / 1e3), unit='timesteps/s',
                                epochs=args.learn_epochs, minibatch_episodes=w['learn_batch'], ms=lms, dtype=args.learn_dtype,
-                               note='sequence model fwd/bwd = torch ops (SURVEY 8f-1 next); GAE, fused loss fwd+bwd, '
-                                    'optimiser+EMA = libxtrl kernels; one flat-gradient all-reduce per optimiser step')
+                               fused_sequence_model=bool(agent.fused_learn and agent.model.fused_state() is not None),
+                               note='bf16 class: sequence-model layers = libxtrl tcgen05 kernels (LN+QKV+rotary, causal attention core '
+                                    'with dropout, out-proj+mask+residual, LN+FF+GELU+dropout+residual; fwd and bwd, SURVEY 8f-1); embeddings '
+                                    'and the four heads = torch ops; GAE, fused loss fwd+bwd, optimiser+EMA = libxtrl kernels; one '
+                                    'flat-gradient all-reduce per optimiser step')
 
     # ---- gene pool (evolutionary workloads): evolve_ launch + the cross-rank fitness gather ----------------------
     if evolutionary:

@@ -37,7 +37,7 @@ struct Args {
     __nv_bfloat16 *out, *dq, *dk, *dv;
     float *lse;
     const int64_t *rng_step;
-    uint32_t rng_key, drop_thr4;              // keep a score when its hash byte >= threshold (replicated x4); 0 = no dropout
+    uint32_t rng_key, drop_add4;              // (128 - threshold) replicated in 4 bytes, see keep4(); 0 = no dropout
     float drop_scale, drop_log2scale, scale;
     int n;
 };
@@ -55,9 +55,19 @@ __device__ __forceinline__ uint32_t cta_key(const int64_t *rng_step, uint32_t ke
     const uint64_t s = (uint64_t)(rng_step ? *rng_step : 0) * 0x9E3779B97F4A7C15ull;
     return mix32((uint32_t)(s >> 32) ^ (uint32_t)s ^ (key * 0x632BE5ABu) ^ (bh * 0x9E3779B1u + 0x7F4A7C15u));
 }
-// byte mask (0xFF = keep) of the four keys 4*g4 .. 4*g4+3 of query qrow: one hash, four 8-bit uniforms
-__device__ __forceinline__ uint32_t keep4(uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t thr4) {
-    return __vcmpgeu4(mix32((qrow * (uint32_t)(R / 4) + g4) * 0x9E3779B1u ^ ckey), thr4);
+// Dropout decisions of the four keys 4*g4 .. 4*g4+3 of query qrow: one hash -> four 7-bit uniforms u; the sign bit of
+// byte j of the result is set <=> u_j >= threshold <=> keep.  hseed = (qrow * R/4 + first g4 of the chunk) * golden + CTA key;
+// add4 = (128 - threshold) in every byte.  PRMT's sign-replicate selectors (8 | byte) turn the sign bits into masks.
+constexpr uint32_t kGolden = 0x9E3779B1u;
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {          // PTX prmt (default mode): selector bit 3 = replicate the sign
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t keep4(uint32_t hseed, int g, uint32_t add4) {
+    uint32_t h = hseed + (uint32_t)g * kGolden;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 15;
+    return (h & 0x7f7f7f7fu) + add4;
 }
 // [n][16] bf16 rows of one (episode, head) -> 512-row token-major image (rows >= n zero, up to `rows`)
 __device__ __forceinline__ void load_img(unsigned char *img, const __nv_bfloat16 *src, int n, int rows, int tid) {
@@ -147,7 +157,7 @@ __device__ __forceinline__ StepGeom geom(int qt, int kt, int c4) {
 // one 16-key chunk of the forward: P = 2^(s*sl2 + off) (dropout folded in), returns the chunk's row sum
 template <bool DIAG>
 __device__ __forceinline__ float fwd_chunk(uint32_t taddr, unsigned char *sP, int row, int col0, int keyb, float sl2, float off,
-                                           uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t thr4) {
+                                           uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t add4) {
     uint32_t r[16], w[8];
     tmem_ld16_issue(taddr, r);
     tmem_ld_wait();
@@ -160,12 +170,13 @@ __device__ __forceinline__ float fwd_chunk(uint32_t taddr, unsigned char *sP, in
         l += p0 + p1;
         w[j >> 1] = pack2(p0, p1);
     }
-    if (thr4) {
+    if (add4) {
+        const uint32_t hseed = (qrow * (uint32_t)(R / 4) + g4) * kGolden + ckey;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            const uint32_t m = keep4(qrow, g4 + g, ckey, thr4);
-            w[2 * g] &= __byte_perm(m, 0, 0x1100);
-            w[2 * g + 1] &= __byte_perm(m, 0, 0x3322);
+            const uint32_t t = keep4(hseed, g, add4);
+            w[2 * g] &= prmt(t, 0x9988);
+            w[2 * g + 1] &= prmt(t, 0xbbaa);
         }
     }
     put16w(sP, row, col0, w);
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
                 tc_fence_after();
                 const int keyb = (kt - 2 * qt) * KT + c4 * 16;
                 const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
-                if (keyb <= q4 * 32 + 31) l += fwd_chunk<true>(tlane + cS + c4 * 16, sP, row, c4 * 16, keyb, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_thr4);
+                if (keyb <= q4 * 32 + 31) l += fwd_chunk<true>(tlane + cS + c4 * 16, sP, row, c4 * 16, keyb, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_add4);
                 else { const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; put16w(sP, row, c4 * 16, z); }
                 images_ready(&bI[0], lane);
             }
@@ -344,8 +355,8 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
             const StepGeom g = geom(qt, kt, c4);
             const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
             unsigned char *img = sP + pb * kStepImg;
-            if (!g.diag) l += fwd_chunk<false>(tlane + cS + sb * KT + c4 * 16, img, row, c4 * 16, 0, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_thr4);
-            else if (g.keyb <= q4 * 32 + 31) l += fwd_chunk<true>(tlane + cS + sb * KT + c4 * 16, img, row, c4 * 16, g.keyb, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_thr4);
+            if (!g.diag) l += fwd_chunk<false>(tlane + cS + sb * KT + c4 * 16, img, row, c4 * 16, 0, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_add4);
+            else if (g.keyb <= q4 * 32 + 31) l += fwd_chunk<true>(tlane + cS + sb * KT + c4 * 16, img, row, c4 * 16, g.keyb, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_add4);
             else { const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; put16w(img, row, c4 * 16, z); }
             images_ready(&bI[pb], lane);
             const bool last_of_q = kt == 2 * qt + 1;
@@ -373,23 +384,24 @@ constexpr int kBwdSmem = 4 * kStepImg + 4 * kImg + 2 * R * 4 + 128;
 // one 16-key chunk of the backward: P~ and dS' = P~ dP~ - P delta (the softmax scale is applied to dQ / dK at the end)
 template <bool DIAG>
 __device__ __forceinline__ void bwd_chunk(uint32_t ts, uint32_t tdp, unsigned char *sP, unsigned char *sdS, int row, int col0, int keyb,
-                                          float sl2, float off, float ndelta, uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t thr4) {
+                                          float sl2, float off, float ndelta, uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t add4) {
     uint32_t rs[16], rd[16], wp[8], wd[8];
     tmem_ld16_issue(ts, rs);
     tmem_ld16_issue(tdp, rd);
     tmem_ld_wait();
     tmem_pin16(rs);
     tmem_pin16(rd);
+    const uint32_t hseed = (qrow * (uint32_t)(R / 4) + g4) * kGolden + ckey;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        const uint32_t m = thr4 ? keep4(qrow, g4 + g, ckey, thr4) : 0xffffffffu;
+        const uint32_t t = add4 ? keep4(hseed, g, add4) : 0x80808080u;
         float pd[4], ds[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int j = 4 * g + i;
             float ps = ex2(fmaf(__uint_as_float(rs[j]), sl2, off));          // P * drop_scale
             if (DIAG) ps = keyb + j <= row ? ps : 0.f;
-            pd[i] = __uint_as_float(__float_as_uint(ps) & __byte_perm(m, 0, 0x1111 * i));
+            pd[i] = __uint_as_float(__float_as_uint(ps) & prmt(t, 0x8888 + 0x1111 * i));
             ds[i] = fmaf(pd[i], __uint_as_float(rd[j]), ps * ndelta);
         }
         wp[2 * g] = pack2(pd[0], pd[1]); wp[2 * g + 1] = pack2(pd[2], pd[3]);
@@ -513,8 +525,8 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
             const float off = sL[qrow], ndelta = sDelta[qrow];
             const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
             const uint32_t ts = tlane + cS + sb * KT + c4 * 16, tdp = tlane + cDP + sb * KT + c4 * 16;
-            if (!g.diag) bwd_chunk<false>(ts, tdp, imgP, imgS, row, c4 * 16, 0, sl2, off, ndelta, (uint32_t)qrow, g4, ckey, a.drop_thr4);
-            else if (g.keyb <= q4 * 32 + 31) bwd_chunk<true>(ts, tdp, imgP, imgS, row, c4 * 16, g.keyb, sl2, off, ndelta, (uint32_t)qrow, g4, ckey, a.drop_thr4);
+            if (!g.diag) bwd_chunk<false>(ts, tdp, imgP, imgS, row, c4 * 16, 0, sl2, off, ndelta, (uint32_t)qrow, g4, ckey, a.drop_add4);
+            else if (g.keyb <= q4 * 32 + 31) bwd_chunk<true>(ts, tdp, imgP, imgS, row, c4 * 16, g.keyb, sl2, off, ndelta, (uint32_t)qrow, g4, ckey, a.drop_add4);
             else {
                 const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 put16w(imgP, row, c4 * 16, z);
@@ -547,9 +559,9 @@ static int fill(const xtrl_attn_core_io *io, int32_t n, int32_t dim_head, Args &
     a.out = static_cast<__nv_bfloat16 *>(io->o_out); a.dq = static_cast<__nv_bfloat16 *>(io->dq); a.dk = static_cast<__nv_bfloat16 *>(io->dk);
     a.dv = static_cast<__nv_bfloat16 *>(io->dv); a.lse = io->lse;
     a.rng_step = io->rng_step; a.rng_key = io->rng_key;
-    const uint32_t thr = (uint32_t)(io->dropout * 256.f + 0.5f);              // the drop probability is quantised to 1/256
-    a.drop_thr4 = thr * 0x01010101u;
-    a.drop_scale = 1.f / (1.f - (float)thr / 256.f);
+    const uint32_t thr = (uint32_t)(io->dropout * 128.f + 0.5f);              // the drop probability is quantised to 1/128
+    a.drop_add4 = thr ? (128u - thr) * 0x01010101u : 0u;
+    a.drop_scale = 1.f / (1.f - (float)thr / 128.f);
     a.drop_log2scale = log2f(a.drop_scale);
     a.scale = io->scale; a.n = n;
     return XTRL_OK;
