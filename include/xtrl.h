@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define XTRL_ABI_VERSION 4
+#define XTRL_ABI_VERSION 5
 
 #define XTRL_OK            0
 #define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
@@ -315,10 +315,21 @@ typedef struct xtrl_attn_io {
     const float *dy;                /* [b*n][dim]              post bwd in (dx of the residual path = dy) */
     void *d_o;                      /* bf16 [b][H][n][16]      post bwd out                    */
     float *d_wo;                    /* += post bwd                                             */
+    /* optional extra projection blocks of `pre` (value gate: to_v_gate; learned value-residual mix:
+     * to_value_residual_mix) -- present when the output pointer (fwd) / gradient pointer (bwd) is non-NULL.
+     * pre emits the PRE-activations (bias added); sigmoid / multiply / lerp are the caller's.            */
+    const float *gate_bias;         /* [H*16]                                                  */
+    const float *mix_bias;          /* [H]                                                     */
+    void *gate;                     /* bf16 [b][H][n][16]      pre fwd out                     */
+    void *mix;                      /* bf16 [b*n][16], first H columns valid   pre fwd out     */
+    const void *d_gate, *d_mix;     /* same layouts            pre bwd in                      */
+    float *d_wg, *d_bg, *d_wm, *d_bm;                     /* += pre bwd                        */
 } xtrl_attn_io;
 
-int64_t xtrl_attn_img_bytes(int32_t dim, int32_t heads, int32_t dim_head);   /* -1 if not built */
+/* built: heads 4 or 8, gate 0/1, mix 0/1 except (8 heads, gate, mix); -1 otherwise */
+int64_t xtrl_attn_img_bytes(int32_t dim, int32_t heads, int32_t dim_head, int32_t gate, int32_t mix);
 int xtrl_attn_pack(const float *wq, const float *wk, const float *wv /*[H*16][dim]*/, const float *wo /*[dim][H*16]*/,
+                   const float *wg /*[H*16][dim] or NULL*/, const float *wm /*[H][dim] or NULL*/,
                    void *img, int32_t dim, int32_t heads, int32_t dim_head, void *stream);
 int xtrl_attn_pre_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
 int xtrl_attn_pre_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);

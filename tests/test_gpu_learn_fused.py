@@ -137,10 +137,12 @@ def test_fused_bf16_learn_step_tracks_fp32(tmp_path, wm):
     assert err_fused < 3e-2, (err_fused, err_unfused)
     assert err_fused < 1.5 * err_unfused + 5e-3, (err_fused, err_unfused)       # no worse than torch's own bf16 autocast path
     for n, o0, o1 in zip(names, offs[:-1], offs[1:]):                            # and tensor by tensor on the fused sub-layers
-        fused_attn = not wm.get('attn_gate_values') and ('.to_q.' in n or '.to_k.' in n or '.to_v.' in n or '.to_out.' in n or
-                                                         ('layers.0.' in n or 'layers.2.' in n) and n.endswith('gamma'))
+        fused_attn = ('.to_q.' in n or '.to_k.' in n or '.to_v.' in n or '.to_out.' in n or '.to_v_gate.' in n or
+                      '.to_value_residual_mix.' in n or ('layers.0.' in n or 'layers.2.' in n) and n.endswith('gamma'))
         if '.ff.' in n or ('layers.1.' in n or 'layers.3.' in n) and n.endswith('gamma') or fused_attn:
             ref = g32[o0:o1]
+            if ref.abs().max() < 1e-3 * g32.abs().max():      # e.g. the value gate at its bias-10 init: sigmoid'(10) rounds to 0 in bf16
+                continue
             assert float((gfu[o0:o1] - ref).abs().max() / ref.abs().max().clamp(min=1e-12)) < 5e-2, n
 
 
@@ -203,6 +205,58 @@ def test_attn_pre_post_vs_torch(H, b, n):
     d_o = ops.attn_post_bwd(dy, o, lens, img, d_wo)
     assert maxrel(d_o.float(), o32.grad) < TOL_BF16
     assert maxrel(d_wo, wo.grad) < 2 * TOL_BF16
+
+
+@pytest.mark.parametrize('H,gate,mix', [(4, True, True), (4, True, False), (4, False, True), (8, True, False), (8, False, True)])
+def test_attn_pre_gate_and_mix_blocks_vs_torch(H, gate, mix):
+    """the optional extra projection blocks: value-gate pre-activations and value-residual mix logits (+ their biases),
+    forward and every gradient."""
+    ops = xtrl().ops
+    b, n, D, I = 3, 150, 48, 16 * H
+    g = torch.Generator().manual_seed(H * 100 + gate * 10 + mix)
+    r = lambda *s, sc=1.: (torch.randn(*s, generator=g) * sc).to(DEV).requires_grad_()
+    gamma, wq, wk, wv, wo = r(D, sc=0.2), r(I, D, sc=D ** -0.5), r(I, D, sc=D ** -0.5), r(I, D, sc=D ** -0.5), r(D, I, sc=I ** -0.5)
+    wg, bg, wm, bm = r(I, D, sc=D ** -0.5), r(I, sc=0.5), r(H, D, sc=D ** -0.5), r(H, sc=0.5)
+    with torch.no_grad():
+        gamma += 1.
+    x = (torch.randn(b, n, D, generator=g) * 1.3 + 0.2).to(DEV).requires_grad_()
+    cos, sin = _tables(n)
+    cos8, sin8 = cos.repeat_interleave(2, -1), sin.repeat_interleave(2, -1)
+    img = ops.attn_pack(wq.detach(), wk.detach(), wv.detach(), wo.detach(), wg=wg.detach() if gate else None, wm=wm.detach() if mix else None)
+    xn = F.layer_norm(x, (D,)) * gamma
+    split = lambda t: t.view(b, n, H, 16).transpose(1, 2)
+    refs = [_rotate_ref(split(xn @ wq.T), cos8, sin8), _rotate_ref(split(xn @ wk.T), cos8, sin8), split(xn @ wv.T)]
+    if gate:
+        refs.append(split(xn @ wg.T + bg))
+    if mix:
+        refs.append(xn @ wm.T + bm)                                   # (b, n, H)
+    outs = ops.attn_pre_fwd(x.detach(), gamma.detach(), img, cos, sin, H, gate_bias=bg.detach() if gate else None,
+                            mix_bias=bm.detach() if mix else None)
+    assert len(outs) == len(refs)
+    for i, (got, ref) in enumerate(zip(outs, refs)):
+        got = got[..., :H] if (mix and i == len(refs) - 1) else got
+        assert maxrel(got.float(), ref.detach()) < TOL_BF16, i
+    douts = [torch.randn(b, H, n, 16, generator=g).to(DEV).bfloat16() for _ in range(3 + gate)]
+    dmix = None
+    if mix:
+        dmix = torch.zeros(b, n, 16, device=DEV, dtype=torch.bfloat16)
+        dmix[..., :H] = torch.randn(b, n, H, generator=g).to(DEV).bfloat16()
+    loss = sum((ref * d.float()).sum() for ref, d in zip(refs[:3 + gate], douts))
+    if mix:
+        loss = loss + (refs[-1] * dmix[..., :H].float()).sum()
+    loss.backward()
+    names = dict(gamma=gamma, wq=wq, wk=wk, wv=wv, **(dict(wg=wg, bg=bg) if gate else {}), **(dict(wm=wm, bm=bm) if mix else {}))
+    gr = {k_: torch.zeros_like(t) for k_, t in names.items()}
+    dx = ops.attn_pre_bwd(x.detach(), douts[0], douts[1], douts[2], gamma.detach(), img, cos, sin, gr['gamma'], gr['wq'], gr['wk'], gr['wv'],
+                          dg=douts[3] if gate else None, dmix=dmix, d_wg=gr.get('wg'), d_bg=gr.get('bg'), d_wm=gr.get('wm'), d_bm=gr.get('bm'))
+    assert maxrel(dx, x.grad) < TOL_BF16
+    for k_, t in names.items():
+        assert maxrel(gr[k_], t.grad) < 2 * TOL_BF16, (k_, maxrel(gr[k_], t.grad))
+    # the output projection still reads its image from the front of the same buffer
+    lens = torch.full((b,), n, dtype=torch.int32, device=DEV)
+    o = torch.randn(b, H, n, 16, generator=g).to(DEV).bfloat16()
+    y = ops.attn_post_fwd(x.detach(), o, lens, img)
+    assert maxrel(y - x.detach(), (o.float().transpose(1, 2).reshape(b, n, I) @ wo.T).detach()) < TOL_BF16
 
 
 # ---------------------------------------------------------------------------------------------

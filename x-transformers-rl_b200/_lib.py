@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-XTRL_ABI_VERSION = 4
+XTRL_ABI_VERSION = 5
 XTRL_MAX_DEPTH = 16
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -80,7 +80,8 @@ class FfIO(C.Structure):
 
 class AttnIO(C.Structure):
     _fields_ = [(n, c_vp) for n in ('x', 'ln_gamma', 'cos_tab', 'sin_tab', 'w_img', 'q', 'k', 'v', 'dq', 'dk', 'dv', 'dx',
-                                    'd_ln_gamma', 'd_wq', 'd_wk', 'd_wv', 'o', 'lens', 'y', 'dy', 'd_o', 'd_wo')]
+                                    'd_ln_gamma', 'd_wq', 'd_wk', 'd_wv', 'o', 'lens', 'y', 'dy', 'd_o', 'd_wo',
+                                    'gate_bias', 'mix_bias', 'gate', 'mix', 'd_gate', 'd_mix', 'd_wg', 'd_bg', 'd_wm', 'd_bm')]
 
 
 class AttnCoreIO(C.Structure):
@@ -110,8 +111,8 @@ SYMBOLS = {
     'xtrl_ff_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'xtrl_ff_fwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
     'xtrl_ff_bwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
-    'xtrl_attn_img_bytes': (c_i64, [c_i32, c_i32, c_i32]),
-    'xtrl_attn_pack': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_attn_img_bytes': (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32]),
+    'xtrl_attn_pack': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_pre_fwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_pre_bwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_post_fwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),

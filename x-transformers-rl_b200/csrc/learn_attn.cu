@@ -8,7 +8,10 @@
 // Replaces, inside Agent.learn's teacher-forced pass (x_transformers_rl.py:928-935; x-transformers Decoder
 // attention sub-layer): LayerNorm, to_q / to_k / to_v, rotary, the head split / merge
 // transposes, to_out, the padded-row zeroing and the residual add -- and their backward.  SURVEY 8f row 1.
-// Built for the plain attention block (no value gate, no value residual); those variants keep the torch ops.
+// Value gates and the learned value-residual mix (c2's block) ride along as extra output blocks of the same GEMM:
+// pre also emits the gate pre-activation (bf16 [b][H][n][16], bias added) and the mix logits (bf16 [b*n][16], first H
+// valid), pre_bwd takes their gradients as extra K blocks; the sigmoid / lerp / multiply on those small tensors stay
+// element-wise ops of the caller.  Image order: [Wo | Wq Wk Wv (Wg) (Wm, zero-padded to 16 rows)].
 //
 // Same machinery as learn_ff.cu: 128-token tiles, TMEM lane = token, thread (row, half) owns half of the
 // columns, bf16 canonical images in shared memory, weight gradients accumulated in TMEM across the CTA's
@@ -32,6 +35,10 @@ struct Args {
     const float *dy;                                      // post bwd in
     __nv_bfloat16 *d_o;                                   // post bwd out
     float *dwo;
+    const float *bg, *bm;                                 // gate / mix biases (pre fwd)
+    __nv_bfloat16 *g, *mix;                               // pre fwd out: gate pre-activation [b][H][n][16], mix logits [N][16]
+    const __nv_bfloat16 *dg, *dmix;                       // pre bwd in
+    float *dwg, *dbg, *dwm, *dbm;                         // pre bwd out
     int N, n;
 };
 
@@ -61,32 +68,38 @@ __device__ __forceinline__ void copy_block(unsigned char *img, int row, int blk,
     *reinterpret_cast<uint4 *>(p + kCore) = b;
 }
 
-template <int H> struct Dims {
-    static constexpr int I = 16 * H, NQ = 3 * I;
+// NB = 3 (q, k, v) or 4 (+ gate) blocks of I outputs; MIX adds one 16-wide block of per-head mix logits
+template <int H, int NB = 3, int MIX = 0> struct Dims {
+    static constexpr int I = 16 * H, NQ = NB * I + 16 * MIX;
+    static constexpr int NBLK = NB * H + MIX;             // 16-column output blocks
     static constexpr int kWqkv = NQ * D * 2, kWo = D * I * 2;
-    static constexpr int kMT = (NQ + 127) / 128;          // 128-row tiles of the Wqkv gradient
+    static constexpr int kMT = (NQ + 127) / 128;          // 128-row tiles of the projection-weight gradient
+    static constexpr int XW = 64;                         // Xn image width in the backward: 48 features + ones column + pad
 };
 
 // -------------------------------------------------------------------------------------------- pre fwd
-template <int H>
+template <int H, int NB, int MIX>
 __global__ void __launch_bounds__(NT, 1) attn_pre_fwd_kernel(const Args a) {
-    using P = Dims<H>;
-    constexpr int NQ = P::NQ, TCOLS = NQ > 256 ? 512 : 256;
+    using P = Dims<H, NB, MIX>;
+    constexpr int NQ = P::NQ, I = P::I, NBLK = P::NBLK, TCOLS = NQ > 256 ? 512 : 256;
+    constexpr int BLK0 = (NBLK + 1) / 2;                                    // blocks of half 0; half 1 takes the rest
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem, *sXn = sW + P::kWqkv;
-    float *sG = reinterpret_cast<float *>(sXn + TOK * D * 2);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
+    float *sG = reinterpret_cast<float *>(sXn + TOK * D * 2), *sBias = sG + D;       // bias of the gate block / mix block
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + I + 16);
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tslot, TCOLS);
     if (tid < D) sG[tid] = a.gamma[tid];
+    for (int i = tid; i < I + 16; i += NT)
+        sBias[i] = i < I ? (NB == 4 ? a.bg[i] : 0.f) : ((MIX && i - I < H) ? a.bm[i - I] : 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
-    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg, P::kWqkv, &bars[0]); }
+    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg + P::kWo, P::kWqkv, &bars[0]); }
     uint32_t ph = 0;
     bool first = true;
     const int ntiles = (a.N + TOK - 1) / TOK;
@@ -126,14 +139,25 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_fwd_kernel(const Args a) {
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
+        const int b0 = half ? BLK0 : 0, b1 = half ? NBLK : BLK0;
 #pragma unroll 1
-        for (int bb = 0; bb < 3 * H / 2; ++bb) {
-            const int bi = half * (3 * H / 2) + bb, which = bi / H, h = bi - which * H;
+        for (int bi = b0; bi < b1; ++bi) {
             float v[16];
             tmem_ld16(tlane + bi * 16, v);
-            if (which < 2) rotary8(v, cs, sn, false);
-            __nv_bfloat16 *dst = (which == 0 ? a.q : which == 1 ? a.k : a.v) + ((size_t)(e * H + h) * a.n + pos) * 16;
-            if (ok) store16(dst, v);
+            if (bi < NB * H) {
+                const int which = bi / H, h = bi - which * H;
+                if (which < 2) rotary8(v, cs, sn, false);
+                if (NB == 4 && which == 3) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += sBias[h * 16 + j];
+                }
+                __nv_bfloat16 *dst = (which == 0 ? a.q : which == 1 ? a.k : which == 2 ? a.v : a.g) + ((size_t)(e * H + h) * a.n + pos) * 16;
+                if (ok) store16(dst, v);
+            } else {                                                          // mix logits, one per head
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += sBias[I + j];
+                if (ok) store16(a.mix + (size_t)t * 16, v);
+            }
         }
         tc_fence_before();
     }
@@ -142,26 +166,32 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_fwd_kernel(const Args a) {
 }
 
 // -------------------------------------------------------------------------------------------- pre bwd
-template <int H>
+template <int H, int NB, int MIX>
 __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
-    using P = Dims<H>;
-    constexpr int NQ = P::NQ, I = P::I;
+    using P = Dims<H, NB, MIX>;
+    constexpr int NQ = P::NQ, I = P::I, NBLK = P::NBLK, XW = P::XW;
+    constexpr int BLK0 = (NBLK + 1) / 2;
     constexpr uint32_t cDxn = 0, cAcc = 64;
+    constexpr int TCOLS = 64 + P::kMT * XW > 256 ? 512 : 256;
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sDQ = smem, *sXn = sDQ + TOK * NQ * 2, *sW = sXn + TOK * D * 2;     // sDQ first: its MN-major over-read lands in sXn / sW
+    unsigned char *sDQ = smem, *sXn = sDQ + TOK * NQ * 2, *sW = sXn + TOK * XW * 2;    // sDQ first: its MN-major over-read lands in sXn / sW
     float *sG = reinterpret_cast<float *>(sW + P::kWqkv);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc(tslot, 256);
+    if (warp == 0) tmem_alloc(tslot, TCOLS);
     if (tid < D) sG[tid] = a.gamma[tid];
+    if (half == 0) {                                                          // constant ones column (bias gradients) + zero pad
+        const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        put8(sXn, row, 6, one); put8(sXn, row, 7, zero);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
-    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg, P::kWqkv, &bars[0]); }
+    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg + P::kWo, P::kWqkv, &bars[0]); }
     uint32_t ph = 0;
     bool first = true;
     float dg_acc[24];
@@ -188,10 +218,12 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         }
         const float4 cs = ok ? __ldg(reinterpret_cast<const float4 *>(a.cos_tab) + pos) : make_float4(1.f, 1.f, 1.f, 1.f);
         const float4 sn = ok ? __ldg(reinterpret_cast<const float4 *>(a.sin_tab) + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int b0 = half ? BLK0 : 0, b1 = half ? NBLK : BLK0;
 #pragma unroll 1
-        for (int bb = 0; bb < 3 * H / 2; ++bb) {
-            const int bi = half * (3 * H / 2) + bb, which = bi / H, h = bi - which * H;
-            const __nv_bfloat16 *src = (which == 0 ? a.dq : which == 1 ? a.dk : a.dv) + ((size_t)(e * H + h) * a.n + pos) * 16;
+        for (int bi = b0; bi < b1; ++bi) {
+            const int which = bi / H, h = bi - which * H;
+            const __nv_bfloat16 *src = bi >= NB * H ? a.dmix + (size_t)t * 16
+                : (which == 0 ? a.dq : which == 1 ? a.dk : which == 2 ? a.dv : a.dg) + ((size_t)(e * H + h) * a.n + pos) * 16;
             if (which < 2) {
                 float lo[8], hi[8], v[16];
                 const uint4 z = make_uint4(0, 0, 0, 0);
@@ -214,16 +246,16 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
             if (first) mbar_wait(&bars[0], 0);
             tc_fence_after();
 #pragma unroll
-            for (int s = 0; s < NQ / 16; ++s)                                    // dXn = dQKV * Wqkv (image read MN-major)
+            for (int s = 0; s < NQ / 16; ++s)                                    // dXn = dY * W (image read MN-major)
                 mma_bf16_ss(tbase + cDxn, smem_desc(sDQ + s * 2 * kCore, kCore, 128), smem_desc(sW + s * 256, 128, NQ * 16),
                             idesc_bf16(128, D) | kIdB, s > 0);
 #pragma unroll
-            for (int s = 0; s < TOK / 16; ++s) {                                 // dWqkv += dQKV^T * Xn
+            for (int s = 0; s < TOK / 16; ++s) {                                 // dW | db += dY^T * [Xn | 1]
                 const uint64_t bd = smem_desc(sXn + s * 256, 128, kCore);
 #pragma unroll
                 for (int m = 0; m < P::kMT; ++m)
-                    mma_bf16_ss(tbase + cAcc + m * D, smem_desc(sDQ + m * 16 * kCore + s * 256, 128, kCore), bd,
-                                idesc_bf16(128, D) | kIdA | kIdB, !first || s > 0);
+                    mma_bf16_ss(tbase + cAcc + m * XW, smem_desc(sDQ + m * 16 * kCore + s * 256, 128, kCore), bd,
+                                idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
             }
             mma_commit(&bars[1]);
         }
@@ -267,22 +299,35 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         tc_fence_after();
 #pragma unroll 1
         for (int m = 0; m < P::kMT; ++m) {
-            const int j = m * 128 + row, which = j / I, jj = j - which * I;
-            float *dst = (which == 0 ? a.dwq : which == 1 ? a.dwk : a.dwv) + jj * D + half * 24;
+            const int j = m * 128 + row;                                          // output row of [Wq; Wk; Wv; (Wg); (Wm)]
+            const int which = j / I, jj = j - which * I;
+            float *wdst = nullptr, *bdst = nullptr;
+            if (j < NB * I) {
+                wdst = (which == 0 ? a.dwq : which == 1 ? a.dwk : which == 2 ? a.dwv : a.dwg) + jj * D;
+                if (which == 3) bdst = a.dbg + jj;
+            } else if (MIX && j - NB * I < H) {
+                wdst = a.dwm + (j - NB * I) * D;
+                bdst = a.dbm + (j - NB * I);
+            }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
+            for (int c = 0; c < 4; ++c) {                                         // half 0: columns 0..31, half 1: 32..63
+                const int col0 = half * 32 + c * 8;
+                if (col0 > D) break;
                 float v[8];
-                tmem_ld8(tlane + cAcc + m * D + half * 24 + c * 8, v);
-                if (j < NQ) {
+                tmem_ld8(tlane + cAcc + m * XW + col0, v);
+                if (wdst) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) atomicAdd(dst + c * 8 + i, v[i]);
+                    for (int i = 0; i < 8; ++i) {
+                        if (col0 + i < D) atomicAdd(wdst + col0 + i, v[i]);
+                        else if (col0 + i == D && bdst) atomicAdd(bdst, v[i]);
+                    }
                 }
             }
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 256);
+    if (warp == 0) tmem_dealloc(tbase, TCOLS);
 }
 
 // ------------------------------------------------------------------------------------------- post fwd
@@ -302,7 +347,7 @@ __global__ void __launch_bounds__(NT, 2) attn_post_fwd_kernel(const Args a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
-    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWo); bulk_g2s(sW, a.wimg + P::kWqkv, P::kWo, &bars[0]); }
+    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWo); bulk_g2s(sW, a.wimg, P::kWo, &bars[0]); }
     uint32_t ph = 0;
     bool first = true;
     const int ntiles = (a.N + TOK - 1) / TOK;
@@ -371,7 +416,7 @@ __global__ void __launch_bounds__(NT, 2) attn_post_bwd_kernel(const Args a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
-    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWo); bulk_g2s(sW, a.wimg + P::kWqkv, P::kWo, &bars[0]); }
+    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWo); bulk_g2s(sW, a.wimg, P::kWo, &bars[0]); }
     uint32_t ph = 0;
     bool first = true;
     const int ntiles = (a.N + TOK - 1) / TOK;
@@ -438,26 +483,33 @@ __global__ void __launch_bounds__(NT, 2) attn_post_bwd_kernel(const Args a) {
     if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
-template <int H>
+template <int H, int NB, int MIX>
 __global__ void attn_pack_kernel(const float *__restrict__ wq, const float *__restrict__ wk, const float *__restrict__ wv,
-                                 const float *__restrict__ wo, unsigned char *__restrict__ img) {
-    using P = Dims<H>;
+                                 const float *__restrict__ wo, const float *__restrict__ wg, const float *__restrict__ wm,
+                                 unsigned char *__restrict__ img) {
+    using P = Dims<H, NB, MIX>;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P::NQ * D) {
-        const int j = i / D, k = i % D, which = j / P::I, jj = j % P::I;         // Wqkv rows: q, k, v outputs; K = 48
-        const float w = (which == 0 ? wq : which == 1 ? wk : wv)[jj * D + k];
-        *reinterpret_cast<__nv_bfloat16 *>(img + img_off_bf16(P::NQ, j, k)) = __float2bfloat16(w);
-    }
     if (i < D * P::I) {
         const int r = i / P::I, c = i % P::I;                                    // Wo [48][I]: rows = outputs, K = I
-        *reinterpret_cast<__nv_bfloat16 *>(img + P::kWqkv + img_off_bf16(D, r, c)) = __float2bfloat16(wo[i]);
+        *reinterpret_cast<__nv_bfloat16 *>(img + img_off_bf16(D, r, c)) = __float2bfloat16(wo[i]);
+    }
+    if (i < P::NQ * D) {
+        const int j = i / D, k = i % D;                                          // projection rows: q, k, v, (gate), (mix padded to 16); K = 48
+        float w = 0.f;
+        if (j < NB * P::I) {
+            const int which = j / P::I, jj = j % P::I;
+            w = (which == 0 ? wq : which == 1 ? wk : which == 2 ? wv : wg)[jj * D + k];
+        } else if (j - NB * P::I < H) {
+            w = wm[(j - NB * P::I) * D + k];
+        }
+        *reinterpret_cast<__nv_bfloat16 *>(img + P::kWo + img_off_bf16(P::NQ, j, k)) = __float2bfloat16(w);
     }
 }
 
-template <int H> struct Smem {
-    using P = Dims<H>;
-    static constexpr int pre_fwd = P::kWqkv + TOK * D * 2 + D * 4 + 64;
-    static constexpr int pre_bwd = TOK * P::NQ * 2 + TOK * D * 2 + P::kWqkv + D * 4 + 64;
+template <int H, int NB, int MIX> struct Smem {
+    using P = Dims<H, NB, MIX>;
+    static constexpr int pre_fwd = P::kWqkv + TOK * D * 2 + (D + P::I + 16) * 4 + 64;
+    static constexpr int pre_bwd = TOK * P::NQ * 2 + TOK * P::XW * 2 + P::kWqkv + D * 4 + 64;
     static constexpr int post_fwd = TOK * P::I * 2 + P::kWo + 64;
     static constexpr int post_bwd = TOK * P::I * 2 + TOK * D * 2 + P::kWo + 64;
 };
@@ -471,19 +523,23 @@ static int fill(const xtrl_attn_io *io, int32_t b, int32_t n, Args &a) {
     a.dx = io->dx; a.dgamma = io->d_ln_gamma; a.dwq = io->d_wq; a.dwk = io->d_wk; a.dwv = io->d_wv;
     a.o = static_cast<const __nv_bfloat16 *>(io->o); a.lens = io->lens; a.y = io->y; a.dy = io->dy;
     a.d_o = static_cast<__nv_bfloat16 *>(io->d_o); a.dwo = io->d_wo;
+    a.bg = io->gate_bias; a.bm = io->mix_bias;
+    a.g = static_cast<__nv_bfloat16 *>(io->gate); a.mix = static_cast<__nv_bfloat16 *>(io->mix);
+    a.dg = static_cast<const __nv_bfloat16 *>(io->d_gate); a.dmix = static_cast<const __nv_bfloat16 *>(io->d_mix);
+    a.dwg = io->d_wg; a.dbg = io->d_bg; a.dwm = io->d_wm; a.dbm = io->d_bm;
     a.N = b * n; a.n = n;
     return XTRL_OK;
 }
 
 template <typename K>
 static int launch(K kernel, const char *name, int smem, int ctas_per_sm, const Args &a, void *stream) {
-    static const void *seen[16];                    // kernels whose shared-memory limit is already raised
+    static const void *seen[32];                    // kernels whose shared-memory limit is already raised
     static int nseen = 0;
     bool known = false;
     for (int i = 0; i < nseen; ++i) known |= seen[i] == (const void *)kernel;
     if (!known) {
         XTRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (nseen < 16) seen[nseen++] = (const void *)kernel;
+        if (nseen < 32) seen[nseen++] = (const void *)kernel;
     }
     const int ntiles = (a.N + TOK - 1) / TOK, cap = ctas_per_sm * kNumSMs;
     kernel<<<ntiles < cap ? ntiles : cap, NT, smem, (cudaStream_t)stream>>>(a);
@@ -491,80 +547,104 @@ static int launch(K kernel, const char *name, int smem, int ctas_per_sm, const A
     return XTRL_OK;
 }
 
+// the built (heads, gate, mix) combinations; everything else is XTRL_E_UNSUPPORTED
+static bool variant_ok(int heads, int gate, int mix) {
+    return (heads == 4 || heads == 8) && (gate == 0 || gate == 1) && (mix == 0 || mix == 1) && !(heads == 8 && gate && mix);
+}
+#define XTRL_ATTN_VARIANT(heads, gate, mix, CALL)                                   \
+    do {                                                                             \
+        if ((heads) == 4 && !(gate) && !(mix)) { CALL(4, 3, 0); }                    \
+        else if ((heads) == 4 && !(gate) && (mix)) { CALL(4, 3, 1); }                \
+        else if ((heads) == 4 && (gate) && !(mix)) { CALL(4, 4, 0); }                \
+        else if ((heads) == 4 && (gate) && (mix)) { CALL(4, 4, 1); }                 \
+        else if ((heads) == 8 && !(gate) && !(mix)) { CALL(8, 3, 0); }               \
+        else if ((heads) == 8 && !(gate) && (mix)) { CALL(8, 3, 1); }                \
+        else { CALL(8, 4, 0); }                                                      \
+    } while (0)
+
 }  // namespace attn
 }  // namespace xtrl
 
-static int attn_check(int32_t dim, int32_t heads, int32_t dim_head) {
+static int attn_check(int32_t dim, int32_t heads, int32_t dim_head, int32_t gate, int32_t mix) {
     using namespace xtrl;
-    XTRL_REQUIRE(dim == learn::D && dim_head == 16 && (heads == 4 || heads == 8), XTRL_E_UNSUPPORTED,
-                 "xtrl_attn_*: built for dim=48, dim_head=16, heads in {4, 8} (got %d, %d, %d)", dim, dim_head, heads);
+    XTRL_REQUIRE(dim == learn::D && dim_head == 16 && attn::variant_ok(heads, gate, mix), XTRL_E_UNSUPPORTED,
+                 "xtrl_attn_*: built for dim=48, dim_head=16, heads in {4, 8}, not (8 heads + gate + mix) (got dim=%d dim_head=%d heads=%d gate=%d mix=%d)",
+                 dim, dim_head, heads, gate, mix);
     return XTRL_OK;
 }
 
-extern "C" int64_t xtrl_attn_img_bytes(int32_t dim, int32_t heads, int32_t dim_head) {
+extern "C" int64_t xtrl_attn_img_bytes(int32_t dim, int32_t heads, int32_t dim_head, int32_t gate, int32_t mix) {
     using namespace xtrl::attn;
-    if (dim != xtrl::learn::D || dim_head != 16 || (heads != 4 && heads != 8)) return -1;
-    return heads == 4 ? Dims<4>::kWqkv + Dims<4>::kWo : Dims<8>::kWqkv + Dims<8>::kWo;
+    if (dim != xtrl::learn::D || dim_head != 16 || !variant_ok(heads, gate, mix)) return -1;
+    const int I = 16 * heads, NQ = (gate ? 4 : 3) * I + (mix ? 16 : 0);
+    return (int64_t)xtrl::learn::D * I * 2 + (int64_t)NQ * xtrl::learn::D * 2;
 }
 
-extern "C" int xtrl_attn_pack(const float *wq, const float *wk, const float *wv, const float *wo, void *img,
-                              int32_t dim, int32_t heads, int32_t dim_head, void *stream) {
+extern "C" int xtrl_attn_pack(const float *wq, const float *wk, const float *wv, const float *wo, const float *wg, const float *wm,
+                              void *img, int32_t dim, int32_t heads, int32_t dim_head, void *stream) {
     using namespace xtrl; using namespace xtrl::attn;
-    if (int rc = attn_check(dim, heads, dim_head)) return rc;
+    const int gate = wg != nullptr, mix = wm != nullptr;
+    if (int rc = attn_check(dim, heads, dim_head, gate, mix)) return rc;
     XTRL_REQUIRE(wq && wk && wv && wo && img, XTRL_E_BADARG, "xtrl_attn_pack: null pointer");
     unsigned char *p = static_cast<unsigned char *>(img);
-    if (heads == 4) attn_pack_kernel<4><<<(Dims<4>::NQ * learn::D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wq, wk, wv, wo, p);
-    else attn_pack_kernel<8><<<(Dims<8>::NQ * learn::D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wq, wk, wv, wo, p);
+#define CALL(H, NB, MIX) attn_pack_kernel<H, NB, MIX><<<(Dims<H, NB, MIX>::NQ * learn::D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wq, wk, wv, wo, wg, wm, p)
+    XTRL_ATTN_VARIANT(heads, gate, mix, CALL);
+#undef CALL
     XTRL_LAUNCH_CHECK("attn_pack_kernel");
     return XTRL_OK;
 }
 
 extern "C" int xtrl_attn_pre_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream) {
     using namespace xtrl; using namespace xtrl::attn;
-    if (int rc = attn_check(learn::D, heads, 16)) return rc;
     XTRL_REQUIRE(io && b >= 0 && n >= 0, XTRL_E_BADARG, "xtrl_attn_pre_fwd: bad arguments");
+    const int gate = io->gate != nullptr, mix = io->mix != nullptr;
+    if (int rc = attn_check(learn::D, heads, 16, gate, mix)) return rc;
     if ((int64_t)b * n == 0) return XTRL_OK;
-    XTRL_REQUIRE(io->x && io->ln_gamma && io->cos_tab && io->sin_tab && io->w_img && io->q && io->k && io->v, XTRL_E_BADARG,
-                 "xtrl_attn_pre_fwd: null pointer");
+    XTRL_REQUIRE(io->x && io->ln_gamma && io->cos_tab && io->sin_tab && io->w_img && io->q && io->k && io->v && (!gate || io->gate_bias) &&
+                 (!mix || io->mix_bias), XTRL_E_BADARG, "xtrl_attn_pre_fwd: null pointer");
     Args a;
     if (int rc = fill(io, b, n, a)) return rc;
-    return heads == 4 ? launch(attn_pre_fwd_kernel<4>, "attn_pre_fwd_kernel", Smem<4>::pre_fwd, 1, a, stream)
-                      : launch(attn_pre_fwd_kernel<8>, "attn_pre_fwd_kernel", Smem<8>::pre_fwd, 1, a, stream);
+#define CALL(H, NB, MIX) return launch(attn_pre_fwd_kernel<H, NB, MIX>, "attn_pre_fwd_kernel", Smem<H, NB, MIX>::pre_fwd, 1, a, stream)
+    XTRL_ATTN_VARIANT(heads, gate, mix, CALL);
+#undef CALL
 }
 
 extern "C" int xtrl_attn_pre_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream) {
     using namespace xtrl; using namespace xtrl::attn;
-    if (int rc = attn_check(learn::D, heads, 16)) return rc;
     XTRL_REQUIRE(io && b >= 0 && n >= 0, XTRL_E_BADARG, "xtrl_attn_pre_bwd: bad arguments");
+    const int gate = io->d_gate != nullptr, mix = io->d_mix != nullptr;
+    if (int rc = attn_check(learn::D, heads, 16, gate, mix)) return rc;
     if ((int64_t)b * n == 0) return XTRL_OK;
     XTRL_REQUIRE(io->x && io->ln_gamma && io->cos_tab && io->sin_tab && io->w_img && io->dq && io->dk && io->dv && io->dx &&
-                 io->d_ln_gamma && io->d_wq && io->d_wk && io->d_wv, XTRL_E_BADARG, "xtrl_attn_pre_bwd: null pointer");
+                 io->d_ln_gamma && io->d_wq && io->d_wk && io->d_wv && (!gate || (io->d_wg && io->d_bg)) && (!mix || (io->d_wm && io->d_bm)),
+                 XTRL_E_BADARG, "xtrl_attn_pre_bwd: null pointer");
     Args a;
     if (int rc = fill(io, b, n, a)) return rc;
-    return heads == 4 ? launch(attn_pre_bwd_kernel<4>, "attn_pre_bwd_kernel", Smem<4>::pre_bwd, 1, a, stream)
-                      : launch(attn_pre_bwd_kernel<8>, "attn_pre_bwd_kernel", Smem<8>::pre_bwd, 1, a, stream);
+#define CALL(H, NB, MIX) return launch(attn_pre_bwd_kernel<H, NB, MIX>, "attn_pre_bwd_kernel", Smem<H, NB, MIX>::pre_bwd, 1, a, stream)
+    XTRL_ATTN_VARIANT(heads, gate, mix, CALL);
+#undef CALL
 }
 
 extern "C" int xtrl_attn_post_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream) {
     using namespace xtrl; using namespace xtrl::attn;
-    if (int rc = attn_check(learn::D, heads, 16)) return rc;
+    if (int rc = attn_check(learn::D, heads, 16, 0, 0)) return rc;
     XTRL_REQUIRE(io && b >= 0 && n >= 0, XTRL_E_BADARG, "xtrl_attn_post_fwd: bad arguments");
     if ((int64_t)b * n == 0) return XTRL_OK;
     XTRL_REQUIRE(io->x && io->o && io->lens && io->w_img && io->y, XTRL_E_BADARG, "xtrl_attn_post_fwd: null pointer");
     Args a;
     if (int rc = fill(io, b, n, a)) return rc;
-    return heads == 4 ? launch(attn_post_fwd_kernel<4>, "attn_post_fwd_kernel", Smem<4>::post_fwd, 2, a, stream)
-                      : launch(attn_post_fwd_kernel<8>, "attn_post_fwd_kernel", Smem<8>::post_fwd, 2, a, stream);
+    return heads == 4 ? launch(attn_post_fwd_kernel<4>, "attn_post_fwd_kernel", Smem<4, 3, 0>::post_fwd, 2, a, stream)
+                      : launch(attn_post_fwd_kernel<8>, "attn_post_fwd_kernel", Smem<8, 3, 0>::post_fwd, 2, a, stream);
 }
 
 extern "C" int xtrl_attn_post_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream) {
     using namespace xtrl; using namespace xtrl::attn;
-    if (int rc = attn_check(learn::D, heads, 16)) return rc;
+    if (int rc = attn_check(learn::D, heads, 16, 0, 0)) return rc;
     XTRL_REQUIRE(io && b >= 0 && n >= 0, XTRL_E_BADARG, "xtrl_attn_post_bwd: bad arguments");
     if ((int64_t)b * n == 0) return XTRL_OK;
     XTRL_REQUIRE(io->dy && io->o && io->lens && io->w_img && io->d_o && io->d_wo, XTRL_E_BADARG, "xtrl_attn_post_bwd: null pointer");
     Args a;
     if (int rc = fill(io, b, n, a)) return rc;
-    return heads == 4 ? launch(attn_post_bwd_kernel<4>, "attn_post_bwd_kernel", Smem<4>::post_bwd, 2, a, stream)
-                      : launch(attn_post_bwd_kernel<8>, "attn_post_bwd_kernel", Smem<8>::post_bwd, 2, a, stream);
+    return heads == 4 ? launch(attn_post_bwd_kernel<4>, "attn_post_bwd_kernel", Smem<4, 3, 0>::post_bwd, 2, a, stream)
+                      : launch(attn_post_bwd_kernel<8>, "attn_post_bwd_kernel", Smem<8, 3, 0>::post_bwd, 2, a, stream);
 }

@@ -122,23 +122,33 @@ class _FusedFeedForward(torch.autograd.Function):
 
 
 class _FusedAttnPre(torch.autograd.Function):
-    """x -> q, k, v (b, H, n, 16) bf16 through xtrl_attn_pre_fwd / _bwd (csrc/learn_attn.cu): LayerNorm, the three
-    projections, partial rotary, head-major layout.  Returns only the LayerNorm path's dx; the residual path of x is
-    autograd's.  Parameter gradients go straight into the flat gradient buffer, as in _FusedFeedForward."""
+    """x -> q, k, v (b, H, n, 16) bf16 [, value-gate pre-activation (b, H, n, 16)] [, value-residual mix logits (b, n, 16)]
+    through xtrl_attn_pre_fwd / _bwd (csrc/learn_attn.cu): LayerNorm, the projections, partial rotary, head-major layout.
+    Returns only the LayerNorm path's dx; the residual path of x is autograd's.  Parameter gradients go straight into the
+    flat gradient buffer, as in _FusedFeedForward."""
 
     @staticmethod
-    def forward(ctx, x, norm, attn, img, cos, sin, heads):
+    def forward(ctx, x, norm, attn, img, cos, sin, heads, gate, mix):
         x = x.float().contiguous()
         ctx.save_for_backward(x)
-        ctx.mods, ctx.aux = (norm, attn), (img, cos, sin)
-        return ops.attn_pre_fwd(x, norm.gamma.data, img, cos, sin, heads)
+        ctx.mods, ctx.aux, ctx.flags = (norm, attn), (img, cos, sin), (gate, mix)
+        return ops.attn_pre_fwd(x, norm.gamma.data, img, cos, sin, heads,
+                                gate_bias=attn.to_v_gate.bias.data if gate else None,
+                                mix_bias=attn.to_value_residual_mix[0].bias.data if mix else None)
 
     @staticmethod
-    def backward(ctx, dq, dk, dv):
-        (x,), (norm, attn), (img, cos, sin) = ctx.saved_tensors, ctx.mods, ctx.aux
+    def backward(ctx, dq, dk, dv, *extra):
+        (x,), (norm, attn), (img, cos, sin), (gate, mix) = ctx.saved_tensors, ctx.mods, ctx.aux, ctx.flags
+        extra = list(extra)
+        dg = extra.pop(0).contiguous() if gate else None
+        dmix = extra.pop(0).contiguous() if mix else None
+        lin_m = attn.to_value_residual_mix[0] if mix else None
         dx = ops.attn_pre_bwd(x, dq.contiguous(), dk.contiguous(), dv.contiguous(), norm.gamma.data, img, cos, sin,
-                              norm.gamma.grad, attn.to_q.weight.grad, attn.to_k.weight.grad, attn.to_v.weight.grad)
-        return dx, None, None, None, None, None, None
+                              norm.gamma.grad, attn.to_q.weight.grad, attn.to_k.weight.grad, attn.to_v.weight.grad,
+                              dg=dg, dmix=dmix, d_wg=attn.to_v_gate.weight.grad if gate else None,
+                              d_bg=attn.to_v_gate.bias.grad if gate else None,
+                              d_wm=lin_m.weight.grad if mix else None, d_bm=lin_m.bias.grad if mix else None)
+        return dx, None, None, None, None, None, None, None, None
 
 
 class _FusedAttnCore(torch.autograd.Function):
@@ -217,10 +227,12 @@ class WorldModelActorCritic(nn.Module):
             ok = dev.type == 'cuda' and ops.ff_supported(cfg.dim, 4 * cfg.dim)
             u8 = lambda nbytes: [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(cfg.depth)]
             lib = ops.L.load()
-            # the fused attention projections cover the plain block; value gates / value residual keep the torch ops
-            attn_ok = ok and not cfg.gate_values and not cfg.value_residual and ops.attn_supported(cfg.dim, cfg.heads, cfg.dim_head)
-            self._fused = dict(ff_img=u8(lib.xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim)),
-                               attn_img=u8(lib.xtrl_attn_img_bytes(cfg.dim, cfg.heads, cfg.dim_head)) if attn_ok else None,
+            # layer l's projection image carries the value gate (if any) and, for l > 0, the learned value-residual mix
+            mix = lambda l: bool(cfg.value_residual and cfg.learned_mix and l > 0)
+            attn_ok = ok and all(ops.attn_supported(cfg.dim, cfg.heads, cfg.dim_head, cfg.gate_values, mix(l)) for l in range(cfg.depth))
+            attn_img = [torch.empty(lib.xtrl_attn_img_bytes(cfg.dim, cfg.heads, cfg.dim_head, int(cfg.gate_values), int(mix(l))),
+                                    dtype=torch.uint8, device=dev) for l in range(cfg.depth)] if attn_ok else None
+            self._fused = dict(ff_img=u8(lib.xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim)), attn_img=attn_img,
                                rng_step=torch.zeros((), dtype=torch.int64, device=dev)) if ok else False
         return self._fused or None
 
@@ -272,7 +284,10 @@ class WorldModelActorCritic(nn.Module):
                 ops.ff_pack(ff.ff[0][0].weight.data, ff.ff[2].weight.data, out=fs['ff_img'][l])
                 if fs['attn_img'] is not None:
                     at = dec.layers[2 * l][1]
-                    ops.attn_pack(at.to_q.weight.data, at.to_k.weight.data, at.to_v.weight.data, at.to_out.weight.data, out=fs['attn_img'][l])
+                    ops.attn_pack(at.to_q.weight.data, at.to_k.weight.data, at.to_v.weight.data, at.to_out.weight.data,
+                                  wg=at.to_v_gate.weight.data if cfg.gate_values else None,
+                                  wm=at.to_value_residual_mix[0].weight.data if (cfg.value_residual and cfg.learned_mix and l > 0) else None,
+                                  out=fs['attn_img'][l])
             if fs['attn_img'] is not None:
                 fs['core'] = ops.attn_core_supported(n, dh) and os.environ.get('XTRL_LEARN_CORE', '1') != '0'
                 lens32 = mask.sum(dim=1, dtype=torch.int32)          # episodes are right-padded: mask == position < length
@@ -281,11 +296,22 @@ class WorldModelActorCritic(nn.Module):
         for l in range(cfg.depth):
             norm, attn = dec.layers[2 * l]
             if fs is not None and fs['attn_img'] is not None:
-                q, k, v = _FusedAttnPre.apply(x, norm, attn, fs['attn_img'][l], cos4, sin4, h)
+                has_mix = bool(cfg.value_residual and cfg.learned_mix and l > 0)
+                outs = _FusedAttnPre.apply(x, norm, attn, fs['attn_img'][l], cos4, sin4, h, cfg.gate_values, has_mix)
+                q, k, v = outs[:3]
+                if cfg.value_residual:                                   # the small element-wise tail stays with autograd
+                    if l == 0:
+                        first_v = v
+                    elif cfg.learned_mix:
+                        v = first_v.lerp(v, outs[-1][..., :h].sigmoid().transpose(1, 2)[..., None])
+                    else:
+                        v = first_v * 0.5 + v * 0.5
                 if fs['core']:
                     out = _FusedAttnCore.apply(q, k, v, fs['rng_step'], 1000 + l, p_drop)
                 else:
                     out = F.scaled_dot_product_attention(q, k, v, is_causal=True, dropout_p=p_drop)
+                if cfg.gate_values:
+                    out = out * outs[3].sigmoid()
                 x = _FusedAttnPost.apply(x, out, attn, fs['attn_img'][l], lens32)
                 norm, ff = dec.layers[2 * l + 1]
                 x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)

@@ -223,39 +223,46 @@ def ff_bwd(x, dy, ln_gamma, b1, img, d_ln_gamma, d_w1, d_b1, d_w2, d_b2, *, drop
     return dx
 
 
-def attn_supported(dim, heads, dim_head) -> bool:
-    return L.load().xtrl_attn_img_bytes(dim, heads, dim_head) > 0
+def attn_supported(dim, heads, dim_head, gate=False, mix=False) -> bool:
+    return L.load().xtrl_attn_img_bytes(dim, heads, dim_head, int(gate), int(mix)) > 0
 
 
-def attn_pack(wq, wk, wv, wo, out=None):
-    """bf16 operand images of to_q/to_k/to_v (H*16, dim) and to_out (dim, H*16); once per weight update."""
+def attn_pack(wq, wk, wv, wo, wg=None, wm=None, out=None):
+    """bf16 operand images of to_q/to_k/to_v (H*16, dim), to_out (dim, H*16) and, optionally, to_v_gate (H*16, dim) and
+    to_value_residual_mix (H, dim); once per weight update."""
     lib = L.load()
     inner, dim = wq.shape
     heads = inner // 16
-    nbytes = lib.xtrl_attn_img_bytes(dim, heads, 16)
+    nbytes = lib.xtrl_attn_img_bytes(dim, heads, 16, int(wg is not None), int(wm is not None))
     if nbytes < 0:
-        raise L.XtrlError(f'attn_pack: dim={dim}, heads={heads} is not built')
+        raise L.XtrlError(f'attn_pack: dim={dim}, heads={heads}, gate={wg is not None}, mix={wm is not None} is not built')
     out = torch.empty(nbytes, dtype=torch.uint8, device=wq.device) if out is None else out
     f32 = torch.float32
     L.check(lib.xtrl_attn_pack(_ptr(wq, f32, 'wq'), _ptr(wk, f32, 'wk'), _ptr(wv, f32, 'wv'), _ptr(wo, f32, 'wo'),
-                               _ptr(out, torch.uint8, 'img'), dim, heads, 16, _stream()), 'xtrl_attn_pack')
+                               _ptr(wg, f32, 'wg'), _ptr(wm, f32, 'wm'), _ptr(out, torch.uint8, 'img'), dim, heads, 16, _stream()),
+            'xtrl_attn_pack')
     return out
 
 
-def attn_pre_fwd(x, ln_gamma, img, cos_tab, sin_tab, heads):
-    """x (b, n, dim) fp32 -> q, k, v bf16 (b, H, n, 16): LayerNorm, projections, partial rotary on q and k."""
+def attn_pre_fwd(x, ln_gamma, img, cos_tab, sin_tab, heads, gate_bias=None, mix_bias=None):
+    """x (b, n, dim) fp32 -> q, k, v bf16 (b, H, n, 16) [, gate pre-activation (b, H, n, 16)] [, mix logits (b, n, 16)]:
+    LayerNorm, the projections (biases of the optional blocks added), partial rotary on q and k."""
     lib = L.load()
     b, n, _ = x.shape
-    qkv = torch.empty(3, b, heads, n, 16, dtype=torch.bfloat16, device=x.device)
-    f32 = torch.float32
+    bf, f32 = torch.bfloat16, torch.float32
+    nb = 4 if gate_bias is not None else 3
+    qkv = torch.empty(nb, b, heads, n, 16, dtype=bf, device=x.device)
+    mix = torch.empty(b, n, 16, dtype=bf, device=x.device) if mix_bias is not None else None
     io = L.AttnIO(x=_ptr(x, f32, 'x'), ln_gamma=_ptr(ln_gamma, f32, 'ln_gamma'), cos_tab=_ptr(cos_tab, f32, 'cos_tab'),
                   sin_tab=_ptr(sin_tab, f32, 'sin_tab'), w_img=_ptr(img, torch.uint8, 'img'),
-                  q=_ptr(qkv[0]), k=_ptr(qkv[1]), v=_ptr(qkv[2]))
+                  q=_ptr(qkv[0]), k=_ptr(qkv[1]), v=_ptr(qkv[2]), gate=_ptr(qkv[3]) if nb == 4 else None, mix=_ptr(mix),
+                  gate_bias=_ptr(gate_bias, f32, 'gate_bias'), mix_bias=_ptr(mix_bias, f32, 'mix_bias'))
     L.check(lib.xtrl_attn_pre_fwd(C.byref(io), b, n, heads, _stream()), 'xtrl_attn_pre_fwd')
-    return qkv[0], qkv[1], qkv[2]
+    return tuple(qkv[i] for i in range(nb)) + ((mix,) if mix is not None else ())
 
 
-def attn_pre_bwd(x, dq, dk, dv, ln_gamma, img, cos_tab, sin_tab, d_ln_gamma, d_wq, d_wk, d_wv):
+def attn_pre_bwd(x, dq, dk, dv, ln_gamma, img, cos_tab, sin_tab, d_ln_gamma, d_wq, d_wk, d_wv, dg=None, dmix=None,
+                 d_wg=None, d_bg=None, d_wm=None, d_bm=None):
     """dx of the LayerNorm -> projection path; parameter gradients accumulated (+=)."""
     lib = L.load()
     b, heads, n, _ = dq.shape
@@ -264,7 +271,9 @@ def attn_pre_bwd(x, dq, dk, dv, ln_gamma, img, cos_tab, sin_tab, d_ln_gamma, d_w
     io = L.AttnIO(x=_ptr(x, f32, 'x'), ln_gamma=_ptr(ln_gamma, f32, 'ln_gamma'), cos_tab=_ptr(cos_tab, f32, 'cos_tab'),
                   sin_tab=_ptr(sin_tab, f32, 'sin_tab'), w_img=_ptr(img, torch.uint8, 'img'),
                   dq=_ptr(dq, bf, 'dq'), dk=_ptr(dk, bf, 'dk'), dv=_ptr(dv, bf, 'dv'), dx=_ptr(dx, f32, 'dx'),
-                  d_ln_gamma=_ptr(d_ln_gamma, f32), d_wq=_ptr(d_wq, f32), d_wk=_ptr(d_wk, f32), d_wv=_ptr(d_wv, f32))
+                  d_ln_gamma=_ptr(d_ln_gamma, f32), d_wq=_ptr(d_wq, f32), d_wk=_ptr(d_wk, f32), d_wv=_ptr(d_wv, f32),
+                  d_gate=_ptr(dg, bf, 'dg'), d_mix=_ptr(dmix, bf, 'dmix'), d_wg=_ptr(d_wg, f32), d_bg=_ptr(d_bg, f32),
+                  d_wm=_ptr(d_wm, f32), d_bm=_ptr(d_bm, f32))
     L.check(lib.xtrl_attn_pre_bwd(C.byref(io), b, n, heads, _stream()), 'xtrl_attn_pre_bwd')
     return dx
 
