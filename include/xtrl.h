@@ -355,6 +355,12 @@ int xtrl_attn_core_supported(int32_t n, int32_t dim_head);
 int xtrl_attn_core_fwd(const xtrl_attn_core_io *io, int32_t bh, int32_t n, int32_t dim_head, void *stream);
 int xtrl_attn_core_bwd(const xtrl_attn_core_io *io, int32_t bh, int32_t n, int32_t dim_head, void *stream);
 
+/*     the Decoder's final LayerNorm (F.layer_norm(x) * gamma over dim = 48 rows), forward and backward;
+ *     d_gamma is ACCUMULATED (+=).                                                                      */
+int xtrl_ln_fwd(const float *x, const float *gamma, float *y, int64_t N, int32_t dim, void *stream);
+int xtrl_ln_bwd(const float *x, const float *dy, const float *gamma, float *dx, float *d_gamma, int64_t N, int32_t dim,
+                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

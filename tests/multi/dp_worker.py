@@ -19,7 +19,10 @@ learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_time
                     num_episodes_per_update=16, epochs=2, evolutionary=True, evolve_every=1, evolve_after_step=0,
                     latent_gene_pool=dict(dim=32, num_genes_per_island=4, num_selected=2, tournament_size=2),
                     world_model=dict(attn_dim_head=16, heads=4, depth=2, attn_gate_values=True),
-                    agent_kwargs=dict(save_path=os.path.join(tempfile.gettempdir(), f'dp_{os.getpid()}.pt')))
+                    agent_kwargs=dict(save_path=os.path.join(tempfile.gettempdir(), f'dp_{os.getpid()}.pt')),
+                    # bf16: the learn pass runs the fused tcgen05 sub-layers (weight gradients by atomicAdd -- replicas
+                    # must still agree bit for bit, because every rank applies the same all-reduced gradient)
+                    accelerate_kwargs=dict(mixed_precision='bf16') if os.environ.get('XTRL_DP_MIXED') == 'bf16' else {})
 acc = learner.accelerator
 rank, world = acc.process_index, acc.num_processes
 assert world >= 2 and dist.get_backend() == 'nccl'

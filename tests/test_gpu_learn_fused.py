@@ -56,6 +56,21 @@ def test_ff_forward_backward_vs_torch(N):
         assert maxrel(grads[k], 2 * p[k].grad) < 2 * TOL_BF16, k
 
 
+@pytest.mark.parametrize('N', [1, 129, 40000])
+def test_final_layernorm_vs_torch(N):
+    ops = xtrl().ops
+    g = torch.Generator().manual_seed(N)
+    x = (torch.randn(N, 48, generator=g) * 2 + 0.5).to(DEV).requires_grad_()
+    gamma = (1 + 0.3 * torch.randn(48, generator=g)).to(DEV).requires_grad_()
+    dy = torch.randn(N, 48, generator=g).to(DEV)
+    y_ref = F.layer_norm(x, (48,)) * gamma
+    y_ref.backward(dy)
+    assert maxrel(ops.ln_fwd(x.detach(), gamma.detach()), y_ref.detach()) < 1e-5          # fp32 kernel: the fp32 tolerance
+    dgam = torch.zeros(48, device=DEV)
+    dx = ops.ln_bwd(x.detach(), dy, gamma.detach(), dgam)
+    assert maxrel(dx, x.grad) < 1e-4 and maxrel(dgam, gamma.grad) < 1e-4
+
+
 def test_ff_dropout_mask_is_shared_by_forward_and_backward():
     """W1 = 0, b1 = c, W2 = 1: the forward output counts the kept hidden units of a token and dW2 of a one-hot dy
     lists them -- the two must agree, the keep rate must be 1-p, and the mask must follow the rng counter."""

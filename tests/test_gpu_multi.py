@@ -13,10 +13,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
-def test_data_parallel_replicas_stay_identical():
+@pytest.mark.parametrize('mixed', ('fp32', 'bf16'))
+def test_data_parallel_replicas_stay_identical(mixed):
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n}', '--master-addr', '127.0.0.1',
            '--master-port', '29533', os.path.join(ROOT, 'tests', 'multi', 'dp_worker.py')]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, XTRL_DP_MIXED=mixed))
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert 'DP_RESULT identical=True changed=True finite=True' in res.stdout

@@ -120,6 +120,8 @@ SYMBOLS = {
     'xtrl_attn_core_supported': (c_i32, [c_i32, c_i32]),
     'xtrl_attn_core_fwd': (c_i32, [C.POINTER(AttnCoreIO), c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_core_bwd': (c_i32, [C.POINTER(AttnCoreIO), c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_ln_fwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    'xtrl_ln_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
 }
 
 

@@ -46,8 +46,15 @@ class _SafeEmbedding(nn.Module):
         self.embed = nn.Embedding(n, dim)
 
     def forward(self, ids):
+        w = self.embed.weight
+        if ids.is_cuda and torch.is_grad_enabled() and w.requires_grad:
+            # learn pass: the same rows as a one-hot product, so the weight gradient is a split-K GEMM over the tokens
+            # instead of torch's sort-based embedding backward (id -1 -> the dropped column -> a zero row)
+            onehot = F.one_hot(ids + 1, w.shape[0] + 1)[..., 1:].to(w.dtype)
+            with torch.autocast('cuda', enabled=False):
+                return onehot @ w
         has = ids >= 0
-        return self.embed(ids.clamp(min=0)) * has[..., None].to(self.embed.weight.dtype)
+        return self.embed(ids.clamp(min=0)) * has[..., None].to(w.dtype)
 
 
 class _Attention(nn.Module):
@@ -119,6 +126,22 @@ class _FusedFeedForward(torch.autograd.Function):
         dx = ops.ff_bwd(x, dy.float().contiguous(), norm.gamma.data, lin1.bias.data, ctx.img, norm.gamma.grad, lin1.weight.grad,
                         lin1.bias.grad, lin2.weight.grad, lin2.bias.grad, dropout=p_drop, rng_step=rng_step, rng_key=key)
         return dx, None, None, None, None, None, None
+
+
+class _FusedNorm(torch.autograd.Function):
+    """the Decoder's final LayerNorm through xtrl_ln_fwd / _bwd (csrc/learn_ln.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, norm):
+        x = x.float().contiguous()
+        ctx.save_for_backward(x)
+        ctx.norm = norm
+        return ops.ln_fwd(x, norm.gamma.data)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,), norm = ctx.saved_tensors, ctx.norm
+        return ops.ln_bwd(x, dy.float().contiguous(), norm.gamma.data, norm.gamma.grad), None
 
 
 class _FusedAttnPre(torch.autograd.Function):
@@ -341,7 +364,7 @@ class WorldModelActorCritic(nn.Module):
             hid = ff.ff[0](norm(x))
             hid = F.dropout(hid, p_drop, self.training)
             x = x + ff.ff[2](hid)
-        embed = dec.final_norm(x)
+        embed = _FusedNorm.apply(x, dec.final_norm) if fs is not None else dec.final_norm(x)
 
         ewa = torch.cat((embed, self.action_embeds(next_actions)), dim=-1)          # :516-529
         state_pred_raw = self.to_pred(ewa)

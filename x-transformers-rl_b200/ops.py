@@ -300,6 +300,21 @@ def attn_post_bwd(dy, o, lens, img, d_wo):
     return d_o
 
 
+def ln_fwd(x, gamma):
+    """F.layer_norm(x) * gamma over the last dim (48), fp32."""
+    y = torch.empty_like(x)
+    L.check(L.load().xtrl_ln_fwd(_ptr(x, torch.float32, 'x'), _ptr(gamma, torch.float32, 'gamma'), _ptr(y), x.numel() // x.shape[-1],
+                                 x.shape[-1], _stream()), 'xtrl_ln_fwd')
+    return y
+
+
+def ln_bwd(x, dy, gamma, d_gamma):
+    dx = torch.empty_like(x)
+    L.check(L.load().xtrl_ln_bwd(_ptr(x, torch.float32, 'x'), _ptr(dy, torch.float32, 'dy'), _ptr(gamma, torch.float32, 'gamma'), _ptr(dx),
+                                 _ptr(d_gamma, torch.float32, 'd_gamma'), x.numel() // x.shape[-1], x.shape[-1], _stream()), 'xtrl_ln_bwd')
+    return dx
+
+
 def attn_core_supported(n, dim_head) -> bool:
     return bool(L.load().xtrl_attn_core_supported(n, dim_head))
 
