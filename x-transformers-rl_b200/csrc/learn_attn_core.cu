@@ -3,20 +3,23 @@
 //
 // Replaces the attention core of the teacher-forced pass inside Agent.learn (x_transformers_rl.py:928-935;
 // x-transformers Attention, SURVEY App. A.1: causal softmax(q k^T * dh^-1/2), attention dropout, @ v) and its
-// backward.  SURVEY 8f row 1.  With dh = 16 the matmuls are tiny (one K-step per 128 x 128 score tile); the
-// work is the per-score softmax arithmetic, so the design keeps that at ~10 (fwd) / ~20 (bwd) instructions per
-// score and lets the tensor core do everything else:
-//   * one CTA per (episode, head); q, k, v (and dO) live in shared memory as token-major bf16 images for the
-//     life of the CTA; 512 threads = 4 threads per query row of a 128 x 128 score tile (TMEM lane = query).
-//   * forward: pass A recomputes S tile by tile for the exact row max, pass B recomputes S, writes
-//     P = exp(S - max) (dropout applied, bf16) as an operand image and accumulates O += P V in TMEM; nothing is
-//     rescaled and every exp is evaluated once.  Saves logsumexp per row.
-//   * backward: per tile pair S and dP = dO V^T from the tensor core; the threads form P~ (dropped P) and
-//     dS = P (dP~ - delta) scale as operand images; dV += P~^T dO, dK += dS^T Q, dQ += dS K accumulate in TMEM
-//     (the transposed operands are the same images read MN-major).  dQ of all four query tiles stays in TMEM
-//     until the end: no atomics, deterministic.
+// backward.  SURVEY 8f row 1.  With dh = 16 the matmuls are tiny (one K-step per score tile); the work is the
+// per-score softmax arithmetic, so the design is about instructions per score and about never making the threads wait
+// for the tensor core:
+//   * one CTA per (episode, head); q, k, v (and dO) live in shared memory as token-major bf16 images for the life of
+//     the CTA.  16 compute warps = 4 threads per query row of a [128 queries x 64 keys] step (TMEM lane = query),
+//     plus ONE warp that only issues MMAs.  Rings of TMEM score tiles, operand images and mbarriers keep the tensor
+//     core a step or more ahead of and behind the threads; the loop has no __syncthreads.
+//   * forward: the softmax shift of a row is the bound scale * |q_row| * max|k| (Cauchy-Schwarz), so each score is visited
+//     once: P = exp(s - shift), rounded to bf16 with the dropout mask ANDed in, is written as the A operand of O += P V;
+//     the row sum is kept in fp32; logsumexp is saved.  If the bound is loose (> 40) the CTA takes an unpipelined path
+//     with an exact row-max pass first.
+//   * backward: per step S and dP~ = dO V^T from the tensor core; the threads form P~ (dropped P) and
+//     dS' = P~ dP~ - P delta as operand images; dV += P~^T dO, dK += dS'^T Q, dQ += dS' K accumulate in TMEM (the
+//     transposed operands are the same images read MN-major; scale is applied when dQ / dK are written).  dQ of all four
+//     query tiles stays in TMEM until the end: no atomics, deterministic.
 // The dropout mask is a counter hash of (call key, step counter, episode*head, query, key), regenerated in the
-// backward.
+// backward; p is quantised to 1/128.
 #include "learn_common.cuh"
 
 namespace xtrl {
