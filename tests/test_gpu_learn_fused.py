@@ -340,3 +340,17 @@ def test_attn_core_dropout_mask_is_shared_and_unbiased():
     dq, dk, dv = ops.attn_core_bwd(q, k, v, o, lse, d_o, **kw)
     for got, ref, name in ((dq, q32.grad, 'dq'), (dk, k32.grad, 'dk'), (dv, v32.grad, 'dv')):
         assert maxrel(got.float(), ref) < 2 * TOL_BF16, (name, maxrel(got.float(), ref))
+
+
+def test_fused_learn_step_falls_back_where_a_shape_is_not_built(tmp_path):
+    """sequences longer than the attention core's 512 keep torch's SDPA between the fused projection kernels; a hidden
+    size other than 48 keeps the whole torch expression -- both still learn, on the GPU, with finite gradients."""
+    g_long, s_long, _, _ = _learn_once(tmp_path, 'long', mixed=True, fused=True, wm=WM_PLAIN8, T=520, B=2)
+    g_ref, s_ref, _, _ = _learn_once(tmp_path, 'long32', mixed=False, fused=False, wm=WM_PLAIN8, T=520, B=2)
+    assert torch.isfinite(g_long).all() and float(torch.dot(g_long, g_ref) / (g_long.norm() * g_ref.norm())) > 0.999
+    from importlib import import_module
+    model_mod = import_module('x-transformers-rl_b200.model')
+    ops = xtrl().ops
+    cfg = ops.ModelConfig(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=16, dim=64, heads=4, dim_head=16, depth=1)
+    m = model_mod.WorldModelActorCritic(cfg).to(DEV)
+    assert m.fused_state() is None
