@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define XTRL_ABI_VERSION 5
+#define XTRL_ABI_VERSION 6
 
 #define XTRL_OK            0
 #define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
@@ -354,6 +354,31 @@ typedef struct xtrl_attn_core_io {
 int xtrl_attn_core_supported(int32_t n, int32_t dim_head);
 int xtrl_attn_core_fwd(const xtrl_attn_core_io *io, int32_t bh, int32_t n, int32_t dim_head, void *stream);
 int xtrl_attn_core_bwd(const xtrl_attn_core_io *io, int32_t bh, int32_t n, int32_t dim_head, void *stream);
+
+/*     two-layer head MLPs:  y = W2 . act(W1 . [src0 | src1 | (src2)] + b1) + b2,  act = SiLU on hidden units < n_silu,
+ *     identity on the rest (the done logit rides through the world-model head as one linear hidden unit).
+ *     Sources are 48-wide fp32 rows ([N][48]; src2 optionally one row per episode); weights are ZERO-PADDED dense
+ *     matrices w1 [hidden][in_dim], w2 [out][hidden] (built: (in_dim, hidden, out) in {(96|144, 96, 112), (96|144, 96, 16),
+ *     (96, 64, 32)}); y / gy: bf16 [N][out_cols], out_cols <= out.  The backward recomputes the hidden layer, returns
+ *     d_src* ([N][48] fp32 each, per token also for a per-episode src2) and ACCUMULATES (+=) the padded parameter
+ *     gradients d_w1 [hidden][in_dim], d_b1 [hidden], d_w2 [out][hidden], d_b2 [out].                              */
+typedef struct xtrl_mlp_io {
+    const float *src0, *src1, *src2;
+    int32_t src2_per_episode;
+    const float *b1, *b2;           /* [hidden], [out] (padded)                               */
+    const void *w_img;              /* xtrl_mlp_pack output                                   */
+    void *y;                        /* fwd out                                                */
+    const void *gy;                 /* bwd in                                                 */
+    float *d_src0, *d_src1, *d_src2;
+    float *d_w1, *d_b1, *d_w2, *d_b2;
+    int32_t n_silu;
+    int32_t out_cols;
+} xtrl_mlp_io;
+
+int64_t xtrl_mlp_img_bytes(int32_t in_dim, int32_t hidden, int32_t out);      /* -1 if not built */
+int xtrl_mlp_pack(const float *w1, const float *w2, void *img, int32_t in_dim, int32_t hidden, int32_t out, void *stream);
+int xtrl_mlp_fwd(const xtrl_mlp_io *io, int64_t N, int32_t n, int32_t in_dim, int32_t hidden, int32_t out, void *stream);
+int xtrl_mlp_bwd(const xtrl_mlp_io *io, int64_t N, int32_t n, int32_t in_dim, int32_t hidden, int32_t out, void *stream);
 
 /*     the Decoder's final LayerNorm (F.layer_norm(x) * gamma over dim = 48 rows), forward and backward;
  *     d_gamma is ACCUMULATED (+=).                                                                      */

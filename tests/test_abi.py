@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(L.SYMBOLS) == names, (sorted(L.SYMBOLS), names)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.xtrl_abi_version() == L.XTRL_ABI_VERSION == 5
+    assert lib.xtrl_abi_version() == L.XTRL_ABI_VERSION == 6
     assert os.path.basename(pkg.lib_path()) == 'libxtrl.so' and ROOT in pkg.lib_path()   # in-tree, not site-packages
 
 

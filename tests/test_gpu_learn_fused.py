@@ -354,3 +354,48 @@ def test_fused_learn_step_falls_back_where_a_shape_is_not_built(tmp_path):
     cfg = ops.ModelConfig(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=16, dim=64, heads=4, dim_head=16, depth=1)
     m = model_mod.WorldModelActorCritic(cfg).to(DEV)
     assert m.fused_state() is None
+
+
+# ---------------------------------------------------------------------------------------------
+# head MLPs (critic / actor / world-model + done), zero-padded dense weights
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('nsrc,hid,outp,cols,n_silu', [(2, 96, 112, 100, 96), (2, 96, 16, 4, 96), (2, 64, 32, 19, 48), (3, 96, 112, 100, 96), (3, 96, 16, 8, 96)])
+def test_head_mlp_forward_backward_vs_torch(nsrc, hid, outp, cols, n_silu):
+    ops = xtrl().ops
+    b, n = 5, 77                                                    # 385 tokens: three full tiles and a ragged one
+    N, kin = b * n, 48 * nsrc
+    g = torch.Generator().manual_seed(nsrc * 1000 + hid + cols)
+    r = lambda *s, sc=1.: (torch.randn(*s, generator=g) * sc).to(DEV)
+    w1, b1, w2, b2 = r(hid, kin, sc=kin ** -0.5), r(hid, sc=0.3), r(outp, hid, sc=hid ** -0.5), r(outp, sc=0.3)
+    w1[n_silu + 1:] = 0; b1[n_silu + 1:] = 0; w2[cols:] = 0; b2[cols:] = 0; w2[:, n_silu + 1:] = 0        # padding rows / columns are zero
+    params = [t.clone().requires_grad_() for t in (w1, b1, w2, b2)]
+    srcs = [r(N, 48).requires_grad_(), r(N, 48).requires_grad_()] + ([r(b, 48).requires_grad_()] if nsrc == 3 else [])
+    full = list(srcs[:2]) + ([srcs[2][:, None].expand(b, n, 48).reshape(N, 48)] if nsrc == 3 else [])
+    pre = torch.cat(full, -1) @ params[0].T + params[1]
+    h = torch.cat((F.silu(pre[:, :n_silu]), pre[:, n_silu:]), -1)
+    y_ref = (h @ params[2].T + params[3])[:, :cols]
+    gy = (torch.randn(N, cols, generator=g) * 1e-2).to(DEV).bfloat16()
+    y_ref.backward(gy.float())
+    img = ops.mlp_pack(w1, w2)
+    det = [s.detach() for s in srcs]
+    y = ops.mlp_fwd(det, n, b1, b2, img, cols, n_silu, per_episode2=nsrc == 3)
+    assert y.shape == (N, cols) and maxrel(y.float(), y_ref.detach()) < TOL_BF16
+    gr = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
+    dsrc = ops.mlp_bwd(det, n, gy, b1, img, *gr, n_silu, per_episode2=nsrc == 3)
+    for i in range(2):
+        assert maxrel(dsrc[i], srcs[i].grad) < 2 * TOL_BF16, i
+    if nsrc == 3:
+        assert maxrel(dsrc[2].view(b, n, 48).sum(1), srcs[2].grad) < 2 * TOL_BF16
+    names = ('w1', 'b1', 'w2', 'b2')
+    for name, got, p in zip(names, gr, params):
+        ref = p.grad
+        if name == 'w1':
+            got, ref = got[:n_silu + 1], ref[:n_silu + 1]             # rows of zero-padded hidden units carry no meaning
+        if name == 'b1':
+            got, ref = got[:n_silu + 1], ref[:n_silu + 1]
+        if name == 'w2':
+            got, ref = got[:cols, :n_silu + 1], ref[:cols, :n_silu + 1]
+        if name == 'b2':
+            got, ref = got[:cols], ref[:cols]
+        assert maxrel(got, ref) < 2 * TOL_BF16, (name, maxrel(got, ref))

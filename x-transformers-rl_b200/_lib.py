@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-XTRL_ABI_VERSION = 5
+XTRL_ABI_VERSION = 6
 XTRL_MAX_DEPTH = 16
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -89,6 +89,12 @@ class AttnCoreIO(C.Structure):
         ('rng_key', C.c_uint32), ('dropout', c_f32), ('scale', c_f32)]
 
 
+class MlpIO(C.Structure):
+    _fields_ = [('src0', c_vp), ('src1', c_vp), ('src2', c_vp), ('src2_per_episode', c_i32), ('b1', c_vp), ('b2', c_vp), ('w_img', c_vp),
+                ('y', c_vp), ('gy', c_vp), ('d_src0', c_vp), ('d_src1', c_vp), ('d_src2', c_vp), ('d_w1', c_vp), ('d_b1', c_vp),
+                ('d_w2', c_vp), ('d_b2', c_vp), ('n_silu', c_i32), ('out_cols', c_i32)]
+
+
 # every symbol include/xtrl.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'xtrl_abi_version': (c_i32, []),
@@ -120,6 +126,10 @@ SYMBOLS = {
     'xtrl_attn_core_supported': (c_i32, [c_i32, c_i32]),
     'xtrl_attn_core_fwd': (c_i32, [C.POINTER(AttnCoreIO), c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_core_bwd': (c_i32, [C.POINTER(AttnCoreIO), c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_mlp_img_bytes': (c_i64, [c_i32, c_i32, c_i32]),
+    'xtrl_mlp_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_mlp_fwd': (c_i32, [C.POINTER(MlpIO), c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_mlp_bwd': (c_i32, [C.POINTER(MlpIO), c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_ln_fwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     'xtrl_ln_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
 }

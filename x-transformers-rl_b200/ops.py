@@ -300,6 +300,51 @@ def attn_post_bwd(dy, o, lens, img, d_wo):
     return d_o
 
 
+def mlp_supported(in_dim, hidden, out) -> bool:
+    return L.load().xtrl_mlp_img_bytes(in_dim, hidden, out) > 0
+
+
+def mlp_pack(w1p, w2p, out=None):
+    """operand images of the zero-padded dense head weights w1p (hidden, in_dim), w2p (out, hidden)."""
+    lib = L.load()
+    hidden, in_dim = w1p.shape
+    outp = w2p.shape[0]
+    nbytes = lib.xtrl_mlp_img_bytes(in_dim, hidden, outp)
+    if nbytes < 0:
+        raise L.XtrlError(f'mlp_pack: ({in_dim}, {hidden}, {outp}) is not built')
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w1p.device) if out is None else out
+    L.check(lib.xtrl_mlp_pack(_ptr(w1p, torch.float32, 'w1p'), _ptr(w2p, torch.float32, 'w2p'), _ptr(out, torch.uint8, 'img'), in_dim, hidden,
+                              outp, _stream()), 'xtrl_mlp_pack')
+    return out
+
+
+def mlp_fwd(srcs, n, b1p, b2p, img, out_cols, n_silu, per_episode2=False):
+    """y (N, out_cols) bf16 = W2 act(W1 [srcs] + b1) + b2; srcs: 2 or 3 fp32 tensors of 48-wide rows (N tokens, n per episode)."""
+    lib = L.load()
+    f32 = torch.float32
+    N = srcs[0].numel() // 48
+    y = torch.empty(N, out_cols, dtype=torch.bfloat16, device=srcs[0].device)
+    io = L.MlpIO(src0=_ptr(srcs[0], f32, 'src0'), src1=_ptr(srcs[1], f32, 'src1'), src2=_ptr(srcs[2], f32, 'src2') if len(srcs) > 2 else None,
+                 src2_per_episode=int(per_episode2), b1=_ptr(b1p, f32, 'b1'), b2=_ptr(b2p, f32, 'b2'), w_img=_ptr(img, torch.uint8, 'img'),
+                 y=_ptr(y), n_silu=n_silu, out_cols=out_cols)
+    L.check(lib.xtrl_mlp_fwd(C.byref(io), N, n, 48 * len(srcs), b1p.numel(), b2p.numel(), _stream()), 'xtrl_mlp_fwd')
+    return y
+
+
+def mlp_bwd(srcs, n, gy, b1p, img, d_w1p, d_b1p, d_w2p, d_b2p, n_silu, per_episode2=False):
+    """gradients w.r.t. every source ((N, 48) fp32 each); padded parameter gradients accumulated (+=)."""
+    lib = L.load()
+    f32 = torch.float32
+    N = srcs[0].numel() // 48
+    dsrc = [torch.empty(N, 48, dtype=f32, device=gy.device) for _ in srcs]
+    io = L.MlpIO(src0=_ptr(srcs[0], f32, 'src0'), src1=_ptr(srcs[1], f32, 'src1'), src2=_ptr(srcs[2], f32, 'src2') if len(srcs) > 2 else None,
+                 src2_per_episode=int(per_episode2), b1=_ptr(b1p, f32, 'b1'), w_img=_ptr(img, torch.uint8, 'img'), gy=_ptr(gy, torch.bfloat16, 'gy'),
+                 d_src0=_ptr(dsrc[0]), d_src1=_ptr(dsrc[1]), d_src2=_ptr(dsrc[2]) if len(srcs) > 2 else None,
+                 d_w1=_ptr(d_w1p, f32), d_b1=_ptr(d_b1p, f32), d_w2=_ptr(d_w2p, f32), d_b2=_ptr(d_b2p, f32), n_silu=n_silu, out_cols=gy.shape[-1])
+    L.check(lib.xtrl_mlp_bwd(C.byref(io), N, n, 48 * len(srcs), b1p.numel(), d_b2p.numel(), _stream()), 'xtrl_mlp_bwd')
+    return dsrc
+
+
 def ln_fwd(x, gamma):
     """F.layer_norm(x) * gamma over the last dim (48), fp32."""
     y = torch.empty_like(x)
