@@ -386,6 +386,12 @@ int xtrl_ln_fwd(const float *x, const float *gamma, float *y, int64_t N, int32_t
 int xtrl_ln_bwd(const float *x, const float *dy, const float *gamma, float *dx, float *d_gamma, int64_t N, int32_t dim,
                 void *stream);
 
+/*     weight gradient of a skinny input layer into 48 outputs (+=): d_w[k][j] (out_kj = 1, embedding layout [K][48]) or
+ *     d_w[j][k] (out_kj = 0, Linear layout [48][K]) = sum_t f[t][k] dy[t][j]; f = feats [N][K] fp32, or the one-hot of
+ *     ids[t] in [-1, K) (int64, -1 = no row); d_b[j] += sum_t dy[t][j] when d_b is given.  K <= 16.                   */
+int xtrl_small_dw(const float *feats, const int64_t *ids, const float *dy, float *d_w, float *d_b, int64_t N, int32_t K,
+                  int32_t dim, int32_t out_kj, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

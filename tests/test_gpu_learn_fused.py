@@ -71,6 +71,22 @@ def test_final_layernorm_vs_torch(N):
     assert maxrel(dx, x.grad) < 1e-4 and maxrel(dgam, gamma.grad) < 1e-4
 
 
+@pytest.mark.parametrize('N,K', [(1, 4), (333, 8), (70000, 8), (70000, 4)])
+def test_skinny_weight_gradient_vs_torch(N, K):
+    ops = xtrl().ops
+    g = torch.Generator().manual_seed(N + K)
+    dy = torch.randn(N, 48, generator=g).to(DEV)
+    feats = torch.randn(N, K, generator=g).to(DEV)
+    dw, db = torch.zeros(48, K, device=DEV), torch.zeros(48, device=DEV)
+    ops.small_dw(dy, dw, feats=feats, d_b=db)
+    assert maxrel(dw, dy.double().T @ feats.double()) < 1e-4 and maxrel(db, dy.double().sum(0)) < 1e-4          # fp32 sums in another order
+    ids = torch.randint(-1, K, (N,), generator=g).to(DEV)
+    de = torch.zeros(K, 48, device=DEV)
+    ops.small_dw(dy, de, ids=ids, out_kj=True)
+    ref = torch.zeros(K + 1, 48, device=DEV, dtype=torch.float64).index_add_(0, ids + 1, dy.double())[1:]
+    assert maxrel(de, ref) < 1e-4
+
+
 def test_ff_dropout_mask_is_shared_by_forward_and_backward():
     """W1 = 0, b1 = c, W2 = 1: the forward output counts the kept hidden units of a token and dW2 of a one-hot dy
     lists them -- the two must agree, the keep rate must be 1-p, and the mask must follow the rng counter."""

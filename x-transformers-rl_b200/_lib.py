@@ -130,6 +130,7 @@ SYMBOLS = {
     'xtrl_mlp_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_mlp_fwd': (c_i32, [C.POINTER(MlpIO), c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_mlp_bwd': (c_i32, [C.POINTER(MlpIO), c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_small_dw': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_ln_fwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     'xtrl_ln_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
 }

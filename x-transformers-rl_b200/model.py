@@ -47,12 +47,8 @@ class _SafeEmbedding(nn.Module):
 
     def forward(self, ids):
         w = self.embed.weight
-        if ids.is_cuda and torch.is_grad_enabled() and w.requires_grad:
-            # learn pass: the same rows as a one-hot product, so the weight gradient is a split-K GEMM over the tokens
-            # instead of torch's sort-based embedding backward (id -1 -> the dropped column -> a zero row)
-            onehot = F.one_hot(ids + 1, w.shape[0] + 1)[..., 1:].to(w.dtype)
-            with torch.autocast('cuda', enabled=False):
-                return onehot @ w
+        if ids.is_cuda and torch.is_grad_enabled() and w.requires_grad and w.shape[0] <= 16 and w.shape[1] == 48:
+            return _EmbedRows.apply(ids, w)          # learn pass: same rows, weight gradient by one pass over dy
         has = ids >= 0
         return self.embed(ids.clamp(min=0)) * has[..., None].to(w.dtype)
 
@@ -126,6 +122,111 @@ class _FusedFeedForward(torch.autograd.Function):
         dx = ops.ff_bwd(x, dy.float().contiguous(), norm.gamma.data, lin1.bias.data, ctx.img, norm.gamma.grad, lin1.weight.grad,
                         lin1.bias.grad, lin2.weight.grad, lin2.bias.grad, dropout=p_drop, rng_step=rng_step, rng_key=key)
         return dx, None, None, None, None, None, None
+
+
+class _EmbedRows(torch.autograd.Function):
+    """rows of an embedding table by id (-1 -> zeros); the weight gradient is one xtrl_small_dw pass over dy instead of
+    torch's sort-based embedding backward."""
+
+    @staticmethod
+    def forward(ctx, ids, weight):
+        ctx.save_for_backward(ids)
+        ctx.shape = weight.shape
+        return F.embedding(ids.clamp(min=0), weight) * (ids >= 0)[..., None].to(weight.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        dw = torch.zeros(ctx.shape, dtype=torch.float32, device=dy.device)
+        return None, ops.small_dw(dy.float().contiguous(), dw, ids=ids.long().contiguous(), out_kj=True)
+
+
+class _SkinnyLinear(torch.autograd.Function):
+    """fp32 Linear from a few input features (no gradient to the input) with the weight / bias gradient as one
+    xtrl_small_dw pass."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.float().contiguous()
+        ctx.save_for_backward(x)
+        ctx.shape = weight.shape
+        return F.linear(x, weight.float(), bias.float())
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dw = torch.zeros(ctx.shape, dtype=torch.float32, device=dy.device)
+        db = torch.zeros(ctx.shape[0], dtype=torch.float32, device=dy.device)
+        ops.small_dw(dy.float().contiguous(), dw, feats=x, d_b=db)
+        return None, dw, db
+
+
+class _FracGrad(torch.autograd.Function):
+    """forward identity, backward x frac (x_transformers_rl.py:114-116) without the detach / scale / add round trip."""
+
+    @staticmethod
+    def forward(ctx, x, frac):
+        ctx.frac = frac
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.frac, None
+
+
+class _Head:
+    """device state of one fused head MLP (csrc/learn_mlp.cu): zero-padded dense copies of the head's weights, their
+    operand image, and padded gradient scratch; `refresh` follows the live parameters, `scatter` adds the scratch back
+    into the parameters' .grad views.  `rows1` / `rows2`: (parameter-weight, bias, first padded row, rows) of each layer."""
+
+    def __init__(self, in_dim, hid_p, out_p, out_cols, n_silu, dev):
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.in_dim, self.hid_p, self.out_p, self.out_cols, self.n_silu = in_dim, hid_p, out_p, out_cols, n_silu
+        self.w1, self.b1, self.w2, self.b2 = z(hid_p, in_dim), z(hid_p), z(out_p, hid_p), z(out_p)
+        self.gw1, self.gb1, self.gw2, self.gb2 = z(hid_p, in_dim), z(hid_p), z(out_p, hid_p), z(out_p)
+        self.img = torch.empty(ops.L.load().xtrl_mlp_img_bytes(in_dim, hid_p, out_p), dtype=torch.uint8, device=dev)
+        self.l1, self.l2 = [], []          # (linear, first row) ; (linear, first row, hidden columns)
+
+    def refresh(self):
+        for lin, r0 in self.l1:
+            self.w1[r0:r0 + lin.weight.shape[0]].copy_(lin.weight.data)
+            self.b1[r0:r0 + lin.weight.shape[0]].copy_(lin.bias.data)
+        for lin, r0, cols in self.l2:
+            self.w2[r0:r0 + lin.weight.shape[0], :cols].copy_(lin.weight.data)
+            self.b2[r0:r0 + lin.weight.shape[0]].copy_(lin.bias.data)
+        ops.mlp_pack(self.w1, self.w2, out=self.img)
+
+    def scatter(self):
+        for lin, r0 in self.l1:
+            lin.weight.grad += self.gw1[r0:r0 + lin.weight.shape[0]]
+            lin.bias.grad += self.gb1[r0:r0 + lin.weight.shape[0]]
+        for lin, r0, cols in self.l2:
+            lin.weight.grad += self.gw2[r0:r0 + lin.weight.shape[0], :cols]
+            lin.bias.grad += self.gb2[r0:r0 + lin.weight.shape[0]]
+
+
+class _FusedHead(torch.autograd.Function):
+    """(src0, src1[, src2 per episode]) -> head output (b, n, out_cols) bf16 through xtrl_mlp_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, head, n, src0, src1, src2):
+        srcs = [t.float().contiguous() for t in (src0, src1, src2) if t is not None]
+        ctx.save_for_backward(*srcs)
+        ctx.head, ctx.n = head, n
+        y = ops.mlp_fwd(srcs, n, head.b1, head.b2, head.img, head.out_cols, head.n_silu, per_episode2=len(srcs) == 3)
+        return y.view(-1, n, head.out_cols)
+
+    @staticmethod
+    def backward(ctx, gy):
+        srcs, head, n = list(ctx.saved_tensors), ctx.head, ctx.n
+        for t in (head.gw1, head.gb1, head.gw2, head.gb2):
+            t.zero_()
+        gy = gy.reshape(-1, head.out_cols).to(torch.bfloat16).contiguous()
+        d = ops.mlp_bwd(srcs, n, gy, head.b1, head.img, head.gw1, head.gb1, head.gw2, head.gb2, head.n_silu, per_episode2=len(srcs) == 3)
+        head.scatter()
+        b = srcs[0].numel() // (48 * n)
+        d2 = d[2].view(b, n, 48).sum(1) if len(srcs) == 3 else None
+        return None, None, d[0].view(b, n, 48), d[1].view(b, n, 48), d2
 
 
 class _FusedNorm(torch.autograd.Function):
@@ -255,7 +356,21 @@ class WorldModelActorCritic(nn.Module):
             attn_ok = ok and all(ops.attn_supported(cfg.dim, cfg.heads, cfg.dim_head, cfg.gate_values, mix(l)) for l in range(cfg.depth))
             attn_img = [torch.empty(lib.xtrl_attn_img_bytes(cfg.dim, cfg.heads, cfg.dim_head, int(cfg.gate_values), int(mix(l))),
                                     dtype=torch.uint8, device=dev) for l in range(cfg.depth)] if attn_ok else None
-            self._fused = dict(ff_img=u8(lib.xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim)), attn_img=attn_img,
+            heads = None
+            A_out = self.action_head[2].weight.shape[0]
+            kin = (3 if self.evolutionary else 2) * cfg.dim
+            n_pred = 2 * (cfg.state_dim + 1)
+            if (ok and cfg.dim == 48 and not cfg.continuous and cfg.num_bins <= 112 and A_out <= 16 and n_pred + 1 <= 32
+                    and ops.mlp_supported(kin, 96, 112) and os.environ.get('XTRL_LEARN_HEADS', '1') != '0'):
+                critic = _Head(kin, 96, 112, cfg.num_bins, 96, dev)
+                critic.l1, critic.l2 = [(self.critic_head[0], 0)], [(self.critic_head[2], 0, 96)]
+                actor = _Head(kin, 96, 16, A_out, 96, dev)
+                actor.l1, actor.l2 = [(self.action_head[0], 0)], [(self.action_head[2], 0, 96)]
+                pred = _Head(96, 64, 32, n_pred + 1, 48, dev)      # hidden unit 48 = the (linear) done logit, routed to output n_pred
+                pred.l1, pred.l2 = [(self.to_pred[0], 0), (self.to_pred_done[0], 48)], [(self.to_pred[2], 0, 48)]
+                pred.w2[n_pred, 48] = 1.
+                heads = dict(critic=critic, actor=actor, pred=pred)
+            self._fused = dict(ff_img=u8(lib.xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim)), attn_img=attn_img, heads=heads,
                                rng_step=torch.zeros((), dtype=torch.int64, device=dev)) if ok else False
         return self._fused or None
 
@@ -290,7 +405,6 @@ class WorldModelActorCritic(nn.Module):
         b, n, _ = state.shape
         h, dh, rot = cfg.heads, cfg.dim_head, cfg.dim_head // 2
         p_drop = self.dropout if self.training else 0.
-        state_embed = self.to_state_embed(state)
         x = tfm.project_in(state) + self.action_embeds(actions) + rewards[..., None] * self.reward_embed * reward_flag
         ang = torch.arange(n, device=state.device, dtype=torch.float32)[:, None] * dec.rotary_pos_emb.inv_freq[None]
         ang = ang.repeat_interleave(2, dim=-1)                       # (n, rot) interleaved (t0,t0,t1,t1,..)
@@ -366,12 +480,26 @@ class WorldModelActorCritic(nn.Module):
             x = x + ff.ff[2](hid)
         embed = _FusedNorm.apply(x, dec.final_norm) if fs is not None else dec.final_norm(x)
 
+        if fs is not None and fs['heads'] is not None:                 # the three head MLPs as tcgen05 kernels
+            hd = fs['heads']
+            for hs in hd.values():
+                hs.refresh()
+            with torch.autocast('cuda', enabled=False):
+                se32 = (_SkinnyLinear.apply(state, self.to_state_embed.weight, self.to_state_embed.bias) if cfg.state_dim <= 16
+                        else self.to_state_embed(state.float()))
+                lat = self.latent_to_embed(latent_gene.float()) if self.evolutionary else None
+            sp_done = _FusedHead.apply(hd['pred'], n, embed, self.action_embeds(next_actions), None)
+            emb_ac = _FracGrad.apply(embed, self.frac)
+            n_pred = 2 * (cfg.state_dim + 1)
+            return (_FusedHead.apply(hd['actor'], n, emb_ac, se32, lat), _FusedHead.apply(hd['critic'], n, emb_ac, se32, lat),
+                    sp_done[..., :n_pred], sp_done[..., n_pred])
+
         ewa = torch.cat((embed, self.action_embeds(next_actions)), dim=-1)          # :516-529
         state_pred_raw = self.to_pred(ewa)
         done_logit = self.to_pred_done(ewa)[..., 0]
 
         embed = embed.detach() * (1. - self.frac) + embed * self.frac             # frac_gradient :114-116,:533
-        ac_in = torch.cat((embed, state_embed), dim=-1)
+        ac_in = torch.cat((embed, self.to_state_embed(state)), dim=-1)
         if self.evolutionary:
             lat = self.latent_to_embed(latent_gene)
             ac_in = torch.cat((ac_in, lat[:, None].expand(-1, n, -1).to(ac_in.dtype)), dim=-1)

@@ -345,6 +345,15 @@ def mlp_bwd(srcs, n, gy, b1p, img, d_w1p, d_b1p, d_w2p, d_b2p, n_silu, per_episo
     return dsrc
 
 
+def small_dw(dy, d_w, *, feats=None, ids=None, d_b=None, out_kj=False):
+    """d_w (+=) sum_t f[t] (x) dy[t] for a skinny input layer (K <= 16 features, or the one-hot of ids) into 48 outputs."""
+    K = d_w.shape[0] if out_kj else d_w.shape[1]
+    L.check(L.load().xtrl_small_dw(_ptr(feats, torch.float32, 'feats'), _ptr(ids, torch.int64, 'ids'), _ptr(dy, torch.float32, 'dy'),
+                                   _ptr(d_w, torch.float32, 'd_w'), _ptr(d_b, torch.float32, 'd_b'), dy.numel() // 48, K, 48, int(out_kj),
+                                   _stream()), 'xtrl_small_dw')
+    return d_w
+
+
 def ln_fwd(x, gamma):
     """F.layer_norm(x) * gamma over the last dim (48), fp32."""
     y = torch.empty_like(x)
