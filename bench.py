@@ -345,10 +345,10 @@ def run_b200(args, w):
         result['learn'] = dict(metric='PPO learn-timesteps/sec', value=world * processed / (lms / 1e3), unit='timesteps/s',
                                epochs=args.learn_epochs, minibatch_episodes=w['learn_batch'], ms=lms, dtype=args.learn_dtype,
                                fused_sequence_model=bool(agent.fused_learn and agent.model.fused_state() is not None),
-                               note='bf16 class: sequence-model layers = libxtrl tcgen05 kernels (LN+QKV+rotary, causal attention core '
-                                    'with dropout, out-proj+mask+residual, LN+FF+GELU+dropout+residual; fwd and bwd, SURVEY 8f-1); embeddings '
-                                    'and the four heads = torch ops; GAE, fused loss fwd+bwd, optimiser+EMA = libxtrl kernels; one '
-                                    'flat-gradient all-reduce per optimiser step')
+                               note='bf16 class: sequence-model layers, final norm and the head MLPs = libxtrl tcgen05 kernels (LN+QKV+rotary, '
+                                    'causal attention core with dropout, out-proj+mask+residual, LN+FF+GELU+dropout+residual, heads; fwd and '
+                                    'bwd, SURVEY 8f-1); input projections / embedding gathers = torch ops; GAE, fused loss fwd+bwd, '
+                                    'optimiser+EMA = libxtrl kernels; one flat-gradient all-reduce per optimiser step')
 
     # ---- gene pool (evolutionary workloads): evolve_ launch + the cross-rank fitness gather ----------------------
     if evolutionary:

@@ -30,6 +30,14 @@ o, lse = ops.attn_core_fwd(q, k, v, dropout=p, rng_step=step, rng_key=1)
 z = lambda t: torch.zeros_like(t)
 gr = dict(gamma=z(gamma), w1=z(w1), b1=z(b1), w2=z(w2), b2=z(b2), wq=z(wq), wk=z(wk), wv=z(wv), wo=z(wo))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+# critic head: [embed | state_embed] (96) -> 96 -> 100 bins
+w1p, b1p, w2p, b2p = r(96, 96, sc=96 ** -.5), r(96, sc=.1), r(112, 96, sc=96 ** -.5), r(112, sc=.1)
+w2p[100:] = 0; b2p[100:] = 0
+mlp_img = ops.mlp_pack(w1p, w2p)
+src = [r(N, 48), r(N, 48)]
+gy = (r(N, 100) * 1e-3).bfloat16()
+gm = [z(w1p), z(b1p), z(w2p), z(b2p)]
+xf, dyf, dgam = x.view(N, D), dy.view(N, D), z(gamma)
 
 cases = {
     'ff_fwd': (lambda: ops.ff_fwd(x, gamma, b1, b2, ff_img, dropout=p, rng_step=step, rng_key=0), N * D * 4 * 2),
@@ -38,6 +46,10 @@ cases = {
     'attn_pre_bwd': (lambda: ops.attn_pre_bwd(x, q, k, v, gamma, at_img, cos, sin, gr['gamma'], gr['wq'], gr['wk'], gr['wv']), N * D * 4 * 2 + N * 3 * I * 2),
     'attn_post_fwd': (lambda: ops.attn_post_fwd(x, o, lens, at_img), N * D * 4 * 2 + N * I * 2),
     'attn_post_bwd': (lambda: ops.attn_post_bwd(dy, o, lens, at_img, gr['wo']), N * D * 4 + N * I * 2 * 2),
+    'mlp_critic_fwd': (lambda: ops.mlp_fwd(src, n, b1p, b2p, mlp_img, 100, 96), N * 96 * 4 + N * 100 * 2),
+    'mlp_critic_bwd': (lambda: ops.mlp_bwd(src, n, gy, b1p, mlp_img, *gm, 96), N * 96 * 4 * 2 + N * 100 * 2),
+    'ln_fwd': (lambda: ops.ln_fwd(xf, gamma), N * D * 4 * 2),
+    'ln_bwd': (lambda: ops.ln_bwd(xf, dyf, gamma, dgam), N * D * 4 * 3),
     'attn_core_fwd': (lambda: ops.attn_core_fwd(q, k, v, dropout=p, rng_step=step, rng_key=1), N * I * 2 * 4 + N * H * 4),
     'attn_core_bwd': (lambda: ops.attn_core_bwd(q, k, v, o, lse, d_o, dropout=p, rng_step=step, rng_key=1), N * I * 2 * 8 + N * H * 4),
 }
