@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
 // shared-memory order: the step images first -- dV / dK read them MN-major with M = 128 keys although a step holds
 // 64, so each read runs 16 KB past its image into the next one (the last into sQ); the accumulator rows those
 // bytes feed (TMEM lanes 64..127) are never read.
-constexpr int kBwdSmem = 4 * kStepImg + 4 * kImg + 2 * R * 4 + 128;
+constexpr int kBwdRing = 3;                   // (P~, dS) image pairs in flight
+constexpr int kBwdSmem = 2 * kBwdRing * kStepImg + 4 * kImg + 2 * R * 4 + 128;
 
 // one 16-key chunk of the backward: P~ and dS' = P~ dP~ - P delta (the softmax scale is applied to dQ / dK at the end)
 template <bool DIAG>
@@ -422,18 +423,18 @@ __device__ __forceinline__ void store_row16(__nv_bfloat16 *p, const float (&v)[1
 
 __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sStep = smem;                                             // [2] x (P~ image, dS image)
-    unsigned char *sQ = sStep + 4 * kStepImg, *sK = sQ + kImg, *sV = sK + kImg, *sdO = sV + kImg;
+    unsigned char *sStep = smem;                                             // [kBwdRing] x (P~ image, dS image)
+    unsigned char *sQ = sStep + 2 * kBwdRing * kStepImg, *sK = sQ + kImg, *sV = sK + kImg, *sdO = sV + kImg;
     float *sL = reinterpret_cast<float *>(sdO + kImg), *sDelta = sL + R;
-    uint64_t *bS = reinterpret_cast<uint64_t *>(sDelta + R), *bP = bS + 3, *bI = bP + 2;   // S / dP~ ready (ring of 3), products done, images ready (rings of 2)
+    uint64_t *bS = reinterpret_cast<uint64_t *>(sDelta + R), *bP = bS + 3, *bI = bP + kBwdRing;   // S / dP~ ready (ring of 3), products done, images ready
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bI + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q4 = warp & 3, c4 = warp >> 2, row = q4 * 32 + lane;           // c4 == 4: the MMA warp
     const int bh = blockIdx.x, n = a.n, nt = (n + 127) >> 7;
     constexpr uint32_t cS = 0, cDP = 192, cDQ = 384, cDK = 448, cDV = 480;    // S, dP~: rings of 3 x 64; dK, dV: two buffers of 16 columns
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(&bS[i], 1);
-        mbar_init(&bI[0], NCOMP / 32); mbar_init(&bI[1], NCOMP / 32);
+        for (int i = 0; i < 3 + kBwdRing; ++i) mbar_init(&bS[i], 1);
+        for (int i = 0; i < kBwdRing; ++i) mbar_init(&bI[i], NCOMP / 32);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tslot, 512);
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
         // ---- MMA warp ----
         if (lane == 0) {
             const ImgDesc dQ_(sQ), dK_(sK), dV_(sV), dO_(sdO);
-            const StepDesc dP0(sStep), dS0(sStep + kStepImg), dP1(sStep + 2 * kStepImg), dS1(sStep + 3 * kStepImg);
+            const StepDesc dP0(sStep), dS0(sStep + kStepImg);                 // slot b: + b * 2 * kStepImg bytes = + b * 2048 in descriptor units
             auto issue_s = [&](int kt, int qt, int buf, uint64_t *bar) {     // S = Q K^T and dP~ = dO V^T of one step
                 mma_bf16_ss(tbase + cS + buf * KT, dQ_.rows + qt * 128, dK_.rows + kt * 64, idesc_bf16(128, KT), 0);
                 mma_bf16_ss(tbase + cDP + buf * KT, dO_.rows + qt * 128, dV_.rows + kt * 64, idesc_bf16(128, KT), 0);
@@ -484,13 +485,16 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
             tc_fence_after();
             for (int i = 0; i < 3 && i < total; ++i) { issue_s(ik, iq, i, &bS[i]); advance(ik, iq); }
             for (int i = 0; i < total; ++i) {
-                const int b = i & 1;
-                mbar_wait(&bI[b], (i >> 1) & 1);
+                const int b = i % kBwdRing;
+                mbar_wait(&bI[b], (i / kBwdRing) & 1);
                 tc_fence_after();
-                const StepDesc &dP = b ? dP1 : dP0, &dS = b ? dS1 : dS0;
+                StepDesc dP = dP0, dS = dS0;
+                dP.kmaj += b * (2 * kStepImg / 16); dP.mnmaj += b * (2 * kStepImg / 16);
+                dS.kmaj += b * (2 * kStepImg / 16); dS.mnmaj += b * (2 * kStepImg / 16);
                 const bool first_q = qt == (kt >> 1);
                 const uint64_t doc = dO_.cols + qt * 128, qc = dQ_.cols + qt * 128, kc = dK_.cols + kt * 64;
                 const uint32_t tdv = tbase + cDV + (kt & 1) * DH, tdk = tbase + cDK + (kt & 1) * DH, tdq = tbase + cDQ + qt * DH;
+#ifndef XTRL_EXP_NOPROD
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {                                 // K = 128 queries
                     mma_bf16_ss(tdv, dP.mnmaj + s * 16, doc + s * 16, idesc_bf16(128, DH) | kIdA | kIdB, !first_q || s > 0);        // dV += P~^T dO
@@ -499,6 +503,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
 #pragma unroll
                 for (int s = 0; s < KT / 16; ++s)                             // K = 64 keys
                     mma_bf16_ss(tdq, dS.kmaj + s * 256, kc + s * 16, idesc_bf16(128, DH) | kIdB, kt > 0 || s > 0);                  // dQ += dS K
+#endif
                 mma_commit(&bP[b]);
                 if (i + 3 < total) { issue_s(ik, iq, i % 3, &bS[i % 3]); advance(ik, iq); }
                 advance(kt, qt);
@@ -516,12 +521,20 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
         };
         int kt = 0, qt = 0, pend_kt = -1, pend_ready = 0;                     // a finished key tile whose dK, dV are still in TMEM
         for (int i = 0; i < total; ++i) {
-            const int b = i & 1, sb = i % 3;
+            const int b = i % kBwdRing, sb = i % 3;
             mbar_wait(&bS[sb], (i / 3) & 1);
-            if (i >= 2) mbar_wait(&bP[b], ((i - 2) >> 1) & 1);                // the products that read these images are done
+            if (i >= kBwdRing) mbar_wait(&bP[b], ((i - kBwdRing) / kBwdRing) & 1);      // the products that read these images are done
             tc_fence_after();
-            if (pend_kt >= 0 && i >= pend_ready + 2) { write_dkv(pend_kt); pend_kt = -1; }    // products(pend_ready) completed with the wait above
-            if (qt == (kt >> 1) && kt > 0) { pend_kt = kt - 1; pend_ready = i - 1; }             // written two steps after its last product: no drain
+            const bool new_tile = qt == (kt >> 1) && kt > 0;
+            if (pend_kt >= 0 && (i >= pend_ready + kBwdRing || new_tile)) {       // dK, dV of a finished key tile: normally its products
+                if (i < pend_ready + kBwdRing) {                                 // completed with the wait above; a one-step tile in
+                    mbar_wait(&bP[pend_ready % kBwdRing], (pend_ready / kBwdRing) & 1);      // between forces an explicit wait
+                    tc_fence_after();
+                }
+                write_dkv(pend_kt);
+                pend_kt = -1;
+            }
+            if (new_tile) { pend_kt = kt - 1; pend_ready = i - 1; }
             unsigned char *imgP = sStep + b * 2 * kStepImg, *imgS = imgP + kStepImg;
             const StepGeom g = geom(qt, kt, c4);
             const int qrow = qt * 128 + row;
@@ -538,7 +551,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
             images_ready(&bI[b], lane);
             advance(kt, qt);
         }
-        mbar_wait(&bP[(total - 1) & 1], ((total - 1) >> 1) & 1);
+        mbar_wait(&bP[(total - 1) % kBwdRing], ((total - 1) / kBwdRing) & 1);
         tc_fence_after();
         if (pend_kt >= 0) write_dkv(pend_kt);
         write_dkv(2 * nt - 1);
