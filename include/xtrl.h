@@ -392,6 +392,11 @@ int xtrl_ln_bwd(const float *x, const float *dy, const float *gamma, float *dx, 
 int xtrl_small_dw(const float *feats, const int64_t *ids, const float *dy, float *d_w, float *d_b, int64_t N, int32_t K,
                   int32_t dim, int32_t out_kj, void *stream);
 
+/* sizeof of the ABI structures as this library was compiled (binding self-check): 0 xtrl_model_desc, 1 xtrl_weight_layout,
+ * 2 xtrl_step_io, 3 xtrl_loss_cfg, 4 xtrl_loss_io, 5 xtrl_pool_desc, 6 xtrl_opt_cfg, 7 xtrl_ff_io, 8 xtrl_attn_io,
+ * 9 xtrl_attn_core_io, 10 xtrl_mlp_io; -1 for anything else.                                                      */
+int64_t xtrl_struct_size(int32_t which);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,9 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert lib.xtrl_abi_version() == L.XTRL_ABI_VERSION == 6
+    for which, st in enumerate(L.ABI_STRUCTS):                       # every ctypes mirror has the size the C side compiled
+        assert lib.xtrl_struct_size(which) == C.sizeof(st), st.__name__
+    assert lib.xtrl_struct_size(len(L.ABI_STRUCTS)) == -1
     assert os.path.basename(pkg.lib_path()) == 'libxtrl.so' and ROOT in pkg.lib_path()   # in-tree, not site-packages
 
 
@@ -83,3 +86,14 @@ def test_pack_weights_roundtrip_on_cpu():
     assert torch.equal(a2[:, :3], sd['action_head.2.weight'].T) and torch.all(a2[:, 3] == 0)
     inp = blob[lay.in_proj: lay.in_proj + 8 * 2 * D].view(8, 2 * D)
     assert torch.equal(inp[:5, :D], sd['transformer.project_in.weight'].T) and torch.all(inp[5:] == 0)
+
+
+def test_learn_side_shape_queries_are_host_only():
+    """which learn-side shapes are built is answered without a GPU (the caller keeps its torch ops for the rest)."""
+    lib = xtrl().load_library()
+    assert lib.xtrl_ff_img_bytes(48, 192) == 2 * 2 * 48 * 192 and lib.xtrl_ff_img_bytes(64, 256) == -1
+    assert lib.xtrl_attn_img_bytes(48, 8, 16, 0, 0) == 2 * (48 * 128 + 384 * 48)
+    assert lib.xtrl_attn_img_bytes(48, 4, 16, 1, 1) == 2 * (48 * 64 + (4 * 64 + 16) * 48)
+    assert lib.xtrl_attn_img_bytes(48, 8, 16, 1, 1) == -1 and lib.xtrl_attn_img_bytes(48, 8, 32, 0, 0) == -1
+    assert lib.xtrl_attn_core_supported(500, 16) == 1 and lib.xtrl_attn_core_supported(513, 16) == 0
+    assert lib.xtrl_mlp_img_bytes(96, 96, 112) == 2 * (96 * 96 + 112 * 96) and lib.xtrl_mlp_img_bytes(144, 64, 32) == -1

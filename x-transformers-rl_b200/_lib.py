@@ -130,10 +130,15 @@ SYMBOLS = {
     'xtrl_mlp_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_mlp_fwd': (c_i32, [C.POINTER(MlpIO), c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_mlp_bwd': (c_i32, [C.POINTER(MlpIO), c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_struct_size': (c_i64, [c_i32]),
     'xtrl_small_dw': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_ln_fwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     'xtrl_ln_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
 }
+
+
+# order of xtrl_struct_size(which)
+ABI_STRUCTS = (ModelDesc, WeightLayout, StepIO, LossCfg, LossIO, PoolDesc, OptCfg, FfIO, AttnIO, AttnCoreIO, MlpIO)
 
 
 class XtrlError(RuntimeError):
@@ -171,6 +176,9 @@ def load():
     got = lib.xtrl_abi_version()
     if got != XTRL_ABI_VERSION:
         raise XtrlError(f'libxtrl.so ABI {got} != binding {XTRL_ABI_VERSION}')
+    for which, st in enumerate(ABI_STRUCTS):
+        if lib.xtrl_struct_size(which) != C.sizeof(st):
+            raise XtrlError(f'{st.__name__}: ctypes size {C.sizeof(st)} != library {lib.xtrl_struct_size(which)}')
     _lib = lib
     return lib
 

@@ -22,3 +22,20 @@ extern "C" int xtrl_device_sm(void) {
     XTRL_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
     return major * 10 + minor;
 }
+
+extern "C" int64_t xtrl_struct_size(int32_t which) {
+    switch (which) {
+        case 0: return sizeof(xtrl_model_desc);
+        case 1: return sizeof(xtrl_weight_layout);
+        case 2: return sizeof(xtrl_step_io);
+        case 3: return sizeof(xtrl_loss_cfg);
+        case 4: return sizeof(xtrl_loss_io);
+        case 5: return sizeof(xtrl_pool_desc);
+        case 6: return sizeof(xtrl_opt_cfg);
+        case 7: return sizeof(xtrl_ff_io);
+        case 8: return sizeof(xtrl_attn_io);
+        case 9: return sizeof(xtrl_attn_core_io);
+        case 10: return sizeof(xtrl_mlp_io);
+        default: return -1;
+    }
+}

@@ -190,9 +190,14 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         for (int c = 0; c < NOUT / 16; ++c) {                                  // dY image (zero beyond out_cols and beyond N)
             const int col0 = c * 16 + half * 8;
             float v[8];
+            const __nv_bfloat16 *src = a.gy + (size_t)t * a.out_cols + col0;
+            if (ok && col0 + 8 <= a.out_cols && (a.out_cols & 3) == 0) {        // rows are 8-byte aligned: two 8-byte loads
+                const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(src)), hi = __ldg(reinterpret_cast<const uint2 *>(src) + 1);
+                unpack8(make_uint4(lo.x, lo.y, hi.x, hi.y), v);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                v[j] = (ok && col0 + j < a.out_cols) ? __bfloat162float(a.gy[(size_t)t * a.out_cols + col0 + j]) : 0.f;
+                for (int j = 0; j < 8; ++j) v[j] = (ok && col0 + j < a.out_cols) ? __bfloat162float(src[j]) : 0.f;
+            }
             put8(sDY, row, col0 / 8, v);
         }
         fence_proxy_async();
