@@ -1,9 +1,11 @@
 """Learn-side (teacher-forced, full-sequence) world-model / actor-critic.
 
-Host-side plumbing for `Agent.learn`: the sequence model is expressed with torch ops + autograd
-(SURVEY 8f row 1 lists its fused fwd/bwd kernels as the next step); the hot arithmetic the
-north star names -- the PPO / value / world-model losses with their backward, GAE, the optimiser and
-the rollout step -- runs in libxtrl.so.  Parameter names and shapes equal the reference's
+Host-side plumbing for `Agent.learn`.  Two expressions of the same model live here: the plain torch-op one (the fp32
+class, pinned to the reference's goldens on CPU and to the oracle's autograd on the GPU), and -- `forward(fused=True)`,
+the bf16 class -- the same layers as libxtrl tcgen05 kernels strung together by small `torch.autograd.Function`s
+(attention projections, attention core, output projection, feed-forward, final norm, head MLPs,
+forward and backward; csrc/learn_*.cu).  The losses with their backward, GAE, the optimiser and the rollout step run
+in libxtrl.so in both classes.  Parameter names and shapes equal the reference's
 `WorldModelActorCritic.state_dict()` (x_transformers_rl.py:281-369 with x-transformers'
 ContinuousTransformerWrapper/Decoder underneath, :721-734) so `Agent.save/load`
 checkpoints interchange and `ops.pack_weights` can feed the rollout kernel from the same dict.
