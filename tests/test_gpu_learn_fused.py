@@ -121,17 +121,19 @@ def test_ff_dropout_mask_is_shared_by_forward_and_backward():
 # gradient for gradient against the oracle in test_gpu_learner.py) on the same weights and the same minibatch
 # ---------------------------------------------------------------------------------------------
 
-def _learn_once(tmp_path, tag, mixed, fused, wm, T=40, B=12):
+def _learn_once(tmp_path, tag, mixed, fused, wm, T=40, B=12, evolutionary=False):
     from importlib import import_module
     L = import_module('x-transformers-rl_b200.learner')
     agent_mod = import_module('x-transformers-rl_b200.agent')
     torch.manual_seed(3)
-    learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=T, batch_size=B, num_episodes_per_update=B,
-                        world_model=wm, epochs=1,
+    evo = dict(evolutionary=True, latent_gene_pool=dict(dim=32, num_genes_per_island=3, num_selected=2, tournament_size=2)) if evolutionary else {}
+    learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=T, batch_size=B // 3 if evolutionary else B,
+                        num_episodes_per_update=B // 3 if evolutionary else B, world_model=wm, epochs=1, **evo,
                         agent_kwargs=dict(save_path=str(tmp_path / f'{tag}.pt'), dropout=0.),
                         accelerate_kwargs=dict(mixed_precision='bf16') if mixed else {})
     agent, dev = learner.agent, learner.device
     agent.fused_learn = fused
+    agent.batch_size = B
     with torch.no_grad():
         g0 = torch.Generator(device=dev).manual_seed(11)
         agent.model.flat_params.add_(torch.randn(agent.model.flat_params.shape, generator=g0, device=dev) * 0.1)
@@ -145,6 +147,8 @@ def _learn_once(tmp_path, tag, mixed, fused, wm, T=40, B=12):
     for k, v in data.items():
         getattr(buf, k).copy_(torch.where(tm_mask if v.ndim == 2 else tm_mask[..., None], v, torch.zeros_like(v)))
     buf.episode_lens.copy_(lens)
+    if evolutionary:
+        buf.gene_ids.copy_(torch.arange(B, dtype=torch.int32) % 3)
     agent.keep_last_grads = True
     torch.manual_seed(0)                                   # same reward-dropout flag in every variant
     agent.learn(buf, fitnesses=None, permutations=[torch.arange(B)])
@@ -358,6 +362,18 @@ def test_attn_core_dropout_mask_is_shared_and_unbiased():
         assert maxrel(got.float(), ref) < 2 * TOL_BF16, (name, maxrel(got.float(), ref))
 
 
+def test_fused_bf16_learn_step_evolutionary_tracks_fp32(tmp_path):
+    """latent genes: the heads take a third, per-episode source (K_in 144) and hand its gradient back summed over time."""
+    g32, s32, offs, names = _learn_once(tmp_path, 'e32', mixed=False, fused=False, wm=WM_LANDER, evolutionary=True)
+    gfu, sfu, _, _ = _learn_once(tmp_path, 'efu', mixed=True, fused=True, wm=WM_LANDER, evolutionary=True)
+    assert abs(float(sfu[0] - s32[0])) < TOL_BF16 * abs(float(s32[0]))
+    assert float(torch.dot(gfu, g32) / (gfu.norm() * g32.norm())) > 0.999
+    for n, o0, o1 in zip(names, offs[:-1], offs[1:]):
+        if 'latent_to_embed' in n or 'critic_head' in n or 'action_head' in n:
+            ref = g32[o0:o1]
+            assert float((gfu[o0:o1] - ref).abs().max() / ref.abs().max().clamp(min=1e-12)) < 5e-2, n
+
+
 def test_fused_learn_step_falls_back_where_a_shape_is_not_built(tmp_path):
     """sequences longer than the attention core's 512 keep torch's SDPA between the fused projection kernels; a hidden
     size other than 48 keeps the whole torch expression -- both still learn, on the GPU, with finite gradients."""
@@ -415,3 +431,22 @@ def test_head_mlp_forward_backward_vs_torch(nsrc, hid, outp, cols, n_silu):
         if name == 'b2':
             got, ref = got[:cols], ref[:cols]
         assert maxrel(got, ref) < 2 * TOL_BF16, (name, maxrel(got, ref))
+
+
+def test_attn_core_exact_max_path_for_large_norms():
+    """when scale * max|q| * max|k| exceeds the bound threshold the forward takes its exact-row-max path: same result."""
+    ops = xtrl().ops
+    b, H, n = 1, 2, 300
+    g = torch.Generator().manual_seed(77)
+    q, k = ((torch.randn(b, H, n, 16, generator=g) * 5.).to(DEV).bfloat16() for _ in range(2))          # |q||k| / 4 ~ 100 > 40
+    v, d_o = ((torch.randn(b, H, n, 16, generator=g)).to(DEV).bfloat16() for _ in range(2))
+    assert float(0.25 * q.float().norm(dim=-1).max() * k.float().norm(dim=-1).max()) > 40.
+    q32, k32, v32 = (t.float().requires_grad_() for t in (q, k, v))
+    o_ref = _core_reference(q32, k32, v32)
+    o_ref.backward(d_o.float())
+    o, lse = ops.attn_core_fwd(q, k, v)
+    assert maxrel(o.float(), o_ref.detach()) < TOL_BF16
+    dq, dk, dv = ops.attn_core_bwd(q, k, v, o, lse, d_o)
+    for got, ref, name in ((dq, q32.grad, 'dq'), (dk, k32.grad, 'dk'), (dv, v32.grad, 'dv')):
+        err = float((got.float() - ref).abs().max() / ref.abs().max().clamp(min=0.5))
+        assert err < 2 * TOL_BF16, (name, err)
