@@ -9,7 +9,10 @@ HBM) followed by the GAE kernel over the trajectory buffer.  `value` = env-steps
 Extra keys: `roofline` (dominant kernel = wm_step_kernel, CUDA-event timed per launch), `cpu_baseline`
 (the oracle port timed on this box's host cores), `e2e` (the same rollout through the public
 Learner API with a HOST-memory env: per-step pinned H2D of states/rewards, D2H of actions),
-`learn` (PPO learn-timesteps/sec of Agent.learn on the trajectories), `clocks`, `gpu_launches`.
+`learn` (the second half of BASELINE.json's metric: PPO learn-timesteps/sec of Agent.learn on the trajectories, timed over
+>= 3 calls with CUDA events, max over ranks, with its own `roofline` (tensor pipe + HBM as built), `clocks`,
+`kernel_share`, `cpu_baseline`; `learn_value` repeats it at the top level), `replicas_identical` (N > 1), `clocks`,
+`gpu_launches`.  Both arms print the same `config` keys.
 
 Workloads (BASELINE.json configs):
   c3  4096 vectorised synthetic envs, S8 A4 T500, depth 4 heads 8 (the default; largest 1-GPU config)
@@ -37,6 +40,8 @@ sys.path.insert(0, ROOT)
 if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
     os.environ['NCCL_DEBUG'] = 'WARN'
 
+METRIC = 'env-steps/sec (rollout) and PPO learn-timesteps/sec'      # BASELINE.json's metric: `value` = the rollout half, `learn_value` = the learn half
+
 WORKLOADS = {
     'c1': dict(S=5, A=2, T=10, envs=64, reward_range=(-1., 1.), world_model=dict(attn_dim_head=16, heads=4, depth=1),
                genes=0, learn_batch=8),
@@ -61,6 +66,34 @@ def algorithmic_bytes_per_env_step(w, t, kv_bytes=4):
     wm = w['world_model']
     L, I = wm['depth'], wm['heads'] * wm['attn_dim_head']
     return L * 2 * I * (t + 2) * kv_bytes + 4 * (w['S'] + 3) + 12
+
+
+def learn_flops_per_timestep(w):
+    """forward MACs x 2, x 3 for forward + backward (c3: 2 779 776)."""
+    wm = w['world_model']
+    L, H, dh, D, S, A, K, T = wm['depth'], wm['heads'], wm['attn_dim_head'], 48, w['S'], w['A'], 100, w['T']
+    I = H * dh
+    gate, vres = int(bool(wm.get('attn_gate_values'))), int(bool(wm.get('learned_value_residual_mix')))
+    G = w.get('gene_dim', 0) if w['genes'] > 0 else 0
+    hin = (3 if G else 2) * D
+    macs = (L * (3 * D * I + I * D + 8 * D * D + gate * D * I + vres * D * H) + L * 2 * I * (T + 1) // 2 + 2 * S * D
+            + hin * 2 * D * 2 + 2 * D * A + 2 * D * K + G * D + 2 * D * D + D * 2 * (S + 1) + 2 * D)
+    return 3 * 2 * macs
+
+
+def learn_hbm_bytes_per_timestep(w):
+    """HBM bytes per token the learn pass moves AS BUILT: per layer the fp32 residual stream crosses 4
+    sub-layer kernels forward and backward, q/k/v/o and their gradients cross as bf16 [b][H][n][16]; then final norm,
+    three heads (48-wide fp32 sources in, bf16 logits out and back) and the loss kernel's rows."""
+    wm = w['world_model']
+    L, I, D, S, A, K = wm['depth'], wm['heads'] * wm['attn_dim_head'], 48, w['S'], w['A'], 100
+    res = 4 * D                                                     # one fp32 residual row
+    fwd_layer = (res + 3 * I * 2) + (3 * I * 2 + I * 2 + 4 * I // 16) + (res + I * 2 + res) + (res + res)       # pre, core, post, ff
+    bwd_layer = (2 * res + res) + (res + I * 2 + I * 2) + (5 * I * 2 + 4 * I // 16 + 3 * I * 2) + (res + 3 * I * 2 + res)   # ff, post, core, pre
+    W = A + K + 2 * (S + 1) + 1                                     # head output columns (actor, critic, world model + done)
+    heads = (3 * 2 * res + 2 * W) + (3 * 2 * res + 2 * W + 3 * 2 * res)    # fwd: sources in, bf16 logits out; bwd: + source gradients out
+    loss = 2 * 2 * W + 4 * (S + 1) + 21
+    return L * (fwd_layer + bwd_layer) + 5 * res + heads + loss            # 5 res: final LayerNorm fwd (2) + bwd (3)
 
 
 class ClockSampler:
@@ -178,14 +211,20 @@ def run_reference(args, w):
     steps, secs, threads = cpu_rollout_port(w, args.steps)
     v = steps / secs
     sample = f'{args.steps} batch-1 episode(s) x {w["T"]} timesteps, growing KV cache, oracle port (reference deps absent)'
-    print(json.dumps({
-        'impl': 'reference', 'metric': 'env-steps/sec (rollout)', 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': secs / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args.workload, w, 1),
+        'config': workload_config(args.workload, w, args.gpus),
         'cpu_baseline': dict(value=v, unit='env-steps/s', cores=threads, kind='port', sample=sample),
         'e2e': dict(value=v, unit='env-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-    }))
+    }
+    if not args.no_learn:
+        lv, n, lsecs, lthreads = cpu_learn_port(w)
+        line['learn'] = dict(metric='PPO learn-timesteps/sec', value=lv, unit='timesteps/s', cores=lthreads, kind='port',
+                             sample=f'{n} minibatch(es) of 8 episodes x {w["T"]} steps, fwd + losses + backward in {lsecs:.1f}s, oracle/restated.py')
+        line['learn_value'] = lv
+    print(json.dumps(line))
 
 
 def dense_name(dense):
@@ -231,8 +270,7 @@ def run_b200(args, w):
         if evolutionary:
             kw['latent_gene_pool'] = dict(dim=w['gene_dim'], num_genes_per_island=w['genes'],
                                           **w.get('pool', dict(num_selected=2, tournament_size=2)))
-        if args.learn_dtype == 'bf16':
-            kw['accelerate_kwargs'] = dict(mixed_precision='bf16')
+        kw['accelerate_kwargs'] = dict(mixed_precision='bf16' if args.learn_dtype == 'bf16' else 'no')
         return learner_mod.Learner(**kw)
 
     learner = make_learner(args.kv, args.dense)
@@ -277,10 +315,11 @@ def run_b200(args, w):
     gpu_launches = args.steps * (T + 1)
 
     result = {
-        'metric': 'env-steps/sec (rollout)', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
+        'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': dtype_name(args.kv, args.dense), 'data': 'synthetic',
-        'config': workload_config(args.workload, w, world, kv_cache=args.kv, dense=dense_name(args.dense)),
+        'config': workload_config(args.workload, w, world),                 # the same keys as the reference arm prints
+        'precision': dict(kv_cache=args.kv, rollout_dense=dense_name(args.dense), learn=args.learn_dtype),
         'gpu_launches': gpu_launches, 'clocks': clocks.summary(),
     }
 
@@ -312,7 +351,9 @@ def run_b200(args, w):
         if os.path.exists(prof):
             traffic = json.load(open(prof)).get(f'{args.workload}_{kv}')
         return dict(kernel='wm_step_kernel', bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                    traffic=traffic, peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s',
+                    traffic=traffic, traffic_source='profiles/r01_wm_step_traffic.json (one ncu --set full capture of the launch at t=250; '
+                                                             'a recorded number, not measured in this run)' if traffic else None,
+                    peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s',
                     bytes_per_launch=alg, launch_ms_avg=avg_s * 1e3, launch_ms_first=kern_ms[0], launch_ms_last=kern_ms[-1],
                     kernel_share_of_step=sum(kern_ms) / e0.elapsed_time(e1))
 
@@ -340,15 +381,49 @@ def run_b200(args, w):
     # ---- learn leg: PPO learn-timesteps/sec of Agent.learn on the trajectories just collected --------
     if not args.no_learn:
         buf.gene_ids.copy_(gids)
-        agent.learn(buf)                                   # warm-up (allocator, SDPA heuristics)
-        lms, processed = timed(lambda: agent.learn(buf), 1)
-        result['learn'] = dict(metric='PPO learn-timesteps/sec', value=world * processed / (lms / 1e3), unit='timesteps/s',
-                               epochs=args.learn_epochs, minibatch_episodes=w['learn_batch'], ms=lms, dtype=args.learn_dtype,
-                               fused_sequence_model=bool(agent.fused_learn and agent.model.fused_state() is not None),
-                               note='bf16 class: sequence-model layers, final norm and the head MLPs = libxtrl tcgen05 kernels (LN+QKV+rotary, '
-                                    'causal attention core with dropout, out-proj+mask+residual, LN+FF+GELU+dropout+residual, heads; fwd and '
-                                    'bwd, SURVEY 8f-1); input projections / embedding gathers = torch ops; GAE, fused loss fwd+bwd, '
-                                    'optimiser+EMA = libxtrl kernels; one flat-gradient all-reduce per optimiser step')
+        for _ in range(2):
+            agent.learn(buf)                               # warm-up (allocator, graph capture)
+        agent.event_log = []
+        with ClockSampler(dev.index or 0) as lclocks:
+            lms, processed = timed(lambda: agent.learn(buf), args.learn_steps)
+        torch.cuda.synchronize(dev)
+        fb_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in agent.event_log)
+        opt_ms = sum(e1.elapsed_time(e2) for _, e1, e2 in agent.event_log)
+        n_opt = len(agent.event_log)
+        agent.event_log = None
+        lval = world * processed * args.learn_steps / (lms / 1e3)
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+        tf_peak, hbm_peak = peaks.get('bf16_tflops_sustained', 1400.0), peaks.get('hbm_gbs', 6650.0)
+        fl, by = learn_flops_per_timestep(w), learn_hbm_bytes_per_timestep(w)
+        per_gpu = lval / world
+        fused = bool(agent.fused_learn)
+        result['learn'] = dict(
+            metric='PPO learn-timesteps/sec', value=lval, unit='timesteps/s', learn_calls=args.learn_steps, epochs=args.learn_epochs,
+            minibatch_episodes=w['learn_batch'], optimizer_steps=n_opt, ms_per_learn_call=lms / args.learn_steps,
+            ms_per_minibatch=lms / max(n_opt, 1), dtype=args.learn_dtype, fused_sequence_model=fused,
+            clocks=lclocks.summary(),
+            kernel_share=dict(fwd_bwd_graph=fb_ms / lms, optimizer=opt_ms / lms,
+                              note='CUDA events around every graph replay (prep + sequence model + loss + backward + all-reduce) and '
+                                   'every optimiser launch inside the timed calls; the rest is GAE, the minibatch gathers and host gaps'),
+            roofline=dict(bound='tensor', achieved=per_gpu * fl / 1e12, peak=tf_peak, unit='TFLOP/s', frac=per_gpu * fl / 1e12 / tf_peak,
+                          flops_per_timestep=fl, traffic=None,
+                          peak_source='MEASURED_PEAKS.json bf16_tflops_sustained (of measured; a kernel timed inside a long step)' if peaks else 'fallback',
+                          hbm_as_built=dict(bytes_per_timestep=by, achieved=per_gpu * by / 1e9, peak=hbm_peak, unit='GB/s',
+                                            frac=per_gpu * by / 1e9 / hbm_peak,
+                                            note='activation bytes the sub-layer kernels move per token as built (DESIGN.md 3.6); '
+                                                 'the attention core is instruction-bound, neither pipe')),
+            note='bf16 class (default): sequence-model layers, final norm and the head MLPs = libxtrl tcgen05 kernels (LN+QKV+rotary, '
+                 'causal attention core with dropout, out-proj+mask+residual, LN+FF+GELU+dropout+residual, heads; fwd and bwd, '
+                 'SURVEY 8f-1); GAE, fused loss fwd+bwd, one-launch clip+AdoptAtan2+EMA = libxtrl kernels; the flat-gradient '
+                 'all-reduce is the last node of the captured minibatch graph')
+        result['learn_value'] = lval
+        if world > 1:                                      # replicas must stay bit-identical (the driver's test box has one GPU)
+            st = torch.cat([agent.model.flat_params, agent.ema_params, agent.opt_m, agent.opt_v, agent.rsnorm.running_mean,
+                            agent.rsnorm.running_variance])
+            h = st.view(torch.int32).to(torch.int64).sum().reshape(1)
+            hs = [torch.empty_like(h) for _ in range(world)]
+            dist.all_gather(hs, h)
+            result['replicas_identical'] = bool(all(int(x) == int(hs[0]) for x in hs)) and bool(torch.isfinite(st).all())
 
     # ---- gene pool (evolutionary workloads): evolve_ launch + the cross-rank fitness gather ----------------------
     if evolutionary:
@@ -402,6 +477,7 @@ def main():
     ap.add_argument('--no-variants', action='store_true')
     ap.add_argument('--learn-dtype', default='bf16', choices=('fp32', 'bf16'))
     ap.add_argument('--learn-epochs', type=int, default=4)
+    ap.add_argument('--learn-steps', type=int, default=3, help='timed Agent.learn calls (after 2 warm-up calls)')
     ap.add_argument('--cpu-seconds', type=float, default=15.)
     ap.add_argument('--no-learn', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define XTRL_ABI_VERSION 6
+#define XTRL_ABI_VERSION 7
 
 #define XTRL_OK            0
 #define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
@@ -32,6 +32,8 @@ int         xtrl_abi_version(void);
 const char *xtrl_last_error(void);
 /* compute capability of the current device as major*10+minor, or a negative error.           */
 int         xtrl_device_sm(void);
+/* number of SMs of the current device (grids are sized from this, never from a constant).      */
+int         xtrl_device_num_sms(void);
 
 /* ------------------------------------------------------------------------------------------
  * (1) world-model / actor-critic rollout step
@@ -252,10 +254,13 @@ typedef struct xtrl_opt_cfg {
     float ema_mode;                 /* 0 none, 1 copy online->ema, 2 lerp with ema_decay      */
     float ema_decay;
     int32_t copy_ema_to_online;     /* update_model_with_ema_every hit                        */
+    float grad_scale;               /* gradients are read as grads * grad_scale: 1 / world size after a SUM
+                                       all-reduce (DDP's mean, :885/:981), 1 on one GPU; must be > 0        */
 } xtrl_opt_cfg;
 
 /* params, grads, m, v, param_init, ema: [n] fp32; seg_offsets [num_tensors+1] (int64, device):
- * the cautious mask is normalised per parameter tensor; workspace: 2 + num_tensors doubles.   */
+ * the cautious mask is normalised per parameter tensor; workspace: 2 + num_tensors doubles.
+ * ONE cooperative launch (two grid-wide barriers): the grid is sized to be co-resident.       */
 int64_t xtrl_opt_workspace_bytes(int32_t num_tensors);
 int xtrl_adopt_atan2_step(float *params, const float *grads, float *m, float *v, float *param_init,
                           float *ema, const int64_t *seg_offsets, int32_t num_tensors, int64_t n,

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 L = importlib.import_module('x-transformers-rl_b200.learner')
 E = importlib.import_module('x-transformers-rl_b200.envs')
 
-torch.manual_seed(0)                                   # same initial weights / genes on every rank
+torch.manual_seed(1000 + int(os.environ.get('RANK', '0')))   # DIFFERENT local init per rank: the Agent broadcasts rank 0's weights / genes
 learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=16, batch_size=8,
                     num_episodes_per_update=16, epochs=2, evolutionary=True, evolve_every=1, evolve_after_step=0,
                     latent_gene_pool=dict(dim=32, num_genes_per_island=4, num_selected=2, tournament_size=2),
@@ -22,7 +22,7 @@ learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_time
                     agent_kwargs=dict(save_path=os.path.join(tempfile.gettempdir(), f'dp_{os.getpid()}.pt')),
                     # bf16: the learn pass runs the fused tcgen05 sub-layers (weight gradients by atomicAdd -- replicas
                     # must still agree bit for bit, because every rank applies the same all-reduced gradient)
-                    accelerate_kwargs=dict(mixed_precision='bf16') if os.environ.get('XTRL_DP_MIXED') == 'bf16' else {})
+                    accelerate_kwargs=dict(mixed_precision='bf16' if os.environ.get('XTRL_DP_MIXED') == 'bf16' else 'no'))
 acc = learner.accelerator
 rank, world = acc.process_index, acc.num_processes
 assert world >= 2 and dist.get_backend() == 'nccl'

@@ -121,16 +121,16 @@ def test_ff_dropout_mask_is_shared_by_forward_and_backward():
 # gradient for gradient against the oracle in test_gpu_learner.py) on the same weights and the same minibatch
 # ---------------------------------------------------------------------------------------------
 
-def _learn_once(tmp_path, tag, mixed, fused, wm, T=40, B=12, evolutionary=False):
+def _learn_once(tmp_path, tag, mixed, fused, wm, T=40, B=12, evolutionary=False, continuous=False):
     from importlib import import_module
     L = import_module('x-transformers-rl_b200.learner')
     agent_mod = import_module('x-transformers-rl_b200.agent')
     torch.manual_seed(3)
     evo = dict(evolutionary=True, latent_gene_pool=dict(dim=32, num_genes_per_island=3, num_selected=2, tournament_size=2)) if evolutionary else {}
     learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=T, batch_size=B // 3 if evolutionary else B,
-                        num_episodes_per_update=B // 3 if evolutionary else B, world_model=wm, epochs=1, **evo,
+                        num_episodes_per_update=B // 3 if evolutionary else B, world_model=wm, epochs=1, continuous_actions=continuous, **evo,
                         agent_kwargs=dict(save_path=str(tmp_path / f'{tag}.pt'), dropout=0.),
-                        accelerate_kwargs=dict(mixed_precision='bf16') if mixed else {})
+                        accelerate_kwargs=dict(mixed_precision='bf16' if mixed else 'no'))
     agent, dev = learner.agent, learner.device
     agent.fused_learn = fused
     agent.batch_size = B
@@ -138,12 +138,15 @@ def _learn_once(tmp_path, tag, mixed, fused, wm, T=40, B=12, evolutionary=False)
         g0 = torch.Generator(device=dev).manual_seed(11)
         agent.model.flat_params.add_(torch.randn(agent.model.flat_params.shape, generator=g0, device=dev) * 0.1)
     g = torch.Generator().manual_seed(5)
-    buf = agent_mod.RolloutBuffer.allocate(T, B, 8, dev)
+    buf = agent_mod.RolloutBuffer.allocate(T, B, 8, dev, continuous_dim=4 if continuous else 0)
     lens = torch.randint(T // 2, T + 1, (B,), generator=g).int()
     tm_mask = torch.arange(T)[:, None] < lens[None, :]
     data = dict(states=torch.randn(T, B, 8, generator=g), actions=torch.randint(0, 4, (T, B), generator=g).int(),
                 log_probs=-torch.rand(T, B, generator=g) * 1.5, rewards=torch.randn(T, B, generator=g),
                 values=torch.randn(T, B, generator=g), is_boundary=torch.rand(T, B, generator=g) < 0.05)
+    if continuous:                                         # tanh-squashed float actions, per-dimension log-probs
+        data['actions'] = torch.tanh(torch.randn(T, B, 4, generator=g)) * 0.9
+        data['log_probs'] = -torch.rand(T, B, 4, generator=g) * 1.5
     for k, v in data.items():
         getattr(buf, k).copy_(torch.where(tm_mask if v.ndim == 2 else tm_mask[..., None], v, torch.zeros_like(v)))
     buf.episode_lens.copy_(lens)
@@ -374,18 +377,30 @@ def test_fused_bf16_learn_step_evolutionary_tracks_fp32(tmp_path):
             assert float((gfu[o0:o1] - ref).abs().max() / ref.abs().max().clamp(min=1e-12)) < 5e-2, n
 
 
-def test_fused_learn_step_falls_back_where_a_shape_is_not_built(tmp_path):
-    """sequences longer than the attention core's 512 keep torch's SDPA between the fused projection kernels; a hidden
-    size other than 48 keeps the whole torch expression -- both still learn, on the GPU, with finite gradients."""
-    g_long, s_long, _, _ = _learn_once(tmp_path, 'long', mixed=True, fused=True, wm=WM_PLAIN8, T=520, B=2)
+def test_unbuilt_shapes_are_errors_in_the_bf16_class(tmp_path):
+    """no multi-backend dispatch: sequences longer than the attention core's 512, or a hidden size other than 48, raise in
+    the bf16 (tensor-core) class and point at the explicit fp32 parity class -- which runs them."""
+    pkg = xtrl()
+    with pytest.raises(pkg.XtrlError, match='sequences up to 512'):
+        _learn_once(tmp_path, 'long', mixed=True, fused=True, wm=WM_PLAIN8, T=520, B=2)
     g_ref, s_ref, _, _ = _learn_once(tmp_path, 'long32', mixed=False, fused=False, wm=WM_PLAIN8, T=520, B=2)
-    assert torch.isfinite(g_long).all() and float(torch.dot(g_long, g_ref) / (g_long.norm() * g_ref.norm())) > 0.999
+    assert torch.isfinite(g_ref).all()
     from importlib import import_module
     model_mod = import_module('x-transformers-rl_b200.model')
-    ops = xtrl().ops
+    ops = pkg.ops
     cfg = ops.ModelConfig(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=16, dim=64, heads=4, dim_head=16, depth=1)
     m = model_mod.WorldModelActorCritic(cfg).to(DEV)
-    assert m.fused_state() is None
+    with pytest.raises(pkg.XtrlError, match='hidden_dim=64'):
+        m.fused_state()
+
+
+def test_fused_bf16_learn_step_continuous_tracks_fp32(tmp_path):
+    """continuous actions in the bf16 class: Gaussian actor head (2A outputs) and the nn.Linear action embedding feed the
+    fused head kernels."""
+    g32, s32, offs, names = _learn_once(tmp_path, 'c32', mixed=False, fused=False, wm=WM_PLAIN4, continuous=True)
+    gfu, sfu, _, _ = _learn_once(tmp_path, 'cfu', mixed=True, fused=True, wm=WM_PLAIN4, continuous=True)
+    assert abs(float(sfu[0] - s32[0])) < TOL_BF16 * max(1., abs(float(s32[0])))
+    assert float(torch.dot(gfu, g32) / (gfu.norm() * g32.norm())) > 0.995
 
 
 # ---------------------------------------------------------------------------------------------

@@ -71,6 +71,7 @@ def _make(tmp_path, B, T, **kw):
     Learner = _learner_cls()
     args = dict(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=T, batch_size=B,
                 num_episodes_per_update=B, world_model=LANDER_WM, epochs=1,
+                accelerate_kwargs=dict(mixed_precision='no'),          # the fp32 parity class (the default is the bf16 class)
                 agent_kwargs=dict(save_path=str(tmp_path / 'ppo.pt'), dropout=0.))
     args.update(kw)
     return Learner(**args)

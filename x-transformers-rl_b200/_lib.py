@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-XTRL_ABI_VERSION = 6
+XTRL_ABI_VERSION = 7
 XTRL_MAX_DEPTH = 16
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -69,7 +69,7 @@ class PoolDesc(C.Structure):
 class OptCfg(C.Structure):
     _fields_ = [(n, c_f32) for n in ('lr', 'init_lr', 'beta1', 'beta2', 'regen_rate', 'cautious_factor',
                                      'a', 'b', 'max_grad_norm')] + [
-        ('first_step', c_i32), ('ema_mode', c_f32), ('ema_decay', c_f32), ('copy_ema_to_online', c_i32)]
+        ('first_step', c_i32), ('ema_mode', c_f32), ('ema_decay', c_f32), ('copy_ema_to_online', c_i32), ('grad_scale', c_f32)]
 
 
 class FfIO(C.Structure):
@@ -100,6 +100,7 @@ SYMBOLS = {
     'xtrl_abi_version': (c_i32, []),
     'xtrl_last_error': (C.c_char_p, []),
     'xtrl_device_sm': (c_i32, []),
+    'xtrl_device_num_sms': (c_i32, []),
     'xtrl_wm_weight_layout': (c_i32, [C.POINTER(ModelDesc), C.POINTER(WeightLayout)]),
     'xtrl_wm_kv_cache_bytes': (c_i64, [C.POINTER(ModelDesc), c_i64]),
     'xtrl_wm_tc_weights_bytes': (c_i64, [C.POINTER(ModelDesc)]),

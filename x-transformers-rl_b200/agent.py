@@ -7,8 +7,6 @@ reads), AdoptAtan2 state (three more flat buffers), RSNorm statistics and the ge
 """
 from __future__ import annotations
 
-import os
-
 from collections import namedtuple
 from dataclasses import dataclass
 from pathlib import Path
@@ -18,7 +16,7 @@ import torch.nn.functional as F
 from torch import nn, tensor
 
 from . import ops
-from .distributed import Accelerator, all_reduce_mean_
+from .distributed import Accelerator, all_reduce_sum_, broadcast_from_rank0_, world_size
 from .evolution import LatentGenePool
 from .model import FusedPPOLoss, WorldModelActorCritic
 from .schedule import EmaSchedule
@@ -109,22 +107,30 @@ class _LearnGraph:
         self.flag = torch.ones((), device=dev)
         self.graph, self.scalars = None, None
 
-    def run(self):
+    def capture(self):
+        """two eager warm-up passes on a side stream, then the capture.  A failure here is an error (there is no eager
+        fallback): the gradient buffer is left zeroed either way, so nothing half-accumulated survives."""
         agent = self.agent
-        if self.graph is None:
+        try:
             cur = torch.cuda.current_stream(agent.device)
             side = torch.cuda.Stream(agent.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    agent._fwd_bwd(self.mb, self.flag)
-                agent.model.flat_grads.zero_()
+                    agent._fwd_bwd(self.mb, self.flag, collective=False)
             cur.wait_stream(side)
+            agent._comm.zero_()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.scalars = agent._fwd_bwd(self.mb, self.flag)
             self.graph = graph
-            agent.model.flat_grads.zero_()          # capture does not execute; start the replay from clean gradients
+        finally:
+            torch.cuda.current_stream(agent.device).synchronize()
+            agent._comm.zero_()                     # capture does not execute; start the replay from clean gradients
+
+    def run(self):
+        if self.graph is None:
+            self.capture()
         self.graph.replay()
         return self.scalars
 
@@ -193,11 +199,19 @@ class Agent(nn.Module):
         self.last_logs = None
         self.keep_last_grads = False
         self.last_grads = None
-        # bf16 learn passes run the sequence model's sub-layers as fused tcgen05 kernels (csrc/learn_*.cu); the fp32 class
-        # keeps the exact torch expression.  XTRL_LEARN_FUSED=0 is the A/B switch for measurements.
-        self.fused_learn = self.accelerator.mixed_precision == 'bf16' and os.environ.get('XTRL_LEARN_FUSED', '1') != '0'
-        self.use_cuda_graph_learn = True     # fwd + losses + bwd of a minibatch as one graph replay (launch-bound at small batches)
+        self.event_log = None                # bench.py: a list -> (start, graph done, optimiser done) CUDA events per minibatch
+        # The bf16 class (the default, see distributed.Accelerator) runs the sequence model as fused tcgen05 kernels
+        # (csrc/learn_*.cu); a shape those kernels are not built for is an ERROR there (model.fused_state), never a silent
+        # switch of back end.  mixed_precision='no' is the explicit fp32 parity class (the torch expression).
+        self.fused_learn = self.accelerator.mixed_precision == 'bf16'
+        self.use_cuda_graph_learn = True     # fwd + losses + bwd (+ the gradient all-reduce) of a minibatch as one graph replay
         self._learn_graphs = {}
+        # replicas start from rank 0's values, as DDP's wrap does in the reference (:885), whatever each rank's RNG drew
+        if self.evolutionary:
+            broadcast_from_rank0_(self.model.flat_params, self.gene_pool.genes.data)
+        else:
+            broadcast_from_rank0_(self.model.flat_params)
+        self.ema_params.copy_(self.model.flat_params)
 
     @property
     def device(self):
@@ -227,10 +241,12 @@ class Agent(nn.Module):
         for episode in memories:
             cols = list(zip(*episode))
             eps.append([torch.stack([torch.as_tensor(v) for v in col]).to(dev) for col in cols])
-        pad = lambda i: nn.utils.rnn.pad_sequence([e[i] for e in eps], batch_first=True)
-        states, actions, logp, rewards, bd, values = (pad(i) for i in range(6))
-        if values.ndim == 3:
-            values = ops.hl_decode(values.float().contiguous(), self.cfg.reward_range)       # :843
+        pad = lambda i, value=0.: nn.utils.rnn.pad_sequence([e[i] for e in eps], batch_first=True, padding_value=value)
+        states, actions, logp, rewards, bd = (pad(i) for i in range(5))
+        if eps[0][5].ndim == 2:                    # value LOGITS, zero-padded as in the reference, decoded after (:837, :843)
+            values = ops.hl_decode(pad(5).float().contiguous(), self.cfg.reward_range)
+        else:                                      # scalar values: pad with what zero logits decode to (the support's midpoint)
+            values = pad(5, float(sum(self.cfg.reward_range)) / 2.)
         return dict(states=states.float(), actions=actions.float() if self.continuous_actions else actions.int(),
                     old_log_probs=logp.float(), rewards=rewards.float(),
                     dones=bd.bool(), old_values=values.float(), lens=episode_lens.to(dev).int(),
@@ -267,18 +283,31 @@ class Agent(nn.Module):
                 idx = perm[lo:lo + self.batch_size]
                 flag = float(torch.rand(()) >= 0.5) if model.training else 1.                        # reward dropout :501
                 lg = self._learn_graph(idx.numel(), T) if self.use_cuda_graph_learn else None
+                if self.event_log is not None:
+                    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 if lg is not None:                       # static minibatch buffers -> one graph replay (fwd + losses + bwd)
                     for k in fields:
                         torch.index_select(data[k], 0, idx, out=lg.mb[k])
                     lg.flag.fill_(flag)
+                    if self.event_log is not None:
+                        evs[0].record()
                     scalars = lg.run()
                 else:
                     scalars = self._fwd_bwd({k: data[k][idx] for k in fields}, flag)
-                all_reduce_mean_(self._comm)             # gradients (+ RSNorm batch mean in the tail), one collective
+                # self._comm now holds the SUM over ranks of [gradients | RSNorm batch mean] (the all-reduce is the last
+                # node of the replayed graph); the mean's 1/world is folded into the optimiser kernel and the 9-float tail
+                inv_world = 1. / world_size()
                 if self.keep_last_grads:
-                    self.last_grads = model.flat_grads.clone()
-                self._optimizer_step()
-                rs_copy.update_(self._comm[n:])
+                    self.last_grads = model.flat_grads * inv_world
+                rs_mean = self._comm[n:] * inv_world
+                if self.event_log is not None:
+                    evs[1].record()
+                self._optimizer_step(inv_world)
+                if self.event_log is not None:
+                    evs[2].record()
+                    if lg is not None:
+                        self.event_log.append(tuple(evs))
+                rs_copy.update_(rs_mean)
                 self.last_logs = scalars
                 if (self.evolutionary and fitnesses is not None and self._step_host > self.evolve_after_step
                         and self._step_host % self.evolve_every == 0):                                # :1009-1015
@@ -289,10 +318,11 @@ class Agent(nn.Module):
         self._step_host += 1
         return self.epochs * int(data['lens'].sum().item())        # learn-timesteps processed
 
-    def _fwd_bwd(self, mb, flag):
+    def _fwd_bwd(self, mb, flag, collective=True):
         """one minibatch: prep (:903-926) -> sequence model -> fused loss kernel (fwd + grads w.r.t. head outputs) ->
-        autograd backward into the flat gradient buffer; the RSNorm batch mean lands in the buffer's tail.  No host
-        synchronisation and only static shapes, so the whole thing can be captured in a CUDA graph (_LearnGraph)."""
+        autograd backward into the flat gradient buffer; the RSNorm batch mean lands in the buffer's tail; then the one
+        SUM all-reduce of that buffer across ranks (NCCL, captured with the rest).  No host synchronisation and only
+        static shapes, so the whole thing is one CUDA graph (_LearnGraph)."""
         model, cfg = self.model, self.cfg
         S, n = cfg.state_dim, model.flat_params.numel()
         states, actions, rewards, lens = mb['states'], mb['actions'], mb['rewards'], mb['lens']
@@ -316,31 +346,27 @@ class Agent(nn.Module):
         # RSNorm batch mean over the masked rows rides in the tail of the gradient buffer (:1005, :601)
         mf = mask[..., None].float()
         self._comm[n:] = (packed * mf).sum(dim=(0, 1)) / mf.sum().clamp(min=1.)
+        if collective:
+            all_reduce_sum_(self._comm)              # gradients (+ RSNorm batch mean in the tail), one collective
         return scalars
 
     def _learn_graph(self, b, T):
-        """the captured fwd+bwd of a (b, T) minibatch, or None (capture disabled / failed -> eager launches)."""
+        """the captured fwd + bwd (+ all-reduce) of a (b, T) minibatch"""
         key = (b, T)
         if key not in self._learn_graphs:
-            try:
-                self._learn_graphs[key] = _LearnGraph(self, b, T)
-            except Exception as exc:                # host orchestration only: the same kernels run, launched one by one
-                import warnings
-                warnings.warn(f'CUDA-graph capture of the learn step failed ({exc!r}); using eager launches')
-                self._learn_graphs[key] = None
-                self.model.flat_grads.zero_()
+            self._learn_graphs[key] = _LearnGraph(self, b, T)
         return self._learn_graphs[key]
 
-    def _optimizer_step(self):
+    def _optimizer_step(self, grad_scale=1.):
         model = self.model
         mode, decay, back = self.ema_schedule.next()
         ops.adopt_atan2_step(model.flat_params, model.flat_grads, self.opt_m, self.opt_v, self.opt_param_init,
                              self.ema_params, model.seg_offsets, lr=self.lr, init_lr=self.lr, betas=self.betas,
                              regen_rate=self.regen_reg_rate, cautious_factor=self.cautious_factor,
                              max_grad_norm=self.max_grad_norm, first_step=(self.opt_steps == 0), ema_mode=mode,
-                             ema_decay=decay, copy_ema_to_online=back, workspace=self._opt_ws)
+                             ema_decay=decay, copy_ema_to_online=back, workspace=self._opt_ws, grad_scale=grad_scale)
         self.opt_steps += 1
-        model.flat_grads.zero_()
+        self._comm.zero_()
 
     # ---- deploy --------------------------------------------------------------------------------
     @torch.no_grad()

@@ -11,6 +11,17 @@ int fail(int code, const char *fmt, ...) {
     va_end(ap);
     return code;
 }
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
 }  // namespace xtrl
 
 extern "C" int xtrl_abi_version(void) { return XTRL_ABI_VERSION; }
@@ -22,6 +33,8 @@ extern "C" int xtrl_device_sm(void) {
     XTRL_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
     return major * 10 + minor;
 }
+
+extern "C" int xtrl_device_num_sms(void) { return xtrl::num_sms(); }
 
 extern "C" int64_t xtrl_struct_size(int32_t which) {
     switch (which) {

@@ -18,7 +18,7 @@ int   fail(int code, const char *fmt, ...);           // formats into the slot, 
 #define XTRL_LAUNCH_CHECK(name) do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) \
     return ::xtrl::fail(XTRL_E_CUDA, "launch of %s failed: %s", (name), cudaGetErrorString(_e)); } while (0)
 
-constexpr int kNumSMs = 148;                          // B200
+int   num_sms();                                     // SM count of the current device, queried once (api.cu); 148 on B200
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -541,7 +541,7 @@ static int launch(K kernel, const char *name, int smem, int ctas_per_sm, const A
         XTRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (nseen < 32) seen[nseen++] = (const void *)kernel;
     }
-    const int ntiles = (a.N + TOK - 1) / TOK, cap = ctas_per_sm * kNumSMs;
+    const int ntiles = (a.N + TOK - 1) / TOK, cap = ctas_per_sm * num_sms();
     kernel<<<ntiles < cap ? ntiles : cap, NT, smem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK(name);
     return XTRL_OK;

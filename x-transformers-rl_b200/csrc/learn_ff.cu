@@ -463,7 +463,7 @@ extern "C" int xtrl_ff_fwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t
     static bool attr = false;
     if (!attr) { XTRL_CUDA(cudaFuncSetAttribute(ff_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
     const int ntiles = (int)((N + TOK - 1) / TOK);
-    const int grid = ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
+    const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
     ff_fwd_kernel<<<grid, NT, kFwdSmem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("ff_fwd_kernel");
     return XTRL_OK;
@@ -481,7 +481,7 @@ extern "C" int xtrl_ff_bwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t
     static bool attr = false;
     if (!attr) { XTRL_CUDA(cudaFuncSetAttribute(ff_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
     const int ntiles = (int)((N + TOK - 1) / TOK);
-    const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
     ff_bwd_kernel<<<grid, NT, kBwdSmem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("ff_bwd_kernel");
     return XTRL_OK;

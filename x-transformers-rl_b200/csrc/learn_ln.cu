@@ -112,7 +112,7 @@ extern "C" int xtrl_small_dw(const float *feats, const int64_t *ids, const float
     if (N == 0) return XTRL_OK;
     XTRL_REQUIRE((feats != nullptr) != (ids != nullptr) && dy && d_w, XTRL_E_BADARG, "xtrl_small_dw: exactly one of feats / ids, and dy, d_w");
     const int64_t want = (N + 5 * 64 - 1) / (5 * 64);
-    const int blocks = (int)(want < 4 * kNumSMs ? want : 4 * kNumSMs);
+    const int blocks = (int)(want < 4 * num_sms() ? want : 4 * num_sms());
     if (ids) ln::small_dw_kernel<true><<<blocks, 240, 0, (cudaStream_t)stream>>>(feats, ids, dy, d_w, d_b, (int)N, K, out_kj);
     else ln::small_dw_kernel<false><<<blocks, 240, 0, (cudaStream_t)stream>>>(feats, ids, dy, d_w, d_b, (int)N, K, out_kj);
     XTRL_LAUNCH_CHECK("small_dw_kernel");
@@ -126,7 +126,7 @@ extern "C" int xtrl_ln_fwd(const float *x, const float *gamma, float *y, int64_t
     if (N == 0) return XTRL_OK;
     XTRL_REQUIRE(x && gamma && y, XTRL_E_BADARG, "xtrl_ln_fwd: null pointer");
     const int blocks = (int)((N + 127) / 128);
-    ln::ln_fwd_kernel<<<blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs, 128, 0, (cudaStream_t)stream>>>(x, gamma, y, (int)N);
+    ln::ln_fwd_kernel<<<blocks < 8 * num_sms() ? blocks : 8 * num_sms(), 128, 0, (cudaStream_t)stream>>>(x, gamma, y, (int)N);
     XTRL_LAUNCH_CHECK("ln_fwd_kernel");
     return XTRL_OK;
 }
@@ -138,7 +138,7 @@ extern "C" int xtrl_ln_bwd(const float *x, const float *dy, const float *gamma, 
     if (N == 0) return XTRL_OK;
     XTRL_REQUIRE(x && dy && gamma && dx && d_gamma, XTRL_E_BADARG, "xtrl_ln_bwd: null pointer");
     const int blocks = (int)((N + 127) / 128);
-    ln::ln_bwd_kernel<<<blocks < 4 * kNumSMs ? blocks : 4 * kNumSMs, 128, 0, (cudaStream_t)stream>>>(x, dy, gamma, dx, d_gamma, (int)N);
+    ln::ln_bwd_kernel<<<blocks < 4 * num_sms() ? blocks : 4 * num_sms(), 128, 0, (cudaStream_t)stream>>>(x, dy, gamma, dx, d_gamma, (int)N);
     XTRL_LAUNCH_CHECK("ln_bwd_kernel");
     return XTRL_OK;
 }

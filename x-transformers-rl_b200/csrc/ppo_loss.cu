@@ -550,7 +550,7 @@ extern "C" int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_i
     XTRL_REQUIRE(!io->state_pred_raw || io->target, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: state_pred_raw without target");
     XTRL_REQUIRE(!io->done_logit || io->dones, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: done_logit without dones");
     XTRL_CUDA(cudaMemsetAsync(io->workspace, 0, sizeof(double) * 16, s));
-    const int sblocks = (int)((N + 255) / 256 < 4 * kNumSMs ? (N + 255) / 256 : 4 * kNumSMs);
+    const int sblocks = (int)((N + 255) / 256 < 4 * num_sms() ? (N + 255) / 256 : 4 * num_sms());
     ppo_stats_kernel<<<sblocks, 256, 0, s>>>(io->returns, io->old_values, io->episode_lens, batch, num_timesteps, io->workspace);
     XTRL_LAUNCH_CHECK("ppo_stats_kernel");
     LossArgs la;
@@ -569,7 +569,7 @@ extern "C" int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_i
         XTRL_REQUIRE(((uintptr_t)p & 15) == 0, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: input pointers must be 16-byte aligned");
     const int64_t ntiles = (N + kTileRows - 1) / kTileRows;
     const int per_sm = smem <= 100 * 1024 ? 2 : 1;
-    const int blocks = (int)(ntiles < (int64_t)per_sm * kNumSMs ? ntiles : (int64_t)per_sm * kNumSMs);   // persistent CTAs
+    const int blocks = (int)(ntiles < (int64_t)per_sm * num_sms() ? ntiles : (int64_t)per_sm * num_sms());   // persistent CTAs
     int rc = cfg->bf16_io ? launch_loss<__nv_bfloat16>(la, KJ, blocks, smem, s) : launch_loss<float>(la, KJ, blocks, smem, s);
     if (rc) return rc;
     ppo_finalize_kernel<<<1, 1, 0, s>>>(io->workspace, io->scalars, N, cfg->state_dim + 1, cfg->autoreg_weight,
@@ -585,7 +585,7 @@ extern "C" int xtrl_hl_decode(const float *logits, float *out, int64_t n, int32_
     if (n == 0) return XTRL_OK;
     XTRL_REQUIRE(logits && out, XTRL_E_BADARG, "xtrl_hl_decode: null pointer");
     const int64_t want = (n + 7) / 8;
-    const int blocks = (int)(want < 8 * kNumSMs ? want : 8 * kNumSMs);
+    const int blocks = (int)(want < 8 * num_sms() ? want : 8 * num_sms());
     hl_decode_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, out, n, make_support(reward_min, reward_max, num_bins));
     XTRL_LAUNCH_CHECK("hl_decode_kernel");
     return XTRL_OK;

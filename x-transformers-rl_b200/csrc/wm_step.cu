@@ -838,7 +838,7 @@ extern "C" int xtrl_wm_step(const xtrl_model_desc *desc, const float *weights, v
     }
     // spread the envs so that every CTA slot of the chip (2 per SM while shared memory allows) gets the same
     // share: 4096 envs -> 14 per CTA, 293 CTAs on 296 slots instead of 256 CTAs (108 SMs with two, 40 with one)
-    const int slots = (smem <= 113 * 1024 ? 2 : 1) * kNumSMs;
+    const int slots = (smem <= 113 * 1024 ? 2 : 1) * num_sms();
     int epc = (num_envs + slots - 1) / slots;
     if (io->envs_per_cta > 0) epc = io->envs_per_cta;                 // caller overlaps several calls on different streams
     epc = epc < 1 ? 1 : (epc > kTE ? kTE : epc);

@@ -50,9 +50,12 @@ class Accelerator:
             self.device = torch.device('cuda', torch.cuda.current_device())
         else:
             self.device = torch.device('cpu')
-        if mixed_precision not in (None, 'no', 'bf16'):
-            raise ValueError(f"mixed_precision={mixed_precision!r}: only None/'no'/'bf16'")
-        self.mixed_precision = None if mixed_precision in (None, 'no') else 'bf16'
+        if mixed_precision not in (None, 'no', 'fp32', 'bf16'):
+            raise ValueError(f"mixed_precision={mixed_precision!r}: only None/'bf16' (tensor-core class) or 'no'/'fp32'")
+        # Precision classes of the learn pass (north star: fp32 1e-5, bf16 1e-2).  The DEFAULT is the bf16 class: the
+        # sequence model runs as libxtrl tcgen05 kernels (bf16 operands, fp32 accumulate, fp32 master weights).
+        # mixed_precision='no' selects the fp32 parity class explicitly (the exact torch expression, oracle-pinned).
+        self.mixed_precision = None if mixed_precision in ('no', 'fp32') else 'bf16'
         self.last_logs = None
 
     def wait_for_everyone(self):
@@ -95,11 +98,35 @@ def all_reduce_mean_(flat: torch.Tensor) -> torch.Tensor:
     return flat
 
 
+def all_reduce_sum_(flat: torch.Tensor) -> torch.Tensor:
+    """in-place SUM all-reduce of the flat gradient buffer; the 1/world factor is applied by the consumers (the
+    optimiser kernel scales gradients by xtrl_opt_cfg.grad_scale, the RSNorm tail is divided on its 9 floats)."""
+    if is_distributed():
+        dist.all_reduce(flat)
+    return flat
+
+
+def world_size() -> int:
+    return dist.get_world_size() if is_distributed() else 1
+
+
+def broadcast_from_rank0_(*tensors: torch.Tensor) -> None:
+    """what accelerator.prepare (DDP) does at wrap time in the reference (x_transformers_rl.py:885): every replica starts
+    from rank 0's values, whatever each rank's RNG produced locally."""
+    if is_distributed():
+        for t in tensors:
+            dist.broadcast(t, src=0)
+
+
 def shard_episode_genes(num_episodes_per_update: int, num_genes: int, num_processes: int, process_index: int):
     """the (episode, gene) pairs this rank rolls out: cartesian_prod(...).chunk(world)[rank]
     (x_transformers_rl.py:1146-1154)."""
     pairs = torch.cartesian_prod(torch.arange(num_episodes_per_update), torch.arange(num_genes))
     if pairs.ndim == 1:
         pairs = pairs[:, None]
-    assert pairs.size(0) >= num_processes
+    if pairs.size(0) % num_processes != 0:
+        # unequal shards would make ranks issue different numbers of gradient all-reduces (a hang) and bias the
+        # mean-of-means gradient; the reference hides this behind an all-gather + sharded DataLoader (:868-885)
+        raise ValueError(f'num_episodes_per_update * num_genes = {pairs.size(0)} must be a multiple of the number of '
+                         f'processes ({num_processes}): every rank learns from an equal shard of episodes')
     return pairs.chunk(num_processes, dim=0)[process_index].tolist()

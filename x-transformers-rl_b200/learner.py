@@ -11,7 +11,6 @@ keeps the reference's one-episode-at-a-time semantics through the same kernel wi
 """
 from __future__ import annotations
 
-import os
 import weakref
 
 import numpy as np
@@ -65,8 +64,9 @@ class Learner(nn.Module):
         self.use_cuda_graph = True       # device envs that declare cuda_graph_safe: the T-step rollout is one graph replay
         self._graphs = {}
         # host-memory envs that can split(): groups of envs stepped on separate streams through the raw-pointer loop
-        self.rollout_groups = int(os.environ.get('XTRL_ROLLOUT_GROUPS', '2'))
-        self.rollout_group_epc = os.environ.get('XTRL_GROUP_EPC', 'share')     # 'share' the CTA slots or 'fill' per call
+        self.rollout_groups = 2
+        self.rollout_group_epc = 'share'     # 'share' the CTA slots between the groups' concurrent kernels, or 'fill' per call
+        self._group_res = {}
         self.timings = dict(rollout_s=0., learn_s=0., env_steps=0, learn_timesteps=0)
 
     @property
@@ -242,9 +242,14 @@ class Learner(nn.Module):
         for g, sub in enumerate(subs):
             st = self._stepper(Bg, T, group=g)
             st.load_state_dict(sd)
-            grp.append(dict(env=sub, st=st, lo=g * Bg, hi=(g + 1) * Bg, stream=torch.cuda.Stream(dev), ev=torch.cuda.Event(),
-                            pin_s=torch.empty(Bg, S).pin_memory(), pin_r=torch.empty(Bg).pin_memory(),
-                            pin_a=torch.empty(Bg, dtype=torch.int32).pin_memory(), state=sub.reset()))
+            # streams, events and pinned staging live on the Learner: raw cudaMemcpyAsync calls are invisible to torch's
+            # caching host allocator, so these blocks must never go back to it while a copy may be in flight
+            res = self._group_res.get((g, Bg, S))
+            if res is None:
+                res = self._group_res[(g, Bg, S)] = dict(
+                    stream=torch.cuda.Stream(dev), ev=torch.cuda.Event(), pin_s=torch.empty(Bg, S).pin_memory(),
+                    pin_r=torch.empty(Bg).pin_memory(), pin_a=torch.empty(Bg, dtype=torch.int32).pin_memory())
+            grp.append(dict(env=sub, st=st, lo=g * Bg, hi=(g + 1) * Bg, state=sub.reset(), **res))
         for q in grp:
             q['stream'].wait_stream(main)
         # Hot loop on raw pointers: the per-timestep host work (2 x G times per timestep) is a numpy copy into pinned
@@ -265,7 +270,7 @@ class Learner(nn.Module):
             io.reward_flag, io.tc_weights = 1., (st.tc_weights.data_ptr() if st.tc_weights is not None else None)
             # the groups' kernels run concurrently: size each grid as if the whole batch were one call, so that a group
             # takes its share of the CTA slots instead of paying the per-CTA fixed cost twice
-            io.envs_per_cta = min(16, max(1, -(-B // (2 * 148)))) if self.rollout_group_epc == 'share' else 0
+            io.envs_per_cta = min(16, max(1, -(-B // (2 * lib.xtrl_device_num_sms())))) if self.rollout_group_epc == 'share' else 0
             q['p'] = dict(states=buf.states.data_ptr() + lo * S * f4, actions=buf.actions.data_ptr() + lo * 4,
                           logp=buf.log_probs.data_ptr() + lo * f4, values=buf.values.data_ptr() + lo * f4,
                           rewards=buf.rewards.data_ptr() + lo * f4, u=u.data_ptr() + lo * f4,
@@ -298,6 +303,7 @@ class Learner(nn.Module):
                 q['ev'].record(q['stream'])
         for q in grp:
             main.wait_stream(q['stream'])
+            q['stream'].synchronize()             # the last H2D out of the pinned blocks is done before the host may touch them again
         buf.episode_lens.fill_(T)
         return buf, buf.rewards.sum(dim=0)
 

@@ -16,8 +16,6 @@ kernel, the EMA copy and the NCCL gradient all-reduce each touch a single contig
 from __future__ import annotations
 
 
-import os
-
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -346,35 +344,47 @@ class WorldModelActorCritic(nn.Module):
         self._fused = None                       # lazily built device state of the fused learn-side kernels
 
     def fused_state(self):
-        """per-layer operand images + the dropout counter of the tcgen05 sub-layer kernels, or None when this
-        shape is not built (then the torch-op expression below runs)."""
+        """per-layer operand images, head state and the dropout counter of the tcgen05 learn-side kernels.  A shape
+        those kernels are not built for raises XtrlError -- the bf16 class never falls back to another back end."""
         if self._fused is None:
             cfg, dev = self.cfg, self.flat_params.device
-            ok = dev.type == 'cuda' and ops.ff_supported(cfg.dim, 4 * cfg.dim)
-            u8 = lambda nbytes: [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(cfg.depth)]
+            if dev.type != 'cuda':
+                raise ops.L.XtrlError('the tensor-core (bf16 class) learn pass needs CUDA parameters: there is no CPU path')
             lib = ops.L.load()
-            # layer l's projection image carries the value gate (if any) and, for l > 0, the learned value-residual mix
             mix = lambda l: bool(cfg.value_residual and cfg.learned_mix and l > 0)
-            attn_ok = ok and all(ops.attn_supported(cfg.dim, cfg.heads, cfg.dim_head, cfg.gate_values, mix(l)) for l in range(cfg.depth))
-            attn_img = [torch.empty(lib.xtrl_attn_img_bytes(cfg.dim, cfg.heads, cfg.dim_head, int(cfg.gate_values), int(mix(l))),
-                                    dtype=torch.uint8, device=dev) for l in range(cfg.depth)] if attn_ok else None
-            heads = None
             A_out = self.action_head[2].weight.shape[0]
             kin = (3 if self.evolutionary else 2) * cfg.dim
             n_pred = 2 * (cfg.state_dim + 1)
-            if (ok and cfg.dim == 48 and not cfg.continuous and cfg.num_bins <= 112 and A_out <= 16 and n_pred + 1 <= 32
-                    and ops.mlp_supported(kin, 96, 112) and os.environ.get('XTRL_LEARN_HEADS', '1') != '0'):
-                critic = _Head(kin, 96, 112, cfg.num_bins, 96, dev)
-                critic.l1, critic.l2 = [(self.critic_head[0], 0)], [(self.critic_head[2], 0, 96)]
-                actor = _Head(kin, 96, 16, A_out, 96, dev)
-                actor.l1, actor.l2 = [(self.action_head[0], 0)], [(self.action_head[2], 0, 96)]
-                pred = _Head(96, 64, 32, n_pred + 1, 48, dev)      # hidden unit 48 = the (linear) done logit, routed to output n_pred
-                pred.l1, pred.l2 = [(self.to_pred[0], 0), (self.to_pred_done[0], 48)], [(self.to_pred[2], 0, 48)]
-                pred.w2[n_pred, 48] = 1.
-                heads = dict(critic=critic, actor=actor, pred=pred)
-            self._fused = dict(ff_img=u8(lib.xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim)), attn_img=attn_img, heads=heads,
-                               rng_step=torch.zeros((), dtype=torch.int64, device=dev)) if ok else False
-        return self._fused or None
+            problems = []
+            if cfg.dim != 48 or not ops.ff_supported(cfg.dim, 4 * cfg.dim):
+                problems.append(f'hidden_dim={cfg.dim} (built: 48)')
+            elif not all(ops.attn_supported(cfg.dim, cfg.heads, cfg.dim_head, cfg.gate_values, mix(l)) for l in range(cfg.depth)):
+                problems.append(f'heads={cfg.heads}, dim_head={cfg.dim_head} (built: dim_head 16, heads in (4, 8))')
+            if cfg.num_bins > 112:
+                problems.append(f'critic bins={cfg.num_bins} (built: <= 112)')
+            if A_out > 16:
+                problems.append(f'actor head width={A_out} (built: <= 16)')
+            if n_pred + 1 > 32 or cfg.state_dim > 16:
+                problems.append(f'state_dim={cfg.state_dim} (built: <= 15)')
+            if not problems and not (ops.mlp_supported(kin, 96, 112) and ops.mlp_supported(96, 64, 32)):
+                problems.append(f'head input width {kin}')
+            if problems:
+                raise ops.L.XtrlError('the tensor-core (bf16 class) learn kernels are not built for ' + '; '.join(problems) +
+                                      ". Pass accelerate_kwargs=dict(mixed_precision='no') for the fp32 parity class.")
+            u8 = lambda nbytes: [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(cfg.depth)]
+            attn_img = [torch.empty(lib.xtrl_attn_img_bytes(cfg.dim, cfg.heads, cfg.dim_head, int(cfg.gate_values), int(mix(l))),
+                                    dtype=torch.uint8, device=dev) for l in range(cfg.depth)]
+            critic = _Head(kin, 96, 112, cfg.num_bins, 96, dev)
+            critic.l1, critic.l2 = [(self.critic_head[0], 0)], [(self.critic_head[2], 0, 96)]
+            actor = _Head(kin, 96, 16, A_out, 96, dev)
+            actor.l1, actor.l2 = [(self.action_head[0], 0)], [(self.action_head[2], 0, 96)]
+            pred = _Head(96, 64, 32, n_pred + 1, 48, dev)      # hidden unit 48 = the (linear) done logit, routed to output n_pred
+            pred.l1, pred.l2 = [(self.to_pred[0], 0), (self.to_pred_done[0], 48)], [(self.to_pred[2], 0, 48)]
+            pred.w2[n_pred, 48] = 1.
+            self._fused = dict(ff_img=u8(lib.xtrl_ff_img_bytes(cfg.dim, 4 * cfg.dim)), attn_img=attn_img,
+                               heads=dict(critic=critic, actor=actor, pred=pred),
+                               rng_step=torch.zeros((), dtype=torch.int64, device=dev))
+        return self._fused
 
     def _bind(self, flat, flat_grad):
         self.flat_params, self.flat_grads = flat, flat_grad
@@ -414,47 +424,11 @@ class WorldModelActorCritic(nn.Module):
         # Episodes are right-padded, so every padded key lies in the causal future of every valid query:
         # the causal flag alone reproduces the reference's key-padding + causal mask on valid rows, and
         # padded rows are zeroed after to_out exactly as the reference does (App. A.1) -- no mask tensor.
+        if fused:
+            return self._forward_fused(x, state, next_actions, mask, latent_gene, ang, p_drop)
         first_v = None
-        fs = self.fused_state() if fused else None
-        if fs is not None:                        # bf16 operand images follow the current weights; one counter bump per pass
-            fs['rng_step'].add_(1)
-            for l in range(cfg.depth):
-                ff = dec.layers[2 * l + 1][1]
-                ops.ff_pack(ff.ff[0][0].weight.data, ff.ff[2].weight.data, out=fs['ff_img'][l])
-                if fs['attn_img'] is not None:
-                    at = dec.layers[2 * l][1]
-                    ops.attn_pack(at.to_q.weight.data, at.to_k.weight.data, at.to_v.weight.data, at.to_out.weight.data,
-                                  wg=at.to_v_gate.weight.data if cfg.gate_values else None,
-                                  wm=at.to_value_residual_mix[0].weight.data if (cfg.value_residual and cfg.learned_mix and l > 0) else None,
-                                  out=fs['attn_img'][l])
-            if fs['attn_img'] is not None:
-                fs['core'] = ops.attn_core_supported(n, dh) and os.environ.get('XTRL_LEARN_CORE', '1') != '0'
-                lens32 = mask.sum(dim=1, dtype=torch.int32)          # episodes are right-padded: mask == position < length
-                ang4 = ang[:, ::2].contiguous()
-                cos4, sin4 = ang4.cos(), ang4.sin()
         for l in range(cfg.depth):
             norm, attn = dec.layers[2 * l]
-            if fs is not None and fs['attn_img'] is not None:
-                has_mix = bool(cfg.value_residual and cfg.learned_mix and l > 0)
-                outs = _FusedAttnPre.apply(x, norm, attn, fs['attn_img'][l], cos4, sin4, h, cfg.gate_values, has_mix)
-                q, k, v = outs[:3]
-                if cfg.value_residual:                                   # the small element-wise tail stays with autograd
-                    if l == 0:
-                        first_v = v
-                    elif cfg.learned_mix:
-                        v = first_v.lerp(v, outs[-1][..., :h].sigmoid().transpose(1, 2)[..., None])
-                    else:
-                        v = first_v * 0.5 + v * 0.5
-                if fs['core']:
-                    out = _FusedAttnCore.apply(q, k, v, fs['rng_step'], 1000 + l, p_drop)
-                else:
-                    out = F.scaled_dot_product_attention(q, k, v, is_causal=True, dropout_p=p_drop)
-                if cfg.gate_values:
-                    out = out * outs[3].sigmoid()
-                x = _FusedAttnPost.apply(x, out, attn, fs['attn_img'][l], lens32)
-                norm, ff = dec.layers[2 * l + 1]
-                x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)
-                continue
             xn = norm(x)
             split = lambda t: t.view(b, n, h, dh).transpose(1, 2)
             q, k, v = split(attn.to_q(xn)), split(attn.to_k(xn)), split(attn.to_v(xn))
@@ -474,27 +448,10 @@ class WorldModelActorCritic(nn.Module):
             out = attn.to_out(out).masked_fill(~mask[..., None], 0.)
             x = x + out
             norm, ff = dec.layers[2 * l + 1]
-            if fs is not None:
-                x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)
-                continue
             hid = ff.ff[0](norm(x))
             hid = F.dropout(hid, p_drop, self.training)
             x = x + ff.ff[2](hid)
-        embed = _FusedNorm.apply(x, dec.final_norm) if fs is not None else dec.final_norm(x)
-
-        if fs is not None and fs['heads'] is not None:                 # the three head MLPs as tcgen05 kernels
-            hd = fs['heads']
-            for hs in hd.values():
-                hs.refresh()
-            with torch.autocast('cuda', enabled=False):
-                se32 = (_SkinnyLinear.apply(state, self.to_state_embed.weight, self.to_state_embed.bias) if cfg.state_dim <= 16
-                        else self.to_state_embed(state.float()))
-                lat = self.latent_to_embed(latent_gene.float()) if self.evolutionary else None
-            sp_done = _FusedHead.apply(hd['pred'], n, embed, self.action_embeds(next_actions), None)
-            emb_ac = _FracGrad.apply(embed, self.frac)
-            n_pred = 2 * (cfg.state_dim + 1)
-            return (_FusedHead.apply(hd['actor'], n, emb_ac, se32, lat), _FusedHead.apply(hd['critic'], n, emb_ac, se32, lat),
-                    sp_done[..., :n_pred], sp_done[..., n_pred])
+        embed = dec.final_norm(x)
 
         ewa = torch.cat((embed, self.action_embeds(next_actions)), dim=-1)          # :516-529
         state_pred_raw = self.to_pred(ewa)
@@ -506,6 +463,60 @@ class WorldModelActorCritic(nn.Module):
             lat = self.latent_to_embed(latent_gene)
             ac_in = torch.cat((ac_in, lat[:, None].expand(-1, n, -1).to(ac_in.dtype)), dim=-1)
         return self.action_head(ac_in), self.critic_head(ac_in), state_pred_raw, done_logit
+
+
+    def _forward_fused(self, x, state, next_actions, mask, latent_gene, ang, p_drop):
+        """the bf16 class: every sub-layer of the Decoder, the final norm and the three head MLPs are libxtrl tcgen05
+        kernels behind autograd seams (csrc/learn_*.cu).  Unsupported shapes raise (fused_state / attn core)."""
+        cfg, dec = self.cfg, self.transformer.attn_layers
+        b, n, _ = state.shape
+        h, dh = cfg.heads, cfg.dim_head
+        fs = self.fused_state()
+        if not ops.attn_core_supported(n, dh):
+            raise ops.L.XtrlError(f'the tensor-core attention core is built for dim_head=16 and sequences up to 512 (got dim_head={dh}, '
+                                  f"n={n}). Pass accelerate_kwargs=dict(mixed_precision='no') for the fp32 parity class.")
+        fs['rng_step'].add_(1)                    # one counter bump per pass: fresh dropout masks on every graph replay
+        for l in range(cfg.depth):                # bf16 operand images follow the current weights
+            ff, at = dec.layers[2 * l + 1][1], dec.layers[2 * l][1]
+            ops.ff_pack(ff.ff[0][0].weight.data, ff.ff[2].weight.data, out=fs['ff_img'][l])
+            ops.attn_pack(at.to_q.weight.data, at.to_k.weight.data, at.to_v.weight.data, at.to_out.weight.data,
+                          wg=at.to_v_gate.weight.data if cfg.gate_values else None,
+                          wm=at.to_value_residual_mix[0].weight.data if (cfg.value_residual and cfg.learned_mix and l > 0) else None,
+                          out=fs['attn_img'][l])
+        lens32 = mask.sum(dim=1, dtype=torch.int32)          # episodes are right-padded: mask == position < length
+        ang4 = ang[:, ::2].contiguous()
+        cos4, sin4 = ang4.cos(), ang4.sin()
+        first_v = None
+        for l in range(cfg.depth):
+            norm, attn = dec.layers[2 * l]
+            has_mix = bool(cfg.value_residual and cfg.learned_mix and l > 0)
+            outs = _FusedAttnPre.apply(x, norm, attn, fs['attn_img'][l], cos4, sin4, h, cfg.gate_values, has_mix)
+            q, k, v = outs[:3]
+            if cfg.value_residual:                                   # the small element-wise tail stays with autograd
+                if l == 0:
+                    first_v = v
+                elif cfg.learned_mix:
+                    v = first_v.lerp(v, outs[-1][..., :h].sigmoid().transpose(1, 2)[..., None])
+                else:
+                    v = first_v * 0.5 + v * 0.5
+            out = _FusedAttnCore.apply(q, k, v, fs['rng_step'], 1000 + l, p_drop)
+            if cfg.gate_values:
+                out = out * outs[3].sigmoid()
+            x = _FusedAttnPost.apply(x, out, attn, fs['attn_img'][l], lens32)
+            norm, ff = dec.layers[2 * l + 1]
+            x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)
+        embed = _FusedNorm.apply(x, dec.final_norm)
+        hd = fs['heads']
+        for hs in hd.values():
+            hs.refresh()
+        with torch.autocast('cuda', enabled=False):
+            se32 = _SkinnyLinear.apply(state, self.to_state_embed.weight, self.to_state_embed.bias)
+            lat = self.latent_to_embed(latent_gene.float()) if self.evolutionary else None
+        sp_done = _FusedHead.apply(hd['pred'], n, embed, self.action_embeds(next_actions), None)
+        emb_ac = _FracGrad.apply(embed, self.frac)
+        n_pred = 2 * (cfg.state_dim + 1)
+        return (_FusedHead.apply(hd['actor'], n, emb_ac, se32, lat), _FusedHead.apply(hd['critic'], n, emb_ac, se32, lat),
+                sp_done[..., :n_pred], sp_done[..., n_pred])
 
 
 class FusedPPOLoss(torch.autograd.Function):
