@@ -114,3 +114,26 @@ def random_state_dict(cfg: R.Config, seed=0, scale=0.2):
         sd[f'{pf}.1.ff.2.weight'] = rn(D, 4 * D)
         sd[f'{pf}.1.ff.2.bias'] = rn(D)
     return sd
+
+
+# ---- goldens of the reference's own Agent.learn (oracle/golden_learn.py) ----------------------
+
+def learn_golden(name):
+    """-> (z, meta, oracle Config, sd0 (dict of float tensors), data dict) of tests/golden/learn_<name>.npz"""
+    z = load_golden(f'learn_{name}.npz')
+    meta = json.loads(str(z['config_json']))
+    cfg = oracle_config(meta['learner'])
+    sd0 = {k: v for k, v in split(z, 'sd0').items() if v.is_floating_point() and 'inv_freq' not in k}
+    i = split(z, 'in')
+    data = dict(states=i['states'], actions=i['actions'], log_probs=i['log_probs'], rewards=i['rewards'],
+                is_boundary=i['is_boundary'].bool(), value_logits=i['value_logits'], lens=i['lens'], gene_ids=i['gene_ids'])
+    return z, meta, cfg, sd0, data
+
+
+def learn_golden_noises(z, u):
+    """the evolve_ noise triples recorded for update u, in call order"""
+    out, j = [], 0
+    while f'u{u}/noise{j}/tourn' in z:
+        out.append(tuple(t(z[f'u{u}/noise{j}/{k}']) for k in ('tourn', 'cross', 'mut')))
+        j += 1
+    return out

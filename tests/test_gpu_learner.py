@@ -176,15 +176,17 @@ def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary, continuou
     assert rel_err(torch.tensor(got_total), loss.detach()) < 1e-4
     names = [n for n, _ in agent.model.named_parameters()]
     offs = agent.model._offsets
-    worst = 0.
+    worst, worst_name = 0., ''
     for n, o0, o1 in zip(names, offs[:-1], offs[1:]):
         want = sd[n].grad if sd[n].grad is not None else torch.zeros_like(sd[n])
         got = agent.last_grads[o0:o1].view(want.shape).cpu()
         if want.abs().max() < 1e-7:
             assert got.abs().max() < 1e-6, n
             continue
-        worst = max(worst, rel_err(got, want))
+        if rel_err(got, want) > worst:
+            worst, worst_name = rel_err(got, want), n
         assert rel_err(got, want) < 2e-3, n          # whole-model fp32 fwd+bwd on two different back ends
+    print('GRAD_WORST', evolutionary, continuous, worst_name, worst)
     # RSNorm copy was updated from the batch mean of the already-normalised rows
     m2, v2, _ = R.rsnorm_update(packed_masked.detach(), mean, var, 1)
     assert rel_err(agent.rsnorm.running_mean.cpu(), m2) < 1e-4
@@ -242,3 +244,91 @@ def test_pipelined_host_env_rollout_equals_single_stream(tmp_path):
     for name in ('states', 'actions', 'log_probs', 'rewards', 'values', 'episode_lens'):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert torch.equal(cum_a, cum_b)
+
+
+# ---- Agent.learn as a whole against the reference's own learn() (goldens: oracle/golden_learn.py) ----------------------
+
+@pytest.mark.parametrize('name', ('c1', 'c2s', 'c4c'))
+def test_agent_learn_matches_reference_golden(name, tmp_path):
+    """the CUDA Agent.learn (fp32 parity class) through two learning updates == the reference's Agent.learn
+    (x_transformers_rl.py:808-1023) on the same memories (list[list[Memory]] with value LOGITS, ragged, one terminated
+    episode), the same shuffle, reward-dropout flags and evolve noise: parameters after clip + AdoptAtan2, the EMA copy
+    (copy, lerp and copy-back all inside the 8 steps), RSNorm statistics, genes, and the logged losses."""
+    import json
+    from importlib import import_module
+    from helpers import learn_golden, learn_golden_noises, split
+    agent_mod = import_module('x-transformers-rl_b200.agent')
+    z, meta, cfg, sd0, data = learn_golden(name)
+    kw = dict(meta['learner'])
+    Learner = _learner_cls()
+    learner = Learner(batch_size=meta['batch_size'], num_episodes_per_update=2, epochs=meta['epochs'], **kw, **meta['extra'],
+                      accelerate_kwargs=dict(mixed_precision='no'),
+                      agent_kwargs=dict(save_path=str(tmp_path / 'ppo.pt'), dropout=0., ema_kwargs=dict(meta['ema_kwargs'])))
+    agent, dev = learner.agent, learner.device
+    evo = bool(kw.get('evolutionary'))
+    i = split(z, 'in')
+    agent.model.load_state_dict({k: v.to(dev) for k, v in split(z, 'sd0').items()}, strict=True)
+    agent.ema_params.copy_(agent.model.flat_params)
+    agent.rsnorm.running_mean.copy_(i['rs_mean']); agent.rsnorm.running_variance.copy_(i['rs_var'])
+    agent.rsnorm.step.fill_(int(i['rs_step'])); agent.rsnorm.time = int(i['rs_step'])
+    agent.step.fill_(meta['agent_step0']); agent._step_host = meta['agent_step0']
+    if evo:
+        agent.gene_pool.genes.data.copy_(i['genes'])
+    lens = data['lens']
+    memories = [[agent_mod.Memory(data['states'][e, t], data['actions'][e, t], data['log_probs'][e, t], data['rewards'][e, t],
+                                  data['is_boundary'][e, t], data['value_logits'][e, t]) for t in range(int(lens[e]))]
+                for e in range(len(lens))]
+    fit = i['fitnesses'].to(dev) if evo else None
+    sd_names = [n for n, _ in agent.model.named_parameters()]
+    worst = {}
+    for u in range(meta['updates']):
+        g = split(z, f'u{u}')
+        if evo:
+            noises = iter(learn_golden_noises(z, u))
+            agent.gene_pool.draw_noise = lambda device, _n=noises: tuple(t.to(device) for t in next(_n))
+        agent.learn(memories, lens, data['gene_ids'], fit, permutations=[p for p in g['perms']], reward_flags=g['flags'].tolist())
+        got_sd = {k: v.detach().cpu() for k, v in agent.model.state_dict().items()}
+        got_ema = {k: v.cpu() for k, v in agent.ema_state_dict().items()}
+        for k, v in split(z, f'u{u}/sd').items():
+            if k in sd_names:
+                worst[k] = max(worst.get(k, 0.), rel_err(got_sd[k], v))
+        for k, v in split(z, f'u{u}/ema').items():
+            if k in sd_names:
+                worst['ema/' + k] = max(worst.get('ema/' + k, 0.), rel_err(got_ema[k], v))
+        assert rel_err(agent.rsnorm.running_mean.cpu(), g['rs_mean']) < 1e-5
+        assert rel_err(agent.rsnorm.running_variance.cpu(), g['rs_var']) < 1e-5
+        assert agent.rsnorm.time == int(g['rs_step']) and agent._step_host == int(g['agent_step'])
+        if evo:
+            assert rel_err(agent.gene_pool.genes.data.cpu(), g['genes']) < 1e-5
+        logs = agent.last_logs.cpu()                     # scalars: total, actor, critic, autoreg, done, ...
+        for j, k in enumerate(('actor_loss', 'critic_loss', 'autoreg_loss', 'pred_done_loss')):
+            assert rel_err(logs[1 + j], g[f'logs/{k}']) < 1e-4, (u, k, float(logs[1 + j]), float(g[f'logs/{k}']))
+    bad = {k: v for k, v in worst.items() if v > 2e-4}
+    print('AGENT_LEARN_WORST', name, json.dumps(dict(sorted(worst.items(), key=lambda kv: -kv[1])[:5])))
+    assert not bad, bad
+
+
+def test_plain_env_padding_of_scalar_values_uses_the_support_midpoint(tmp_path):
+    """ragged episodes through the reference-format path with SCALAR values (what rollout_episode stores) and an asymmetric
+    reward range: the padding must decode like the reference's zero logits do -- (lo + hi) / 2 -- because the padded value
+    feeds v_{t+1} of a shorter episode that did not terminate (:837, :843)."""
+    from importlib import import_module
+    agent_mod = import_module('x-transformers-rl_b200.agent')
+    Learner = _learner_cls()
+    learner = Learner(state_dim=4, num_actions=2, reward_range=(0., 500.), max_timesteps=6, batch_size=2, num_episodes_per_update=2,
+                      world_model=dict(attn_dim_head=16, heads=4, depth=1), accelerate_kwargs=dict(mixed_precision='no'),
+                      agent_kwargs=dict(save_path=str(tmp_path / 'ppo.pt'), dropout=0.))
+    agent, dev = learner.agent, learner.device
+    g = torch.Generator().manual_seed(0)
+    lens = [6, 3]
+    mk = lambda v: agent_mod.Memory(torch.randn(4, generator=g), torch.tensor(1), torch.tensor(-0.7), torch.randn((), generator=g),
+                                    torch.tensor(False), v)
+    scal = [[mk(torch.rand((), generator=g) * 400 + 50) for _ in range(n)] for n in lens]
+    buf = agent._buffer_from_memories(scal, torch.tensor(lens), torch.zeros(2, dtype=torch.long))
+    assert torch.equal(buf['old_values'][1, 3:].cpu(), torch.full((3,), 250.))
+    logits = [[m._replace(value=torch.zeros(100)) for m in ep] for ep in scal]          # zero logits decode to the midpoint too
+    buf2 = agent._buffer_from_memories(logits, torch.tensor(lens), torch.zeros(2, dtype=torch.long))
+    assert rel_err(buf2['old_values'].cpu(), torch.full((2, 6), 250.)) < 1e-6
+    ret = xtrl().ops.gae(buf['rewards'].contiguous(), buf['old_values'].contiguous(), buf['dones'].contiguous())
+    want = R.calc_gae(buf['rewards'].cpu(), buf['old_values'].cpu(), ~buf['dones'].cpu())
+    assert rel_err(ret.cpu(), want) < 1e-5

@@ -142,3 +142,78 @@ def test_sample_inverse_cdf_edges():
         assert R.sample_inverse_cdf(p, torch.tensor([u])).item() == a
     # u beyond the accumulated mass (rounding) falls into the last action
     assert R.sample_inverse_cdf(torch.tensor([[0.5, 0.49999]]), torch.tensor([0.999999])).item() == 1
+
+
+# ---- Agent.learn as a whole (x_transformers_rl.py:808-1023), goldens from the reference's own learn() --------------------
+
+@pytest.mark.parametrize('name', ('c1', 'c2s', 'c4c'))
+def test_agent_learn_restatement_matches_reference(name):
+    """two consecutive learning updates (2 epochs x 2 minibatches each, ragged episodes, one terminated): parameters, EMA copy,
+    RSNorm statistics, genes and the logged losses of oracle/restated.agent_learn == the reference's Agent.learn, fed the
+    shuffle / reward-dropout flags / evolve noise the reference drew."""
+    from helpers import learn_golden, learn_golden_noises
+    z, meta, cfg, sd0, data = learn_golden(name)
+    kw = meta['learner']
+    sd = {k: v.clone().requires_grad_() for k, v in sd0.items()}
+    ema_sd = {k: v.clone() for k, v in sd0.items()}
+    i = split(z, 'in')
+    rs = dict(mean=i['rs_mean'].clone(), var=i['rs_var'].clone(), step=int(i['rs_step']))
+    evo = bool(kw.get('evolutionary'))
+    genes = i['genes'].clone() if evo else None
+    pool = R.PoolConfig(**kw['latent_gene_pool']) if evo else None
+    fit = i['fitnesses'] if evo else None
+    opt_state, ema_state = {}, R.EmaState(beta=0.9, **meta['ema_kwargs'])
+    ema_state.initted = False
+    agent_step, pool_step = meta['agent_step0'], 0
+    extra = meta['extra']
+    for u in range(meta['updates']):
+        g = split(z, f'u{u}')
+        logs, _, pool_step = R.agent_learn(
+            sd, ema_sd, cfg, data, rs, opt_state, ema_state, [p for p in g['perms']], g['flags'].tolist(),
+            batch_size=meta['batch_size'], genes=genes, pool=pool, pool_step=pool_step, fitnesses=fit,
+            noises=learn_golden_noises(z, u), agent_step=agent_step, evolve_every=extra.get('evolve_every', 10),
+            evolve_after_step=extra.get('evolve_after_step', 20))
+        agent_step += 1
+        assert int(g['num_evolves']) == (4 if evo else 0)
+        want_sd, want_ema = split(z, f'u{u}/sd'), split(z, f'u{u}/ema')
+        assert len(want_sd) >= 5
+        for k, v in want_sd.items():
+            if k in sd:
+                assert rel_err(sd[k].detach(), v) < 5e-5, (u, k)
+        for k, v in want_ema.items():
+            if k in ema_sd:
+                assert rel_err(ema_sd[k], v) < 5e-5, (u, k)
+        assert rel_err(rs['mean'], g['rs_mean']) < 1e-5 and rel_err(rs['var'], g['rs_var']) < 1e-5
+        assert rs['step'] == int(g['rs_step']) and agent_step == int(g['agent_step'])
+        if evo:
+            assert rel_err(genes, g['genes']) < 1e-5
+        for k in ('actor_loss', 'critic_loss', 'autoreg_loss', 'pred_done_loss'):
+            assert rel_err(logs[k], g[f'logs/{k}']) < 5e-5, (u, k)
+    # the update moved the weights by more than the tolerance asks of them
+    moved = max(rel_err(sd[k].detach(), sd0[k]) for k in sd0)
+    assert moved > 1e-3
+
+
+def test_hl_gauss_reduction_u3_scalar_alternative_is_different():
+    """the reference calls hl_gauss(values, returns) without `reduction=` and then treats the result
+    per element (torch.min / torch.where with (b, n) conditions, `[mask]`, :461-475, :973).  Some versions of hl-gauss-pytorch
+    return the MEAN scalar by default, which would still broadcast.  The oracle and the kernels implement the per-element
+    reading; this test documents what the scalar reading would compute instead and that the two differ."""
+    cfg = R.Config(state_dim=4, num_actions=2, reward_range=(-3., 3.))
+    g = torch.Generator().manual_seed(0)
+    b, n = 3, 7
+    values, returns, old = torch.randn(b, n, cfg.num_bins, generator=g), torch.randn(b, n, generator=g), torch.randn(b, n, generator=g) * 0.3
+    per_elem = R.critic_loss(values, returns, old, cfg)                                   # (b, n): the implemented reading
+    assert per_elem.shape == (b, n)
+    # the scalar alternative: both cross entropies collapse to their batch means before the clip logic
+    ce = R.hl_cross_entropy(values, returns, cfg).mean()
+    ce_clip = R.hl_cross_entropy(values, returns.clamp(-cfg.value_clip, cfg.value_clip), cfg).mean()
+    v, lo, hi = R.hl_decode(values, cfg), old - cfg.value_clip, old + cfg.value_clip
+    zero = ((returns < v) & (v < lo)) | ((hi < v) & (v < returns))
+    scalar_alt = torch.where(zero, torch.zeros(()), torch.minimum(ce, ce_clip).expand(b, n))
+    assert scalar_alt.shape == (b, n)
+    assert scalar_alt[~zero].unique().numel() <= 1                                        # one number wherever the clip does not zero it
+    assert per_elem[~zero].unique().numel() > 1 and not torch.allclose(per_elem, scalar_alt)
+    # both readings agree on WHICH elements the clip zeroes, and on the mean of the unclipped cross entropy
+    assert torch.equal(per_elem == 0, scalar_alt == 0) or zero.sum() == 0
+    assert rel_err(R.hl_cross_entropy(values, returns, cfg).mean(), ce) < 1e-6

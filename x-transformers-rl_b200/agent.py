@@ -252,10 +252,11 @@ class Agent(nn.Module):
                     dones=bd.bool(), old_values=values.float(), lens=episode_lens.to(dev).int(),
                     gene_ids=gene_ids.to(dev).int(), time_major=False)
 
-    def learn(self, memories, episode_lens=None, gene_ids=None, fitnesses=None, permutations=None):
+    def learn(self, memories, episode_lens=None, gene_ids=None, fitnesses=None, permutations=None, reward_flags=None):
         """reference signature (:808-814).  `memories` is either the reference's list[list[Memory]] or a
-        RolloutBuffer (vectorised rollouts).  permutations: optional list (one per epoch) of episode
-        orders, for tests that must replay the reference's DataLoader shuffle."""
+        RolloutBuffer (vectorised rollouts).  permutations / reward_flags: optional replay of the reference's random
+        draws for parity tests -- one episode order per epoch (DataLoader shuffle :878) and one reward-conditioning
+        Bernoulli per minibatch (:501)."""
         cfg, dev, model = self.cfg, self.device, self.model
         if isinstance(memories, RolloutBuffer):
             buf = memories
@@ -277,11 +278,14 @@ class Agent(nn.Module):
         model.train()
         self.last_grads = None
         fields = ('states', 'actions', 'rewards', 'old_log_probs', 'returns', 'old_values', 'dones', 'lens', 'gene_ids')
+        reward_flags = iter(reward_flags) if reward_flags is not None else None
         for epoch in range(self.epochs):
             perm = permutations[epoch].to(dev) if permutations is not None else torch.randperm(E, device=dev)
             for lo in range(0, E, self.batch_size):
                 idx = perm[lo:lo + self.batch_size]
                 flag = float(torch.rand(()) >= 0.5) if model.training else 1.                        # reward dropout :501
+                if reward_flags is not None:
+                    flag = float(next(reward_flags))
                 lg = self._learn_graph(idx.numel(), T) if self.use_cuda_graph_learn else None
                 if self.event_log is not None:
                     evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
