@@ -168,12 +168,12 @@ def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary, continuou
     loss.backward()
     # reward dropout: the product drew its own Bernoulli flag; replay the oracle with the flag it used
     got_total = agent.last_logs[0].item()
-    if abs(got_total - loss.item()) > 1e-4 * abs(loss.item()):
+    if abs(got_total - loss.item()) > 1e-5 * abs(loss.item()):
         for p in sd.values():
             p.grad = None
         loss, logs, packed_masked = R.learn_minibatch(sd, cfg, batch, mean, var, reward_flag=0., genes=genes)
         loss.backward()
-    assert rel_err(torch.tensor(got_total), loss.detach()) < 1e-4
+    assert rel_err(torch.tensor(got_total), loss.detach()) < 1e-5
     names = [n for n, _ in agent.model.named_parameters()]
     offs = agent.model._offsets
     worst, worst_name = 0., ''
@@ -185,7 +185,7 @@ def test_learn_gradients_match_oracle_autograd(tmp_path, evolutionary, continuou
             continue
         if rel_err(got, want) > worst:
             worst, worst_name = rel_err(got, want), n
-        assert rel_err(got, want) < 2e-3, n          # whole-model fp32 fwd+bwd on two different back ends
+        assert rel_err(got, want) < 1e-5, n          # north star: 1e-5 relative in fp32 (measured worst tensor: 2e-6)
     print('GRAD_WORST', evolutionary, continuous, worst_name, worst)
     # RSNorm copy was updated from the batch mean of the already-normalised rows
     m2, v2, _ = R.rsnorm_update(packed_masked.detach(), mean, var, 1)
@@ -302,8 +302,8 @@ def test_agent_learn_matches_reference_golden(name, tmp_path):
             assert rel_err(agent.gene_pool.genes.data.cpu(), g['genes']) < 1e-5
         logs = agent.last_logs.cpu()                     # scalars: total, actor, critic, autoreg, done, ...
         for j, k in enumerate(('actor_loss', 'critic_loss', 'autoreg_loss', 'pred_done_loss')):
-            assert rel_err(logs[1 + j], g[f'logs/{k}']) < 1e-4, (u, k, float(logs[1 + j]), float(g[f'logs/{k}']))
-    bad = {k: v for k, v in worst.items() if v > 2e-4}
+            assert rel_err(logs[1 + j], g[f'logs/{k}']) < 2e-5, (u, k, float(logs[1 + j]), float(g[f'logs/{k}']))
+    bad = {k: v for k, v in worst.items() if v > 1e-5}        # measured worst tensor over both updates: 7e-7
     print('AGENT_LEARN_WORST', name, json.dumps(dict(sorted(worst.items(), key=lambda kv: -kv[1])[:5])))
     assert not bad, bad
 
