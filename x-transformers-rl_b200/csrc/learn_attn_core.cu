@@ -21,6 +21,7 @@
 // The dropout mask is a counter hash of (call key, step counter, episode*head, query, key), regenerated in the
 // backward; p is quantised to 1/128.
 #include "learn_common.cuh"
+#include <stdlib.h>
 
 namespace xtrl {
 namespace core {
@@ -567,6 +568,263 @@ __global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+// ------------------------------------------------------------------------------------ backward, version 2
+// Key-row orientation: the tensor core produces S^T = K Q^T and dP~^T = V dO^T, so TMEM lane = KEY and a thread walks along
+// queries.  P~^T and dS'^T are then exactly the A operands of dV += P~^T dO and dK += dS'^T Q with M = keys, and are handed to
+// the tensor core THROUGH TENSOR MEMORY (tcgen05.st + the A-from-TMEM form of tcgen05.mma): no shared-memory image and no
+// 4 KB operand read per product (measured, scripts/umma_issue_probe.cu: N = 16 products cost <= 14 cycles of tensor time from
+// TMEM against 39 from shared memory).  Only dS' still crosses shared memory (read MN-major with M = queries for dQ += dS' K).
+// One issuing warp sustains one tcgen05.mma per ~55 cycles whatever its size (same probe), and a [128 keys x 128 queries]
+// tile needs 28 of them, so TWO warps issue: warp A the S^T / dP~^T tiles and the dQ products, warp B the dV / dK products.
+// A tile is processed as two halves of 64 queries (TMEM budget: 2 x (S^T 64 + dP~^T 64 + P~^T 32 + dS'^T 32) + dV, dK 2 x 16
+// each + dQ 4 x 16 = 512 columns); 16 compute warps = 4 lane quarters (keys) x 4 groups of 16 queries per half.
+// Per-query statistics (logsumexp, delta) are warp-uniform here and come from shared memory as broadcast loads; the softmax /
+// dS' arithmetic runs on packed fp32 pairs (FFMA2 / FMUL2).  The dropout mask is the forward's: one hash per (query, 4 keys);
+// the four lanes that own those keys compute a quarter of the hashes each and exchange them by shuffle.
+constexpr int NTH2 = NCOMP + 64;              // 16 compute warps + two MMA-issuing warps
+constexpr int kTileImg2 = 128 * 128 * 2;      // dS' image of one [128 keys x 128 queries] tile (rows = keys)
+constexpr int kBwd2Smem = 2 * kTileImg2 + 4 * kImg + 2 * R * 4 + 128;
+
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t keep_word(uint32_t h, uint32_t add4) {       // keep4()'s mixing of an already-seeded word
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 15;
+    return (h & 0x7f7f7f7fu) + add4;
+}
+
+// one chunk of the backward in key-row orientation: my key, the 16 queries q0 .. q0 + 15 of this half.
+//   ts / tdp: TMEM addresses of my 16 S^T / dP~^T columns; stat: (off, ndelta) pairs of the 16 queries (shared memory, broadcast)
+//   returns the packed P~^T (wp) and dS'^T (wd) rows: 8 words each.
+template <bool DIAG>
+__device__ __forceinline__ void bwd2_chunk(uint32_t ts, uint32_t tdp, const float2 *stat, int key_local, int q_local0, float sl2,
+                                           uint32_t hbase, uint32_t q_abs0, uint32_t add4, int lane, uint32_t (&wp)[8], uint32_t (&wd)[8]) {
+    uint32_t rs[16], rd[16];
+    tmem_ld16_issue(ts, rs);
+    tmem_ld16_issue(tdp, rd);
+    // the quad's hashes: lane (l & 3) seeds queries e = (l & 3) + 4 k
+    uint32_t town[4];
+    if (add4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            town[k] = keep_word((q_abs0 + (uint32_t)(4 * k + (lane & 3))) * ((uint32_t)(R / 4) * kGolden) + hbase, add4);
+    }
+    const uint32_t sel = 0x8888u + 0x1111u * (uint32_t)(lane & 3);           // replicate the sign of MY key's byte
+    const uint64_t sl22 = pk2(sl2, sl2);
+    tmem_ld_wait();
+    tmem_pin16(rs);
+    tmem_pin16(rd);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 st01 = *reinterpret_cast<const float4 *>(stat + 4 * k), st23 = *reinterpret_cast<const float4 *>(stat + 4 * k + 2);
+        const float offv[4] = {st01.x, st01.z, st23.x, st23.z}, ndv[4] = {st01.y, st01.w, st23.y, st23.w};
+        float ps[4], pd[4], ds[4];
+        uint32_t msk[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            msk[d] = add4 ? prmt(__shfl_sync(0xffffffffu, town[k], (lane & ~3) + d), sel) : 0xffffffffu;
+#pragma unroll
+        for (int d = 0; d < 4; d += 2) {
+            const int j = 4 * k + d;
+            const uint64_t x = fma2(pk2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), sl22, pk2(offv[d], offv[d + 1]));
+            float x0, x1;
+            upk2(x, x0, x1);
+            ps[d] = ex2(x0); ps[d + 1] = ex2(x1);                                 // P * drop_scale
+            if (DIAG) { ps[d] = key_local <= q_local0 + j ? ps[d] : 0.f; ps[d + 1] = key_local <= q_local0 + j + 1 ? ps[d + 1] : 0.f; }
+            pd[d] = __uint_as_float(__float_as_uint(ps[d]) & msk[d]);
+            pd[d + 1] = __uint_as_float(__float_as_uint(ps[d + 1]) & msk[d + 1]);
+            const uint64_t pn = mul2(pk2(ps[d], ps[d + 1]), pk2(ndv[d], ndv[d + 1]));
+            const uint64_t dd = fma2(pk2(pd[d], pd[d + 1]), pk2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), pn);
+            upk2(dd, ds[d], ds[d + 1]);
+        }
+        wp[2 * k] = pack2(pd[0], pd[1]); wp[2 * k + 1] = pack2(pd[2], pd[3]);
+        wd[2 * k] = pack2(ds[0], ds[1]); wd[2 * k + 1] = pack2(ds[2], ds[3]);
+    }
+}
+
+__global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *sImg = smem;                                              // [2] dS' tile images (rows = keys, columns = queries)
+    unsigned char *sQ = sImg + 2 * kTileImg2, *sK = sQ + kImg, *sV = sK + kImg, *sdO = sV + kImg;
+    float2 *sStat = reinterpret_cast<float2 *>(sdO + kImg);                  // per query: (drop_log2scale - lse * log2e, -delta / drop_scale)
+    uint64_t *bS = reinterpret_cast<uint64_t *>(sStat + R), *bI = bS + 2, *bP = bI + 2, *bF = bP + 2;
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bF + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q4 = warp & 3, c4 = warp >> 2;                                 // c4 == 4: the MMA warps (warp 16: A, warp 17: B)
+    const int bh = blockIdx.x, n = a.n, nt = (n + 127) >> 7;
+    constexpr uint32_t cST = 0, cDPT = 128, cPT = 256, cDST = 320, cDV = 384, cDK = 416, cDQ = 448;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&bS[i], 1); mbar_init(&bI[i], NCOMP / 32); mbar_init(&bP[i], 1); }
+        mbar_init(bF, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tslot, 512);
+    const size_t base = (size_t)bh * n * DH;
+    {
+        unsigned char *const imgs[4] = {sQ, sK, sV, sdO};
+        const __nv_bfloat16 *const srcs[4] = {a.q + base, a.k + base, a.v + base, a.d_o + base};
+        for (int i = tid; i < nt * 128 * 2; i += NTH2) {
+            const int r = i >> 1, c = i & 1;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const uint4 v = r < n ? __ldg(reinterpret_cast<const uint4 *>(srcs[m] + (size_t)r * DH) + c) : make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(imgs[m] + c * kChunk + (r >> 3) * 128 + (r & 7) * 16) = v;
+            }
+        }
+    }
+    for (int r = tid; r < nt * 128; r += NTH2) {                             // delta = rowsum(dO . O); logsumexp in log2 units
+        float d = 0.f, L = 1e30f;
+        if (r < n) {
+            const uint4 *po = reinterpret_cast<const uint4 *>(a.o + base + (size_t)r * DH), *pd = reinterpret_cast<const uint4 *>(a.d_o + base + (size_t)r * DH);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float x[8], y[8];
+                learn::unpack8(__ldg(po + c), x);
+                learn::unpack8(__ldg(pd + c), y);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d = fmaf(x[j], y[j], d);
+            }
+            L = a.lse[(size_t)bh * n + r] * kLog2e;
+        }
+        sStat[r] = make_float2(a.drop_log2scale - L, -d / a.drop_scale);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q4 * 32) << 16);
+    const int total = nt * (nt + 1);                                         // half-steps: tiles (kt, qt >= kt) x 2 halves of 64 queries
+    auto next_tile = [&](int &kt, int &qt) { if (++qt >= nt) { ++kt; qt = kt; } };
+
+    if (warp == NCOMP / 32) {
+        // ---- MMA warp A: S^T / dP~^T of every half (two halves ahead of the threads), dQ += dS' K per finished tile ----
+        if (lane == 0) {
+            const ImgDesc dQ_(sQ), dK_(sK), dV_(sV), dO_(sdO);
+            const StepDesc im0(sImg);
+            auto issue_s = [&](int kt, int qt, int h) {
+                mma_bf16_ss(tbase + cST + h * 64, dK_.rows + kt * 128, dQ_.rows + qt * 128 + h * 64, idesc_bf16(128, 64), 0);
+                mma_bf16_ss(tbase + cDPT + h * 64, dV_.rows + kt * 128, dO_.rows + qt * 128 + h * 64, idesc_bf16(128, 64), 0);
+                mma_commit(&bS[h]);
+            };
+            int kt = 0, qt = 0, ikt = 0, iqt = 0;                            // tile of half i; tile of the half being issued (i + 2)
+            tc_fence_after();
+            issue_s(0, 0, 0);
+            issue_s(0, 0, 1);
+            next_tile(ikt, iqt);
+            for (int i = 0; i < total; ++i) {
+                const int h = i & 1;
+                mbar_wait(&bI[h], (i >> 1) & 1);
+                tc_fence_after();
+                if (h == 1) {                                                // both halves of the tile are in the image
+                    const uint64_t am = im0.mnmaj + ((i >> 1) & 1) * (kTileImg2 / 16), kc = dK_.cols + kt * 128;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)                               // K = 128 keys
+                        mma_bf16_ss(tbase + cDQ + qt * DH, am + s * 16, kc + s * 16, idesc_bf16(128, DH) | kIdA | kIdB, kt > 0 || s > 0);
+                }
+                if (i + 2 < total) issue_s(ikt, iqt, h);
+                if (h == 1) { next_tile(kt, qt); next_tile(ikt, iqt); }
+            }
+            mma_commit(bF);
+        }
+    } else if (warp == NCOMP / 32 + 1) {
+        // ---- MMA warp B: dV += P~^T dO and dK += dS'^T Q of every half, A operands from tensor memory ----
+        if (lane == 0) {
+            const ImgDesc dQ_(sQ), dO_(sdO);
+            int kt = 0, qt = 0;
+            tc_fence_after();
+            for (int i = 0; i < total; ++i) {
+                const int h = i & 1;
+                mbar_wait(&bI[h], (i >> 1) & 1);
+                tc_fence_after();
+                const bool first = qt == kt && h == 0;
+                const uint64_t doc = dO_.cols + qt * 128 + h * 64, qc = dQ_.cols + qt * 128 + h * 64;
+                const uint32_t tdv = tbase + cDV + (kt & 1) * DH, tdk = tbase + cDK + (kt & 1) * DH;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {                                 // K = 64 queries
+                    mma_bf16_ts(tdv, tbase + cPT + h * 32 + s * 8, doc + s * 16, idesc_bf16(128, DH) | kIdB, !first || s > 0);
+                    mma_bf16_ts(tdk, tbase + cDST + h * 32 + s * 8, qc + s * 16, idesc_bf16(128, DH) | kIdB, !first || s > 0);
+                }
+                mma_commit(&bP[h]);
+                if (h == 1) next_tile(kt, qt);
+            }
+        }
+    } else {
+        // ---- compute warps: lane = key row (q4 * 32 + lane of the key tile), c4 = group of 16 queries of the half ----
+        const uint32_t ckey = cta_key(a.rng_step, a.rng_key, (uint32_t)bh);
+        const float sl2 = a.scale * kLog2e;
+        const int key_local = q4 * 32 + lane;
+        auto write_dkv = [&](int kt) {                                       // dK (c4 == 0) and dV (c4 == 1) rows of key tile kt
+            if (c4 < 2) {
+                float v[16];
+                tmem_ld16(tlane + (c4 == 0 ? cDK : cDV) + (kt & 1) * DH, v);
+                const int krow = kt * 128 + key_local;
+                if (krow < n) store_row16((c4 == 0 ? a.dk : a.dv) + base + (size_t)krow * DH, v, c4 == 0 ? a.scale : 1.f);
+            }
+        };
+        int kt = 0, qt = 0;
+        for (int i = 0; i < total; ++i) {
+            const int h = i & 1;
+            mbar_wait(&bS[h], (i >> 1) & 1);
+            tc_fence_after();
+            if (h == 0 && qt == kt && kt > 0) {                              // a key tile has finished: its dK, dV leave tensor memory
+                mbar_wait(&bP[1], ((i - 1) >> 1) & 1);
+                tc_fence_after();
+                write_dkv(kt - 1);
+            }
+            const bool diag = qt == kt;
+            const int q_local0 = h * 64 + c4 * 16;                           // first query of my chunk inside the query tile
+            const uint32_t q_abs0 = (uint32_t)(qt * 128 + q_local0);
+            const uint32_t hbase = (uint32_t)(kt * 32 + q4 * 8 + (lane >> 2)) * kGolden + ckey;
+            const uint32_t ts = tlane + cST + h * 64 + c4 * 16, tdp = tlane + cDPT + h * 64 + c4 * 16;
+            uint32_t wp[8], wd[8];
+            if (!diag || q_local0 >= q4 * 32 + 31) bwd2_chunk<false>(ts, tdp, sStat + q_abs0, key_local, q_local0, sl2, hbase, q_abs0, a.drop_add4, lane, wp, wd);
+            else if (q_local0 + 15 >= q4 * 32) bwd2_chunk<true>(ts, tdp, sStat + q_abs0, key_local, q_local0, sl2, hbase, q_abs0, a.drop_add4, lane, wp, wd);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { wp[j] = 0u; wd[j] = 0u; }
+            }
+            if (i >= 2) { mbar_wait(&bP[h], ((i - 2) >> 1) & 1); tc_fence_after(); }      // the products that read these TMEM operands are done
+            tmem_st8(tlane + cPT + h * 32 + c4 * 8, wp);
+            tmem_st8(tlane + cDST + h * 32 + c4 * 8, wd);
+            // dS' also goes to the tile image (rows = keys, columns = queries) for dQ += dS' K
+            {
+                unsigned char *img = sImg + ((i >> 1) & 1) * kTileImg2 + (q_local0 >> 3) * kTCore + (key_local >> 3) * 128 + (key_local & 7) * 16;
+                *reinterpret_cast<uint4 *>(img) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                *reinterpret_cast<uint4 *>(img + kTCore) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+            }
+            tmem_st_wait();
+            images_ready(&bI[h], lane);
+            if (h == 1) next_tile(kt, qt);
+        }
+        mbar_wait(&bP[1], ((total - 1) >> 1) & 1);                            // the last products (dK, dV of the last key tile)
+        mbar_wait(bF, 0);                                                     // the last dQ products
+        tc_fence_after();
+        write_dkv(nt - 1);
+        if (c4 < nt) {                                                       // dQ of query tile c4 (lane = query row)
+            float v[16];
+            tmem_ld16(tlane + cDQ + c4 * DH, v);
+            const int qrow = c4 * 128 + key_local;
+            if (qrow < n) store_row16(a.dq + base + (size_t)qrow * DH, v, a.scale);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
 static int fill(const xtrl_attn_core_io *io, int32_t n, int32_t dim_head, Args &a) {
     XTRL_REQUIRE(dim_head == DH && n >= 1 && n <= R, XTRL_E_UNSUPPORTED, "xtrl_attn_core_*: built for dim_head=16, 1 <= n <= 512 (got %d, %d)", dim_head, n);
     XTRL_REQUIRE(io->dropout >= 0.f && io->dropout < 1.f, XTRL_E_BADARG, "xtrl_attn_core_*: dropout %f not in [0,1)", io->dropout);
@@ -611,8 +869,13 @@ extern "C" int xtrl_attn_core_bwd(const xtrl_attn_core_io *io, int32_t bh, int32
     Args a;
     if (int rc = fill(io, n, dim_head, a)) return rc;
     static bool attr = false;
-    if (!attr) { XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
-    attn_core_bwd_kernel<<<bh, NTH, kBwdSmem, (cudaStream_t)stream>>>(a);
+    if (!attr) {
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
+        attr = true;
+    }
+    if (getenv("XTRL_CORE_BWD_V1")) attn_core_bwd_kernel<<<bh, NTH, kBwdSmem, (cudaStream_t)stream>>>(a);
+    else attn_core_bwd2_kernel<<<bh, NTH2, kBwd2Smem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("attn_core_bwd_kernel");
     return XTRL_OK;
 }
