@@ -158,6 +158,29 @@ __device__ __forceinline__ StepGeom geom(int qt, int kt, int c4) {
     return g;
 }
 
+// packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 issue two fp32 operations per instruction)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // one 16-key chunk of the forward: P = 2^(s*sl2 + off) (dropout folded in), returns the chunk's row sum
 template <bool DIAG>
 __device__ __forceinline__ float fwd_chunk(uint32_t taddr, unsigned char *sP, int row, int col0, int keyb, float sl2, float off,
@@ -166,14 +189,20 @@ __device__ __forceinline__ float fwd_chunk(uint32_t taddr, unsigned char *sP, in
     tmem_ld16_issue(taddr, r);
     tmem_ld_wait();
     tmem_pin16(r);
-    float l = 0.f;
+    const uint64_t sl22 = pk2(sl2, sl2), off2 = pk2(off, off);
+    uint64_t l2 = pk2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-        float p0 = ex2(fmaf(__uint_as_float(r[j]), sl2, off)), p1 = ex2(fmaf(__uint_as_float(r[j + 1]), sl2, off));
+        float x0, x1;
+        upk2(fma2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sl22, off2), x0, x1);
+        float p0 = ex2(x0), p1 = ex2(x1);
         if (DIAG) { p0 = keyb + j <= row ? p0 : 0.f; p1 = keyb + j + 1 <= row ? p1 : 0.f; }
-        l += p0 + p1;
+        l2 = add2(l2, pk2(p0, p1));
         w[j >> 1] = pack2(p0, p1);
     }
+    float l, lh;
+    upk2(l2, l, lh);
+    l += lh;
     if (add4) {
         const uint32_t hseed = (qrow * (uint32_t)(R / 4) + g4) * kGolden + ckey;
 #pragma unroll
@@ -256,7 +285,7 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
             if (bounded) {
                 for (int i = 0; i < 3 && i < total; ++i) { issue_s(iq, ik, i, &bS[i]); advance(iq, ik); }
                 for (int i = 0; i < total; ++i) {
-                    mbar_wait(&bI[i & 1], (i >> 1) & 1);
+                    mbar_wait_sleep(&bI[i & 1], (i >> 1) & 1, 1000);
                     tc_fence_after();
                     issue_pv(qt, kt, i & 1, &bP[i & 1]);
                     if (i + 3 < total) { issue_s(iq, ik, i % 3, &bS[i % 3]); advance(iq, ik); }
@@ -353,7 +382,7 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
         float off = a.drop_log2scale - m * kLog2e;
         for (int i = 0; i < total; ++i) {
             const int sb = i % 3, pb = i & 1;
-            mbar_wait(&bS[sb], (i / 3) & 1);
+            mbar_wait_sleep(&bS[sb], (i / 3) & 1, 400);
             if (i >= 2) mbar_wait(&bP[pb], ((i - 2) >> 1) & 1);               // the P.V that read this image is done
             tc_fence_after();
             const StepGeom g = geom(qt, kt, c4);
@@ -585,39 +614,24 @@ constexpr int NTH2 = NCOMP + 64;              // 16 compute warps + two MMA-issu
 constexpr int kTileImg2 = 128 * 128 * 2;      // dS' image of one [128 keys x 128 queries] tile (rows = keys)
 constexpr int kBwd2Smem = 2 * kTileImg2 + 4 * kImg + 2 * R * 4 + 128;
 
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 __device__ __forceinline__ uint32_t keep_word(uint32_t h, uint32_t add4) {       // keep4()'s mixing of an already-seeded word
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 15;
     return (h & 0x7f7f7f7fu) + add4;
 }
 
 // one chunk of the backward in key-row orientation: my key, the 16 queries q0 .. q0 + 15 of this half.
-//   ts / tdp: TMEM addresses of my 16 S^T / dP~^T columns; stat: (off, ndelta) pairs of the 16 queries (shared memory, broadcast)
+//   ts / tdp: TMEM addresses of my 16 S^T / dP~^T columns; stat: the 16 queries' statistics in blocks of two queries
+//   [off_q, off_q+1, ndelta_q, ndelta_q+1] (shared memory, broadcast loads that land as ready-made fp32 pairs)
 //   returns the packed P~^T (wp) and dS'^T (wd) rows: 8 words each.
-template <bool DIAG>
-__device__ __forceinline__ void bwd2_chunk(uint32_t ts, uint32_t tdp, const float2 *stat, int key_local, int q_local0, float sl2,
+template <bool DIAG, bool DROP>
+__device__ __forceinline__ void bwd2_chunk(uint32_t ts, uint32_t tdp, const float4 *stat, int key_local, int q_local0, float sl2,
                                            uint32_t hbase, uint32_t q_abs0, uint32_t add4, int lane, uint32_t (&wp)[8], uint32_t (&wd)[8]) {
     uint32_t rs[16], rd[16];
     tmem_ld16_issue(ts, rs);
     tmem_ld16_issue(tdp, rd);
     // the quad's hashes: lane (l & 3) seeds queries e = (l & 3) + 4 k
     uint32_t town[4];
-    if (add4) {
+    if (DROP) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             town[k] = keep_word((q_abs0 + (uint32_t)(4 * k + (lane & 3))) * ((uint32_t)(R / 4) * kGolden) + hbase, add4);
@@ -629,13 +643,14 @@ __device__ __forceinline__ void bwd2_chunk(uint32_t ts, uint32_t tdp, const floa
     tmem_pin16(rd);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float4 st01 = *reinterpret_cast<const float4 *>(stat + 4 * k), st23 = *reinterpret_cast<const float4 *>(stat + 4 * k + 2);
-        const float offv[4] = {st01.x, st01.z, st23.x, st23.z}, ndv[4] = {st01.y, st01.w, st23.y, st23.w};
+        const float4 st01 = stat[2 * k], st23 = stat[2 * k + 1];
+        const float offv[4] = {st01.x, st01.y, st23.x, st23.y}, ndv[4] = {st01.z, st01.w, st23.z, st23.w};
         float ps[4], pd[4], ds[4];
         uint32_t msk[4];
+        if (DROP) {
 #pragma unroll
-        for (int d = 0; d < 4; ++d)
-            msk[d] = add4 ? prmt(__shfl_sync(0xffffffffu, town[k], (lane & ~3) + d), sel) : 0xffffffffu;
+            for (int d = 0; d < 4; ++d) msk[d] = prmt(__shfl_sync(0xffffffffu, town[k], (lane & ~3) + d), sel);
+        }
 #pragma unroll
         for (int d = 0; d < 4; d += 2) {
             const int j = 4 * k + d;
@@ -644,8 +659,8 @@ __device__ __forceinline__ void bwd2_chunk(uint32_t ts, uint32_t tdp, const floa
             upk2(x, x0, x1);
             ps[d] = ex2(x0); ps[d + 1] = ex2(x1);                                 // P * drop_scale
             if (DIAG) { ps[d] = key_local <= q_local0 + j ? ps[d] : 0.f; ps[d + 1] = key_local <= q_local0 + j + 1 ? ps[d + 1] : 0.f; }
-            pd[d] = __uint_as_float(__float_as_uint(ps[d]) & msk[d]);
-            pd[d + 1] = __uint_as_float(__float_as_uint(ps[d + 1]) & msk[d + 1]);
+            pd[d] = DROP ? __uint_as_float(__float_as_uint(ps[d]) & msk[d]) : ps[d];
+            pd[d + 1] = DROP ? __uint_as_float(__float_as_uint(ps[d + 1]) & msk[d + 1]) : ps[d + 1];
             const uint64_t pn = mul2(pk2(ps[d], ps[d + 1]), pk2(ndv[d], ndv[d + 1]));
             const uint64_t dd = fma2(pk2(pd[d], pd[d + 1]), pk2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), pn);
             upk2(dd, ds[d], ds[d + 1]);
@@ -655,19 +670,23 @@ __device__ __forceinline__ void bwd2_chunk(uint32_t ts, uint32_t tdp, const floa
     }
 }
 
-__global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
+// CQ = chunks of 16 queries a compute warp handles per half (1: 16 compute warps, 2: 8 compute warps with twice the work each,
+// i.e. the per-half barrier / fence / geometry cost amortised over 32 scores per thread)
+template <bool DROP, int CQ>
+__global__ void __launch_bounds__((16 / CQ + 2) * 32, 1) attn_core_bwd2_kernel(const Args a) {
+    constexpr int NW = 16 / CQ, NTHK = (NW + 2) * 32;                        // compute warps; threads
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sImg = smem;                                              // [2] dS' tile images (rows = keys, columns = queries)
     unsigned char *sQ = sImg + 2 * kTileImg2, *sK = sQ + kImg, *sV = sK + kImg, *sdO = sV + kImg;
-    float2 *sStat = reinterpret_cast<float2 *>(sdO + kImg);                  // per query: (drop_log2scale - lse * log2e, -delta / drop_scale)
-    uint64_t *bS = reinterpret_cast<uint64_t *>(sStat + R), *bI = bS + 2, *bP = bI + 2, *bF = bP + 2;
+    float *sStat = reinterpret_cast<float *>(sdO + kImg);                    // per pair of queries: [off, off, ndelta, ndelta], off = drop_log2scale
+    uint64_t *bS = reinterpret_cast<uint64_t *>(sStat + 2 * R), *bI = bS + 2, *bP = bI + 2, *bF = bP + 2;      // - lse * log2e, ndelta = -delta / drop_scale
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bF + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q4 = warp & 3, c4 = warp >> 2;                                 // c4 == 4: the MMA warps (warp 16: A, warp 17: B)
+    const int q4 = warp & 3, c4 = warp >> 2;                                 // c4 == NW / 4: the MMA warps (A, then B)
     const int bh = blockIdx.x, n = a.n, nt = (n + 127) >> 7;
     constexpr uint32_t cST = 0, cDPT = 128, cPT = 256, cDST = 320, cDV = 384, cDK = 416, cDQ = 448;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&bS[i], 1); mbar_init(&bI[i], NCOMP / 32); mbar_init(&bP[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bS[i], 1); mbar_init(&bI[i], NW); mbar_init(&bP[i], 1); }
         mbar_init(bF, 1);
         fence_mbar_init();
     }
@@ -676,7 +695,7 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
     {
         unsigned char *const imgs[4] = {sQ, sK, sV, sdO};
         const __nv_bfloat16 *const srcs[4] = {a.q + base, a.k + base, a.v + base, a.d_o + base};
-        for (int i = tid; i < nt * 128 * 2; i += NTH2) {
+        for (int i = tid; i < nt * 128 * 2; i += NTHK) {
             const int r = i >> 1, c = i & 1;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
@@ -685,7 +704,7 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
             }
         }
     }
-    for (int r = tid; r < nt * 128; r += NTH2) {                             // delta = rowsum(dO . O); logsumexp in log2 units
+    for (int r = tid; r < nt * 128; r += NTHK) {                             // delta = rowsum(dO . O); logsumexp in log2 units
         float d = 0.f, L = 1e30f;
         if (r < n) {
             const uint4 *po = reinterpret_cast<const uint4 *>(a.o + base + (size_t)r * DH), *pd = reinterpret_cast<const uint4 *>(a.d_o + base + (size_t)r * DH);
@@ -699,7 +718,8 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
             }
             L = a.lse[(size_t)bh * n + r] * kLog2e;
         }
-        sStat[r] = make_float2(a.drop_log2scale - L, -d / a.drop_scale);
+        sStat[(r >> 1) * 4 + (r & 1)] = a.drop_log2scale - L;
+        sStat[(r >> 1) * 4 + 2 + (r & 1)] = -d / a.drop_scale;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -709,7 +729,7 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
     const int total = nt * (nt + 1);                                         // half-steps: tiles (kt, qt >= kt) x 2 halves of 64 queries
     auto next_tile = [&](int &kt, int &qt) { if (++qt >= nt) { ++kt; qt = kt; } };
 
-    if (warp == NCOMP / 32) {
+    if (warp == NW) {
         // ---- MMA warp A: S^T / dP~^T of every half (two halves ahead of the threads), dQ += dS' K per finished tile ----
         if (lane == 0) {
             const ImgDesc dQ_(sQ), dK_(sK), dV_(sV), dO_(sdO);
@@ -726,7 +746,7 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
             next_tile(ikt, iqt);
             for (int i = 0; i < total; ++i) {
                 const int h = i & 1;
-                mbar_wait(&bI[h], (i >> 1) & 1);
+                mbar_wait_sleep(&bI[h], (i >> 1) & 1, 1000);
                 tc_fence_after();
                 if (h == 1) {                                                // both halves of the tile are in the image
                     const uint64_t am = im0.mnmaj + ((i >> 1) & 1) * (kTileImg2 / 16), kc = dK_.cols + kt * 128;
@@ -739,7 +759,7 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
             }
             mma_commit(bF);
         }
-    } else if (warp == NCOMP / 32 + 1) {
+    } else if (warp == NW + 1) {
         // ---- MMA warp B: dV += P~^T dO and dK += dS'^T Q of every half, A operands from tensor memory ----
         if (lane == 0) {
             const ImgDesc dQ_(sQ), dO_(sdO);
@@ -747,7 +767,7 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
             tc_fence_after();
             for (int i = 0; i < total; ++i) {
                 const int h = i & 1;
-                mbar_wait(&bI[h], (i >> 1) & 1);
+                mbar_wait_sleep(&bI[h], (i >> 1) & 1, 1000);
                 tc_fence_after();
                 const bool first = qt == kt && h == 0;
                 const uint64_t doc = dO_.cols + qt * 128 + h * 64, qc = dQ_.cols + qt * 128 + h * 64;
@@ -774,10 +794,11 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
                 if (krow < n) store_row16((c4 == 0 ? a.dk : a.dv) + base + (size_t)krow * DH, v, c4 == 0 ? a.scale : 1.f);
             }
         };
+        static_assert(NW / 4 >= 2, "dK / dV leave through two column groups of warps");
         int kt = 0, qt = 0;
         for (int i = 0; i < total; ++i) {
             const int h = i & 1;
-            mbar_wait(&bS[h], (i >> 1) & 1);
+            mbar_wait_sleep(&bS[h], (i >> 1) & 1, 400);
             tc_fence_after();
             if (h == 0 && qt == kt && kt > 0) {                              // a key tile has finished: its dK, dV leave tensor memory
                 mbar_wait(&bP[1], ((i - 1) >> 1) & 1);
@@ -785,25 +806,31 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
                 write_dkv(kt - 1);
             }
             const bool diag = qt == kt;
-            const int q_local0 = h * 64 + c4 * 16;                           // first query of my chunk inside the query tile
-            const uint32_t q_abs0 = (uint32_t)(qt * 128 + q_local0);
+            uint32_t wp[CQ][8], wd[CQ][8];
             const uint32_t hbase = (uint32_t)(kt * 32 + q4 * 8 + (lane >> 2)) * kGolden + ckey;
-            const uint32_t ts = tlane + cST + h * 64 + c4 * 16, tdp = tlane + cDPT + h * 64 + c4 * 16;
-            uint32_t wp[8], wd[8];
-            if (!diag || q_local0 >= q4 * 32 + 31) bwd2_chunk<false>(ts, tdp, sStat + q_abs0, key_local, q_local0, sl2, hbase, q_abs0, a.drop_add4, lane, wp, wd);
-            else if (q_local0 + 15 >= q4 * 32) bwd2_chunk<true>(ts, tdp, sStat + q_abs0, key_local, q_local0, sl2, hbase, q_abs0, a.drop_add4, lane, wp, wd);
-            else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { wp[j] = 0u; wd[j] = 0u; }
+            for (int cc = 0; cc < CQ; ++cc) {
+                const int q_local0 = h * 64 + (c4 * CQ + cc) * 16;           // first query of the chunk inside the query tile
+                const uint32_t q_abs0 = (uint32_t)(qt * 128 + q_local0);
+                const uint32_t ts = tlane + cST + h * 64 + (c4 * CQ + cc) * 16, tdp = tlane + cDPT + h * 64 + (c4 * CQ + cc) * 16;
+                const float4 *stat = reinterpret_cast<const float4 *>(sStat) + (q_abs0 >> 1);
+                if (!diag || q_local0 >= q4 * 32 + 31) bwd2_chunk<false, DROP>(ts, tdp, stat, key_local, q_local0, sl2, hbase, q_abs0, a.drop_add4, lane, wp[cc], wd[cc]);
+                else if (q_local0 + 15 >= q4 * 32) bwd2_chunk<true, DROP>(ts, tdp, stat, key_local, q_local0, sl2, hbase, q_abs0, a.drop_add4, lane, wp[cc], wd[cc]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { wp[cc][j] = 0u; wd[cc][j] = 0u; }
+                }
             }
             if (i >= 2) { mbar_wait(&bP[h], ((i - 2) >> 1) & 1); tc_fence_after(); }      // the products that read these TMEM operands are done
-            tmem_st8(tlane + cPT + h * 32 + c4 * 8, wp);
-            tmem_st8(tlane + cDST + h * 32 + c4 * 8, wd);
-            // dS' also goes to the tile image (rows = keys, columns = queries) for dQ += dS' K
-            {
+#pragma unroll
+            for (int cc = 0; cc < CQ; ++cc) {
+                const int q_local0 = h * 64 + (c4 * CQ + cc) * 16;
+                tmem_st8(tlane + cPT + h * 32 + (c4 * CQ + cc) * 8, wp[cc]);
+                tmem_st8(tlane + cDST + h * 32 + (c4 * CQ + cc) * 8, wd[cc]);
+                // dS' also goes to the tile image (rows = keys, columns = queries) for dQ += dS' K
                 unsigned char *img = sImg + ((i >> 1) & 1) * kTileImg2 + (q_local0 >> 3) * kTCore + (key_local >> 3) * 128 + (key_local & 7) * 16;
-                *reinterpret_cast<uint4 *>(img) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-                *reinterpret_cast<uint4 *>(img + kTCore) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+                *reinterpret_cast<uint4 *>(img) = make_uint4(wd[cc][0], wd[cc][1], wd[cc][2], wd[cc][3]);
+                *reinterpret_cast<uint4 *>(img + kTCore) = make_uint4(wd[cc][4], wd[cc][5], wd[cc][6], wd[cc][7]);
             }
             tmem_st_wait();
             images_ready(&bI[h], lane);
@@ -813,10 +840,10 @@ __global__ void __launch_bounds__(NTH2, 1) attn_core_bwd2_kernel(const Args a) {
         mbar_wait(bF, 0);                                                     // the last dQ products
         tc_fence_after();
         write_dkv(nt - 1);
-        if (c4 < nt) {                                                       // dQ of query tile c4 (lane = query row)
+        for (int t = c4; t < nt; t += NW / 4) {                               // dQ of query tile t (lane = query row)
             float v[16];
-            tmem_ld16(tlane + cDQ + c4 * DH, v);
-            const int qrow = c4 * 128 + key_local;
+            tmem_ld16(tlane + cDQ + t * DH, v);
+            const int qrow = t * 128 + key_local;
             if (qrow < n) store_row16(a.dq + base + (size_t)qrow * DH, v, a.scale);
         }
         tc_fence_before();
@@ -871,11 +898,18 @@ extern "C" int xtrl_attn_core_bwd(const xtrl_attn_core_io *io, int32_t bh, int32
     static bool attr = false;
     if (!attr) {
         XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
         attr = true;
     }
     if (getenv("XTRL_CORE_BWD_V1")) attn_core_bwd_kernel<<<bh, NTH, kBwdSmem, (cudaStream_t)stream>>>(a);
-    else attn_core_bwd2_kernel<<<bh, NTH2, kBwd2Smem, (cudaStream_t)stream>>>(a);
+    else if (getenv("XTRL_CORE_BWD_CQ2")) {
+        if (a.drop_add4) attn_core_bwd2_kernel<true, 2><<<bh, 320, kBwd2Smem, (cudaStream_t)stream>>>(a);
+        else attn_core_bwd2_kernel<false, 2><<<bh, 320, kBwd2Smem, (cudaStream_t)stream>>>(a);
+    } else if (a.drop_add4) attn_core_bwd2_kernel<true, 1><<<bh, NTH2, kBwd2Smem, (cudaStream_t)stream>>>(a);
+    else attn_core_bwd2_kernel<false, 1><<<bh, NTH2, kBwd2Smem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("attn_core_bwd_kernel");
     return XTRL_OK;
 }
