@@ -8,9 +8,7 @@
 //   compute_done_loss :406-411, and the assembly + backward of Agent.learn :939-983.
 //
 // HBM-bound: per timestep 8A+8K+21 B (+20(S+1)+9 B for the world-model terms), each byte touched
-// once.  One warp per timestep row: the K critic logits and their gradients move as coalesced
-// 128 B rows (lane <-> bin, stride 32), bin-edge erf values are shared between neighbouring lanes
-// by shuffle, and erf is only evaluated where fp32 erf is not saturated.
+// once.  One THREAD per timestep row over shared-memory tiles of 128 rows (see ppo_loss_rows_kernel).
 // Launch sequence (all on the caller's stream): memset workspace -> stats (masked advantage
 // mean / unbiased variance, counts; fp64 accumulators) -> main -> finalize (8 scalars).
 #include "common.cuh"
@@ -87,75 +85,84 @@ struct LossArgs {
     int b, T;
 };
 
-constexpr int kLossWarps = 8;
-constexpr int kTileRows = 64;            // rows (timesteps) staged per tile; 8 per warp
+// ---- main: one THREAD per timestep row ----------------------------------------------------------------------------
+// A warp-per-row layout (round 1) spent ~600 warp instructions per row on the K-wide critic term: five butterfly reductions,
+// 4 x 32 exp slots for 100 bins, and erf evaluated by whole warps although only the ~24 bin edges within 4 sigma-widths of the
+// target have a non-saturated erf.  Here a thread owns a row: max / sum-exp / expectation are register recurrences over the K
+// logits (read as 16-byte pieces from a shared-memory tile whose row stride is an odd number of 16-byte units: conflict-free),
+// the HL-Gauss histogram is evaluated only over its 26-bin window with a rolling erf (every other bin is exactly 0 in fp32,
+// as in the oracle, because erff saturates to +-1 beyond |z| = 4), and the gradient row is written in place over the logits
+// and leaves the tile as coalesced row copies.  ~100 warp-instruction equivalents per row.  Narrow per-row fields (actor
+// logits, state prediction, targets, returns ...) are read straight from global memory by the row's thread.
+constexpr int kRowThreads = 128;         // rows per tile = threads per CTA
+constexpr int kWin = 26;                 // bins a histogram window can touch: 2 * 4 / (step / denom) + margins = 22.6 + 3
 
-// ---- asynchronous tile staging (cp.async 16 B, zero-fill past the end of the source) -----------
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-// copies bytes [start, start+want) of a buffer of `total` bytes into smem (16-byte chunks; everything
-// past `total` reads as zero).  start is a multiple of 16 by construction (tile starts are 64 rows).
-__device__ __forceinline__ void stage_region(unsigned char *dst, const void *base, int64_t start, int want, int64_t total) {
-    if (base == nullptr) return;
-    const unsigned char *src = (const unsigned char *)base;
-    for (int c = threadIdx.x; c * 16 < want; c += kLossWarps * 32) {
-        const int64_t off = start + (int64_t)c * 16;
-        const int64_t left = total - off;
-        const int valid = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
-        cp_async16(dst + c * 16, valid > 0 ? src + off : src, valid);
+template <typename TIO> struct RowIO;
+template <> struct RowIO<float> {
+    static constexpr int VE = 4;
+    static __device__ __forceinline__ void load(const unsigned char *row, int piece, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4 *>(row + piece * 16);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
-}
-
-struct TileLayout {                      // byte offsets inside one stage of shared memory
-    int vl, ra, sp, dl, act, olp, ret, ov, tgt, dn, total;
+    static __device__ __forceinline__ void store(unsigned char *row, int piece, const float (&v)[4]) {
+        *reinterpret_cast<float4 *>(row + piece * 16) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    static __device__ __forceinline__ float ld(const unsigned char *row, int k) { return reinterpret_cast<const float *>(row)[k]; }
+    static __device__ __forceinline__ void st(unsigned char *row, int k, float v) { reinterpret_cast<float *>(row)[k] = v; }
+    static __device__ __forceinline__ float ex(float x) { return expf(x); }
 };
-__host__ __device__ static inline TileLayout tile_layout(int AW, int AL, int K, int S1, int sz) {   // AW: actor head width, AL: actions per row
-    TileLayout t; int o = 0;
-    auto take = [&](int n) { int at = o; o += (n + 15) & ~15; return at; };
-    t.vl = take(kTileRows * K * sz);
-    t.ra = take(kTileRows * AW * sz);
-    t.sp = take(kTileRows * 2 * S1 * sz);
-    t.dl = take(kTileRows * sz);
-    t.act = take(kTileRows * 4 * AL);
-    t.olp = take(kTileRows * 4 * AL);
-    t.ret = take(kTileRows * 4);
-    t.ov = take(kTileRows * 4);
-    t.tgt = take((kTileRows + 1) * S1 * 4);
-    t.dn = take(kTileRows);
-    t.total = o;
-    return t;
+template <> struct RowIO<__nv_bfloat16> {
+    static constexpr int VE = 8;
+    static __device__ __forceinline__ void load(const unsigned char *row, int piece, float (&v)[8]) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(row + piece * 16);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+    static __device__ __forceinline__ void store(unsigned char *row, int piece, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t *>(&h); }
+        *reinterpret_cast<uint4 *>(row + piece * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static __device__ __forceinline__ float ld(const unsigned char *row, int k) { return __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(row)[k]); }
+    static __device__ __forceinline__ void st(unsigned char *row, int k, float v) { reinterpret_cast<__nv_bfloat16 *>(row)[k] = __float2bfloat16_rn(v); }
+    static __device__ __forceinline__ float ex(float x) { return __expf(x); }      // the 1e-2 class
+};
+
+// cooperative copy of one row of `rowbytes` bytes in units of `unit` bytes (16 / 8 / 4 / 2: the largest that divides rowbytes)
+__device__ __forceinline__ void copy_row(unsigned char *dst, const unsigned char *src, int rowbytes, int unit, int lane) {
+    if (unit == 16) { for (int o = lane * 16; o < rowbytes; o += 512) *reinterpret_cast<uint4 *>(dst + o) = *reinterpret_cast<const uint4 *>(src + o); }
+    else if (unit == 8) { for (int o = lane * 8; o < rowbytes; o += 256) *reinterpret_cast<uint2 *>(dst + o) = *reinterpret_cast<const uint2 *>(src + o); }
+    else if (unit == 4) { for (int o = lane * 4; o < rowbytes; o += 128) *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(src + o); }
+    else { for (int o = lane * 2; o < rowbytes; o += 64) *reinterpret_cast<uint16_t *>(dst + o) = *reinterpret_cast<const uint16_t *>(src + o); }
 }
 
-template <typename T> __device__ __forceinline__ float sm_as_float(const T *p);
-template <> __device__ __forceinline__ float sm_as_float<float>(const float *p) { return *p; }
-template <> __device__ __forceinline__ float sm_as_float<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
-
-// erf with the fp32-saturated region (|z| >= 4 rounds to +-1 exactly) skipped warp-uniformly
-__device__ __forceinline__ float erf_window(float z) {
-    const bool need = fabsf(z) < 4.f;
-    float c = copysignf(1.f, z);
-    if (__any_sync(0xffffffffu, need)) { const float e = erff(z); c = need ? e : c; }
-    return c;
+struct HistWindow { int k0, k1; };       // bins [k0, k1) can be non-zero
+__device__ __forceinline__ HistWindow hist_window(const HlSupport &sup, float y, int K) {
+    const float pos = (y - 4.f * sup.denom - sup.lo) / sup.step;             // edges below this index have erf == -1 exactly
+    int k0 = (int)floorf(pos) - 1;
+    k0 = k0 < 0 ? 0 : (k0 > K ? K : k0);
+    HistWindow w;
+    w.k0 = k0; w.k1 = k0 + kWin < K ? k0 + kWin : K;
+    return w;
 }
 
-template <typename TIO, int KJ>
-__global__ void __launch_bounds__(kLossWarps * 32, 2)
-ppo_loss_kernel(const LossArgs a) {
+template <typename TIO>
+__global__ void __launch_bounds__(kRowThreads)
+ppo_loss_rows_kernel(const LossArgs a, int row_stride, int unit) {
+    using IO = RowIO<TIO>;
+    constexpr int VE = IO::VE;
     extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = a.cfg.num_actions, K = a.cfg.num_bins, S1 = a.cfg.state_dim + 1, T = a.T;
     const int64_t N = (int64_t)a.b * T;
     const double *ws = a.io.workspace;
     const bool cont = a.cfg.continuous != 0;
-    const int AW = cont ? 2 * A : A, AL = cont ? A : 1;
-    const TileLayout tl = tile_layout(AW, AL, K, S1, (int)sizeof(TIO));
+    float *s_edge = reinterpret_cast<float *>(smem + (size_t)kRowThreads * row_stride);      // [K + 1] bin edges, [K] centres
+    float *s_centre = s_edge + K + 1;
+    for (int k = tid; k <= K; k += kRowThreads) { s_edge[k] = a.sup.edge(k); if (k < K) s_centre[k] = a.sup.centre(k); }
 
-    // masked advantage statistics (normalize(), :103-112)
     const double n_mask = ws[WS_N_MASK], n_wm = ws[WS_N_WM];
     float adv_mean = 0.f, adv_inv_std = 1.f;
     if (a.cfg.normalize_advantages && n_mask > 0.) {
@@ -167,127 +174,72 @@ ppo_loss_kernel(const LossArgs a) {
     const float g_ac = n_mask > 0. ? (float)(1. / n_mask) : 0.f;                      // d mean / d elem
     const float g_done = g_ac * a.cfg.autoreg_weight;
     const float g_wm = n_wm > 0. ? a.cfg.autoreg_weight * (float)(1. / (n_wm * S1)) : 0.f;
-    const float feps = 1.1920928955078125e-07f;                                      // finfo(fp32).eps
-
-    TIO *g_ra = (TIO *)a.io.g_raw_actions;
-    TIO *g_vl = (TIO *)a.io.g_value_logits;
-    TIO *g_sp = (TIO *)a.io.g_state_pred_raw;
-    TIO *g_dl = (TIO *)a.io.g_done_logit;
-    const bool has_sp = a.io.state_pred_raw != nullptr, has_dl = a.io.done_logit != nullptr;
-
-    const int64_t ntiles = (N + kTileRows - 1) / kTileRows;
-    auto stage = [&](int64_t tile, int buf) {
-        unsigned char *st = smem + (size_t)buf * tl.total;
-        const int64_t r0 = tile * kTileRows;
-        const int sz = (int)sizeof(TIO);
-        stage_region(st + tl.vl, a.io.value_logits, r0 * K * sz, kTileRows * K * sz, N * K * sz);
-        stage_region(st + tl.ra, a.io.raw_actions, r0 * AW * sz, kTileRows * AW * sz, N * AW * sz);
-        stage_region(st + tl.sp, a.io.state_pred_raw, r0 * 2 * S1 * sz, kTileRows * 2 * S1 * sz, N * 2 * S1 * sz);
-        stage_region(st + tl.dl, a.io.done_logit, r0 * sz, kTileRows * sz, N * sz);
-        stage_region(st + tl.act, cont ? (const void *)a.io.actions_f : (const void *)a.io.actions, r0 * 4 * AL, kTileRows * 4 * AL, N * 4 * AL);
-        stage_region(st + tl.olp, a.io.old_log_probs, r0 * 4 * AL, kTileRows * 4 * AL, N * 4 * AL);
-        stage_region(st + tl.ret, a.io.returns, r0 * 4, kTileRows * 4, N * 4);
-        stage_region(st + tl.ov, a.io.old_values, r0 * 4, kTileRows * 4, N * 4);
-        stage_region(st + tl.tgt, a.io.target, r0 * S1 * 4, (kTileRows + 1) * S1 * 4, N * S1 * 4);
-        stage_region(st + tl.dn, a.io.dones, r0, kTileRows, N);
-        cp_async_commit();
-    };
-
-    float acc_ac = 0.f, acc_actor = 0.f, acc_critic = 0.f, acc_nll = 0.f, acc_done = 0.f;   // per THREAD partial sums
-    __shared__ float s_crit[kTileRows];
-
-    // per-lane constants of my KJ bins: lower edge and centre (lane <-> bin k = j*32 + lane)
-    float edge_lo[KJ], centre[KJ];
-#pragma unroll
-    for (int j = 0; j < KJ; ++j) {
-        const int k = j * 32 + lane;
-        edge_lo[j] = a.sup.edge(min(k, K));
-        centre[j] = k < K ? a.sup.centre(k) : 0.f;
-    }
+    const float feps = 1.1920928955078125e-07f;
     const float inv_denom = 1.f / a.sup.denom;
+    const TIO *in_vl = (const TIO *)a.io.value_logits, *in_ra = (const TIO *)a.io.raw_actions;
+    const TIO *in_sp = (const TIO *)a.io.state_pred_raw, *in_dl = (const TIO *)a.io.done_logit;
+    TIO *g_ra = (TIO *)a.io.g_raw_actions, *g_vl = (TIO *)a.io.g_value_logits, *g_sp = (TIO *)a.io.g_state_pred_raw, *g_dl = (TIO *)a.io.g_done_logit;
+    const int rowbytes = K * (int)sizeof(TIO), npieces = (K + VE - 1) / VE, nfull = K / VE;
+    float acc_ac = 0.f, acc_actor = 0.f, acc_critic = 0.f, acc_nll = 0.f, acc_done = 0.f;
 
-    int buf = 0;
-    if ((int64_t)blockIdx.x < ntiles) stage(blockIdx.x, 0);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const int64_t next = tile + gridDim.x;
-        if (next < ntiles) { stage(next, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    const int64_t ntiles = (N + kRowThreads - 1) / kRowThreads;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * kRowThreads;
+        const int nrows = (int)(N - r0 < kRowThreads ? N - r0 : kRowThreads);
+        __syncthreads();                                                     // the previous tile has left shared memory (and the tables are written)
+        for (int row = warp; row < nrows; row += kRowThreads / 32)
+            copy_row(smem + (size_t)row * row_stride, reinterpret_cast<const unsigned char *>(in_vl) + (r0 + row) * rowbytes, rowbytes, unit, lane);
         __syncthreads();
-        const unsigned char *st = smem + (size_t)buf * tl.total;
-        const TIO *s_vl = (const TIO *)(st + tl.vl), *s_ra = (const TIO *)(st + tl.ra);
-        const TIO *s_sp = (const TIO *)(st + tl.sp), *s_dl = (const TIO *)(st + tl.dl);
-        const int32_t *s_act = (const int32_t *)(st + tl.act);
-        const float *s_olp = (const float *)(st + tl.olp), *s_ret = (const float *)(st + tl.ret);
-        const float *s_ov = (const float *)(st + tl.ov), *s_tgt = (const float *)(st + tl.tgt);
-        const uint8_t *s_dn = (const uint8_t *)(st + tl.dn);
-
-        for (int lr = warp; lr < kTileRows; lr += kLossWarps) {
-            const int64_t r = tile * kTileRows + lr;
-            if (r >= N) break;
+        if (tid < nrows) {
+            const int64_t r = r0 + tid;
             const int e = (int)(r / T), t = (int)(r - (int64_t)e * T);
             const bool masked = t < __ldg(a.io.episode_lens + e);
-            const float ret = s_ret[lr];
-            const float v_old = s_ov[lr];
+            const float ret = __ldg(a.io.returns + r), v_old = __ldg(a.io.old_values + r);
+            unsigned char *xr = smem + (size_t)tid * row_stride;
 
-            // ---------------- critic: HL-Gauss CE against returns and clamped returns ------------
-            float lg[KJ], ex[KJ];
+            // ---------------- critic: HL-Gauss CE against returns and clamped returns (:446-477) ------------
             float mx = -INFINITY;
+            for (int p = 0; p < npieces; ++p) {
+                float v[VE];
+                IO::load(xr, p, v);
 #pragma unroll
-            for (int j = 0; j < KJ; ++j) {
-                const int k = j * 32 + lane;
-                lg[j] = k < K ? sm_as_float(s_vl + lr * K + k) : -INFINITY;
-                mx = fmaxf(mx, lg[j]);
+                for (int j = 0; j < VE; ++j) if (p < nfull || p * VE + j < K) mx = fmaxf(mx, v[j]);
             }
-            mx = warp_max(mx);
             float se = 0.f, sc = 0.f;
+            for (int p = 0; p < npieces; ++p) {
+                float v[VE];
+                IO::load(xr, p, v);
 #pragma unroll
-            for (int j = 0; j < KJ; ++j) {
-                const int k = j * 32 + lane;
-                ex[j] = k < K ? expf(lg[j] - mx) : 0.f;
-                se += ex[j];
-                sc = fmaf(ex[j], centre[j], sc);
+                for (int j = 0; j < VE; ++j) {
+                    if (p < nfull || p * VE + j < K) {
+                        const float ex = IO::ex(v[j] - mx);
+                        se += ex;
+                        sc = fmaf(ex, s_centre[p * VE + j], sc);
+                    }
+                }
             }
-            se = warp_sum(se); sc = warp_sum(sc);
-            const float v_new = sc / se;                       // hl_gauss(values), :455
-            const float lse = logf(se) + mx;
-
+            const float v_new = sc / se;                                      // hl_gauss(values), :455
+            const float lse = logf(se) + mx, inv_se = 1.f / se;
             const float y0 = fminf(fmaxf(ret, a.sup.lo), a.sup.hi);                                     // clamp_to_range
             const float y1 = fminf(fmaxf(fminf(fmaxf(ret, -a.cfg.value_clip), a.cfg.value_clip), a.sup.lo), a.sup.hi);  // :459
-            const bool same = y0 == y1;                        // returns inside +-value_clip: one histogram serves both
-            // normalisers: lanes 0..3 evaluate erf at (hi,y0) (lo,y0) (hi,y1) (lo,y1), then broadcast
-            const float zarg = ((lane & 1) ? a.sup.lo : a.sup.hi) - ((lane & 2) ? y1 : y0);
-            const float zerf = erff(zarg * inv_denom);
-            const float iz0 = 1.f / fmaxf(__shfl_sync(0xffffffffu, zerf, 0) - __shfl_sync(0xffffffffu, zerf, 1), 1e-10f);
-            const float iz1 = 1.f / fmaxf(__shfl_sync(0xffffffffu, zerf, 2) - __shfl_sync(0xffffffffu, zerf, 3), 1e-10f);
-            // cdf at the lower edge of each of my bins; the upper edge comes from the next lane
-            float c0[KJ], c1[KJ];
-#pragma unroll
-            for (int j = 0; j < KJ; ++j) {
-                c0[j] = erf_window((edge_lo[j] - y0) * inv_denom);
-                c1[j] = same ? c0[j] : erf_window((edge_lo[j] - y1) * inv_denom);
-            }
-            float p0[KJ], p1[KJ];
-            float ce0 = 0.f, ce1 = 0.f, sp0 = 0.f, sp1 = 0.f;
-#pragma unroll
-            for (int j = 0; j < KJ; ++j) {
-                const int k = j * 32 + lane;
-                // upper edge k+1: lane+1 of this j, or lane 0 of j+1
-                float u0 = __shfl_down_sync(0xffffffffu, c0[j], 1);
-                float u1 = __shfl_down_sync(0xffffffffu, c1[j], 1);
-                const float n0 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c0[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
-                const float n1 = __shfl_sync(0xffffffffu, (j + 1 < KJ) ? c1[(j + 1 < KJ) ? j + 1 : j] : 0.f, 0);
-                if (lane == 31) { u0 = n0; u1 = n1; }
-                if (k + 1 == K && (K & 31) == 0) {               // the last edge has no lane of its own
-                    u0 = erff((a.sup.hi - y0) * inv_denom);
-                    u1 = erff((a.sup.hi - y1) * inv_denom);
+            const bool same = y0 == y1;
+            const float iz0 = 1.f / fmaxf(erff((a.sup.hi - y0) * inv_denom) - erff((a.sup.lo - y0) * inv_denom), 1e-10f);
+            const float iz1 = same ? iz0 : 1.f / fmaxf(erff((a.sup.hi - y1) * inv_denom) - erff((a.sup.lo - y1) * inv_denom), 1e-10f);
+            auto ce_of = [&](float y, float iz, float &ce, float &sp) {      // cross entropy and histogram mass over the window
+                const HistWindow w = hist_window(a.sup, y, K);
+                ce = 0.f; sp = 0.f;
+                float c_prev = erff((s_edge[w.k0] - y) * inv_denom);
+                for (int k = w.k0; k < w.k1; ++k) {
+                    const float c_next = erff((s_edge[k + 1] - y) * inv_denom);
+                    const float p = (c_next - c_prev) * iz;
+                    ce -= p * (IO::ld(xr, k) - lse);
+                    sp += p;
+                    c_prev = c_next;
                 }
-                p0[j] = k < K ? (u0 - c0[j]) * iz0 : 0.f;
-                p1[j] = k < K ? (u1 - c1[j]) * iz1 : 0.f;
-                const float lsm = k < K ? lg[j] - lse : 0.f;
-                ce0 -= p0[j] * lsm; ce1 -= p1[j] * lsm;
-                sp0 += p0[j]; sp1 += p1[j];
-            }
-            ce0 = warp_sum(ce0); sp0 = warp_sum(sp0);
-            if (same) { ce1 = ce0; sp1 = sp0; } else { ce1 = warp_sum(ce1); sp1 = warp_sum(sp1); }
+            };
+            float ce0, sp0, ce1, sp1;
+            ce_of(y0, iz0, ce0, sp0);
+            if (same) { ce1 = ce0; sp1 = sp0; } else ce_of(y1, iz1, ce1, sp1);
             const float lo_old = v_old - a.cfg.value_clip, hi_old = v_old + a.cfg.value_clip;
             const bool zero = (ret < v_new && v_new < lo_old) || (hi_old < v_new && v_new < ret);   // :470-472
             const float critic = zero ? 0.f : fminf(ce0, ce1);
@@ -296,48 +248,60 @@ ppo_loss_kernel(const LossArgs a) {
                 const float w0 = zero ? 0.f : (ce0 < ce1 ? 1.f : (ce0 > ce1 ? 0.f : 0.5f));
                 const float w1 = zero ? 0.f : 1.f - w0;
                 const float gc = masked ? g_ac * a.cfg.critic_weight : 0.f;
-                const float inv_se = 1.f / se;
+                const float Asm = gc * (w0 * sp0 + w1 * sp1) * inv_se;        // coefficient of exp(x_k - mx) in every bin
+                // histogram term, window of the selected target first (reads x_k, writes g_k in place)
+                const bool use0 = same || w0 >= 0.5f;
+                const float ysel = use0 ? y0 : y1, izsel = use0 ? iz0 : iz1;
+                const float wsel = same ? gc * (w0 + w1) : gc * (use0 ? w0 : w1);
+                const HistWindow w = hist_window(a.sup, ysel, K);
+                {
+                    float c_prev = erff((s_edge[w.k0] - ysel) * inv_denom);
+                    for (int k = w.k0; k < w.k1; ++k) {
+                        const float c_next = erff((s_edge[k + 1] - ysel) * inv_denom);
+                        const float p = (c_next - c_prev) * izsel;
+                        IO::st(xr, k, Asm * IO::ex(IO::ld(xr, k) - mx) - wsel * p);
+                        c_prev = c_next;
+                    }
+                }
+                for (int p = 0; p < npieces; ++p) {                           // every other bin: A * softmax_k
+                    const int kb = p * VE;
+                    if (p < nfull && (kb + VE <= w.k0 || kb >= w.k1)) {
+                        float v[VE];
+                        IO::load(xr, p, v);
 #pragma unroll
-                for (int j = 0; j < KJ; ++j) {
-                    const int k = j * 32 + lane;
-                    if (k < K) {
-                        const float sm = ex[j] * inv_se;
-                        const float g = gc * (w0 * (sm * sp0 - p0[j]) + w1 * (sm * sp1 - p1[j]));
-                        st_from_float(g_vl + r * K + k, g);
+                        for (int j = 0; j < VE; ++j) v[j] = Asm * IO::ex(v[j] - mx);
+                        IO::store(xr, p, v);
+                    } else {
+                        for (int k = kb; k < kb + VE && k < K; ++k)
+                            if (k < w.k0 || k >= w.k1) IO::st(xr, k, Asm * IO::ex(IO::ld(xr, k) - mx));
+                    }
+                }
+                if (!same && w0 == 0.5f) {                                    // exact tie of two different targets: the other half
+                    const HistWindow w2 = hist_window(a.sup, y1, K);
+                    float c_prev = erff((s_edge[w2.k0] - y1) * inv_denom);
+                    for (int k = w2.k0; k < w2.k1; ++k) {
+                        const float c_next = erff((s_edge[k + 1] - y1) * inv_denom);
+                        IO::st(xr, k, IO::ld(xr, k) - gc * w1 * (c_next - c_prev) * iz1);
+                        c_prev = c_next;
                     }
                 }
             }
 
-            if (lane == 0) s_crit[lr] = critic;
-        }
-        __syncthreads();
-
-        // ---- phase B: the narrow terms, one THREAD per (row, part) instead of one warp per row -------------
-        // part 0: actor (A logits), part 1: world-model NLL over the S+1 dims, part 2: done BCE.  A warp now
-        // finishes 32 rows of a part per pass; these terms cost ~16 warp-instructions per row instead of ~430.
-        for (int item = threadIdx.x; item < kTileRows * 3; item += kLossWarps * 32) {
-            const int part = item / kTileRows, lr = item - part * kTileRows;
-            const int64_t r = tile * kTileRows + lr;
-            if (r >= N) continue;
-            const int e = (int)(r / T), t = (int)(r - (int64_t)e * T);
-            const bool masked = t < __ldg(a.io.episode_lens + e);
-            if (part == 0 && cont) {
-                // actor, Continuous (:224-277, :413-444): per action dim, summed over dims (:442)
-                const float ret = s_ret[lr], v_old = s_ov[lr];
-                const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
-                const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
-                const float *s_af = (const float *)s_act;
-                float actor = 0.f;
+            // ---------------- actor: clipped surrogate + entropy (:413-444) ------------------------------------
+            const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
+            const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
+            float actor = 0.f;
+            if (cont) {                                                      // Continuous (:224-277): per action dim, summed (:442)
                 for (int i = 0; i < A; ++i) {
-                    const float mean = sm_as_float(s_ra + (lr * A + i) * 2), lv = sm_as_float(s_ra + (lr * A + i) * 2 + 1);
+                    const float mean = ld_as_float(in_ra + (r * A + i) * 2), lv = ld_as_float(in_ra + (r * A + i) * 2 + 1);
                     const float th = tanhf(lv / 3.f), var = expf(th * 3.f);
                     const bool inside = var > 1e-5f;
                     const float sd = sqrtf(fmaxf(var, 1e-5f));
-                    const float v = s_af[lr * A + i], df = v - mean;
+                    const float v = __ldg(a.io.actions_f + r * A + i), df = v - mean;
                     float logp = -(df * df) / (2.f * sd * sd) - logf(sd) - 0.91893853320467274178f;
                     if (a.cfg.squash) logp -= logf(fmaxf(1.f - v * v, 1e-20f));
-                    const float ent = a.cfg.squash ? -logp : 1.41893853320467274178f + logf(sd);   // 0.5 + 0.5 log(2 pi) + log sd
-                    const float ratio = expf(logp - s_olp[lr * A + i]);
+                    const float ent = a.cfg.squash ? -logp : 1.41893853320467274178f + logf(sd);
+                    const float ratio = expf(logp - __ldg(a.io.old_log_probs + r * A + i));
                     const float clipped = fminf(fmaxf(ratio, 1.f - a.cfg.eps_clip), 1.f + a.cfg.eps_clip);
                     const float surr1 = ratio * adv, surr2 = clipped * adv;
                     actor += -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
@@ -353,44 +317,31 @@ ppo_loss_kernel(const LossArgs a) {
                         st_from_float(g_ra + (r * A + i) * 2 + 1, g_lv);
                     }
                 }
-                const float critic = s_crit[lr];
-                if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
-                acc_actor += actor; acc_critic += critic;
-                if (masked) acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
-            } else if (part == 0) {
-                // actor: clipped surrogate + entropy (:413-444, Discrete :197-222)
-                const int act = s_act[lr];
-                const float ret = s_ret[lr], v_old = s_ov[lr];
+            } else {                                                         // Discrete (:197-222)
+                const int act = __ldg(a.io.actions + r);
                 float amx = -INFINITY;
-                for (int i = 0; i < A; ++i) amx = fmaxf(amx, sm_as_float(s_ra + lr * A + i));
+                for (int i = 0; i < A; ++i) amx = fmaxf(amx, ld_as_float(in_ra + r * A + i));
                 float qs = 0.f;
-                for (int i = 0; i < A; ++i) qs += expf(sm_as_float(s_ra + lr * A + i) - amx);
+                for (int i = 0; i < A; ++i) qs += expf(ld_as_float(in_ra + r * A + i) - amx);
                 float ssum = 0.f;
-                for (int i = 0; i < A; ++i) ssum += expf(sm_as_float(s_ra + lr * A + i) - amx) / qs;   // Categorical renormalises
+                for (int i = 0; i < A; ++i) ssum += expf(ld_as_float(in_ra + r * A + i) - amx) / qs;   // Categorical renormalises
                 float ent = 0.f, logp = 0.f, p_act = 1.f, dot_p = 0.f;
                 bool in_act = false;
                 for (int i = 0; i < A; ++i) {
-                    const float sm = expf(sm_as_float(s_ra + lr * A + i) - amx) / qs, p = sm / ssum;
+                    const float sm = expf(ld_as_float(in_ra + r * A + i) - amx) / qs, p = sm / ssum;
                     const float L = logf(fminf(fmaxf(p, feps), 1.f - feps));
                     ent -= p * L;
                     if (i == act) { logp = L; p_act = p; in_act = p >= feps && p <= 1.f - feps; }
                 }
-                const float ratio = expf(logp - s_olp[lr]);
+                const float ratio = expf(logp - __ldg(a.io.old_log_probs + r));
                 const float clipped = fminf(fmaxf(ratio, 1.f - a.cfg.eps_clip), 1.f + a.cfg.eps_clip);
-                const float adv = ((ret - v_old) - adv_mean) * adv_inv_std;
                 const float surr1 = ratio * adv, surr2 = clipped * adv;
-                const float actor = -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
-                const float critic = s_crit[lr];
-                if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
-                acc_actor += actor; acc_critic += critic;
-                if (masked) acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
+                actor = -fminf(surr1, surr2) - a.cfg.entropy_weight * ent;
                 if (g_ra) {
                     const bool in_range = ratio >= 1.f - a.cfg.eps_clip && ratio <= 1.f + a.cfg.eps_clip;
                     const float dmin = in_range ? adv : (surr1 < surr2 ? adv : 0.f);
-                    const float ga = masked ? g_ac * a.cfg.actor_weight : 0.f;
                     const float g_logp = -ga * dmin * ratio;
-                    // gp_i = d/dp_i of (-beta*ent + logp term);  p = sm / sum(sm);  sm = softmax(logits)
-                    auto gp_of = [&](int i, float p, float L) {
+                    auto gp_of = [&](int i, float p, float L) {              // d/dp_i of (-beta * ent + logp term)
                         const bool inside = p >= feps && p <= 1.f - feps;
                         float gp = ga * a.cfg.entropy_weight * (L + (inside ? 1.f : 0.f));
                         if (i == act && in_act) gp += g_logp / p_act;
@@ -398,49 +349,48 @@ ppo_loss_kernel(const LossArgs a) {
                     };
                     float dot_q = 0.f;
                     for (int i = 0; i < A; ++i) {
-                        const float sm = expf(sm_as_float(s_ra + lr * A + i) - amx) / qs, p = sm / ssum;
+                        const float sm = expf(ld_as_float(in_ra + r * A + i) - amx) / qs, p = sm / ssum;
                         dot_p += gp_of(i, p, logf(fminf(fmaxf(p, feps), 1.f - feps))) * p;
                     }
                     for (int i = 0; i < A; ++i) {
-                        const float sm = expf(sm_as_float(s_ra + lr * A + i) - amx) / qs, p = sm / ssum;
-                        const float gq = (gp_of(i, p, logf(fminf(fmaxf(p, feps), 1.f - feps))) - dot_p) / ssum;
-                        dot_q += gq * sm;
+                        const float sm = expf(ld_as_float(in_ra + r * A + i) - amx) / qs, p = sm / ssum;
+                        dot_q += (gp_of(i, p, logf(fminf(fmaxf(p, feps), 1.f - feps))) - dot_p) / ssum * sm;
                     }
                     for (int i = 0; i < A; ++i) {
-                        const float sm = expf(sm_as_float(s_ra + lr * A + i) - amx) / qs, p = sm / ssum;
+                        const float sm = expf(ld_as_float(in_ra + r * A + i) - amx) / qs, p = sm / ssum;
                         const float gq = (gp_of(i, p, logf(fminf(fmaxf(p, feps), 1.f - feps))) - dot_p) / ssum;
                         st_from_float(g_ra + r * A + i, sm * (gq - dot_q));
                     }
                 }
-            } else if (part == 1) {
-                // world model: Gaussian NLL of next (state || reward) (:398-404, :232-241)
-                if (has_sp) {
-                    const bool valid = masked && t < T - 1;
-                    float nll = 0.f;
-                    for (int dd = 0; dd < S1; ++dd) {
-                        const float mean = sm_as_float(s_sp + (lr * S1 + dd) * 2);
-                        const float lv = sm_as_float(s_sp + (lr * S1 + dd) * 2 + 1);
-                        float gm = 0.f, gl = 0.f;
-                        if (valid) {
-                            const float th = tanhf(lv / 3.f);
-                            const float var = fmaxf(expf(th * 3.f), 1e-6f);
-                            const float d = mean - s_tgt[(lr + 1) * S1 + dd];
-                            nll += 0.5f * (logf(var) + d * d / var);
-                            gm = g_wm * d / var;
-                            gl = g_wm * 0.5f * (1.f / var - d * d / (var * var)) * var * (1.f - th * th);
-                        }
-                        if (g_sp) {
-                            st_from_float(g_sp + (r * S1 + dd) * 2, gm);
-                            st_from_float(g_sp + (r * S1 + dd) * 2 + 1, gl);
-                        }
+            }
+            if (a.io.per_step) { a.io.per_step[r * 2] = actor; a.io.per_step[r * 2 + 1] = critic; }
+            acc_actor += actor; acc_critic += critic;
+            if (masked) acc_ac += a.cfg.actor_weight * actor + a.cfg.critic_weight * critic;
+
+            // ---------------- world model: Gaussian NLL of next (state || reward) (:398-404, :232-241) ----------
+            if (in_sp) {
+                const bool valid = masked && t < T - 1;
+                float nll = 0.f;
+                for (int dd = 0; dd < S1; ++dd) {
+                    float gm = 0.f, gl = 0.f;
+                    if (valid) {
+                        const float mean = ld_as_float(in_sp + (r * S1 + dd) * 2), lv = ld_as_float(in_sp + (r * S1 + dd) * 2 + 1);
+                        const float th = tanhf(lv / 3.f);
+                        const float var = fmaxf(expf(th * 3.f), 1e-6f);
+                        const float d = mean - __ldg(a.io.target + (r + 1) * S1 + dd);
+                        nll += 0.5f * (logf(var) + d * d / var);
+                        gm = g_wm * d / var;
+                        gl = g_wm * 0.5f * (1.f / var - d * d / (var * var)) * var * (1.f - th * th);
                     }
-                    acc_nll += nll;
+                    if (g_sp) { st_from_float(g_sp + (r * S1 + dd) * 2, gm); st_from_float(g_sp + (r * S1 + dd) * 2 + 1, gl); }
                 }
-            } else if (has_dl) {
-                // done head: BCE on sigmoid(logit) (:406-411)
-                const float z = sm_as_float(s_dl + lr);
+                acc_nll += nll;
+            }
+            // ---------------- done head: BCE on sigmoid(logit) (:406-411) ---------------------------------------
+            if (in_dl) {
+                const float z = ld_as_float(in_dl + r);
                 const float pd = 1.f / (1.f + expf(-z));
-                const float y = s_dn[lr] ? 1.f : 0.f;
+                const float y = __ldg(a.io.dones + r) ? 1.f : 0.f;
                 const float l1 = logf(pd), l0 = logf(1.f - pd);
                 const float bce = -(y * fmaxf(l1, -100.f) + (1.f - y) * fmaxf(l0, -100.f));
                 float g = 0.f;
@@ -453,17 +403,20 @@ ppo_loss_kernel(const LossArgs a) {
                 if (g_dl) st_from_float(g_dl + r, g);
             }
         }
-        __syncthreads();                                           // this stage is refilled two tiles from now
+        __syncthreads();
+        if (g_vl)
+            for (int row = warp; row < nrows; row += kRowThreads / 32)
+                copy_row(reinterpret_cast<unsigned char *>(g_vl) + (r0 + row) * rowbytes, smem + (size_t)row * row_stride, rowbytes, unit, lane);
     }
 
     acc_ac = warp_sum(acc_ac); acc_actor = warp_sum(acc_actor); acc_critic = warp_sum(acc_critic);
     acc_nll = warp_sum(acc_nll); acc_done = warp_sum(acc_done);
-    __shared__ float sh[5][kLossWarps];
+    __shared__ float sh[5][kRowThreads / 32];
     if (lane == 0) { sh[0][warp] = acc_ac; sh[1][warp] = acc_actor; sh[2][warp] = acc_critic; sh[3][warp] = acc_nll; sh[4][warp] = acc_done; }
     __syncthreads();
     if (threadIdx.x < 5) {
         double s = 0.;
-        for (int i = 0; i < kLossWarps; ++i) s += (double)sh[threadIdx.x][i];
+        for (int i = 0; i < kRowThreads / 32; ++i) s += (double)sh[threadIdx.x][i];
         atomicAdd(a.io.workspace + WS_AC_MASKED + threadIdx.x, s);
     }
 }
@@ -504,24 +457,6 @@ hl_decode_kernel(const float *__restrict__ logits, float *__restrict__ out, int6
     }
 }
 
-template <typename TIO, int KJ>
-static int launch_loss_kj(const LossArgs &la, int blocks, size_t smem, cudaStream_t s) {
-    XTRL_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<TIO, KJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ppo_loss_kernel<TIO, KJ><<<blocks, kLossWarps * 32, smem, s>>>(la);
-    XTRL_LAUNCH_CHECK("ppo_loss_kernel");
-    return XTRL_OK;
-}
-
-template <typename TIO>
-static int launch_loss(const LossArgs &la, int KJ, int blocks, size_t smem, cudaStream_t s) {
-    switch (KJ) {
-        case 1: return launch_loss_kj<TIO, 1>(la, blocks, smem, s);
-        case 2: return launch_loss_kj<TIO, 2>(la, blocks, smem, s);
-        case 4: return launch_loss_kj<TIO, 4>(la, blocks, smem, s);
-        default: return launch_loss_kj<TIO, 8>(la, blocks, smem, s);
-    }
-}
-
 }  // namespace xtrl
 
 extern "C" int64_t xtrl_ppo_loss_workspace_bytes(void) { return (int64_t)sizeof(double) * 16; }
@@ -556,22 +491,30 @@ extern "C" int xtrl_ppo_loss_fwd_bwd(const xtrl_loss_cfg *cfg, const xtrl_loss_i
     LossArgs la;
     la.cfg = *cfg; la.io = *io; la.b = batch; la.T = num_timesteps;
     la.sup = make_support(cfg->reward_min, cfg->reward_max, cfg->num_bins);
-    const int kj = (cfg->num_bins + 31) / 32;
-    const int KJ = kj <= 1 ? 1 : kj <= 2 ? 2 : kj <= 4 ? 4 : 8;
     const int sz = cfg->bf16_io ? 2 : 4;
-    const int AWh = cfg->continuous ? 2 * cfg->num_actions : cfg->num_actions, ALh = cfg->continuous ? cfg->num_actions : 1;
-    const TileLayout tl = tile_layout(AWh, ALh, cfg->num_bins, cfg->state_dim + 1, sz);
-    const size_t smem = 2 * (size_t)tl.total;                              // double-buffered tile stages
-    XTRL_REQUIRE(smem <= 200 * 1024, XTRL_E_UNSUPPORTED, "xtrl_ppo_loss_fwd_bwd: tile needs %zu B shared memory", smem);
     const void *ptrs[] = {io->raw_actions, io->value_logits, io->state_pred_raw, io->done_logit, io->actions, io->old_log_probs,
-                          io->returns, io->old_values, io->target, io->dones, io->actions_f};
+                          io->returns, io->old_values, io->target, io->dones, io->actions_f, io->g_value_logits};
     for (const void *p : ptrs)
         XTRL_REQUIRE(((uintptr_t)p & 15) == 0, XTRL_E_BADARG, "xtrl_ppo_loss_fwd_bwd: input pointers must be 16-byte aligned");
-    const int64_t ntiles = (N + kTileRows - 1) / kTileRows;
-    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    // one thread per row; the tile's row stride is an odd number of 16-byte units (16-byte row pieces are then conflict-free)
+    const int rowbytes = cfg->num_bins * sz;
+    int stride = (rowbytes + 15) & ~15;
+    if (((stride / 16) & 1) == 0) stride += 16;
+    const int unit = rowbytes % 16 == 0 ? 16 : rowbytes % 8 == 0 ? 8 : rowbytes % 4 == 0 ? 4 : 2;
+    const size_t smem = (size_t)kRowThreads * stride + (size_t)(2 * cfg->num_bins + 1) * sizeof(float) + 16;
+    XTRL_REQUIRE(smem <= 200 * 1024, XTRL_E_UNSUPPORTED, "xtrl_ppo_loss_fwd_bwd: tile needs %zu B shared memory", smem);
+    const int64_t ntiles = (N + kRowThreads - 1) / kRowThreads;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    per_sm = per_sm > 12 ? 12 : (per_sm < 1 ? 1 : per_sm);
     const int blocks = (int)(ntiles < (int64_t)per_sm * num_sms() ? ntiles : (int64_t)per_sm * num_sms());   // persistent CTAs
-    int rc = cfg->bf16_io ? launch_loss<__nv_bfloat16>(la, KJ, blocks, smem, s) : launch_loss<float>(la, KJ, blocks, smem, s);
-    if (rc) return rc;
+    if (cfg->bf16_io) {
+        XTRL_CUDA(cudaFuncSetAttribute(ppo_loss_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ppo_loss_rows_kernel<__nv_bfloat16><<<blocks, kRowThreads, smem, s>>>(la, stride, unit);
+    } else {
+        XTRL_CUDA(cudaFuncSetAttribute(ppo_loss_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ppo_loss_rows_kernel<float><<<blocks, kRowThreads, smem, s>>>(la, stride, unit);
+    }
+    XTRL_LAUNCH_CHECK("ppo_loss_rows_kernel");
     ppo_finalize_kernel<<<1, 1, 0, s>>>(io->workspace, io->scalars, N, cfg->state_dim + 1, cfg->autoreg_weight,
                                         cfg->normalize_advantages);
     XTRL_LAUNCH_CHECK("ppo_finalize_kernel");
