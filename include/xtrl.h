@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define XTRL_ABI_VERSION 7
+#define XTRL_ABI_VERSION 8
 
 #define XTRL_OK            0
 #define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
@@ -397,9 +397,59 @@ int xtrl_ln_bwd(const float *x, const float *dy, const float *gamma, float *dx, 
 int xtrl_small_dw(const float *feats, const int64_t *ids, const float *dy, float *d_w, float *d_b, int64_t N, int32_t K,
                   int32_t dim, int32_t out_kj, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (7) minibatch prologue of Agent.learn and its backward -- replace the DataLoader gather (:876-901), the prev-action /
+ *     prev-reward shifts (:911-918), RSNorm.eval on the packed rows (:920-926), the masked batch mean of the RSNorm copy
+ *     update (:1005, :601) and the input side of WorldModelActorCritic.forward (:492-503, :516-529).
+ *     Sources are EPISODE-major [E][T][..]; outputs are minibatch-major [b][T][..], hidden size 48.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct xtrl_prep_io {
+    const float   *states;          /* [E][T][S]                                              */
+    const void    *actions;         /* [E][T] int32, or [E][T][A] float when continuous       */
+    const float   *rewards;         /* [E][T]                                                 */
+    const float   *old_log_probs;   /* [E][T], or [E][T][A] when continuous                   */
+    const float   *returns, *old_values;                    /* [E][T]                         */
+    const uint8_t *dones;           /* [E][T]                                                 */
+    const int32_t *lens;            /* [E]                                                    */
+    const int32_t *gene_ids;        /* [E] or NULL                                            */
+    const int64_t *idx;             /* [b] the minibatch's episodes                           */
+    const float   *rs_mean, *rs_var;                        /* [S+1] RSNorm statistics         */
+    const float   *w_in;            /* transformer.project_in.weight [48][S]                  */
+    const float   *w_se, *b_se;     /* to_state_embed weight [48][S], bias [48]               */
+    const float   *w_act;           /* action_embeds: table [A][48], or Linear weight [48][A] when continuous */
+    const float   *b_act;           /* Linear bias [48] (continuous), else NULL               */
+    const float   *reward_embed;    /* [48]                                                   */
+    const float   *reward_flag;     /* device scalar: the reward-conditioning Bernoulli (:501) */
+    float *x0;                      /* [b][T][48] project_in(state) + action_embeds(prev action) + prev reward * reward_embed * flag */
+    float *se;                      /* [b][T][48] to_state_embed(state)                       */
+    float *ae_next;                 /* [b][T][48] action_embeds(action)                       */
+    float *packed;                  /* [b][T][S+1] normalised (state || prev reward)          */
+    void  *mb_actions;              /* gathered copies of the per-row fields, layouts as the sources */
+    float *mb_old_log_probs, *mb_returns, *mb_old_values;
+    uint8_t *mb_dones;
+    int32_t *mb_lens, *mb_gene_ids; /* [b]                                                    */
+    float *rs_sum;                  /* [S+2] += masked column sums of packed, then the masked row count */
+} xtrl_prep_io;
+
+typedef struct xtrl_prep_bwd_io {
+    const float *dx0;               /* [b][T][48]                                             */
+    const float *d_se;              /* [b][T][48] or NULL                                     */
+    const float *d_ae_next;         /* [b][T][48] or NULL                                     */
+    const float *packed;            /* [b][T][S+1]                                            */
+    const void  *mb_actions;        /* [b][T] int32 / [b][T][A] float                         */
+    const float *reward_flag;
+    int32_t T;                      /* timesteps per episode (row r starts an episode when r % T == 0) */
+    float *d_w_in, *d_w_se, *d_b_se, *d_w_act, *d_b_act, *d_reward_embed;      /* += ; layouts of the parameters */
+} xtrl_prep_bwd_io;
+
+int xtrl_learn_prep_fwd(const xtrl_prep_io *io, int32_t b, int32_t T, int32_t state_dim, int32_t num_actions,
+                        int32_t continuous, void *stream);
+int xtrl_learn_prep_bwd(const xtrl_prep_bwd_io *io, int32_t b, int32_t T, int32_t state_dim, int32_t num_actions,
+                        int32_t continuous, void *stream);
+
 /* sizeof of the ABI structures as this library was compiled (binding self-check): 0 xtrl_model_desc, 1 xtrl_weight_layout,
  * 2 xtrl_step_io, 3 xtrl_loss_cfg, 4 xtrl_loss_io, 5 xtrl_pool_desc, 6 xtrl_opt_cfg, 7 xtrl_ff_io, 8 xtrl_attn_io,
- * 9 xtrl_attn_core_io, 10 xtrl_mlp_io; -1 for anything else.                                                      */
+ * 9 xtrl_attn_core_io, 10 xtrl_mlp_io, 11 xtrl_prep_io, 12 xtrl_prep_bwd_io; -1 for anything else.                     */
 int64_t xtrl_struct_size(int32_t which);
 
 #ifdef __cplusplus

@@ -7,7 +7,7 @@ B, T = 1024, 500
 dt = sys.argv[1] if len(sys.argv) > 1 else 'bf16'
 learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=T, world_model=dict(attn_dim_head=16, heads=8, depth=4),
                     batch_size=256, num_episodes_per_update=B, epochs=1, agent_kwargs=dict(save_path=os.path.join(tempfile.gettempdir(), 'p.pt')),
-                    accelerate_kwargs=dict(mixed_precision=dt) if dt == 'bf16' else {})
+                    accelerate_kwargs=dict(mixed_precision='bf16' if dt == 'bf16' else 'no'))
 env = E.SyntheticVecEnv(B, 8, T, device=learner.device)
 gids = torch.zeros(B, dtype=torch.int32, device=learner.device)
 buf, _ = learner.rollout_vectorized(env, gids, T)

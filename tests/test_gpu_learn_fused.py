@@ -465,3 +465,61 @@ def test_attn_core_exact_max_path_for_large_norms():
     for got, ref, name in ((dq, q32.grad, 'dq'), (dk, k32.grad, 'dk'), (dv, v32.grad, 'dv')):
         err = float((got.float() - ref).abs().max() / ref.abs().max().clamp(min=0.5))
         assert err < 2 * TOL_BF16, (name, err)
+
+
+# ---------------------------------------------------------------------------------------------
+# minibatch prologue (gather + shifts + RSNorm + input embeddings) and its backward, csrc/learn_prep.cu
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('continuous', (False, True))
+@pytest.mark.parametrize('S,A,E,b,T', ((8, 4, 9, 5, 37), (5, 2, 4, 4, 10), (16, 16, 3, 2, 130)))
+def test_learn_prologue_forward_backward_vs_torch(continuous, S, A, E, b, T):
+    """xtrl_learn_prep_fwd / _bwd against the torch expression of Agent.learn's minibatch prep (:903-926) and the input side of
+    WorldModelActorCritic.forward (:492-503, :516-529): exact fp32 arithmetic, so 1e-5."""
+    ops = xtrl().ops
+    g = torch.Generator().manual_seed(S * 100 + A + T)
+    r = lambda *s, sc=1.: (torch.randn(*s, generator=g) * sc).to(DEV)
+    lens = torch.randint(1, T + 1, (E,), generator=g).int().to(DEV)
+    src = dict(states=r(E, T, S), actions=(torch.tanh(r(E, T, A)) if continuous else torch.randint(0, A, (E, T), generator=g).int().to(DEV)),
+               rewards=r(E, T), old_log_probs=-r(E, T, A).abs() if continuous else -r(E, T).abs(), returns=r(E, T), old_values=r(E, T),
+               dones=(torch.rand(E, T, generator=g) < 0.1).to(DEV), lens=lens, gene_ids=torch.arange(E, dtype=torch.int32, device=DEV) % 3)
+    idx = torch.randperm(E, generator=g)[:b].to(DEV)
+    mean, var = r(S + 1, sc=0.3), (torch.rand(S + 1, generator=g) + 0.5).to(DEV)
+    var[1] = 0.                                                       # the clamp (variance 0 after the first RSNorm update, SURVEY B.4)
+    w_in, w_se, b_se, re = r(48, S, sc=0.3).requires_grad_(), r(48, S, sc=0.3).requires_grad_(), r(48, sc=0.1).requires_grad_(), r(48, sc=0.1).requires_grad_()
+    w_act = (r(48, A, sc=0.3) if continuous else r(A, 48, sc=0.3)).requires_grad_()
+    b_act = r(48, sc=0.1).requires_grad_() if continuous else None
+    flag = torch.tensor(1., device=DEV)
+    out = ops.learn_prep_fwd(src, idx, mean, var, w_in.detach(), w_se.detach(), b_se.detach(), w_act.detach(),
+                             b_act.detach() if continuous else None, re.detach(), flag, continuous=continuous)
+    # torch reference
+    st, ac, rw = src['states'][idx], src['actions'][idx], src['rewards'][idx]
+    prev_r = F.pad(rw, (1, -1), value=0.)
+    packed = (torch.cat((st, prev_r[..., None]), -1) - mean) / var.sqrt().clamp(min=1e-5)
+    if continuous:
+        prev_a = F.pad(ac, (0, 0, 1, -1), value=0.)
+        ae_prev, ae_next = F.linear(prev_a, w_act, b_act), F.linear(ac, w_act, b_act)
+    else:
+        prev_a = F.pad(ac, (1, -1), value=-1)
+        emb = lambda ids: F.embedding(ids.clamp(min=0).long(), w_act) * (ids >= 0)[..., None]
+        ae_prev, ae_next = emb(prev_a), emb(ac)
+    x0 = F.linear(packed[..., :S], w_in) + ae_prev + packed[..., S:] * re * flag
+    se = F.linear(packed[..., :S], w_se, b_se)
+    assert maxrel(out['packed'], packed) < 1e-5 and maxrel(out['x0'], x0.detach()) < 1e-5
+    assert maxrel(out['se'], se.detach()) < 1e-5 and maxrel(out['ae_next'], ae_next.detach()) < 1e-5
+    for k in ('returns', 'old_values', 'old_log_probs'):
+        assert torch.equal(out[k], src[k][idx]), k
+    assert torch.equal(out['actions'], ac) and torch.equal(out['dones'].bool(), src['dones'][idx])
+    assert torch.equal(out['lens'], lens[idx]) and torch.equal(out['gene_ids'], src['gene_ids'][idx])
+    mask = torch.arange(T, device=DEV)[None] < lens[idx][:, None]
+    want_sum = (packed * mask[..., None]).sum((0, 1))
+    assert maxrel(out['rs_sum'][:S + 1], want_sum) < 1e-4 and float(out['rs_sum'][S + 1]) == float(mask.sum())
+    # backward
+    dx0, dse, dae = r(b, T, 48, sc=1e-2), r(b, T, 48, sc=1e-2), r(b, T, 48, sc=1e-2)
+    ((x0 * dx0).sum() + (se * dse).sum() + (ae_next * dae).sum()).backward()
+    grads = dict(w_in=torch.zeros_like(w_in), w_se=torch.zeros_like(w_se), b_se=torch.zeros_like(b_se), w_act=torch.zeros_like(w_act),
+                 b_act=torch.zeros(48, device=DEV) if continuous else None, re=torch.zeros_like(re))
+    ops.learn_prep_bwd(dx0, dse, dae, out['packed'], out['actions'], flag, grads['w_in'], grads['w_se'], grads['b_se'], grads['w_act'],
+                       grads['b_act'], grads['re'], continuous=continuous)
+    for name, p in (('w_in', w_in), ('w_se', w_se), ('b_se', b_se), ('w_act', w_act), ('re', re)) + ((('b_act', b_act),) if continuous else ()):
+        assert maxrel(grads[name], p.grad) < 1e-4, (name, maxrel(grads[name], p.grad))

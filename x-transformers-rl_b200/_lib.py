@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-XTRL_ABI_VERSION = 7
+XTRL_ABI_VERSION = 8
 XTRL_MAX_DEPTH = 16
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -95,6 +95,18 @@ class MlpIO(C.Structure):
                 ('d_w2', c_vp), ('d_b2', c_vp), ('n_silu', c_i32), ('out_cols', c_i32)]
 
 
+class PrepIO(C.Structure):
+    _fields_ = [(n, c_vp) for n in ('states', 'actions', 'rewards', 'old_log_probs', 'returns', 'old_values', 'dones', 'lens', 'gene_ids', 'idx',
+                                    'rs_mean', 'rs_var', 'w_in', 'w_se', 'b_se', 'w_act', 'b_act', 'reward_embed', 'reward_flag',
+                                    'x0', 'se', 'ae_next', 'packed', 'mb_actions', 'mb_old_log_probs', 'mb_returns', 'mb_old_values',
+                                    'mb_dones', 'mb_lens', 'mb_gene_ids', 'rs_sum')]
+
+
+class PrepBwdIO(C.Structure):
+    _fields_ = [(n, c_vp) for n in ('dx0', 'd_se', 'd_ae_next', 'packed', 'mb_actions', 'reward_flag')] + [('T', c_i32)] + [
+        (n, c_vp) for n in ('d_w_in', 'd_w_se', 'd_b_se', 'd_w_act', 'd_b_act', 'd_reward_embed')]
+
+
 # every symbol include/xtrl.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'xtrl_abi_version': (c_i32, []),
@@ -135,11 +147,13 @@ SYMBOLS = {
     'xtrl_small_dw': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_ln_fwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     'xtrl_ln_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    'xtrl_learn_prep_fwd': (c_i32, [C.POINTER(PrepIO), c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_learn_prep_bwd': (c_i32, [C.POINTER(PrepBwdIO), c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
 }
 
 
 # order of xtrl_struct_size(which)
-ABI_STRUCTS = (ModelDesc, WeightLayout, StepIO, LossCfg, LossIO, PoolDesc, OptCfg, FfIO, AttnIO, AttnCoreIO, MlpIO)
+ABI_STRUCTS = (ModelDesc, WeightLayout, StepIO, LossCfg, LossIO, PoolDesc, OptCfg, FfIO, AttnIO, AttnCoreIO, MlpIO, PrepIO, PrepBwdIO)
 
 
 class XtrlError(RuntimeError):

@@ -96,16 +96,25 @@ class _LearnGraph:
     """static minibatch buffers + the CUDA graph of Agent._fwd_bwd over them.  Captured lazily on the first real
     minibatch (after two eager warm-up passes on a side stream, as graph capture requires)."""
 
-    def __init__(self, agent, b, T):
+    def __init__(self, agent, b, T, E):
         self.agent, dev, cfg = agent, agent.device, agent.cfg
         A = cfg.num_actions
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=dev, dtype=dt)
         cont = agent.continuous_actions
-        self.mb = dict(states=z(b, T, cfg.state_dim), actions=z(b, T, A) if cont else z(b, T, dt=torch.int32), rewards=z(b, T),
-                       old_log_probs=z(b, T, A) if cont else z(b, T), returns=z(b, T), old_values=z(b, T),
-                       dones=z(b, T, dt=torch.bool), lens=z(b, dt=torch.int32), gene_ids=z(b, dt=torch.int32))
+        if agent.fused_learn:          # bf16 class: the prologue kernel gathers straight out of the persistent episode-major sources
+            self.src, self.idx, self.mb = agent._learn_sources(E, T), z(b, dt=torch.int64), None
+        else:
+            self.mb = dict(states=z(b, T, cfg.state_dim), actions=z(b, T, A) if cont else z(b, T, dt=torch.int32), rewards=z(b, T),
+                           old_log_probs=z(b, T, A) if cont else z(b, T), returns=z(b, T), old_values=z(b, T),
+                           dones=z(b, T, dt=torch.bool), lens=z(b, dt=torch.int32), gene_ids=z(b, dt=torch.int32))
         self.flag = torch.ones((), device=dev)
         self.graph, self.scalars = None, None
+
+    def _pass(self, collective=True):
+        agent = self.agent
+        if agent.fused_learn:
+            return agent._fwd_bwd_prepared(self.src, self.idx, self.flag, collective=collective)
+        return agent._fwd_bwd(self.mb, self.flag, collective=collective)
 
     def capture(self):
         """two eager warm-up passes on a side stream, then the capture.  A failure here is an error (there is no eager
@@ -117,12 +126,12 @@ class _LearnGraph:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    agent._fwd_bwd(self.mb, self.flag, collective=False)
+                    self._pass(collective=False)
             cur.wait_stream(side)
             agent._comm.zero_()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self.scalars = agent._fwd_bwd(self.mb, self.flag)
+                self.scalars = self._pass()
             self.graph = graph
         finally:
             torch.cuda.current_stream(agent.device).synchronize()
@@ -206,6 +215,7 @@ class Agent(nn.Module):
         self.fused_learn = self.accelerator.mixed_precision == 'bf16'
         self.use_cuda_graph_learn = True     # fwd + losses + bwd (+ the gradient all-reduce) of a minibatch as one graph replay
         self._learn_graphs = {}
+        self._learn_src = {}
         # replicas start from rank 0's values, as DDP's wrap does in the reference (:885), whatever each rank's RNG drew
         if self.evolutionary:
             broadcast_from_rank0_(self.model.flat_params, self.gene_pool.genes.data)
@@ -279,6 +289,10 @@ class Agent(nn.Module):
         self.last_grads = None
         fields = ('states', 'actions', 'rewards', 'old_log_probs', 'returns', 'old_values', 'dones', 'lens', 'gene_ids')
         reward_flags = iter(reward_flags) if reward_flags is not None else None
+        if self.fused_learn:                 # persistent episode-major sources: captured graphs keep reading the same addresses
+            src = self._learn_sources(E, T)
+            for k in fields:
+                src[k].copy_(data[k])
         for epoch in range(self.epochs):
             perm = permutations[epoch].to(dev) if permutations is not None else torch.randperm(E, device=dev)
             for lo in range(0, E, self.batch_size):
@@ -286,16 +300,21 @@ class Agent(nn.Module):
                 flag = float(torch.rand(()) >= 0.5) if model.training else 1.                        # reward dropout :501
                 if reward_flags is not None:
                     flag = float(next(reward_flags))
-                lg = self._learn_graph(idx.numel(), T) if self.use_cuda_graph_learn else None
+                lg = self._learn_graph(idx.numel(), T, E) if self.use_cuda_graph_learn else None
                 if self.event_log is not None:
                     evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 if lg is not None:                       # static minibatch buffers -> one graph replay (fwd + losses + bwd)
-                    for k in fields:
-                        torch.index_select(data[k], 0, idx, out=lg.mb[k])
+                    if self.fused_learn:
+                        lg.idx.copy_(idx)                # the prologue kernel gathers inside the graph
+                    else:
+                        for k in fields:
+                            torch.index_select(data[k], 0, idx, out=lg.mb[k])
                     lg.flag.fill_(flag)
                     if self.event_log is not None:
                         evs[0].record()
                     scalars = lg.run()
+                elif self.fused_learn:
+                    scalars = self._fwd_bwd_prepared(src, idx.long(), torch.full((), flag, device=dev))
                 else:
                     scalars = self._fwd_bwd({k: data[k][idx] for k in fields}, flag)
                 # self._comm now holds the SUM over ranks of [gradients | RSNorm batch mean] (the all-reduce is the last
@@ -354,12 +373,42 @@ class Agent(nn.Module):
             all_reduce_sum_(self._comm)              # gradients (+ RSNorm batch mean in the tail), one collective
         return scalars
 
-    def _learn_graph(self, b, T):
-        """the captured fwd + bwd (+ all-reduce) of a (b, T) minibatch"""
-        key = (b, T)
+    def _learn_graph(self, b, T, E):
+        """the captured fwd + bwd (+ all-reduce) of a (b, T) minibatch drawn from E episodes"""
+        key = (b, T, E)
         if key not in self._learn_graphs:
-            self._learn_graphs[key] = _LearnGraph(self, b, T)
+            self._learn_graphs[key] = _LearnGraph(self, b, T, E)
         return self._learn_graphs[key]
+
+    def _learn_sources(self, E, T):
+        """episode-major trajectory tensors of one learning update at fixed addresses (what xtrl_learn_prep_fwd gathers from)"""
+        key = (E, T)
+        if key not in self._learn_src:
+            cfg, dev, A, cont = self.cfg, self.device, self.cfg.num_actions, self.continuous_actions
+            z = lambda *s, dt=torch.float32: torch.zeros(*s, device=dev, dtype=dt)
+            self._learn_src = {key: dict(                  # one set alive at a time
+                states=z(E, T, cfg.state_dim), actions=z(E, T, A) if cont else z(E, T, dt=torch.int32), rewards=z(E, T),
+                old_log_probs=z(E, T, A) if cont else z(E, T), returns=z(E, T), old_values=z(E, T), dones=z(E, T, dt=torch.bool),
+                lens=z(E, dt=torch.int32), gene_ids=z(E, dt=torch.int32))}
+            self._learn_graphs = {k: v for k, v in self._learn_graphs.items() if (k[2], k[1]) == key}
+        return self._learn_src[key]
+
+    def _fwd_bwd_prepared(self, src, idx, flag, collective=True):
+        """one minibatch of the bf16 class: prologue kernel (gather, shifts, RSNorm, input embeddings :903-926, :492-503) ->
+        tcgen05 sequence model -> fused loss kernel -> backward into the flat gradient buffer; the RSNorm batch mean lands in the
+        buffer's tail; then the SUM all-reduce.  `flag` is a device scalar."""
+        model, cfg = self.model, self.cfg
+        S, n = cfg.state_dim, model.flat_params.numel()
+        gene_fn = (lambda ids: self.gene_pool[ids]) if self.evolutionary else None                  # :906
+        ra, vl, spr, dl, box = model.forward_prepared(src, idx, self.rsnorm.running_mean, self.rsnorm.running_variance, flag, gene_fn)
+        loss, scalars = FusedPPOLoss.apply(self.loss_cfg, ra, vl, spr, dl, box['actions'], box['old_log_probs'], box['returns'],
+                                           box['old_values'], box['packed'], box['dones'], box['lens'])
+        loss.backward()
+        rs = box['rs_sum']                                                                           # :1005, :601
+        self._comm[n:] = rs[:S + 1] / rs[S + 1].clamp(min=1.)
+        if collective:
+            all_reduce_sum_(self._comm)
+        return scalars
 
     def _optimizer_step(self, grad_scale=1.):
         model = self.model

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libxtrl.so')
 STAMP = LIB_PATH + '.srchash'
-SOURCES = ('api.cu', 'gae.cu', 'ppo_loss.cu', 'evolve.cu', 'optim.cu', 'wm_step.cu', 'learn_ff.cu', 'learn_attn.cu', 'learn_attn_core.cu', 'learn_ln.cu', 'learn_mlp.cu')
+SOURCES = ('api.cu', 'gae.cu', 'ppo_loss.cu', 'evolve.cu', 'optim.cu', 'wm_step.cu', 'learn_ff.cu', 'learn_attn.cu', 'learn_attn_core.cu', 'learn_ln.cu', 'learn_mlp.cu', 'learn_prep.cu')
 NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared', '-cudart', 'shared')
 

@@ -49,6 +49,8 @@ extern "C" int64_t xtrl_struct_size(int32_t which) {
         case 8: return sizeof(xtrl_attn_io);
         case 9: return sizeof(xtrl_attn_core_io);
         case 10: return sizeof(xtrl_mlp_io);
+        case 11: return sizeof(xtrl_prep_io);
+        case 12: return sizeof(xtrl_prep_bwd_io);
         default: return -1;
     }
 }

@@ -161,6 +161,36 @@ class _SkinnyLinear(torch.autograd.Function):
         return None, dw, db
 
 
+class _FusedPrep(torch.autograd.Function):
+    """autograd seam around xtrl_learn_prep_fwd / _bwd (csrc/learn_prep.cu): the minibatch gather + RSNorm + input embeddings.
+    Returns (x0, se, ae_next); everything else the prologue produced is in `out` (not differentiable).  The parameters are not
+    autograd inputs: their gradients are accumulated straight into the .grad views of the flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, src, idx, rs_mean, rs_var, flag, out_box):
+        cont = model.cfg.continuous
+        ae = model.action_embeds
+        out = ops.learn_prep_fwd(src, idx, rs_mean, rs_var, model.transformer.project_in.weight.data, model.to_state_embed.weight.data,
+                                 model.to_state_embed.bias.data, ae.weight.data if cont else ae.embed.weight.data,
+                                 ae.bias.data if cont else None, model.reward_embed.data, flag, continuous=cont)
+        out_box.update(out)
+        ctx.model, ctx.flag = model, flag
+        ctx.save_for_backward(out['packed'], out['actions'])
+        return out['x0'], out['se'], out['ae_next']
+
+    @staticmethod
+    def backward(ctx, dx0, d_se, d_ae):
+        packed, acts = ctx.saved_tensors
+        model = ctx.model
+        cont = model.cfg.continuous
+        ae = model.action_embeds
+        c = lambda t: None if t is None else t.float().contiguous()
+        ops.learn_prep_bwd(c(dx0), c(d_se), c(d_ae), packed, acts, ctx.flag, model.transformer.project_in.weight.grad,
+                           model.to_state_embed.weight.grad, model.to_state_embed.bias.grad, ae.weight.grad if cont else ae.embed.weight.grad,
+                           ae.bias.grad if cont else None, model.reward_embed.grad, continuous=cont)
+        return None, None, None, None, None, None, None, None
+
+
 class _FracGrad(torch.autograd.Function):
     """forward identity, backward x frac (x_transformers_rl.py:114-116) without the detach / scale / add round trip."""
 
@@ -466,10 +496,35 @@ class WorldModelActorCritic(nn.Module):
 
 
     def _forward_fused(self, x, state, next_actions, mask, latent_gene, ang, p_drop):
-        """the bf16 class: every sub-layer of the Decoder, the final norm and the three head MLPs are libxtrl tcgen05
-        kernels behind autograd seams (csrc/learn_*.cu).  Unsupported shapes raise (fused_state / attn core)."""
+        """the bf16 class from torch-made inputs (model-level tests): input embeddings by torch ops, then the fused trunk / heads."""
+        n = state.shape[1]
+        lens32 = mask.sum(dim=1, dtype=torch.int32)          # episodes are right-padded: mask == position < length
+        with torch.autocast('cuda', enabled=False):
+            se32 = _SkinnyLinear.apply(state, self.to_state_embed.weight, self.to_state_embed.bias)
+            lat = self.latent_to_embed(latent_gene.float()) if self.evolutionary else None
+        embed = self._fused_trunk(x, lens32, n, ang, p_drop)
+        return self._fused_heads(embed, se32, self.action_embeds(next_actions), lat, n)
+
+    def forward_prepared(self, src, idx, rs_mean, rs_var, flag, latent_gene_fn=None):
+        """the bf16 class as Agent.learn runs it: prologue kernel (gather + RSNorm + input embeddings, csrc/learn_prep.cu) ->
+        fused trunk -> fused heads.  Returns (raw_actions, value_logits, state_pred_raw, done_logit, prologue outputs dict)."""
+        cfg = self.cfg
+        n = src['states'].shape[1]
+        box = {}
+        x0, se, ae_next = _FusedPrep.apply(self.reward_embed, self, src, idx, rs_mean, rs_var, flag, box)
+        lat = None
+        if self.evolutionary:
+            lat = self.latent_to_embed(latent_gene_fn(box['gene_ids'].long()).float())
+        ang = torch.arange(n, device=x0.device, dtype=torch.float32)[:, None] * self.transformer.attn_layers.rotary_pos_emb.inv_freq[None]
+        ang = ang.repeat_interleave(2, dim=-1)
+        p_drop = self.dropout if self.training else 0.
+        embed = self._fused_trunk(x0, box['lens'], n, ang, p_drop)
+        return (*self._fused_heads(embed, se, ae_next, lat, n), box)
+
+    def _fused_trunk(self, x, lens32, n, ang, p_drop):
+        """every sub-layer of the Decoder and the final norm as libxtrl tcgen05 kernels behind autograd seams (csrc/learn_*.cu).
+        Unsupported shapes raise (fused_state / attention core)."""
         cfg, dec = self.cfg, self.transformer.attn_layers
-        b, n, _ = state.shape
         h, dh = cfg.heads, cfg.dim_head
         fs = self.fused_state()
         if not ops.attn_core_supported(n, dh):
@@ -483,7 +538,6 @@ class WorldModelActorCritic(nn.Module):
                           wg=at.to_v_gate.weight.data if cfg.gate_values else None,
                           wm=at.to_value_residual_mix[0].weight.data if (cfg.value_residual and cfg.learned_mix and l > 0) else None,
                           out=fs['attn_img'][l])
-        lens32 = mask.sum(dim=1, dtype=torch.int32)          # episodes are right-padded: mask == position < length
         ang4 = ang[:, ::2].contiguous()
         cos4, sin4 = ang4.cos(), ang4.sin()
         first_v = None
@@ -505,14 +559,15 @@ class WorldModelActorCritic(nn.Module):
             x = _FusedAttnPost.apply(x, out, attn, fs['attn_img'][l], lens32)
             norm, ff = dec.layers[2 * l + 1]
             x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)
-        embed = _FusedNorm.apply(x, dec.final_norm)
-        hd = fs['heads']
+        return _FusedNorm.apply(x, dec.final_norm)
+
+    def _fused_heads(self, embed, se32, ae_next, lat, n):
+        """the three head MLPs (critic, actor, world model + done) as tcgen05 kernels (csrc/learn_mlp.cu)"""
+        cfg = self.cfg
+        hd = self.fused_state()['heads']
         for hs in hd.values():
             hs.refresh()
-        with torch.autocast('cuda', enabled=False):
-            se32 = _SkinnyLinear.apply(state, self.to_state_embed.weight, self.to_state_embed.bias)
-            lat = self.latent_to_embed(latent_gene.float()) if self.evolutionary else None
-        sp_done = _FusedHead.apply(hd['pred'], n, embed, self.action_embeds(next_actions), None)
+        sp_done = _FusedHead.apply(hd['pred'], n, embed, ae_next, None)
         emb_ac = _FracGrad.apply(embed, self.frac)
         n_pred = 2 * (cfg.state_dim + 1)
         return (_FusedHead.apply(hd['actor'], n, emb_ac, se32, lat), _FusedHead.apply(hd['critic'], n, emb_ac, se32, lat),

@@ -371,6 +371,57 @@ def ln_bwd(x, dy, gamma, d_gamma):
     return dx
 
 
+def learn_prep_fwd(src, idx, rs_mean, rs_var, w_in, w_se, b_se, w_act, b_act, reward_embed, reward_flag, *, continuous=False):
+    """minibatch prologue (csrc/learn_prep.cu): gather the episodes `idx` (b,) int64 out of the episode-major trajectory tensors
+    `src` (dict: states (E,T,S), actions (E,T) i32 | (E,T,A) f32, rewards, old_log_probs, returns, old_values (E,T) f32, dones (E,T)
+    bool/u8, lens (E,) i32[, gene_ids (E,) i32]), normalise (state || prev reward), and form the model's input rows.
+    Returns dict(x0, se, ae_next (b,T,48) f32, packed (b,T,S+1), actions, old_log_probs, returns, old_values, dones, lens[, gene_ids],
+    rs_sum (S+2,): masked column sums of packed and the masked row count)."""
+    lib = L.load()
+    f32, dev = torch.float32, idx.device
+    E, T, S = src['states'].shape
+    b = idx.numel()
+    A = w_act.shape[1] if continuous else w_act.shape[0]
+    z = lambda *shape, dt=f32: torch.empty(*shape, dtype=dt, device=dev)
+    out = dict(x0=z(b, T, 48), se=z(b, T, 48), ae_next=z(b, T, 48), packed=z(b, T, S + 1),
+               actions=z(b, T, A) if continuous else z(b, T, dt=torch.int32), old_log_probs=z(b, T, A) if continuous else z(b, T),
+               returns=z(b, T), old_values=z(b, T), dones=z(b, T, dt=torch.uint8), lens=z(b, dt=torch.int32),
+               rs_sum=torch.zeros(S + 2, dtype=f32, device=dev))
+    has_genes = src.get('gene_ids') is not None
+    if has_genes:
+        out['gene_ids'] = z(b, dt=torch.int32)
+    dn = src['dones'].view(torch.uint8) if src['dones'].dtype == torch.bool else src['dones']
+    io = L.PrepIO(states=_ptr(src['states'], f32, 'states'),
+                  actions=_ptr(src['actions'], f32 if continuous else torch.int32, 'actions'), rewards=_ptr(src['rewards'], f32, 'rewards'),
+                  old_log_probs=_ptr(src['old_log_probs'], f32, 'old_log_probs'), returns=_ptr(src['returns'], f32, 'returns'),
+                  old_values=_ptr(src['old_values'], f32, 'old_values'), dones=_ptr(dn, torch.uint8, 'dones'), lens=_ptr(src['lens'], torch.int32, 'lens'),
+                  gene_ids=_ptr(src['gene_ids'], torch.int32, 'gene_ids') if has_genes else None, idx=_ptr(idx, torch.int64, 'idx'),
+                  rs_mean=_ptr(rs_mean, f32, 'rs_mean'), rs_var=_ptr(rs_var, f32, 'rs_var'), w_in=_ptr(w_in, f32, 'w_in'), w_se=_ptr(w_se, f32, 'w_se'),
+                  b_se=_ptr(b_se, f32, 'b_se'), w_act=_ptr(w_act, f32, 'w_act'), b_act=_ptr(b_act, f32, 'b_act') if continuous else None,
+                  reward_embed=_ptr(reward_embed, f32, 'reward_embed'), reward_flag=_ptr(reward_flag, f32, 'reward_flag'),
+                  x0=_ptr(out['x0']), se=_ptr(out['se']), ae_next=_ptr(out['ae_next']), packed=_ptr(out['packed']), mb_actions=_ptr(out['actions']),
+                  mb_old_log_probs=_ptr(out['old_log_probs']), mb_returns=_ptr(out['returns']), mb_old_values=_ptr(out['old_values']),
+                  mb_dones=_ptr(out['dones']), mb_lens=_ptr(out['lens']), mb_gene_ids=_ptr(out['gene_ids']) if has_genes else None,
+                  rs_sum=_ptr(out['rs_sum']))
+    L.check(lib.xtrl_learn_prep_fwd(C.byref(io), b, T, S, A, int(continuous), _stream()), 'xtrl_learn_prep_fwd')
+    return out
+
+
+def learn_prep_bwd(dx0, d_se, d_ae_next, packed, mb_actions, reward_flag, d_w_in, d_w_se, d_b_se, d_w_act, d_b_act, d_reward_embed, *,
+                   continuous=False):
+    """every skinny parameter gradient of the prologue in one pass; accumulated (+=) into the d_* tensors."""
+    lib = L.load()
+    f32 = torch.float32
+    b, T, _ = dx0.shape
+    S = packed.shape[-1] - 1
+    A = d_w_act.shape[1] if continuous else d_w_act.shape[0]
+    io = L.PrepBwdIO(dx0=_ptr(dx0, f32, 'dx0'), d_se=_ptr(d_se, f32, 'd_se'), d_ae_next=_ptr(d_ae_next, f32, 'd_ae_next'), packed=_ptr(packed, f32, 'packed'),
+                     mb_actions=_ptr(mb_actions, f32 if continuous else torch.int32, 'actions'), reward_flag=_ptr(reward_flag, f32, 'reward_flag'), T=T,
+                     d_w_in=_ptr(d_w_in, f32), d_w_se=_ptr(d_w_se, f32), d_b_se=_ptr(d_b_se, f32), d_w_act=_ptr(d_w_act, f32),
+                     d_b_act=_ptr(d_b_act, f32) if continuous else None, d_reward_embed=_ptr(d_reward_embed, f32))
+    L.check(lib.xtrl_learn_prep_bwd(C.byref(io), b, T, S, A, int(continuous), _stream()), 'xtrl_learn_prep_bwd')
+
+
 def attn_core_supported(n, dim_head) -> bool:
     return bool(L.load().xtrl_attn_core_supported(n, dim_head))
 
