@@ -193,7 +193,13 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
 constexpr int kBwdH = TOK * HW * 2, kBwdDP = TOK * F * 2, kBwdX = TOK * XW * 2;
 constexpr int kBwdSmem = kBwdH + kBwdDP + 2 * kBwdX + kW1 + kW2 + (F + D) * 4 + 64;
 
-__global__ void __launch_bounds__(NT, 1) ff_bwd_kernel(const Args a) {
+// 512 threads: thread (row, cq) owns a QUARTER of the row's columns in every epilogue (48 of the 192 hidden units; 16 of the
+// 48 features for cq < 3).  The epilogues -- GELU, its derivative and the dropout hash on 128 x 192 values per tile -- are the
+// bulk of this kernel's time and are latency-bound, so sixteen warps per SM (one CTA per SM: shared memory) nearly halve it
+// against eight.  Rows are re-read from L2 where a second use is far from the first instead of living in registers.
+constexpr int NT4 = 512;
+
+__global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sH = smem, *sDP = sH + kBwdH, *sXn = sDP + kBwdDP, *sDY = sXn + kBwdX;
     unsigned char *sW1 = sDY + kBwdX, *sW2 = sW1 + kW1;
@@ -201,14 +207,14 @@ __global__ void __launch_bounds__(NT, 1) ff_bwd_kernel(const Args a) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+    const int q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     constexpr uint32_t cPre = 0, cDxn = 192, cA = 256, cB = 320, cC = 384, cD = 448;
 
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tslot, 512);
-    for (int i = tid; i < F; i += NT) sB1[i] = a.b1[i];
+    for (int i = tid; i < F; i += NT4) sB1[i] = a.b1[i];
     if (tid < D) sG[tid] = a.gamma[tid];
-    if (half == 0) {                       // constant columns: [1, 0 x 7] then zeros
+    if (cq == 0) {                         // constant columns: [1, 0 x 7] then zeros
         const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         put8(sXn, row, 6, one); put8(sXn, row, 7, zero);
         put8(sDY, row, 6, one); put8(sDY, row, 7, zero);
@@ -222,34 +228,40 @@ __global__ void __launch_bounds__(NT, 1) ff_bwd_kernel(const Args a) {
     const uint32_t key = fold_key(a.rng_step, a.rng_key);
     uint32_t ph = 0;
     bool first = true;
-    float dg_acc[24];
+    float dg_acc[16];
 #pragma unroll
-    for (int i = 0; i < 24; ++i) dg_acc[i] = 0.f;
+    for (int i = 0; i < 16; ++i) dg_acc[i] = 0.f;
     const int ntiles = (a.N + TOK - 1) / TOK;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
-        float xr[D], dyr[24];
-        load_row(a.x + (size_t)t * D, ok, xr);
+        float mean, rstd, dyr[16];
+        {
+            float xr[D];
+            load_row(a.x + (size_t)t * D, ok, xr);
+            ln_stats(xr, mean, rstd);
+            if (cq < 3) {                                                        // my 16 features of the Xn and dY images
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(a.dy + (size_t)t * D + half * 24) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            dyr[4 * i] = v.x; dyr[4 * i + 1] = v.y; dyr[4 * i + 2] = v.z; dyr[4 * i + 3] = v.w;
-        }
-        float mean, rstd;
-        ln_stats(xr, mean, rstd);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(a.dy + (size_t)t * D + cq * 16) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dyr[4 * i] = v.x; dyr[4 * i + 1] = v.y; dyr[4 * i + 2] = v.z; dyr[4 * i + 3] = v.w;
+                }
 #pragma unroll
-        for (int i = 0; i < D; ++i) xr[i] = (xr[i] - mean) * rstd;               // xr is xhat from here on
-        float own[24];
+                for (int c = 0; c < 2; ++c) {
+                    float v[8], w[8];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) own[i] = half ? xr[24 + i] : xr[i];         // this thread's half of xhat
+                    for (int j = 0; j < 8; ++j) {
+                        const int f = cq * 16 + c * 8 + j;
+                        float xv = xr[0];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float v[8], w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] = own[c * 8 + j] * sG[half * 24 + c * 8 + j]; w[j] = dyr[c * 8 + j]; }
-            put8(sXn, row, half * 3 + c, v);
-            put8(sDY, row, half * 3 + c, w);
+                        for (int m = 0; m < 3; ++m) if (cq == m) xv = xr[m * 16 + c * 8 + j];      // static register indices
+                        v[j] = (xv - mean) * rstd * sG[f];
+                        w[j] = dyr[c * 8 + j];
+                    }
+                    put8(sXn, row, cq * 2 + c, v);
+                    put8(sDY, row, cq * 2 + c, w);
+                }
+            }
         }
         fence_proxy_async();
         __syncthreads();
@@ -265,8 +277,8 @@ __global__ void __launch_bounds__(NT, 1) ff_bwd_kernel(const Args a) {
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 6; ++c) {                                            // H and gelu'.mask
-            const int col0 = half * 96 + c * 16;
+        for (int c = 0; c < 3; ++c) {                                            // H and gelu'.mask, my 48 hidden units
+            const int col0 = cq * 48 + c * 16;
             float v[16], d[16];
             tmem_ld16(tlane + cPre + col0, v);
 #pragma unroll
@@ -311,8 +323,8 @@ __global__ void __launch_bounds__(NT, 1) ff_bwd_kernel(const Args a) {
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 6; ++c) {                                            // dPRE = dH . gelu'.mask
-            const int col0 = half * 96 + c * 16;
+        for (int c = 0; c < 3; ++c) {                                            // dPRE = dH . gelu'.mask
+            const int col0 = cq * 48 + c * 16;
             float v[16], lo[8], hi[8];
             tmem_ld16(tlane + cPre + col0, v);
             unsigned char *p = sDP + (col0 / 8) * kCore + (row >> 3) * 128 + (row & 7) * 16;
@@ -343,45 +355,50 @@ __global__ void __launch_bounds__(NT, 1) ff_bwd_kernel(const Args a) {
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
-        {                                                                        // LayerNorm backward + residual
-            float dxn[D];
+        if (cq < 3) {                                                            // LayerNorm backward + residual, my 16 features
+            float c1 = 0.f, c2 = 0.f, dxo[16], xho[16];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
+            for (int c = 0; c < 6; ++c) {                                        // the row sums need all 48 features: stream them
                 float v[8];
                 tmem_ld8(tlane + cDxn + c * 8, v);
+                const float4 x0 = ok ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)t * D + c * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 x1 = ok ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)t * D + c * 8) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dxn[c * 8 + j] = v[j];
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (xs[j] - mean) * rstd, dh = v[j] * sG[c * 8 + j];
+                    c1 += dh; c2 = fmaf(dh, xh, c2);
+                    if ((c >> 1) == cq) { dxo[(c & 1) * 8 + j] = v[j]; xho[(c & 1) * 8 + j] = xh; }
+                }
             }
-            float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < D; ++i) { const float dh = dxn[i] * sG[i]; c1 += dh; c2 = fmaf(dh, xr[i], c2); }
             c1 *= (1.f / D); c2 *= (1.f / D);
-            float o[24];
+            float o[16];
 #pragma unroll
-            for (int i = 0; i < 24; ++i) {
-                const float dxi = half ? dxn[24 + i] : dxn[i];
-                dg_acc[i] = fmaf(dxi, own[i], dg_acc[i]);
-                o[i] = dyr[i] + rstd * (dxi * sG[half * 24 + i] - c1 - own[i] * c2);
+            for (int i = 0; i < 16; ++i) {
+                dg_acc[i] = fmaf(dxo[i], xho[i], dg_acc[i]);
+                o[i] = dyr[i] + rstd * (dxo[i] * sG[cq * 16 + i] - c1 - xho[i] * c2);
             }
             if (ok) {
-                float4 *dst = reinterpret_cast<float4 *>(a.dx + (size_t)t * D + half * 24);
+                float4 *dst = reinterpret_cast<float4 *>(a.dx + (size_t)t * D + cq * 16);
 #pragma unroll
-                for (int i = 0; i < 6; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             }
         }
         tc_fence_before();
     }
     // ---- flush the per-CTA weight-gradient accumulators ----
+    if (cq < 3) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
-        const float s = warp_sum(dg_acc[i]);
-        if (lane == 0 && s != 0.f) atomicAdd(a.dgamma + half * 24 + i, s);
+        for (int i = 0; i < 16; ++i) {
+            const float s = warp_sum(dg_acc[i]);
+            if (lane == 0 && s != 0.f) atomicAdd(a.dgamma + cq * 16 + i, s);
+        }
     }
     if (!first) {                                                                // this CTA saw at least one tile
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {                                            // half 0: columns 0..31, half 1: 32..63
-            const int col0 = half * 32 + c * 8;
+        for (int c = 0; c < 2; ++c) {                                            // quarter cq: columns 16 cq .. 16 cq + 15 (48 = the bias column)
+            const int col0 = cq * 16 + c * 8;
             if (col0 > D) break;
             float va[8], vb[8], vc[8], vd[8];
             tmem_ld8(tlane + cA + col0, va);
@@ -482,7 +499,7 @@ extern "C" int xtrl_ff_bwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t
     if (!attr) { XTRL_CUDA(cudaFuncSetAttribute(ff_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
     const int ntiles = (int)((N + TOK - 1) / TOK);
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    ff_bwd_kernel<<<grid, NT, kBwdSmem, (cudaStream_t)stream>>>(a);
+    ff_bwd_kernel<<<grid, NT4, kBwdSmem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("ff_bwd_kernel");
     return XTRL_OK;
 }

@@ -29,43 +29,46 @@ struct Args {
     int b, T, S, A, cont;
 };
 
+// SM / AM: compile-time bounds of state_dim / num_actions (the loops over them are fully unrolled and predicated)
+template <int SM, int AM>
 __global__ void __launch_bounds__(NT) prep_fwd_kernel(const Args a) {
-    __shared__ float s_packed[TOK][SMAX + 1];
-    __shared__ float s_act[TOK][AMAX];                        // continuous: prev action / action vectors
-    __shared__ float s_nact[TOK][AMAX];
+    __shared__ float s_packed[TOK][SM + 1];
+    __shared__ float s_act[TOK][AM];                          // continuous: prev action / action vectors
+    __shared__ float s_nact[TOK][AM];
     __shared__ int s_pa[TOK], s_na[TOK];                      // discrete: prev action (-1 none), action
-    __shared__ float s_sum[SMAX + 2];
+    __shared__ float s_valid[TOK];                            // 1 where the row lies inside its episode's length
+    __shared__ float s_sum[SM + 2];
     const xtrl_prep_io &io = a.io;
     const int tid = threadIdx.x, j = tid % D, tl = tid / D;
     const int S = a.S, S1 = S + 1, A = a.A, T = a.T;
-    const int64_t N = (int64_t)a.b * T;
+    const int N = a.b * T;                                    // < 2^31 (checked by the launcher): 32-bit row arithmetic throughout
     // this thread's rows of the skinny weights
-    float w_in[SMAX], w_se[SMAX], w_ac[AMAX];
+    float w_in[SM], w_se[SM], w_ac[AM];
 #pragma unroll
-    for (int s = 0; s < SMAX; ++s) { w_in[s] = s < S ? __ldg(io.w_in + j * S + s) : 0.f; w_se[s] = s < S ? __ldg(io.w_se + j * S + s) : 0.f; }
+    for (int s = 0; s < SM; ++s) { w_in[s] = s < S ? __ldg(io.w_in + j * S + s) : 0.f; w_se[s] = s < S ? __ldg(io.w_se + j * S + s) : 0.f; }
 #pragma unroll
-    for (int i = 0; i < AMAX; ++i) w_ac[i] = (a.cont && i < A) ? __ldg(io.w_act + j * A + i) : 0.f;
+    for (int i = 0; i < AM; ++i) w_ac[i] = (a.cont && i < A) ? __ldg(io.w_act + j * A + i) : 0.f;
     const float b_se = __ldg(io.b_se + j), b_ac = a.cont ? __ldg(io.b_act + j) : 0.f;
     const float re = __ldg(io.reward_embed + j) * __ldg(io.reward_flag);
-    if (tid < SMAX + 2) s_sum[tid] = 0.f;
+    if (tid < SM + 2) s_sum[tid] = 0.f;
     float my_sum = 0.f;                                       // thread tid < S1: column tid of packed; tid == S1: the row count
 
-    const int64_t ntiles = (N + TOK - 1) / TOK;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t r0 = tile * TOK;
+    const int ntiles = (N + TOK - 1) / TOK;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * TOK;
         __syncthreads();
         // phase 1: gather + normalise the tile's rows (one (token, column) item per thread and pass)
         for (int item = tid; item < TOK * (S1 + 1); item += NT) {
-            const int tk = item / (S1 + 1), c = item - tk * (S1 + 1);
-            const int64_t r = r0 + tk;
-            if (r >= N) continue;
-            const int bi = (int)(r / T), t = (int)(r - (int64_t)bi * T);
+            const int tk = (unsigned)item / (unsigned)(S1 + 1), c = item - tk * (S1 + 1);
+            const int r = r0 + tk;
+            if (r >= N) { if (c == S1) s_valid[tk] = 0.f; continue; }
+            const int bi = (unsigned)r / (unsigned)T, t = r - bi * T;
             const int64_t e = __ldg(io.idx + bi), src = e * T + t;
             if (c < S1) {
                 const float raw = c < S ? __ldg(io.states + src * S + c) : (t > 0 ? __ldg(io.rewards + src - 1) : 0.f);
                 const float v = (raw - __ldg(io.rs_mean + c)) / fmaxf(sqrtf(__ldg(io.rs_var + c)), 1e-5f);
                 s_packed[tk][c] = v;
-                io.packed[r * S1 + c] = v;
+                io.packed[(int64_t)r * S1 + c] = v;
             } else {                                          // the row's scalar fields
                 io.mb_returns[r] = __ldg(io.returns + src);
                 io.mb_old_values[r] = __ldg(io.old_values + src);
@@ -81,22 +84,20 @@ __global__ void __launch_bounds__(NT) prep_fwd_kernel(const Args a) {
                     for (int i = 0; i < A; ++i) {
                         const float na = __ldg(acts + src * A + i);
                         s_nact[tk][i] = na; s_act[tk][i] = t > 0 ? __ldg(acts + (src - 1) * A + i) : 0.f;
-                        static_cast<float *>(io.mb_actions)[r * A + i] = na;
-                        io.mb_old_log_probs[r * A + i] = __ldg(io.old_log_probs + src * A + i);
+                        static_cast<float *>(io.mb_actions)[(int64_t)r * A + i] = na;
+                        io.mb_old_log_probs[(int64_t)r * A + i] = __ldg(io.old_log_probs + src * A + i);
                     }
                 }
-                if (t == 0) { io.mb_lens[bi] = __ldg(io.lens + e); if (io.gene_ids) io.mb_gene_ids[bi] = __ldg(io.gene_ids + e); }
+                const int len = __ldg(io.lens + e);
+                s_valid[tk] = t < len ? 1.f : 0.f;
+                if (t == 0) { io.mb_lens[bi] = len; if (io.gene_ids) io.mb_gene_ids[bi] = __ldg(io.gene_ids + e); }
             }
         }
         __syncthreads();
         // masked column sums of packed for the RSNorm batch mean (:1005, :601): thread c sums column c over the tile
         if (tid <= S1) {
-            for (int tk = 0; tk < TOK; ++tk) {
-                const int64_t r = r0 + tk;
-                if (r >= N) break;
-                const int bi = (int)(r / T), t = (int)(r - (int64_t)bi * T);
-                if (t < __ldg(io.lens + __ldg(io.idx + bi))) my_sum += tid < S1 ? s_packed[tk][tid] : 1.f;
-            }
+            const int lim = N - r0 < TOK ? N - r0 : TOK;
+            for (int tk = 0; tk < lim; ++tk) my_sum += s_valid[tk] * (tid < S1 ? s_packed[tk][tid] : 1.f);
         }
         // phase 2: the three 48-wide rows of every token
         for (int tk = tl; tk < TOK; tk += TL) {
@@ -104,11 +105,11 @@ __global__ void __launch_bounds__(NT) prep_fwd_kernel(const Args a) {
             if (r >= N) break;
             float x = 0.f, se = b_se, ae_p = 0.f, ae_n = 0.f;
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s) if (s < S) { const float v = s_packed[tk][s]; x = fmaf(w_in[s], v, x); se = fmaf(w_se[s], v, se); }
+            for (int s = 0; s < SM; ++s) if (s < S) { const float v = s_packed[tk][s]; x = fmaf(w_in[s], v, x); se = fmaf(w_se[s], v, se); }
             if (a.cont) {
                 ae_p = b_ac; ae_n = b_ac;
 #pragma unroll
-                for (int i = 0; i < AMAX; ++i) if (i < A) { ae_p = fmaf(w_ac[i], s_act[tk][i], ae_p); ae_n = fmaf(w_ac[i], s_nact[tk][i], ae_n); }
+                for (int i = 0; i < AM; ++i) if (i < A) { ae_p = fmaf(w_ac[i], s_act[tk][i], ae_p); ae_n = fmaf(w_ac[i], s_nact[tk][i], ae_n); }
             } else {
                 const int pa = s_pa[tk], na = s_na[tk];
                 ae_p = pa >= 0 ? __ldg(io.w_act + pa * D + j) : 0.f;           // SafeEmbedding (:181-195): id -1 -> zeros
@@ -128,61 +129,65 @@ struct BwdArgs {
     int S, A, cont;
 };
 
+template <int SM, int AM>
 __global__ void __launch_bounds__(NT) prep_bwd_kernel(const BwdArgs a) {
     const xtrl_prep_bwd_io &io = a.io;
     const int tid = threadIdx.x, j = tid % D, tl = tid / D;
     const int S = a.S, S1 = S + 1, A = a.A;
     const float flag = __ldg(io.reward_flag);
-    float g_in[SMAX + 1], g_se[SMAX + 1], g_ac[AMAX], g_bac = 0.f;      // g_in[S]: reward_embed; g_se[S]: to_state_embed bias
+    float g_in[SM + 1], g_se[SM + 1], g_ac[AM], g_bac = 0.f;      // g_in[S]: reward_embed; g_se[S]: to_state_embed bias
 #pragma unroll
-    for (int s = 0; s <= SMAX; ++s) { g_in[s] = 0.f; g_se[s] = 0.f; }
+    for (int s = 0; s <= SM; ++s) { g_in[s] = 0.f; g_se[s] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < AMAX; ++i) g_ac[i] = 0.f;
-    int64_t per = (a.N + gridDim.x - 1) / gridDim.x;
+    for (int i = 0; i < AM; ++i) g_ac[i] = 0.f;
+    const int Nr = (int)a.N;                                  // < 2^31 (checked by the launcher)
+    int per = (Nr + gridDim.x - 1) / gridDim.x;
     per = (per + TL - 1) / TL * TL;
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < a.N ? lo + per : a.N;
-    for (int64_t r = lo + tl; r < hi; r += TL) {
+    const int lo = blockIdx.x * per, hi = lo + per < Nr ? lo + per : Nr;
+    int t = lo + tl < Nr ? (int)((unsigned)(lo + tl) % (unsigned)io.T) : 0;      // timestep of row r, advanced without divisions
+    for (int64_t r = lo + tl; r < hi; r += TL, t += TL) {
+        while (t >= io.T) t -= io.T;
         const float dx = __ldg(io.dx0 + r * D + j), dse = io.d_se ? __ldg(io.d_se + r * D + j) : 0.f, dae = io.d_ae_next ? __ldg(io.d_ae_next + r * D + j) : 0.f;
         const float *pk = io.packed + r * S1;
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) if (s < S) { const float v = __ldg(pk + s); g_in[s] = fmaf(dx, v, g_in[s]); g_se[s] = fmaf(dse, v, g_se[s]); }
-        g_in[SMAX] = fmaf(dx, __ldg(pk + S) * flag, g_in[SMAX]);
-        g_se[SMAX] += dse;
+        for (int s = 0; s < SM; ++s) if (s < S) { const float v = __ldg(pk + s); g_in[s] = fmaf(dx, v, g_in[s]); g_se[s] = fmaf(dse, v, g_se[s]); }
+        g_in[SM] = fmaf(dx, __ldg(pk + S) * flag, g_in[SM]);
+        g_se[SM] += dse;
         if (a.cont) {
             const float *an = static_cast<const float *>(io.mb_actions) + r * A;
-            const bool first = (r % io.T) == 0;
+            const bool first = t == 0;
 #pragma unroll
-            for (int i = 0; i < AMAX; ++i) if (i < A) g_ac[i] += dae * __ldg(an + i) + (first ? 0.f : dx * __ldg(an + i - A));
+            for (int i = 0; i < AM; ++i) if (i < A) g_ac[i] += dae * __ldg(an + i) + (first ? 0.f : dx * __ldg(an + i - A));
             g_bac += dae + dx;
         } else {
             const int32_t *acts = static_cast<const int32_t *>(io.mb_actions);
-            const int na = __ldg(acts + r), pa = (r % io.T) == 0 ? -1 : __ldg(acts + r - 1);
+            const int na = __ldg(acts + r), pa = t == 0 ? -1 : __ldg(acts + r - 1);
 #pragma unroll
-            for (int i = 0; i < AMAX; ++i) if (i < A) g_ac[i] += (na == i ? dae : 0.f) + (pa == i ? dx : 0.f);
+            for (int i = 0; i < AM; ++i) if (i < A) g_ac[i] += (na == i ? dae : 0.f) + (pa == i ? dx : 0.f);
         }
     }
     // the TL token lanes of a feature meet in shared memory, then one atomicAdd per value and CTA
-    __shared__ float red[TL][D][2 * (SMAX + 1) + AMAX + 1];
+    __shared__ float red[TL][D][2 * (SM + 1) + AM + 1];
     float *mine = red[tl][j];
 #pragma unroll
-    for (int s = 0; s <= SMAX; ++s) { mine[s] = g_in[s]; mine[SMAX + 1 + s] = g_se[s]; }
+    for (int s = 0; s <= SM; ++s) { mine[s] = g_in[s]; mine[SM + 1 + s] = g_se[s]; }
 #pragma unroll
-    for (int i = 0; i < AMAX; ++i) mine[2 * (SMAX + 1) + i] = g_ac[i];
-    mine[2 * (SMAX + 1) + AMAX] = g_bac;
+    for (int i = 0; i < AM; ++i) mine[2 * (SM + 1) + i] = g_ac[i];
+    mine[2 * (SM + 1) + AM] = g_bac;
     __syncthreads();
     if (tl == 0) {
         auto tot = [&](int k) { float s = 0.f; for (int l = 0; l < TL; ++l) s += red[l][j][k]; return s; };
         for (int s = 0; s < S; ++s) {
             atomicAdd(io.d_w_in + j * S + s, tot(s));
-            if (io.d_w_se) atomicAdd(io.d_w_se + j * S + s, tot(SMAX + 1 + s));
+            if (io.d_w_se) atomicAdd(io.d_w_se + j * S + s, tot(SM + 1 + s));
         }
-        atomicAdd(io.d_reward_embed + j, tot(SMAX));
-        if (io.d_b_se) atomicAdd(io.d_b_se + j, tot(2 * SMAX + 1));
+        atomicAdd(io.d_reward_embed + j, tot(SM));
+        if (io.d_b_se) atomicAdd(io.d_b_se + j, tot(2 * SM + 1));
         for (int i = 0; i < A; ++i) {
-            const float v = tot(2 * (SMAX + 1) + i);
+            const float v = tot(2 * (SM + 1) + i);
             if (a.cont) atomicAdd(io.d_w_act + j * A + i, v); else atomicAdd(io.d_w_act + i * D + j, v);
         }
-        if (a.cont) atomicAdd(io.d_b_act + j, tot(2 * (SMAX + 1) + AMAX));
+        if (a.cont) atomicAdd(io.d_b_act + j, tot(2 * (SM + 1) + AM));
     }
 }
 
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(NT) prep_bwd_kernel(const BwdArgs a) {
 extern "C" int xtrl_learn_prep_fwd(const xtrl_prep_io *io, int32_t b, int32_t T, int32_t state_dim, int32_t num_actions,
                                    int32_t continuous, void *stream) {
     using namespace xtrl; using namespace xtrl::prep;
-    XTRL_REQUIRE(io && b >= 0 && T >= 1, XTRL_E_BADARG, "xtrl_learn_prep_fwd: bad arguments");
+    XTRL_REQUIRE(io && b >= 0 && T >= 1 && (int64_t)b * T < (1LL << 31), XTRL_E_BADARG, "xtrl_learn_prep_fwd: bad arguments");
     XTRL_REQUIRE(state_dim >= 1 && state_dim <= SMAX && num_actions >= 1 && num_actions <= AMAX, XTRL_E_UNSUPPORTED,
                  "xtrl_learn_prep_fwd: built for state_dim <= %d, num_actions <= %d (got %d, %d)", SMAX, AMAX, state_dim, num_actions);
     if (b == 0) return XTRL_OK;
@@ -203,8 +208,10 @@ extern "C" int xtrl_learn_prep_fwd(const xtrl_prep_io *io, int32_t b, int32_t T,
                  XTRL_E_BADARG, "xtrl_learn_prep_fwd: null pointer");
     Args a;
     a.io = *io; a.b = b; a.T = T; a.S = state_dim; a.A = num_actions; a.cont = continuous != 0;
-    const int64_t ntiles = ((int64_t)b * T + TOK - 1) / TOK, cap = 8LL * num_sms();
-    prep_fwd_kernel<<<(int)(ntiles < cap ? ntiles : cap), NT, 0, (cudaStream_t)stream>>>(a);
+    const int64_t ntiles = ((int64_t)b * T + TOK - 1) / TOK, cap = 6LL * num_sms();
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    if (state_dim <= 8 && num_actions <= 4) prep_fwd_kernel<8, 4><<<grid, NT, 0, (cudaStream_t)stream>>>(a);
+    else prep_fwd_kernel<SMAX, AMAX><<<grid, NT, 0, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("prep_fwd_kernel");
     return XTRL_OK;
 }
@@ -212,7 +219,7 @@ extern "C" int xtrl_learn_prep_fwd(const xtrl_prep_io *io, int32_t b, int32_t T,
 extern "C" int xtrl_learn_prep_bwd(const xtrl_prep_bwd_io *io, int32_t b, int32_t T, int32_t state_dim, int32_t num_actions,
                                    int32_t continuous, void *stream) {
     using namespace xtrl; using namespace xtrl::prep;
-    XTRL_REQUIRE(io && b >= 0 && T >= 1, XTRL_E_BADARG, "xtrl_learn_prep_bwd: bad arguments");
+    XTRL_REQUIRE(io && b >= 0 && T >= 1 && (int64_t)b * T < (1LL << 31), XTRL_E_BADARG, "xtrl_learn_prep_bwd: bad arguments");
     XTRL_REQUIRE(state_dim >= 1 && state_dim <= SMAX && num_actions >= 1 && num_actions <= AMAX, XTRL_E_UNSUPPORTED,
                  "xtrl_learn_prep_bwd: built for state_dim <= %d, num_actions <= %d (got %d, %d)", SMAX, AMAX, state_dim, num_actions);
     if (b == 0) return XTRL_OK;
@@ -220,8 +227,10 @@ extern "C" int xtrl_learn_prep_bwd(const xtrl_prep_bwd_io *io, int32_t b, int32_
                  (!continuous || io->d_b_act) && io->T == T, XTRL_E_BADARG, "xtrl_learn_prep_bwd: null pointer / inconsistent T");
     BwdArgs a;
     a.io = *io; a.N = (int64_t)b * T; a.S = state_dim; a.A = num_actions; a.cont = continuous != 0;
-    const int64_t want = (a.N + 255) / 256, cap = 2LL * num_sms();
-    prep_bwd_kernel<<<(int)(want < cap ? want : cap), NT, 0, (cudaStream_t)stream>>>(a);
+    const int64_t want = (a.N + 255) / 256, cap = 4LL * num_sms();
+    const int grid = (int)(want < cap ? want : cap);
+    if (state_dim <= 8 && num_actions <= 4) prep_bwd_kernel<8, 4><<<grid, NT, 0, (cudaStream_t)stream>>>(a);
+    else prep_bwd_kernel<SMAX, AMAX><<<grid, NT, 0, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("prep_bwd_kernel");
     return XTRL_OK;
 }
