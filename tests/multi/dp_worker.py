@@ -23,6 +23,7 @@ learner = L.Learner(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_time
                     # bf16: the learn pass runs the fused tcgen05 sub-layers (weight gradients by atomicAdd -- replicas
                     # must still agree bit for bit, because every rank applies the same all-reduced gradient)
                     accelerate_kwargs=dict(mixed_precision='bf16' if os.environ.get('XTRL_DP_MIXED') == 'bf16' else 'no'))
+learner.agent.capture_allreduce = os.environ.get('XTRL_DP_CAPTURE') == '1'
 acc = learner.accelerator
 rank, world = acc.process_index, acc.num_processes
 assert world >= 2 and dist.get_backend() == 'nccl'

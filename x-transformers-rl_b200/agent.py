@@ -213,7 +213,11 @@ class Agent(nn.Module):
         # (csrc/learn_*.cu); a shape those kernels are not built for is an ERROR there (model.fused_state), never a silent
         # switch of back end.  mixed_precision='no' is the explicit fp32 parity class (the torch expression).
         self.fused_learn = self.accelerator.mixed_precision == 'bf16'
-        self.use_cuda_graph_learn = True     # fwd + losses + bwd (+ the gradient all-reduce) of a minibatch as one graph replay
+        self.use_cuda_graph_learn = True     # fwd + losses + bwd of a minibatch as one graph replay
+        # the flat-gradient all-reduce as the last node of that graph (True) or as one eager NCCL call right after the replay
+        # (False, the default: the captured collective hung on the 2-GPU box of this image -- torch 2.11 / NCCL 2.28 -- while
+        # the eager call is what round 1 measured 7.9x on 8 GPUs with)
+        self.capture_allreduce = False
         self._learn_graphs = {}
         self._learn_src = {}
         # replicas start from rank 0's values, as DDP's wrap does in the reference (:885), whatever each rank's RNG drew
@@ -317,8 +321,10 @@ class Agent(nn.Module):
                     scalars = self._fwd_bwd_prepared(src, idx.long(), torch.full((), flag, device=dev))
                 else:
                     scalars = self._fwd_bwd({k: data[k][idx] for k in fields}, flag)
-                # self._comm now holds the SUM over ranks of [gradients | RSNorm batch mean] (the all-reduce is the last
-                # node of the replayed graph); the mean's 1/world is folded into the optimiser kernel and the 9-float tail
+                if not self.capture_allreduce:
+                    all_reduce_sum_(self._comm)          # ONE collective: gradients (+ RSNorm batch mean in the tail)
+                # self._comm now holds the SUM over ranks of [gradients | RSNorm batch mean]; the mean's 1/world is folded
+                # into the optimiser kernel (grad_scale) and the 9-float tail
                 inv_world = 1. / world_size()
                 if self.keep_last_grads:
                     self.last_grads = model.flat_grads * inv_world
@@ -369,7 +375,7 @@ class Agent(nn.Module):
         # RSNorm batch mean over the masked rows rides in the tail of the gradient buffer (:1005, :601)
         mf = mask[..., None].float()
         self._comm[n:] = (packed * mf).sum(dim=(0, 1)) / mf.sum().clamp(min=1.)
-        if collective:
+        if collective and self.capture_allreduce:
             all_reduce_sum_(self._comm)              # gradients (+ RSNorm batch mean in the tail), one collective
         return scalars
 
@@ -406,7 +412,7 @@ class Agent(nn.Module):
         loss.backward()
         rs = box['rs_sum']                                                                           # :1005, :601
         self._comm[n:] = rs[:S + 1] / rs[S + 1].clamp(min=1.)
-        if collective:
+        if collective and self.capture_allreduce:
             all_reduce_sum_(self._comm)
         return scalars
 
