@@ -37,8 +37,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION) out of it
-if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-    os.environ['NCCL_DEBUG'] = 'WARN'
+if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):       # both levels print "NCCL version ..." on stdout
+    del os.environ['NCCL_DEBUG']
 
 METRIC = 'env-steps/sec (rollout) and PPO learn-timesteps/sec'      # BASELINE.json's metric: `value` = the rollout half, `learn_value` = the learn half
 
