@@ -239,7 +239,7 @@ typedef struct xtrl_pool_desc {
 
 /* genes [I*g][G] updated IN PLACE; fitness [I*g]; noise_tourn [I][c][s]; noise_cross [I][c][G];
  * noise_mut [I][g - (elites?1:0)][G]; selected_ids [I][s] (int64, as the reference returns);
- * scratch: I*g*G floats.                                                                      */
+ * scratch: unused since ABI 8 (the step is in place through shared memory); may be NULL.          */
 int xtrl_evolve(float *genes, const float *fitness, const float *noise_tourn,
                 const float *noise_cross, const float *noise_mut, int64_t *selected_ids,
                 float *scratch, const xtrl_pool_desc *desc, void *stream);

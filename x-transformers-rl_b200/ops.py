@@ -143,12 +143,11 @@ def evolve_(genes, fitness, noise_tourn, noise_cross, noise_mut, *, num_islands,
     lib = L.load()
     G = genes.shape[-1]
     sel = torch.empty(num_islands, num_selected, device=genes.device, dtype=torch.int64)
-    scratch = torch.empty_like(genes)
     pd = L.PoolDesc(G, num_islands, num_genes_per_island, num_selected, tournament_size, num_elites,
                     int(migrate), int(num_migrate), mutation_std_dev, temperature)
     L.check(lib.xtrl_evolve(_ptr(genes, torch.float32, 'genes'), _ptr(fitness, torch.float32, 'fitness'),
                             _ptr(noise_tourn, torch.float32, 'noise_tourn'), _ptr(noise_cross, torch.float32, 'noise_cross'),
-                            _ptr(noise_mut, torch.float32, 'noise_mut'), _ptr(sel), _ptr(scratch), C.byref(pd),
+                            _ptr(noise_mut, torch.float32, 'noise_mut'), _ptr(sel), _ptr(None), C.byref(pd),
                             _stream()), 'xtrl_evolve')
     return sel
 
