@@ -408,6 +408,209 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
     if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
+// ---------------------------------------------------------------------------------------- forward, version 2
+// Steps of one [128 queries x 128 keys] tile: a thread turns 32 scores per step into probabilities (two chunks of 16 keys), so
+// the per-step barrier / fence / geometry cost is spread over twice the work, and P goes to the tensor core THROUGH TENSOR
+// MEMORY (tcgen05.st + the A-from-TMEM form of tcgen05.mma) instead of a shared-memory image: no 16-byte scatter, no
+// generic->async proxy fence, no 4 KB operand read per product.  One S tile lives in TMEM at a time; the next one is issued as
+// soon as every warp has READ the current one (barrier bR, half way through the step), so it is ready when the step ends;
+// two CTAs per SM cover what is left.  The exact-row-max case (norm bound too loose) is the same loop run twice per query
+// tile: a pass that only takes maxima, then the pass that forms P.
+constexpr int kFwd2Smem = 3 * kImg + 2 * 4 * 128 * 4 + R * 4 + 128;
+
+template <bool DIAG, bool DROP>
+__device__ __forceinline__ float fwd2_chunk(uint32_t taddr, int row, int keyb, float sl2, float off, uint32_t qrow, uint32_t g4, uint32_t ckey,
+                                            uint32_t add4, uint32_t (&w)[8]) {
+    uint32_t r[16];
+    tmem_ld16_issue(taddr, r);
+    tmem_ld_wait();
+    tmem_pin16(r);
+    const uint64_t sl22 = pk2(sl2, sl2), off2 = pk2(off, off);
+    uint64_t l2 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        float x0, x1;
+        upk2(fma2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sl22, off2), x0, x1);
+        float p0 = ex2(x0), p1 = ex2(x1);
+        if (DIAG) { p0 = keyb + j <= row ? p0 : 0.f; p1 = keyb + j + 1 <= row ? p1 : 0.f; }
+        l2 = add2(l2, pk2(p0, p1));
+        w[j >> 1] = pack2(p0, p1);
+    }
+    if (DROP) {
+        const uint32_t hseed = (qrow * (uint32_t)(R / 4) + g4) * kGolden + ckey;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t t = keep4(hseed, g, add4);
+            w[2 * g] &= prmt(t, 0x9988);
+            w[2 * g + 1] &= prmt(t, 0xbbaa);
+        }
+    }
+    float l, lh;
+    upk2(l2, l, lh);
+    return l + lh;
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(NTH, 2) attn_core_fwd2_kernel(const Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *sQ = smem, *sK = sQ + kImg, *sV = sK + kImg;
+    float *sRed = reinterpret_cast<float *>(sV + kImg);                     // [2][4][128]
+    float *sQn = sRed + 2 * 4 * 128;                                         // |q_row|^2
+    uint64_t *bS = reinterpret_cast<uint64_t *>(sQn + R), *bR = bS + 1, *bI = bR + 1, *bPV = bI + 1;
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bPV + 1);
+    int *sMax = reinterpret_cast<int *>(tslot + 1);                          // [0] max |k|^2, [1] max |q|^2 (float bits)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q4 = warp & 3, c4 = warp >> 2, row = q4 * 32 + lane;           // c4 == 4: the MMA warp
+    const int bh = blockIdx.x, n = a.n, nt = (n + 127) >> 7;
+    constexpr uint32_t cS = 0, cP = 128, cO = 192;
+    if (tid == 0) {
+        mbar_init(bS, 1); mbar_init(bR, NCOMP / 32); mbar_init(bI, NCOMP / 32); mbar_init(bPV, 1);
+        fence_mbar_init(); sMax[0] = 0; sMax[1] = 0;
+    }
+    if (warp == 0) tmem_alloc(tslot, 256);
+    const size_t base = (size_t)bh * n * DH;
+    {
+        unsigned char *const imgs[3] = {sQ, sK, sV};
+        const __nv_bfloat16 *const srcs[3] = {a.q + base, a.k + base, a.v + base};
+        load_imgs<3>(imgs, srcs, n, nt * 128, tid);
+    }
+    __syncthreads();
+    for (int r = tid; r < nt * 128 + 32; r += NTH) {                         // norms for the softmax shift bound (whole warps: shuffles)
+        const bool in = r < nt * 128;
+        const float qn = in ? row_norm2(sQ, r) : 0.f, kn = learn::warp_max_f(in ? row_norm2(sK, r) : 0.f), qm = learn::warp_max_f(qn);
+        if (in) sQn[r] = qn;
+        if (lane == 0) { atomicMax(&sMax[0], __float_as_int(kn)); atomicMax(&sMax[1], __float_as_int(qm)); }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q4 * 32) << 16);
+    const float sl2 = a.scale * kLog2e;
+    const float kmax2 = __int_as_float(sMax[0]);
+    const bool bounded = a.scale * sqrtf(kmax2 * __int_as_float(sMax[1])) <= kBoundMax;          // CTA-uniform
+    const int npass = bounded ? 1 : 2;
+    const int total = npass * (nt * (nt + 1) / 2);                           // steps: (query tile, pass, key tile <= query tile)
+    auto advance = [&](int &qt, int &ps, int &kt) { if (++kt > qt) { kt = 0; if (++ps >= npass) { ps = 0; ++qt; } } };
+
+    if (warp == NCOMP / 32) {
+        // ---- MMA warp: S of the next step as soon as the current S tile has been read; O += P V as soon as P is written ----
+        if (lane == 0) {
+            const ImgDesc dQ_(sQ), dK_(sK), dV_(sV);
+            int qt = 0, ps = 0, kt = 0, iq = 0, ip = 0, ik = 0;
+            tc_fence_after();
+            mma_bf16_ss(tbase + cS, dQ_.rows + 0, dK_.rows + 0, idesc_bf16(128, 128), 0);
+            mma_commit(bS);
+            advance(iq, ip, ik);
+            for (int i = 0; i < total; ++i) {
+                mbar_wait_sleep(bR, i & 1, 400);
+                tc_fence_after();
+                if (i + 1 < total) {
+                    mma_bf16_ss(tbase + cS, dQ_.rows + iq * 128, dK_.rows + ik * 128, idesc_bf16(128, 128), 0);
+                    mma_commit(bS);
+                    advance(iq, ip, ik);
+                }
+                mbar_wait_sleep(bI, i & 1, 400);
+                tc_fence_after();
+                if (ps == npass - 1) {
+                    const uint64_t vb = dV_.cols + kt * 128;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)                               // K = 128 keys, A = P from tensor memory
+                        mma_bf16_ts(tbase + cO + (qt & 1) * DH, tbase + cP + s * 8, vb + s * 16, idesc_bf16(128, DH) | kIdB, kt > 0 || s > 0);
+                }
+                mma_commit(bPV);
+                advance(qt, ps, kt);
+            }
+        }
+    } else {
+        // ---- compute warps: row = query, chunks c4 and c4 + 4 of the step's eight 16-key chunks ----
+        const uint32_t ckey = cta_key(a.rng_step, a.rng_key, (uint32_t)bh);
+        auto arrive = [&](uint64_t *bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
+        auto finalize = [&](int qt, float m) {                               // O / l and logsumexp of query tile qt (its last P.V is complete)
+            const int qrow = qt * 128 + row;
+            const float *red = sRed + (qt & 1) * 512;
+            const float l = ((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])) / a.drop_scale;
+            if (c4 < 2) {
+                float o[8];
+                tmem_ld8(tlane + cO + (qt & 1) * DH + c4 * 8, o);
+                const float inv = 1.f / l;
+                if (qrow < n)
+                    *reinterpret_cast<uint4 *>(a.out + base + (size_t)qrow * DH + c4 * 8) =
+                        make_uint4(pack2(o[0] * inv, o[1] * inv), pack2(o[2] * inv, o[3] * inv), pack2(o[4] * inv, o[5] * inv), pack2(o[6] * inv, o[7] * inv));
+            } else if (c4 == 2 && qrow < n) {
+                a.lse[(size_t)bh * n + qrow] = m + __logf(l);
+            }
+            tc_fence_before();
+        };
+        int qt = 0, ps = 0, kt = 0;
+        float m = 0.f, m_prev = 0.f, l = 0.f, mx = -INFINITY;
+        if (bounded) m = a.scale * sqrtf(kmax2 * sQn[row]) * 1.0002f + 1e-4f;                      // >= every scaled score of the row (Cauchy-Schwarz)
+        float off = a.drop_log2scale - m * kLog2e;
+        for (int i = 0; i < total; ++i) {
+            mbar_wait_sleep(bS, i & 1, 200);
+            tc_fence_after();
+            const bool diag = kt == qt, main_pass = ps == npass - 1;
+            const uint32_t qabs = (uint32_t)(qt * 128 + row);
+            uint32_t w[2][8];
+            if (!main_pass) {
+                // exact row maximum over this key tile (scaled later)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int keyb = (c4 + 4 * cc) * 16;
+                    if (!diag || keyb <= q4 * 32 + 31) {
+                        float sv[16];
+                        tmem_ld16(tlane + cS + keyb, sv);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, (!diag || keyb + j <= row) ? sv[j] : -INFINITY);
+                    }
+                }
+                arrive(bR);
+                arrive(bI);
+                if (kt == qt) {                                              // last key tile of the max pass: the four column groups meet
+                    sRed[(qt & 1) * 512 + c4 * 128 + row] = mx;
+                    csync();
+                    const float *red = sRed + (qt & 1) * 512;
+                    m = fmaxf(fmaxf(red[row], red[128 + row]), fmaxf(red[256 + row], red[384 + row])) * a.scale;
+                    off = a.drop_log2scale - m * kLog2e;
+                    mx = -INFINITY;
+                    csync();
+                }
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int keyb = (c4 + 4 * cc) * 16;                     // first key of the chunk inside the key tile
+                    const uint32_t g4 = (uint32_t)(kt * 128 + keyb) >> 2;
+                    if (!diag) l += fwd2_chunk<false, DROP>(tlane + cS + keyb, row, 0, sl2, off, qabs, g4, ckey, a.drop_add4, w[cc]);
+                    else if (keyb <= q4 * 32 + 31) l += fwd2_chunk<true, DROP>(tlane + cS + keyb, row, keyb, sl2, off, qabs, g4, ckey, a.drop_add4, w[cc]);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w[cc][j] = 0u;
+                    }
+                }
+                arrive(bR);                                                  // the S tile has been read: the next one may be issued
+                if (i > 0) { mbar_wait(bPV, (i - 1) & 1); tc_fence_after(); }      // the P.V that read the P columns is complete
+                if (kt == 0 && qt > 0) finalize(qt - 1, m_prev);             // ... and so is the previous query tile's last one
+                tmem_st8(tlane + cP + c4 * 8, w[0]);
+                tmem_st8(tlane + cP + (c4 + 4) * 8, w[1]);
+                tmem_st_wait();
+                arrive(bI);
+                if (kt == qt) {                                              // last key tile of the query tile: row sums of the four column groups
+                    sRed[(qt & 1) * 512 + c4 * 128 + row] = l;
+                    csync();
+                    m_prev = m; l = 0.f;
+                    if (bounded && qt + 1 < nt) { m = a.scale * sqrtf(kmax2 * sQn[(qt + 1) * 128 + row]) * 1.0002f + 1e-4f; off = a.drop_log2scale - m * kLog2e; }
+                }
+            }
+            advance(qt, ps, kt);
+        }
+        mbar_wait(bPV, (total - 1) & 1);
+        tc_fence_after();
+        finalize(nt - 1, m_prev);
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
 // ------------------------------------------------------------------------------------------- backward
 // shared-memory order: the step images first -- dV / dK read them MN-major with M = 128 keys although a step holds
 // 64, so each read runs 16 KB past its image into the next one (the last into sQ); the accumulator rows those
@@ -881,8 +1084,15 @@ extern "C" int xtrl_attn_core_fwd(const xtrl_attn_core_io *io, int32_t bh, int32
     Args a;
     if (int rc = fill(io, n, dim_head, a)) return rc;
     static bool attr = false;
-    if (!attr) { XTRL_CUDA(cudaFuncSetAttribute(attn_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
-    attn_core_fwd_kernel<<<bh, NTH, kFwdSmem, (cudaStream_t)stream>>>(a);
+    if (!attr) {
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem));
+        XTRL_CUDA(cudaFuncSetAttribute(attn_core_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem));
+        attr = true;
+    }
+    if (getenv("XTRL_CORE_FWD_V1")) attn_core_fwd_kernel<<<bh, NTH, kFwdSmem, (cudaStream_t)stream>>>(a);
+    else if (a.drop_add4) attn_core_fwd2_kernel<true><<<bh, NTH, kFwd2Smem, (cudaStream_t)stream>>>(a);
+    else attn_core_fwd2_kernel<false><<<bh, NTH, kFwd2Smem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("attn_core_fwd_kernel");
     return XTRL_OK;
 }
