@@ -417,6 +417,10 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
 // two CTAs per SM cover what is left.  The exact-row-max case (norm bound too loose) is the same loop run twice per query
 // tile: a pass that only takes maxima, then the pass that forms P.
 constexpr int kFwd2Smem = 3 * kImg + 2 * 4 * 128 * 4 + R * 4 + 128;
+#ifndef XTRL_WAIT_NS
+#define XTRL_WAIT_NS 2000
+#endif
+constexpr uint32_t kWaitNs = XTRL_WAIT_NS;   // suspend-time hint of the compute warps' barrier waits (a sleeping warp costs no issue slots)
 
 template <bool DIAG, bool DROP>
 __device__ __forceinline__ float fwd2_chunk(uint32_t taddr, int row, int keyb, float sl2, float off, uint32_t qrow, uint32_t g4, uint32_t ckey,
@@ -547,7 +551,7 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd2_kernel(const Args a) {
         if (bounded) m = a.scale * sqrtf(kmax2 * sQn[row]) * 1.0002f + 1e-4f;                      // >= every scaled score of the row (Cauchy-Schwarz)
         float off = a.drop_log2scale - m * kLog2e;
         for (int i = 0; i < total; ++i) {
-            mbar_wait_sleep(bS, i & 1, 200);
+            mbar_wait_sleep(bS, i & 1, kWaitNs);
             tc_fence_after();
             const bool diag = kt == qt, main_pass = ps == npass - 1;
             const uint32_t qabs = (uint32_t)(qt * 128 + row);
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd2_kernel(const Args a) {
                     }
                 }
                 arrive(bR);                                                  // the S tile has been read: the next one may be issued
-                if (i > 0) { mbar_wait(bPV, (i - 1) & 1); tc_fence_after(); }      // the P.V that read the P columns is complete
+                if (i > 0) { mbar_wait_sleep(bPV, (i - 1) & 1, kWaitNs); tc_fence_after(); }      // the P.V that read the P columns is complete
                 if (kt == 0 && qt > 0) finalize(qt - 1, m_prev);             // ... and so is the previous query tile's last one
                 tmem_st8(tlane + cP + c4 * 8, w[0]);
                 tmem_st8(tlane + cP + (c4 + 4) * 8, w[1]);
@@ -1001,7 +1005,7 @@ __global__ void __launch_bounds__((16 / CQ + 2) * 32, 1) attn_core_bwd2_kernel(c
         int kt = 0, qt = 0;
         for (int i = 0; i < total; ++i) {
             const int h = i & 1;
-            mbar_wait_sleep(&bS[h], (i >> 1) & 1, 400);
+            mbar_wait_sleep(&bS[h], (i >> 1) & 1, kWaitNs);
             tc_fence_after();
             if (h == 0 && qt == kt && kt > 0) {                              // a key tile has finished: its dK, dV leave tensor memory
                 mbar_wait(&bP[1], ((i - 1) >> 1) & 1);
@@ -1024,7 +1028,7 @@ __global__ void __launch_bounds__((16 / CQ + 2) * 32, 1) attn_core_bwd2_kernel(c
                     for (int j = 0; j < 8; ++j) { wp[cc][j] = 0u; wd[cc][j] = 0u; }
                 }
             }
-            if (i >= 2) { mbar_wait(&bP[h], ((i - 2) >> 1) & 1); tc_fence_after(); }      // the products that read these TMEM operands are done
+            if (i >= 2) { mbar_wait_sleep(&bP[h], ((i - 2) >> 1) & 1, kWaitNs); tc_fence_after(); }      // the products that read these TMEM operands are done
 #pragma unroll
             for (int cc = 0; cc < CQ; ++cc) {
                 const int q_local0 = h * 64 + (c4 * CQ + cc) * 16;
