@@ -107,6 +107,10 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_fwd_kernel(const Args a) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
         const int e = t / a.n, pos = t - e * a.n;
+        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
+            const int t0 = (tile + gridDim.x) * TOK;
+            prefetch_rows48(a.x, t0, min(TOK, a.N - t0), tid, NT);
+        }
         float xr[D], own[24], mean, rstd;
         load_row(a.x + (size_t)t * D, ok, xr);
         ln_stats(xr, mean, rstd);
@@ -202,6 +206,19 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
         const int e = t / a.n, pos = t - e * a.n;
+        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
+            const int t0 = (tile + gridDim.x) * TOK, tn = t0 + row;
+            prefetch_rows48(a.x, t0, min(TOK, a.N - t0), tid, NT);
+            if (tn < a.N && (row & 3) == 0) {                                    // 4 tokens share a 128-byte line of a (token, head) block
+                const int en = tn / a.n, pn = tn - en * a.n;
+                const int p0 = half ? BLK0 : 0, p1 = half ? NBLK : BLK0;
+                for (int bi = p0; bi < p1; ++bi) {
+                    const int which = bi / H, h = bi - which * H;
+                    prefetch_l2(bi >= NB * H ? a.dmix + (size_t)tn * 16
+                                : (which == 0 ? a.dq : which == 1 ? a.dk : which == 2 ? a.dv : a.dg) + ((size_t)(en * H + h) * a.n + pn) * 16);
+                }
+            }
+        }
         float xr[D], own[24], mean, rstd;
         load_row(a.x + (size_t)t * D, ok, xr);
         ln_stats(xr, mean, rstd);
@@ -219,7 +236,7 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         const float4 cs = ok ? __ldg(reinterpret_cast<const float4 *>(a.cos_tab) + pos) : make_float4(1.f, 1.f, 1.f, 1.f);
         const float4 sn = ok ? __ldg(reinterpret_cast<const float4 *>(a.sin_tab) + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int b0 = half ? BLK0 : 0, b1 = half ? NBLK : BLK0;
-#pragma unroll 1
+#pragma unroll 2
         for (int bi = b0; bi < b1; ++bi) {
             const int which = bi / H, h = bi - which * H;
             const __nv_bfloat16 *src = bi >= NB * H ? a.dmix + (size_t)t * 16

@@ -45,6 +45,16 @@ __device__ __forceinline__ void put8(unsigned char *img, int row, int chunk, con
 }
 
 
+// pull the 128-byte line of `p` into L2 (no register, no wait).  Every persistent CTA of the sub-layer kernels prefetches the
+// rows of its NEXT tile while it works on the current one: all SMs load their tiles at the same moment, so without this each
+// tile starts with a burst of DRAM round trips that nothing overlaps (ncu: 34 % of attn_pre_bwd's stall samples).
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// rows [t0, t0 + rows) of a row-major fp32 [N][48] tensor: 192 bytes per row, one prefetch per 128-byte line
+__device__ __forceinline__ void prefetch_rows48(const float *base, int t0, int rows, int tid, int nthreads) {
+    const char *p = reinterpret_cast<const char *>(base + (size_t)t0 * D);
+    for (int o = tid * 128; o < rows * D * 4; o += nthreads * 128) prefetch_l2(p + o);
+}
+
 __device__ __forceinline__ float warp_max_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
+        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
+            const int t0 = (tile + gridDim.x) * TOK;
+            prefetch_rows48(a.x, t0, min(TOK, a.N - t0), tid, NT);
+        }
         float xr[D];
         load_row(a.x + (size_t)t * D, ok, xr);
         float mean, rstd, own[24];
@@ -235,6 +239,11 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
+        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
+            const int t0 = (tile + gridDim.x) * TOK, nr = min(TOK, a.N - t0);
+            prefetch_rows48(a.x, t0, nr, tid, NT4);
+            prefetch_rows48(a.dy, t0, nr, tid, NT4);
+        }
         float mean, rstd, dyr[16];
         {
             float xr[D];

@@ -90,6 +90,13 @@ __global__ void __launch_bounds__(NT, 2) mlp_fwd_kernel(const Args a) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
+        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
+            const int t0 = (tile + gridDim.x) * TOK, nr = min(TOK, a.N - t0);
+            prefetch_rows48(a.src[0], t0, nr, tid, NT);
+            prefetch_rows48(a.src[1], t0, nr, tid, NT);
+            if (P::NSRC == 3 && !a.per_episode2) prefetch_rows48(a.src[2], t0, nr, tid, NT);
+            if (a.gy) { const char *g = reinterpret_cast<const char *>(a.gy + (size_t)t0 * a.out_cols); for (int o = tid * 128; o < nr * a.out_cols * 2; o += NT * 128) prefetch_l2(g + o); }
+        }
         build_x<P::NSRC>(sX, a, t, ok, row, half);
         fence_proxy_async();
         __syncthreads();
@@ -185,6 +192,13 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
+        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
+            const int t0 = (tile + gridDim.x) * TOK, nr = min(TOK, a.N - t0);
+            prefetch_rows48(a.src[0], t0, nr, tid, NT);
+            prefetch_rows48(a.src[1], t0, nr, tid, NT);
+            if (P::NSRC == 3 && !a.per_episode2) prefetch_rows48(a.src[2], t0, nr, tid, NT);
+            if (a.gy) { const char *g = reinterpret_cast<const char *>(a.gy + (size_t)t0 * a.out_cols); for (int o = tid * 128; o < nr * a.out_cols * 2; o += NT * 128) prefetch_l2(g + o); }
+        }
         build_x<P::NSRC>(sX, a, t, ok, row, half);
 #pragma unroll 1
         for (int c = 0; c < NOUT / 16; ++c) {                                  // dY image (zero beyond out_cols and beyond N)
