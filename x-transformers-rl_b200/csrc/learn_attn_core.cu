@@ -26,7 +26,7 @@
 namespace xtrl {
 namespace core {
 using namespace umma;
-using learn::pack2;
+using learn::pack2; using learn::pk2; using learn::upk2; using learn::fma2; using learn::mul2; using learn::add2;
 
 constexpr int R = 512, NCOMP = 512, NTH = NCOMP + 32, DH = 16;      // 16 compute warps + one warp that only issues MMAs
 constexpr int kImg = R * DH * 2;              // one q / k / v / dO image: 2 chunks of 8 dims x 512 rows x 16 B
@@ -156,29 +156,6 @@ __device__ __forceinline__ StepGeom geom(int qt, int kt, int c4) {
     g.qt = qt; g.kt = kt; g.diag = (kt >> 1) == qt;
     g.keyb = (kt - 2 * qt) * KT + c4 * 16;
     return g;
-}
-
-// packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 issue two fp32 operations per instruction)
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
 }
 
 // one 16-key chunk of the forward: P = 2^(s*sl2 + off) (dropout folded in), returns the chunk's row sum

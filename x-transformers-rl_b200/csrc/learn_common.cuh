@@ -45,6 +45,29 @@ __device__ __forceinline__ void put8(unsigned char *img, int row, int chunk, con
 }
 
 
+// packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 issue two fp32 operations per instruction)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // pull the 128-byte line of `p` into L2 (no register, no wait).  Every persistent CTA of the sub-layer kernels prefetches the
 // rows of its NEXT tile while it works on the current one: all SMs load their tiles at the same moment, so without this each
 // tile starts with a burst of DRAM round trips that nothing overlaps (ncu: 34 % of attn_pre_bwd's stall samples).

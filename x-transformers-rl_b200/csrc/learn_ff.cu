@@ -51,21 +51,72 @@ __device__ __forceinline__ void gelu_both(float x, float &g, float &dg) {
     dg = fmaf(x * 0.3989422804014327f, e, cdf);
 }
 __device__ __forceinline__ float gelu(float x) { float g, d; gelu_both(x, g, d); return g; }
-// two 16-bit uniforms per (token, column pair): murmur3 finaliser over a counter
-__device__ __forceinline__ uint32_t hash2(uint32_t idx, uint32_t key) {
-    uint32_t h = idx * 0x9E3779B1u ^ key;
-    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-    return h;
+// The same pair of functions on packed fp32 pairs: half the floating-point instructions (FFMA2 / FMUL2 / FADD2).
+// g = x * Phi(x), dg = Phi(x) + x * phi(x);  Phi = 0.5 + copysign(0.5 - half_erfc(|x|), x).
+__device__ __forceinline__ void gelu_both2(uint64_t x2, uint64_t &g2, uint64_t &d2) {
+    float x0, x1;
+    upk2(x2, x0, x1);
+    const uint64_t z = mul2(pk2(fabsf(x0), fabsf(x1)), pk2(0.70710678118654752f, 0.70710678118654752f));
+    float u0, u1;
+    upk2(fma2(pk2(0.3275911f, 0.3275911f), z, pk2(1.f, 1.f)), u0, u1);
+    const uint64_t t = pk2(__frcp_rn(u0), __frcp_rn(u1));
+    float a0, a1;
+    upk2(mul2(mul2(x2, x2), pk2(-0.72134752044448170f, -0.72134752044448170f)), a0, a1);
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    const uint64_t e = pk2(e0, e1);                                                        // exp(-x^2 / 2)
+    uint64_t poly = fma2(pk2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, pk2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+    poly = fma2(poly, t, pk2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+    poly = fma2(poly, t, pk2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+    poly = fma2(poly, t, pk2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+    float h0, h1;
+    upk2(fma2(mul2(poly, t), pk2(-e0, -e1), pk2(0.5f, 0.5f)), h0, h1);                     // 0.5 - 0.5 erfc(|x| / sqrt 2) >= 0
+    const uint64_t cdf = add2(pk2(copysignf(h0, x0), copysignf(h1, x1)), pk2(0.5f, 0.5f));
+    g2 = mul2(x2, cdf);
+    d2 = fma2(mul2(x2, pk2(0.3989422804014327f, 0.3989422804014327f)), e, cdf);
 }
+// Dropout decisions of the four hidden units 4 g .. 4 g + 3 of token t: one hash -> four 7-bit uniforms; the sign bit of byte j
+// of the result is set <=> keep (p is quantised to 1/128, as in the attention core).  add4 = (128 - threshold) in every byte.
 __device__ __forceinline__ uint32_t fold_key(const int64_t *rng_step, uint32_t key) {
     const uint64_t s = (uint64_t)(rng_step ? *rng_step : 0) * 0x9E3779B97F4A7C15ull;
     return (uint32_t)(s >> 32) ^ (uint32_t)s ^ (key * 0x632BE5ABu);
 }
-// keep-factors (0 or 1/(1-p)) for columns c, c+1 of token t
-__device__ __forceinline__ void drop2(uint32_t t, int c, uint32_t key, uint32_t thr, float scale, float &k0, float &k1) {
-    const uint32_t h = hash2(t * (uint32_t)(F / 2) + (uint32_t)(c >> 1), key);
-    k0 = (h & 0xffffu) >= thr ? scale : 0.f;
-    k1 = (h >> 16) >= thr ? scale : 0.f;
+__device__ __forceinline__ uint32_t keep4(uint32_t t, int g, uint32_t key, uint32_t add4) {
+    uint32_t h = (t * (uint32_t)(F / 4) + (uint32_t)g) * 0x9E3779B1u ^ key;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 15;
+    return (h & 0x7f7f7f7fu) + add4;
+}
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t sel) {                 // selector nibble 8 | j: replicate the sign of byte j
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+    return d;
+}
+// 16 pre-activations of token t (columns col0 .. col0 + 15, accumulator values + bias) -> GELU values g and, if WITH_D, the
+// derivative d, both already multiplied by the dropout keep factor (0 or drop_scale)
+template <bool WITH_D>
+__device__ __forceinline__ void act16(const float (&pre)[16], const float *bias, uint32_t t, int col0, uint32_t key, uint32_t add4, float scale,
+                                      float (&g)[16], float (&d)[16]) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 b = *reinterpret_cast<const float4 *>(bias + 4 * q4);
+        const uint32_t kw = add4 ? keep4(t, (col0 >> 2) + q4, key, add4) : 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 4 * q4 + 2 * h;
+            uint64_t g2, d2;
+            gelu_both2(add2(pk2(pre[j], pre[j + 1]), h ? pk2(b.z, b.w) : pk2(b.x, b.y)), g2, d2);
+            if (add4) {                                                                   // keep factor as a float: mask & scale bits
+                const uint64_t k2 = pk2(__uint_as_float(prmt_sign(kw, 0x8888u + 0x1111u * (2 * h)) & __float_as_uint(scale)),
+                                        __uint_as_float(prmt_sign(kw, 0x8888u + 0x1111u * (2 * h + 1)) & __float_as_uint(scale)));
+                g2 = mul2(g2, k2);
+                if (WITH_D) d2 = mul2(d2, k2);
+            }
+            upk2(g2, g[j], g[j + 1]);
+            if (WITH_D) upk2(d2, d[j], d[j + 1]);
+        }
+    }
+
 }
 
 struct Args {
@@ -73,7 +124,7 @@ struct Args {
     const unsigned char *wimg;
     float *y, *dx, *dgamma, *dW1, *db1, *dW2, *db2;
     const int64_t *rng_step;
-    uint32_t rng_key, drop_thr;
+    uint32_t rng_key, drop_add4;              // (128 - threshold) replicated in 4 bytes; 0 = no dropout
     float drop_scale;
     int N;
 };
@@ -142,16 +193,11 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
             const int col0 = half * 96 + c * 16;
             float v[16];
             tmem_ld16(tlane + col0, v);
+            {
+                float g[16], dummy[16];
+                act16<false>(v, sB1 + col0, (uint32_t)t, col0, key, a.drop_add4, a.drop_scale, g, dummy);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                const float p0 = v[j] + sB1[col0 + j], p1 = v[j + 1] + sB1[col0 + j + 1];
-                float g0 = gelu(p0), g1 = gelu(p1);
-                if (a.drop_thr) {
-                    float k0, k1;
-                    drop2((uint32_t)t, col0 + j, key, a.drop_thr, a.drop_scale, k0, k1);
-                    g0 *= k0; g1 *= k1;
-                }
-                v[j] = g0; v[j + 1] = g1;
+                for (int j = 0; j < 16; ++j) v[j] = g[j];
             }
             float lo[8], hi[8];
 #pragma unroll
@@ -289,18 +335,10 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
         for (int c = 0; c < 3; ++c) {                                            // H and gelu'.mask, my 48 hidden units
             const int col0 = cq * 48 + c * 16;
             float v[16], d[16];
-            tmem_ld16(tlane + cPre + col0, v);
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                float g0, g1, d0, d1;
-                gelu_both(v[j] + sB1[col0 + j], g0, d0);
-                gelu_both(v[j + 1] + sB1[col0 + j + 1], g1, d1);
-                if (a.drop_thr) {
-                    float k0, k1;
-                    drop2((uint32_t)t, col0 + j, key, a.drop_thr, a.drop_scale, k0, k1);
-                    g0 *= k0; g1 *= k1; d0 *= k0; d1 *= k1;
-                }
-                v[j] = g0; v[j + 1] = g1; d[j] = d0; d[j + 1] = d1;
+            {
+                float pre[16];
+                tmem_ld16(tlane + cPre + col0, pre);
+                act16<true>(pre, sB1 + col0, (uint32_t)t, col0, key, a.drop_add4, a.drop_scale, v, d);
             }
             float lo[8], hi[8];
 #pragma unroll
@@ -455,8 +493,9 @@ static int fill(const xtrl_ff_io *io, int64_t N, Args &a) {
     a.wimg = static_cast<const unsigned char *>(io->w_img);
     a.y = io->y; a.dx = io->dx; a.dgamma = io->d_ln_gamma; a.dW1 = io->d_w1; a.db1 = io->d_b1; a.dW2 = io->d_w2; a.db2 = io->d_b2;
     a.rng_step = io->rng_step; a.rng_key = io->rng_key;
-    a.drop_thr = (uint32_t)(io->dropout * 65536.f + 0.5f);
-    a.drop_scale = 1.f / (1.f - (float)a.drop_thr / 65536.f);
+    const uint32_t thr = (uint32_t)(io->dropout * 128.f + 0.5f);             // the drop probability is quantised to 1/128
+    a.drop_add4 = thr ? (128u - thr) * 0x01010101u : 0u;
+    a.drop_scale = 1.f / (1.f - (float)thr / 128.f);
     a.N = (int)N;
     return XTRL_OK;
 }
