@@ -24,7 +24,7 @@ class _Guarded:
         n = 1
         for s_ in shape:
             n *= int(s_)
-        item = torch.empty((), dtype=dtype).element_size()
+        item = self._real_empty((), dtype=dtype).element_size()
         g = GUARD // item
         raw = self._real_empty(n + 2 * g, dtype=dtype, device=device)
         sent = raw.view(torch.uint8)
