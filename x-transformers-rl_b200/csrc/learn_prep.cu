@@ -129,8 +129,11 @@ struct BwdArgs {
     int S, A, cont;
 };
 
+// backward: 48 features x TLB token lanes per CTA, one CTA per SM (few CTAs = few same-address atomics at the end)
+constexpr int TLB = 16, NTB = D * TLB;
+
 template <int SM, int AM>
-__global__ void __launch_bounds__(NT) prep_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(NTB) prep_bwd_kernel(const BwdArgs a) {
     const xtrl_prep_bwd_io &io = a.io;
     const int tid = threadIdx.x, j = tid % D, tl = tid / D;
     const int S = a.S, S1 = S + 1, A = a.A;
@@ -142,41 +145,78 @@ __global__ void __launch_bounds__(NT) prep_bwd_kernel(const BwdArgs a) {
     for (int i = 0; i < AM; ++i) g_ac[i] = 0.f;
     const int Nr = (int)a.N;                                  // < 2^31 (checked by the launcher)
     int per = (Nr + gridDim.x - 1) / gridDim.x;
-    per = (per + TL - 1) / TL * TL;
+    per = (per + TLB - 1) / TLB * TLB;
     const int lo = blockIdx.x * per, hi = lo + per < Nr ? lo + per : Nr;
-    int t = lo + tl < Nr ? (int)((unsigned)(lo + tl) % (unsigned)io.T) : 0;      // timestep of row r, advanced without divisions
-    for (int64_t r = lo + tl; r < hi; r += TL, t += TL) {
-        while (t >= io.T) t -= io.T;
-        const float dx = __ldg(io.dx0 + r * D + j), dse = io.d_se ? __ldg(io.d_se + r * D + j) : 0.f, dae = io.d_ae_next ? __ldg(io.d_ae_next + r * D + j) : 0.f;
-        const float *pk = io.packed + r * S1;
+    // Rows are taken U at a time: all of their loads are issued before the first accumulate, so U x 14 independent loads are in
+    // flight per thread instead of one row's (the loop is latency-bound otherwise).
+    constexpr int U = 2;
+    struct Row { float dx, dse, dae, pk[SM + 1]; float av[AM]; int na, pa; bool live; };
+    auto load_row = [&](int64_t r, int t, Row &w) {
+        w.live = r < hi;
+        const int64_t rr = w.live ? r : lo;
+        w.dx = w.live ? __ldg(io.dx0 + rr * D + j) : 0.f;
+        w.dse = (w.live && io.d_se) ? __ldg(io.d_se + rr * D + j) : 0.f;
+        w.dae = (w.live && io.d_ae_next) ? __ldg(io.d_ae_next + rr * D + j) : 0.f;
+        const float *pk = io.packed + rr * S1;
 #pragma unroll
-        for (int s = 0; s < SM; ++s) if (s < S) { const float v = __ldg(pk + s); g_in[s] = fmaf(dx, v, g_in[s]); g_se[s] = fmaf(dse, v, g_se[s]); }
-        g_in[SM] = fmaf(dx, __ldg(pk + S) * flag, g_in[SM]);
-        g_se[SM] += dse;
+        for (int s = 0; s < SM; ++s) w.pk[s] = s < S ? __ldg(pk + s) : 0.f;
+        w.pk[SM] = __ldg(pk + S) * flag;
         if (a.cont) {
-            const float *an = static_cast<const float *>(io.mb_actions) + r * A;
-            const bool first = t == 0;
+            const float *an = static_cast<const float *>(io.mb_actions) + rr * A;
 #pragma unroll
-            for (int i = 0; i < AM; ++i) if (i < A) g_ac[i] += dae * __ldg(an + i) + (first ? 0.f : dx * __ldg(an + i - A));
-            g_bac += dae + dx;
+            for (int i = 0; i < AM; ++i) w.av[i] = i < A ? __ldg(an + i) : 0.f;
+            w.na = t;                                                          // continuous: na carries t (first row of an episode has no prev action)
+            w.pa = 0;
         } else {
             const int32_t *acts = static_cast<const int32_t *>(io.mb_actions);
-            const int na = __ldg(acts + r), pa = t == 0 ? -1 : __ldg(acts + r - 1);
-#pragma unroll
-            for (int i = 0; i < AM; ++i) if (i < A) g_ac[i] += (na == i ? dae : 0.f) + (pa == i ? dx : 0.f);
+            w.na = __ldg(acts + rr);
+            w.pa = t == 0 ? -1 : __ldg(acts + rr - 1);
         }
+    };
+    auto accumulate = [&](const Row &w, int64_t r) {
+        if (!w.live) return;
+#pragma unroll
+        for (int s = 0; s < SM; ++s) { g_in[s] = fmaf(w.dx, w.pk[s], g_in[s]); g_se[s] = fmaf(w.dse, w.pk[s], g_se[s]); }
+        g_in[SM] = fmaf(w.dx, w.pk[SM], g_in[SM]);
+        g_se[SM] += w.dse;
+        if (a.cont) {
+            const float *an = static_cast<const float *>(io.mb_actions) + r * A;
+#pragma unroll
+            for (int i = 0; i < AM; ++i) if (i < A) g_ac[i] += w.dae * w.av[i] + (w.na == 0 ? 0.f : w.dx * __ldg(an + i - A));
+            g_bac += w.dae + w.dx;
+        } else {
+#pragma unroll
+            for (int i = 0; i < AM; ++i) g_ac[i] += (w.na == i ? w.dae : 0.f) + (w.pa == i ? w.dx : 0.f);
+        }
+    };
+    int t = lo + tl < Nr ? (int)((unsigned)(lo + tl) % (unsigned)io.T) : 0;      // timestep of row r, advanced without divisions
+    for (int64_t r = lo + tl; r < hi; r += U * TLB) {
+        Row w[U];
+        int tt = t;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            while (tt >= io.T) tt -= io.T;
+            load_row(r + u * TLB, tt, w[u]);
+            tt += TLB;
+        }
+        t = tt;
+#pragma unroll
+        for (int u = 0; u < U; ++u) accumulate(w[u], r + u * TLB);
     }
-    // the TL token lanes of a feature meet in shared memory, then one atomicAdd per value and CTA
-    __shared__ float red[TL][D][2 * (SM + 1) + AM + 1];
-    float *mine = red[tl][j];
+    // the TLB token lanes of a feature meet in shared memory (atomics), then one global atomicAdd per value and CTA
+    constexpr int NV = 2 * (SM + 1) + AM + 1;
+    __shared__ float red[D][NV];
+    for (int i = tid; i < D * NV; i += NTB) (&red[0][0])[i] = 0.f;
+    __syncthreads();
+    float *mine = red[j];
 #pragma unroll
-    for (int s = 0; s <= SM; ++s) { mine[s] = g_in[s]; mine[SM + 1 + s] = g_se[s]; }
+    for (int s = 0; s <= SM; ++s) { atomicAdd(mine + s, g_in[s]); atomicAdd(mine + SM + 1 + s, g_se[s]); }
 #pragma unroll
-    for (int i = 0; i < AM; ++i) mine[2 * (SM + 1) + i] = g_ac[i];
-    mine[2 * (SM + 1) + AM] = g_bac;
+    for (int i = 0; i < AM; ++i) atomicAdd(mine + 2 * (SM + 1) + i, g_ac[i]);
+    atomicAdd(mine + 2 * (SM + 1) + AM, g_bac);
     __syncthreads();
     if (tl == 0) {
-        auto tot = [&](int k) { float s = 0.f; for (int l = 0; l < TL; ++l) s += red[l][j][k]; return s; };
+        auto tot = [&](int k) { return red[j][k]; };
         for (int s = 0; s < S; ++s) {
             atomicAdd(io.d_w_in + j * S + s, tot(s));
             if (io.d_w_se) atomicAdd(io.d_w_se + j * S + s, tot(SM + 1 + s));
@@ -227,10 +267,10 @@ extern "C" int xtrl_learn_prep_bwd(const xtrl_prep_bwd_io *io, int32_t b, int32_
                  (!continuous || io->d_b_act) && io->T == T, XTRL_E_BADARG, "xtrl_learn_prep_bwd: null pointer / inconsistent T");
     BwdArgs a;
     a.io = *io; a.N = (int64_t)b * T; a.S = state_dim; a.A = num_actions; a.cont = continuous != 0;
-    const int64_t want = (a.N + 255) / 256, cap = 4LL * num_sms();
+    const int64_t want = (a.N + 2 * TLB - 1) / (2 * TLB), cap = num_sms();
     const int grid = (int)(want < cap ? want : cap);
-    if (state_dim <= 8 && num_actions <= 4) prep_bwd_kernel<8, 4><<<grid, NT, 0, (cudaStream_t)stream>>>(a);
-    else prep_bwd_kernel<SMAX, AMAX><<<grid, NT, 0, (cudaStream_t)stream>>>(a);
+    if (state_dim <= 8 && num_actions <= 4) prep_bwd_kernel<8, 4><<<grid, NTB, 0, (cudaStream_t)stream>>>(a);
+    else prep_bwd_kernel<SMAX, AMAX><<<grid, NTB, 0, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("prep_bwd_kernel");
     return XTRL_OK;
 }
