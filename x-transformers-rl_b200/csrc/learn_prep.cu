@@ -100,9 +100,10 @@ __global__ void __launch_bounds__(NT) prep_fwd_kernel(const Args a) {
             for (int tk = 0; tk < lim; ++tk) my_sum += s_valid[tk] * (tid < S1 ? s_packed[tk][tid] : 1.f);
         }
         // phase 2: the three 48-wide rows of every token
+#pragma unroll 4
         for (int tk = tl; tk < TOK; tk += TL) {
-            const int64_t r = r0 + tk;
-            if (r >= N) break;
+            const int r = r0 + tk;
+            if (r >= N) continue;
             float x = 0.f, se = b_se, ae_p = 0.f, ae_n = 0.f;
 #pragma unroll
             for (int s = 0; s < SM; ++s) if (s < S) { const float v = s_packed[tk][s]; x = fmaf(w_in[s], v, x); se = fmaf(w_se[s], v, se); }
@@ -115,9 +116,9 @@ __global__ void __launch_bounds__(NT) prep_fwd_kernel(const Args a) {
                 ae_p = pa >= 0 ? __ldg(io.w_act + pa * D + j) : 0.f;           // SafeEmbedding (:181-195): id -1 -> zeros
                 ae_n = na >= 0 ? __ldg(io.w_act + na * D + j) : 0.f;
             }
-            io.x0[r * D + j] = x + ae_p + s_packed[tk][S] * re;
-            io.se[r * D + j] = se;
-            io.ae_next[r * D + j] = ae_n;
+            io.x0[(int64_t)r * D + j] = x + ae_p + s_packed[tk][S] * re;
+            io.se[(int64_t)r * D + j] = se;
+            io.ae_next[(int64_t)r * D + j] = ae_n;
         }
     }
     if (tid <= S1 && my_sum != 0.f) atomicAdd(io.rs_sum + tid, my_sum);
