@@ -202,25 +202,37 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
 #pragma unroll
     for (int i = 0; i < 24; ++i) dg_acc[i] = 0.f;
     const int ntiles = (a.N + TOK - 1) / TOK;
+    const int b0 = half ? BLK0 : 0, b1 = half ? NBLK : BLK0;
+    // this thread's gradient blocks of a tile, global -> the dY image, all in flight at once (sDQ must be free: the MMAs
+    // of the previous tile have completed)
+    auto fetch_dy = [&](int tile) {
+        const int t = tile * TOK + row;
+        const bool ok = t < a.N;
+        const int tc = ok ? t : 0, e = tc / a.n, pos = tc - e * a.n;
+#pragma unroll 4
+        for (int bi = b0; bi < b1; ++bi) {
+            const int which = bi / H, h = bi - which * H;
+            const __nv_bfloat16 *src = bi >= NB * H ? a.dmix + (size_t)tc * 16
+                : (which == 0 ? a.dq : which == 1 ? a.dk : which == 2 ? a.dv : a.dg) + ((size_t)(e * H + h) * a.n + pos) * 16;
+            unsigned char *p = sDQ + (2 * bi) * kCore + (row >> 3) * 128 + (row & 7) * 16;
+            cp_async16(p, src, ok);
+            cp_async16(p + kCore, src + 8, ok);
+        }
+        cp_async_commit();
+    };
+    if ((int)blockIdx.x < ntiles) fetch_dy(blockIdx.x);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
         const int e = t / a.n, pos = t - e * a.n;
         if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
-            const int t0 = (tile + gridDim.x) * TOK, tn = t0 + row;
+            const int t0 = (tile + gridDim.x) * TOK;
             prefetch_rows48(a.x, t0, min(TOK, a.N - t0), tid, NT);
-            if (tn < a.N && (row & 3) == 0) {                                    // 4 tokens share a 128-byte line of a (token, head) block
-                const int en = tn / a.n, pn = tn - en * a.n;
-                const int p0 = half ? BLK0 : 0, p1 = half ? NBLK : BLK0;
-                for (int bi = p0; bi < p1; ++bi) {
-                    const int which = bi / H, h = bi - which * H;
-                    prefetch_l2(bi >= NB * H ? a.dmix + (size_t)tn * 16
-                                : (which == 0 ? a.dq : which == 1 ? a.dk : which == 2 ? a.dv : a.dg) + ((size_t)(en * H + h) * a.n + pn) * 16);
-                }
-            }
         }
         float xr[D], own[24], mean, rstd;
         load_row(a.x + (size_t)t * D, ok, xr);
+        const float4 cs = ok ? __ldg(reinterpret_cast<const float4 *>(a.cos_tab) + pos) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 sn = ok ? __ldg(reinterpret_cast<const float4 *>(a.sin_tab) + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
         ln_stats(xr, mean, rstd);
 #pragma unroll
         for (int i = 0; i < D; ++i) xr[i] = (xr[i] - mean) * rstd;
@@ -233,29 +245,22 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
             for (int j = 0; j < 8; ++j) v[j] = own[c * 8 + j] * sG[half * 24 + c * 8 + j];
             put8(sXn, row, half * 3 + c, v);
         }
-        const float4 cs = ok ? __ldg(reinterpret_cast<const float4 *>(a.cos_tab) + pos) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 sn = ok ? __ldg(reinterpret_cast<const float4 *>(a.sin_tab) + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int b0 = half ? BLK0 : 0, b1 = half ? NBLK : BLK0;
+        cp_async_wait_all();
+        // un-rotate the first 8 dims of this thread's q / k blocks where they lie (the thread's own copies: no barrier)
 #pragma unroll 2
         for (int bi = b0; bi < b1; ++bi) {
-            const int which = bi / H, h = bi - which * H;
-            const __nv_bfloat16 *src = bi >= NB * H ? a.dmix + (size_t)t * 16
-                : (which == 0 ? a.dq : which == 1 ? a.dk : which == 2 ? a.dv : a.dg) + ((size_t)(e * H + h) * a.n + pos) * 16;
-            if (which < 2) {
-                float lo[8], hi[8], v[16];
-                const uint4 z = make_uint4(0, 0, 0, 0);
-                unpack8(ok ? __ldg(reinterpret_cast<const uint4 *>(src)) : z, lo);
-                unpack8(ok ? __ldg(reinterpret_cast<const uint4 *>(src) + 1) : z, hi);
+            if (bi >= 2 * H) break;
+            uint4 *p = reinterpret_cast<uint4 *>(sDQ + (2 * bi) * kCore + (row >> 3) * 128 + (row & 7) * 16);
+            float lo[8];
+            unpack8(*p, lo);
+            const float c[4] = {cs.x, cs.y, cs.z, cs.w}, sv[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { v[j] = lo[j]; v[8 + j] = hi[j]; }
-                rotary8(v, cs, sn, true);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) lo[j] = v[j];
-                put8(sDQ, row, 2 * bi, lo);
-                put8(sDQ, row, 2 * bi + 1, hi);
-            } else {
-                copy_block(sDQ, row, bi, src, ok);
+            for (int i = 0; i < 4; ++i) {
+                const float x0 = lo[2 * i], x1 = lo[2 * i + 1];
+                lo[2 * i] = x0 * c[i] + x1 * sv[i];
+                lo[2 * i + 1] = x1 * c[i] - x0 * sv[i];
             }
+            *p = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
         }
         fence_proxy_async();
         __syncthreads();
@@ -279,6 +284,7 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
+        if (tile + (int)gridDim.x < ntiles) fetch_dy(tile + gridDim.x);          // flies under the epilogue and the next row load
         {
             float dxn[D];
 #pragma unroll
@@ -314,32 +320,37 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
     }
     if (!first) {
         tc_fence_after();
+        float *stage = reinterpret_cast<float *>(sDQ);                            // [128][D + 1] fp32, the dY image is done with
+        constexpr int PITCH = D + 1;
+        auto wrow = [&](int j, float *&bdst) -> float * {                         // output row j of [Wq; Wk; Wv; (Wg); (Wm)]
+            const int which = j / I, jj = j - which * I;
+            bdst = nullptr;
+            if (j < NB * I) {
+                if (which == 3) bdst = a.dbg + jj;
+                return (which == 0 ? a.dwq : which == 1 ? a.dwk : which == 2 ? a.dwv : a.dwg) + jj * D;
+            }
+            if (MIX && j - NB * I < H) { bdst = a.dbm + (j - NB * I); return a.dwm + (j - NB * I) * D; }
+            return nullptr;
+        };
 #pragma unroll 1
         for (int m = 0; m < P::kMT; ++m) {
-            const int j = m * 128 + row;                                          // output row of [Wq; Wk; Wv; (Wg); (Wm)]
-            const int which = j / I, jj = j - which * I;
-            float *wdst = nullptr, *bdst = nullptr;
-            if (j < NB * I) {
-                wdst = (which == 0 ? a.dwq : which == 1 ? a.dwk : which == 2 ? a.dwv : a.dwg) + jj * D;
-                if (which == 3) bdst = a.dbg + jj;
-            } else if (MIX && j - NB * I < H) {
-                wdst = a.dwm + (j - NB * I) * D;
-                bdst = a.dbm + (j - NB * I);
-            }
+            float *bdst;
+            wrow(m * 128 + row, bdst);
+            __syncthreads();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {                                         // half 0: columns 0..31, half 1: 32..63
                 const int col0 = half * 32 + c * 8;
                 if (col0 > D) break;
                 float v[8];
                 tmem_ld8(tlane + cAcc + m * XW + col0, v);
-                if (wdst) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (col0 + i < D) atomicAdd(wdst + col0 + i, v[i]);
-                        else if (col0 + i == D && bdst) atomicAdd(bdst, v[i]);
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    if (col0 + i < D) stage[row * PITCH + col0 + i] = v[i];
+                    else if (col0 + i == D && bdst) atomicAdd(bdst, v[i]);
                 }
             }
+            __syncthreads();
+            flush_rows(stage, PITCH, 128, D, tid, NT, [&](int r, int c) { float *bd; float *w = wrow(m * 128 + r, bd); return w ? w + c : nullptr; });
         }
         tc_fence_before();
     }

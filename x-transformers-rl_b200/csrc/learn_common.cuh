@@ -78,6 +78,32 @@ __device__ __forceinline__ void prefetch_rows48(const float *base, int t0, int r
     for (int o = tid * 128; o < rows * D * 4; o += nthreads * 128) prefetch_l2(p + o);
 }
 
+// 16 bytes global -> shared without a register round trip (LDGSTS); ok = false writes zeros.  A thread queues all the
+// pieces of its tile row back to back and waits once: one memory round trip per tile instead of one per piece.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool ok) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Weight-gradient flush.  The accumulators live in TMEM with lane = weight row, so a thread that adds its own values to a
+// row-major [rows][ncols] gradient makes every warp instruction touch 32 different lines -- 32 L2 atomic transactions per
+// 32 values, and with 148 CTAs flushing ~19k values each the flush cost as much as the tile loop (ncu: 44 % of
+// attn_pre_bwd's samples).  Instead the rows are staged in shared memory (odd pitch: conflict-free transposed writes) and
+// added by flat index: consecutive lanes, consecutive addresses, one transaction per 128 bytes.
+// addr(r, c) -> destination of element (r, c) or nullptr.
+template <class F>
+__device__ __forceinline__ void flush_rows(const float *stage, int pitch, int nrows, int ncols, int tid, int nthreads, F addr) {
+    for (int f = tid; f < nrows * ncols; f += nthreads) {
+        const int r = f / ncols, c = f - r * ncols;
+        float *p = addr(r, c);
+        const float v = stage[r * pitch + c];
+        if (p && v != 0.f) atomicAdd(p, v);
+    }
+}
+
 __device__ __forceinline__ float warp_max_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -443,6 +443,9 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
     }
     if (!first) {                                                                // this CTA saw at least one tile
         tc_fence_after();
+        float *stage = reinterpret_cast<float *>(sH);                            // dW1 rows [192][D + 1] fp32 (see flush_rows); the H image is done with
+        static_assert(F * (D + 1) * 4 <= kBwdH + kBwdDP, "stage fits the tile images");
+        __syncthreads();
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {                                            // quarter cq: columns 16 cq .. 16 cq + 15 (48 = the bias column)
             const int col0 = cq * 16 + c * 8;
@@ -456,9 +459,9 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
             for (int j = 0; j < 8; ++j) {
                 const int i = col0 + j;
                 if (i < D) {
-                    atomicAdd(a.dW1 + row * D + i, va[j]);
-                    atomicAdd(a.dW2 + i * F + row, vc[j]);
-                    if (row < 64) { atomicAdd(a.dW1 + (128 + row) * D + i, vb[j]); atomicAdd(a.dW2 + i * F + 128 + row, vd[j]); }
+                    stage[row * (D + 1) + i] = va[j];
+                    atomicAdd(a.dW2 + i * F + row, vc[j]);                         // lanes = consecutive addresses already
+                    if (row < 64) { stage[(128 + row) * (D + 1) + i] = vb[j]; atomicAdd(a.dW2 + i * F + 128 + row, vd[j]); }
                     if (row == 64) atomicAdd(a.db2 + i, vd[j]);
                 } else if (i == D) {
                     atomicAdd(a.db1 + row, va[j]);
@@ -466,6 +469,8 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
                 }
             }
         }
+        __syncthreads();
+        flush_rows(stage, D + 1, F, D, tid, NT4, [&](int r, int c) { return a.dW1 + r * D + c; });
         tc_fence_before();
     }
     __syncthreads();

@@ -299,8 +299,11 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         }
         tc_fence_before();
     }
-    if (!first) {                                                             // flush the weight-gradient accumulators
+    if (!first) {                                                             // flush the weight-gradient accumulators (see flush_rows)
         tc_fence_after();
+        float *stage = reinterpret_cast<float *>(smem);                       // over the dY / dPRE / H images, which are done with
+        static_assert((HID > NOUT ? HID : NOUT) * ((KIN > HID ? KIN : HID) + 1) * 4 <= P::kDY + P::kDP + P::kH, "stage fits the tile images");
+        __syncthreads();
 #pragma unroll 1
         for (int c = 0; c < XW / 16; ++c) {
             const int col0 = c * 16 + half * 8;
@@ -309,11 +312,14 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
             if (row < HID) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (col0 + j < KIN) atomicAdd(a.dW1 + row * KIN + col0 + j, v[j]);
+                    if (col0 + j < KIN) stage[row * (KIN + 1) + col0 + j] = v[j];
                     else if (col0 + j == KIN) atomicAdd(a.db1 + row, v[j]);
                 }
             }
         }
+        __syncthreads();
+        flush_rows(stage, KIN + 1, HID, KIN, tid, NT, [&](int r, int c) { return a.dW1 + r * KIN + c; });
+        __syncthreads();
 #pragma unroll 1
         for (int c = 0; c < HW / 16; ++c) {
             const int col0 = c * 16 + half * 8;
@@ -322,11 +328,13 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
             if (row < NOUT) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (col0 + j < HID) atomicAdd(a.dW2 + row * HID + col0 + j, v[j]);
+                    if (col0 + j < HID) stage[row * (HID + 1) + col0 + j] = v[j];
                     else if (col0 + j == HID) atomicAdd(a.db2 + row, v[j]);
                 }
             }
         }
+        __syncthreads();
+        flush_rows(stage, HID + 1, NOUT, HID, tid, NT, [&](int r, int c) { return a.dW2 + r * HID + c; });
         tc_fence_before();
     }
     __syncthreads();
