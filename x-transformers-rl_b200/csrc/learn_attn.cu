@@ -77,6 +77,16 @@ template <int H, int NB = 3, int MIX = 0> struct Dims {
     static constexpr int XW = 64;                         // Xn image width in the backward: 48 features + ones column + pad
 };
 
+template <int H, int NB, int MIX> struct Smem {
+    using P = Dims<H, NB, MIX>;
+    static constexpr int pre_fwd = P::kWqkv + TOK * D * 2 + kRowTile + (D + P::I + 16) * 4 + 64;
+    static constexpr int pre_bwd_base = TOK * P::NQ * 2 + TOK * P::XW * 2 + P::kWqkv + kRowTile + D * 4 + 64;
+    static constexpr bool pre_bwd_ostage = pre_bwd_base + 2 * kRowTile <= 227 * 1024;
+    static constexpr int pre_bwd = pre_bwd_base + (pre_bwd_ostage ? 2 * kRowTile : 0);
+    static constexpr int post_fwd = TOK * P::I * 2 + P::kWo + 64;
+    static constexpr int post_bwd = TOK * P::I * 2 + TOK * D * 2 + P::kWo + 64;
+};
+
 // -------------------------------------------------------------------------------------------- pre fwd
 template <int H, int NB, int MIX>
 __global__ void __launch_bounds__(NT, 1) attn_pre_fwd_kernel(const Args a) {
@@ -85,12 +95,13 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_fwd_kernel(const Args a) {
     constexpr int BLK0 = (NBLK + 1) / 2;                                    // blocks of half 0; half 1 takes the rest
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem, *sXn = sW + P::kWqkv;
-    float *sG = reinterpret_cast<float *>(sXn + TOK * D * 2), *sBias = sG + D;       // bias of the gate block / mix block
+    float *sX32 = reinterpret_cast<float *>(sXn + TOK * D * 2);                      // fp32 row tile (TMA staging)
+    float *sG = sX32 + TOK * D, *sBias = sG + D;                                     // bias of the gate block / mix block
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + I + 16);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tslot, TCOLS);
     if (tid < D) sG[tid] = a.gamma[tid];
     for (int i = tid; i < I + 16; i += NT)
@@ -99,20 +110,20 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_fwd_kernel(const Args a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
-    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg + P::kWo, P::kWqkv, &bars[0]); }
-    uint32_t ph = 0;
-    bool first = true;
     const int ntiles = (a.N + TOK - 1) / TOK;
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg + P::kWo, P::kWqkv, &bars[0]);
+        if ((int)blockIdx.x < ntiles) rows_fetch(sX32, a.x, blockIdx.x, a.N, &bars[2]);
+    }
+    uint32_t ph = 0, phx = 0;
+    bool first = true;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
         const int e = t / a.n, pos = t - e * a.n;
-        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
-            const int t0 = (tile + gridDim.x) * TOK;
-            prefetch_rows48(a.x, t0, min(TOK, a.N - t0), tid, NT);
-        }
         float xr[D], own[24], mean, rstd;
-        load_row(a.x + (size_t)t * D, ok, xr);
+        mbar_wait(&bars[2], phx); phx ^= 1;
+        rows_read(sX32, row, ok, xr);
         ln_stats(xr, mean, rstd);
 #pragma unroll
         for (int i = 0; i < 24; ++i) own[i] = half ? xr[24 + i] : xr[i];
@@ -139,6 +150,7 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_fwd_kernel(const Args a) {
                                 smem_desc(sW + (c0 / 8) * 128 + s * 2 * NQ * 16, NQ * 16, 128), idesc_bf16(128, nc), s > 0);
             }
             mma_commit(&bars[1]);
+            if (tile + (int)gridDim.x < ntiles) rows_fetch(sX32, a.x, tile + gridDim.x, a.N, &bars[2]);   // every thread has read its row
         }
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
@@ -179,12 +191,15 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
     constexpr int TCOLS = 64 + P::kMT * XW > 256 ? 512 : 256;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sDQ = smem, *sXn = sDQ + TOK * NQ * 2, *sW = sXn + TOK * XW * 2;    // sDQ first: its MN-major over-read lands in sXn / sW
-    float *sG = reinterpret_cast<float *>(sW + P::kWqkv);
+    float *sX32 = reinterpret_cast<float *>(sW + P::kWqkv);                             // fp32 row tile of x (TMA staging)
+    constexpr bool OST = Smem<H, NB, MIX>::pre_bwd_ostage;                              // dx leaves through shared memory too (two buffers)
+    float *sOut = sX32 + TOK * D;
+    float *sG = sOut + (OST ? 2 * TOK * D : 0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tslot, TCOLS);
     if (tid < D) sG[tid] = a.gamma[tid];
     if (half == 0) {                                                          // constant ones column (bias gradients) + zero pad
@@ -195,13 +210,17 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
-    if (tid == 0) { mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg + P::kWo, P::kWqkv, &bars[0]); }
-    uint32_t ph = 0;
+    const int ntiles = (a.N + TOK - 1) / TOK;
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg + P::kWo, P::kWqkv, &bars[0]);
+        if ((int)blockIdx.x < ntiles) rows_fetch(sX32, a.x, blockIdx.x, a.N, &bars[2]);
+    }
+    uint32_t ph = 0, phx = 0;
     bool first = true;
+    int pend = -1, it = 0;                                                    // tile whose dx still sits in sOut[(it - 1) & 1]
     float dg_acc[24];
 #pragma unroll
     for (int i = 0; i < 24; ++i) dg_acc[i] = 0.f;
-    const int ntiles = (a.N + TOK - 1) / TOK;
     const int b0 = half ? BLK0 : 0, b1 = half ? NBLK : BLK0;
     // this thread's gradient blocks of a tile, global -> the dY image, all in flight at once (sDQ must be free: the MMAs
     // of the previous tile have completed)
@@ -225,12 +244,9 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
         const int e = t / a.n, pos = t - e * a.n;
-        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
-            const int t0 = (tile + gridDim.x) * TOK;
-            prefetch_rows48(a.x, t0, min(TOK, a.N - t0), tid, NT);
-        }
         float xr[D], own[24], mean, rstd;
-        load_row(a.x + (size_t)t * D, ok, xr);
+        mbar_wait(&bars[2], phx); phx ^= 1;
+        rows_read(sX32, row, ok, xr);
         const float4 cs = ok ? __ldg(reinterpret_cast<const float4 *>(a.cos_tab) + pos) : make_float4(1.f, 1.f, 1.f, 1.f);
         const float4 sn = ok ? __ldg(reinterpret_cast<const float4 *>(a.sin_tab) + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
         ln_stats(xr, mean, rstd);
@@ -265,6 +281,7 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
+            if (OST && pend >= 0) { bulk_wait_read(); rows_store(a.dx, sOut + ((it - 1) & 1) * TOK * D, pend, a.N); }
             if (first) mbar_wait(&bars[0], 0);
             tc_fence_after();
 #pragma unroll
@@ -280,6 +297,7 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
                                 idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
             }
             mma_commit(&bars[1]);
+            if (tile + (int)gridDim.x < ntiles) rows_fetch(sX32, a.x, tile + gridDim.x, a.N, &bars[2]);   // every thread has read its row
         }
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
@@ -305,13 +323,19 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
                 dg_acc[i] = fmaf(dxi, own[i], dg_acc[i]);
                 o[i] = rstd * (dxi * sG[half * 24 + i] - c1 - own[i] * c2);
             }
-            if (ok) {
-                float4 *dst = reinterpret_cast<float4 *>(a.dx + (size_t)t * D + half * 24);
+            if (OST || ok) {
+                float4 *dst = reinterpret_cast<float4 *>(OST ? sOut + (it & 1) * TOK * D + row * D + half * 24 : a.dx + (size_t)t * D + half * 24);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             }
         }
+        pend = tile; ++it;
         tc_fence_before();
+    }
+    if (OST && pend >= 0) {                                                    // the last tile's dx
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) rows_store(a.dx, sOut + ((it - 1) & 1) * TOK * D, pend, a.N);
     }
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
@@ -354,6 +378,7 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         }
         tc_fence_before();
     }
+    if (OST && tid == 0) bulk_wait_all();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, TCOLS);
 }
@@ -534,13 +559,6 @@ __global__ void attn_pack_kernel(const float *__restrict__ wq, const float *__re
     }
 }
 
-template <int H, int NB, int MIX> struct Smem {
-    using P = Dims<H, NB, MIX>;
-    static constexpr int pre_fwd = P::kWqkv + TOK * D * 2 + (D + P::I + 16) * 4 + 64;
-    static constexpr int pre_bwd = TOK * P::NQ * 2 + TOK * P::XW * 2 + P::kWqkv + D * 4 + 64;
-    static constexpr int post_fwd = TOK * P::I * 2 + P::kWo + 64;
-    static constexpr int post_bwd = TOK * P::I * 2 + TOK * D * 2 + P::kWo + 64;
-};
 
 static int fill(const xtrl_attn_io *io, int32_t b, int32_t n, Args &a) {
     XTRL_REQUIRE((int64_t)b * n <= (int64_t)1 << 24, XTRL_E_BADARG, "xtrl_attn_*: at most 2^24 tokens per call");
@@ -630,6 +648,7 @@ extern "C" int xtrl_attn_pre_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, i
     if ((int64_t)b * n == 0) return XTRL_OK;
     XTRL_REQUIRE(io->x && io->ln_gamma && io->cos_tab && io->sin_tab && io->w_img && io->q && io->k && io->v && (!gate || io->gate_bias) &&
                  (!mix || io->mix_bias), XTRL_E_BADARG, "xtrl_attn_pre_fwd: null pointer");
+    XTRL_REQUIRE(((uintptr_t)io->x & 15) == 0, XTRL_E_BADARG, "xtrl_attn_pre_fwd: x must be 16-byte aligned (row tiles move by bulk copy)");
     Args a;
     if (int rc = fill(io, b, n, a)) return rc;
 #define CALL(H, NB, MIX) return launch(attn_pre_fwd_kernel<H, NB, MIX>, "attn_pre_fwd_kernel", Smem<H, NB, MIX>::pre_fwd, 1, a, stream)
@@ -646,6 +665,7 @@ extern "C" int xtrl_attn_pre_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, i
     XTRL_REQUIRE(io->x && io->ln_gamma && io->cos_tab && io->sin_tab && io->w_img && io->dq && io->dk && io->dv && io->dx &&
                  io->d_ln_gamma && io->d_wq && io->d_wk && io->d_wv && (!gate || (io->d_wg && io->d_bg)) && (!mix || (io->d_wm && io->d_bm)),
                  XTRL_E_BADARG, "xtrl_attn_pre_bwd: null pointer");
+    XTRL_REQUIRE((((uintptr_t)io->x | (uintptr_t)io->dx) & 15) == 0, XTRL_E_BADARG, "xtrl_attn_pre_bwd: x and dx must be 16-byte aligned (row tiles move by bulk copy)");
     Args a;
     if (int rc = fill(io, b, n, a)) return rc;
 #define CALL(H, NB, MIX) return launch(attn_pre_bwd_kernel<H, NB, MIX>, "attn_pre_bwd_kernel", Smem<H, NB, MIX>::pre_bwd, 1, a, stream)

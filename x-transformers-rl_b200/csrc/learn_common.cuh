@@ -88,6 +88,30 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, boo
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Row tiles by TMA.  The 128 rows of a tile of a row-major fp32 [N][48] tensor are 24 KB contiguous in global memory, so a
+// tile moves by ONE bulk copy issued by one thread instead of 12 row-strided 16-byte loads per thread (every warp
+// instruction of those touches 32 lines: ~3000 L1 requests per tile and operand).  The fetch of tile i+1 is issued as soon
+// as every thread has read tile i out of the staging buffer, so it lands under the MMAs and the epilogue of tile i.
+constexpr int kRowTile = TOK * D * 4;
+__device__ __forceinline__ void rows_fetch(float *sX, const float *x, int tile, int N, uint64_t *bar) {        // one thread
+    const int t0 = tile * TOK, rows = min(TOK, N - t0);
+    const uint32_t bytes = (uint32_t)rows * D * 4;
+    umma::mbar_expect_tx(bar, bytes);
+    umma::bulk_g2s(sX, x + (size_t)t0 * D, bytes, bar);
+}
+__device__ __forceinline__ void rows_read(const float *sX, int row, bool ok, float (&xr)[D]) {                 // this thread's row
+    const float4 *p = reinterpret_cast<const float4 *>(sX + row * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+        const float4 v = ok ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void rows_store(float *dst, const float *sOut, int tile, int N) {                   // one thread
+    const int t0 = tile * TOK, rows = min(TOK, N - t0);
+    umma::bulk_s2g(dst + (size_t)t0 * D, sOut, (uint32_t)rows * D * 4);
+}
+
 // Weight-gradient flush.  The accumulators live in TMEM with lane = weight row, so a thread that adds its own values to a
 // row-major [rows][ncols] gradient makes every warp instruction touch 32 different lines -- 32 L2 atomic transactions per
 // 32 values, and with 148 CTAs flushing ~19k values each the flush cost as much as the tile loop (ncu: 44 % of
