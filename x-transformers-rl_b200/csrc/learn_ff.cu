@@ -137,11 +137,16 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
     unsigned char *sW1 = smem, *sW2 = sW1 + kW1, *sXn = sW2 + kW2, *sH = sXn + TOK * D * 2;
     float *sB1 = reinterpret_cast<float *>(sH + TOK * F * 2), *sB2 = sB1 + F, *sG = sB2 + D;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 3);
+    // fp32 row tiles move by bulk copy (rows_fetch / rows_store) through the two halves of the H image, which is idle from
+    // the end of one tile's second GEMM to the first epilogue of the next: x of the next tile lands in the lower half, y of
+    // this tile leaves from the upper half
+    float *sXs = reinterpret_cast<float *>(sH), *sYs = sXs + TOK * D;
+    static_assert(2 * kRowTile <= TOK * F * 2, "row-tile staging fits the H image");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
 
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tslot, 256);
     for (int i = tid; i < F; i += NT) sB1[i] = a.b1[i];
     if (tid < D) { sB2[tid] = a.b2[tid]; sG[tid] = a.gamma[tid]; }
@@ -149,20 +154,21 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
-    if (tid == 0) { mbar_expect_tx(&bars[0], kW1 + kW2); bulk_g2s(sW1, a.wimg, kW1 + kW2, &bars[0]); }
-    const uint32_t key = fold_key(a.rng_step, a.rng_key);
-    uint32_t ph = 0;
-    bool first = true;
     const int ntiles = (a.N + TOK - 1) / TOK;
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], kW1 + kW2); bulk_g2s(sW1, a.wimg, kW1 + kW2, &bars[0]);
+        if ((int)blockIdx.x < ntiles) rows_fetch(sXs, a.x, blockIdx.x, a.N, &bars[2]);
+    }
+    const uint32_t key = fold_key(a.rng_step, a.rng_key);
+    uint32_t ph = 0, phx = 0;
+    int pend = -1;                                                               // tile whose y still sits in sYs
+    bool first = true;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
-        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
-            const int t0 = (tile + gridDim.x) * TOK;
-            prefetch_rows48(a.x, t0, min(TOK, a.N - t0), tid, NT);
-        }
         float xr[D];
-        load_row(a.x + (size_t)t * D, ok, xr);
+        mbar_wait(&bars[2], phx); phx ^= 1;
+        rows_read(sXs, row, ok, xr);
         float mean, rstd, own[24];
         ln_stats(xr, mean, rstd);
 #pragma unroll
@@ -177,12 +183,14 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
+            if (pend >= 0) rows_store(a.y, sYs, pend, a.N);
             if (first) mbar_wait(&bars[0], 0);
             tc_fence_after();
 #pragma unroll
             for (int s = 0; s < D / 16; ++s)
                 mma_bf16_ss(tbase, smem_desc(sXn + s * 2 * kCore, kCore, 128), smem_desc(sW1 + s * 2 * F * 16, F * 16, 128),
                             idesc_bf16(128, F), s > 0);
+            if (pend >= 0) bulk_wait_read();                                     // the epilogue below overwrites sYs: commit only once it is read
             mma_commit(&bars[1]);
         }
         first = false;
@@ -218,19 +226,26 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
         }
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
+        if (tid == 0 && tile + (int)gridDim.x < ntiles) rows_fetch(sXs, a.x, tile + gridDim.x, a.N, &bars[2]);   // the H image is idle now
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float v[8];
             tmem_ld8(tlane + F + half * 24 + c * 8, v);
-            if (ok) {
-                float4 *dst = reinterpret_cast<float4 *>(a.y + (size_t)t * D + half * 24 + c * 8);
+            {
+                float4 *dst = reinterpret_cast<float4 *>(sYs + row * D + half * 24 + c * 8);
                 const int f = half * 24 + c * 8;
                 const float *o = own + c * 8;
                 dst[0] = make_float4(v[0] + sB2[f] + o[0], v[1] + sB2[f + 1] + o[1], v[2] + sB2[f + 2] + o[2], v[3] + sB2[f + 3] + o[3]);
                 dst[1] = make_float4(v[4] + sB2[f + 4] + o[4], v[5] + sB2[f + 5] + o[5], v[6] + sB2[f + 6] + o[6], v[7] + sB2[f + 7] + o[7]);
             }
         }
+        pend = tile;
         tc_fence_before();
+    }
+    if (pend >= 0) {                                                             // the last tile's y
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { rows_store(a.y, sYs, pend, a.N); bulk_wait_all(); }
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 256);
@@ -241,7 +256,7 @@ __global__ void __launch_bounds__(NT, 2) ff_fwd_kernel(const Args a) {
 // dPRE images (64 real + 64 beyond the image); what follows each image is more shared memory of this
 // CTA, and the accumulator rows those bytes feed (>= 64, resp. > 64) are never read.
 constexpr int kBwdH = TOK * HW * 2, kBwdDP = TOK * F * 2, kBwdX = TOK * XW * 2;
-constexpr int kBwdSmem = kBwdH + kBwdDP + 2 * kBwdX + kW1 + kW2 + (F + D) * 4 + 64;
+constexpr int kBwdSmem = kBwdH + kBwdDP + 2 * kBwdX + kW1 + kW2 + 2 * kRowTile + (F + D) * 4 + 64;
 
 // 512 threads: thread (row, cq) owns a QUARTER of the row's columns in every epilogue (48 of the 192 hidden units; 16 of the
 // 48 features for cq < 3).  The epilogues -- GELU, its derivative and the dropout hash on 128 x 192 values per tile -- are the
@@ -253,14 +268,15 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sH = smem, *sDP = sH + kBwdH, *sXn = sDP + kBwdDP, *sDY = sXn + kBwdX;
     unsigned char *sW1 = sDY + kBwdX, *sW2 = sW1 + kW1;
-    float *sB1 = reinterpret_cast<float *>(sW2 + kW2), *sG = sB1 + F;
+    float *sX32 = reinterpret_cast<float *>(sW2 + kW2);                          // two fp32 row tiles of x (TMA staging, see rows_fetch):
+    float *sB1 = sX32 + 2 * TOK * D, *sG = sB1 + F;                              // a tile's rows are read at its start and again at its end
     uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     constexpr uint32_t cPre = 0, cDxn = 192, cA = 256, cB = 320, cC = 384, cD = 448;
 
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tslot, 512);
     for (int i = tid; i < F; i += NT4) sB1[i] = a.b1[i];
     if (tid < D) sG[tid] = a.gamma[tid];
@@ -274,26 +290,31 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
-    if (tid == 0) { mbar_expect_tx(&bars[0], kW1 + kW2); bulk_g2s(sW1, a.wimg, kW1 + kW2, &bars[0]); }
+    const int ntiles = (a.N + TOK - 1) / TOK;
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], kW1 + kW2); bulk_g2s(sW1, a.wimg, kW1 + kW2, &bars[0]);
+        if ((int)blockIdx.x < ntiles) rows_fetch(sX32, a.x, blockIdx.x, a.N, &bars[2]);
+    }
     const uint32_t key = fold_key(a.rng_step, a.rng_key);
-    uint32_t ph = 0;
+    uint32_t ph = 0, phx = 0;
+    int it = 0;
     bool first = true;
     float dg_acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) dg_acc[i] = 0.f;
-    const int ntiles = (a.N + TOK - 1) / TOK;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int t = tile * TOK + row;
         const bool ok = t < a.N;
-        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's rows -> L2
+        const float *sx = sX32 + (it & 1) * TOK * D;
+        if (tile + (int)gridDim.x < ntiles) {                                    // next tile's dy rows -> L2
             const int t0 = (tile + gridDim.x) * TOK, nr = min(TOK, a.N - t0);
-            prefetch_rows48(a.x, t0, nr, tid, NT4);
             prefetch_rows48(a.dy, t0, nr, tid, NT4);
         }
         float mean, rstd, dyr[16];
         {
             float xr[D];
-            load_row(a.x + (size_t)t * D, ok, xr);
+            mbar_wait(&bars[2], phx); phx ^= 1;
+            rows_read(sx, row, ok, xr);
             ln_stats(xr, mean, rstd);
             if (cq < 3) {                                                        // my 16 features of the Xn and dY images
 #pragma unroll
@@ -328,6 +349,8 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
                 mma_bf16_ss(tbase + cPre, smem_desc(sXn + s * 2 * kCore, kCore, 128), smem_desc(sW1 + s * 2 * F * 16, F * 16, 128),
                             idesc_bf16(128, F), s > 0);
             mma_commit(&bars[1]);
+            // the other x buffer was last read at the end of the previous tile, which every thread has left
+            if (tile + (int)gridDim.x < ntiles) rows_fetch(sX32 + ((it + 1) & 1) * TOK * D, a.x, tile + gridDim.x, a.N, &bars[2]);
         }
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
@@ -408,8 +431,8 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
             for (int c = 0; c < 6; ++c) {                                        // the row sums need all 48 features: stream them
                 float v[8];
                 tmem_ld8(tlane + cDxn + c * 8, v);
-                const float4 x0 = ok ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)t * D + c * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 x1 = ok ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)t * D + c * 8) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 x0 = ok ? *(reinterpret_cast<const float4 *>(sx + row * D + c * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 x1 = ok ? *(reinterpret_cast<const float4 *>(sx + row * D + c * 8) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -528,6 +551,7 @@ extern "C" int xtrl_ff_fwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t
     XTRL_REQUIRE(io && N >= 0, XTRL_E_BADARG, "xtrl_ff_fwd: bad arguments");
     if (N == 0) return XTRL_OK;
     XTRL_REQUIRE(io->x && io->ln_gamma && io->b1 && io->b2 && io->w_img && io->y, XTRL_E_BADARG, "xtrl_ff_fwd: null pointer");
+    XTRL_REQUIRE((((uintptr_t)io->x | (uintptr_t)io->y) & 15) == 0, XTRL_E_BADARG, "xtrl_ff_fwd: x and y must be 16-byte aligned (row tiles move by bulk copy)");
     Args a;
     if (int rc = fill(io, N, a)) return rc;
     static bool attr = false;
@@ -546,6 +570,7 @@ extern "C" int xtrl_ff_bwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t
     if (N == 0) return XTRL_OK;
     XTRL_REQUIRE(io->x && io->dy && io->ln_gamma && io->b1 && io->w_img && io->dx && io->d_ln_gamma && io->d_w1 && io->d_b1 &&
                  io->d_w2 && io->d_b2, XTRL_E_BADARG, "xtrl_ff_bwd: null pointer");
+    XTRL_REQUIRE(((uintptr_t)io->x & 15) == 0, XTRL_E_BADARG, "xtrl_ff_bwd: x must be 16-byte aligned (row tiles move by bulk copy)");
     Args a;
     if (int rc = fill(io, N, a)) return rc;
     static bool attr = false;
