@@ -44,7 +44,23 @@ struct Args {
     uint32_t rng_key, drop_add4;              // (128 - threshold) replicated in 4 bytes, see keep4(); 0 = no dropout
     float drop_scale, drop_log2scale, scale;
     int n;
+    int ahead;                                // CTAs resident at once: head bh + ahead is the one this SM runs next
 };
+
+// Pull the rows of the head this SM will work on next into L2 while this CTA runs (CTAs are handed out in blockIdx order, one
+// wave = `ahead` CTAs).  The prologue of a CTA is two dependent rounds of global loads that nothing overlaps -- with one CTA
+// per SM (the backward) they are pure dead time, 13.8 waves deep -- so they should at least hit L2 instead of DRAM.
+__device__ __forceinline__ void warm_next_head(const Args &a, int bh_next, int nbh, int tid, int nthreads, bool bwd) {
+    if (bh_next >= nbh) return;
+    const size_t off = (size_t)bh_next * a.n * 16;
+    const int lines = (a.n * 16 * 2 + 127) >> 7, na = bwd ? 5 : 3;
+    for (int i = tid; i < lines * na; i += nthreads) {
+        const int m = i / lines, l = i - m * lines;
+        const __nv_bfloat16 *p = m == 0 ? a.q : m == 1 ? a.k : m == 2 ? a.v : m == 3 ? a.d_o : a.o;
+        learn::prefetch_l2(reinterpret_cast<const char *>(p + off) + l * 128);
+    }
+    if (bwd) for (int i = tid; i < (a.n * 4 + 127) >> 7; i += nthreads) learn::prefetch_l2(reinterpret_cast<const char *>(a.lse + (size_t)bh_next * a.n) + i * 128);
+}
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -905,6 +921,7 @@ __global__ void __launch_bounds__((16 / CQ + 2) * 32, 1) attn_core_bwd2_kernel(c
         sStat[(r >> 1) * 4 + (r & 1)] = a.drop_log2scale - L;
         sStat[(r >> 1) * 4 + 2 + (r & 1)] = -d / a.drop_scale;
     }
+    warm_next_head(a, bh + a.ahead, gridDim.x, tid, NTHK, true);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -1048,7 +1065,7 @@ static int fill(const xtrl_attn_core_io *io, int32_t n, int32_t dim_head, Args &
     a.drop_add4 = thr ? (128u - thr) * 0x01010101u : 0u;
     a.drop_scale = 1.f / (1.f - (float)thr / 128.f);
     a.drop_log2scale = log2f(a.drop_scale);
-    a.scale = io->scale; a.n = n;
+    a.scale = io->scale; a.n = n; a.ahead = num_sms();
     return XTRL_OK;
 }
 

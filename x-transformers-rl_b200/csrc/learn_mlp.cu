@@ -200,19 +200,30 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
             if (a.gy) { const char *g = reinterpret_cast<const char *>(a.gy + (size_t)t0 * a.out_cols); for (int o = tid * 128; o < nr * a.out_cols * 2; o += NT * 128) prefetch_l2(g + o); }
         }
         build_x<P::NSRC>(sX, a, t, ok, row, half);
-#pragma unroll 1
-        for (int c = 0; c < NOUT / 16; ++c) {                                  // dY image (zero beyond out_cols and beyond N)
-            const int col0 = c * 16 + half * 8;
-            float v[8];
-            const __nv_bfloat16 *src = a.gy + (size_t)t * a.out_cols + col0;
-            if (ok && col0 + 8 <= a.out_cols && (a.out_cols & 3) == 0) {        // rows are 8-byte aligned: two 8-byte loads
-                const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(src)), hi = __ldg(reinterpret_cast<const uint2 *>(src) + 1);
-                unpack8(make_uint4(lo.x, lo.y, hi.x, hi.y), v);
-            } else {
+        {                                                                      // dY image (zero beyond out_cols and beyond N)
+            // all of the row's pieces are requested before the first is used: one memory round trip, not NOUT / 16 of them
+            const bool fast = (a.out_cols & 3) == 0;                          // rows are 8-byte aligned: two 8-byte loads per piece
+            uint2 lo[NOUT / 16], hi[NOUT / 16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = (ok && col0 + j < a.out_cols) ? __bfloat162float(src[j]) : 0.f;
+            for (int c = 0; c < NOUT / 16; ++c) {
+                const int col0 = c * 16 + half * 8;
+                const __nv_bfloat16 *src = a.gy + (size_t)t * a.out_cols + col0;
+                lo[c] = hi[c] = make_uint2(0u, 0u);
+                if (ok && fast && col0 + 8 <= a.out_cols) { lo[c] = __ldg(reinterpret_cast<const uint2 *>(src)); hi[c] = __ldg(reinterpret_cast<const uint2 *>(src) + 1); }
             }
-            put8(sDY, row, col0 / 8, v);
+#pragma unroll
+            for (int c = 0; c < NOUT / 16; ++c) {
+                const int col0 = c * 16 + half * 8;
+                float v[8];
+                if (fast && (col0 + 8 <= a.out_cols || !ok || col0 >= a.out_cols)) {
+                    unpack8(make_uint4(lo[c].x, lo[c].y, hi[c].x, hi[c].y), v);
+                } else {
+                    const __nv_bfloat16 *src = a.gy + (size_t)t * a.out_cols + col0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = (ok && col0 + j < a.out_cols) ? __bfloat162float(src[j]) : 0.f;
+                }
+                put8(sDY, row, col0 / 8, v);
+            }
         }
         fence_proxy_async();
         __syncthreads();
