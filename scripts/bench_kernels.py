@@ -10,7 +10,22 @@ ap = argparse.ArgumentParser(); ap.add_argument('--iters', type=int, default=10)
 a = ap.parse_args()
 dev = 'cuda'
 peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.
-flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+flush_buf = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+_flush_sink = torch.zeros(1, dtype=torch.int64, device=dev)
+
+
+_FLUSH_WRITE = os.environ.get('XTRL_FLUSH', '') == 'write'
+
+
+def flush_l2():
+    """replace the contents of L2 by reading 256 MB.  A write (fill_) would leave L2 full of dirty lines, and the timed kernel
+    would then pay for their write-back on top of its own traffic (up to 126 MB, ~20 us at full HBM speed -- more than the
+    small kernels here take).  XTRL_FLUSH=write restores the old behaviour for comparison."""
+    if _FLUSH_WRITE:
+        flush_l2()
+    else:
+        torch.sum(flush_buf.view(torch.int64), dim=0, keepdim=True, out=_flush_sink)
+
 
 
 def timeit(fn, iters=a.iters):
@@ -30,10 +45,31 @@ def timeit(fn, iters=a.iters):
         fn()
     ms = []
     for _ in range(iters):
-        flush_buf.fill_(1)
+        flush_l2()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); graph.replay(); e1.record(); torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+def timeit_rot(fns, iters=a.iters):
+    """per-launch device time of small kernels: len(fns) launches on DIFFERENT buffers captured back to back in one graph, so
+    the ~10 us a graph launch costs between the two events is shared by all of them; the buffer sets together exceed L2 (and
+    L2 is flushed before every replay), so every launch still reads its inputs from DRAM."""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for f in fns:
+            f()
+    ms = []
+    for _ in range(iters):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); graph.replay(); e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1) / len(fns))
     ms.sort()
     return ms[len(ms) // 2]
 
@@ -53,6 +89,12 @@ if not a.only or 'gae' in a.only:
     rt, vt, bt = r.T.contiguous(), v.T.contiguous(), bd.T.contiguous()
     outt = torch.empty_like(rt)
     report('gae_time_major (T=500,B=4096)', 13 * E * T, timeit(lambda: ops.gae(rt, vt, bt, time_major=True, out=outt)), unit_bytes=13)
+    sets = [(torch.randn(T, E, device=dev, generator=g), torch.randn(T, E, device=dev, generator=g), torch.rand(T, E, device=dev, generator=g) < 0.02,
+             torch.empty(T, E, device=dev)) for _ in range(8)]
+    report('gae_time_major (T=500,B=4096), 8 launches on 8 buffer sets per graph', 13 * E * T,
+           timeit_rot([(lambda s_=s_: ops.gae(s_[0], s_[1], s_[2], time_major=True, out=s_[3])) for s_ in sets]), unit_bytes=13,
+           note='the single-launch line above includes the fixed cost of launching a one-node graph')
+    del sets
     E8 = 8 * E                                              # c5 total: 32768 episodes (213 MB)
     r8, v8 = torch.randn(T, E8, device=dev, generator=g), torch.randn(T, E8, device=dev, generator=g)
     b8 = torch.rand(T, E8, device=dev, generator=g) < 0.02
