@@ -271,12 +271,14 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
     float *sX32 = reinterpret_cast<float *>(sW2 + kW2);                          // two fp32 row tiles of x (TMA staging, see rows_fetch):
     float *sB1 = sX32 + 2 * TOK * D, *sG = sB1 + F;                              // a tile's rows are read at its start and again at its end
     uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 3);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     constexpr uint32_t cPre = 0, cDxn = 192, cA = 256, cB = 320, cC = 384, cD = 448;
 
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
+    // bars: 0 weights, 1 the GEMMs the next epilogue waits for, 2 x tile landed, 3 the weight-gradient GEMMs of a tile (the
+    // last readers of its images: they run under the LayerNorm backward and the next tile's row statistics)
+    if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tslot, 512);
     for (int i = tid; i < F; i += NT4) sB1[i] = a.b1[i];
     if (tid < D) sG[tid] = a.gamma[tid];
@@ -322,6 +324,9 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
                     const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(a.dy + (size_t)t * D + cq * 16) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                     dyr[4 * i] = v.x; dyr[4 * i + 1] = v.y; dyr[4 * i + 2] = v.z; dyr[4 * i + 3] = v.w;
                 }
+            }
+            if (it > 0) { mbar_wait(&bars[3], (it - 1) & 1); tc_fence_after(); }   // the previous tile's images are free
+            if (cq < 3) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     float v[8], w[8];
@@ -382,12 +387,6 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
             for (int s = 0; s < D / 16; ++s)                                     // dH = dY * W2 (W2 image read MN-major)
                 mma_bf16_ss(tbase + cPre, smem_desc(sDY + s * 2 * kCore, kCore, 128), smem_desc(sW2 + s * 256, 128, D * 16),
                             idesc_bf16(128, F) | kIdB, s > 0);
-#pragma unroll
-            for (int s = 0; s < TOK / 16; ++s) {                                 // dW2^T | db2 += [H|1]^T * dY
-                const uint64_t bd = smem_desc(sDY + s * 256, 128, kCore);
-                mma_bf16_ss(tbase + cC, smem_desc(sH + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
-                mma_bf16_ss(tbase + cD, smem_desc(sH + 16 * kCore + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
-            }
             mma_commit(&bars[1]);
         }
         mbar_wait(&bars[1], ph); ph ^= 1;
@@ -414,13 +413,20 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
             for (int s = 0; s < F / 16; ++s)                                     // dXn = dPRE * W1 (W1 image read MN-major)
                 mma_bf16_ss(tbase + cDxn, smem_desc(sDP + s * 2 * kCore, kCore, 128), smem_desc(sW1 + s * 256, 128, F * 16),
                             idesc_bf16(128, D) | kIdB, s > 0);
+            mma_commit(&bars[1]);                                                // the LayerNorm backward can start
+#pragma unroll
+            for (int s = 0; s < TOK / 16; ++s) {                                 // dW2^T | db2 += [H|1]^T * dY
+                const uint64_t bd = smem_desc(sDY + s * 256, 128, kCore);
+                mma_bf16_ss(tbase + cC, smem_desc(sH + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
+                mma_bf16_ss(tbase + cD, smem_desc(sH + 16 * kCore + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
+            }
 #pragma unroll
             for (int s = 0; s < TOK / 16; ++s) {                                 // dW1 | db1 += dPRE^T * [Xn|1]
                 const uint64_t bd = smem_desc(sXn + s * 256, 128, kCore);
                 mma_bf16_ss(tbase + cA, smem_desc(sDP + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
                 mma_bf16_ss(tbase + cB, smem_desc(sDP + 16 * kCore + s * 256, 128, kCore), bd, idesc_bf16(128, XW) | kIdA | kIdB, !first || s > 0);
             }
-            mma_commit(&bars[1]);
+            mma_commit(&bars[3]);
         }
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
@@ -465,6 +471,7 @@ __global__ void __launch_bounds__(NT4, 1) ff_bwd_kernel(const Args a) {
         }
     }
     if (!first) {                                                                // this CTA saw at least one tile
+        mbar_wait(&bars[3], (it - 1) & 1);                                       // the last weight-gradient GEMMs
         tc_fence_after();
         float *stage = reinterpret_cast<float *>(sH);                            // dW1 rows [192][D + 1] fp32 (see flush_rows); the H image is done with
         static_assert(F * (D + 1) * 4 <= kBwdH + kBwdDP, "stage fits the tile images");
