@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(NT, 2) mlp_fwd_kernel(const Args a) {
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < HID / 16; ++c) {                                  // 8-column pieces: this thread takes every other one
             float v[8];
             const int col0 = c * 16 + half * 8;
@@ -135,12 +135,16 @@ __global__ void __launch_bounds__(NT, 2) mlp_fwd_kernel(const Args a) {
         }
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < NOUT / 16; ++c) {
             float v[8];
             const int col0 = c * 16 + half * 8;
             tmem_ld8(tlane + HID + col0, v);
-            if (ok) {
+            if (ok && (a.out_cols & 7) == 0 && col0 + 8 <= a.out_cols) {      // 16-byte aligned piece: one store
+                const float *bb = sB2 + col0;
+                *reinterpret_cast<uint4 *>(a.y + (size_t)t * a.out_cols + col0) =
+                    make_uint4(pack2(v[0] + bb[0], v[1] + bb[1]), pack2(v[2] + bb[2], v[3] + bb[3]), pack2(v[4] + bb[4], v[5] + bb[5]), pack2(v[6] + bb[6], v[7] + bb[7]));
+            } else if (ok) {
                 __nv_bfloat16 *dst = a.y + (size_t)t * a.out_cols + col0;
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         }
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < HID / 16; ++c) {                                  // H and act' (parked in dPRE's slot)
             const int col0 = c * 16 + half * 8;
             float v[8], d[8];
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         }
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < HID / 16; ++c) {                                  // dPRE = dH . act'
             const int col0 = c * 16 + half * 8;
             float v[8], d[8];
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < KIN / 16; ++c) {                                  // dX, 8 columns at a time, to the source it belongs to
             const int col0 = c * 16 + half * 8, s = col0 / D, off = col0 - s * D;
             float v[8];
