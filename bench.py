@@ -20,7 +20,8 @@ Workloads (BASELINE.json configs):
   c5  4096 envs per GPU, depth 6 heads 8 (32768 envs on 8 GPUs)
   c1  README Sim: S5 A2 T10 depth 1 heads 4, 64 envs
 Multi-GPU: episodes shard across ranks with no data-path collective during rollouts (weak scaling:
-per-GPU envs fixed); the learn leg all-reduces one flat gradient buffer per optimiser step.
+per-GPU envs fixed); the learn leg sums one flat gradient buffer over the ranks per optimiser step -- inside the optimiser
+kernel, over CUDA-IPC peer memory (NVLink / NVSwitch), or by NCCL all_reduce where that cannot be set up (`learn.collective`).
 """
 from __future__ import annotations
 
@@ -403,8 +404,12 @@ def run_b200(args, w):
             ms_per_minibatch=lms / max(n_opt, 1), dtype=args.learn_dtype, fused_sequence_model=fused,
             clocks=lclocks.summary(),
             kernel_share=dict(fwd_bwd_graph=fb_ms / lms, optimizer=opt_ms / lms,
-                              note='CUDA events around every graph replay (prep + sequence model + loss + backward + all-reduce) and '
-                                   'every optimiser launch inside the timed calls; the rest is GAE, the minibatch gathers and host gaps'),
+                              note='CUDA events around every graph replay (prep + sequence model + loss + backward) and every optimiser '
+                                   'launch (with the gradient exchange, see collective) inside the timed calls; the rest is GAE, the '
+                                   'minibatch gathers and host gaps'),
+            collective=('none (one GPU)' if world == 1 else
+                        'fused: the optimiser kernel sums the ranks\' gradient buffers over CUDA-IPC peer memory (xtrl_adopt_atan2_step_peers)'
+                        if agent._peers is not None else 'torch.distributed.all_reduce (NCCL) before the optimiser launch'),
             roofline=dict(bound='tensor', achieved=per_gpu * fl / 1e12, peak=tf_peak, unit='TFLOP/s', frac=per_gpu * fl / 1e12 / tf_peak,
                           flops_per_timestep=fl, traffic=None,
                           peak_source='MEASURED_PEAKS.json bf16_tflops_sustained (of measured; a kernel timed inside a long step)' if peaks else 'fallback',
@@ -414,8 +419,7 @@ def run_b200(args, w):
                                                  'the attention core is instruction-bound, neither pipe')),
             note='bf16 class (default): sequence-model layers, final norm and the head MLPs = libxtrl tcgen05 kernels (LN+QKV+rotary, '
                  'causal attention core with dropout, out-proj+mask+residual, LN+FF+GELU+dropout+residual, heads; fwd and bwd, '
-                 'SURVEY 8f-1); GAE, fused loss fwd+bwd, one-launch clip+AdoptAtan2+EMA = libxtrl kernels; the flat-gradient '
-                 'all-reduce is the last node of the captured minibatch graph')
+                 'SURVEY 8f-1); GAE, fused loss fwd+bwd, one-launch (gradient exchange +) clip+AdoptAtan2+EMA = libxtrl kernels')
         result['learn_value'] = lval
         if world > 1:                                      # replicas must stay bit-identical (the driver's test box has one GPU)
             st = torch.cat([agent.model.flat_params, agent.ema_params, agent.opt_m, agent.opt_v, agent.rsnorm.running_mean,

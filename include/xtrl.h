@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define XTRL_ABI_VERSION 8
+#define XTRL_ABI_VERSION 9
 
 #define XTRL_OK            0
 #define XTRL_E_BADARG     -1   /* null pointer, negative size, inconsistent shapes            */
@@ -267,6 +267,36 @@ int xtrl_adopt_atan2_step(float *params, const float *grads, float *m, float *v,
                           const xtrl_opt_cfg *cfg, double *workspace, float *grad_norm_out,
                           void *stream);
 
+/* The same step with the data-parallel gradient all-reduce fused in as its first phase -- replaces DDP's gradient
+ * all-reduce inside accelerator.backward (x_transformers_rl.py:885, :981) together with the optimiser (:987-991).
+ * Every rank of the node keeps [gradients | extra sums] (n_reduce floats) followed by 2*world uint32 flags in a block from
+ * xtrl_peer_alloc; the other ranks map it with xtrl_peer_open (CUDA IPC, NVLink / NVSwitch peer access).  The kernel
+ * waits until every rank's block is complete, sums the `world` buffers in rank order into `reduced` (identical bits on
+ * every rank), runs clip + AdoptAtan2 + EMA on reduced[0:n] * cfg->grad_scale, and does not return before every peer has
+ * finished reading this rank's buffer (the caller may overwrite it afterwards).  All ranks must call it the same number
+ * of times with epoch = 1, 2, 3, ...; a rank that waits longer than timeout_s (<= 0: 10 s) sets *status = 1.           */
+typedef struct xtrl_peer_ctx {
+    const float *const *grads;      /* HOST array [world]: every rank's gradient block as mapped on this device;
+                                       grads[rank] == this rank's own `grads` argument                             */
+    uint32_t *const *flags;         /* HOST array [world]: every rank's flag words (ready[world] | done[world])  */
+    float *reduced;                 /* [n_reduce] fp32 on this device: receives the sum over ranks                */
+    int32_t *status;                /* device int, 0 = ok                                                         */
+    int64_t n_reduce;               /* >= n: elements summed (the optimiser consumes the first n)                 */
+    int32_t rank, world;            /* world <= 8 (one NVSwitch node)                                             */
+    uint32_t epoch;
+    float timeout_s;
+} xtrl_peer_ctx;
+
+int xtrl_adopt_atan2_step_peers(float *params, const float *grads, float *m, float *v, float *param_init,
+                                float *ema, const int64_t *seg_offsets, int32_t num_tensors, int64_t n,
+                                const xtrl_opt_cfg *cfg, double *workspace, float *grad_norm_out,
+                                const xtrl_peer_ctx *peers, void *stream);
+/* peer memory: a zero-filled cudaMalloc block + its 64-byte IPC handle; map / unmap a peer's block; free one's own */
+int xtrl_peer_alloc(int64_t bytes, void **ptr, void *handle64);
+int xtrl_peer_open(const void *handle64, void **ptr);
+int xtrl_peer_close(void *ptr);
+int xtrl_peer_free(void *ptr);
+
 /* ------------------------------------------------------------------------------------------
  * (6) learn-side sequence model, fused sub-layers on tcgen05 -- replace the
  *     teacher-forced Decoder pass inside Agent.learn (x_transformers_rl.py:928-935; x-transformers
@@ -449,7 +479,7 @@ int xtrl_learn_prep_bwd(const xtrl_prep_bwd_io *io, int32_t b, int32_t T, int32_
 
 /* sizeof of the ABI structures as this library was compiled (binding self-check): 0 xtrl_model_desc, 1 xtrl_weight_layout,
  * 2 xtrl_step_io, 3 xtrl_loss_cfg, 4 xtrl_loss_io, 5 xtrl_pool_desc, 6 xtrl_opt_cfg, 7 xtrl_ff_io, 8 xtrl_attn_io,
- * 9 xtrl_attn_core_io, 10 xtrl_mlp_io, 11 xtrl_prep_io, 12 xtrl_prep_bwd_io; -1 for anything else.                     */
+ * 9 xtrl_attn_core_io, 10 xtrl_mlp_io, 11 xtrl_prep_io, 12 xtrl_prep_bwd_io, 13 xtrl_peer_ctx; -1 for anything else.   */
 int64_t xtrl_struct_size(int32_t which);
 
 #ifdef __cplusplus

@@ -11,7 +11,7 @@ for w in "$@"; do
 import json
 try:
     r=json.loads(open('gpurun_out/r02_bench_${w}_n${N}.json').read().strip().splitlines()[-1])
-    print('${w}', 'n', r['n_gpus'], 'rollout %.4g'%r['value'], 'e2e %.4g'%r['e2e']['value'], 'learn %.4g'%r['learn_value'], 'ms/mb %.3f'%r['learn']['ms_per_minibatch'], 'identical', r.get('replicas_identical'), 'evolve', r.get('evolve',{}).get('ms_per_fitness_gather'))
+    print('${w}', 'n', r['n_gpus'], 'rollout %.4g'%r['value'], 'e2e %.4g'%r['e2e']['value'], 'learn %.4g'%r['learn_value'], 'ms/mb %.3f'%r['learn']['ms_per_minibatch'], 'identical', r.get('replicas_identical'), 'coll', r['learn'].get('collective','')[:5], 'opt_share %.4f'%r['learn']['kernel_share']['optimizer'], 'evolve', r.get('evolve',{}).get('ms_per_fitness_gather'))
 except Exception as e: print('${w}', 'ERR', e)
 PY
 done

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(L.SYMBOLS) == names, (sorted(L.SYMBOLS), names)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.xtrl_abi_version() == L.XTRL_ABI_VERSION == 8
+    assert lib.xtrl_abi_version() == L.XTRL_ABI_VERSION == 9
     for which, st in enumerate(L.ABI_STRUCTS):                       # every ctypes mirror has the size the C side compiled
         assert lib.xtrl_struct_size(which) == C.sizeof(st), st.__name__
     assert lib.xtrl_struct_size(len(L.ABI_STRUCTS)) == -1

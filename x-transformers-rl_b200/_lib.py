@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-XTRL_ABI_VERSION = 8
+XTRL_ABI_VERSION = 9
 XTRL_MAX_DEPTH = 16
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -72,6 +72,11 @@ class OptCfg(C.Structure):
         ('first_step', c_i32), ('ema_mode', c_f32), ('ema_decay', c_f32), ('copy_ema_to_online', c_i32), ('grad_scale', c_f32)]
 
 
+class PeerCtx(C.Structure):
+    _fields_ = [('grads', c_vp), ('flags', c_vp), ('reduced', c_vp), ('status', c_vp), ('n_reduce', c_i64),
+                ('rank', c_i32), ('world', c_i32), ('epoch', C.c_uint32), ('timeout_s', c_f32)]
+
+
 class FfIO(C.Structure):
     _fields_ = [(n, c_vp) for n in ('x', 'dy', 'ln_gamma', 'b1', 'b2', 'w_img', 'y', 'dx',
                                     'd_ln_gamma', 'd_w1', 'd_b1', 'd_w2', 'd_b2', 'rng_step')] + [
@@ -126,6 +131,12 @@ SYMBOLS = {
     'xtrl_opt_workspace_bytes': (c_i64, [c_i32]),
     'xtrl_adopt_atan2_step': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64,
                                       C.POINTER(OptCfg), c_vp, c_vp, c_vp]),
+    'xtrl_adopt_atan2_step_peers': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64,
+                                            C.POINTER(OptCfg), c_vp, c_vp, C.POINTER(PeerCtx), c_vp]),
+    'xtrl_peer_alloc': (c_i32, [c_i64, C.POINTER(c_vp), c_vp]),
+    'xtrl_peer_open': (c_i32, [c_vp, C.POINTER(c_vp)]),
+    'xtrl_peer_close': (c_i32, [c_vp]),
+    'xtrl_peer_free': (c_i32, [c_vp]),
     'xtrl_ff_img_bytes': (c_i64, [c_i32, c_i32]),
     'xtrl_ff_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'xtrl_ff_fwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
@@ -153,7 +164,7 @@ SYMBOLS = {
 
 
 # order of xtrl_struct_size(which)
-ABI_STRUCTS = (ModelDesc, WeightLayout, StepIO, LossCfg, LossIO, PoolDesc, OptCfg, FfIO, AttnIO, AttnCoreIO, MlpIO, PrepIO, PrepBwdIO)
+ABI_STRUCTS = (ModelDesc, WeightLayout, StepIO, LossCfg, LossIO, PoolDesc, OptCfg, FfIO, AttnIO, AttnCoreIO, MlpIO, PrepIO, PrepBwdIO, PeerCtx)
 
 
 class XtrlError(RuntimeError):

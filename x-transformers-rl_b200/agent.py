@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from torch import nn, tensor
 
 from . import ops
-from .distributed import Accelerator, all_reduce_sum_, broadcast_from_rank0_, world_size
+from .distributed import Accelerator, PeerGroup, all_reduce_sum_, broadcast_from_rank0_, world_size
 from .evolution import LatentGenePool
 from .model import FusedPPOLoss, WorldModelActorCritic
 from .schedule import EmaSchedule
@@ -151,7 +151,7 @@ class Agent(nn.Module):
                  evolve_after_step=20, latent_gene_pool=None, world_model=None, dropout=0.25, max_grad_norm=0.5,
                  frac_actor_critic_head_gradient=0.5, ema_kwargs=None, save_path='./ppo.pt', accelerator=None,
                  actor_loss_weight=1., critic_loss_weight=1., autoregressive_loss_weight=1.,
-                 rollout_positions='reference', kv_cache_dtype='fp32', rollout_dense_dtype='fp32'):
+                 rollout_positions='reference', kv_cache_dtype='fp32', rollout_dense_dtype='fp32', peer_allreduce=True):
         super().__init__()
         latent_gene_pool = latent_gene_pool if latent_gene_pool is not None else dict(
             dim=128, num_genes_per_island=3, num_selected=2, tournament_size=2)
@@ -203,7 +203,10 @@ class Agent(nn.Module):
         self._opt_ws = torch.empty(ops.L.load().xtrl_opt_workspace_bytes(len(self.model._offsets) - 1) // 8,
                                    device=device, dtype=torch.float64)
         # gradient all-reduce buffer: [flat grads | RSNorm batch mean] so one collective carries both
-        self._comm = torch.zeros(n + state_dim + 1, device=device, dtype=torch.float32)
+        # On several GPUs of one node the buffer lives in a block the other ranks map (distributed.PeerGroup) and the
+        # optimiser kernel sums the ranks' buffers itself; where that cannot be set up: torch.distributed.all_reduce.
+        self._peers = PeerGroup.create(n + state_dim + 1, torch.device(device)) if peer_allreduce else None
+        self._comm = self._peers.local if self._peers is not None else torch.zeros(n + state_dim + 1, device=device, dtype=torch.float32)
         self.model._bind(self.model.flat_params, self._comm[:n])
         self.last_logs = None
         self.keep_last_grads = False
@@ -321,17 +324,28 @@ class Agent(nn.Module):
                     scalars = self._fwd_bwd_prepared(src, idx.long(), torch.full((), flag, device=dev))
                 else:
                     scalars = self._fwd_bwd({k: data[k][idx] for k in fields}, flag)
-                if not self.capture_allreduce:
-                    all_reduce_sum_(self._comm)          # ONE collective: gradients (+ RSNorm batch mean in the tail)
-                # self._comm now holds the SUM over ranks of [gradients | RSNorm batch mean]; the mean's 1/world is folded
-                # into the optimiser kernel (grad_scale) and the 9-float tail
                 inv_world = 1. / world_size()
-                if self.keep_last_grads:
-                    self.last_grads = model.flat_grads * inv_world
-                rs_mean = self._comm[n:] * inv_world
-                if self.event_log is not None:
+                if self.event_log is not None and self._peers is not None:
                     evs[1].record()
+                if self._peers is None:
+                    if not self.capture_allreduce:
+                        all_reduce_sum_(self._comm)      # ONE collective: gradients (+ RSNorm batch mean in the tail)
+                    summed = self._comm
+                else:
+                    summed = self._peers.reduced         # filled by the optimiser kernel's first phase (csrc/optim.cu)
+                # `summed` holds the SUM over ranks of [gradients | RSNorm batch mean]; the mean's 1/world is folded into the
+                # optimiser kernel (grad_scale) and the 9-float tail
+                if self._peers is None:
+                    if self.keep_last_grads:
+                        self.last_grads = summed[:n] * inv_world
+                    rs_mean = summed[n:] * inv_world
+                    if self.event_log is not None:
+                        evs[1].record()
                 self._optimizer_step(inv_world)
+                if self._peers is not None:
+                    if self.keep_last_grads:
+                        self.last_grads = summed[:n] * inv_world
+                    rs_mean = summed[n:] * inv_world
                 if self.event_log is not None:
                     evs[2].record()
                     if lg is not None:
@@ -343,6 +357,8 @@ class Agent(nn.Module):
                     self.gene_pool.evolve_(fitnesses)
                 self.accelerator.log(dict(losses=scalars))
         self.rsnorm.copy_from(rs_copy)
+        if self._peers is not None:
+            self._peers.check()
         self.step.add_(1)
         self._step_host += 1
         return self.epochs * int(data['lens'].sum().item())        # learn-timesteps processed
@@ -423,9 +439,10 @@ class Agent(nn.Module):
                              self.ema_params, model.seg_offsets, lr=self.lr, init_lr=self.lr, betas=self.betas,
                              regen_rate=self.regen_reg_rate, cautious_factor=self.cautious_factor,
                              max_grad_norm=self.max_grad_norm, first_step=(self.opt_steps == 0), ema_mode=mode,
-                             ema_decay=decay, copy_ema_to_online=back, workspace=self._opt_ws, grad_scale=grad_scale)
+                             ema_decay=decay, copy_ema_to_online=back, workspace=self._opt_ws, grad_scale=grad_scale,
+                             peers=self._peers)
         self.opt_steps += 1
-        self._comm.zero_()
+        self._comm.zero_()                   # (with peers: the kernel returned only after every rank had read this buffer)
 
     # ---- deploy --------------------------------------------------------------------------------
     @torch.no_grad()

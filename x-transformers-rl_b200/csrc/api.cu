@@ -51,6 +51,7 @@ extern "C" int64_t xtrl_struct_size(int32_t which) {
         case 10: return sizeof(xtrl_mlp_io);
         case 11: return sizeof(xtrl_prep_io);
         case 12: return sizeof(xtrl_prep_bwd_io);
+        case 13: return sizeof(xtrl_peer_ctx);
         default: return -1;
     }
 }

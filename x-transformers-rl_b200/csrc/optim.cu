@@ -11,6 +11,16 @@
 // buffers exceed L2 (the gradient is read once per phase).  Each CTA owns a contiguous span of the buffer
 // and every thread walks it forward in 16-byte units, so the parameter-tensor (segment) of an element is
 // found by a monotone cursor instead of a search, and the per-tensor sums are aggregated per warp.
+//
+// Multi-GPU (xtrl_adopt_atan2_step_peers): the gradient all-reduce is phase 1 of the SAME kernel.  Every rank's gradient
+// buffer and a small flag block live in cudaMalloc memory that the other ranks map through CUDA IPC (xtrl_peer_alloc /
+// xtrl_peer_open; NVLink / NVSwitch peer access).  The kernel announces "my gradients are complete" in every peer's flag
+// block, waits for the same from every peer, and then phase 1 reads each 16-byte unit from all `world` buffers in rank order
+// (one-shot all-reduce: identical sums on every rank, so replicas stay bit-identical), writes the sum to a local buffer the
+// later phases read, and takes the squared norm on the way.  After the grid barrier the rank announces "done reading" and,
+// before it exits, waits until every peer is done with ITS buffer (so the caller may zero it).  No NCCL call, no extra
+// launch, no extra pass over the gradient: 7 x 0.84 MB over NVLink per step at c3 instead of a ~70 us latency-bound
+// collective between the backward graph and the optimiser.
 #include "common.cuh"
 #include <cooperative_groups.h>
 
@@ -18,6 +28,7 @@ namespace xtrl {
 namespace cg = cooperative_groups;
 
 constexpr int kOptThreads = 256;
+constexpr int kMaxPeers = 8;
 
 struct OptArgs {
     float *p, *m, *v, *p_init, *ema;
@@ -28,7 +39,59 @@ struct OptArgs {
     xtrl_opt_cfg c;
     double *ws;
     float *grad_norm_out;
+    // peers (world > 1): every rank's gradient buffer / flag block as mapped on this device, own included
+    const float *pg[kMaxPeers];
+    uint32_t *pf[kMaxPeers];              // [2 * world]: ready[world] | done[world], values = epoch
+    float *reduced;                       // [n_reduce] local: the rank-ordered sum
+    int *status;                          // set to 1 when a wait timed out
+    int64_t n_reduce;
+    int rank, world;
+    uint32_t epoch;
+    long long timeout_ns;
 };
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p has reached `epoch` (wrap-safe); gives up after timeout_ns and reports through *status
+__device__ __forceinline__ void wait_epoch(const uint32_t *p, uint32_t epoch, long long timeout_ns, int *status) {
+    const long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
+        if (global_ns() - t0 > timeout_ns) { atomicExch(status, 1); return; }
+        __nanosleep(64);
+    }
+}
+// peer memory is read around L1 and at system scope: the same addresses held last step's gradients
+__device__ __forceinline__ float4 ld_sys4(const float *p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_sys1(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int V>
+__device__ __forceinline__ void load_unit_sys(const float *base, int64_t i0, int64_t n, float (&x)[V]) {
+    if constexpr (V == 4) {
+        if (i0 + 4 <= n) {
+            const float4 t = ld_sys4(base + i0);
+            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+            return;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) x[e] = i0 + e < n ? ld_sys1(base + i0 + e) : 0.f;
+}
 
 __device__ __forceinline__ int find_segment(const int64_t *__restrict__ off, int nt, int64_t i) {
     int lo = 0, hi = nt;                       // off[lo] <= i < off[hi]
@@ -95,11 +158,40 @@ opt_fused_kernel(const OptArgs a) {
     const float gs = c.grad_scale;
     __shared__ double sh[kOptThreads / 32];
 
-    // ---- phase 1: squared norm of the gradient (fp32 within a unit, fp64 across units) ----
+    // ---- phase 0 (world > 1): every rank's gradient buffer is complete ----
+    const float *gsrc = a.g;
+    const bool peers = a.world > 1;
+    if (peers) {
+        if (blockIdx.x == 0 && tid < a.world) {                  // the earlier kernels of this stream have finished: announce
+            __threadfence_system();
+            st_release_sys(a.pf[tid] + a.rank, a.epoch);
+        }
+        if (tid < a.world) wait_epoch(a.pf[a.rank] + tid, a.epoch, a.timeout_ns, a.status);
+        __syncthreads();
+        gsrc = a.reduced;
+        if (blockIdx.x == 0)                                      // the tail beyond the parameters (the caller's extra sums)
+            for (int64_t i = n + tid; i < a.n_reduce; i += kOptThreads) {
+                float t = 0.f;
+                for (int r = 0; r < a.world; ++r) t += ld_sys1(a.pg[r] + i);
+                a.reduced[i] = t;
+            }
+    }
+    // ---- phase 1: (sum over ranks,) squared norm of the gradient (fp32 within a unit, fp64 across units) ----
     double s = 0.;
     for (int64_t u = u_lo + tid; u < u_hi; u += kOptThreads) {
         float x[V];
-        load_unit<V>(a.g, u * V, n, x);
+        if (peers) {
+            load_unit_sys<V>(a.pg[0], u * V, n, x);
+            for (int r = 1; r < a.world; ++r) {
+                float y[V];
+                load_unit_sys<V>(a.pg[r], u * V, n, y);
+#pragma unroll
+                for (int e = 0; e < V; ++e) x[e] += y[e];
+            }
+            store_unit<V>(a.reduced, u * V, n, x);
+        } else {
+            load_unit<V>(a.g, u * V, n, x);
+        }
         float q = 0.f;
 #pragma unroll
         for (int e = 0; e < V; ++e) { const float t = x[e] * gs; q = fmaf(t, t, q); }
@@ -114,6 +206,7 @@ opt_fused_kernel(const OptArgs a) {
         if (t != 0.) atomicAdd(a.ws, t);
     }
     grid.sync();
+    if (peers && blockIdx.x == 0 && tid < a.world) st_release_sys(a.pf[tid] + a.world + a.rank, a.epoch);   // done reading rank tid's buffer
     const float total = (float)sqrt(__ldcg(a.ws));
     const float coef = (c.max_grad_norm > 0.f ? fminf(c.max_grad_norm / (total + 1e-6f), 1.f) : 1.f) * gs;
     if (a.grad_norm_out && blockIdx.x == 0 && tid == 0) *a.grad_norm_out = total;
@@ -135,7 +228,7 @@ opt_fused_kernel(const OptArgs a) {
             float gx[V], mx[V], vx[V];
             bool al[V] = {};
             if (live) {
-                load_unit<V>(a.g, i0, n, gx); load_unit<V>(a.m, i0, n, mx); load_unit<V>(a.v, i0, n, vx);
+                load_unit<V>(gsrc, i0, n, gx); load_unit<V>(a.m, i0, n, mx); load_unit<V>(a.v, i0, n, vx);
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     const float g = gx[e] * coef;
@@ -183,7 +276,7 @@ opt_fused_kernel(const OptArgs a) {
         for (int64_t u = u_lo + tid; u < u_hi; u += kOptThreads) {
             const int64_t i0 = u * V;
             float gx[V], px[V], vx[V], mx[V], ix[V], ex[V];
-            load_unit<V>(a.g, i0, n, gx); load_unit<V>(a.p, i0, n, px);
+            load_unit<V>(gsrc, i0, n, gx); load_unit<V>(a.p, i0, n, px);
             if (c.first_step) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) { const float g = gx[e] * coef; mx[e] = 0.f; vx[e] = g * g; ix[e] = px[e]; }
@@ -223,6 +316,8 @@ opt_fused_kernel(const OptArgs a) {
             store_unit<V>(a.p, i0, n, px);
         }
     }
+    // every peer has finished reading this rank's gradient buffer: the caller may overwrite it after this kernel
+    if (peers && blockIdx.x == 0 && tid < a.world) wait_epoch(a.pf[a.rank] + a.world + tid, a.epoch, a.timeout_ns, a.status);
 }
 
 template <int V>
@@ -247,10 +342,10 @@ extern "C" int64_t xtrl_opt_workspace_bytes(int32_t num_tensors) {
     return (int64_t)sizeof(double) * (2 + (num_tensors > 0 ? num_tensors : 0));
 }
 
-extern "C" int xtrl_adopt_atan2_step(float *params, const float *grads, float *m, float *v, float *param_init,
-                                     float *ema, const int64_t *seg_offsets, int32_t num_tensors, int64_t n,
-                                     const xtrl_opt_cfg *cfg, double *workspace, float *grad_norm_out,
-                                     void *stream) {
+static int adopt_step(float *params, const float *grads, float *m, float *v, float *param_init,
+                      float *ema, const int64_t *seg_offsets, int32_t num_tensors, int64_t n,
+                      const xtrl_opt_cfg *cfg, double *workspace, float *grad_norm_out, const xtrl_peer_ctx *pc,
+                      void *stream) {
     using namespace xtrl;
     XTRL_REQUIRE(cfg, XTRL_E_BADARG, "xtrl_adopt_atan2_step: null cfg");
     XTRL_REQUIRE(n >= 0 && num_tensors >= 1, XTRL_E_BADARG, "xtrl_adopt_atan2_step: bad sizes");
@@ -263,6 +358,75 @@ extern "C" int xtrl_adopt_atan2_step(float *params, const float *grads, float *m
     OptArgs a;
     a.p = params; a.g = grads; a.m = m; a.v = v; a.p_init = param_init; a.ema = ema; a.seg = seg_offsets; a.nt = num_tensors; a.n = n;
     a.c = *cfg; a.ws = workspace; a.grad_norm_out = grad_norm_out;
-    const uintptr_t bits = (uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v | (uintptr_t)param_init | (uintptr_t)ema;
+    uintptr_t bits = (uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v | (uintptr_t)param_init | (uintptr_t)ema;
+    a.world = 1; a.rank = 0; a.reduced = nullptr; a.status = nullptr; a.n_reduce = n; a.epoch = 0; a.timeout_ns = 0;
+    for (int r = 0; r < kMaxPeers; ++r) { a.pg[r] = nullptr; a.pf[r] = nullptr; }
+    if (pc && pc->world > 1) {
+        XTRL_REQUIRE(pc->world <= kMaxPeers && pc->rank >= 0 && pc->rank < pc->world, XTRL_E_BADARG,
+                     "xtrl_adopt_atan2_step_peers: rank %d / world %d (at most %d peers)", pc->rank, pc->world, kMaxPeers);
+        XTRL_REQUIRE(pc->grads && pc->flags && pc->reduced && pc->status && pc->n_reduce >= n, XTRL_E_BADARG,
+                     "xtrl_adopt_atan2_step_peers: null pointer or n_reduce < n");
+        for (int r = 0; r < pc->world; ++r) {
+            XTRL_REQUIRE(pc->grads[r] && pc->flags[r], XTRL_E_BADARG, "xtrl_adopt_atan2_step_peers: null peer pointer (rank %d)", r);
+            a.pg[r] = pc->grads[r]; a.pf[r] = pc->flags[r];
+            bits |= (uintptr_t)pc->grads[r];
+        }
+        XTRL_REQUIRE(a.pg[pc->rank] == grads, XTRL_E_BADARG, "xtrl_adopt_atan2_step_peers: grads[rank] must be this rank's gradient buffer");
+        bits |= (uintptr_t)pc->reduced;
+        a.world = pc->world; a.rank = pc->rank; a.reduced = pc->reduced; a.status = pc->status; a.n_reduce = pc->n_reduce;
+        a.epoch = pc->epoch; a.timeout_ns = (long long)((pc->timeout_s > 0.f ? pc->timeout_s : 10.f) * 1e9);
+    }
     return (bits & 15) == 0 ? launch_opt<4>(a, s) : launch_opt<1>(a, s);      // 16-byte units when every buffer allows it
+}
+
+extern "C" int xtrl_adopt_atan2_step(float *params, const float *grads, float *m, float *v, float *param_init,
+                                     float *ema, const int64_t *seg_offsets, int32_t num_tensors, int64_t n,
+                                     const xtrl_opt_cfg *cfg, double *workspace, float *grad_norm_out,
+                                     void *stream) {
+    return adopt_step(params, grads, m, v, param_init, ema, seg_offsets, num_tensors, n, cfg, workspace, grad_norm_out, nullptr, stream);
+}
+
+extern "C" int xtrl_adopt_atan2_step_peers(float *params, const float *grads, float *m, float *v, float *param_init,
+                                           float *ema, const int64_t *seg_offsets, int32_t num_tensors, int64_t n,
+                                           const xtrl_opt_cfg *cfg, double *workspace, float *grad_norm_out,
+                                           const xtrl_peer_ctx *peers, void *stream) {
+    using namespace xtrl;
+    XTRL_REQUIRE(peers, XTRL_E_BADARG, "xtrl_adopt_atan2_step_peers: null peer context");
+    return adopt_step(params, grads, m, v, param_init, ema, seg_offsets, num_tensors, n, cfg, workspace, grad_norm_out, peers, stream);
+}
+
+// ---- peer memory: cudaMalloc blocks the other ranks of the node map through CUDA IPC ----
+extern "C" int xtrl_peer_alloc(int64_t bytes, void **ptr, void *handle64) {
+    using namespace xtrl;
+    XTRL_REQUIRE(bytes > 0 && ptr && handle64, XTRL_E_BADARG, "xtrl_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    void *p = nullptr;
+    XTRL_CUDA(cudaMalloc(&p, (size_t)bytes));
+    XTRL_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(XTRL_E_CUDA, "xtrl_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return XTRL_OK;
+}
+extern "C" int xtrl_peer_open(const void *handle64, void **ptr) {
+    using namespace xtrl;
+    XTRL_REQUIRE(handle64 && ptr, XTRL_E_BADARG, "xtrl_peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    XTRL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = p;
+    return XTRL_OK;
+}
+extern "C" int xtrl_peer_close(void *ptr) {
+    using namespace xtrl;
+    if (ptr) XTRL_CUDA(cudaIpcCloseMemHandle(ptr));
+    return XTRL_OK;
+}
+extern "C" int xtrl_peer_free(void *ptr) {
+    using namespace xtrl;
+    if (ptr) XTRL_CUDA(cudaFree(ptr));
+    return XTRL_OK;
 }

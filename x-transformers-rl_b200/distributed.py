@@ -106,6 +106,115 @@ def all_reduce_sum_(flat: torch.Tensor) -> torch.Tensor:
     return flat
 
 
+class _DeviceBlock:
+    """a raw device allocation seen by torch through __cuda_array_interface__ (torch.as_tensor keeps this object alive)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = dict(shape=(nbytes,), typestr='|u1', data=(ptr, False), version=3, strides=None)
+
+
+class PeerGroup:
+    """The flat gradient buffers of all ranks of one node, mapped into each other's address space (CUDA IPC over NVLink /
+    NVSwitch), so that the optimiser kernel itself sums them: csrc/optim.cu, xtrl_adopt_atan2_step_peers.  Replaces DDP's
+    gradient all-reduce (x_transformers_rl.py:885, :981) without an NCCL call on the critical path.
+
+    local   this rank's [n_reduce] fp32 buffer (lives in the shared block; the model's .grad views point into it)
+    reduced [n_reduce] fp32, the sum over ranks after a step
+    Construction is collective (all ranks); it returns None from `create` when any rank could not set it up, in which
+    case every rank keeps the NCCL all-reduce."""
+
+    def __init__(self):
+        raise TypeError('use PeerGroup.create')
+
+    @classmethod
+    def create(cls, n_reduce: int, device: torch.device):
+        import ctypes as C
+        from . import _lib as L
+        if not is_distributed() or device.type != 'cuda' or dist.get_world_size() > 8:
+            return None
+        lib = L.load()
+        world, rank = dist.get_world_size(), dist.get_rank()
+        self = object.__new__(cls)
+        self.lib, self.world, self.rank, self.n_reduce, self.epoch = lib, world, rank, n_reduce, 0
+        self.flag_off = (n_reduce * 4 + 255) // 256 * 256
+        nbytes = self.flag_off + 2 * world * 4
+        self.base, self.opened, err = None, [], None
+        handle = C.create_string_buffer(64)
+        try:
+            with torch.cuda.device(device):
+                p = C.c_void_p()
+                L.check(lib.xtrl_peer_alloc(nbytes, C.byref(p), handle), 'xtrl_peer_alloc')
+                self.base = p.value
+        except Exception as e:                                   # noqa: BLE001 -- reported to every rank below
+            err = repr(e)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (handle.raw if err is None else None, err, _hostname()))
+        ok = all(h is not None for h, _, _ in gathered) and len({hn for _, _, hn in gathered}) == 1
+        ptrs = [None] * world
+        if ok:
+            try:
+                with torch.cuda.device(device):
+                    for r in range(world):
+                        if r == rank:
+                            ptrs[r] = self.base
+                        else:
+                            q = C.c_void_p()
+                            L.check(lib.xtrl_peer_open(gathered[r][0], C.byref(q)), 'xtrl_peer_open')
+                            ptrs[r] = q.value
+                            self.opened.append(q.value)
+            except Exception as e:                               # noqa: BLE001
+                err = repr(e)
+        flags = [None] * world
+        dist.all_gather_object(flags, ok and err is None)
+        if not all(flags):
+            self.close()
+            if rank == 0:
+                import warnings
+                warnings.warn('peer-memory gradient exchange unavailable (' + '; '.join(str(e) for _, e, _ in gathered if e) + f' {err or ""}); '
+                              'using the NCCL all-reduce')
+            return None
+        self.grads_arr = (C.c_void_p * world)(*ptrs)
+        self.flags_arr = (C.c_void_p * world)(*[q + self.flag_off for q in ptrs])
+        block = torch.as_tensor(_DeviceBlock(self.base, nbytes), device=device)
+        self.local = block[:n_reduce * 4].view(torch.float32)
+        self.reduced = torch.zeros(n_reduce, device=device, dtype=torch.float32)
+        self.status = torch.zeros(1, device=device, dtype=torch.int32)
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        return self
+
+    def ctx(self, timeout_s: float = 10.):
+        """the xtrl_peer_ctx of the next step (bumps the epoch; every rank must call in lock step)"""
+        from . import _lib as L
+        import ctypes as C
+        self.epoch += 1
+        return L.PeerCtx(C.cast(self.grads_arr, C.c_void_p), C.cast(self.flags_arr, C.c_void_p), self.reduced.data_ptr(),
+                         self.status.data_ptr(), self.n_reduce, self.rank, self.world, self.epoch & 0xffffffff, timeout_s)
+
+    def check(self):
+        """raises if a step gave up waiting for a peer (one host sync: call once per learn(), not per step)"""
+        if int(self.status.item()) != 0:
+            from . import _lib as L
+            raise L.XtrlError('peer-memory gradient exchange timed out waiting for another rank')
+
+    def close(self):
+        for q in self.opened:
+            self.lib.xtrl_peer_close(q)
+        self.opened = []
+
+    def __del__(self):
+        # the block itself is left to process exit: other ranks may still have it mapped
+        try:
+            self.close()
+        except Exception:                                        # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
+def _hostname() -> str:
+    import socket
+    return socket.gethostname()
+
+
 def world_size() -> int:
     return dist.get_world_size() if is_distributed() else 1
 

@@ -158,9 +158,10 @@ def evolve_(genes, fitness, noise_tourn, noise_cross, noise_mut, *, num_islands,
 
 def adopt_atan2_step(params, grads, m, v, param_init, ema, seg_offsets, *, lr, init_lr, betas, regen_rate,
                      cautious_factor, max_grad_norm, first_step, ema_mode=0, ema_decay=0., copy_ema_to_online=False,
-                     a=1.27, b=1., workspace=None, grad_norm_out=None, grad_scale=1.):
+                     a=1.27, b=1., workspace=None, grad_norm_out=None, grad_scale=1., peers=None):
     """one cooperative launch: global-norm clip of grads * grad_scale, AdoptAtan2, EMA (csrc/optim.cu).  grad_scale = 1 / world
-    after a SUM all-reduce of the flat gradient buffer."""
+    after a SUM all-reduce of the flat gradient buffer -- or, with peers (a distributed.PeerGroup whose `local` holds grads),
+    the sum over the ranks' buffers is the first phase of the same kernel (peers.reduced receives it)."""
     lib = L.load()
     nt = seg_offsets.numel() - 1
     n = params.numel()
@@ -168,6 +169,16 @@ def adopt_atan2_step(params, grads, m, v, param_init, ema, seg_offsets, *, lr, i
         workspace = torch.empty(lib.xtrl_opt_workspace_bytes(nt) // 8, device=params.device, dtype=torch.float64)
     cfg = L.OptCfg(lr, init_lr, betas[0], betas[1], regen_rate, cautious_factor, a, b, max_grad_norm,
                    int(first_step), float(ema_mode), ema_decay, int(copy_ema_to_online), float(grad_scale))
+    if peers is not None:
+        if grads.data_ptr() != peers.local.data_ptr():
+            raise L.XtrlError('adopt_atan2_step: with peers the gradients must be the head of peers.local')
+        pc = peers.ctx()
+        L.check(lib.xtrl_adopt_atan2_step_peers(_ptr(params, torch.float32, 'params'), _ptr(grads, torch.float32, 'grads'),
+                                                _ptr(m, torch.float32), _ptr(v, torch.float32), _ptr(param_init, torch.float32),
+                                                _ptr(ema, torch.float32), _ptr(seg_offsets, torch.int64, 'seg_offsets'), nt, n,
+                                                C.byref(cfg), _ptr(workspace), _ptr(grad_norm_out), C.byref(pc), _stream()),
+                'xtrl_adopt_atan2_step_peers')
+        return
     L.check(lib.xtrl_adopt_atan2_step(_ptr(params, torch.float32, 'params'), _ptr(grads, torch.float32, 'grads'),
                                       _ptr(m, torch.float32), _ptr(v, torch.float32), _ptr(param_init, torch.float32),
                                       _ptr(ema, torch.float32), _ptr(seg_offsets, torch.int64, 'seg_offsets'), nt, n,
