@@ -347,7 +347,9 @@ typedef struct xtrl_attn_io {
     const void *o;                  /* bf16 [b][H][n][16]      post fwd/bwd in                 */
     const int32_t *lens;            /* [b]                     post                            */
     float *y;                       /* [b*n][dim]              post fwd out                    */
-    const float *dy;                /* [b*n][dim]              post bwd in (dx of the residual path = dy) */
+    const float *dy;                /* [b*n][dim]              post bwd in (dx of the residual path = dy);
+                                       pre bwd: optional -- when non-NULL, dx = dy + the LayerNorm path's gradient, i.e.
+                                       the whole block's dx (y = x + attn(LN(x))) without a separate add          */
     void *d_o;                      /* bf16 [b][H][n][16]      post bwd out                    */
     float *d_wo;                    /* += post bwd                                             */
     /* optional extra projection blocks of `pre` (value gate: to_v_gate; learned value-residual mix:
@@ -409,6 +411,16 @@ typedef struct xtrl_mlp_io {
     int32_t n_silu;
     int32_t out_cols;
 } xtrl_mlp_io;
+
+/*     rectangular blocks between the live parameters (several nn.Linear weights / biases) and the zero-padded dense
+ *     buffers the head kernels use: dst[r][c] = src[r][c] (accumulate = 0: refresh before the forward) or += (1: add the
+ *     padded gradient scratch to the parameters' gradients after the backward); up to 8 blocks per launch.            */
+typedef struct xtrl_seg2d {
+    const float *src;
+    float *dst;
+    int32_t rows, cols, src_pitch, dst_pitch;   /* pitches in floats */
+} xtrl_seg2d;
+int xtrl_seg2d_copy(const xtrl_seg2d *segs, int32_t nseg, int32_t accumulate, void *stream);
 
 int64_t xtrl_mlp_img_bytes(int32_t in_dim, int32_t hidden, int32_t out);      /* -1 if not built */
 int xtrl_mlp_pack(const float *w1, const float *w2, void *img, int32_t in_dim, int32_t hidden, int32_t out, void *stream);
@@ -479,7 +491,7 @@ int xtrl_learn_prep_bwd(const xtrl_prep_bwd_io *io, int32_t b, int32_t T, int32_
 
 /* sizeof of the ABI structures as this library was compiled (binding self-check): 0 xtrl_model_desc, 1 xtrl_weight_layout,
  * 2 xtrl_step_io, 3 xtrl_loss_cfg, 4 xtrl_loss_io, 5 xtrl_pool_desc, 6 xtrl_opt_cfg, 7 xtrl_ff_io, 8 xtrl_attn_io,
- * 9 xtrl_attn_core_io, 10 xtrl_mlp_io, 11 xtrl_prep_io, 12 xtrl_prep_bwd_io, 13 xtrl_peer_ctx; -1 for anything else.   */
+ * 9 xtrl_attn_core_io, 10 xtrl_mlp_io, 11 xtrl_prep_io, 12 xtrl_prep_bwd_io, 13 xtrl_peer_ctx, 14 xtrl_seg2d; -1 otherwise. */
 int64_t xtrl_struct_size(int32_t which);
 
 #ifdef __cplusplus

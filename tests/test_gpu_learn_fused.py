@@ -228,6 +228,12 @@ def test_attn_pre_post_vs_torch(H, b, n):
     assert maxrel(dx, x.grad) < TOL_BF16
     for k_, t in dict(gamma=gamma, wq=wq, wk=wk, wv=wv).items():
         assert maxrel(gr[k_], t.grad) < 2 * TOL_BF16, k_
+    # the block's residual-path gradient added inside the kernel: exactly dx + d_res (same arithmetic, one more fp32 add)
+    d_res = torch.randn(b, n, D, generator=g).to(DEV)
+    scratch = {k_: torch.zeros_like(t) for k_, t in dict(gamma=gamma, wq=wq, wk=wk, wv=wv).items()}
+    dx2 = ops.attn_pre_bwd(x.detach(), dq, dk, dv, gamma.detach(), img, cos, sin, scratch['gamma'], scratch['wq'], scratch['wk'],
+                           scratch['wv'], d_res=d_res)
+    assert torch.equal(dx2, dx + d_res)
     # ---- post ----
     x.grad = None
     lens = torch.randint(1, n + 1, (b,), generator=g).int().to(DEV)

@@ -77,6 +77,10 @@ class PeerCtx(C.Structure):
                 ('rank', c_i32), ('world', c_i32), ('epoch', C.c_uint32), ('timeout_s', c_f32)]
 
 
+class Seg2d(C.Structure):
+    _fields_ = [('src', c_vp), ('dst', c_vp), ('rows', c_i32), ('cols', c_i32), ('src_pitch', c_i32), ('dst_pitch', c_i32)]
+
+
 class FfIO(C.Structure):
     _fields_ = [(n, c_vp) for n in ('x', 'dy', 'ln_gamma', 'b1', 'b2', 'w_img', 'y', 'dx',
                                     'd_ln_gamma', 'd_w1', 'd_b1', 'd_w2', 'd_b2', 'rng_step')] + [
@@ -137,6 +141,7 @@ SYMBOLS = {
     'xtrl_peer_open': (c_i32, [c_vp, C.POINTER(c_vp)]),
     'xtrl_peer_close': (c_i32, [c_vp]),
     'xtrl_peer_free': (c_i32, [c_vp]),
+    'xtrl_seg2d_copy': (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     'xtrl_ff_img_bytes': (c_i64, [c_i32, c_i32]),
     'xtrl_ff_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'xtrl_ff_fwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
@@ -164,7 +169,7 @@ SYMBOLS = {
 
 
 # order of xtrl_struct_size(which)
-ABI_STRUCTS = (ModelDesc, WeightLayout, StepIO, LossCfg, LossIO, PoolDesc, OptCfg, FfIO, AttnIO, AttnCoreIO, MlpIO, PrepIO, PrepBwdIO, PeerCtx)
+ABI_STRUCTS = (ModelDesc, WeightLayout, StepIO, LossCfg, LossIO, PoolDesc, OptCfg, FfIO, AttnIO, AttnCoreIO, MlpIO, PrepIO, PrepBwdIO, PeerCtx, Seg2d)
 
 
 class XtrlError(RuntimeError):

@@ -386,7 +386,7 @@ class Agent(nn.Module):
                                     latent_gene=gene, reward_flag=flag, fused=self.fused_learn)
         loss, scalars = FusedPPOLoss.apply(self.loss_cfg, ra, vl, spr, dl, actions.contiguous(), mb['old_log_probs'].contiguous(),
                                            mb['returns'].contiguous(), mb['old_values'].contiguous(), packed.contiguous(),
-                                           mb['dones'].contiguous(), lens.contiguous())
+                                           mb['dones'].contiguous(), lens.contiguous(), True)
         loss.backward()
         # RSNorm batch mean over the masked rows rides in the tail of the gradient buffer (:1005, :601)
         mf = mask[..., None].float()
@@ -424,7 +424,7 @@ class Agent(nn.Module):
         gene_fn = (lambda ids: self.gene_pool[ids]) if self.evolutionary else None                  # :906
         ra, vl, spr, dl, box = model.forward_prepared(src, idx, self.rsnorm.running_mean, self.rsnorm.running_variance, flag, gene_fn)
         loss, scalars = FusedPPOLoss.apply(self.loss_cfg, ra, vl, spr, dl, box['actions'], box['old_log_probs'], box['returns'],
-                                           box['old_values'], box['packed'], box['dones'], box['lens'])
+                                           box['old_values'], box['packed'], box['dones'], box['lens'], True)
         loss.backward()
         rs = box['rs_sum']                                                                           # :1005, :601
         self._comm[n:] = rs[:S + 1] / rs[S + 1].clamp(min=1.)

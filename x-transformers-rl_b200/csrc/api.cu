@@ -52,6 +52,7 @@ extern "C" int64_t xtrl_struct_size(int32_t which) {
         case 11: return sizeof(xtrl_prep_io);
         case 12: return sizeof(xtrl_prep_bwd_io);
         case 13: return sizeof(xtrl_peer_ctx);
+        case 14: return sizeof(xtrl_seg2d);
         default: return -1;
     }
 }

@@ -196,10 +196,10 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
     float *sOut = sX32 + TOK * D;
     float *sG = sOut + (OST ? 2 * TOK * D : 0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sG + D);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 3);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
+    if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }   // 3: residual-gradient tile landed
     if (warp == 0) tmem_alloc(tslot, TCOLS);
     if (tid < D) sG[tid] = a.gamma[tid];
     if (half == 0) {                                                          // constant ones column (bias gradients) + zero pad
@@ -215,9 +215,10 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         mbar_expect_tx(&bars[0], P::kWqkv); bulk_g2s(sW, a.wimg + P::kWo, P::kWqkv, &bars[0]);
         if ((int)blockIdx.x < ntiles) rows_fetch(sX32, a.x, blockIdx.x, a.N, &bars[2]);
     }
-    uint32_t ph = 0, phx = 0;
+    uint32_t ph = 0, phx = 0, phr = 0;
     bool first = true;
     int pend = -1, it = 0;                                                    // tile whose dx still sits in sOut[(it - 1) & 1]
+    const bool res = a.dy != nullptr;                                         // dx = dy (the block's residual path) + the LayerNorm path
     float dg_acc[24];
 #pragma unroll
     for (int i = 0; i < 24; ++i) dg_acc[i] = 0.f;
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
         __syncthreads();
         if (tid == 0) {
             if (OST && pend >= 0) { bulk_wait_read(); rows_store(a.dx, sOut + ((it - 1) & 1) * TOK * D, pend, a.N); }
+            if (OST && res) rows_fetch(sOut + (it & 1) * TOK * D, a.dy, tile, a.N, &bars[3]);   // lands where this tile's dx is formed
             if (first) mbar_wait(&bars[0], 0);
             tc_fence_after();
 #pragma unroll
@@ -325,6 +327,15 @@ __global__ void __launch_bounds__(NT, 1) attn_pre_bwd_kernel(const Args a) {
             }
             if (OST || ok) {
                 float4 *dst = reinterpret_cast<float4 *>(OST ? sOut + (it & 1) * TOK * D + row * D + half * 24 : a.dx + (size_t)t * D + half * 24);
+                if (res) {
+                    if (OST) { mbar_wait(&bars[3], phr); phr ^= 1; }
+                    const float4 *rsd = OST ? dst : reinterpret_cast<const float4 *>(a.dy + (size_t)t * D + half * 24);
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const float4 r4 = (OST && !ok) ? make_float4(0.f, 0.f, 0.f, 0.f) : rsd[i];
+                        o[4 * i] += r4.x; o[4 * i + 1] += r4.y; o[4 * i + 2] += r4.z; o[4 * i + 3] += r4.w;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             }
@@ -665,7 +676,8 @@ extern "C" int xtrl_attn_pre_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, i
     XTRL_REQUIRE(io->x && io->ln_gamma && io->cos_tab && io->sin_tab && io->w_img && io->dq && io->dk && io->dv && io->dx &&
                  io->d_ln_gamma && io->d_wq && io->d_wk && io->d_wv && (!gate || (io->d_wg && io->d_bg)) && (!mix || (io->d_wm && io->d_bm)),
                  XTRL_E_BADARG, "xtrl_attn_pre_bwd: null pointer");
-    XTRL_REQUIRE((((uintptr_t)io->x | (uintptr_t)io->dx) & 15) == 0, XTRL_E_BADARG, "xtrl_attn_pre_bwd: x and dx must be 16-byte aligned (row tiles move by bulk copy)");
+    XTRL_REQUIRE((((uintptr_t)io->x | (uintptr_t)io->dx | (uintptr_t)io->dy) & 15) == 0, XTRL_E_BADARG,
+                 "xtrl_attn_pre_bwd: x, dx and dy must be 16-byte aligned (row tiles move by bulk copy)");
     Args a;
     if (int rc = fill(io, b, n, a)) return rc;
 #define CALL(H, NB, MIX) return launch(attn_pre_bwd_kernel<H, NB, MIX>, "attn_pre_bwd_kernel", Smem<H, NB, MIX>::pre_bwd, 1, a, stream)

@@ -408,6 +408,45 @@ static int fill(const xtrl_mlp_io *io, int64_t N, int32_t n, int32_t in_dim, int
 }  // namespace mlp
 }  // namespace xtrl
 
+// ---- dense padded copies of the head parameters <-> the live parameters, one launch per head ----
+// The head kernels work on zero-padded dense weights (hidden / out rounded up, several nn.Linear layers stacked as row blocks).
+// refresh = copy every parameter block into its place (mode 0); scatter = add every block of the padded gradient scratch to the
+// parameter's gradient (mode 1).  Up to kMaxSegs rectangular blocks per launch, passed by value.
+namespace xtrl {
+constexpr int kMaxSegs = 8;
+struct SegArgs { xtrl_seg2d seg[kMaxSegs]; int n, mode; };
+__global__ void seg2d_kernel(const SegArgs a) {
+    const xtrl_seg2d g = a.seg[blockIdx.y];
+    const int total = g.rows * g.cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / g.cols, c = i - r * g.cols;
+        const float v = g.src[(size_t)r * g.src_pitch + c];
+        float *d = g.dst + (size_t)r * g.dst_pitch + c;
+        *d = a.mode ? *d + v : v;
+    }
+}
+}  // namespace xtrl
+
+extern "C" int xtrl_seg2d_copy(const xtrl_seg2d *segs, int32_t nseg, int32_t accumulate, void *stream) {
+    using namespace xtrl;
+    XTRL_REQUIRE(segs && nseg >= 1 && nseg <= kMaxSegs, XTRL_E_BADARG, "xtrl_seg2d_copy: 1..%d segments (got %d)", kMaxSegs, nseg);
+    SegArgs a;
+    int most = 0;
+    for (int i = 0; i < nseg; ++i) {
+        XTRL_REQUIRE(segs[i].src && segs[i].dst && segs[i].rows >= 0 && segs[i].cols >= 0 && segs[i].src_pitch >= segs[i].cols &&
+                     segs[i].dst_pitch >= segs[i].cols, XTRL_E_BADARG, "xtrl_seg2d_copy: bad segment %d", i);
+        a.seg[i] = segs[i];
+        const int t = segs[i].rows * segs[i].cols;
+        most = t > most ? t : most;
+    }
+    if (most == 0) return XTRL_OK;
+    a.n = nseg; a.mode = accumulate != 0;
+    const int bx = (most + 255) / 256;
+    seg2d_kernel<<<dim3(bx < 64 ? bx : 64, nseg), 256, 0, (cudaStream_t)stream>>>(a);
+    XTRL_LAUNCH_CHECK("seg2d_kernel");
+    return XTRL_OK;
+}
+
 extern "C" int64_t xtrl_mlp_img_bytes(int32_t in_dim, int32_t hidden, int32_t out) {
     return xtrl::mlp::variant_ok(in_dim, hidden, out) ? (int64_t)hidden * in_dim * 2 + (int64_t)out * hidden * 2 : -1;
 }

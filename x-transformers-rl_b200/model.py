@@ -213,26 +213,38 @@ class _Head:
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         self.in_dim, self.hid_p, self.out_p, self.out_cols, self.n_silu = in_dim, hid_p, out_p, out_cols, n_silu
         self.w1, self.b1, self.w2, self.b2 = z(hid_p, in_dim), z(hid_p), z(out_p, hid_p), z(out_p)
-        self.gw1, self.gb1, self.gw2, self.gb2 = z(hid_p, in_dim), z(hid_p), z(out_p, hid_p), z(out_p)
+        # the padded gradient scratch is ONE buffer (one fill per backward) viewed as the four tensors
+        sizes = (hid_p * in_dim, hid_p, out_p * hid_p, out_p)
+        self.gflat = z(sum(sizes))
+        parts = self.gflat.split(sizes)
+        self.gw1, self.gb1, self.gw2, self.gb2 = parts[0].view(hid_p, in_dim), parts[1], parts[2].view(out_p, hid_p), parts[3]
         self.img = torch.empty(ops.L.load().xtrl_mlp_img_bytes(in_dim, hid_p, out_p), dtype=torch.uint8, device=dev)
         self.l1, self.l2 = [], []          # (linear, first row) ; (linear, first row, hidden columns)
+        self._tables = None
+
+    def _seg_tables(self):
+        """(refresh, scatter) block tables over the CURRENT addresses of the parameters' data / grad views (they live in the
+        model's flat buffers; rebuilt if those move)"""
+        key = tuple((lin.weight.data_ptr(), lin.weight.grad.data_ptr() if lin.weight.grad is not None else 0) for lin, *_ in self.l1 + self.l2)
+        if self._tables is None or self._tables[0] != key:
+            fwd, bwd = [], []
+            for lin, r0 in self.l1:
+                n = lin.weight.shape[0]
+                fwd += [(lin.weight.data, self.w1[r0:r0 + n]), (lin.bias.data, self.b1[r0:r0 + n])]
+                bwd += [(self.gw1[r0:r0 + n], lin.weight.grad), (self.gb1[r0:r0 + n], lin.bias.grad)]
+            for lin, r0, cols in self.l2:
+                n = lin.weight.shape[0]
+                fwd += [(lin.weight.data, self.w2[r0:r0 + n, :cols]), (lin.bias.data, self.b2[r0:r0 + n])]
+                bwd += [(self.gw2[r0:r0 + n, :cols], lin.weight.grad), (self.gb2[r0:r0 + n], lin.bias.grad)]
+            self._tables = (key, ops.SegTable(fwd), ops.SegTable(bwd))
+        return self._tables[1], self._tables[2]
 
     def refresh(self):
-        for lin, r0 in self.l1:
-            self.w1[r0:r0 + lin.weight.shape[0]].copy_(lin.weight.data)
-            self.b1[r0:r0 + lin.weight.shape[0]].copy_(lin.bias.data)
-        for lin, r0, cols in self.l2:
-            self.w2[r0:r0 + lin.weight.shape[0], :cols].copy_(lin.weight.data)
-            self.b2[r0:r0 + lin.weight.shape[0]].copy_(lin.bias.data)
+        self._seg_tables()[0].run()                              # one launch: every parameter block into the padded copies
         ops.mlp_pack(self.w1, self.w2, out=self.img)
 
     def scatter(self):
-        for lin, r0 in self.l1:
-            lin.weight.grad += self.gw1[r0:r0 + lin.weight.shape[0]]
-            lin.bias.grad += self.gb1[r0:r0 + lin.weight.shape[0]]
-        for lin, r0, cols in self.l2:
-            lin.weight.grad += self.gw2[r0:r0 + lin.weight.shape[0], :cols]
-            lin.bias.grad += self.gb2[r0:r0 + lin.weight.shape[0]]
+        self._seg_tables()[1].run(accumulate=True)               # one launch: padded gradient blocks += into the .grad views
 
 
 class _FusedHead(torch.autograd.Function):
@@ -249,8 +261,7 @@ class _FusedHead(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         srcs, head, n = list(ctx.saved_tensors), ctx.head, ctx.n
-        for t in (head.gw1, head.gb1, head.gw2, head.gb2):
-            t.zero_()
+        head.gflat.zero_()
         gy = gy.reshape(-1, head.out_cols).to(torch.bfloat16).contiguous()
         d = ops.mlp_bwd(srcs, n, gy, head.b1, head.img, head.gw1, head.gb1, head.gw2, head.gb2, head.n_silu, per_episode2=len(srcs) == 3)
         head.scatter()
@@ -338,6 +349,33 @@ class _FusedAttnPost(torch.autograd.Function):
         o, lens = ctx.saved_tensors
         dy = dy.float().contiguous()
         return dy, ops.attn_post_bwd(dy, o, lens, ctx.img, ctx.attn.to_out.weight.grad), None, None, None
+
+
+class _FusedAttnBlock(torch.autograd.Function):
+    """the whole plain attention block y = x + mask * to_out(attn(rotary(to_qkv(LN(x))))) (no value gate / value residual) as ONE
+    autograd node over the same kernels as _FusedAttnPre / _FusedAttnCore / _FusedAttnPost.  Its point is the backward: the
+    gradient arriving over the residual path (dy) is added inside xtrl_attn_pre_bwd, so autograd has no (b, n, 48) add to do
+    per layer."""
+
+    @staticmethod
+    def forward(ctx, x, norm, attn, img, cos, sin, heads, lens, rng_step, key, p_drop):
+        x = x.float().contiguous()
+        q, k, v = ops.attn_pre_fwd(x, norm.gamma.data, img, cos, sin, heads)[:3]
+        o, lse = ops.attn_core_fwd(q, k, v, dropout=p_drop, rng_step=rng_step, rng_key=key)
+        ctx.save_for_backward(x, q, k, v, o, lse, lens)
+        ctx.mods, ctx.aux, ctx.rng = (norm, attn), (img, cos, sin), (rng_step, key, p_drop)
+        return ops.attn_post_fwd(x, o, lens, img)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, q, k, v, o, lse, lens = ctx.saved_tensors
+        (norm, attn), (img, cos, sin), (rng_step, key, p_drop) = ctx.mods, ctx.aux, ctx.rng
+        dy = dy.float().contiguous()
+        d_o = ops.attn_post_bwd(dy, o, lens, img, attn.to_out.weight.grad)
+        dq, dk, dv = ops.attn_core_bwd(q, k, v, o, lse, d_o, dropout=p_drop, rng_step=rng_step, rng_key=key)
+        dx = ops.attn_pre_bwd(x, dq, dk, dv, norm.gamma.data, img, cos, sin, norm.gamma.grad, attn.to_q.weight.grad,
+                              attn.to_k.weight.grad, attn.to_v.weight.grad, d_res=dy)
+        return (dx,) + (None,) * 10
 
 
 class WorldModelActorCritic(nn.Module):
@@ -515,11 +553,25 @@ class WorldModelActorCritic(nn.Module):
         lat = None
         if self.evolutionary:
             lat = self.latent_to_embed(latent_gene_fn(box['gene_ids'].long()).float())
-        ang = torch.arange(n, device=x0.device, dtype=torch.float32)[:, None] * self.transformer.attn_layers.rotary_pos_emb.inv_freq[None]
-        ang = ang.repeat_interleave(2, dim=-1)
         p_drop = self.dropout if self.training else 0.
-        embed = self._fused_trunk(x0, box['lens'], n, ang, p_drop)
+        embed = self._fused_trunk(x0, box['lens'], n, None, p_drop)
         return (*self._fused_heads(embed, se, ae_next, lat, n), box)
+
+    def _rotary_tables(self, n, ang=None):
+        """cos / sin of position * inv_freq for the kernels' partial rotary, [n][dim_head / 4] each.  inv_freq is a constant
+        buffer, so the tables are computed once per sequence length (outside graph capture) instead of six small launches
+        per pass; `ang` (n, dim_head / 2, every frequency twice) is what callers that already formed the angles pass in."""
+        cache = self.fused_state().setdefault('rotary', {})
+        if n in cache:
+            return cache[n]
+        if ang is None:
+            ang = torch.arange(n, device=self.flat_params.device, dtype=torch.float32)[:, None] * self.transformer.attn_layers.rotary_pos_emb.inv_freq[None]
+            ang = ang.repeat_interleave(2, dim=-1)
+        ang4 = ang[:, ::2].contiguous()
+        tabs = (ang4.cos(), ang4.sin())
+        if not torch.cuda.is_current_stream_capturing():
+            cache[n] = tabs
+        return tabs
 
     def _fused_trunk(self, x, lens32, n, ang, p_drop):
         """every sub-layer of the Decoder and the final norm as libxtrl tcgen05 kernels behind autograd seams (csrc/learn_*.cu).
@@ -538,11 +590,16 @@ class WorldModelActorCritic(nn.Module):
                           wg=at.to_v_gate.weight.data if cfg.gate_values else None,
                           wm=at.to_value_residual_mix[0].weight.data if (cfg.value_residual and cfg.learned_mix and l > 0) else None,
                           out=fs['attn_img'][l])
-        ang4 = ang[:, ::2].contiguous()
-        cos4, sin4 = ang4.cos(), ang4.sin()
+        cos4, sin4 = self._rotary_tables(n, ang)
         first_v = None
+        plain = not (cfg.gate_values or cfg.value_residual)
         for l in range(cfg.depth):
             norm, attn = dec.layers[2 * l]
+            if plain:                                                # one autograd node per block (residual add inside pre_bwd)
+                x = _FusedAttnBlock.apply(x, norm, attn, fs['attn_img'][l], cos4, sin4, h, lens32, fs['rng_step'], 1000 + l, p_drop)
+                norm, ff = dec.layers[2 * l + 1]
+                x = _FusedFeedForward.apply(x, norm, ff, fs['ff_img'][l], fs['rng_step'], l, p_drop)
+                continue
             has_mix = bool(cfg.value_residual and cfg.learned_mix and l > 0)
             outs = _FusedAttnPre.apply(x, norm, attn, fs['attn_img'][l], cos4, sin4, h, cfg.gate_values, has_mix)
             q, k, v = outs[:3]
@@ -581,7 +638,10 @@ class FusedPPOLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, raw_actions, value_logits, state_pred_raw, done_logit, actions, old_log_probs, returns,
-                old_values, target, dones, episode_lens):
+                old_values, target, dones, episode_lens, unit_grad=False):
+        # unit_grad: the caller promises to call .backward() on the returned total itself (incoming gradient == 1), so the
+        # stored gradients are handed over as they are instead of through four multiplications by one (47 us at c3)
+        ctx.unit_grad = bool(unit_grad)
         scalars, grads = ops.ppo_loss_fwd_bwd(cfg, raw_actions.contiguous(), value_logits.contiguous(),
                                               state_pred_raw.contiguous(), done_logit.contiguous(), actions,
                                               old_log_probs, returns, old_values, target, dones, episode_lens)
@@ -592,5 +652,7 @@ class FusedPPOLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, _g_scalars):
         g_ra, g_vl, g_sp, g_dl = ctx.saved_tensors
+        if ctx.unit_grad:
+            return (None, g_ra, g_vl, g_sp, g_dl) + (None,) * 8
         s = g_total.to(g_ra.dtype)
-        return (None, g_ra * s, g_vl * s, g_sp * s, g_dl * s, None, None, None, None, None, None, None)
+        return (None, g_ra * s, g_vl * s, g_sp * s, g_dl * s) + (None,) * 8

@@ -274,8 +274,9 @@ def attn_pre_fwd(x, ln_gamma, img, cos_tab, sin_tab, heads, gate_bias=None, mix_
 
 
 def attn_pre_bwd(x, dq, dk, dv, ln_gamma, img, cos_tab, sin_tab, d_ln_gamma, d_wq, d_wk, d_wv, dg=None, dmix=None,
-                 d_wg=None, d_bg=None, d_wm=None, d_bm=None):
-    """dx of the LayerNorm -> projection path; parameter gradients accumulated (+=)."""
+                 d_wg=None, d_bg=None, d_wm=None, d_bm=None, d_res=None):
+    """dx of the LayerNorm -> projection path (+ d_res, the gradient arriving over the block's residual path, when given);
+    parameter gradients accumulated (+=)."""
     lib = L.load()
     b, heads, n, _ = dq.shape
     dx = torch.empty_like(x)
@@ -285,7 +286,7 @@ def attn_pre_bwd(x, dq, dk, dv, ln_gamma, img, cos_tab, sin_tab, d_ln_gamma, d_w
                   dq=_ptr(dq, bf, 'dq'), dk=_ptr(dk, bf, 'dk'), dv=_ptr(dv, bf, 'dv'), dx=_ptr(dx, f32, 'dx'),
                   d_ln_gamma=_ptr(d_ln_gamma, f32), d_wq=_ptr(d_wq, f32), d_wk=_ptr(d_wk, f32), d_wv=_ptr(d_wv, f32),
                   d_gate=_ptr(dg, bf, 'dg'), d_mix=_ptr(dmix, bf, 'dmix'), d_wg=_ptr(d_wg, f32), d_bg=_ptr(d_bg, f32),
-                  d_wm=_ptr(d_wm, f32), d_bm=_ptr(d_bm, f32))
+                  d_wm=_ptr(d_wm, f32), d_bm=_ptr(d_bm, f32), dy=_ptr(d_res, f32, 'd_res'))
     L.check(lib.xtrl_attn_pre_bwd(C.byref(io), b, n, heads, _stream()), 'xtrl_attn_pre_bwd')
     return dx
 
@@ -314,6 +315,29 @@ def attn_post_bwd(dy, o, lens, img, d_wo):
 
 def mlp_supported(in_dim, hidden, out) -> bool:
     return L.load().xtrl_mlp_img_bytes(in_dim, hidden, out) > 0
+
+
+class SegTable:
+    """a fixed list of rectangular blocks (src tensor view -> dst tensor view, both 1-D or 2-D fp32 with unit inner stride) for
+    xtrl_seg2d_copy; built once, replayed every step (the views' addresses are captured here)."""
+
+    def __init__(self, pairs):
+        segs = []
+        for src, dst in pairs:
+            assert src.shape == dst.shape and src.dtype == dst.dtype == torch.float32 and src.dim() in (1, 2)
+            if src.dim() == 1:
+                src, dst = src[None], dst[None]
+            assert src.stride(1) == 1 and dst.stride(1) == 1
+            rows, cols = src.shape
+            segs.append(L.Seg2d(src.data_ptr(), dst.data_ptr(), rows, cols, src.stride(0) if rows > 1 else cols,
+                                dst.stride(0) if rows > 1 else cols))
+        self.keep = pairs
+        self.chunks = [(L.Seg2d * len(segs[i:i + 8]))(*segs[i:i + 8]) for i in range(0, len(segs), 8)]
+
+    def run(self, accumulate=False):
+        lib = L.load()
+        for ch in self.chunks:
+            L.check(lib.xtrl_seg2d_copy(C.cast(ch, C.c_void_p), len(ch), int(accumulate), _stream()), 'xtrl_seg2d_copy')
 
 
 def mlp_pack(w1p, w2p, out=None):
