@@ -7,21 +7,21 @@
 // per-score softmax arithmetic, so the design is about instructions per score and about never making the threads wait
 // for the tensor core:
 //   * one CTA per (episode, head); q, k, v (and dO) live in shared memory as token-major bf16 images for the life of
-//     the CTA.  16 compute warps = 4 threads per query row of a [128 queries x 64 keys] step (TMEM lane = query),
-//     plus ONE warp that only issues MMAs.  Rings of TMEM score tiles, operand images and mbarriers keep the tensor
-//     core a step or more ahead of and behind the threads; the loop has no __syncthreads.
+//     the CTA.  16 compute warps work on [128 x 128] score tiles (TMEM lane = query in the forward, = key in the
+//     backward), plus one (forward) or two (backward) warps that only issue MMAs.  TMEM score tiles and mbarriers keep the
+//     tensor core ahead of and behind the threads; the loops have no __syncthreads.
 //   * forward: the softmax shift of a row is the bound scale * |q_row| * max|k| (Cauchy-Schwarz), so each score is visited
-//     once: P = exp(s - shift), rounded to bf16 with the dropout mask ANDed in, is written as the A operand of O += P V;
-//     the row sum is kept in fp32; logsumexp is saved.  If the bound is loose (> 40) the CTA takes an unpipelined path
-//     with an exact row-max pass first.
-//   * backward: per step S and dP~ = dO V^T from the tensor core; the threads form P~ (dropped P) and
-//     dS' = P~ dP~ - P delta as operand images; dV += P~^T dO, dK += dS'^T Q, dQ += dS' K accumulate in TMEM (the
-//     transposed operands are the same images read MN-major; scale is applied when dQ / dK are written).  dQ of all four
-//     query tiles stays in TMEM until the end: no atomics, deterministic.
+//     once: P = exp(s - shift), rounded to bf16 with the dropout mask ANDed in, goes to the tensor core THROUGH TENSOR
+//     MEMORY as the A operand of O += P V; the row sum is kept in fp32; logsumexp is saved.  If the bound is loose (> 40)
+//     the same loop runs twice per query tile: an exact row-max pass first.
+//   * backward: S^T and dP~^T from the tensor core; the threads form P~^T (dropped P) and dS'^T = P~ dP~ - P delta, which
+//     feed dV += P~^T dO and dK += dS'^T Q through tensor memory and dQ += dS' K through one shared-memory image; scale is
+//     applied when dQ / dK are written.  dQ of all four query tiles stays in TMEM until the end: no atomics, deterministic.
+// (The round-1 kernels -- 64-key steps, P / dS handed over as shared-memory images -- are in the history: 190 / 379 us
+//  against 165 / 303 us at the c3 minibatch.)
 // The dropout mask is a counter hash of (call key, step counter, episode*head, query, key), regenerated in the
 // backward; p is quantised to 1/128.
 #include "learn_common.cuh"
-#include <stdlib.h>
 
 namespace xtrl {
 namespace core {
@@ -31,7 +31,6 @@ using learn::pack2; using learn::pk2; using learn::upk2; using learn::fma2; usin
 constexpr int R = 512, NCOMP = 512, NTH = NCOMP + 32, DH = 16;      // 16 compute warps + one warp that only issues MMAs
 constexpr int kImg = R * DH * 2;              // one q / k / v / dO image: 2 chunks of 8 dims x 512 rows x 16 B
 constexpr int kChunk = R * 16;                // bytes between the two 8-dim chunks
-constexpr int kTileImg = 128 * 128 * 2;       // P / dS operand image of one tile
 constexpr int kTCore = 128 * 16;              // bytes between 8-key chunks of a tile image
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr uint32_t kIdA = learn::kIdA, kIdB = learn::kIdB;
@@ -89,14 +88,6 @@ __device__ __forceinline__ uint32_t keep4(uint32_t hseed, int g, uint32_t add4) 
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 15;
     return (h & 0x7f7f7f7fu) + add4;
 }
-// [n][16] bf16 rows of one (episode, head) -> 512-row token-major image (rows >= n zero, up to `rows`)
-__device__ __forceinline__ void load_img(unsigned char *img, const __nv_bfloat16 *src, int n, int rows, int tid) {
-    for (int i = tid; i < rows * 2; i += NTH) {
-        const int r = i >> 1, c = i & 1;
-        const uint4 v = r < n ? __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * DH) + c) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4 *>(img + c * kChunk + (r >> 3) * 128 + (r & 7) * 16) = v;
-    }
-}
 // NA arrays at once: every thread first issues all its 16-byte loads (2 per array), then stores them
 template <int NA>
 __device__ __forceinline__ void load_imgs(unsigned char *const (&img)[NA], const __nv_bfloat16 *const (&src)[NA], int n, int rows, int tid) {
@@ -126,12 +117,6 @@ __device__ __forceinline__ float row_norm2(const unsigned char *img, int r) {
     for (int j = 0; j < 8; ++j) s = fmaf(x[j], x[j], fmaf(y[j], y[j], s));
     return s;
 }
-// 16 consecutive keys of this thread's query row (already packed bf16 pairs) -> two 16-byte pieces of a tile image
-__device__ __forceinline__ void put16w(unsigned char *img, int row, int col0, const uint32_t (&w)[8]) {
-    unsigned char *p = img + (col0 >> 3) * kTCore + (row >> 3) * 128 + (row & 7) * 16;
-    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4 *>(p + kTCore) = make_uint4(w[4], w[5], w[6], w[7]);
-}
 // Descriptors are built once per operand; every MMA then only adds a start-address offset (in 16-byte units) -- a
 // tcgen05.mma of these shapes costs ~48 cycles of issue, building a descriptor from a pointer costs about as much again.
 // token-major 512-row image: rows(t) = K-major operand [128 rows of tile t x K=16] (64-row key tiles: + kt * 64);
@@ -158,248 +143,7 @@ __device__ __forceinline__ void images_ready(uint64_t *bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
-// ---- step schedule ---------------------------------------------------------------------------------------
-// Scores are produced in steps of one [128 queries x 64 keys] tile.  A step is software-pipelined against the
-// tensor core: while the threads turn tile i into operand images, the MMAs that produce tile i+1.. and the
-// products of tile i-1 are in flight (rings of TMEM tiles, operand images and mbarriers).
-constexpr int KT = 64;                        // keys per step
-constexpr int kStepImg = 128 * KT * 2;        // P / dS operand image of one step (8 key chunks x 2048 B)
-
-// block-local first key of this thread's 16-key chunk relative to the query tile's first row (>= 0 only on the diagonal block)
-struct StepGeom { int qt, kt, keyb; bool diag; };
-__device__ __forceinline__ StepGeom geom(int qt, int kt, int c4) {
-    StepGeom g;
-    g.qt = qt; g.kt = kt; g.diag = (kt >> 1) == qt;
-    g.keyb = (kt - 2 * qt) * KT + c4 * 16;
-    return g;
-}
-
-// one 16-key chunk of the forward: P = 2^(s*sl2 + off) (dropout folded in), returns the chunk's row sum
-template <bool DIAG>
-__device__ __forceinline__ float fwd_chunk(uint32_t taddr, unsigned char *sP, int row, int col0, int keyb, float sl2, float off,
-                                           uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t add4) {
-    uint32_t r[16], w[8];
-    tmem_ld16_issue(taddr, r);
-    tmem_ld_wait();
-    tmem_pin16(r);
-    const uint64_t sl22 = pk2(sl2, sl2), off2 = pk2(off, off);
-    uint64_t l2 = pk2(0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-        float x0, x1;
-        upk2(fma2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sl22, off2), x0, x1);
-        float p0 = ex2(x0), p1 = ex2(x1);
-        if (DIAG) { p0 = keyb + j <= row ? p0 : 0.f; p1 = keyb + j + 1 <= row ? p1 : 0.f; }
-        l2 = add2(l2, pk2(p0, p1));
-        w[j >> 1] = pack2(p0, p1);
-    }
-    float l, lh;
-    upk2(l2, l, lh);
-    l += lh;
-    if (add4) {
-        const uint32_t hseed = (qrow * (uint32_t)(R / 4) + g4) * kGolden + ckey;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const uint32_t t = keep4(hseed, g, add4);
-            w[2 * g] &= prmt(t, 0x9988);
-            w[2 * g + 1] &= prmt(t, 0xbbaa);
-        }
-    }
-    put16w(sP, row, col0, w);
-    return l;
-}
-
-// -------------------------------------------------------------------------------------------- forward
-constexpr int kFwdSmem = 3 * kImg + 2 * kStepImg + 2 * 4 * 128 * 4 + R * 4 + 128;
 constexpr float kBoundMax = 40.f;             // use the norm bound instead of the exact row max while it is below this
-
-__global__ void __launch_bounds__(NTH, 2) attn_core_fwd_kernel(const Args a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sQ = smem, *sK = sQ + kImg, *sV = sK + kImg, *sP = sV + kImg;              // sP: ring of 2 step images
-    float *sRed = reinterpret_cast<float *>(sP + 2 * kStepImg);             // [2][4][128]
-    float *sQn = sRed + 2 * 4 * 128;                                         // |q_row|^2
-    uint64_t *bS = reinterpret_cast<uint64_t *>(sQn + R), *bP = bS + 3, *bI = bP + 2;      // S tile ready (3), P.V done (2), image ready (2)
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bI + 2);
-    int *sMax = reinterpret_cast<int *>(tslot + 1);                          // [0] max |k|^2, [1] max |q|^2 (float bits)
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q4 = warp & 3, c4 = warp >> 2, row = q4 * 32 + lane;           // c4 == 4: the MMA warp
-    const int bh = blockIdx.x, n = a.n, nt = (n + 127) >> 7;
-    constexpr uint32_t cS = 0, cO = 192;
-    if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(&bS[i], 1);
-        mbar_init(&bI[0], NCOMP / 32); mbar_init(&bI[1], NCOMP / 32);
-        fence_mbar_init(); sMax[0] = 0; sMax[1] = 0;
-    }
-    if (warp == 0) tmem_alloc(tslot, 256);
-    const size_t base = (size_t)bh * n * DH;
-    {
-        unsigned char *const imgs[3] = {sQ, sK, sV};
-        const __nv_bfloat16 *const srcs[3] = {a.q + base, a.k + base, a.v + base};
-        load_imgs<3>(imgs, srcs, n, nt * 128, tid);
-    }
-    __syncthreads();
-    for (int r = tid; r < nt * 128 + 32; r += NTH) {                         // norms for the softmax shift bound (whole warps: shuffles)
-        const bool in = r < nt * 128;
-        const float qn = in ? row_norm2(sQ, r) : 0.f, kn = learn::warp_max_f(in ? row_norm2(sK, r) : 0.f), qm = learn::warp_max_f(qn);
-        if (in) sQn[r] = qn;
-        if (lane == 0) { atomicMax(&sMax[0], __float_as_int(kn)); atomicMax(&sMax[1], __float_as_int(qm)); }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q4 * 32) << 16);
-    const uint32_t ckey = cta_key(a.rng_step, a.rng_key, (uint32_t)bh);
-    const float sl2 = a.scale * kLog2e;
-    const float kmax2 = __int_as_float(sMax[0]);
-    const bool bounded = a.scale * sqrtf(kmax2 * __int_as_float(sMax[1])) <= kBoundMax;          // CTA-uniform
-    const int total = nt * (nt + 1);                                         // steps: sum over qt of 2 qt + 2
-    auto advance = [&](int &qt, int &kt) { if (++kt > 2 * qt + 1) { kt = 0; ++qt; } };
-    const ImgDesc dQ_(sQ), dK_(sK), dV_(sV);
-    const StepDesc dP0(sP), dP1(sP + kStepImg);
-    auto issue_s = [&](int qt, int kt, int buf, uint64_t *bar) {             // S tile = Q_qt K_kt^T (one thread)
-        mma_bf16_ss(tbase + cS + buf * KT, dQ_.rows + qt * 128, dK_.rows + kt * 64, idesc_bf16(128, KT), 0);
-        mma_commit(bar);
-    };
-    auto issue_pv = [&](int qt, int kt, int slot, uint64_t *bar) {           // O[qt & 1] (+)= P V_kt
-        const uint64_t pa = slot ? dP1.kmaj : dP0.kmaj, vb = dV_.cols + kt * 64;
-#pragma unroll
-        for (int s = 0; s < KT / 16; ++s)
-            mma_bf16_ss(tbase + cO + (qt & 1) * DH, pa + s * 256, vb + s * 16, idesc_bf16(128, DH) | kIdB, kt > 0 || s > 0);
-        mma_commit(bar);
-    };
-
-    if (warp == NCOMP / 32) {
-        // ---- MMA warp: keeps three S tiles in flight, turns every finished P image into O += P V ----
-        if (lane == 0) {
-            uint32_t phx = 0;
-            int iq = 0, ik = 0, qt = 0, kt = 0;
-            tc_fence_after();
-            if (bounded) {
-                for (int i = 0; i < 3 && i < total; ++i) { issue_s(iq, ik, i, &bS[i]); advance(iq, ik); }
-                for (int i = 0; i < total; ++i) {
-                    mbar_wait_sleep(&bI[i & 1], (i >> 1) & 1, 1000);
-                    tc_fence_after();
-                    issue_pv(qt, kt, i & 1, &bP[i & 1]);
-                    if (i + 3 < total) { issue_s(iq, ik, i % 3, &bS[i % 3]); advance(iq, ik); }
-                    advance(qt, kt);
-                }
-            } else {
-                // exact-max fallback: per query tile one pass of S tiles for the max, then S / P.V one step at a time
-                for (int q = 0; q < nt; ++q) {
-                    for (int pass = 0; pass < 2; ++pass)
-                        for (int k = 0; k <= 2 * q + 1; ++k) {
-                            issue_s(q, k, 0, &bS[0]);
-                            mbar_wait(&bI[0], phx); phx ^= 1;                 // the compute warps are done with the S tile (and wrote P in pass 1)
-                            tc_fence_after();
-                            if (pass == 1) issue_pv(q, k, 0, &bP[0]);
-                        }
-                }
-            }
-        }
-    } else if (!bounded) {
-        // ---- compute warps, exact-max fallback (norm bound too loose to be a safe softmax shift; unpipelined) ----
-        uint32_t phs = 0, php = 0;
-        for (int qt = 0; qt < nt; ++qt) {
-            float m = -INFINITY;
-            for (int kt = 0; kt <= 2 * qt + 1; ++kt) {
-                mbar_wait(&bS[0], phs); phs ^= 1;
-                tc_fence_after();
-                float s[16];
-                tmem_ld16(tlane + cS + c4 * 16, s);
-                const int keyb = (kt - 2 * qt) * KT + c4 * 16;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) m = fmaxf(m, keyb + j <= row ? s[j] : -INFINITY);
-                images_ready(&bI[0], lane);
-            }
-            sRed[c4 * 128 + row] = m;
-            csync();
-            m = fmaxf(fmaxf(sRed[row], sRed[128 + row]), fmaxf(sRed[256 + row], sRed[384 + row])) * a.scale;
-            csync();
-            const float off = a.drop_log2scale - m * kLog2e;
-            float l = 0.f;
-            for (int kt = 0; kt <= 2 * qt + 1; ++kt) {
-                mbar_wait(&bS[0], phs); phs ^= 1;
-                if (kt > 0 || qt > 0) { mbar_wait(&bP[0], php); php ^= 1; }   // the previous P.V has read the image
-                tc_fence_after();
-                const int keyb = (kt - 2 * qt) * KT + c4 * 16;
-                const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
-                if (keyb <= q4 * 32 + 31) l += fwd_chunk<true>(tlane + cS + c4 * 16, sP, row, c4 * 16, keyb, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_add4);
-                else { const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; put16w(sP, row, c4 * 16, z); }
-                images_ready(&bI[0], lane);
-            }
-            sRed[c4 * 128 + row] = l;
-            csync();
-            mbar_wait(&bP[0], php);                                           // last P.V of the tile (parity consumed by the next tile's first wait)
-            tc_fence_after();
-            const int qrow = qt * 128 + row;
-            const float lt = ((sRed[row] + sRed[128 + row]) + (sRed[256 + row] + sRed[384 + row])) / a.drop_scale;
-            if (c4 < 2) {
-                float o[8];
-                tmem_ld8(tlane + cO + (qt & 1) * DH + c4 * 8, o);
-                const float inv = 1.f / lt;
-                if (qrow < n)
-                    *reinterpret_cast<uint4 *>(a.out + base + (size_t)qrow * DH + c4 * 8) =
-                        make_uint4(pack2(o[0] * inv, o[1] * inv), pack2(o[2] * inv, o[3] * inv), pack2(o[4] * inv, o[5] * inv), pack2(o[6] * inv, o[7] * inv));
-            } else if (c4 == 2 && qrow < n) {
-                a.lse[(size_t)bh * n + qrow] = m + __logf(lt);
-            }
-            tc_fence_before();
-            csync();
-        }
-    } else {
-        // ---- compute warps, pipelined ----
-        auto row_shift = [&](int qt) -> float {                              // >= every scaled score of the row (Cauchy-Schwarz)
-            return a.scale * sqrtf(kmax2 * sQn[qt * 128 + row]) * 1.0002f + 1e-4f;
-        };
-        auto finalize = [&](int qt, float m, int wait_step) {                // O / l and logsumexp of query tile qt
-            if (wait_step >= 0) mbar_wait(&bP[wait_step & 1], (wait_step >> 1) & 1);
-            tc_fence_after();
-            const int qrow = qt * 128 + row;
-            const float *red = sRed + (qt & 1) * 512;
-            const float l = ((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])) / a.drop_scale;
-            if (c4 < 2) {
-                float o[8];
-                tmem_ld8(tlane + cO + (qt & 1) * DH + c4 * 8, o);
-                const float inv = 1.f / l;
-                if (qrow < n)
-                    *reinterpret_cast<uint4 *>(a.out + base + (size_t)qrow * DH + c4 * 8) =
-                        make_uint4(pack2(o[0] * inv, o[1] * inv), pack2(o[2] * inv, o[3] * inv), pack2(o[4] * inv, o[5] * inv), pack2(o[6] * inv, o[7] * inv));
-            } else if (c4 == 2 && qrow < n) {
-                a.lse[(size_t)bh * n + qrow] = m + __logf(l);
-            }
-            tc_fence_before();
-        };
-        int qt = 0, kt = 0;
-        float m = row_shift(0), m_prev = 0.f, l = 0.f;
-        float off = a.drop_log2scale - m * kLog2e;
-        for (int i = 0; i < total; ++i) {
-            const int sb = i % 3, pb = i & 1;
-            mbar_wait_sleep(&bS[sb], (i / 3) & 1, 400);
-            if (i >= 2) mbar_wait(&bP[pb], ((i - 2) >> 1) & 1);               // the P.V that read this image is done
-            tc_fence_after();
-            const StepGeom g = geom(qt, kt, c4);
-            const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
-            unsigned char *img = sP + pb * kStepImg;
-            if (!g.diag) l += fwd_chunk<false>(tlane + cS + sb * KT + c4 * 16, img, row, c4 * 16, 0, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_add4);
-            else if (g.keyb <= q4 * 32 + 31) l += fwd_chunk<true>(tlane + cS + sb * KT + c4 * 16, img, row, c4 * 16, g.keyb, sl2, off, (uint32_t)(qt * 128 + row), g4, ckey, a.drop_add4);
-            else { const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; put16w(img, row, c4 * 16, z); }
-            images_ready(&bI[pb], lane);
-            const bool last_of_q = kt == 2 * qt + 1;
-            if (kt == 1 && qt > 0) finalize(qt - 1, m_prev, -1);              // one step late: its last P.V (step i-2) completed with the wait above
-            if (last_of_q) {
-                sRed[(qt & 1) * 512 + c4 * 128 + row] = l;
-                csync();                                                     // row sums of the four column quarters meet here
-                m_prev = m; l = 0.f;
-                if (qt + 1 < nt) { m = row_shift(qt + 1); off = a.drop_log2scale - m * kLog2e; }
-            }
-            advance(qt, kt);
-        }
-        finalize(nt - 1, m_prev, total - 1);
-    }
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 256);
-}
 
 // ---------------------------------------------------------------------------------------- forward, version 2
 // Steps of one [128 queries x 128 keys] tile: a thread turns 32 scores per step into probabilities (two chunks of 16 keys), so
@@ -608,193 +352,11 @@ __global__ void __launch_bounds__(NTH, 2) attn_core_fwd2_kernel(const Args a) {
     if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
-// ------------------------------------------------------------------------------------------- backward
-// shared-memory order: the step images first -- dV / dK read them MN-major with M = 128 keys although a step holds
-// 64, so each read runs 16 KB past its image into the next one (the last into sQ); the accumulator rows those
-// bytes feed (TMEM lanes 64..127) are never read.
-constexpr int kBwdRing = 3;                   // (P~, dS) image pairs in flight
-constexpr int kBwdSmem = 2 * kBwdRing * kStepImg + 4 * kImg + 2 * R * 4 + 128;
-
-// one 16-key chunk of the backward: P~ and dS' = P~ dP~ - P delta (the softmax scale is applied to dQ / dK at the end)
-template <bool DIAG>
-__device__ __forceinline__ void bwd_chunk(uint32_t ts, uint32_t tdp, unsigned char *sP, unsigned char *sdS, int row, int col0, int keyb,
-                                          float sl2, float off, float ndelta, uint32_t qrow, uint32_t g4, uint32_t ckey, uint32_t add4) {
-    uint32_t rs[16], rd[16], wp[8], wd[8];
-    tmem_ld16_issue(ts, rs);
-    tmem_ld16_issue(tdp, rd);
-    tmem_ld_wait();
-    tmem_pin16(rs);
-    tmem_pin16(rd);
-    const uint32_t hseed = (qrow * (uint32_t)(R / 4) + g4) * kGolden + ckey;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint32_t t = add4 ? keep4(hseed, g, add4) : 0x80808080u;
-        float pd[4], ds[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int j = 4 * g + i;
-            float ps = ex2(fmaf(__uint_as_float(rs[j]), sl2, off));          // P * drop_scale
-            if (DIAG) ps = keyb + j <= row ? ps : 0.f;
-            pd[i] = __uint_as_float(__float_as_uint(ps) & prmt(t, 0x8888 + 0x1111 * i));
-            ds[i] = fmaf(pd[i], __uint_as_float(rd[j]), ps * ndelta);
-        }
-        wp[2 * g] = pack2(pd[0], pd[1]); wp[2 * g + 1] = pack2(pd[2], pd[3]);
-        wd[2 * g] = pack2(ds[0], ds[1]); wd[2 * g + 1] = pack2(ds[2], ds[3]);
-    }
-    put16w(sP, row, col0, wp);
-    put16w(sdS, row, col0, wd);
-}
-
+// ---- shared by the backward ----
 __device__ __forceinline__ void store_row16(__nv_bfloat16 *p, const float (&v)[16], float f) {
     uint4 *dst = reinterpret_cast<uint4 *>(p);
     dst[0] = make_uint4(pack2(v[0] * f, v[1] * f), pack2(v[2] * f, v[3] * f), pack2(v[4] * f, v[5] * f), pack2(v[6] * f, v[7] * f));
     dst[1] = make_uint4(pack2(v[8] * f, v[9] * f), pack2(v[10] * f, v[11] * f), pack2(v[12] * f, v[13] * f), pack2(v[14] * f, v[15] * f));
-}
-
-__global__ void __launch_bounds__(NTH, 1) attn_core_bwd_kernel(const Args a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sStep = smem;                                             // [kBwdRing] x (P~ image, dS image)
-    unsigned char *sQ = sStep + 2 * kBwdRing * kStepImg, *sK = sQ + kImg, *sV = sK + kImg, *sdO = sV + kImg;
-    float *sL = reinterpret_cast<float *>(sdO + kImg), *sDelta = sL + R;
-    uint64_t *bS = reinterpret_cast<uint64_t *>(sDelta + R), *bP = bS + 3, *bI = bP + kBwdRing;   // S / dP~ ready (ring of 3), products done, images ready
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bI + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q4 = warp & 3, c4 = warp >> 2, row = q4 * 32 + lane;           // c4 == 4: the MMA warp
-    const int bh = blockIdx.x, n = a.n, nt = (n + 127) >> 7;
-    constexpr uint32_t cS = 0, cDP = 192, cDQ = 384, cDK = 448, cDV = 480;    // S, dP~: rings of 3 x 64; dK, dV: two buffers of 16 columns
-    if (tid == 0) {
-        for (int i = 0; i < 3 + kBwdRing; ++i) mbar_init(&bS[i], 1);
-        for (int i = 0; i < kBwdRing; ++i) mbar_init(&bI[i], NCOMP / 32);
-        fence_mbar_init();
-    }
-    if (warp == 0) tmem_alloc(tslot, 512);
-    const size_t base = (size_t)bh * n * DH;
-    {
-        unsigned char *const imgs[4] = {sQ, sK, sV, sdO};
-        const __nv_bfloat16 *const srcs[4] = {a.q + base, a.k + base, a.v + base, a.d_o + base};
-        load_imgs<4>(imgs, srcs, n, nt * 128, tid);
-    }
-    for (int r = tid; r < nt * 128; r += NTH) {                              // delta = rowsum(dO . O); logsumexp in log2 units
-        float d = 0.f, L = 1e30f;
-        if (r < n) {
-            const uint4 *po = reinterpret_cast<const uint4 *>(a.o + base + (size_t)r * DH), *pd = reinterpret_cast<const uint4 *>(a.d_o + base + (size_t)r * DH);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float x[8], y[8];
-                learn::unpack8(__ldg(po + c), x);
-                learn::unpack8(__ldg(pd + c), y);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) d = fmaf(x[j], y[j], d);
-            }
-            L = a.lse[(size_t)bh * n + r] * kLog2e;
-        }
-        sDelta[r] = -d / a.drop_scale;
-        sL[r] = a.drop_log2scale - L;
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q4 * 32) << 16);
-    const uint32_t ckey = cta_key(a.rng_step, a.rng_key, (uint32_t)bh);
-    const float sl2 = a.scale * kLog2e;
-    const int total = nt * (nt + 1);                                         // steps: key tile kt (64 keys) x query tiles qt >= kt/2
-    auto advance = [&](int &kt, int &qt) { if (++qt >= nt) { ++kt; qt = kt >> 1; } };
-
-    if (warp == NCOMP / 32) {
-        // ---- MMA warp ----
-        if (lane == 0) {
-            const ImgDesc dQ_(sQ), dK_(sK), dV_(sV), dO_(sdO);
-            const StepDesc dP0(sStep), dS0(sStep + kStepImg);                 // slot b: + b * 2 * kStepImg bytes = + b * 2048 in descriptor units
-            auto issue_s = [&](int kt, int qt, int buf, uint64_t *bar) {     // S = Q K^T and dP~ = dO V^T of one step
-                mma_bf16_ss(tbase + cS + buf * KT, dQ_.rows + qt * 128, dK_.rows + kt * 64, idesc_bf16(128, KT), 0);
-                mma_bf16_ss(tbase + cDP + buf * KT, dO_.rows + qt * 128, dV_.rows + kt * 64, idesc_bf16(128, KT), 0);
-                mma_commit(bar);
-            };
-            int ik = 0, iq = 0, kt = 0, qt = 0;
-            tc_fence_after();
-            for (int i = 0; i < 3 && i < total; ++i) { issue_s(ik, iq, i, &bS[i]); advance(ik, iq); }
-            for (int i = 0; i < total; ++i) {
-                const int b = i % kBwdRing;
-                mbar_wait(&bI[b], (i / kBwdRing) & 1);
-                tc_fence_after();
-                StepDesc dP = dP0, dS = dS0;
-                dP.kmaj += b * (2 * kStepImg / 16); dP.mnmaj += b * (2 * kStepImg / 16);
-                dS.kmaj += b * (2 * kStepImg / 16); dS.mnmaj += b * (2 * kStepImg / 16);
-                const bool first_q = qt == (kt >> 1);
-                const uint64_t doc = dO_.cols + qt * 128, qc = dQ_.cols + qt * 128, kc = dK_.cols + kt * 64;
-                const uint32_t tdv = tbase + cDV + (kt & 1) * DH, tdk = tbase + cDK + (kt & 1) * DH, tdq = tbase + cDQ + qt * DH;
-#ifndef XTRL_EXP_NOPROD
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {                                 // K = 128 queries
-                    mma_bf16_ss(tdv, dP.mnmaj + s * 16, doc + s * 16, idesc_bf16(128, DH) | kIdA | kIdB, !first_q || s > 0);        // dV += P~^T dO
-                    mma_bf16_ss(tdk, dS.mnmaj + s * 16, qc + s * 16, idesc_bf16(128, DH) | kIdA | kIdB, !first_q || s > 0);         // dK += dS^T Q
-                }
-#pragma unroll
-                for (int s = 0; s < KT / 16; ++s)                             // K = 64 keys
-                    mma_bf16_ss(tdq, dS.kmaj + s * 256, kc + s * 16, idesc_bf16(128, DH) | kIdB, kt > 0 || s > 0);                  // dQ += dS K
-#endif
-                mma_commit(&bP[b]);
-                if (i + 3 < total) { issue_s(ik, iq, i % 3, &bS[i % 3]); advance(ik, iq); }
-                advance(kt, qt);
-            }
-        }
-    } else {
-        // ---- compute warps ----
-        auto write_dkv = [&](int kt) {                                       // dK, dV rows of key tile kt (lanes 0..63)
-            if (c4 < 2 && q4 < 2) {
-                float v[16];
-                tmem_ld16(tlane + (c4 == 0 ? cDK : cDV) + (kt & 1) * DH, v);
-                const int krow = kt * KT + row;
-                if (krow < n) store_row16((c4 == 0 ? a.dk : a.dv) + base + (size_t)krow * DH, v, c4 == 0 ? a.scale : 1.f);
-            }
-        };
-        int kt = 0, qt = 0, pend_kt = -1, pend_ready = 0;                     // a finished key tile whose dK, dV are still in TMEM
-        for (int i = 0; i < total; ++i) {
-            const int b = i % kBwdRing, sb = i % 3;
-            mbar_wait(&bS[sb], (i / 3) & 1);
-            if (i >= kBwdRing) mbar_wait(&bP[b], ((i - kBwdRing) / kBwdRing) & 1);      // the products that read these images are done
-            tc_fence_after();
-            const bool new_tile = qt == (kt >> 1) && kt > 0;
-            if (pend_kt >= 0 && (i >= pend_ready + kBwdRing || new_tile)) {       // dK, dV of a finished key tile: normally its products
-                if (i < pend_ready + kBwdRing) {                                 // completed with the wait above; a one-step tile in
-                    mbar_wait(&bP[pend_ready % kBwdRing], (pend_ready / kBwdRing) & 1);      // between forces an explicit wait
-                    tc_fence_after();
-                }
-                write_dkv(pend_kt);
-                pend_kt = -1;
-            }
-            if (new_tile) { pend_kt = kt - 1; pend_ready = i - 1; }
-            unsigned char *imgP = sStep + b * 2 * kStepImg, *imgS = imgP + kStepImg;
-            const StepGeom g = geom(qt, kt, c4);
-            const int qrow = qt * 128 + row;
-            const float off = sL[qrow], ndelta = sDelta[qrow];
-            const uint32_t g4 = (uint32_t)(kt * KT + c4 * 16) >> 2;
-            const uint32_t ts = tlane + cS + sb * KT + c4 * 16, tdp = tlane + cDP + sb * KT + c4 * 16;
-            if (!g.diag) bwd_chunk<false>(ts, tdp, imgP, imgS, row, c4 * 16, 0, sl2, off, ndelta, (uint32_t)qrow, g4, ckey, a.drop_add4);
-            else if (g.keyb <= q4 * 32 + 31) bwd_chunk<true>(ts, tdp, imgP, imgS, row, c4 * 16, g.keyb, sl2, off, ndelta, (uint32_t)qrow, g4, ckey, a.drop_add4);
-            else {
-                const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                put16w(imgP, row, c4 * 16, z);
-                put16w(imgS, row, c4 * 16, z);
-            }
-            images_ready(&bI[b], lane);
-            advance(kt, qt);
-        }
-        mbar_wait(&bP[(total - 1) % kBwdRing], ((total - 1) / kBwdRing) & 1);
-        tc_fence_after();
-        if (pend_kt >= 0) write_dkv(pend_kt);
-        write_dkv(2 * nt - 1);
-        if (c4 < nt) {                                                       // dQ of query tile c4
-            float v[16];
-            tmem_ld16(tlane + cDQ + c4 * DH, v);
-            const int qrow = c4 * 128 + row;
-            if (qrow < n) store_row16(a.dq + base + (size_t)qrow * DH, v, a.scale);
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------ backward, version 2
@@ -1083,13 +645,11 @@ extern "C" int xtrl_attn_core_fwd(const xtrl_attn_core_io *io, int32_t bh, int32
     if (int rc = fill(io, n, dim_head, a)) return rc;
     static bool attr = false;
     if (!attr) {
-        XTRL_CUDA(cudaFuncSetAttribute(attn_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
         XTRL_CUDA(cudaFuncSetAttribute(attn_core_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem));
         XTRL_CUDA(cudaFuncSetAttribute(attn_core_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem));
         attr = true;
     }
-    if (getenv("XTRL_CORE_FWD_V1")) attn_core_fwd_kernel<<<bh, NTH, kFwdSmem, (cudaStream_t)stream>>>(a);
-    else if (a.drop_add4) attn_core_fwd2_kernel<true><<<bh, NTH, kFwd2Smem, (cudaStream_t)stream>>>(a);
+    if (a.drop_add4) attn_core_fwd2_kernel<true><<<bh, NTH, kFwd2Smem, (cudaStream_t)stream>>>(a);
     else attn_core_fwd2_kernel<false><<<bh, NTH, kFwd2Smem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("attn_core_fwd_kernel");
     return XTRL_OK;
@@ -1105,18 +665,11 @@ extern "C" int xtrl_attn_core_bwd(const xtrl_attn_core_io *io, int32_t bh, int32
     if (int rc = fill(io, n, dim_head, a)) return rc;
     static bool attr = false;
     if (!attr) {
-        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
         XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
         XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
-        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
-        XTRL_CUDA(cudaFuncSetAttribute(attn_core_bwd2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwd2Smem));
         attr = true;
     }
-    if (getenv("XTRL_CORE_BWD_V1")) attn_core_bwd_kernel<<<bh, NTH, kBwdSmem, (cudaStream_t)stream>>>(a);
-    else if (getenv("XTRL_CORE_BWD_CQ2")) {
-        if (a.drop_add4) attn_core_bwd2_kernel<true, 2><<<bh, 320, kBwd2Smem, (cudaStream_t)stream>>>(a);
-        else attn_core_bwd2_kernel<false, 2><<<bh, 320, kBwd2Smem, (cudaStream_t)stream>>>(a);
-    } else if (a.drop_add4) attn_core_bwd2_kernel<true, 1><<<bh, NTH2, kBwd2Smem, (cudaStream_t)stream>>>(a);
+    if (a.drop_add4) attn_core_bwd2_kernel<true, 1><<<bh, NTH2, kBwd2Smem, (cudaStream_t)stream>>>(a);
     else attn_core_bwd2_kernel<false, 1><<<bh, NTH2, kBwd2Smem, (cudaStream_t)stream>>>(a);
     XTRL_LAUNCH_CHECK("attn_core_bwd_kernel");
     return XTRL_OK;
