@@ -529,3 +529,66 @@ def test_learn_prologue_forward_backward_vs_torch(continuous, S, A, E, b, T):
                        grads['b_act'], grads['re'], continuous=continuous)
     for name, p in (('w_in', w_in), ('w_se', w_se), ('b_se', b_se), ('w_act', w_act), ('re', re)) + ((('b_act', b_act),) if continuous else ()):
         assert maxrel(grads[name], p.grad) < 1e-4, (name, maxrel(grads[name], p.grad))
+
+
+# ---------------------------------------------------------------------------------------------
+# the launch-count helpers of the captured learn graph
+# ---------------------------------------------------------------------------------------------
+
+def test_seg2d_copy_and_accumulate_vs_torch():
+    """xtrl_seg2d_copy: rectangular blocks between parameter tensors and padded dense buffers (head refresh / scatter)"""
+    ops = xtrl().ops
+    g = torch.Generator().manual_seed(3)
+    r = lambda *s: torch.randn(*s, generator=g).to(DEV)
+    pad_w, pad_b = torch.zeros(64, 96, device=DEV), torch.zeros(64, device=DEV)
+    w0, b0, w1, b1 = r(48, 96), r(48), r(1, 96), r(1)
+    pad_w2, w2 = torch.zeros(32, 64, device=DEV), r(19, 48)
+    pairs = [(w0, pad_w[0:48]), (b0, pad_b[0:48]), (w1, pad_w[48:49]), (b1, pad_b[48:49]), (w2, pad_w2[0:19, :48])]
+    ops.SegTable(pairs).run()
+    assert torch.equal(pad_w[:48], w0) and torch.equal(pad_w[48], w1[0]) and torch.equal(pad_b[:48], b0) and pad_b[48] == b1[0]
+    assert torch.equal(pad_w2[:19, :48], w2) and float(pad_w2[:, 48:].abs().sum()) == 0 and float(pad_w[49:].abs().sum()) == 0
+    # nine blocks (two launches of <= 8) accumulating the other way, as the gradient scatter does
+    grads = [torch.ones_like(t) for t, _ in pairs] + [torch.ones(5, device=DEV) for _ in range(4)]
+    srcs = [d for _, d in pairs] + [r(5) for _ in range(4)]
+    want = [gd + s_ for gd, s_ in zip(grads, srcs)]
+    ops.SegTable(list(zip(srcs, grads))).run(accumulate=True)
+    for got, ref in zip(grads, want):
+        assert torch.equal(got, ref)
+
+
+def test_attention_block_node_equals_the_three_nodes():
+    """_FusedAttnBlock (one autograd node, residual gradient added inside xtrl_attn_pre_bwd) against _FusedAttnPre ->
+    _FusedAttnCore -> _FusedAttnPost with autograd's own add: same forward bits, same dx up to the order of one fp32 add,
+    parameter gradients equal up to the atomicAdd order of the weight-gradient flush."""
+    from importlib import import_module
+    M, ops = import_module('x-transformers-rl_b200.model'), xtrl().ops
+    torch.manual_seed(0)
+    cfg = ops.ModelConfig(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=200, depth=1, heads=8, dim_head=16)
+    model = M.WorldModelActorCritic(cfg, dropout=0.25).to(DEV)
+    dec = model.transformer.attn_layers
+    norm, attn = dec.layers[0]
+    fs = model.fused_state()
+    ops.attn_pack(attn.to_q.weight.data, attn.to_k.weight.data, attn.to_v.weight.data, attn.to_out.weight.data, out=fs['attn_img'][0])
+    b, n = 3, 200
+    cos4, sin4 = model._rotary_tables(n)
+    assert model._rotary_tables(n)[0] is cos4                                  # cached per sequence length
+    lens = torch.tensor([200, 37, 150], dtype=torch.int32, device=DEV)
+    x0 = torch.randn(b, n, 48, device=DEV)
+    dy = torch.randn(b, n, 48, device=DEV)
+    outs = {}
+    for mode in ('block', 'nodes'):
+        model.flat_grads.zero_()
+        x = x0.clone().requires_grad_()
+        fs['rng_step'].fill_(7)                                                # the same dropout mask in both runs
+        if mode == 'block':
+            y = M._FusedAttnBlock.apply(x, norm, attn, fs['attn_img'][0], cos4, sin4, 8, lens, fs['rng_step'], 1000, 0.25)
+        else:
+            q, k, v = M._FusedAttnPre.apply(x, norm, attn, fs['attn_img'][0], cos4, sin4, 8, False, False)[:3]
+            o = M._FusedAttnCore.apply(q, k, v, fs['rng_step'], 1000, 0.25)
+            y = M._FusedAttnPost.apply(x, o, attn, fs['attn_img'][0], lens)
+        y.backward(dy)
+        outs[mode] = (y.detach().clone(), x.grad.clone(), model.flat_grads.clone())
+    (yb, dxb, gb), (yn, dxn, gn) = outs['block'], outs['nodes']
+    assert torch.equal(yb, yn)
+    assert maxrel(dxb, dxn) < 1e-6
+    assert maxrel(gb, gn) < 1e-5
