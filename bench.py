@@ -348,11 +348,11 @@ def run_b200(args, w):
         peak = peaks.get('hbm_gbs', 6650.0)
         achieved = alg / avg_s / 1e9
         traffic = None
-        prof = os.path.join(ROOT, 'profiles', 'r01_wm_step_traffic.json')
+        prof = os.path.join(ROOT, 'profiles', 'r02_wm_step_traffic.json')
         if os.path.exists(prof):
             traffic = json.load(open(prof)).get(f'{args.workload}_{kv}')
         return dict(kernel='wm_step_kernel', bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                    traffic=traffic, traffic_source='profiles/r01_wm_step_traffic.json (one ncu --set full capture of the launch at t=250; '
+                    traffic=traffic, traffic_source='profiles/r02_wm_step_traffic.json (one ncu --set full capture of the launch at t=250; '
                                                              'a recorded number, not measured in this run)' if traffic else None,
                     peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s',
                     bytes_per_launch=alg, launch_ms_avg=avg_s * 1e3, launch_ms_first=kern_ms[0], launch_ms_last=kern_ms[-1],
