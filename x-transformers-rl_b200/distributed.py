@@ -183,7 +183,7 @@ class PeerGroup:
         dist.barrier()
         return self
 
-    def ctx(self, timeout_s: float = 10.):
+    def ctx(self, timeout_s: float = 60.):
         """the xtrl_peer_ctx of the next step (bumps the epoch; every rank must call in lock step)"""
         from . import _lib as L
         import ctypes as C
