@@ -410,6 +410,11 @@ typedef struct xtrl_mlp_io {
     float *d_w1, *d_b1, *d_w2, *d_b2;
     int32_t n_silu;
     int32_t out_cols;
+    /* backward: d_src[s] = (bit s of d_src_accumulate ? d_src[s] : 0) + d_src_scale[s] * dX_s  (scale 0 is read as 1).  Lets
+     * several heads that share an input add their gradients into ONE buffer (with frac_gradient's factor, :114-116, :533)
+     * instead of three tensors and the adds that sum them.                                                          */
+    float d_src_scale[3];
+    int32_t d_src_accumulate;
 } xtrl_mlp_io;
 
 /*     rectangular blocks between the live parameters (several nn.Linear weights / biases) and the zero-padded dense

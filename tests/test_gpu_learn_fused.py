@@ -592,3 +592,40 @@ def test_attention_block_node_equals_the_three_nodes():
     assert torch.equal(yb, yn)
     assert maxrel(dxb, dxn) < 1e-6
     assert maxrel(gb, gn) < 1e-5
+
+
+def test_three_heads_node_equals_separate_heads():
+    """_FusedHeads3 (one autograd node; the three xtrl_mlp_bwd launches add into shared d_embed / d_se buffers with
+    frac_gradient's factor, xtrl_mlp_io.d_src_scale / d_src_accumulate) against three _FusedHead nodes + _FracGrad + autograd's
+    adds: same outputs, the same input and parameter gradients up to fp32 summation order."""
+    from importlib import import_module
+    M, ops = import_module('x-transformers-rl_b200.model'), xtrl().ops
+    torch.manual_seed(1)
+    cfg = ops.ModelConfig(state_dim=8, num_actions=4, reward_range=(-5., 5.), max_timesteps=150, depth=1, heads=8, dim_head=16)
+    model = M.WorldModelActorCritic(cfg, dropout=0.).to(DEV)
+    hd = model.fused_state()['heads']
+    for h in hd.values():
+        h.refresh()
+    b, n = 3, 150                                                              # 450 tokens: three full tiles and a partial one
+    src = [torch.randn(b, n, 48, device=DEV) for _ in range(3)]
+    gs = None
+    outs = {}
+    for mode in ('one', 'three'):
+        model.flat_grads.zero_()
+        embed, se, ae = (t.clone().requires_grad_() for t in src)
+        if mode == 'one':
+            ra, vl, sp = M._FusedHeads3.apply(hd, n, model.frac, embed, se, ae)
+        else:
+            sp = M._FusedHead.apply(hd['pred'], n, embed, ae, None)
+            emb_ac = M._FracGrad.apply(embed, model.frac)
+            ra, vl = M._FusedHead.apply(hd['actor'], n, emb_ac, se, None), M._FusedHead.apply(hd['critic'], n, emb_ac, se, None)
+        if gs is None:
+            gs = [torch.randn_like(t.float()).to(t.dtype) for t in (ra, vl, sp)]
+        torch.autograd.backward([ra, vl, sp], gs)
+        outs[mode] = ([t.detach().clone() for t in (ra, vl, sp)], [t.grad.clone() for t in (embed, se, ae)], model.flat_grads.clone())
+    (ya, ga, pa), (yb, gb, pb) = outs['one'], outs['three']
+    for u, v in zip(ya, yb):
+        assert torch.equal(u, v)
+    for u, v, name in zip(ga, gb, ('d_embed', 'd_se', 'd_ae')):
+        assert maxrel(u, v) < 1e-5, (name, maxrel(u, v))
+    assert maxrel(pa, pb) < 1e-5

@@ -101,7 +101,7 @@ class AttnCoreIO(C.Structure):
 class MlpIO(C.Structure):
     _fields_ = [('src0', c_vp), ('src1', c_vp), ('src2', c_vp), ('src2_per_episode', c_i32), ('b1', c_vp), ('b2', c_vp), ('w_img', c_vp),
                 ('y', c_vp), ('gy', c_vp), ('d_src0', c_vp), ('d_src1', c_vp), ('d_src2', c_vp), ('d_w1', c_vp), ('d_b1', c_vp),
-                ('d_w2', c_vp), ('d_b2', c_vp), ('n_silu', c_i32), ('out_cols', c_i32)]
+                ('d_w2', c_vp), ('d_b2', c_vp), ('n_silu', c_i32), ('out_cols', c_i32), ('d_src_scale', c_f32 * 3), ('d_src_accumulate', c_i32)]
 
 
 class PrepIO(C.Structure):

@@ -26,6 +26,8 @@ struct Args {
     __nv_bfloat16 *y;                                     // [N][out_cols]
     const __nv_bfloat16 *gy;
     float *dsrc[3];                                       // [N][48] each
+    float dscale[3];                                      // d_src[s] = (dacc bit s ? d_src[s] : 0) + dscale[s] * dX_s
+    int dacc;
     float *dW1, *db1, *dW2, *db2;                         // dense padded, +=
     int N, n, n_silu, out_cols;
 };
@@ -43,7 +45,10 @@ template <int KIN, int HID, int NOUT> struct Dims {
     static constexpr int kX = TOK * XW * 2, kH = TOK * HW * 2, kDP = TOK * HID * 2, kDY = TOK * NOUT * 2;
     static constexpr int fwd_smem = kW1 + kW2 + TOK * KIN * 2 + TOK * HID * 2 + (HID + NOUT) * 4 + 64;
     // backward order: dY, dPRE first -- their MN-major reads run past the image (M = 128 > NOUT / HID) into what follows
-    static constexpr int bwd_smem = kDY + kDP + kH + kX + kW1 + kW2 + HID * 4 + 64;
+    static constexpr int bwd_base = kDY + kDP + kH + kX + kW1 + kW2 + HID * 4 + 64;
+    // two sources: their dX tiles leave (and, when accumulating, first arrive) by bulk copy through two row-tile buffers
+    static constexpr bool ost = NSRC == 2 && bwd_base + 2 * kRowTile <= 227 * 1024;
+    static constexpr int bwd_smem = bwd_base + (ost ? 2 * kRowTile : 0);
     static_assert(kDP + kH + kX >= (128 - NOUT) * kCore / 8 && kH + kX >= (128 - HID) * kCore / 8, "over-read stays inside the CTA's shared memory");
 };
 
@@ -172,12 +177,14 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
     static_assert(cB + HW <= 512, "TMEM budget");
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sDY = smem, *sDP = sDY + P::kDY, *sH = sDP + P::kDP, *sX = sH + P::kH, *sW1 = sX + P::kX, *sW2 = sW1 + P::kW1;
-    float *sB1 = reinterpret_cast<float *>(sW2 + P::kW2);
+    constexpr bool OST = P::ost;
+    float *sOut = reinterpret_cast<float *>(sW2 + P::kW2);                     // [2 sources][128][48] fp32 (OST)
+    float *sB1 = sOut + (OST ? 2 * TOK * D : 0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB1 + HID);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }   // 2: d_src tiles to add to
     if (warp == 0) tmem_alloc(tslot, 512);
     for (int i = tid; i < HID; i += NT) sB1[i] = a.b1[i];
     if (half == 0) {                                                          // constant columns: [1, 0 x 7] then zeros
@@ -190,8 +197,9 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
     tc_fence_after();
     const uint32_t tbase = *tslot, tlane = tbase + ((uint32_t)(q * 32) << 16);
     if (tid == 0) { mbar_expect_tx(&bars[0], P::kW1 + P::kW2); bulk_g2s(sW1, a.wimg, P::kW1 + P::kW2, &bars[0]); }
-    uint32_t ph = 0;
+    uint32_t ph = 0, pha = 0;
     bool first = true;
+    int pend = -1;                                                            // tile whose dX still sits in sOut
     const int ntiles = (a.N + TOK - 1) / TOK;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TOK + row;
@@ -232,6 +240,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {                                                       // PRE = X W1^T
+            if (OST && pend >= 0) { rows_store(a.dsrc[0], sOut, pend, a.N); rows_store(a.dsrc[1], sOut + TOK * D, pend, a.N); }
             if (first) mbar_wait(&bars[0], 0);
             tc_fence_after();
 #pragma unroll
@@ -260,6 +269,16 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
+            if (OST) {
+                if (pend >= 0) bulk_wait_read();                              // the staging buffers are free again
+                if (a.dacc) {                                                 // the rows this tile adds to, into the same buffers
+                    const int t0 = tile * TOK, rows = min(TOK, a.N - t0);
+                    const uint32_t bytes = (uint32_t)rows * D * 4;
+                    mbar_expect_tx(&bars[2], ((a.dacc & 1) ? bytes : 0u) + ((a.dacc & 2) ? bytes : 0u));
+                    if (a.dacc & 1) bulk_g2s(sOut, a.dsrc[0] + (size_t)t0 * D, bytes, &bars[2]);
+                    if (a.dacc & 2) bulk_g2s(sOut + TOK * D, a.dsrc[1] + (size_t)t0 * D, bytes, &bars[2]);
+                }
+            }
             tc_fence_after();
 #pragma unroll
             for (int s = 0; s < NOUT / 16; ++s)                                // dH = dY W2 (W2 image read MN-major)
@@ -301,18 +320,28 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         first = false;
         mbar_wait(&bars[1], ph); ph ^= 1;
         tc_fence_after();
+        if (OST && a.dacc) { mbar_wait(&bars[2], pha); pha ^= 1; }
 #pragma unroll
         for (int c = 0; c < KIN / 16; ++c) {                                  // dX, 8 columns at a time, to the source it belongs to
             const int col0 = c * 16 + half * 8, s = col0 / D, off = col0 - s * D;
             float v[8];
             tmem_ld8(tlane + cDx + col0, v);
-            if (ok) {
-                float4 *dst = reinterpret_cast<float4 *>(a.dsrc[s] + (size_t)t * D + off);
-                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            if (OST || ok) {
+                float4 *dst = reinterpret_cast<float4 *>(OST ? sOut + s * TOK * D + row * D + off : a.dsrc[s] + (size_t)t * D + off);
+                const float sc = a.dscale[s];
+                float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                if ((a.dacc >> s) & 1) { o0 = dst[0]; o1 = dst[1]; }
+                dst[0] = make_float4(fmaf(sc, v[0], o0.x), fmaf(sc, v[1], o0.y), fmaf(sc, v[2], o0.z), fmaf(sc, v[3], o0.w));
+                dst[1] = make_float4(fmaf(sc, v[4], o1.x), fmaf(sc, v[5], o1.y), fmaf(sc, v[6], o1.z), fmaf(sc, v[7], o1.w));
             }
         }
+        pend = tile;
         tc_fence_before();
+    }
+    if (OST && pend >= 0) {                                                   // the last tile's dX
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { rows_store(a.dsrc[0], sOut, pend, a.N); rows_store(a.dsrc[1], sOut + TOK * D, pend, a.N); }
     }
     if (!first) {                                                             // flush the weight-gradient accumulators (see flush_rows)
         tc_fence_after();
@@ -352,6 +381,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const Args a) {
         flush_rows(stage, HID + 1, NOUT, HID, tid, NT, [&](int r, int c) { return a.dW2 + r * HID + c; });
         tc_fence_before();
     }
+    if (OST && tid == 0) bulk_wait_all();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
@@ -400,6 +430,8 @@ static int fill(const xtrl_mlp_io *io, int64_t N, int32_t n, int32_t in_dim, int
     a.b1 = io->b1; a.b2 = io->b2; a.wimg = static_cast<const unsigned char *>(io->w_img);
     a.y = static_cast<__nv_bfloat16 *>(io->y); a.gy = static_cast<const __nv_bfloat16 *>(io->gy);
     a.dsrc[0] = io->d_src0; a.dsrc[1] = io->d_src1; a.dsrc[2] = io->d_src2;
+    a.dacc = io->d_src_accumulate & 7;
+    for (int i = 0; i < 3; ++i) a.dscale[i] = io->d_src_scale[i] != 0.f ? io->d_src_scale[i] : 1.f;
     a.dW1 = io->d_w1; a.db1 = io->d_b1; a.dW2 = io->d_w2; a.db2 = io->d_b2;
     a.N = (int)N; a.n = n; a.n_silu = io->n_silu; a.out_cols = io->out_cols;
     return XTRL_OK;
@@ -484,6 +516,8 @@ extern "C" int xtrl_mlp_bwd(const xtrl_mlp_io *io, int64_t N, int32_t n, int32_t
     if (N == 0) return XTRL_OK;
     XTRL_REQUIRE(io->src0 && io->src1 && (in_dim == 96 || (io->src2 && io->d_src2)) && io->b1 && io->w_img && io->gy && io->d_src0 && io->d_src1 &&
                  io->d_w1 && io->d_b1 && io->d_w2 && io->d_b2, XTRL_E_BADARG, "xtrl_mlp_bwd: null pointer");
+    XTRL_REQUIRE((((uintptr_t)io->d_src0 | (uintptr_t)io->d_src1) & 15) == 0, XTRL_E_BADARG,
+                 "xtrl_mlp_bwd: d_src0 / d_src1 must be 16-byte aligned (row tiles move by bulk copy)");
 #define CALL(KIN, HID, NOUT) return launch(mlp_bwd_kernel<KIN, HID, NOUT>, "mlp_bwd_kernel", Dims<KIN, HID, NOUT>::bwd_smem, 1, a, stream)
     XTRL_MLP_VARIANT(in_dim, hidden, out, CALL);
 #undef CALL

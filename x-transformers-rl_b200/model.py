@@ -270,6 +270,39 @@ class _FusedHead(torch.autograd.Function):
         return None, None, d[0].view(b, n, 48), d[1].view(b, n, 48), d2
 
 
+class _FusedHeads3(torch.autograd.Function):
+    """the three heads of a pass without a latent input as ONE autograd node: world-model head on (embed, ae_next), actor and
+    critic on (frac_gradient(embed), se).  The backward runs the three xtrl_mlp_bwd launches into shared gradient buffers:
+    the world-model head writes d_embed, the other two add frac * dX (frac_gradient, x_transformers_rl.py:114-116, :533) into
+    it and share d_se -- no per-head gradient tensors, no adds, no separate scaling pass."""
+
+    @staticmethod
+    def forward(ctx, heads, n, frac, embed, se, ae_next):
+        embed, se, ae_next = (t.float().contiguous() for t in (embed, se, ae_next))
+        ctx.save_for_backward(embed, se, ae_next)
+        ctx.heads, ctx.n, ctx.frac = heads, n, float(frac)
+        run = lambda h, srcs: ops.mlp_fwd(srcs, n, h.b1, h.b2, h.img, h.out_cols, h.n_silu).view(-1, n, h.out_cols)
+        return run(heads['actor'], [embed, se]), run(heads['critic'], [embed, se]), run(heads['pred'], [embed, ae_next])
+
+    @staticmethod
+    def backward(ctx, g_actor, g_critic, g_pred):
+        embed, se, ae_next = ctx.saved_tensors
+        heads, n, frac = ctx.heads, ctx.n, ctx.frac
+        d_embed, d_se, d_ae = torch.empty_like(embed), torch.empty_like(se), torch.empty_like(ae_next)
+        flat = lambda t: t.view(-1, 48)
+
+        def run(h, gy, srcs, outs, scales, acc):
+            h.gflat.zero_()
+            gy = gy.reshape(-1, h.out_cols).to(torch.bfloat16).contiguous()
+            ops.mlp_bwd(srcs, n, gy, h.b1, h.img, h.gw1, h.gb1, h.gw2, h.gb2, h.n_silu, out=[flat(o) for o in outs], scales=scales, accumulate=acc)
+            h.scatter()
+
+        run(heads['pred'], g_pred, [embed, ae_next], (d_embed, d_ae), (1., 1.), 0)
+        run(heads['actor'], g_actor, [embed, se], (d_embed, d_se), (frac, 1.), 1)
+        run(heads['critic'], g_critic, [embed, se], (d_embed, d_se), (frac, 1.), 3)
+        return None, None, None, d_embed, d_se, d_ae
+
+
 class _FusedNorm(torch.autograd.Function):
     """the Decoder's final LayerNorm through xtrl_ln_fwd / _bwd (csrc/learn_ln.cu)."""
 
@@ -624,9 +657,12 @@ class WorldModelActorCritic(nn.Module):
         hd = self.fused_state()['heads']
         for hs in hd.values():
             hs.refresh()
+        n_pred = 2 * (cfg.state_dim + 1)
+        if lat is None:                                              # one node, shared gradient buffers (see _FusedHeads3)
+            ra, vl, sp_done = _FusedHeads3.apply(hd, n, self.frac, embed, se32, ae_next)
+            return ra, vl, sp_done[..., :n_pred], sp_done[..., n_pred]
         sp_done = _FusedHead.apply(hd['pred'], n, embed, ae_next, None)
         emb_ac = _FracGrad.apply(embed, self.frac)
-        n_pred = 2 * (cfg.state_dim + 1)
         return (_FusedHead.apply(hd['actor'], n, emb_ac, se32, lat), _FusedHead.apply(hd['critic'], n, emb_ac, se32, lat),
                 sp_done[..., :n_pred], sp_done[..., n_pred])
 

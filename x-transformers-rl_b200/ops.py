@@ -367,16 +367,21 @@ def mlp_fwd(srcs, n, b1p, b2p, img, out_cols, n_silu, per_episode2=False):
     return y
 
 
-def mlp_bwd(srcs, n, gy, b1p, img, d_w1p, d_b1p, d_w2p, d_b2p, n_silu, per_episode2=False):
-    """gradients w.r.t. every source ((N, 48) fp32 each); padded parameter gradients accumulated (+=)."""
+def mlp_bwd(srcs, n, gy, b1p, img, d_w1p, d_b1p, d_w2p, d_b2p, n_silu, per_episode2=False, out=None, scales=None, accumulate=0):
+    """gradients w.r.t. every source ((N, 48) fp32 each); padded parameter gradients accumulated (+=).  out: the tensors that
+    receive them (default: new ones); source s gets (bit s of `accumulate` ? out[s] : 0) + scales[s] * dX_s."""
     lib = L.load()
     f32 = torch.float32
     N = srcs[0].numel() // 48
-    dsrc = [torch.empty(N, 48, dtype=f32, device=gy.device) for _ in srcs]
+    dsrc = [torch.empty(N, 48, dtype=f32, device=gy.device) for _ in srcs] if out is None else list(out)
+    if accumulate and out is None:
+        raise L.XtrlError('mlp_bwd: accumulate needs the tensors to add to (out=)')
+    sc = list(scales) + [1.] * (3 - len(scales)) if scales is not None else [1., 1., 1.]
     io = L.MlpIO(src0=_ptr(srcs[0], f32, 'src0'), src1=_ptr(srcs[1], f32, 'src1'), src2=_ptr(srcs[2], f32, 'src2') if len(srcs) > 2 else None,
                  src2_per_episode=int(per_episode2), b1=_ptr(b1p, f32, 'b1'), w_img=_ptr(img, torch.uint8, 'img'), gy=_ptr(gy, torch.bfloat16, 'gy'),
                  d_src0=_ptr(dsrc[0]), d_src1=_ptr(dsrc[1]), d_src2=_ptr(dsrc[2]) if len(srcs) > 2 else None,
-                 d_w1=_ptr(d_w1p, f32), d_b1=_ptr(d_b1p, f32), d_w2=_ptr(d_w2p, f32), d_b2=_ptr(d_b2p, f32), n_silu=n_silu, out_cols=gy.shape[-1])
+                 d_w1=_ptr(d_w1p, f32), d_b1=_ptr(d_b1p, f32), d_w2=_ptr(d_w2p, f32), d_b2=_ptr(d_b2p, f32), n_silu=n_silu, out_cols=gy.shape[-1],
+                 d_src_scale=(C.c_float * 3)(*[float(v) for v in sc]), d_src_accumulate=int(accumulate))
     L.check(lib.xtrl_mlp_bwd(C.byref(io), N, n, 48 * len(srcs), b1p.numel(), d_b2p.numel(), _stream()), 'xtrl_mlp_bwd')
     return dsrc
 
