@@ -75,6 +75,10 @@ def test_single_process_helpers_are_identity():
     assert D.reduce_fitness(t) is t
     assert D.all_reduce_mean_(t.clone()).tolist() == [1., 2.]
     assert D.shard_episode_genes(2, 1, 1, 0) == [[0, 0], [1, 0]]
+    # the peer-memory gradient exchange is a multi-GPU construct: one process, or a CPU device, keeps the plain path
+    assert D.PeerGroup.create(16, torch.device('cpu')) is None
+    with pytest.raises(TypeError):
+        D.PeerGroup()
 
 
 def test_ema_schedule_matches_oracle():

@@ -391,7 +391,7 @@ class Agent(nn.Module):
         # RSNorm batch mean over the masked rows rides in the tail of the gradient buffer (:1005, :601)
         mf = mask[..., None].float()
         self._comm[n:] = (packed * mf).sum(dim=(0, 1)) / mf.sum().clamp(min=1.)
-        if collective and self.capture_allreduce:
+        if collective and self.capture_allreduce and self._peers is None:
             all_reduce_sum_(self._comm)              # gradients (+ RSNorm batch mean in the tail), one collective
         return scalars
 
@@ -428,7 +428,7 @@ class Agent(nn.Module):
         loss.backward()
         rs = box['rs_sum']                                                                           # :1005, :601
         self._comm[n:] = rs[:S + 1] / rs[S + 1].clamp(min=1.)
-        if collective and self.capture_allreduce:
+        if collective and self.capture_allreduce and self._peers is None:
             all_reduce_sum_(self._comm)
         return scalars
 
