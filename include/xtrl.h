@@ -326,6 +326,9 @@ typedef struct xtrl_ff_io {
 int64_t xtrl_ff_img_bytes(int32_t dim, int32_t hidden);          /* -1 if the shape is not built */
 int xtrl_ff_pack(const float *w1 /*[hidden][dim]*/, const float *w2 /*[dim][hidden]*/, void *img,
                  int32_t dim, int32_t hidden, void *stream);
+/* the same for nlayers (<= 8) layers in one launch: HOST arrays of device pointers */
+int xtrl_ff_pack_layers(const float *const *w1, const float *const *w2, void *const *img, int32_t nlayers, int32_t dim,
+                        int32_t hidden, void *stream);
 int xtrl_ff_fwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t hidden, void *stream);
 int xtrl_ff_bwd(const xtrl_ff_io *io, int64_t N, int32_t dim, int32_t hidden, void *stream);
 
@@ -368,6 +371,10 @@ int64_t xtrl_attn_img_bytes(int32_t dim, int32_t heads, int32_t dim_head, int32_
 int xtrl_attn_pack(const float *wq, const float *wk, const float *wv /*[H*16][dim]*/, const float *wo /*[dim][H*16]*/,
                    const float *wg /*[H*16][dim] or NULL*/, const float *wm /*[H][dim] or NULL*/,
                    void *img, int32_t dim, int32_t heads, int32_t dim_head, void *stream);
+/* nlayers (<= 8) layers of ONE variant (wg / wm all given or NULL) in one launch: HOST arrays of device pointers */
+int xtrl_attn_pack_layers(const float *const *wq, const float *const *wk, const float *const *wv, const float *const *wo,
+                          const float *const *wg, const float *const *wm, void *const *img, int32_t nlayers,
+                          int32_t dim, int32_t heads, int32_t dim_head, void *stream);
 int xtrl_attn_pre_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
 int xtrl_attn_pre_bwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);
 int xtrl_attn_post_fwd(const xtrl_attn_io *io, int32_t b, int32_t n, int32_t heads, void *stream);

@@ -614,7 +614,8 @@ def test_three_heads_node_equals_separate_heads():
         model.flat_grads.zero_()
         embed, se, ae = (t.clone().requires_grad_() for t in src)
         if mode == 'one':
-            ra, vl, sp = M._FusedHeads3.apply(hd, n, model.frac, embed, se, ae)
+            ra, vl, sp18, dl = M._FusedHeads3.apply(hd, n, model.frac, embed, se, ae)
+            sp = torch.cat([sp18, dl[..., None]], dim=-1)            # the node hands the loss its two dense inputs
         else:
             sp = M._FusedHead.apply(hd['pred'], n, embed, ae, None)
             emb_ac = M._FracGrad.apply(embed, model.frac)

@@ -144,10 +144,12 @@ SYMBOLS = {
     'xtrl_seg2d_copy': (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     'xtrl_ff_img_bytes': (c_i64, [c_i32, c_i32]),
     'xtrl_ff_pack': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    'xtrl_ff_pack_layers': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_ff_fwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
     'xtrl_ff_bwd': (c_i32, [C.POINTER(FfIO), c_i64, c_i32, c_i32, c_vp]),
     'xtrl_attn_img_bytes': (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32]),
     'xtrl_attn_pack': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'xtrl_attn_pack_layers': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_pre_fwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_pre_bwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),
     'xtrl_attn_post_fwd': (c_i32, [C.POINTER(AttnIO), c_i32, c_i32, c_i32, c_vp]),

@@ -548,11 +548,10 @@ __global__ void __launch_bounds__(NT, 2) attn_post_bwd_kernel(const Args a) {
 }
 
 template <int H, int NB, int MIX>
-__global__ void attn_pack_kernel(const float *__restrict__ wq, const float *__restrict__ wk, const float *__restrict__ wv,
-                                 const float *__restrict__ wo, const float *__restrict__ wg, const float *__restrict__ wm,
-                                 unsigned char *__restrict__ img) {
+__device__ __forceinline__ void attn_pack_one(const float *__restrict__ wq, const float *__restrict__ wk, const float *__restrict__ wv,
+                                              const float *__restrict__ wo, const float *__restrict__ wg, const float *__restrict__ wm,
+                                              unsigned char *__restrict__ img, int i) {
     using P = Dims<H, NB, MIX>;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < D * P::I) {
         const int r = i / P::I, c = i % P::I;                                    // Wo [48][I]: rows = outputs, K = I
         *reinterpret_cast<__nv_bfloat16 *>(img + img_off_bf16(D, r, c)) = __float2bfloat16(wo[i]);
@@ -568,6 +567,20 @@ __global__ void attn_pack_kernel(const float *__restrict__ wq, const float *__re
         }
         *reinterpret_cast<__nv_bfloat16 *>(img + P::kWo + img_off_bf16(P::NQ, j, k)) = __float2bfloat16(w);
     }
+}
+template <int H, int NB, int MIX>
+__global__ void attn_pack_kernel(const float *__restrict__ wq, const float *__restrict__ wk, const float *__restrict__ wv,
+                                 const float *__restrict__ wo, const float *__restrict__ wg, const float *__restrict__ wm,
+                                 unsigned char *__restrict__ img) {
+    attn_pack_one<H, NB, MIX>(wq, wk, wv, wo, wg, wm, img, blockIdx.x * blockDim.x + threadIdx.x);
+}
+// the same for up to kPackLayers layers in one launch (blockIdx.y = layer): the images follow the weights every optimiser step
+constexpr int kPackLayers = 8;
+struct PackN { const float *wq[kPackLayers], *wk[kPackLayers], *wv[kPackLayers], *wo[kPackLayers], *wg[kPackLayers], *wm[kPackLayers]; unsigned char *img[kPackLayers]; };
+template <int H, int NB, int MIX>
+__global__ void attn_pack_n_kernel(const PackN a) {
+    const int l = blockIdx.y;
+    attn_pack_one<H, NB, MIX>(a.wq[l], a.wk[l], a.wv[l], a.wo[l], a.wg[l], a.wm[l], a.img[l], blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 
@@ -648,6 +661,28 @@ extern "C" int xtrl_attn_pack(const float *wq, const float *wk, const float *wv,
     XTRL_ATTN_VARIANT(heads, gate, mix, CALL);
 #undef CALL
     XTRL_LAUNCH_CHECK("attn_pack_kernel");
+    return XTRL_OK;
+}
+
+extern "C" int xtrl_attn_pack_layers(const float *const *wq, const float *const *wk, const float *const *wv, const float *const *wo,
+                                     const float *const *wg, const float *const *wm, void *const *img, int32_t nlayers,
+                                     int32_t dim, int32_t heads, int32_t dim_head, void *stream) {
+    using namespace xtrl; using namespace xtrl::attn;
+    const int gate = wg != nullptr, mix = wm != nullptr;
+    if (int rc = attn_check(dim, heads, dim_head, gate, mix)) return rc;
+    XTRL_REQUIRE(wq && wk && wv && wo && img && nlayers >= 1 && nlayers <= kPackLayers, XTRL_E_BADARG,
+                 "xtrl_attn_pack_layers: null pointer or nlayers not in 1..%d (got %d)", kPackLayers, nlayers);
+    PackN a;
+    for (int l = 0; l < nlayers; ++l) {
+        XTRL_REQUIRE(wq[l] && wk[l] && wv[l] && wo[l] && img[l] && (!gate || wg[l]) && (!mix || wm[l]), XTRL_E_BADARG,
+                     "xtrl_attn_pack_layers: null pointer (layer %d)", l);
+        a.wq[l] = wq[l]; a.wk[l] = wk[l]; a.wv[l] = wv[l]; a.wo[l] = wo[l]; a.wg[l] = gate ? wg[l] : nullptr; a.wm[l] = mix ? wm[l] : nullptr;
+        a.img[l] = static_cast<unsigned char *>(img[l]);
+    }
+#define CALL(H, NB, MIX) attn_pack_n_kernel<H, NB, MIX><<<dim3((Dims<H, NB, MIX>::NQ * learn::D + 255) / 256, nlayers), 256, 0, (cudaStream_t)stream>>>(a)
+    XTRL_ATTN_VARIANT(heads, gate, mix, CALL);
+#undef CALL
+    XTRL_LAUNCH_CHECK("attn_pack_n_kernel");
     return XTRL_OK;
 }
 

@@ -517,6 +517,16 @@ __global__ void ff_pack_kernel(const float *__restrict__ w1, const float *__rest
     }
 }
 
+constexpr int kPackLayers = 8;
+struct PackN { const float *w1[kPackLayers], *w2[kPackLayers]; unsigned char *img[kPackLayers]; };
+__global__ void ff_pack_n_kernel(const PackN a) {                                // blockIdx.y = layer
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y;
+    if (i < F * D) {
+        *reinterpret_cast<__nv_bfloat16 *>(a.img[l] + img_off_bf16(F, i / D, i % D)) = __float2bfloat16(a.w1[l][i]);
+        *reinterpret_cast<__nv_bfloat16 *>(a.img[l] + kW1 + img_off_bf16(D, i / F, i % F)) = __float2bfloat16(a.w2[l][i]);
+    }
+}
+
 static int check_dims(int dim, int hidden) {
     XTRL_REQUIRE(dim == D && hidden == F, XTRL_E_UNSUPPORTED, "xtrl_ff_*: built for dim=%d hidden=%d (got %d, %d)", D, F, dim, hidden);
     return XTRL_OK;
@@ -549,6 +559,22 @@ extern "C" int xtrl_ff_pack(const float *w1, const float *w2, void *img, int32_t
     XTRL_REQUIRE(w1 && w2 && img, XTRL_E_BADARG, "xtrl_ff_pack: null pointer");
     ff_pack_kernel<<<(F * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w1, w2, static_cast<unsigned char *>(img));
     XTRL_LAUNCH_CHECK("ff_pack_kernel");
+    return XTRL_OK;
+}
+
+extern "C" int xtrl_ff_pack_layers(const float *const *w1, const float *const *w2, void *const *img, int32_t nlayers, int32_t dim,
+                                   int32_t hidden, void *stream) {
+    using namespace xtrl; using namespace xtrl::ff;
+    if (int rc = check_dims(dim, hidden)) return rc;
+    XTRL_REQUIRE(w1 && w2 && img && nlayers >= 1 && nlayers <= kPackLayers, XTRL_E_BADARG,
+                 "xtrl_ff_pack_layers: null pointer or nlayers not in 1..%d (got %d)", kPackLayers, nlayers);
+    PackN a;
+    for (int l = 0; l < nlayers; ++l) {
+        XTRL_REQUIRE(w1[l] && w2[l] && img[l], XTRL_E_BADARG, "xtrl_ff_pack_layers: null pointer (layer %d)", l);
+        a.w1[l] = w1[l]; a.w2[l] = w2[l]; a.img[l] = static_cast<unsigned char *>(img[l]);
+    }
+    ff_pack_n_kernel<<<dim3((F * D + 255) / 256, nlayers), 256, 0, (cudaStream_t)stream>>>(a);
+    XTRL_LAUNCH_CHECK("ff_pack_n_kernel");
     return XTRL_OK;
 }
 

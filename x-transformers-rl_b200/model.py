@@ -282,10 +282,15 @@ class _FusedHeads3(torch.autograd.Function):
         ctx.save_for_backward(embed, se, ae_next)
         ctx.heads, ctx.n, ctx.frac = heads, n, float(frac)
         run = lambda h, srcs: ops.mlp_fwd(srcs, n, h.b1, h.b2, h.img, h.out_cols, h.n_silu).view(-1, n, h.out_cols)
-        return run(heads['actor'], [embed, se]), run(heads['critic'], [embed, se]), run(heads['pred'], [embed, ae_next])
+        sp_done = run(heads['pred'], [embed, ae_next])
+        n_pred = heads['pred'].out_cols - 1                          # the world-model head's last column is the done logit
+        # the two dense tensors the loss kernel reads (it would copy the slices anyway); their gradients come back as two
+        # dense tensors and are joined by one cat instead of autograd's zero-fill + copy + zero-fill + copy + add
+        return run(heads['actor'], [embed, se]), run(heads['critic'], [embed, se]), sp_done[..., :n_pred].contiguous(), sp_done[..., n_pred].contiguous()
 
     @staticmethod
-    def backward(ctx, g_actor, g_critic, g_pred):
+    def backward(ctx, g_actor, g_critic, g_sp, g_dl):
+        g_pred = torch.cat([g_sp.reshape(-1, g_sp.shape[-1]), g_dl.reshape(-1, 1)], dim=1)
         embed, se, ae_next = ctx.saved_tensors
         heads, n, frac = ctx.heads, ctx.n, ctx.frac
         d_embed, d_se, d_ae = torch.empty_like(embed), torch.empty_like(se), torch.empty_like(ae_next)
@@ -616,13 +621,18 @@ class WorldModelActorCritic(nn.Module):
             raise ops.L.XtrlError(f'the tensor-core attention core is built for dim_head=16 and sequences up to 512 (got dim_head={dh}, '
                                   f"n={n}). Pass accelerate_kwargs=dict(mixed_precision='no') for the fp32 parity class.")
         fs['rng_step'].add_(1)                    # one counter bump per pass: fresh dropout masks on every graph replay
-        for l in range(cfg.depth):                # bf16 operand images follow the current weights
-            ff, at = dec.layers[2 * l + 1][1], dec.layers[2 * l][1]
-            ops.ff_pack(ff.ff[0][0].weight.data, ff.ff[2].weight.data, out=fs['ff_img'][l])
-            ops.attn_pack(at.to_q.weight.data, at.to_k.weight.data, at.to_v.weight.data, at.to_out.weight.data,
-                          wg=at.to_v_gate.weight.data if cfg.gate_values else None,
-                          wm=at.to_value_residual_mix[0].weight.data if (cfg.value_residual and cfg.learned_mix and l > 0) else None,
-                          out=fs['attn_img'][l])
+        # bf16 operand images follow the current weights: one launch for the feed-forward layers, one per attention variant
+        # (a learned value-residual mix exists from layer 1 on)
+        ffs, ats = [dec.layers[2 * l + 1][1] for l in range(cfg.depth)], [dec.layers[2 * l][1] for l in range(cfg.depth)]
+        ops.ff_pack_layers([f.ff[0][0].weight.data for f in ffs], [f.ff[2].weight.data for f in ffs], fs['ff_img'])
+        mixed = lambda l: bool(cfg.value_residual and cfg.learned_mix and l > 0)
+        for group in ([l for l in range(cfg.depth) if not mixed(l)], [l for l in range(cfg.depth) if mixed(l)]):
+            if group:
+                g = [ats[l] for l in group]
+                ops.attn_pack_layers([t.to_q.weight.data for t in g], [t.to_k.weight.data for t in g], [t.to_v.weight.data for t in g],
+                                     [t.to_out.weight.data for t in g], [t.to_v_gate.weight.data for t in g] if cfg.gate_values else None,
+                                     [t.to_value_residual_mix[0].weight.data for t in g] if mixed(group[0]) else None,
+                                     [fs['attn_img'][l] for l in group])
         cos4, sin4 = self._rotary_tables(n, ang)
         first_v = None
         plain = not (cfg.gate_values or cfg.value_residual)
@@ -659,8 +669,7 @@ class WorldModelActorCritic(nn.Module):
             hs.refresh()
         n_pred = 2 * (cfg.state_dim + 1)
         if lat is None:                                              # one node, shared gradient buffers (see _FusedHeads3)
-            ra, vl, sp_done = _FusedHeads3.apply(hd, n, self.frac, embed, se32, ae_next)
-            return ra, vl, sp_done[..., :n_pred], sp_done[..., n_pred]
+            return _FusedHeads3.apply(hd, n, self.frac, embed, se32, ae_next)
         sp_done = _FusedHead.apply(hd['pred'], n, embed, ae_next, None)
         emb_ac = _FracGrad.apply(embed, self.frac)
         return (_FusedHead.apply(hd['actor'], n, emb_ac, se32, lat), _FusedHead.apply(hd['critic'], n, emb_ac, se32, lat),

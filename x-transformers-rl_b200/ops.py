@@ -256,6 +256,37 @@ def attn_pack(wq, wk, wv, wo, wg=None, wm=None, out=None):
     return out
 
 
+def _ptr_array(tensors, dtype, what):
+    return (C.c_void_p * len(tensors))(*[_ptr(t, dtype, what) for t in tensors])
+
+
+def ff_pack_layers(w1s, w2s, imgs):
+    """ff_pack for several layers (<= 8 per launch) at once"""
+    lib = L.load()
+    hidden, dim = w1s[0].shape
+    for i in range(0, len(w1s), 8):
+        sl = slice(i, i + 8)
+        a1, a2, ai = _ptr_array(w1s[sl], torch.float32, 'w1'), _ptr_array(w2s[sl], torch.float32, 'w2'), _ptr_array(imgs[sl], torch.uint8, 'img')
+        L.check(lib.xtrl_ff_pack_layers(C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), C.cast(ai, C.c_void_p), len(w1s[sl]), dim, hidden,
+                                        _stream()), 'xtrl_ff_pack_layers')
+
+
+def attn_pack_layers(wqs, wks, wvs, wos, wgs, wms, imgs):
+    """attn_pack for several layers of ONE variant (wgs / wms: lists or None) at once (<= 8 per launch)"""
+    lib = L.load()
+    inner, dim = wqs[0].shape
+    f32 = torch.float32
+    for i in range(0, len(wqs), 8):
+        sl = slice(i, i + 8)
+        arrs = [_ptr_array(t[sl], f32, nm) for t, nm in ((wqs, 'wq'), (wks, 'wk'), (wvs, 'wv'), (wos, 'wo'))]
+        ag = _ptr_array(wgs[sl], f32, 'wg') if wgs is not None else None
+        am = _ptr_array(wms[sl], f32, 'wm') if wms is not None else None
+        ai = _ptr_array(imgs[sl], torch.uint8, 'img')
+        cast = lambda a: C.cast(a, C.c_void_p) if a is not None else None
+        L.check(lib.xtrl_attn_pack_layers(*[cast(a) for a in arrs], cast(ag), cast(am), cast(ai), len(wqs[sl]), dim, inner // 16, 16,
+                                          _stream()), 'xtrl_attn_pack_layers')
+
+
 def attn_pre_fwd(x, ln_gamma, img, cos_tab, sin_tab, heads, gate_bias=None, mix_bias=None):
     """x (b, n, dim) fp32 -> q, k, v bf16 (b, H, n, 16) [, gate pre-activation (b, H, n, 16)] [, mix logits (b, n, 16)]:
     LayerNorm, the projections (biases of the optional blocks added), partial rotary on q and k."""
